@@ -1,0 +1,227 @@
+/*
+ * recsys_b200.h — C ABI of the B200-native CTR embedding hot path.
+ *
+ * The reference (neoyinyao/Recommender) has no FFI / plugin interface: the path sits behind
+ * Keras layer calls and TensorFlow-internal ops.  Each entry point below names the reference
+ * call site (file:line under /root/reference) or the TensorFlow op
+ * whose work it replaces.  The Python mirror of the reference's call surface
+ * (recommender_b200/layers.py, model.py) binds these symbols with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the library never
+ *    allocates, frees or retains caller memory — scratch comes in through (ws, ws_bytes),
+ *    sized by the matching *_workspace_bytes() query.
+ *  - every call takes the CUDA stream to launch on (a cudaStream_t passed as void*), is
+ *    asynchronous and stream-ordered; one process per GPU.
+ *  - return value: RB_OK (0) or a negative rb_status; rb_last_error() gives the message
+ *    (thread-local).  Nothing throws.
+ *  - tables are fp32, row-major [rows, D] with row stride == D; rows must be aligned to the
+ *    vector width the kernel uses (16 B if D % 4 == 0, 8 B if D % 2 == 0, else 4 B) and
+ *    D / vector-width <= 32 (D <= 128 for D % 4 == 0).
+ *  - indices are int32 or int64 (both occur: ctr/tfrecord_io.py:82 vs dien/train.py:101).
+ */
+#ifndef RECSYS_B200_H_
+#define RECSYS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_VERSION 100  /* 0.1.0 */
+#define RB_MAX_GRAD_SOURCES 16
+
+typedef enum rb_status {
+  RB_OK = 0,
+  RB_ERR_ARG = -1,        /* null pointer, bad enum, negative size */
+  RB_ERR_SHAPE = -2,      /* unsupported D / F / L combination */
+  RB_ERR_ALIGN = -3,      /* pointer not aligned for the vector width */
+  RB_ERR_WORKSPACE = -4,  /* workspace missing or too small */
+  RB_ERR_CUDA = -5        /* a CUDA runtime call or launch failed */
+} rb_status;
+
+typedef enum rb_index_type { RB_I32 = 0, RB_I64 = 1 } rb_index_type;
+
+/* pooling over the L positions of a bag */
+typedef enum rb_pool_mode {
+  RB_POOL_SUM = 1,          /* tf.reduce_sum(E, axis=1)              ctr/model.py:21        */
+  RB_POOL_MEAN = 2,         /* sum / L                                                       */
+  RB_POOL_MASKED_MEAN = 3   /* compute_his_average                   dien/layers.py:5-17    */
+} rb_pool_mode;
+
+typedef enum rb_optimizer {
+  RB_OPT_SGD = 0,            /* var[r] -= lr*g            (the commented option, ctr/train.py:79) */
+  RB_OPT_ADAGRAD = 1,        /* Keras Adagrad sparse apply (north star)             */
+  RB_OPT_ADAM_LAZY = 2,      /* Keras Adam formula on touched rows only        */
+  RB_OPT_ADAM_TF_DENSE = 3   /* exact Keras Adam._resource_apply_sparse: every row decays/moves */
+} rb_optimizer;
+
+/* Optimizer hyper-parameters.  Defaults of the reference: Adam() at ctr/train.py:80,84. */
+typedef struct rb_opt_params {
+  int32_t optimizer;   /* rb_optimizer */
+  int32_t step;        /* t = iterations + 1 (>= 1); Adam only */
+  float lr;            /* 1e-3 */
+  float beta_1;        /* 0.9 */
+  float beta_2;        /* 0.999 */
+  float epsilon;       /* 1e-7 (outside the square root, Keras form) */
+} rb_opt_params;
+
+/*
+ * Where the gradient row of lookup position p comes from.
+ * With bag b = p / L and l = p % L, the row is
+ *     sum_k  src[k][ b*bag_stride[k] + l*pos_stride[k]  ..  + D )        (added left to right)
+ * then scaled per `scale_mode`, then (optionally) the FM term g_fm[b]*(s[b,:] - W[row,:]) is
+ * added.  Examples: dE[B,F,D] of the un-pooled lookup: L=F, bag_stride=F*D, pos_stride=D;
+ * a pooled bag [B,ld]: pos_stride=0, bag_stride=ld; the slice dX[:, :26] of a [B,27,D] tensor:
+ * bag_stride=27*D; ESMM/MMOE consumers of the concat [B,sum D_f]: one src per consumer.
+ */
+typedef enum rb_grad_scale {
+  RB_SCALE_NONE = 0,
+  RB_SCALE_MEAN = 1,         /* g / L                                  */
+  RB_SCALE_MASKED_MEAN = 2   /* mask ? g / count[b] : 0                dien/layers.py:13-16 */
+} rb_grad_scale;
+
+typedef struct rb_grad_source {
+  int32_t num_src;                           /* 1..RB_MAX_GRAD_SOURCES */
+  int32_t scale_mode;                        /* rb_grad_scale */
+  const float* src[RB_MAX_GRAD_SOURCES];
+  int64_t bag_stride[RB_MAX_GRAD_SOURCES];   /* in elements */
+  int64_t pos_stride[RB_MAX_GRAD_SOURCES];   /* in elements */
+  const void* mask_idx;                      /* RB_SCALE_MASKED_MEAN: index array [n] whose != 0 is the mask
+                                                (same index type as idx); NULL = idx itself */
+  const float* count;                        /* RB_SCALE_MASKED_MEAN: f32[B] valid counts from the forward */
+  const float* fm_g;                         /* optional f32[B]: dL/d(fm)                 ctr/model.py:21-23 */
+  const float* fm_s;                         /* optional f32[B,D]: sum_f E[b,f,:] from rb_gather_fm_fwd */
+} rb_grad_source;
+
+/* ---- library ---------------------------------------------------------------------------- */
+
+int rb_version(void);
+const char* rb_last_error(void);
+/* alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) in fp32, as Keras evaluates it. Host only. */
+float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t step);
+
+/* ---- K1: embedding lookup ---------------------------------------------------------------- */
+
+/*
+ * out[p,:] = table[row(p),:],  p in [0,n).   Replaces keras.layers.Embedding.__call__ /
+ * ResourceGather at ctr/model.py:19, :49; dien/model.py:16-17; esmm/esmm.py:16.
+ *   row(p) = idx[p] (+ field_row_offset[p % L] when field_row_offset != NULL; L = positions per
+ *   sample, used for T>1 tables stored back to back).  hash_mod != 0 first folds
+ *   idx <- uint64(idx) mod hash_mod (the build-defined id->row map).
+ *   out row p is written at out + p*out_stride (elements); out_stride >= D.
+ *   oob_flag (optional int32*): set to 1 if an index falls outside [0, rows); such lookups
+ *   produce zeros (TF's GPU kernel behaviour).
+ */
+int rb_gather_fwd(const float* table, int64_t rows, int32_t D,
+                  const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                  const int64_t* field_row_offset, int64_t hash_mod,
+                  float* out, int64_t out_stride, int32_t* oob_flag, void* stream);
+
+/*
+ * Pooled lookup: out[b, :D] = pool_l table[row(b,l),:]   (written at out + b*out_stride).
+ * Replaces tf.reduce_sum(E,axis=1) (ctr/model.py:21) and compute_flat_embedding +
+ * compute_his_average (dien/model.py:14-19,25-31; dien/layers.py:5-17).
+ *   mask_idx: for RB_POOL_MASKED_MEAN the array whose != 0 is the mask (NULL = idx itself: the
+ *   item-derived mask also gates the cat table, dien/model.py:25).  Masked positions are not read.
+ *   count_out (optional f32[B]) receives the number of valid positions (L for sum/mean).
+ *   No guard for count == 0: the result is NaN, as in the reference (dien/layers.py:16).
+ */
+int rb_bag_pool_fwd(const float* table, int64_t rows, int32_t D,
+                    const void* idx, int32_t idx_type, int64_t B, int32_t L,
+                    const int64_t* field_row_offset, int64_t hash_mod,
+                    int32_t pool_mode, const void* mask_idx,
+                    float* out, int64_t out_stride, float* count_out,
+                    int32_t* oob_flag, void* stream);
+
+/*
+ * DeepFM front end, one pass over the rows (ctr/model.py:19-23):
+ *   E[b,f,:] = table[idx[b,f],:]  (optional, may be NULL),
+ *   s[b,:] = sum_f E[b,f,:] (optional),  fm[b] = 0.5*sum_d(s^2 - sum_f E^2).
+ */
+int rb_gather_fm_fwd(const float* table, int64_t rows, int32_t D,
+                     const void* idx, int32_t idx_type, int64_t B, int32_t F,
+                     const int64_t* field_row_offset, int64_t hash_mod,
+                     float* E, float* s, float* fm, int32_t* oob_flag, void* stream);
+
+/* ---- K3..K6, K10: DotInteraction ------------------------------------------------------------ */
+
+/*
+ * DotInteraction.call (ctr/layers.py:23-43) on bf16 tensor cores, fp32 accumulate, with the
+ * DLRM concats fused (ctr/model.py:51-55):
+ *   X[b] = [ E[b,0..F-1,:] ; dense_vec[b,:] ]  (dense_vec optional -> F' = F or F+1 features)
+ *   Z = X X^T;  kept set: self_interaction ? (j <= i) : (j > i)   (ctr/layers.py:27-33)
+ *   skip_gather: out[b, i*F'+j] = kept ? Z[i,j] : 0   (F'^2 columns)        (ctr/layers.py:36-38)
+ *   else       : kept entries in row-major order     (F'(F'-+1)/2 columns) (ctr/layers.py:39-42)
+ *   tail != 0 : dense_vec[b,:] is also copied to out[b, ncols .. ncols+D)   (ctr/model.py:54)
+ * E == NULL selects the fused gather: rows are read straight from `table` through idx[B,F]
+ * (+field_row_offset), so [B,F,D] never exists in HBM.
+ * out row b starts at out + b*out_stride.  Requires F' <= 32, D % 16 == 0, D <= 128.
+ */
+int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows,
+                           const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                           const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                           int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                           float* out, int64_t out_stride, void* stream);
+
+/*
+ * Backward of the above (TF autodiff of ctr/layers.py:25-42 and ctr/model.py:51-55):
+ *   G = mask (.) dOut,  dX = (G + G^T) X;  dE[b,f,:] = dX[b,f,:] (f < F),
+ *   d_dense[b,:] = dX[b,F,:] (+ dOut[b, ncols .. ncols+D) when tail != 0).
+ * dE row (b,f) is written at dE + (b*F + f)*D.
+ */
+int rb_dot_interaction_bwd(const float* E, const float* table, int64_t rows,
+                           const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                           const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                           int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                           const float* dOut, int64_t dout_stride,
+                           float* dE, float* d_dense, void* stream);
+
+/* ---- K7..K9: backward scatter + sparse optimizer row update ------------------------------- */
+
+size_t rb_sparse_bwd_update_workspace_bytes(int64_t n, int32_t D, int64_t rows);
+
+/*
+ * Gradient of the lookup applied straight to the table: IndexedSlices (A.1) -> duplicate-row
+ * sum (A.2: Keras _deduplicate_indexed_slices = Unique + UnsortedSegmentSum) -> optimizer row
+ * update (A.3/A.4: Adam._resource_apply_sparse at ctr/train.py:80,84,97).
+ * Deterministic: (row, position) pairs are radix-sorted (stable), duplicate rows are summed in
+ * position order by a segmented reduction, no floating-point atomics anywhere.
+ *   state0/state1: Adam m, v; Adagrad acc (state1 unused); SGD: both unused.
+ *   n = number of lookup positions, L = positions per bag (see rb_grad_source).
+ *   RB_OPT_ADAM_TF_DENSE additionally makes the two dense passes over all `rows`.
+ */
+int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                         const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                         const int64_t* field_row_offset, int64_t hash_mod,
+                         const rb_grad_source* grad, const rb_opt_params* opt,
+                         void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
+
+/*
+ * The same sort + segmented reduction WITHOUT the optimizer: writes the unique rows (ascending)
+ * and their summed gradients — the deduplicated IndexedSlices itself.  Used by the parity tests
+ * and by callers that own their optimizer.
+ *   uniq_rows int64[n], uniq_grad f32[n,D], num_unique int64[1] (device).
+ */
+int rb_sparse_bwd_dedup(int64_t rows, int32_t D,
+                        const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                        const int64_t* field_row_offset, int64_t hash_mod,
+                        const rb_grad_source* grad,
+                        int64_t* uniq_rows, float* uniq_grad, int64_t* num_unique,
+                        void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
+
+/* ---- id -> row map ------------------------------------------------------------------------ */
+
+/* rows_out[p] = uint64(ids[p]) mod vocab  (SURVEY §8c "index hashing"; bit-exact with the oracle).
+ * Row-wise sharding: owner = row mod world, local = row div world (world <= 1: no sharding). */
+int rb_hash_ids(const void* ids, int32_t idx_type, int64_t n, int64_t vocab, int32_t world,
+                int64_t* rows_out, int32_t* owner_out, int64_t* local_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RECSYS_B200_H_ */

@@ -1,0 +1,27 @@
+// Library-level entry points: version and the thread-local error message of the C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return RB_ERR_CUDA;
+}
+
+}  // namespace rb
+
+extern "C" int rb_version(void) { return RB_VERSION; }
+
+extern "C" const char* rb_last_error(void) { return rb::g_error; }

@@ -1,0 +1,199 @@
+// Shared device/host helpers for the recsys_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/recsys_b200.h"
+
+namespace rb {
+
+// ---- error plumbing (thread-local message, C ABI returns codes) ---------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RB_CHECK_ARG(cond, code, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::rb::set_error(__VA_ARGS__);        \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define RB_CUDA(call)                                            \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return ::rb::cuda_fail(e__, #call);  \
+  } while (0)
+
+#define RB_LAUNCH_CHECK(name)                                          \
+  do {                                                                 \
+    cudaError_t e__ = cudaPeekAtLastError();                           \
+    if (e__ != cudaSuccess) return ::rb::cuda_fail(e__, name);         \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- layout of one embedding row over a thread group --------------------------------------
+// A row of D floats is handled by a power-of-two group of GS lanes, each moving VEC floats
+// (VEC = 4 -> 128-bit, 2 -> 64-bit, 1 -> 32-bit), chosen from D's alignment.  D / VEC <= 32.
+struct RowGeom {
+  int vec;  // 4, 2 or 1
+  int gs;   // 4, 8, 16 or 32 lanes per row
+};
+
+inline bool row_geom(int D, RowGeom* g) {
+  if (D <= 0) return false;
+  int vec = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1;
+  int q = D / vec;  // vector elements per row
+  if (q > 32) return false;
+  int gs = 4;
+  while (gs < q) gs <<= 1;
+  g->vec = vec;
+  g->gs = gs;
+  return true;
+}
+
+inline bool aligned_for(const void* p, int vec) { return (reinterpret_cast<uintptr_t>(p) % (vec * 4)) == 0; }
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+};
+template <>
+struct Vec<2> {
+  using T = float2;
+};
+template <>
+struct Vec<1> {
+  using T = float;
+};
+
+template <int VEC>
+struct Row {  // VEC floats in registers
+  float v[VEC];
+};
+
+// streaming (read-once / write-once) and default loads/stores of VEC floats
+template <int VEC>
+__device__ __forceinline__ Row<VEC> ld_row(const float* p) {
+  Row<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+// plain (coherent) load: for table/state rows this kernel itself rewrites
+template <int VEC>
+__device__ __forceinline__ Row<VEC> ld_row_rw(const float* p) {
+  Row<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+
+// evict-first streaming load (gradient rows are read exactly once)
+template <int VEC>
+__device__ __forceinline__ Row<VEC> ld_row_stream(const float* p) {
+  Row<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldcs(p);
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_row(float* p, const Row<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else {
+    *p = r.v[0];
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_row_stream(float* p, const Row<VEC>& r) {
+  if constexpr (VEC == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+  } else if constexpr (VEC == 2) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(r.v[0], r.v[1]));
+  } else {
+    __stcs(p, r.v[0]);
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ Row<VEC> zero_row() {
+  Row<VEC> r;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+  return r;
+}
+
+// ---- index decoding --------------------------------------------------------------------------
+// Folds (optional) the id with uint64 mod, adds the per-field row offset, range-checks.
+struct IndexMap {
+  const void* idx;
+  const int64_t* field_row_offset;  // may be null
+  int64_t hash_mod;                 // 0 = off
+  int64_t rows;
+  int32_t L;
+  int32_t is64;
+};
+
+__device__ __forceinline__ int64_t load_raw_index(const void* idx, int is64, int64_t p) {
+  return is64 ? __ldg(reinterpret_cast<const int64_t*>(idx) + p)
+              : static_cast<int64_t>(__ldg(reinterpret_cast<const int32_t*>(idx) + p));
+}
+
+// returns the table row of position p, or -1 when out of range
+__device__ __forceinline__ int64_t map_index(const IndexMap& m, int64_t p) {
+  int64_t id = load_raw_index(m.idx, m.is64, p);
+  if (m.hash_mod > 0) id = static_cast<int64_t>(static_cast<uint64_t>(id) % static_cast<uint64_t>(m.hash_mod));
+  if (m.field_row_offset != nullptr) id += __ldg(m.field_row_offset + (p % m.L));
+  return (id >= 0 && id < m.rows) ? id : -1;
+}
+
+inline IndexMap make_index_map(const void* idx, int idx_type, const int64_t* off, int64_t hash_mod, int64_t rows, int L) {
+  IndexMap m;
+  m.idx = idx;
+  m.field_row_offset = off;
+  m.hash_mod = hash_mod;
+  m.rows = rows;
+  m.L = L > 0 ? L : 1;
+  m.is64 = (idx_type == RB_I64);
+  return m;
+}
+
+inline unsigned int grid_for(int64_t work_items, int items_per_block) {
+  int64_t b = (work_items + items_per_block - 1) / items_per_block;
+  if (b < 1) b = 1;
+  return static_cast<unsigned int>(b);
+}
+
+}  // namespace rb

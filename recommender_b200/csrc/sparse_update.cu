@@ -1,0 +1,613 @@
+// K7..K9: backward scatter of the lookup + fused sparse optimizer row update (sm_100a).
+//
+// Deterministic and free of floating-point atomics:
+//   1. keys[p] = table row of lookup position p, vals[p] = p;  stable LSD radix sort by row
+//      (only ceil(log2(rows)) key bits are sorted).  Within a row, positions stay ascending,
+//      i.e. the order TF's CPU UnsortedSegmentSum adds them.
+//   2. seg_reduce_tiles_kernel: every GS-lane group walks a tile of 32 consecutive sorted
+//      entries, builds each entry's gradient row on the fly (multi-consumer sum, mean /
+//      masked-mean scaling of a bag-level gradient, FM term) and sums runs of equal rows in
+//      order.  A run that lies inside the tile is handed straight to the sink (optimizer row
+//      update, or the compact IndexedSlices writer).  Runs that cross tile borders leave
+//      per-tile partial sums.
+//   3. seg_chain_kernel: the tile where a crossing run starts adds the partials of the
+//      following tiles in order and calls the sink; chains longer than kLongChain tiles (hot
+//      rows: OOV id 0, 3-row ESMM tables) are queued and reduced by a whole CTA each in
+//      seg_long_chain_kernel with a fixed split, so the result is run-to-run identical.
+// HBM traffic is the algorithmic minimum: each gradient row once, each touched table/state
+// row read once and written once; sort traffic is 16 B per lookup per pass.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace rb {
+
+constexpr int kTile = 32;         // sorted entries per group
+constexpr int kSegThreads = 256;  // CTA size of the reduction kernels
+constexpr int kChunk = 4;         // gradient rows in flight per group
+constexpr int kLongChain = 64;    // tiles; longer chains go to the CTA-wide kernel
+
+struct GradSrcDev {
+  int num_src, scale_mode, L, is64;
+  const float* src[RB_MAX_GRAD_SOURCES];
+  int64_t bag_stride[RB_MAX_GRAD_SOURCES];
+  int64_t pos_stride[RB_MAX_GRAD_SOURCES];
+  const void* mask_idx;
+  const float* count;
+  const float* fm_g;
+  const float* fm_s;
+  const float* table;  // read-only view of the table for the FM term
+  int D;
+};
+
+struct LongChain {
+  uint32_t row, first_tile, last_tile, seg_first;
+};
+
+// ---- gradient row of one lookup position ----------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ Row<VEC> load_grad(const GradSrcDev& g, uint32_t p, uint32_t row, int lane) {
+  const uint32_t b = p / static_cast<uint32_t>(g.L);
+  const uint32_t l = p - b * static_cast<uint32_t>(g.L);
+  const int c = lane * VEC;
+  Row<VEC> r = ld_row_stream<VEC>(g.src[0] + b * g.bag_stride[0] + l * g.pos_stride[0] + c);
+  for (int k = 1; k < g.num_src; ++k) {  // consumers are added left to right (esmm/esmm.py:23-24)
+    Row<VEC> t = ld_row_stream<VEC>(g.src[k] + b * g.bag_stride[k] + l * g.pos_stride[k] + c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], t.v[i]);
+  }
+  if (g.scale_mode == RB_SCALE_MEAN) {
+    const float denom = static_cast<float>(g.L);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __fdiv_rn(r.v[i], denom);
+  } else if (g.scale_mode == RB_SCALE_MASKED_MEAN) {
+    const bool keep = load_raw_index(g.mask_idx, g.is64, p) != 0;
+    const float denom = __ldg(g.count + b);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = keep ? __fdiv_rn(r.v[i], denom) : 0.f;
+  }
+  if (g.fm_g != nullptr) {  // dE += g_fm[b] * (s[b,:] - W[row,:])      (ctr/model.py:21-23 backward)
+    const float gb = __ldg(g.fm_g + b);
+    Row<VEC> s = ld_row<VEC>(g.fm_s + static_cast<int64_t>(b) * g.D + c);
+    Row<VEC> w = ld_row_rw<VEC>(g.table + static_cast<int64_t>(row) * g.D + c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(gb, __fsub_rn(s.v[i], w.v[i])));
+  }
+  return r;
+}
+
+// ---- sinks ----------------------------------------------------------------------------------------
+struct OptSink {  // fused optimizer row update; every op explicitly rounded (no FMA) to match numpy
+  float* table;
+  float* s0;
+  float* s1;
+  int D;
+  int opt;  // rb_optimizer, RB_OPT_ADAM_TF_DENSE = scatter-add phase only
+  float lr, b1, b2, omb1, omb2, eps, alpha;
+
+  template <int VEC>
+  __device__ __forceinline__ void apply(uint32_t row, const Row<VEC>& g, int lane, uint32_t /*seg_first*/) const {
+    const int64_t o = static_cast<int64_t>(row) * D + lane * VEC;
+    if (opt == RB_OPT_ADAM_LAZY) {
+      Row<VEC> w = ld_row_rw<VEC>(table + o), m = ld_row_rw<VEC>(s0 + o), v = ld_row_rw<VEC>(s1 + o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        m.v[i] = __fadd_rn(__fmul_rn(m.v[i], b1), __fmul_rn(g.v[i], omb1));
+        v.v[i] = __fadd_rn(__fmul_rn(v.v[i], b2), __fmul_rn(__fmul_rn(g.v[i], g.v[i]), omb2));
+        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(alpha, m.v[i]), __fadd_rn(__fsqrt_rn(v.v[i]), eps)));
+      }
+      st_row<VEC>(s0 + o, m);
+      st_row<VEC>(s1 + o, v);
+      st_row<VEC>(table + o, w);
+    } else if (opt == RB_OPT_ADAM_TF_DENSE) {
+      Row<VEC> m = ld_row_rw<VEC>(s0 + o), v = ld_row_rw<VEC>(s1 + o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], omb1));
+        v.v[i] = __fadd_rn(v.v[i], __fmul_rn(__fmul_rn(g.v[i], g.v[i]), omb2));
+      }
+      st_row<VEC>(s0 + o, m);
+      st_row<VEC>(s1 + o, v);
+    } else if (opt == RB_OPT_ADAGRAD) {
+      Row<VEC> w = ld_row_rw<VEC>(table + o), a = ld_row_rw<VEC>(s0 + o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        a.v[i] = __fadd_rn(a.v[i], __fmul_rn(g.v[i], g.v[i]));
+        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(lr, g.v[i]), __fadd_rn(__fsqrt_rn(a.v[i]), eps)));
+      }
+      st_row<VEC>(s0 + o, a);
+      st_row<VEC>(table + o, w);
+    } else {  // SGD
+      Row<VEC> w = ld_row_rw<VEC>(table + o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) w.v[i] = __fsub_rn(w.v[i], __fmul_rn(lr, g.v[i]));
+      st_row<VEC>(table + o, w);
+    }
+  }
+};
+
+struct DedupSink {  // writes the deduplicated IndexedSlices (rows ascending)
+  const int32_t* seg_incl;  // inclusive scan of the run-head flags over the sorted entries
+  int64_t* uniq_rows;
+  float* uniq_grad;
+  int D;
+
+  template <int VEC>
+  __device__ __forceinline__ void apply(uint32_t row, const Row<VEC>& g, int lane, uint32_t seg_first) const {
+    const int64_t u = static_cast<int64_t>(seg_incl[seg_first]) - 1;
+    if (lane == 0) uniq_rows[u] = static_cast<int64_t>(row);
+    st_row<VEC>(uniq_grad + u * D + lane * VEC, g);
+  }
+};
+
+// ---- step 1: keys ------------------------------------------------------------------------------------
+__global__ void make_keys_kernel(IndexMap m, int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                 int* __restrict__ oob_flag) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int64_t row = map_index(m, p);
+  if (row < 0) {  // the forward already produced zeros for it; keep the pair harmless and flag it
+    if (oob_flag != nullptr) *oob_flag = 1;
+    row = 0;
+  }
+  keys[p] = static_cast<uint32_t>(row);
+  vals[p] = static_cast<uint32_t>(p);
+}
+
+__global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, int n, int64_t* __restrict__ out) {
+  out[0] = (n > 0) ? static_cast<int64_t>(seg_incl[n - 1]) : 0;
+}
+
+// ---- step 2: tiles -------------------------------------------------------------------------------------
+template <int VEC, int GS, class Sink>
+__global__ void __launch_bounds__(kSegThreads)
+seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradSrcDev gsrc,
+                        Sink sink, float* __restrict__ head_part, float* __restrict__ tail_part) {
+  constexpr int kGroups = kSegThreads / GS;
+  constexpr int kEntries = kGroups * kTile;
+  __shared__ uint32_t s_key[kEntries + 2];  // [0] = key before the CTA's range, [kEntries+1] = key after
+  __shared__ uint32_t s_pos[kEntries];
+
+  const int cta_base = blockIdx.x * kEntries;
+  const int cta_cnt = min(kEntries, n - cta_base);
+  for (int i = threadIdx.x; i < cta_cnt; i += kSegThreads) {
+    s_key[i + 1] = keys[cta_base + i];
+    s_pos[i] = vals[cta_base + i];
+  }
+  if (threadIdx.x == 0) {
+    // sentinels differ from every real key on the respective side only when no neighbour exists;
+    // has_prev / has_next below guard their use
+    s_key[0] = (cta_base > 0) ? keys[cta_base - 1] : 0u;
+    s_key[cta_cnt + 1] = (cta_base + cta_cnt < n) ? keys[cta_base + cta_cnt] : 0u;
+  }
+  __syncthreads();
+
+  const int group = threadIdx.x / GS;
+  const int lane = threadIdx.x % GS;
+  const int tbase = group * kTile;                 // offset inside the CTA range
+  const int tcnt = min(kTile, cta_cnt - tbase);    // entries of this tile (<= 0: idle group)
+  if (tcnt <= 0) return;
+  const bool active = lane * VEC < gsrc.D;
+  const int gbase = cta_base + tbase;              // global sorted index of the tile's first entry
+  const int tile_id = gbase / kTile;
+  const bool has_prev = gbase > 0;
+  const bool has_next = gbase + tcnt < n;
+  const uint32_t* tk = s_key + 1 + tbase;          // tk[-1] and tk[tcnt] are the neighbours
+  const uint32_t* tp = s_pos + tbase;
+
+  Row<VEC> acc = zero_row<VEC>();
+  uint32_t cur = tk[0];
+  int seg_start = 0;
+  bool continues_prev = has_prev && (tk[-1] == cur);  // the leading run started in an earlier tile
+
+  for (int j0 = 0; j0 < tcnt; j0 += kChunk) {
+    Row<VEC> g[kChunk];
+    uint32_t key[kChunk];
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {
+      const int j = j0 + u;
+      g[u] = zero_row<VEC>();
+      key[u] = 0;
+      if (j < tcnt) {
+        key[u] = tk[j];
+        if (active) g[u] = load_grad<VEC>(gsrc, tp[j], key[u], lane);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {
+      const int j = j0 + u;
+      if (j < tcnt) {
+        if (key[u] != cur) {  // previous run was closed below; start a new one
+          cur = key[u];
+          acc = zero_row<VEC>();
+          seg_start = j;
+          continues_prev = false;
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], g[u].v[i]);
+        const bool last_in_tile = (j == tcnt - 1);
+        const bool run_ends = last_in_tile ? !(has_next && tk[tcnt] == cur) : (tk[j + 1] != cur);
+        if (run_ends) {
+          if (continues_prev) {
+            if (active) st_row<VEC>(head_part + static_cast<int64_t>(tile_id) * gsrc.D + lane * VEC, acc);
+          } else if (active) {
+            sink.template apply<VEC>(cur, acc, lane, static_cast<uint32_t>(gbase + seg_start));
+          }
+        } else if (last_in_tile && active) {  // run goes on in the next tile
+          float* dst = continues_prev ? head_part : tail_part;
+          st_row<VEC>(dst + static_cast<int64_t>(tile_id) * gsrc.D + lane * VEC, acc);
+        }
+      }
+    }
+  }
+}
+
+// ---- step 3: runs that cross tile borders -------------------------------------------------------------------
+__device__ __forceinline__ int run_end(const uint32_t* __restrict__ keys, int lo, int n, uint32_t key) {
+  // first index in [lo, n) whose key differs from `key` (keys are sorted, keys[lo-1] == key)
+  int hi = n;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    if (keys[mid] == key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <int VEC, int GS, class Sink>
+__global__ void __launch_bounds__(kSegThreads)
+seg_chain_kernel(const uint32_t* __restrict__ keys, int n, int D, Sink sink, const float* __restrict__ head_part,
+                 const float* __restrict__ tail_part, LongChain* __restrict__ long_list, int* __restrict__ long_count,
+                 int long_cap) {
+  const int tile_id = blockIdx.x * (kSegThreads / GS) + threadIdx.x / GS;
+  const int lane = threadIdx.x % GS;
+  const int gbase = tile_id * kTile;
+  if (gbase + kTile >= n) return;                       // no following tile: nothing can continue
+  const uint32_t key = keys[gbase + kTile - 1];
+  if (keys[gbase + kTile] != key) return;               // the trailing run ends here
+  const bool whole_tile = (keys[gbase] == key);
+  if (whole_tile && gbase > 0 && keys[gbase - 1] == key) return;  // interior tile of someone else's chain
+  // this tile owns the run: find where it starts (inside the tile) and where it ends
+  int start = kTile - 1;
+  while (start > 0 && keys[gbase + start - 1] == key) --start;
+  const int end = run_end(keys, gbase + kTile, n, key);  // exclusive
+  const int last_tile = (end - 1) / kTile;
+  const int chain = last_tile - tile_id;                 // following tiles that hold a head partial
+  if (chain > kLongChain) {
+    if (lane == 0) {
+      const int slot = atomicAdd(long_count, 1);         // integer append; order does not affect values
+      if (slot < long_cap) long_list[slot] = LongChain{key, static_cast<uint32_t>(tile_id), static_cast<uint32_t>(last_tile),
+                                                            static_cast<uint32_t>(gbase + start)};
+    }
+    return;
+  }
+  if (lane * VEC >= D) return;
+  Row<VEC> acc = ld_row_rw<VEC>(tail_part + static_cast<int64_t>(tile_id) * D + lane * VEC);
+  for (int t0 = tile_id + 1; t0 <= last_tile; t0 += kChunk) {
+    Row<VEC> h[kChunk];
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u)
+      h[u] = (t0 + u <= last_tile) ? ld_row_rw<VEC>(head_part + static_cast<int64_t>(t0 + u) * D + lane * VEC) : zero_row<VEC>();
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u)
+      if (t0 + u <= last_tile) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], h[u].v[i]);
+      }
+  }
+  sink.template apply<VEC>(key, acc, lane, static_cast<uint32_t>(gbase + start));
+}
+
+template <int VEC, int GS, class Sink>
+__global__ void __launch_bounds__(kSegThreads)
+seg_long_chain_kernel(int D, Sink sink, const float* __restrict__ head_part, const float* __restrict__ tail_part,
+                      const LongChain* __restrict__ long_list, const int* __restrict__ long_count, int long_cap) {
+  constexpr int kGroups = kSegThreads / GS;
+  __shared__ float s_part[kGroups * 128];  // D <= 128
+  const int group = threadIdx.x / GS, lane = threadIdx.x % GS;
+  const bool active = lane * VEC < D;
+  const int count = min(*long_count, long_cap);
+  for (int c = blockIdx.x; c < count; c += gridDim.x) {
+    const LongChain lc = long_list[c];
+    const int ntiles = static_cast<int>(lc.last_tile - lc.first_tile);  // head partials to add
+    const int per = (ntiles + kGroups - 1) / kGroups;
+    const int t_begin = static_cast<int>(lc.first_tile) + 1 + group * per;
+    const int t_end = min(t_begin + per, static_cast<int>(lc.last_tile) + 1);
+    Row<VEC> acc = zero_row<VEC>();
+    if (active) {
+      for (int t0 = t_begin; t0 < t_end; t0 += kChunk) {
+        Row<VEC> h[kChunk];
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+          h[u] = (t0 + u < t_end) ? ld_row_rw<VEC>(head_part + static_cast<int64_t>(t0 + u) * D + lane * VEC) : zero_row<VEC>();
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+          if (t0 + u < t_end) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], h[u].v[i]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) s_part[group * 128 + lane * VEC + i] = acc.v[i];
+    }
+    __syncthreads();
+    if (group == 0 && active) {
+      Row<VEC> tot = ld_row_rw<VEC>(tail_part + static_cast<int64_t>(lc.first_tile) * D + lane * VEC);
+      for (int gidx = 0; gidx < kGroups; ++gidx) {  // fixed order -> deterministic
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) tot.v[i] = __fadd_rn(tot.v[i], s_part[gidx * 128 + lane * VEC + i]);
+      }
+      sink.template apply<VEC>(lc.row, tot, lane, lc.seg_first);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- Keras-exact Adam: the dense passes over every row ----------------------------------------
+__global__ void adam_decay_all_kernel(float* __restrict__ m, float* __restrict__ v, int64_t count, float b1, float b2) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    m[i] = __fmul_rn(m[i], b1);
+    v[i] = __fmul_rn(v[i], b2);
+  }
+}
+__global__ void adam_apply_all_kernel(float* __restrict__ w, const float* __restrict__ m, const float* __restrict__ v,
+                                      int64_t count, float alpha, float eps) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    w[i] = __fsub_rn(w[i], __fdiv_rn(__fmul_rn(alpha, m[i]), __fadd_rn(__fsqrt_rn(v[i]), eps)));
+  }
+}
+
+// ---- workspace -----------------------------------------------------------------------------------------------
+struct WsLayout {
+  size_t keys_a, keys_b, vals_a, vals_b, seg_incl, head_part, tail_part, long_list, long_count, cub_temp, cub_bytes, total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// a chain is "long" when it spans more than kLongChain tiles, so at most this many can exist
+static int long_list_cap(int64_t n) { return static_cast<int>(n / (static_cast<int64_t>(kLongChain) * kTile)) + 2; }
+
+static int key_bits(int64_t rows) {
+  int bits = 1;
+  while (bits < 32 && (int64_t(1) << bits) < rows) ++bits;
+  return bits;
+}
+
+static WsLayout ws_layout(int64_t n, int D, int64_t rows) {
+  WsLayout w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  const size_t n4 = static_cast<size_t>(n) * 4;
+  const size_t tiles = static_cast<size_t>((n + kTile - 1) / kTile) + 1;
+  w.keys_a = take(n4);
+  w.keys_b = take(n4);
+  w.vals_a = take(n4);
+  w.vals_b = take(n4);
+  w.seg_incl = take(n4);
+  w.head_part = take(tiles * D * 4);
+  w.tail_part = take(tiles * D * 4);
+  w.long_list = take(sizeof(LongChain) * static_cast<size_t>(long_list_cap(n)));
+  w.long_count = take(256);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, static_cast<int>(n), 0, key_bits(rows));
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
+                                static_cast<int>(n));
+  w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  w.cub_temp = take(w.cub_bytes + 256);
+  w.total = off;
+  return w;
+}
+
+static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_type, const void* idx, const float* table,
+                         int D, int vec) {
+  RB_CHECK_ARG(g != nullptr && g->num_src >= 1 && g->num_src <= RB_MAX_GRAD_SOURCES, RB_ERR_ARG, "grad source count out of range");
+  RB_CHECK_ARG(g->scale_mode >= RB_SCALE_NONE && g->scale_mode <= RB_SCALE_MASKED_MEAN, RB_ERR_ARG, "bad scale mode");
+  d->num_src = g->num_src;
+  d->scale_mode = g->scale_mode;
+  d->L = L;
+  d->is64 = (idx_type == RB_I64);
+  for (int k = 0; k < RB_MAX_GRAD_SOURCES; ++k) {
+    d->src[k] = nullptr;
+    d->bag_stride[k] = d->pos_stride[k] = 0;
+  }
+  for (int k = 0; k < g->num_src; ++k) {
+    RB_CHECK_ARG(g->src[k] != nullptr, RB_ERR_ARG, "grad source %d is null", k);
+    RB_CHECK_ARG(aligned_for(g->src[k], vec) && g->bag_stride[k] % vec == 0 && g->pos_stride[k] % vec == 0, RB_ERR_ALIGN,
+                 "grad source %d not aligned for vec=%d", k, vec);
+    d->src[k] = g->src[k];
+    d->bag_stride[k] = g->bag_stride[k];
+    d->pos_stride[k] = g->pos_stride[k];
+  }
+  d->mask_idx = g->mask_idx != nullptr ? g->mask_idx : idx;
+  d->count = g->count;
+  RB_CHECK_ARG(g->scale_mode != RB_SCALE_MASKED_MEAN || g->count != nullptr, RB_ERR_ARG, "masked mean needs count");
+  d->fm_g = g->fm_g;
+  d->fm_s = g->fm_s;
+  RB_CHECK_ARG(g->fm_g == nullptr || (g->fm_s != nullptr && aligned_for(g->fm_s, vec)), RB_ERR_ARG, "fm_g needs an aligned fm_s");
+  d->table = table;
+  d->D = D;
+  return RB_OK;
+}
+
+template <class Sink>
+static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t* vals, int n, const GradSrcDev& gsrc,
+                        const Sink& sink, unsigned char* ws, const WsLayout& lay, cudaStream_t st) {
+  float* head = reinterpret_cast<float*>(ws + lay.head_part);
+  float* tail = reinterpret_cast<float*>(ws + lay.tail_part);
+  LongChain* ll = reinterpret_cast<LongChain*>(ws + lay.long_list);
+  int* lc = reinterpret_cast<int*>(ws + lay.long_count);
+  RB_CUDA(cudaMemsetAsync(lc, 0, sizeof(int), st));
+  const int tiles = (n + kTile - 1) / kTile;
+  const int cap = long_list_cap(n);
+#define CALL(V, G)                                                                                                      \
+  {                                                                                                                     \
+    constexpr int kGroups = kSegThreads / G;                                                                            \
+    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, vals, n, gsrc, sink, head, tail); \
+    seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, gsrc.D, sink, head, tail, ll, lc, cap); \
+    seg_long_chain_kernel<V, G, Sink><<<2 * kNumSMs, kSegThreads, 0, st>>>(gsrc.D, sink, head, tail, ll, lc, cap);      \
+  }
+  if (geo.vec == 4) {
+    if (geo.gs == 4) CALL(4, 4) else if (geo.gs == 8) CALL(4, 8) else if (geo.gs == 16) CALL(4, 16) else CALL(4, 32)
+  } else if (geo.vec == 2) {
+    if (geo.gs == 4) CALL(2, 4) else if (geo.gs == 8) CALL(2, 8) else if (geo.gs == 16) CALL(2, 16) else CALL(2, 32)
+  } else {
+    if (geo.gs == 4) CALL(1, 4) else if (geo.gs == 8) CALL(1, 8) else if (geo.gs == 16) CALL(1, 16) else CALL(1, 32)
+  }
+#undef CALL
+  RB_LAUNCH_CHECK("segmented reduction kernels");
+  return RB_OK;
+}
+
+// sort (row, position) pairs; returns pointers to the sorted arrays
+static int sort_pairs(const IndexMap& m, int64_t n, int64_t rows, unsigned char* ws, const WsLayout& lay, int* oob_flag,
+                      cudaStream_t st, const uint32_t** keys_out, const uint32_t** vals_out) {
+  uint32_t* ka = reinterpret_cast<uint32_t*>(ws + lay.keys_a);
+  uint32_t* kb = reinterpret_cast<uint32_t*>(ws + lay.keys_b);
+  uint32_t* va = reinterpret_cast<uint32_t*>(ws + lay.vals_a);
+  uint32_t* vb = reinterpret_cast<uint32_t*>(ws + lay.vals_b);
+  make_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(m, n, ka, va, oob_flag);
+  RB_LAUNCH_CHECK("make_keys_kernel");
+  cub::DoubleBuffer<uint32_t> dk(ka, kb), dv(va, vb);
+  size_t temp = lay.cub_bytes;
+  RB_CUDA(cub::DeviceRadixSort::SortPairs(ws + lay.cub_temp, temp, dk, dv, static_cast<int>(n), 0, key_bits(rows), st));
+  *keys_out = dk.Current();
+  *vals_out = dv.Current();
+  return RB_OK;
+}
+
+static int check_common(int64_t rows, int D, const void* idx, int idx_type, int64_t n, int L, RowGeom* geo) {
+  RB_CHECK_ARG(rows > 0 && rows <= 0xFFFFFFFFll, RB_ERR_ARG, "rows must be in (0, 2^32)");
+  RB_CHECK_ARG(row_geom(D, geo), RB_ERR_SHAPE, "unsupported embedding dim D=%d", D);
+  RB_CHECK_ARG(D <= 128, RB_ERR_SHAPE, "D must be <= 128");
+  RB_CHECK_ARG(n >= 0 && n < 0x7FFFFFFFll && L > 0, RB_ERR_ARG, "n must be in [0, 2^31) and L > 0");
+  RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
+  RB_CHECK_ARG(n == 0 || idx != nullptr, RB_ERR_ARG, "idx is null");
+  return RB_OK;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" size_t rb_sparse_bwd_update_workspace_bytes(int64_t n, int32_t D, int64_t rows) {
+  if (n < 0 || n >= 0x7FFFFFFFll || D <= 0 || rows <= 0) return 0;
+  return ws_layout(n > 0 ? n : 1, D, rows).total;
+}
+
+extern "C" float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t step) {
+  const float t = static_cast<float>(step);
+  const float b1p = powf(beta_1, t);
+  const float b2p = powf(beta_2, t);
+  return lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+}
+
+extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                    const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                                    const int64_t* field_row_offset, int64_t hash_mod, const rb_grad_source* grad,
+                                    const rb_opt_params* opt, void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+  RowGeom geo;
+  int rc = check_common(rows, D, idx, idx_type, n, L, &geo);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(table != nullptr && opt != nullptr, RB_ERR_ARG, "table/opt is null");
+  RB_CHECK_ARG(aligned_for(table, geo.vec), RB_ERR_ALIGN, "table not aligned for vec=%d", geo.vec);
+  const int o = opt->optimizer;
+  RB_CHECK_ARG(o >= RB_OPT_SGD && o <= RB_OPT_ADAM_TF_DENSE, RB_ERR_ARG, "bad optimizer %d", o);
+  const bool adam = (o == RB_OPT_ADAM_LAZY || o == RB_OPT_ADAM_TF_DENSE);
+  RB_CHECK_ARG(!adam || (state0 != nullptr && state1 != nullptr && opt->step >= 1), RB_ERR_ARG, "Adam needs m, v and step >= 1");
+  RB_CHECK_ARG(o != RB_OPT_ADAGRAD || state0 != nullptr, RB_ERR_ARG, "Adagrad needs its accumulator");
+  RB_CHECK_ARG((state0 == nullptr || aligned_for(state0, geo.vec)) && (state1 == nullptr || aligned_for(state1, geo.vec)),
+               RB_ERR_ALIGN, "optimizer state not aligned for vec=%d", geo.vec);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  OptSink sink;
+  sink.table = table;
+  sink.s0 = state0;
+  sink.s1 = state1;
+  sink.D = D;
+  sink.opt = o;
+  sink.lr = opt->lr;
+  sink.b1 = opt->beta_1;
+  sink.b2 = opt->beta_2;
+  sink.omb1 = 1.0f - opt->beta_1;
+  sink.omb2 = 1.0f - opt->beta_2;
+  sink.eps = opt->epsilon;
+  sink.alpha = adam ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
+
+  const int64_t count = rows * D;
+  if (o == RB_OPT_ADAM_TF_DENSE) {
+    adam_decay_all_kernel<<<8 * kNumSMs, 256, 0, st>>>(state0, state1, count, sink.b1, sink.b2);
+    RB_LAUNCH_CHECK("adam_decay_all_kernel");
+  }
+  if (n > 0) {
+    const WsLayout lay = ws_layout(n, D, rows);
+    RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+                 lay.total, ws_bytes);
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
+    GradSrcDev gsrc;
+    rc = fill_grad_src(&gsrc, grad, L, idx_type, idx, table, D, geo.vec);
+    if (rc != RB_OK) return rc;
+    IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, L);
+    const uint32_t *keys, *vals;
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    rc = sort_pairs(m, n, rows, wsb, lay, oob_flag, st, &keys, &vals);
+    if (rc != RB_OK) return rc;
+    rc = run_segments(geo, keys, vals, static_cast<int>(n), gsrc, sink, wsb, lay, st);
+    if (rc != RB_OK) return rc;
+  }
+  if (o == RB_OPT_ADAM_TF_DENSE) {
+    adam_apply_all_kernel<<<8 * kNumSMs, 256, 0, st>>>(table, state0, state1, count, sink.alpha, sink.eps);
+    RB_LAUNCH_CHECK("adam_apply_all_kernel");
+  }
+  return RB_OK;
+}
+
+extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                                   const int64_t* field_row_offset, int64_t hash_mod, const rb_grad_source* grad,
+                                   int64_t* uniq_rows, float* uniq_grad, int64_t* num_unique, void* ws, size_t ws_bytes,
+                                   int32_t* oob_flag, void* stream) {
+  RowGeom geo;
+  int rc = check_common(rows, D, idx, idx_type, n, L, &geo);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(num_unique != nullptr, RB_ERR_ARG, "num_unique is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    RB_CUDA(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), st));
+    return RB_OK;
+  }
+  RB_CHECK_ARG(uniq_rows != nullptr && uniq_grad != nullptr && aligned_for(uniq_grad, geo.vec), RB_ERR_ARG,
+               "uniq_rows/uniq_grad null or misaligned");
+  RB_CHECK_ARG(grad != nullptr && grad->fm_g == nullptr, RB_ERR_ARG, "the dedup entry point takes no FM term (it has no table)");
+  const WsLayout lay = ws_layout(n, D, rows);
+  RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+               lay.total, ws_bytes);
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
+  GradSrcDev gsrc;
+  rc = fill_grad_src(&gsrc, grad, L, idx_type, idx, nullptr, D, geo.vec);
+  if (rc != RB_OK) return rc;
+  IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, L);
+  const uint32_t *keys, *vals;
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  rc = sort_pairs(m, n, rows, wsb, lay, oob_flag, st, &keys, &vals);
+  if (rc != RB_OK) return rc;
+  int32_t* seg = reinterpret_cast<int32_t*>(wsb + lay.seg_incl);
+  head_flags_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, static_cast<int>(n), seg);
+  RB_LAUNCH_CHECK("head_flags_kernel");
+  size_t temp = lay.cub_bytes;
+  RB_CUDA(cub::DeviceScan::InclusiveSum(wsb + lay.cub_temp, temp, seg, seg, static_cast<int>(n), st));
+  write_num_unique_kernel<<<1, 1, 0, st>>>(seg, static_cast<int>(n), num_unique);
+  DedupSink sink{seg, uniq_rows, uniq_grad, D};
+  return run_segments(geo, keys, vals, static_cast<int>(n), gsrc, sink, wsb, lay, st);
+}
