@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Headline benchmark: DLRM Criteo-shape training throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one full training step of DLRM (ctr/model.py:34-58 + Adam, ctr/train.py:80,97) on one
+synthetic Criteo-shaped batch: fused lookup + dot interaction forward, MLPs forward/backward,
+interaction backward, and the sorted backward scatter with the fused sparse Adam row update.
+N = 1 workload = BASELINE config 2: emb dim 64, batch 65536, 26 tables of 1M rows, dot interaction.
+N > 1 (launched by torchrun, one rank per GPU): the same model with the tables row-wise sharded
+over the ranks and B_local = 65536 per GPU (weak scaling), NCCL all-to-all each way.
+
+One JSON line is printed by rank 0 (contract in the task statement): `value` = samples/s with the
+inputs resident in HBM; `e2e` = samples/s through the public API from pinned HOST buffers with the
+host->device copies and the device->host loss read inside the timed region; `roofline` for the
+dominant C-ABI call; `cpu_baseline` = the torch-CPU restatement of the reference timed on this
+box's host cores on a bounded sample.  `--impl reference` times only that restatement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "train samples/s, DLRM Criteo-shape"
+UNIT = "samples/s"
+BOTTOM, TOP = [512, 256, 64], [512, 256, 1]
+F_CAT, F_INT = 26, 13
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch")
+    ap.add_argument("--emb-dim", type=int, default=64)
+    ap.add_argument("--rows-per-table", type=int, default=1_000_000)
+    ap.add_argument("--tables", type=int, default=26, choices=[1, 26])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sharding", default="row", choices=["row", "table"])
+    ap.add_argument("--ring", type=int, default=8, help="distinct synthetic batches cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=8192)
+    ap.add_argument("--ref-adam", default="tf_dense", choices=["tf_dense", "lazy"],
+                    help="Adam semantics of the CPU reference arm: Keras' dense passes (what the reference runs) or lazy")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic Criteo-shaped data: seed 4 (+rank), uniform or Zipf(1.05)+2% id 0
+# ---------------------------------------------------------------------------------------------------
+
+def synth_batches(n, B, V, dist, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        if dist == "uniform":
+            cat = torch.randint(0, V, (B, F_CAT), generator=g, dtype=torch.int64)
+        else:
+            u = torch.rand(B, F_CAT, generator=g, dtype=torch.float64).clamp_(min=1e-12)
+            cat = (u.pow(-1.0 / 0.05).clamp_(max=2.0 ** 62).to(torch.int64) % V)      # Pareto tail ~ Zipf(1.05), folded mod V
+            cat[torch.rand(B, F_CAT, generator=g) < 0.02] = 0                          # OOV -> 0 (ctr/tfrecord_io.py:61-64)
+        dense = torch.log1p(torch.randint(0, 1000, (B, F_INT), generator=g).float())  # ctr/tfrecord_io.py:48-53
+        label = (torch.rand(B, generator=g) < 0.25).to(torch.int64)
+        batch = (cat, dense, label)
+        if pin:
+            batch = tuple(t.pin_memory() for t in batch)
+        out.append(batch)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.thread = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = the upper half of the samples (the sampler also sees idle gaps)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm (torch-CPU restatement of the reference; oracle/torch_cpu_ref.py)
+# ---------------------------------------------------------------------------------------------------
+
+def time_cpu_reference(args, steps, warmup, budget_s=None):
+    from oracle.torch_cpu_ref import DLRMRef
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_sample_batch
+    ref = DLRMRef(BOTTOM[:-1] + [args.emb_dim], TOP, args.emb_dim, args.rows_per_table, num_tables=args.tables, seed=4,
+                  adam=args.ref_adam)
+    batches = synth_batches(2, B, args.rows_per_table, args.dist, seed=4, pin=False)
+    t_start = time.perf_counter()
+    for i in range(warmup):
+        ref.train_step(*batches[i % 2])
+        if budget_s and time.perf_counter() - t_start > budget_s / 2:
+            break
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        ref.train_step(*batches[i % 2])
+        times.append(time.perf_counter() - t0)
+        if budget_s and time.perf_counter() - t_start > budget_s:
+            break
+    sec = sum(times) / len(times)
+    sample = (f"{len(times)} steps of B={B} (1/{max(1, args.batch // B)} of the GPU batch) on the same DLRM "
+              f"({args.tables}x{args.rows_per_table}-row tables, D={args.emb_dim}); torch-CPU restatement of ctr/model.py + "
+              f"Keras Adam ({args.ref_adam}), TensorFlow absent")
+    return dict(value=B / sec, unit=UNIT, cores=cores, kind="port", sample=sample), sec * 1e3, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms, done = time_cpu_reference(args, max(1, args.steps), max(0, args.warmup), budget_s=240)
+    line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=done, warmup=args.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(args, args.gpus), cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return dict(workload=f"DLRM Criteo-shape (BASELINE config 2): emb dim {args.emb_dim}, batch {args.batch} per GPU, "
+                         f"{args.tables} table(s) x {args.rows_per_table} rows, dot interaction, Adam",
+                global_batch=args.batch * world, tables=args.tables, rows_per_table=args.rows_per_table, emb_dim=args.emb_dim,
+                bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
+                sparse_optimizer="adam_lazy", parallelism="single GPU" if world == 1 else f"{args.sharding}-wise sharded tables x{world} + data-parallel MLPs",
+                l2="inputs larger than L2: tables %.1f GB, ring of %d batches, 436 MB gradient tensor per step" % (
+                    args.tables * args.rows_per_table * args.emb_dim * 4 / 1e9, args.ring))
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+
+class CallTimer:
+    """CUDA-event timing of every C-ABI call on the launching (current) stream."""
+
+    def __init__(self, ops, names):
+        self.ops, self.names, self.records, self.enabled = ops, names, {n: [] for n in names}, False
+        self._orig = {}
+
+    def install(self):
+        for n in self.names:
+            self._orig[n] = getattr(self.ops, n)
+            setattr(self.ops, n, self._wrap(n, self._orig[n]))
+
+    def _wrap(self, name, fn):
+        def timed(*a, **k):
+            if not self.enabled:
+                return fn(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            self.records[name].append((s, e))
+            return out
+        return timed
+
+    def summary(self):
+        return {n: (sum(s.elapsed_time(e) for s, e in r) / len(r), len(r)) for n, r in self.records.items() if r}
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    from recommender_b200 import build, ops
+    build.build()
+    from recommender_b200.model import DLRM, bce_clipped
+    from recommender_b200.optimizers import Adam
+
+    D, V, T, B = args.emb_dim, args.rows_per_table, args.tables, args.batch
+    cd = torch.bfloat16 if args.mlp_dtype == "bf16" else None
+    gen = torch.Generator(device=dev).manual_seed(4)
+    if world == 1:
+        model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
+    else:
+        from recommender_b200.sharded import ShardedDLRM
+        model = ShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
+                            sharding=args.sharding)
+    opt = Adam()
+
+    host = synth_batches(args.ring, B, V, args.dist, seed=4 + rank, pin=True)
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def train_step(batch):
+        cat, dense, label = batch
+        prob = model({"cat_features": cat, "int_features": dense})
+        loss = bce_clipped(prob, label)
+        loss.backward()
+        opt.apply_gradients(model)
+        return loss
+
+    timer = CallTimer(ops, ["dot_interaction_fwd", "dot_interaction_bwd", "sparse_bwd_update", "gather_fwd", "bucket_by_owner"])
+    timer.install()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(args.warmup, 3)):
+        loss = train_step(resident[i % args.ring])
+    float(loss.item())
+    ops.check_oob(dev)
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = ops.kernel_launches()
+    timer.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(resident[i % args.ring])
+    e1.record()
+    barrier()
+    timer.enabled = False
+    launches = ops.kernel_launches() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+    final_loss = float(loss.item())
+
+    # ---- e2e: pinned host buffers -> H2D copies, loss read back, all inside the timed region ---------------
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        stage = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(args.steps + 3, dtype=torch.float32).pin_memory()
+
+        def prefetch(i):
+            buf = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[buf])
+                for dst, src in zip(stage[buf], host[i % args.ring]):
+                    dst.copy_(src, non_blocking=True)
+                h2d_done[buf].record(copy_stream)
+
+        def e2e_loop(n, base):
+            for ev in free:
+                ev.record(main)
+            prefetch(0)
+            for i in range(n):
+                buf = i % 2
+                if i + 1 < n:
+                    prefetch(i + 1)
+                main.wait_event(h2d_done[buf])
+                loss = train_step(stage[buf])
+                free[buf].record(main)
+                loss_host[base + i].copy_(loss.detach(), non_blocking=True)      # the step's result, read every step
+            torch.cuda.synchronize()
+
+        e2e_loop(3, 0)
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        e2e_loop(args.steps, 3)
+        s1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), 0.0)) / args.steps
+        e2e = dict(value=B * world / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
+                   ms_per_step=e2e_ms, wall_ms_per_step=wall_ms / args.steps,
+                   api="DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients on batches staged from pinned host memory")
+
+    # ---- roofline of the dominant C-ABI call -------------------------------------------------------------
+    calls = timer.summary()
+    N = B * F_CAT
+    Fp = F_CAT + 1
+    cat0 = resident[0][0]
+    rows0 = cat0 if T == 1 else cat0 + (torch.arange(T, device=dev) * V)[None]
+    U = int(torch.unique(rows0).numel())
+    algo = {
+        # N*idxB + N*D*4 + B*D*4 + B*(F'^2+D)*4
+        "dot_interaction_fwd": N * 8 + N * D * 4 + B * D * 4 + B * (Fp * Fp + D) * 4,
+        # dOut + re-gathered rows + ids + dense vec in; dE + d_dense out
+        "dot_interaction_bwd": B * (Fp * Fp + D) * 4 + N * D * 4 + N * 8 + B * D * 4 + N * D * 4 + B * D * 4,
+        # N*D*4 (dE) + N*idxB + U*D*4*6 (read+write of var, m, v)
+        "sparse_bwd_update": N * D * 4 + N * 8 + U * D * 4 * 6,
+    }
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = {}
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    kernels = {}
+    for name, (ms, cnt) in calls.items():
+        if name in algo and world == 1:
+            gbs = algo[name] / (ms * 1e-3) / 1e9
+            kernels[name] = dict(ms=ms, calls_per_step=cnt / args.steps, algorithmic_bytes=algo[name], achieved_gbs=gbs,
+                                 frac=gbs / peak, share_of_step=ms * cnt / args.steps / ms_step)
+        else:
+            kernels[name] = dict(ms=ms, calls_per_step=cnt / args.steps, share_of_step=ms * cnt / args.steps / ms_step)
+    roofline = None
+    timed = {k: v for k, v in kernels.items() if "achieved_gbs" in v}
+    if timed:
+        top = max(timed, key=lambda k: timed[k]["ms"] * timed[k]["calls_per_step"])
+        roofline = dict(bound="hbm", kernel=top, achieved=timed[top]["achieved_gbs"], peak=peak, unit="GB/s", frac=timed[top]["frac"],
+                        traffic=traffic.get(top), peak_source=peak_src, unique_rows=U,
+                        note="achieved = algorithmic bytes of the whole C-ABI call / its CUDA-event time; for sparse_bwd_update the "
+                             "time includes key generation and the radix sort (overhead, not algorithmic bytes)")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = time_cpu_reference(args, steps=2, warmup=1, budget_s=90)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 tables/optimizer, bf16 MMA operands (f32 accumulate)",
+                    data="synthetic", config=workload_config(args, world), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
+                    kernels=kernels, cpu_baseline=cpu, clocks=clocks, final_loss=final_loss, host_cores=os.cpu_count())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

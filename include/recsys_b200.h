@@ -34,6 +34,7 @@ extern "C" {
 
 #define RB_VERSION 100  /* 0.1.0 */
 #define RB_MAX_GRAD_SOURCES 16
+#define RB_MAX_LOOKUP_GROUPS 4
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -98,10 +99,28 @@ typedef struct rb_grad_source {
   const float* fm_s;                         /* optional f32[B,D]: sum_f E[b,f,:] from rb_gather_fm_fwd */
 } rb_grad_source;
 
+/*
+ * One use of a table inside a training step.  A table that is looked up several times per step
+ * (dien/model.py:26-30: item_embedding serves the target item AND the history) contributes one
+ * group per use; TF concatenates their IndexedSlices in use order before the duplicate-row sum
+ * (SURVEY A.1), which is exactly what passing several groups to one call does.
+ */
+typedef struct rb_lookup_group {
+  const void* idx;                  /* [n] lookup ids of this use */
+  int32_t idx_type;                 /* rb_index_type */
+  int32_t L;                        /* positions per bag */
+  int64_t n;                        /* number of lookup positions (bags * L) */
+  const int64_t* field_row_offset;  /* optional [L] */
+  int64_t hash_mod;                 /* 0 = off */
+  rb_grad_source grad;
+} rb_lookup_group;
+
 /* ---- library ---------------------------------------------------------------------------- */
 
 int rb_version(void);
 const char* rb_last_error(void);
+/* Kernels of this library launched by this process so far (cub's sort/scan passes are not counted). */
+uint64_t rb_kernel_launches(void);
 /* alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) in fp32, as Keras evaluates it. Host only. */
 float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t step);
 
@@ -201,6 +220,12 @@ int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t row
                          const rb_grad_source* grad, const rb_opt_params* opt,
                          void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
 
+/* The general form: the concatenation of `num_groups` (1..RB_MAX_LOOKUP_GROUPS) uses of one table. */
+int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                const rb_lookup_group* groups, int32_t num_groups,
+                                const rb_opt_params* opt,
+                                void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
+
 /*
  * The same sort + segmented reduction WITHOUT the optimizer: writes the unique rows (ascending)
  * and their summed gradients — the deduplicated IndexedSlices itself.  Used by the parity tests
@@ -220,6 +245,24 @@ int rb_sparse_bwd_dedup(int64_t rows, int32_t D,
  * Row-wise sharding: owner = row mod world, local = row div world (world <= 1: no sharding). */
 int rb_hash_ids(const void* ids, int32_t idx_type, int64_t n, int64_t vocab, int32_t world,
                 int64_t* rows_out, int32_t* owner_out, int64_t* local_out, void* stream);
+
+/* ---- row-wise sharding: route lookups to their owner rank -------------------------------------- */
+
+size_t rb_bucket_by_owner_workspace_bytes(int64_t n, int32_t world);
+
+/*
+ * Stable partition of n lookups by owner = row mod world (row-wise sharding), the
+ * send side of the index all-to-all.  row(p) as in rb_gather_fwd (hash_mod, field_row_offset).
+ *   local_rows_out int64[n]: row div world, in bucket order (rank 0's lookups first, ...)
+ *   perm_out       int32[n]: bucket slot -> original lookup position p
+ *   inv_perm_out   int32[n]: original position p -> bucket slot (the index array with which the
+ *                            interaction / gather kernels read the returned rows in place)
+ *   counts_out     int64[world]: lookups per owner
+ */
+int rb_bucket_by_owner(const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                       const int64_t* field_row_offset, int64_t hash_mod, int32_t world,
+                       int64_t* local_rows_out, int32_t* perm_out, int32_t* inv_perm_out,
+                       int64_t* counts_out, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

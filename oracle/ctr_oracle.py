@@ -287,11 +287,25 @@ ADAM_DEFAULTS = dict(lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)       # ct
 ADAGRAD_DEFAULTS = dict(lr=1e-3, initial_accumulator_value=0.1, epsilon=1e-7)
 
 
+def _libm_powf():
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.powf.restype = ctypes.c_float
+    libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    return libm.powf
+
+
+_powf = _libm_powf()
+
+
 def adam_alpha_t(step: int, lr=1e-3, beta_1=0.9, beta_2=0.999) -> np.float32:
-    """A.3: alpha_t = lr * sqrt(1 - b2^t) / (1 - b1^t), evaluated in fp32 like Keras does."""
-    t = F32(step)
-    b1p = np.power(F32(beta_1), t, dtype=F32)
-    b2p = np.power(F32(beta_2), t, dtype=F32)
+    """A.3: alpha_t = lr * sqrt(1 - b2^t) / (1 - b1^t), evaluated in fp32 like Keras does
+    (math_ops.pow on float32 scalars = std::pow<float> = libm powf on TF's CPU device; numpy's
+    SIMD float32 power differs from powf in the last bit for some t, so libm is called directly)."""
+    t = float(step)
+    b1p = F32(_powf(float(F32(beta_1)), t))
+    b2p = F32(_powf(float(F32(beta_2)), t))
     return F32(F32(lr) * np.sqrt(F32(1) - b2p, dtype=F32) / (F32(1) - b1p))
 
 

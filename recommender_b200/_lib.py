@@ -1,0 +1,118 @@
+"""ctypes binding of librecsys_b200.so (include/recsys_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or a symbol the header
+declares is absent, importing the ops raises.  Tensors cross the boundary as raw device
+pointers + sizes (torch is only the carrier of memory and streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "librecsys_b200.so")
+HEADER = os.path.join(os.path.dirname(PKG), "include", "recsys_b200.h")
+
+RB_MAX_GRAD_SOURCES = 16
+RB_MAX_LOOKUP_GROUPS = 4
+
+# enums (recsys_b200.h)
+RB_I32, RB_I64 = 0, 1
+RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
+RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
+RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2
+
+OPTIMIZER_ENUM = {"sgd": RB_OPT_SGD, "adagrad": RB_OPT_ADAGRAD, "adam_lazy": RB_OPT_ADAM_LAZY,
+                  "adam_tf_dense": RB_OPT_ADAM_TF_DENSE}
+POOL_ENUM = {"sum": RB_POOL_SUM, "mean": RB_POOL_MEAN, "masked_mean": RB_POOL_MASKED_MEAN}
+SCALE_ENUM = {"none": RB_SCALE_NONE, "mean": RB_SCALE_MEAN, "masked_mean": RB_SCALE_MASKED_MEAN}
+
+
+class RbOptParams(C.Structure):
+    _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_float), ("beta_1", C.c_float),
+                ("beta_2", C.c_float), ("epsilon", C.c_float)]
+
+
+class RbGradSource(C.Structure):
+    _fields_ = [("num_src", C.c_int32), ("scale_mode", C.c_int32),
+                ("src", C.c_void_p * RB_MAX_GRAD_SOURCES),
+                ("bag_stride", C.c_int64 * RB_MAX_GRAD_SOURCES),
+                ("pos_stride", C.c_int64 * RB_MAX_GRAD_SOURCES),
+                ("mask_idx", C.c_void_p), ("count", C.c_void_p), ("fm_g", C.c_void_p), ("fm_s", C.c_void_p)]
+
+
+class RbLookupGroup(C.Structure):
+    _fields_ = [("idx", C.c_void_p), ("idx_type", C.c_int32), ("L", C.c_int32), ("n", C.c_int64),
+                ("field_row_offset", C.c_void_p), ("hash_mod", C.c_int64), ("grad", RbGradSource)]
+
+
+_p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/recsys_b200.h declares
+SIGNATURES = {
+    "rb_version": (C.c_int, []),
+    "rb_last_error": (C.c_char_p, []),
+    "rb_kernel_launches": (C.c_uint64, []),
+    "rb_adam_alpha_t": (C.c_float, [_f, _f, _f, _i32]),
+    "rb_gather_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
+    "rb_bag_pool_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _i64, _p, _p, _p]),
+    "rb_gather_fm_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p]),
+    "rb_dot_interaction_fwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
+    "rb_dot_interaction_bwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p, _p, _p]),
+    "rb_sparse_bwd_update_workspace_bytes": (C.c_size_t, [_i64, _i32, _i64]),
+    "rb_sparse_bwd_update": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64,
+                                       C.POINTER(RbGradSource), C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
+    "rb_sparse_bwd_update_groups": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32,
+                                              C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
+    "rb_sparse_bwd_dedup": (C.c_int, [_i64, _i32, _p, _i32, _i64, _i32, _p, _i64, C.POINTER(RbGradSource),
+                                      _p, _p, _p, _p, C.c_size_t, _p, _p]),
+    "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+}
+
+
+def header_symbols(path: str = HEADER):
+    """Function names declared in the public header (used by the CPU-side export test)."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", text)))
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m recommender_b200.build` "
+                "(there is no CPU fallback for the CUDA hot path)")
+        dll = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(dll, name, None)
+            if fn is None:
+                raise RuntimeError(f"librecsys_b200.so does not export {name}; rebuild the library")
+            fn.restype = res
+            fn.argtypes = args
+        self._dll = dll
+        return dll
+
+    def __getattr__(self, name):
+        return getattr(self.load(), name)
+
+
+lib = _Lib()
+
+
+class RecsysError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib.rb_last_error()
+        raise RecsysError(f"{what or 'recsys_b200 call'} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace rb {
@@ -15,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
   return RB_ERR_CUDA;
@@ -25,3 +31,5 @@ int cuda_fail(cudaError_t e, const char* what) {
 extern "C" int rb_version(void) { return RB_VERSION; }
 
 extern "C" const char* rb_last_error(void) { return rb::g_error; }
+
+extern "C" uint64_t rb_kernel_launches(void) { return rb::g_launches.load(std::memory_order_relaxed); }

@@ -12,6 +12,7 @@ namespace rb {
 // ---- error plumbing (thread-local message, C ABI returns codes) ---------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launches(int n);  // kernels of THIS library launched so far (rb_kernel_launches)
 
 #define RB_CHECK_ARG(cond, code, ...)      \
   do {                                     \
@@ -31,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                                 \
     cudaError_t e__ = cudaPeekAtLastError();                           \
     if (e__ != cudaSuccess) return ::rb::cuda_fail(e__, name);         \
+    ::rb::count_launches(1);                                           \
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs

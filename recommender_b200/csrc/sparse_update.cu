@@ -37,8 +37,16 @@ struct GradSrcDev {
   const float* count;
   const float* fm_g;
   const float* fm_s;
-  const float* table;  // read-only view of the table for the FM term
+};
+
+// All uses of one table inside a step (their IndexedSlices are concatenated in use
+// order).  Global lookup position p belongs to group k when start[k] <= p < start[k+1].
+struct GradGroupsDev {
+  int num;
   int D;
+  uint32_t start[RB_MAX_LOOKUP_GROUPS + 1];  // unused entries = 0xFFFFFFFF
+  const float* table;                        // read-only view of the table for the FM term
+  GradSrcDev g[RB_MAX_LOOKUP_GROUPS];
 };
 
 struct LongChain {
@@ -47,7 +55,12 @@ struct LongChain {
 
 // ---- gradient row of one lookup position ----------------------------------------------------------
 template <int VEC>
-__device__ __forceinline__ Row<VEC> load_grad(const GradSrcDev& g, uint32_t p, uint32_t row, int lane) {
+__device__ __forceinline__ Row<VEC> load_grad(const GradGroupsDev& gg, uint32_t p, uint32_t row, int lane) {
+  int gi = 0;
+#pragma unroll
+  for (int k = 1; k < RB_MAX_LOOKUP_GROUPS; ++k) gi += (p >= gg.start[k]) ? 1 : 0;
+  const GradSrcDev& g = gg.g[gi];
+  p -= gg.start[gi];
   const uint32_t b = p / static_cast<uint32_t>(g.L);
   const uint32_t l = p - b * static_cast<uint32_t>(g.L);
   const int c = lane * VEC;
@@ -69,8 +82,8 @@ __device__ __forceinline__ Row<VEC> load_grad(const GradSrcDev& g, uint32_t p, u
   }
   if (g.fm_g != nullptr) {  // dE += g_fm[b] * (s[b,:] - W[row,:])      (ctr/model.py:21-23 backward)
     const float gb = __ldg(g.fm_g + b);
-    Row<VEC> s = ld_row<VEC>(g.fm_s + static_cast<int64_t>(b) * g.D + c);
-    Row<VEC> w = ld_row_rw<VEC>(g.table + static_cast<int64_t>(row) * g.D + c);
+    Row<VEC> s = ld_row<VEC>(g.fm_s + static_cast<int64_t>(b) * gg.D + c);
+    Row<VEC> w = ld_row_rw<VEC>(gg.table + static_cast<int64_t>(row) * gg.D + c);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(gb, __fsub_rn(s.v[i], w.v[i])));
   }
@@ -142,8 +155,8 @@ struct DedupSink {  // writes the deduplicated IndexedSlices (rows ascending)
 };
 
 // ---- step 1: keys ------------------------------------------------------------------------------------
-__global__ void make_keys_kernel(IndexMap m, int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                 int* __restrict__ oob_flag) {
+__global__ void make_keys_kernel(IndexMap m, int64_t n, int64_t start, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, int* __restrict__ oob_flag) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= n) return;
   int64_t row = map_index(m, p);
@@ -151,8 +164,8 @@ __global__ void make_keys_kernel(IndexMap m, int64_t n, uint32_t* __restrict__ k
     if (oob_flag != nullptr) *oob_flag = 1;
     row = 0;
   }
-  keys[p] = static_cast<uint32_t>(row);
-  vals[p] = static_cast<uint32_t>(p);
+  keys[start + p] = static_cast<uint32_t>(row);
+  vals[start + p] = static_cast<uint32_t>(start + p);  // global position over the concatenated groups
 }
 
 __global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ flags) {
@@ -167,7 +180,7 @@ __global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, in
 // ---- step 2: tiles -------------------------------------------------------------------------------------
 template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
-seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradSrcDev gsrc,
+seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradGroupsDev gsrc,
                         Sink sink, float* __restrict__ head_part, float* __restrict__ tail_part) {
   constexpr int kGroups = kSegThreads / GS;
   constexpr int kEntries = kGroups * kTile;
@@ -411,8 +424,7 @@ static WsLayout ws_layout(int64_t n, int D, int64_t rows) {
   return w;
 }
 
-static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_type, const void* idx, const float* table,
-                         int D, int vec) {
+static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_type, const void* idx, int vec) {
   RB_CHECK_ARG(g != nullptr && g->num_src >= 1 && g->num_src <= RB_MAX_GRAD_SOURCES, RB_ERR_ARG, "grad source count out of range");
   RB_CHECK_ARG(g->scale_mode >= RB_SCALE_NONE && g->scale_mode <= RB_SCALE_MASKED_MEAN, RB_ERR_ARG, "bad scale mode");
   d->num_src = g->num_src;
@@ -437,13 +449,11 @@ static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_
   d->fm_g = g->fm_g;
   d->fm_s = g->fm_s;
   RB_CHECK_ARG(g->fm_g == nullptr || (g->fm_s != nullptr && aligned_for(g->fm_s, vec)), RB_ERR_ARG, "fm_g needs an aligned fm_s");
-  d->table = table;
-  d->D = D;
   return RB_OK;
 }
 
 template <class Sink>
-static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t* vals, int n, const GradSrcDev& gsrc,
+static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t* vals, int n, const GradGroupsDev& gsrc,
                         const Sink& sink, unsigned char* ws, const WsLayout& lay, cudaStream_t st) {
   float* head = reinterpret_cast<float*>(ws + lay.head_part);
   float* tail = reinterpret_cast<float*>(ws + lay.tail_part);
@@ -468,33 +478,53 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
   }
 #undef CALL
   RB_LAUNCH_CHECK("segmented reduction kernels");
+  count_launches(2);  // three kernels above, one counted by the check
   return RB_OK;
 }
 
-// sort (row, position) pairs; returns pointers to the sorted arrays
-static int sort_pairs(const IndexMap& m, int64_t n, int64_t rows, unsigned char* ws, const WsLayout& lay, int* oob_flag,
-                      cudaStream_t st, const uint32_t** keys_out, const uint32_t** vals_out) {
+static int check_common(int64_t rows, int D, int64_t n, RowGeom* geo) {
+  RB_CHECK_ARG(rows > 0 && rows <= 0xFFFFFFFFll, RB_ERR_ARG, "rows must be in (0, 2^32)");
+  RB_CHECK_ARG(row_geom(D, geo), RB_ERR_SHAPE, "unsupported embedding dim D=%d", D);
+  RB_CHECK_ARG(D <= 128, RB_ERR_SHAPE, "D must be <= 128");
+  RB_CHECK_ARG(n >= 0 && n < 0x7FFFFFFFll, RB_ERR_ARG, "the number of lookups must be in [0, 2^31)");
+  return RB_OK;
+}
+
+// Validates the groups, fills the device-side description and writes + sorts the (row, position)
+// pairs of all groups; returns pointers to the sorted arrays.
+static int prepare_and_sort(const rb_lookup_group* groups, int num_groups, int64_t rows, int D, const float* table,
+                            const RowGeom& geo, int64_t n, unsigned char* ws, const WsLayout& lay, int* oob_flag,
+                            cudaStream_t st, GradGroupsDev* gg, const uint32_t** keys_out, const uint32_t** vals_out) {
+  gg->num = num_groups;
+  gg->D = D;
+  gg->table = table;
+  for (int k = 0; k <= RB_MAX_LOOKUP_GROUPS; ++k) gg->start[k] = 0xFFFFFFFFu;
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + lay.keys_a);
   uint32_t* kb = reinterpret_cast<uint32_t*>(ws + lay.keys_b);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + lay.vals_a);
   uint32_t* vb = reinterpret_cast<uint32_t*>(ws + lay.vals_b);
-  make_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(m, n, ka, va, oob_flag);
-  RB_LAUNCH_CHECK("make_keys_kernel");
+  int64_t start = 0;
+  for (int k = 0; k < num_groups; ++k) {
+    const rb_lookup_group& g = groups[k];
+    RB_CHECK_ARG(g.idx_type == RB_I32 || g.idx_type == RB_I64, RB_ERR_ARG, "group %d: bad index type", k);
+    RB_CHECK_ARG(g.n >= 0 && g.L > 0 && (g.n == 0 || g.idx != nullptr), RB_ERR_ARG, "group %d: bad n/L/idx", k);
+    int rc = fill_grad_src(&gg->g[k], &g.grad, g.L, g.idx_type, g.idx, geo.vec);
+    if (rc != RB_OK) return rc;
+    RB_CHECK_ARG(g.grad.fm_g == nullptr || table != nullptr, RB_ERR_ARG, "the FM term needs the table");
+    gg->start[k] = static_cast<uint32_t>(start);
+    if (g.n > 0) {
+      IndexMap m = make_index_map(g.idx, g.idx_type, g.field_row_offset, g.hash_mod, rows, g.L);
+      make_keys_kernel<<<grid_for(g.n, 256), 256, 0, st>>>(m, g.n, start, ka, va, oob_flag);
+      RB_LAUNCH_CHECK("make_keys_kernel");
+    }
+    start += g.n;
+  }
+  for (int k = num_groups; k < RB_MAX_LOOKUP_GROUPS; ++k) gg->g[k] = gg->g[0];
   cub::DoubleBuffer<uint32_t> dk(ka, kb), dv(va, vb);
   size_t temp = lay.cub_bytes;
   RB_CUDA(cub::DeviceRadixSort::SortPairs(ws + lay.cub_temp, temp, dk, dv, static_cast<int>(n), 0, key_bits(rows), st));
   *keys_out = dk.Current();
   *vals_out = dv.Current();
-  return RB_OK;
-}
-
-static int check_common(int64_t rows, int D, const void* idx, int idx_type, int64_t n, int L, RowGeom* geo) {
-  RB_CHECK_ARG(rows > 0 && rows <= 0xFFFFFFFFll, RB_ERR_ARG, "rows must be in (0, 2^32)");
-  RB_CHECK_ARG(row_geom(D, geo), RB_ERR_SHAPE, "unsupported embedding dim D=%d", D);
-  RB_CHECK_ARG(D <= 128, RB_ERR_SHAPE, "D must be <= 128");
-  RB_CHECK_ARG(n >= 0 && n < 0x7FFFFFFFll && L > 0, RB_ERR_ARG, "n must be in [0, 2^31) and L > 0");
-  RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
-  RB_CHECK_ARG(n == 0 || idx != nullptr, RB_ERR_ARG, "idx is null");
   return RB_OK;
 }
 
@@ -514,12 +544,15 @@ extern "C" float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t s
   return lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
 }
 
-extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,
-                                    const void* idx, int32_t idx_type, int64_t n, int32_t L,
-                                    const int64_t* field_row_offset, int64_t hash_mod, const rb_grad_source* grad,
-                                    const rb_opt_params* opt, void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                           const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
+                                           void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+  RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
+               "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
+  int64_t n = 0;
+  for (int k = 0; k < num_groups; ++k) n += groups[k].n > 0 ? groups[k].n : 0;
   RowGeom geo;
-  int rc = check_common(rows, D, idx, idx_type, n, L, &geo);
+  int rc = check_common(rows, D, n, &geo);
   if (rc != RB_OK) return rc;
   RB_CHECK_ARG(table != nullptr && opt != nullptr, RB_ERR_ARG, "table/opt is null");
   RB_CHECK_ARG(aligned_for(table, geo.vec), RB_ERR_ALIGN, "table not aligned for vec=%d", geo.vec);
@@ -556,15 +589,12 @@ extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, 
     RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
                  lay.total, ws_bytes);
     RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
-    GradSrcDev gsrc;
-    rc = fill_grad_src(&gsrc, grad, L, idx_type, idx, table, D, geo.vec);
-    if (rc != RB_OK) return rc;
-    IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, L);
+    GradGroupsDev gg;
     const uint32_t *keys, *vals;
     unsigned char* wsb = static_cast<unsigned char*>(ws);
-    rc = sort_pairs(m, n, rows, wsb, lay, oob_flag, st, &keys, &vals);
+    rc = prepare_and_sort(groups, num_groups, rows, D, table, geo, n, wsb, lay, oob_flag, st, &gg, &keys, &vals);
     if (rc != RB_OK) return rc;
-    rc = run_segments(geo, keys, vals, static_cast<int>(n), gsrc, sink, wsb, lay, st);
+    rc = run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st);
     if (rc != RB_OK) return rc;
   }
   if (o == RB_OPT_ADAM_TF_DENSE) {
@@ -574,12 +604,28 @@ extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, 
   return RB_OK;
 }
 
+extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                    const void* idx, int32_t idx_type, int64_t n, int32_t L,
+                                    const int64_t* field_row_offset, int64_t hash_mod, const rb_grad_source* grad,
+                                    const rb_opt_params* opt, void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+  RB_CHECK_ARG(grad != nullptr, RB_ERR_ARG, "grad is null");
+  rb_lookup_group g;
+  g.idx = idx;
+  g.idx_type = idx_type;
+  g.L = L;
+  g.n = n;
+  g.field_row_offset = field_row_offset;
+  g.hash_mod = hash_mod;
+  g.grad = *grad;
+  return rb_sparse_bwd_update_groups(table, state0, state1, rows, D, &g, 1, opt, ws, ws_bytes, oob_flag, stream);
+}
+
 extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int32_t idx_type, int64_t n, int32_t L,
                                    const int64_t* field_row_offset, int64_t hash_mod, const rb_grad_source* grad,
                                    int64_t* uniq_rows, float* uniq_grad, int64_t* num_unique, void* ws, size_t ws_bytes,
                                    int32_t* oob_flag, void* stream) {
   RowGeom geo;
-  int rc = check_common(rows, D, idx, idx_type, n, L, &geo);
+  int rc = check_common(rows, D, n, &geo);
   if (rc != RB_OK) return rc;
   RB_CHECK_ARG(num_unique != nullptr, RB_ERR_ARG, "num_unique is null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -594,13 +640,18 @@ extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int
   RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
                lay.total, ws_bytes);
   RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
-  GradSrcDev gsrc;
-  rc = fill_grad_src(&gsrc, grad, L, idx_type, idx, nullptr, D, geo.vec);
-  if (rc != RB_OK) return rc;
-  IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, L);
+  rb_lookup_group g;
+  g.idx = idx;
+  g.idx_type = idx_type;
+  g.L = L;
+  g.n = n;
+  g.field_row_offset = field_row_offset;
+  g.hash_mod = hash_mod;
+  g.grad = *grad;
+  GradGroupsDev gg;
   const uint32_t *keys, *vals;
   unsigned char* wsb = static_cast<unsigned char*>(ws);
-  rc = sort_pairs(m, n, rows, wsb, lay, oob_flag, st, &keys, &vals);
+  rc = prepare_and_sort(&g, 1, rows, D, nullptr, geo, n, wsb, lay, oob_flag, st, &gg, &keys, &vals);
   if (rc != RB_OK) return rc;
   int32_t* seg = reinterpret_cast<int32_t*>(wsb + lay.seg_incl);
   head_flags_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, static_cast<int>(n), seg);
@@ -608,6 +659,7 @@ extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int
   size_t temp = lay.cub_bytes;
   RB_CUDA(cub::DeviceScan::InclusiveSum(wsb + lay.cub_temp, temp, seg, seg, static_cast<int>(n), st));
   write_num_unique_kernel<<<1, 1, 0, st>>>(seg, static_cast<int>(n), num_unique);
+  RB_LAUNCH_CHECK("write_num_unique_kernel");
   DedupSink sink{seg, uniq_rows, uniq_grad, D};
-  return run_segments(geo, keys, vals, static_cast<int>(n), gsrc, sink, wsb, lay, st);
+  return run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st);
 }

@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's layer call surface (ctr/layers.py, keras.layers.Embedding).
+
+Same class names, constructor arguments and call semantics as the reference so that the model
+code in model.py reads like ctr/model.py; every hot-path computation is a call into
+librecsys_b200.so (ops.py).  torch supplies device memory, streams and the autograd tape only.
+
+Training contract.  An `Embedding` owns its table as a plain CUDA tensor (not an autograd
+leaf).  The backward of every lookup records a *lookup group* (index array + where its gradient
+rows live) on the layer; `optimizers.*.apply_gradients()` then runs ONE fused
+sort -> duplicate-row sum -> optimizer-row-update call per table over the concatenation of the
+step's groups — the IndexedSlices concatenation + `_deduplicate_indexed_slices` +
+`_resource_apply_sparse` chain of Keras, never materialising a dense
+[V, D] gradient.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import GradSource, LookupGroup
+
+
+def _default_device(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("recommender_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd glue: forward = one C-ABI call; backward = one C-ABI call or a recorded lookup group
+# ----------------------------------------------------------------------------------------------
+
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, emb, idx):
+        L = idx.shape[-1] if idx.dim() >= 1 else 1
+        out = ops.gather_fwd(emb.embeddings, idx, L=L, field_row_offset=emb.row_offset_for(L), hash_mod=emb.hash_mod)
+        ctx.emb, ctx.idx, ctx.L = emb, idx, L
+        return out
+
+    @staticmethod
+    def backward(ctx, dE):
+        emb = ctx.emb
+        dE = dE.contiguous()
+        emb._record(LookupGroup(ctx.idx, ctx.L, GradSource.per_position(dE, ctx.L),
+                                field_row_offset=emb.row_offset_for(ctx.L), hash_mod=emb.hash_mod))
+        return None, None, None
+
+
+class _BagPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, emb, idx, mode, mask_idx):
+        out, count = ops.bag_pool_fwd(emb.embeddings, idx, mode, mask_idx=mask_idx, hash_mod=emb.hash_mod, want_count=True)
+        ctx.emb, ctx.idx, ctx.mode, ctx.mask_idx, ctx.count = emb, idx, mode, mask_idx, count
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        emb = ctx.emb
+        dout = dout.contiguous()
+        scale = {"sum": "none", "mean": "mean", "masked_mean": "masked_mean"}[ctx.mode]
+        grad = GradSource.per_bag([dout], scale=scale, mask_idx=ctx.mask_idx if ctx.mask_idx is not None else ctx.idx,
+                                  count=ctx.count)
+        emb._record(LookupGroup(ctx.idx, ctx.idx.shape[1], grad, hash_mod=emb.hash_mod))
+        return None, None, None, None, None
+
+
+class _GatherFMFn(torch.autograd.Function):
+    """ctr/model.py:19-23 in one pass: E, and fm = 0.5*sum_d((sum_f E)^2 - sum_f E^2)."""
+
+    @staticmethod
+    def forward(ctx, anchor, emb, idx):
+        F = idx.shape[1]
+        E, s, fm = ops.gather_fm_fwd(emb.embeddings, idx, field_row_offset=emb.row_offset_for(F), hash_mod=emb.hash_mod)
+        ctx.emb, ctx.idx, ctx.s = emb, idx, s
+        return E, fm
+
+    @staticmethod
+    def backward(ctx, dE, dfm):
+        emb = ctx.emb
+        B, F = ctx.idx.shape
+        D = emb.output_dim
+        if dE is None:
+            src, bs, ps = torch.zeros(D, dtype=torch.float32, device=ctx.idx.device), 0, 0
+        else:
+            src, bs, ps = dE.contiguous(), F * D, D
+        grad = GradSource([src], [bs], [ps], fm_g=None if dfm is None else dfm.contiguous(), fm_s=ctx.s)
+        emb._record(LookupGroup(ctx.idx, F, grad, field_row_offset=emb.row_offset_for(F), hash_mod=emb.hash_mod))
+        return None, None, None
+
+
+class _InteractFn(torch.autograd.Function):
+    """Lookup + DLRM concat + DotInteraction + '|| bmlp' tail in one kernel (ctr/model.py:49-55)."""
+
+    @staticmethod
+    def forward(ctx, anchor, emb, idx, dense_vec, self_interaction, skip_gather, tail):
+        F = idx.shape[1]
+        dense_vec = dense_vec.contiguous()
+        out = ops.dot_interaction_fwd(table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
+                                      dense_vec=dense_vec, self_interaction=self_interaction, skip_gather=skip_gather,
+                                      tail=tail)
+        ctx.emb, ctx.idx, ctx.flags = emb, idx, (self_interaction, skip_gather, tail)
+        ctx.save_for_backward(dense_vec)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        (dense_vec,) = ctx.saved_tensors
+        emb, idx = ctx.emb, ctx.idx
+        F = idx.shape[1]
+        si, sg, tail = ctx.flags
+        if dOut.stride(-1) != 1:
+            dOut = dOut.contiguous()
+        dE, d_dense = ops.dot_interaction_bwd(dOut, table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
+                                              dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail)
+        emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
+                                hash_mod=emb.hash_mod))
+        return None, None, None, d_dense, None, None, None
+
+
+class _DotInteractionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, self_interaction, skip_gather):
+        X = X.contiguous()
+        ctx.save_for_backward(X)
+        ctx.flags = (self_interaction, skip_gather)
+        return ops.dot_interaction_fwd(E=X, self_interaction=self_interaction, skip_gather=skip_gather)
+
+    @staticmethod
+    def backward(ctx, dOut):
+        (X,) = ctx.saved_tensors
+        si, sg = ctx.flags
+        if dOut.stride(-1) != 1:
+            dOut = dOut.contiguous()
+        dX, _ = ops.dot_interaction_bwd(dOut, E=X, self_interaction=si, skip_gather=sg)
+        return dX, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# layers
+# ----------------------------------------------------------------------------------------------
+
+class Embedding(nn.Module):
+    """Stand-in for keras.layers.Embedding(input_dim, output_dim, mask_zero=False)
+    (ctr/model.py:10,42; dien/model.py:11-12; esmm/esmm.py:10-11).
+
+    `embeddings` f32[input_dim, output_dim] ~ U(-0.05, 0.05) (the Keras default initialiser).
+    `num_tables` > 1 stores that many input_dim-row tables back to back and routes position f of
+    a [B, num_tables] index array to table f (the T = 26 form of BASELINE config 2).
+    `hash_mod` folds ids with uint64 mod before the lookup (capped tables).
+    """
+
+    def __init__(self, input_dim: int, output_dim: int, mask_zero: bool = False, *, num_tables: int = 1,
+                 hash_mod: int = 0, device=None, generator: Optional[torch.Generator] = None):
+        super().__init__()
+        dev = _default_device(device)
+        self.input_dim, self.output_dim, self.mask_zero = int(input_dim), int(output_dim), bool(mask_zero)
+        self.num_tables, self.hash_mod = int(num_tables), int(hash_mod)
+        rows = self.input_dim * self.num_tables
+        w = torch.empty(rows, self.output_dim, dtype=torch.float32, device=dev)
+        w.uniform_(-0.05, 0.05, generator=generator)
+        self.register_buffer("embeddings", w)
+        self.register_buffer("_row_offset", torch.arange(self.num_tables, dtype=torch.int64, device=dev) * self.input_dim
+                             if self.num_tables > 1 else None, persistent=False)
+        # makes autograd call the lookups' backward although the table itself is not a leaf
+        self._anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
+        self.pending: List[LookupGroup] = []
+        self.opt_state = {}
+
+    # -- helpers used by the autograd functions
+    def row_offset_for(self, L: int):
+        if self.num_tables == 1:
+            return None
+        if L != self.num_tables:
+            raise ValueError(f"a {self.num_tables}-table embedding takes [B, {self.num_tables}] indices, got last dim {L}")
+        return self._row_offset
+
+    def _record(self, group: LookupGroup) -> None:
+        self.pending.append(group)
+
+    # -- the Keras call surface
+    def forward(self, idx: torch.Tensor) -> torch.Tensor:
+        """E[..., :] = embeddings[idx[...], :]   (ctr/model.py:19, :49)."""
+        return _GatherFn.apply(self._anchor, self, idx)
+
+    def compute_mask(self, x, mask=None):
+        return (x != 0) if self.mask_zero else None   # dien/model.py:25
+
+    # -- fused forms of the call sites around the lookup
+    def pooled(self, idx: torch.Tensor, mode: str = "sum", mask_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sum / mean / masked mean over axis 1 of the looked-up rows without materialising them
+        (ctr/model.py:21; dien/layers.py:5-17 with mask = mask_idx != 0, default idx != 0)."""
+        return _BagPoolFn.apply(self._anchor, self, idx, mode, mask_idx)
+
+    def lookup_fm(self, idx: torch.Tensor):
+        """(E[B,F,D], fm[B]) of ctr/model.py:19-23 in one pass over the rows."""
+        return _GatherFMFn.apply(self._anchor, self, idx)
+
+    def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True):
+        """ctr/model.py:49-55 fused: [DotInteraction([E ; dense_vec]) || dense_vec] with E read
+        straight from the table, so [B,F,D] and [B,F+1,D] never exist in HBM."""
+        return _InteractFn.apply(self._anchor, self, idx, dense_vec, self_interaction, skip_gather, tail)
+
+    # -- optimizer side (called by optimizers.*.apply_gradients)
+    def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                      initial_accumulator_value=0.1) -> int:
+        """Runs the fused backward scatter + row update over this step's lookup groups."""
+        if not self.pending:
+            if kind == "adam_tf_dense":   # Keras moves every row every step, gradient or not
+                raise NotImplementedError("adam_tf_dense with no lookup in the step")
+            return 0
+        st = self.opt_state
+        if kind in ("adam_lazy", "adam_tf_dense"):
+            if "m" not in st:
+                st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
+            s0, s1 = st["m"], st["v"]
+        elif kind == "adagrad":
+            if "acc" not in st:
+                st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
+            s0, s1 = st["acc"], None
+        elif kind == "sgd":
+            s0 = s1 = None
+        else:
+            raise ValueError(kind)
+        groups, self.pending = self.pending, []
+        n = sum(g.n for g in groups)
+        ops.sparse_bwd_update(self.embeddings, s0, s1, groups, optimizer=kind, step=step, lr=lr, beta_1=beta_1,
+                              beta_2=beta_2, epsilon=epsilon)
+        return n
+
+
+class MLP(nn.Module):
+    """ctr/layers.py:5-14: Dense layers whose HIDDEN layers are linear; only the last layer has
+    `final_activation` (None | 'relu' | 'sigmoid').  Kernels are [in, units] Glorot-uniform, biases
+    zero (Keras defaults), built on the first call like Keras does.  Dense and data-parallel:
+    it runs on cuBLAS through torch and is not part of the sparse hot path."""
+
+    def __init__(self, units: Sequence[int], final_activation=None, *, compute_dtype: Optional[torch.dtype] = None,
+                 generator: Optional[torch.Generator] = None):
+        super().__init__()
+        if final_activation not in (None, "relu", "sigmoid"):
+            raise ValueError(final_activation)
+        self.units, self.final_activation = list(units), final_activation
+        self.compute_dtype, self._generator = compute_dtype, generator
+        self.kernels = nn.ParameterList()
+        self.biases = nn.ParameterList()
+
+    def build(self, in_dim: int, device) -> None:
+        for u in self.units:
+            lim = math.sqrt(6.0 / (in_dim + u))
+            w = torch.empty(in_dim, u, dtype=torch.float32, device=device).uniform_(-lim, lim, generator=self._generator)
+            self.kernels.append(nn.Parameter(w))
+            self.biases.append(nn.Parameter(torch.zeros(u, dtype=torch.float32, device=device)))
+            in_dim = u
+
+    def load_arrays(self, layers, device) -> None:
+        """Adopt [(kernel[in,units], bias[units])...] (numpy or tensors): the oracle owns the init in
+        parity tests because TF's RNG streams cannot be matched."""
+        self.kernels = nn.ParameterList(nn.Parameter(torch.as_tensor(W, dtype=torch.float32).to(device).contiguous()) for W, _ in layers)
+        self.biases = nn.ParameterList(nn.Parameter(torch.as_tensor(b, dtype=torch.float32).to(device).contiguous()) for _, b in layers)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if len(self.kernels) == 0:
+            self.build(x.shape[-1], x.device)
+        cd = self.compute_dtype
+        last = len(self.kernels) - 1
+        for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
+            if cd is not None:
+                x = torch.addmm(b.to(cd), x.to(cd), W.to(cd))
+            else:
+                x = torch.addmm(b, x, W)
+            if i == last:
+                x = x.float()
+                if self.final_activation == "relu":
+                    x = torch.relu(x)
+                elif self.final_activation == "sigmoid":
+                    x = torch.sigmoid(x)
+        return x
+
+
+class DotInteraction(nn.Module):
+    """ctr/layers.py:17-43.  X f32[B,F',D] -> f32[B,F'^2] (skip_gather=True: kept entries in place,
+    zeros elsewhere) or the compact [B, F'(F'-1)/2] / [B, F'(F'+1)/2] (skip_gather=False).
+    self_interaction=False keeps the strict upper triangle (j > i); True keeps the lower triangle
+    including the diagonal (j <= i) — the reference's `upper_matrix` really is band_part(.,-1,0)."""
+
+    def __init__(self, self_interaction: bool, skip_gather: bool):
+        super().__init__()
+        self.self_interaction, self.skip_gather = bool(self_interaction), bool(skip_gather)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        return _DotInteractionFn.apply(inputs, self.self_interaction, self.skip_gather)
+
+
+def compute_his_average(embedding: Embedding, idx: torch.Tensor, mask_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dien/layers.py:5-17 fused with its lookup (dien/model.py:14-19,25-31): masked mean over the
+    history axis with mask = (mask_idx != 0); an all-pad history yields NaN, as in the reference."""
+    return embedding.pooled(idx, "masked_mean", mask_idx)

@@ -1,0 +1,95 @@
+"""DeepFM and DLRM with the reference's call surface (ctr/model.py), on the CUDA hot path.
+
+Constructor arguments, the input dict ({'cat_features', 'int_features'}) and the f32[B] output
+are those of ctr/model.py:6-58.  `fused=True` (default) routes the lookup + interaction through
+the single-pass kernels; `fused=False` replays the reference's op sequence layer by layer
+(Embedding -> concat -> DotInteraction -> concat) on the same kernels, un-fused.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from .layers import MLP, DotInteraction, Embedding
+
+
+class DeepFM(nn.Module):
+    """ctr/model.py:6-31.  One shared table; FM second order (no first-order term, no bias) + an MLP
+    on [flatten(E) || int_features]; sigmoid(fm + mlp)."""
+
+    def __init__(self, embedding_size: int, vocab_size: int, num_int_fea: int, num_cat_fea: int, mlp_units: Sequence[int],
+                 *, num_tables: int = 1, fused: bool = True, device=None, compute_dtype: Optional[torch.dtype] = None,
+                 generator: Optional[torch.Generator] = None):
+        super().__init__()
+        self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :10
+        self.mlp = MLP(mlp_units, None, compute_dtype=compute_dtype, generator=generator)                                      # :11
+        self.num_int_fea, self.num_cat_fea, self.fused = num_int_fea, num_cat_fea, fused
+
+    def logits(self, inputs):
+        int_features = inputs["int_features"].reshape(-1, self.num_int_fea)            # :17
+        cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :18
+        if self.fused:
+            cat_embedding, interaction = self.embedding_layer.lookup_fm(cat_features)  # :19-23 in one pass
+        else:
+            cat_embedding = self.embedding_layer(cat_features)                          # :19
+            sum_square = torch.square(cat_embedding.sum(dim=1))                         # :21
+            square_sum = torch.square(cat_embedding).sum(dim=1)                         # :22
+            interaction = 0.5 * (sum_square - square_sum).sum(dim=1)                    # :23
+        deep_cat_input = cat_embedding.reshape(-1, self.num_cat_fea * cat_embedding.shape[2])   # :25
+        deep_input = torch.cat([deep_cat_input, int_features], dim=1)                   # :26
+        dense_output = self.mlp(deep_input)                                             # :27
+        return interaction + dense_output.squeeze(1)                                    # :28-29
+
+    def forward(self, inputs, training=None, mask=None):
+        return torch.sigmoid(self.logits(inputs))                                       # :30
+
+
+class DLRM(nn.Module):
+    """ctr/model.py:34-58.  Shared table, bottom MLP (last activation relu) whose output joins the 26
+    embeddings as feature 27, DotInteraction(False, True), [interaction || bottom] -> top MLP (sigmoid)."""
+
+    def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
+                 num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, fused: bool = True, device=None,
+                 compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None):
+        super().__init__()
+        if bottom_mlp_units[-1] != embedding_size:
+            # ctr/model.py:52,55: the concat and the shape-asserting reshape need equal widths
+            raise ValueError("bottom_mlp_units[-1] must equal embedding_size")
+        self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator)      # :38
+        self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)         # :39
+        self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :42
+        self.interaction = DotInteraction(False, True)                                                          # :43
+        self.num_cat_fea, self.num_int_fea, self.embedding_size, self.fused = num_cat_fea, num_int_fea, embedding_size, fused
+
+    def forward(self, inputs, training=None, mask=None):
+        int_features = inputs["int_features"].reshape(-1, self.num_int_fea)            # :47
+        cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :48
+        bmlp_output = self.bottom_mlp(int_features)                                     # :50
+        if self.fused:
+            tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True)   # :49,:51-55
+        else:
+            cat_embedding = self.embedding_layer(cat_features)                          # :49
+            interaction_input = torch.cat([cat_embedding, bmlp_output.unsqueeze(1)], dim=1)            # :51-52
+            interaction_output = self.interaction(interaction_input)                    # :53
+            tmlp_input = torch.cat([interaction_output, bmlp_output], dim=1)            # :54
+        tmlp_input = tmlp_input.reshape(-1, (self.num_cat_fea + 1) ** 2 + self.embedding_size)          # :55
+        output = self.top_mlp(tmlp_input)                                               # :56
+        return output.squeeze(1)                                                        # :57
+
+
+def bce_clipped(prob: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """Keras binary_crossentropy on probabilities, batch mean — what compile(loss=BinaryCrossentropy)
+    evaluates for DLRM (ctr/train.py:85-87)."""
+    eps = 1e-7
+    y = label.to(prob.dtype)
+    p = prob.clamp(eps, 1.0 - eps)
+    return (-(y * torch.log(p + eps) + (1.0 - y) * torch.log(1.0 - p + eps))).mean()
+
+
+def bce_logits(logit: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """sigmoid_cross_entropy_with_logits, batch mean — the form Keras recovers for DeepFM whose last op
+    is Sigmoid (ctr/model.py:30)."""
+    y = label.to(logit.dtype)
+    return (logit.clamp(min=0) - logit * y + torch.log1p(torch.exp(-logit.abs()))).mean()

@@ -1,0 +1,359 @@
+"""Thin Python calls over the C ABI (include/recsys_b200.h): one function per entry point.
+
+torch tensors are only the carrier of device memory and of the CUDA stream; every computation
+happens in librecsys_b200.so.  All calls are asynchronous on torch's current stream.  Nothing
+here falls back to torch/CPU arithmetic: a non-CUDA tensor is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.RecsysError("recommender_b200 ops take CUDA tensors only (there is no CPU path)")
+
+
+def _idx(idx: torch.Tensor):
+    if idx.dtype == torch.int64:
+        return _lib.RB_I64
+    if idx.dtype == torch.int32:
+        return _lib.RB_I32
+    raise TypeError(f"indices must be int32 or int64, got {idx.dtype}")
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def version() -> int:
+    return lib.rb_version()
+
+
+def kernel_launches() -> int:
+    """Kernels of librecsys_b200.so launched by this process so far."""
+    return int(lib.rb_kernel_launches())
+
+
+def adam_alpha_t(lr, beta_1, beta_2, step) -> float:
+    return float(lib.rb_adam_alpha_t(lr, beta_1, beta_2, int(step)))
+
+
+_oob_flags = {}
+
+
+def oob_flag(device) -> torch.Tensor:
+    """Per-device int32 flag the kernels raise when an index falls outside [0, rows)."""
+    key = torch.device(device).index or 0
+    if key not in _oob_flags:
+        _oob_flags[key] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{key}")
+    return _oob_flags[key]
+
+
+def check_oob(device) -> None:
+    """Synchronising debug check (TF's CPU kernel raises InvalidArgument; the GPU one zero-fills)."""
+    f = oob_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError("embedding index out of range (InvalidArgument)")
+
+
+# --------------------------------------------------------------------------------------------
+# K1: lookups
+# --------------------------------------------------------------------------------------------
+
+def gather_fwd(table, idx, *, L=1, field_row_offset=None, hash_mod=0, out=None, out_stride=None):
+    """out[p,:] = table[row(idx[p]),:]   (rb_gather_fwd).  idx any shape; returns [*idx.shape, D]."""
+    _need_cuda(table, idx, field_row_offset, out)
+    _f32c(table, "table")
+    idx = idx.contiguous()
+    rows, D = table.shape
+    n = idx.numel()
+    if out is None:
+        out = torch.empty(*idx.shape, D, dtype=torch.float32, device=table.device)
+        out_stride = D
+    check(lib.rb_gather_fwd(_ptr(table), rows, D, _ptr(idx), _idx(idx), n, int(L), _ptr(field_row_offset), int(hash_mod),
+                            _ptr(out), int(out_stride), _ptr(oob_flag(table.device)), _stream()), "rb_gather_fwd")
+    return out
+
+
+def bag_pool_fwd(table, idx, mode="sum", *, mask_idx=None, field_row_offset=None, hash_mod=0, out=None,
+                 out_stride=None, want_count=False):
+    """Pooled lookup over axis 1 of idx[B,L] (rb_bag_pool_fwd).  Returns out[B,D] (and count[B])."""
+    _need_cuda(table, idx, mask_idx, field_row_offset, out)
+    _f32c(table, "table")
+    idx = idx.contiguous()
+    B, L = idx.shape
+    rows, D = table.shape
+    if mask_idx is not None:
+        mask_idx = mask_idx.contiguous()
+        if mask_idx.dtype != idx.dtype or mask_idx.shape != idx.shape:
+            raise ValueError("mask_idx must have the dtype and shape of idx")
+    if out is None:
+        out = torch.empty(B, D, dtype=torch.float32, device=table.device)
+        out_stride = D
+    count = torch.empty(B, dtype=torch.float32, device=table.device) if want_count else None
+    check(lib.rb_bag_pool_fwd(_ptr(table), rows, D, _ptr(idx), _idx(idx), B, L, _ptr(field_row_offset), int(hash_mod),
+                              _lib.POOL_ENUM[mode], _ptr(mask_idx), _ptr(out), int(out_stride), _ptr(count),
+                              _ptr(oob_flag(table.device)), _stream()), "rb_bag_pool_fwd")
+    return (out, count) if want_count else out
+
+
+def gather_fm_fwd(table, idx, *, field_row_offset=None, hash_mod=0, want_E=True, want_s=True):
+    """DeepFM front end (rb_gather_fm_fwd): returns (E[B,F,D] | None, s[B,D] | None, fm[B])."""
+    _need_cuda(table, idx, field_row_offset)
+    _f32c(table, "table")
+    idx = idx.contiguous()
+    B, F = idx.shape
+    rows, D = table.shape
+    dev = table.device
+    E = torch.empty(B, F, D, dtype=torch.float32, device=dev) if want_E else None
+    s = torch.empty(B, D, dtype=torch.float32, device=dev) if want_s else None
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    check(lib.rb_gather_fm_fwd(_ptr(table), rows, D, _ptr(idx), _idx(idx), B, F, _ptr(field_row_offset), int(hash_mod),
+                               _ptr(E), _ptr(s), _ptr(fm), _ptr(oob_flag(dev)), _stream()), "rb_gather_fm_fwd")
+    return E, s, fm
+
+
+# --------------------------------------------------------------------------------------------
+# K3..K6, K10: DotInteraction
+# --------------------------------------------------------------------------------------------
+
+def interaction_ncols(Fp: int, self_interaction: bool, skip_gather: bool) -> int:
+    if skip_gather:
+        return Fp * Fp
+    return Fp * (Fp + 1) // 2 if self_interaction else Fp * (Fp - 1) // 2
+
+
+def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
+                        self_interaction=False, skip_gather=True, tail=False, out=None, out_stride=None):
+    """rb_dot_interaction_fwd.  Either E[B,F,D] or (table, idx[B,F]) supplies the embedding rows."""
+    _need_cuda(E, table, idx, field_row_offset, dense_vec, out)
+    if E is not None:
+        _f32c(E, "E")
+        B, F, D = E.shape
+        rows, it, dev = 0, _lib.RB_I64, E.device
+    else:
+        _f32c(table, "table")
+        idx = idx.contiguous()
+        B, F = idx.shape
+        rows, D = table.shape
+        it, dev = _idx(idx), table.device
+    if dense_vec is not None:
+        _f32c(dense_vec, "dense_vec")
+        if tuple(dense_vec.shape) != (B, D):
+            raise ValueError(f"dense_vec must be [{B},{D}], got {tuple(dense_vec.shape)}")
+    Fp = F + (dense_vec is not None)
+    ncols = interaction_ncols(Fp, self_interaction, skip_gather)
+    width = ncols + (D if tail else 0)
+    if out is None:
+        out = torch.empty(B, width, dtype=torch.float32, device=dev)
+        out_stride = width
+    check(lib.rb_dot_interaction_fwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
+                                     B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(out), int(out_stride),
+                                     _stream()), "rb_dot_interaction_fwd")
+    return out
+
+
+def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
+                        self_interaction=False, skip_gather=True, tail=False, want_dE=True):
+    """rb_dot_interaction_bwd.  Returns (dE[B,F,D] | None, d_dense[B,D] | None)."""
+    _need_cuda(dOut, E, table, idx, field_row_offset, dense_vec)
+    if E is not None:
+        _f32c(E, "E")
+        B, F, D = E.shape
+        rows, it, dev = 0, _lib.RB_I64, E.device
+    else:
+        _f32c(table, "table")
+        idx = idx.contiguous()
+        B, F = idx.shape
+        rows, D = table.shape
+        it, dev = _idx(idx), table.device
+    if dOut.dtype != torch.float32 or dOut.stride(-1) != 1 or dOut.dim() != 2 or dOut.shape[0] != B:
+        raise ValueError("dOut must be float32 [B, cols] with unit inner stride")
+    dE = torch.empty(B, F, D, dtype=torch.float32, device=dev) if want_dE else None
+    d_dense = torch.empty(B, D, dtype=torch.float32, device=dev) if dense_vec is not None else None
+    check(lib.rb_dot_interaction_bwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
+                                     B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(dOut),
+                                     int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _stream()), "rb_dot_interaction_bwd")
+    return dE, d_dense
+
+
+# --------------------------------------------------------------------------------------------
+# K7..K9: backward scatter + sparse optimizer
+# --------------------------------------------------------------------------------------------
+
+class GradSource:
+    """Python mirror of rb_grad_source (see the header for the addressing rule)."""
+
+    def __init__(self, srcs: Sequence[torch.Tensor], bag_strides: Sequence[int], pos_strides: Sequence[int],
+                 scale="none", mask_idx=None, count=None, fm_g=None, fm_s=None):
+        if not (1 <= len(srcs) <= _lib.RB_MAX_GRAD_SOURCES):
+            raise ValueError(f"1..{_lib.RB_MAX_GRAD_SOURCES} gradient sources, got {len(srcs)}")
+        _need_cuda(*srcs, mask_idx, count, fm_g, fm_s)
+        for s in srcs:
+            if s.dtype != torch.float32:
+                raise TypeError("gradient sources must be float32")
+        self.srcs, self.bag_strides, self.pos_strides = list(srcs), list(bag_strides), list(pos_strides)
+        self.scale, self.mask_idx, self.count, self.fm_g, self.fm_s = scale, mask_idx, count, fm_g, fm_s
+
+    @classmethod
+    def per_position(cls, dE: torch.Tensor, L: int):
+        """dE[..., L, D] contiguous: one gradient row per lookup position (un-pooled lookup)."""
+        _f32c(dE, "dE")
+        D = dE.shape[-1]
+        return cls([dE], [L * D], [D])
+
+    @classmethod
+    def per_bag(cls, douts: Sequence[torch.Tensor], scale="none", mask_idx=None, count=None, col_offset=0, D=None):
+        """Bag-level gradients dout[k][B, ld_k]: every position of bag b receives
+        dout[k][b, col_offset : col_offset + D] (sum / mean / masked-mean pooling, or bag size 1)."""
+        return cls([d[:, col_offset:] if col_offset else d for d in douts], [d.stride(0) for d in douts],
+                   [0] * len(douts), scale=scale, mask_idx=mask_idx, count=count)
+
+    def to_c(self) -> _lib.RbGradSource:
+        g = _lib.RbGradSource()
+        g.num_src = len(self.srcs)
+        g.scale_mode = _lib.SCALE_ENUM[self.scale]
+        for k, (s, bs, ps) in enumerate(zip(self.srcs, self.bag_strides, self.pos_strides)):
+            g.src[k] = s.data_ptr()
+            g.bag_stride[k] = int(bs)
+            g.pos_stride[k] = int(ps)
+        g.mask_idx = _ptr(self.mask_idx)
+        g.count = _ptr(self.count)
+        g.fm_g = _ptr(self.fm_g)
+        g.fm_s = _ptr(self.fm_s)
+        return g
+
+
+class LookupGroup:
+    """One use of a table inside a step: its index array, bag length and gradient source."""
+
+    def __init__(self, idx: torch.Tensor, L: int, grad: GradSource, field_row_offset=None, hash_mod=0):
+        _need_cuda(idx, field_row_offset)
+        self.idx = idx.contiguous()
+        self.L, self.grad, self.field_row_offset, self.hash_mod = int(L), grad, field_row_offset, int(hash_mod)
+
+    @property
+    def n(self) -> int:
+        return self.idx.numel()
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Caller-owned scratch (the library never allocates): grown geometrically, reused per device."""
+    key = torch.device(device).index or 0
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, device=f"cuda:{key}")
+        _workspaces[key] = ws
+    return ws
+
+
+def _opt_params(optimizer: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7) -> _lib.RbOptParams:
+    return _lib.RbOptParams(_lib.OPTIMIZER_ENUM[optimizer], int(step), float(lr), float(beta_1), float(beta_2), float(epsilon))
+
+
+def sparse_bwd_update(table, state0, state1, groups: Sequence[LookupGroup], *, optimizer="adam_lazy", step=1,
+                      lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7) -> None:
+    """IndexedSlices -> duplicate-row sum -> optimizer row update, in place on table/state
+    (rb_sparse_bwd_update_groups; one group = rb_sparse_bwd_update)."""
+    _need_cuda(table, state0, state1)
+    _f32c(table, "table")
+    rows, D = table.shape
+    if not (1 <= len(groups) <= _lib.RB_MAX_LOOKUP_GROUPS):
+        raise ValueError(f"1..{_lib.RB_MAX_LOOKUP_GROUPS} lookup groups per table and step, got {len(groups)}")
+    n = sum(g.n for g in groups)
+    nbytes = lib.rb_sparse_bwd_update_workspace_bytes(n, D, rows)
+    if nbytes == 0:
+        raise _lib.RecsysError("rb_sparse_bwd_update_workspace_bytes rejected the problem size")
+    ws = _workspace(nbytes, table.device)
+    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon)
+    arr = (_lib.RbLookupGroup * len(groups))()
+    for k, g in enumerate(groups):
+        arr[k].idx = g.idx.data_ptr()
+        arr[k].idx_type = _idx(g.idx)
+        arr[k].L = g.L
+        arr[k].n = g.n
+        arr[k].field_row_offset = _ptr(g.field_row_offset)
+        arr[k].hash_mod = g.hash_mod
+        arr[k].grad = g.grad.to_c()
+    check(lib.rb_sparse_bwd_update_groups(_ptr(table), _ptr(state0), _ptr(state1), rows, D, arr, len(groups),
+                                          C.byref(opt), _ptr(ws), ws.numel(), _ptr(oob_flag(table.device)), _stream()),
+          "rb_sparse_bwd_update_groups")
+
+
+def sparse_bwd_dedup(rows: int, D: int, idx, L: int, grad: GradSource, *, field_row_offset=None, hash_mod=0):
+    """The deduplicated IndexedSlices itself (rb_sparse_bwd_dedup): (unique rows ascending, summed grads)."""
+    _need_cuda(idx, field_row_offset)
+    idx = idx.contiguous()
+    n = idx.numel()
+    dev = idx.device
+    uniq_rows = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    uniq_grad = torch.empty(max(n, 1), D, dtype=torch.float32, device=dev)
+    num = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _workspace(max(lib.rb_sparse_bwd_update_workspace_bytes(n, D, rows), 256), dev)
+    g = grad.to_c()
+    check(lib.rb_sparse_bwd_dedup(rows, D, _ptr(idx), _idx(idx), n, int(L), _ptr(field_row_offset), int(hash_mod),
+                                  C.byref(g), _ptr(uniq_rows), _ptr(uniq_grad), _ptr(num), _ptr(ws), ws.numel(),
+                                  _ptr(oob_flag(dev)), _stream()), "rb_sparse_bwd_dedup")
+    u = int(num.item())
+    return uniq_rows[:u], uniq_grad[:u]
+
+
+# --------------------------------------------------------------------------------------------
+# id -> row map, sharding
+# --------------------------------------------------------------------------------------------
+
+def hash_ids(ids, vocab: int, world: int = 1):
+    """rows = uint64(id) mod vocab; owner = row mod world; local = row div world (rb_hash_ids)."""
+    _need_cuda(ids)
+    ids = ids.contiguous()
+    n = ids.numel()
+    rows = torch.empty(ids.shape, dtype=torch.int64, device=ids.device)
+    owner = torch.empty(ids.shape, dtype=torch.int32, device=ids.device)
+    local = torch.empty(ids.shape, dtype=torch.int64, device=ids.device)
+    check(lib.rb_hash_ids(_ptr(ids), _idx(ids), n, int(vocab), int(world), _ptr(rows), _ptr(owner), _ptr(local), _stream()),
+          "rb_hash_ids")
+    return rows, owner, local
+
+
+def bucket_by_owner(idx, world: int, *, L=1, field_row_offset=None, hash_mod=0):
+    """Stable partition of the lookups by owner rank = row mod world (rb_bucket_by_owner).
+
+    Returns (local_rows int64[n] in bucket order, perm int32[n]: bucket slot -> lookup position,
+    inv_perm int32[n]: lookup position -> bucket slot, counts int64[world])."""
+    _need_cuda(idx, field_row_offset)
+    idx = idx.contiguous()
+    n = idx.numel()
+    dev = idx.device
+    local_rows = torch.empty(n, dtype=torch.int64, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    inv_perm = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    ws = _workspace(max(lib.rb_bucket_by_owner_workspace_bytes(n, world), 256), dev)
+    check(lib.rb_bucket_by_owner(_ptr(idx), _idx(idx), n, int(L), _ptr(field_row_offset), int(hash_mod), int(world),
+                                 _ptr(local_rows), _ptr(perm), _ptr(inv_perm), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
+          "rb_bucket_by_owner")
+    return local_rows, perm, inv_perm, counts

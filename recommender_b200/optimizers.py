@@ -1,0 +1,131 @@
+"""Mirrors of the Keras optimizers the reference builds (`Adam()` at ctr/train.py:80,84).
+
+One optimizer object drives both kinds of variables of a model:
+  * dense parameters (the MLPs) — the Keras formula restated with torch foreach ops
+    (`_resource_apply_dense`; note Keras' epsilon placement differs from
+    torch.optim.Adam, which is why torch's own Adam is not used);
+  * embedding tables — ONE fused CUDA call per table (`Embedding.apply_pending`): sort of the
+    (row, position) pairs, duplicate-row sum, optimizer row update (A.1-A.4).
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+
+from . import ops
+from .layers import Embedding
+
+
+def _split(model_or_vars):
+    if isinstance(model_or_vars, torch.nn.Module):
+        embs = [m for m in model_or_vars.modules() if isinstance(m, Embedding)]
+        dense = [p for p in model_or_vars.parameters() if p.requires_grad]
+        return embs, dense
+    embs, dense = [], []
+    for v in model_or_vars:
+        (embs if isinstance(v, Embedding) else dense).append(v)
+    return embs, dense
+
+
+class _Optimizer:
+    sparse_kind = "sgd"
+
+    def __init__(self):
+        self.iterations = 0
+        self._state = {}
+
+    def _sparse_kwargs(self):
+        raise NotImplementedError
+
+    def _dense_step(self, params, grads, step):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def apply_gradients(self, model_or_vars) -> None:
+        """One optimizer step over every dense parameter with a .grad and every Embedding with
+        recorded lookups; then clears them (the reference's `apply_gradients(zip(grads, vars))`,
+        dien/train.py:22)."""
+        embs, dense = _split(model_or_vars)
+        step = self.iterations + 1
+        params = [p for p in dense if p.grad is not None]
+        if params:
+            self._dense_step(params, [p.grad for p in params], step)
+            for p in params:
+                p.grad = None
+        for e in embs:
+            e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+        self.iterations = step
+
+
+class Adam(_Optimizer):
+    """tf.keras.optimizers.Adam(learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7).
+
+    sparse='lazy' (default) updates only the rows a step touches; sparse='tf_dense' reproduces
+    Keras' `_resource_apply_sparse` exactly (m, v decay and var moves on EVERY row each step).
+    Both agree on step 1 from zero state."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, sparse="lazy"):
+        super().__init__()
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.sparse_kind = {"lazy": "adam_lazy", "tf_dense": "adam_tf_dense"}[sparse]
+
+    def _sparse_kwargs(self):
+        return dict(lr=self.learning_rate, beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon)
+
+    def _dense_step(self, params, grads, step):
+        ms, vs = [], []
+        for p in params:
+            st = self._state.get(p)
+            if st is None:
+                st = self._state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+            ms.append(st[0])
+            vs.append(st[1])
+        alpha = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, step)
+        torch._foreach_mul_(ms, self.beta_1)
+        torch._foreach_add_(ms, grads, alpha=1.0 - self.beta_1)
+        torch._foreach_mul_(vs, self.beta_2)
+        torch._foreach_addcmul_(vs, grads, grads, value=1.0 - self.beta_2)
+        denom = torch._foreach_sqrt(vs)
+        torch._foreach_add_(denom, self.epsilon)
+        torch._foreach_addcdiv_(params, ms, denom, value=-alpha)
+
+
+class Adagrad(_Optimizer):
+    """tf.keras.optimizers.Adagrad(learning_rate=1e-3, initial_accumulator_value=0.1, epsilon=1e-7)
+    (named by the north star)."""
+    sparse_kind = "adagrad"
+
+    def __init__(self, learning_rate=1e-3, initial_accumulator_value=0.1, epsilon=1e-7):
+        super().__init__()
+        self.learning_rate, self.initial_accumulator_value, self.epsilon = learning_rate, initial_accumulator_value, epsilon
+
+    def _sparse_kwargs(self):
+        return dict(lr=self.learning_rate, epsilon=self.epsilon, initial_accumulator_value=self.initial_accumulator_value)
+
+    def _dense_step(self, params, grads, step):
+        accs = []
+        for p in params:
+            st = self._state.get(p)
+            if st is None:
+                st = self._state[p] = torch.full_like(p, self.initial_accumulator_value)
+            accs.append(st)
+        torch._foreach_addcmul_(accs, grads, grads, value=1.0)
+        denom = torch._foreach_sqrt(accs)
+        torch._foreach_add_(denom, self.epsilon)
+        torch._foreach_addcdiv_(params, grads, denom, value=-self.learning_rate)
+
+
+class SGD(_Optimizer):
+    """tf.keras.optimizers.SGD(learning_rate) — the commented-out option at ctr/train.py:79."""
+    sparse_kind = "sgd"
+
+    def __init__(self, learning_rate=1e-2):
+        super().__init__()
+        self.learning_rate = learning_rate
+
+    def _sparse_kwargs(self):
+        return dict(lr=self.learning_rate)
+
+    def _dense_step(self, params, grads, step):
+        torch._foreach_add_(params, grads, alpha=-self.learning_rate)

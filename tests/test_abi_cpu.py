@@ -1,0 +1,99 @@
+"""The C-ABI shared library on a machine WITHOUT a GPU: it builds, loads, exports every symbol
+include/recsys_b200.h declares, and its argument validation (which runs before any CUDA call)
+returns the documented status codes.  No kernel is launched here."""
+import ctypes as C
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ctr_oracle as O
+from recommender_b200 import _lib
+
+
+def test_every_header_symbol_is_exported_and_bound(cuda_lib):
+    declared = _lib.header_symbols()
+    assert len(declared) >= 15
+    dll = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), f"{name} declared in recsys_b200.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+
+
+def test_library_targets_sm_100a(cuda_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_struct_layout_matches_header():
+    # plain C layout: 2*int32 + 16 ptr + 16 i64 + 16 i64 + 4 ptr ; group = ptr,2*i32,i64,ptr,i64 + grad
+    assert C.sizeof(_lib.RbGradSource) == 8 + 16 * 8 * 3 + 4 * 8
+    assert C.sizeof(_lib.RbLookupGroup) == 8 + 8 + 8 + 8 + 8 + C.sizeof(_lib.RbGradSource)
+    assert C.sizeof(_lib.RbOptParams) == 24
+
+
+def test_version_and_alpha_t(cuda_lib):
+    assert cuda_lib.rb_version() == 100
+    for step in (1, 2, 10, 1000, 100000):
+        a = cuda_lib.rb_adam_alpha_t(1e-3, 0.9, 0.999, step)
+        b = float(O.adam_alpha_t(step))
+        assert np.float32(a) == np.float32(b), (step, a, b)   # both sides: libm powf in fp32, as TF-CPU
+
+
+def test_argument_validation_without_a_gpu(cuda_lib):
+    L = cuda_lib
+    buf = (C.c_float * 64)()
+    idx = (C.c_int64 * 4)()
+    p = C.addressof(buf)
+    # null table
+    assert L.rb_gather_fwd(None, 10, 16, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, p, 16, None, None) == -1
+    assert b"table" in L.rb_last_error()
+    # unsupported D (D/vec > 32)
+    assert L.rb_gather_fwd(p, 10, 132, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, p, 132, None, None) == -2
+    # misaligned table for vec=4
+    assert L.rb_gather_fwd(p + 4, 10, 16, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, p, 16, None, None) == -3
+    # bad index type
+    assert L.rb_gather_fwd(p, 10, 16, C.addressof(idx), 7, 4, 1, None, 0, p, 16, None, None) == -1
+    # empty problems succeed without touching the device
+    assert L.rb_gather_fwd(p, 10, 16, None, _lib.RB_I64, 0, 1, None, 0, None, 16, None, None) == 0
+    assert L.rb_bag_pool_fwd(p, 10, 16, None, _lib.RB_I32, 0, 5, None, 0, _lib.RB_POOL_SUM, None, None, 16, None, None, None) == 0
+    # interaction: too many features / bad D
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 33, 16, 0, 1, 0, p, 33 * 33, None) == -2
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 24, 0, 1, 0, p, 729, None) == -2
+    # tail without a dense vector
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 26, 16, 0, 1, 1, p, 800, None) == -1
+    # sparse update: workspace too small is reported with the needed size
+    need = L.rb_sparse_bwd_update_workspace_bytes(1000, 16, 5000)
+    assert need > 1000 * 16
+    assert L.rb_sparse_bwd_update_workspace_bytes(-1, 16, 10) == 0
+    gs = _lib.RbGradSource()
+    gs.num_src = 1
+    gs.src[0] = p
+    opt = _lib.RbOptParams(_lib.RB_OPT_ADAM_LAZY, 1, 1e-3, 0.9, 0.999, 1e-7)
+    rc = L.rb_sparse_bwd_update(p, p, p, 5000, 16, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, C.byref(gs), C.byref(opt),
+                                p, 16, None, None)
+    assert rc == -4 and b"workspace" in L.rb_last_error()
+    # Adam without state
+    rc = L.rb_sparse_bwd_update(p, None, None, 5000, 16, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, C.byref(gs),
+                                C.byref(opt), p, need, None, None)
+    assert rc == -1
+    assert L.rb_bucket_by_owner_workspace_bytes(1000, 8) > 0
+    assert L.rb_bucket_by_owner(C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, 0, p, p, p, p, p, 1 << 20, None) == -1
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from recommender_b200 import ops
+    W = torch.zeros(8, 16)
+    idx = torch.zeros(4, dtype=torch.int64)
+    with pytest.raises(_lib.RecsysError):
+        ops.gather_fwd(W, idx)
+    with pytest.raises(_lib.RecsysError):
+        ops.dot_interaction_fwd(E=torch.zeros(2, 27, 16))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    fresh = _lib._Lib()
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fresh.load()

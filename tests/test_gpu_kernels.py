@@ -1,0 +1,389 @@
+"""CUDA kernels against the numpy oracle and the golden fixtures, through the C ABI (ops.py).
+
+Bars (north star): index math and the un-pooled gather bit-exact; pooled outputs fp32 within
+1e-6 relative (summation order equals the oracle's); interaction within the bf16-operand bound
+and tight against the oracle's bf16-operand mode; updated rows bit-exact for duplicate-free
+batches and within fp32 re-association tolerance otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.as_tensor(a).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_lib):
+    from recommender_b200 import ops as _ops
+    return _ops
+
+
+# ---- K1: gather ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("D", [16, 64, 18, 32, 128, 7])
+@pytest.mark.parametrize("itype", [np.int64, np.int32])
+def test_gather_bit_exact(ops, D, itype):
+    rng = np.random.default_rng(D)
+    V, B, F = 5000, 333, 26                       # ragged: n = 8658 is not a multiple of the chunk
+    W = O.init_table(rng, V, D)
+    idx = rng.integers(0, V, size=(B, F)).astype(itype)
+    out = ops.gather_fwd(cu(W), cu(idx)).cpu().numpy()
+    np.testing.assert_array_equal(out, O.embedding_lookup(W, idx))
+    ops.check_oob("cuda")
+
+
+def test_gather_empty_and_single(ops):
+    W = cu(O.init_table(np.random.default_rng(0), 10, 16))
+    out = ops.gather_fwd(W, torch.zeros(0, 26, dtype=torch.int64, device="cuda"))
+    assert out.shape == (0, 26, 16)
+    one = ops.gather_fwd(W, torch.tensor([[9]], device="cuda"))
+    np.testing.assert_array_equal(one.cpu().numpy()[0, 0], W.cpu().numpy()[9])
+
+
+def test_gather_out_of_range_zero_fills_and_flags(ops):
+    W = O.init_table(np.random.default_rng(0), 10, 16)
+    idx = np.array([[0, 10, -1, 3]], dtype=np.int64)
+    out = ops.gather_fwd(cu(W), cu(idx)).cpu().numpy()
+    np.testing.assert_array_equal(out[0, 1], 0)
+    np.testing.assert_array_equal(out[0, 2], 0)
+    np.testing.assert_array_equal(out[0, 3], W[3])
+    with pytest.raises(IndexError):
+        ops.check_oob("cuda")
+    with pytest.raises(IndexError):
+        O.embedding_lookup(W, idx)
+
+
+def test_gather_multi_table_offsets_and_hash(ops):
+    rng = np.random.default_rng(1)
+    T, V, D, B = 26, 100, 16, 64
+    W = O.init_table(rng, T * V, D)
+    ids = rng.integers(-2 ** 62, 2 ** 62, size=(B, T), dtype=np.int64)
+    off = np.arange(T, dtype=np.int64) * V
+    out = ops.gather_fwd(cu(W), cu(ids), L=T, field_row_offset=cu(off), hash_mod=V).cpu().numpy()
+    rows = O.id_to_row(ids, V) + off[None]
+    np.testing.assert_array_equal(out, W[rows])
+
+
+def test_hash_ids_bit_exact(ops):
+    rng = np.random.default_rng(2)
+    ids = rng.integers(-2 ** 63, 2 ** 63 - 1, size=4097, dtype=np.int64)
+    for vocab, world in ((1_000_000, 8), (39_884_406, 4), (7, 2), (1000, 1)):
+        rows, owner, local = ops.hash_ids(cu(ids), vocab, world)
+        ref = O.id_to_row(ids, vocab)
+        np.testing.assert_array_equal(rows.cpu().numpy(), ref)
+        o, l = O.shard_of_row(ref, world)
+        np.testing.assert_array_equal(owner.cpu().numpy(), o)
+        np.testing.assert_array_equal(local.cpu().numpy(), l)
+
+
+# ---- K1/K2/K11: pooled lookups --------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+@pytest.mark.parametrize("D,L", [(16, 26), (64, 26), (32, 100), (18, 5), (64, 1)])
+def test_bag_pool(ops, mode, D, L):
+    rng = np.random.default_rng(L * D)
+    V, B = 3000, 257
+    W = O.init_table(rng, V, D)
+    idx = rng.integers(0, V, size=(B, L)).astype(np.int32)
+    out, cnt = ops.bag_pool_fwd(cu(W), cu(idx), mode, want_count=True)
+    ref = O.bag_pool(W, idx, mode)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), np.full(B, L, np.float32))
+
+
+def test_masked_mean_golden_and_all_pad_is_nan(ops, golden):
+    g = golden("masked_mean")
+    D = g["W_item"].shape[1]
+    item, cat = cu(g["item"]), cu(g["cat"])
+    out = torch.empty(item.shape[0], 2 * D, device="cuda")
+    # dien/model.py:14-19: item || cat on the last axis; the item-derived mask gates both tables
+    ops.bag_pool_fwd(cu(g["W_item"]), item, "masked_mean", out=out, out_stride=2 * D)
+    ops.bag_pool_fwd(cu(g["W_cat"]), cat, "masked_mean", mask_idx=item, out=out[:, D:], out_stride=2 * D)
+    np.testing.assert_allclose(out.cpu().numpy(), g["avg"], rtol=1e-5, atol=1e-7)
+    W = cu(g["W_item"])
+    allpad = torch.zeros(3, 100, dtype=torch.int32, device="cuda")
+    res = ops.bag_pool_fwd(W, allpad, "masked_mean")
+    assert torch.isnan(res).all()                                    # dien/layers.py:16 has no guard
+
+
+def test_gather_fm_golden(ops, golden):
+    g = golden("deepfm_small")
+    E, s, fm = ops.gather_fm_fwd(cu(g["table"]), cu(g["cat"]))
+    np.testing.assert_array_equal(E.cpu().numpy(), g["E"])
+    np.testing.assert_allclose(s.cpu().numpy(), g["E"].sum(1, dtype=np.float32), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(fm.cpu().numpy(), g["fm"], rtol=2e-4, atol=2e-6)
+    ref64 = O.fm_second_order_f64(g["E"])
+    np.testing.assert_allclose(fm.cpu().numpy(), ref64, rtol=2e-4, atol=2e-6)
+
+
+# ---- K3..K6, K10: DotInteraction ----------------------------------------------------------------------
+
+BF16_REL = 2.0 ** -7      # two operands rounded to 8 significant bits, fp32 accumulate
+
+
+@pytest.mark.parametrize("si", [False, True])
+@pytest.mark.parametrize("sg", [False, True])
+def test_dot_interaction_golden_all_modes(ops, golden, si, sg):
+    g = golden("dot_interaction")
+    tag = f"si{int(si)}_sg{int(sg)}"
+    X = cu(g["X"])
+    out = ops.dot_interaction_fwd(E=X, self_interaction=si, skip_gather=sg).cpu().numpy()
+    assert out.shape == g[f"out_{tag}"].shape
+    ref_bf = O.dot_interaction(g["X"], si, sg, operand_dtype="bf16")
+    np.testing.assert_allclose(out, ref_bf, rtol=1e-5, atol=1e-5)                       # same arithmetic
+    scale = np.abs(g[f"out_{tag}"]).max()
+    assert np.abs(out - g[f"out_{tag}"]).max() <= BF16_REL * scale                      # vs the fp32 reference
+    if sg:
+        keep = O.keep_mask(27, si)
+        assert (out.reshape(-1, 27, 27)[:, ~keep] == 0).all()                           # exact zeros (ctr/layers.py:37-38)
+    dout = cu(g[f"dout_{tag}"])
+    dX, _ = ops.dot_interaction_bwd(dout, E=X, self_interaction=si, skip_gather=sg)
+    ref_dX_bf = O.dot_interaction_backward(g["X"], g[f"dout_{tag}"], si, sg, operand_dtype="bf16")
+    np.testing.assert_allclose(dX.cpu().numpy(), ref_dX_bf, rtol=1e-4, atol=1e-4)
+    scale = np.abs(g[f"dX_{tag}"]).max()
+    assert np.abs(dX.cpu().numpy() - g[f"dX_{tag}"]).max() <= 2 * BF16_REL * scale
+
+
+@pytest.mark.parametrize("name", ["dlrm_small", "dlrm_uniform"])
+def test_fused_gather_interaction_golden(ops, golden, name):
+    """ctr/model.py:49-55 in one kernel: rows straight from the table, bottom-MLP vector as feature 27,
+    mask, zero fill and the '|| bmlp' tail."""
+    g = golden(name)
+    D = g["table"].shape[1]
+    bmlp = np.ascontiguousarray(g["X"][:, 26])
+    out = ops.dot_interaction_fwd(table=cu(g["table"]), idx=cu(g["cat"]), dense_vec=cu(bmlp), tail=True).cpu().numpy()
+    assert out.shape == (g["cat"].shape[0], 729 + D)
+    ref_bf = O.dot_interaction(g["X"], False, True, operand_dtype="bf16")
+    np.testing.assert_allclose(out[:, :729], ref_bf, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(out[:, 729:], bmlp)
+    assert np.abs(out[:, :729] - g["inter"]).max() <= BF16_REL * np.abs(g["inter"]).max()
+    # un-fused path (materialised E) gives the identical bits
+    out2 = ops.dot_interaction_fwd(E=cu(np.ascontiguousarray(g["X"][:, :26])), dense_vec=cu(bmlp), tail=True).cpu().numpy()
+    np.testing.assert_array_equal(out, out2)
+    # backward: dX split into dE and d(bmlp) (+ the direct tail gradient)
+    rng = np.random.default_rng(0)
+    dtail = rng.normal(0, 1e-2, size=(out.shape[0], D)).astype(np.float32)
+    dOut = np.concatenate([g["dinter"], dtail], axis=1)
+    dE, d_dense = ops.dot_interaction_bwd(cu(dOut), table=cu(g["table"]), idx=cu(g["cat"]), dense_vec=cu(bmlp), tail=True)
+    ref = O.dot_interaction_backward(g["X"], g["dinter"], False, True, operand_dtype="bf16")
+    tol = dict(rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    np.testing.assert_allclose(dE.cpu().numpy(), ref[:, :26], **tol)
+    np.testing.assert_allclose(d_dense.cpu().numpy(), ref[:, 26] + dtail, **tol)
+    assert np.abs(dE.cpu().numpy() - g["dX"][:, :26]).max() <= 2 * BF16_REL * np.abs(g["dX"]).max()
+
+
+@pytest.mark.parametrize("D", [16, 32, 64, 128])
+@pytest.mark.parametrize("F", [1, 8, 26, 31])
+def test_dot_interaction_shapes(ops, D, F):
+    rng = np.random.default_rng(D + F)
+    B = 37                                            # not a multiple of the warps per CTA
+    E = rng.normal(0, 0.3, size=(B, F, D)).astype(np.float32)
+    dv = rng.normal(0, 0.3, size=(B, D)).astype(np.float32)
+    X = np.concatenate([E, dv[:, None]], axis=1)
+    out = ops.dot_interaction_fwd(E=cu(E), dense_vec=cu(dv), tail=True).cpu().numpy()
+    Fp = F + 1
+    ref = O.dot_interaction(X, False, True, operand_dtype="bf16")
+    np.testing.assert_allclose(out[:, :Fp * Fp], ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(out[:, Fp * Fp:], dv)
+
+
+# ---- K7..K9: backward scatter + sparse optimizers -----------------------------------------------------------
+
+def _state(kind, W):
+    if kind.startswith("adam"):
+        return dict(m=np.zeros_like(W), v=np.zeros_like(W))
+    if kind == "adagrad":
+        return dict(acc=np.full_like(W, 0.1))
+    return {}
+
+
+def _run_update(ops, W, st, idx, dE, kind, step, L=None, **hp):
+    from recommender_b200.ops import GradSource, LookupGroup
+    Wt = cu(W)
+    if kind.startswith("adam"):
+        s0, s1 = cu(st["m"]), cu(st["v"])
+    elif kind == "adagrad":
+        s0, s1 = cu(st["acc"]), None
+    else:
+        s0 = s1 = None
+    L = L or idx.shape[-1]
+    ops.sparse_bwd_update(Wt, s0, s1, [LookupGroup(cu(idx), L, GradSource.per_position(cu(dE), L))], optimizer=kind,
+                          step=step, **hp)
+    res = dict(W=Wt.cpu().numpy())
+    if kind.startswith("adam"):
+        res.update(m=s0.cpu().numpy(), v=s1.cpu().numpy())
+    elif kind == "adagrad":
+        res.update(acc=s0.cpu().numpy())
+    return res
+
+
+@pytest.mark.parametrize("kind", ["adam_lazy", "adam_tf_dense", "adagrad", "sgd"])
+@pytest.mark.parametrize("D", [16, 64])
+def test_sparse_update_unique_rows_bit_exact(ops, kind, D):
+    """No duplicate rows -> no summation-order freedom: every updated element must match numpy's
+    correctly-rounded fp32 arithmetic bit for bit (the kernel uses explicit _rn ops, no FMA)."""
+    rng = np.random.default_rng(D)
+    V, B, F = 4000, 100, 26
+    W = O.init_table(rng, V, D)
+    idx = rng.permutation(V)[: B * F].reshape(B, F).astype(np.int64)
+    st = _state(kind, W)
+    hp = dict(lr=1e-2) if kind == "sgd" else {}
+    for step in (1, 2):
+        dE = rng.normal(0, 1e-3, size=(B, F, D)).astype(np.float32)
+        got = _run_update(ops, W, st, idx, dE, kind, step, **hp)
+        O.sparse_backward_update(W, st, idx, dE, kind, step, **hp)
+        np.testing.assert_array_equal(got["W"], W)
+        for k in st:
+            np.testing.assert_array_equal(got[k], st[k])
+
+
+@pytest.mark.parametrize("kind", ["adam_lazy", "adagrad"])
+@pytest.mark.parametrize("dist", ["uniform", "zipf"])
+def test_sparse_update_with_duplicates(ops, kind, dist):
+    """Duplicate rows (incl. the OOV -> 0 hot row): the sums associate per 32-entry tile instead of
+    strictly left to right, so allow fp32 re-association error on the summed gradient."""
+    V, B, D = 2000, 512, 16
+    cat, _, _ = O.synth_batch(B, V, seed=4, dist=dist)
+    rng = np.random.default_rng(5)
+    W = O.init_table(rng, V, D)
+    st = _state(kind, W)
+    for step in (1, 2, 3):
+        dE = rng.normal(0, 1e-3, size=(B, 26, D)).astype(np.float32)
+        got = _run_update(ops, W, st, cat, dE, kind, step)
+        O.sparse_backward_update(W, st, cat, dE, kind, step)
+        np.testing.assert_allclose(got["W"], W, rtol=0, atol=2e-6)          # |update| <= ~lr = 1e-3
+        for k in st:
+            np.testing.assert_allclose(got[k], st[k], rtol=2e-4, atol=1e-9)
+        W, st = got["W"], {k: got[k] for k in st}                            # continue from the CUDA state
+
+
+def test_sparse_update_is_deterministic(ops):
+    V, B, D = 500, 2048, 64
+    cat, _, _ = O.synth_batch(B, V, seed=9, dist="zipf")
+    rng = np.random.default_rng(1)
+    W = O.init_table(rng, V, D)
+    dE = rng.normal(0, 1e-3, size=(B, 26, D)).astype(np.float32)
+    st = _state("adam_lazy", W)
+    a = _run_update(ops, W, st, cat, dE, "adam_lazy", 1)
+    b = _run_update(ops, W, st, cat, dE, "adam_lazy", 1)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_dedup_matches_oracle(ops):
+    from recommender_b200.ops import GradSource
+    V, B, D = 300, 700, 32
+    cat, _, _ = O.synth_batch(B, V, seed=3, dist="zipf")
+    rng = np.random.default_rng(2)
+    dE = rng.normal(0, 1.0, size=(B, 26, D)).astype(np.float32)
+    rows, summed = ops.sparse_bwd_dedup(V, D, cu(cat), 26, GradSource.per_position(cu(dE), 26))
+    rows, summed = rows.cpu().numpy(), summed.cpu().numpy()
+    ref_rows, ref_sum = O.dedup_indexed_slices(*O.gather_backward(cat, dE))
+    order = np.argsort(ref_rows)                     # the CUDA path emits rows ascending, TF first-occurrence
+    np.testing.assert_array_equal(rows, ref_rows[order])
+    _, ref64 = O.dedup_indexed_slices_f64(*O.gather_backward(cat, dE))
+    counts = np.bincount(cat.reshape(-1), minlength=V)[rows]
+    tol = 1e-6 * np.sqrt(counts)[:, None] * 4 + 1e-6
+    assert (np.abs(summed - ref64) <= tol * np.maximum(1.0, np.abs(ref64))).all()
+    np.testing.assert_allclose(summed, ref_sum[order], rtol=1e-3, atol=2e-5)
+
+
+def test_hot_row_long_chain(ops):
+    """One row receiving > 64 tiles of gradients (ESMM's 3-row tables, OOV id 0) takes the CTA-wide path."""
+    from recommender_b200.ops import GradSource
+    V, D, n = 3, 32, 40000
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, V, size=(n, 1)).astype(np.int32)
+    dE = rng.normal(0, 1.0, size=(n, 1, D)).astype(np.float32)
+    rows, summed = ops.sparse_bwd_dedup(V, D, cu(idx), 1, GradSource.per_position(cu(dE), 1))
+    _, ref64 = O.dedup_indexed_slices_f64(*O.gather_backward(idx, dE))
+    assert rows.cpu().numpy().tolist() == [0, 1, 2]
+    np.testing.assert_allclose(summed.cpu().numpy(), ref64, rtol=1e-4, atol=2e-3)
+
+
+def test_masked_mean_backward_golden(ops, golden):
+    """config 4: bag-level gradient + mask + count -> table gradient, never materialising [B,L,D]."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    g = golden("masked_mean")
+    D = g["W_item"].shape[1]
+    item, cat = cu(g["item"]), cu(g["cat"])
+    davg = cu(g["davg"])
+    _, count = ops.bag_pool_fwd(cu(g["W_item"]), item, "masked_mean", want_count=True)
+    for W, idx, col, key in ((g["W_item"], item, 0, "dW_item"), (g["W_cat"], cat, D, "dW_cat")):
+        Wt = cu(W)
+        src = GradSource([davg[:, col:]], [davg.stride(0)], [0], scale="masked_mean", mask_idx=item, count=count)
+        ops.sparse_bwd_update(Wt, None, None, [LookupGroup(idx, 100, src)], optimizer="sgd", lr=1.0)
+        np.testing.assert_allclose(W - Wt.cpu().numpy(), g[key], rtol=1e-4, atol=1e-8)
+
+
+def test_multi_consumer_and_multi_table_golden(ops, golden):
+    """config 5: one table per feature, bag size 1, the consumers' gradients added left to right
+    inside the scatter (esmm/esmm.py:15-24)."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    g = golden("esmm_small")
+    feats = [str(f) for f in g["feats"]]
+    D = g[f"W_{feats[0]}"].shape[1]
+    B = g[f"idx_{feats[0]}"].shape[0]
+    width = D * len(feats)
+    out = torch.empty(B, width, device="cuda")
+    for k, f in enumerate(feats):                                  # concat on the last axis, written in place
+        ops.gather_fwd(cu(g[f"W_{f}"]), cu(g[f"idx_{f}"][:, 0]), out=out[:, k * D:], out_stride=width)
+    np.testing.assert_array_equal(out.cpu().numpy(), g["emb"])
+    rng = np.random.default_rng(8)
+    consumers = [rng.normal(0, 1e-2, size=(B, width)).astype(np.float32) for _ in range(10)]    # MMOE: 10 consumers
+    total = O.multi_consumer_grad(consumers)
+    cons_t = [cu(c) for c in consumers]
+    for k, f in enumerate(feats):
+        W = g[f"W_{f}"]
+        Wt = cu(W)
+        src = GradSource([c[:, k * D:] for c in cons_t], [width] * 10, [0] * 10)
+        ops.sparse_bwd_update(Wt, None, None, [LookupGroup(cu(g[f"idx_{f}"]), 1, src)], optimizer="sgd", lr=1.0)
+        ref = W.copy()
+        O.sparse_backward_update(ref, {}, g[f"idx_{f}"], total[:, None, k * D:(k + 1) * D], "sgd", lr=1.0)
+        np.testing.assert_allclose(Wt.cpu().numpy(), ref, rtol=0, atol=1e-6)
+
+
+def test_two_uses_of_one_table_are_concatenated(ops):
+    """dien/model.py:26-30: item_embedding serves the target item and the history; TF concatenates
+    the two IndexedSlices before the duplicate-row sum, so Adam sees ONE summed gradient per row."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    rng = np.random.default_rng(10)
+    V, D, B, L = 50, 32, 64, 10
+    W = O.init_table(rng, V, D)
+    tgt = rng.integers(1, V, size=(B, 1)).astype(np.int32)
+    his = rng.integers(0, V, size=(B, L)).astype(np.int32)
+    d_tgt = rng.normal(0, 1e-3, size=(B, 1, D)).astype(np.float32)
+    d_avg = rng.normal(0, 1e-3, size=(B, D)).astype(np.float32)
+    mask = his != 0
+    st = _state("adam_lazy", W)
+    Wt, m, v = cu(W), cu(st["m"]), cu(st["v"])
+    _, count = ops.bag_pool_fwd(Wt, cu(his), "masked_mean", want_count=True)
+    groups = [LookupGroup(cu(tgt), 1, GradSource.per_position(cu(d_tgt), 1)),
+              LookupGroup(cu(his), L, GradSource.per_bag([cu(d_avg)], scale="masked_mean", mask_idx=cu(his), count=count))]
+    ops.sparse_bwd_update(Wt, m, v, groups, optimizer="adam_lazy", step=1)
+    d_his = O.masked_mean_backward(d_avg, mask)
+    ind, val = O.concat_indexed_slices([O.gather_backward(tgt, d_tgt), O.gather_backward(his, d_his)])
+    rows, gsum = O.dedup_indexed_slices(ind, val)
+    O.adam_lazy(W, st["m"], st["v"], rows, gsum, 1)
+    np.testing.assert_allclose(Wt.cpu().numpy(), W, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(v.cpu().numpy(), st["v"], rtol=1e-3, atol=1e-12)
+
+
+def test_bucket_by_owner(ops):
+    rng = np.random.default_rng(11)
+    n, V = 10007, 1000
+    ids = rng.integers(0, V, size=n).astype(np.int64)
+    for world in (1, 2, 4, 8, 3):
+        local, perm, inv, counts = ops.bucket_by_owner(cu(ids), world)
+        local, perm, inv, counts = (t.cpu().numpy() for t in (local, perm, inv, counts))
+        owner, loc = O.shard_of_row(ids, world)
+        ref_perm = np.argsort(owner, kind="stable")
+        np.testing.assert_array_equal(perm, ref_perm)
+        np.testing.assert_array_equal(local, loc[ref_perm])
+        np.testing.assert_array_equal(inv[perm], np.arange(n))
+        np.testing.assert_array_equal(counts, np.bincount(owner, minlength=world))

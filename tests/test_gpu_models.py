@@ -1,0 +1,267 @@
+"""DeepFM / DLRM with the reference's call surface on the CUDA path, against the fixtures frozen
+from the reference's own ctr/model.py (tests/golden) and against multi-step oracle training;
+plus size-independent properties at BASELINE config 2's full size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL = 2.0 ** -7
+
+
+def cu(a):
+    return torch.as_tensor(a).cuda()
+
+
+def _mlp(g, name):
+    layers, i = [], 0
+    while f"{name}_W{i}" in g:
+        layers.append((g[f"{name}_W{i}"], g[f"{name}_b{i}"]))
+        i += 1
+    return layers
+
+
+def _build_dlrm(g, fused=True, num_tables=1, V=None):
+    from recommender_b200.model import DLRM
+    bottom, top = _mlp(g, "bottom"), _mlp(g, "top")
+    D = g["table"].shape[1]
+    V = V or g["table"].shape[0]
+    model = DLRM([W.shape[1] for W, _ in bottom], [W.shape[1] for W, _ in top], D, V, 26, 13, fused=fused,
+                 num_tables=num_tables, device="cuda")
+    model.embedding_layer.embeddings.copy_(cu(g["table"]))
+    model.bottom_mlp.load_arrays(bottom, "cuda")
+    model.top_mlp.load_arrays(top, "cuda")
+    return model
+
+
+@pytest.mark.parametrize("name", ["dlrm_small", "dlrm_uniform"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_dlrm_against_reference_fixture(cuda_lib, golden, name, fused):
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden(name)
+    model = _build_dlrm(g, fused)
+    x = {"cat_features": cu(g["cat"]), "int_features": cu(g["dense"])}
+    prob = model(x)
+    assert prob.shape == (g["cat"].shape[0],)
+    np.testing.assert_allclose(prob.detach().cpu().numpy(), g["prob"], rtol=0, atol=2e-3)     # bf16 operands in the dot
+    params = dict(table=g["table"].copy(), bottom=_mlp(g, "bottom"), top=_mlp(g, "top"))
+    ref_prob, cache = O.dlrm_forward(params, g["cat"], g["dense"], operand_dtype="bf16")
+    np.testing.assert_allclose(prob.detach().cpu().numpy(), ref_prob, rtol=1e-4, atol=1e-6)   # same arithmetic
+    loss = bce_clipped(prob, cu(g["label"]))
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=2e-3)
+    loss.backward()
+    for i, W in enumerate(model.top_mlp.kernels):
+        ref = g[f"top_dW{i}"]
+        assert np.abs(W.grad.cpu().numpy() - ref).max() <= 4 * BF16_REL * np.abs(ref).max() + 1e-7
+    for i, W in enumerate(model.bottom_mlp.kernels):
+        ref = g[f"bottom_dW{i}"]
+        assert np.abs(W.grad.cpu().numpy() - ref).max() <= 4 * BF16_REL * np.abs(ref).max() + 1e-7
+    # sparse side: one recorded lookup group; Adam step 1 against the oracle chain
+    emb = model.embedding_layer
+    assert len(emb.pending) == 1 and emb.pending[0].n == g["cat"].size
+    _, dprob = O.bce_clipped(ref_prob, g["label"])
+    grads = O.dlrm_backward(params, cache, dprob, operand_dtype="bf16")
+    st = dict(m=np.zeros_like(g["table"]), v=np.zeros_like(g["table"]))
+    table_ref = g["table"].copy()
+    O.sparse_backward_update(table_ref, st, g["cat"], grads["dE"], "adam_lazy", 1)
+    Adam().apply_gradients(model)
+    assert emb.pending == []
+    got = emb.embeddings.cpu().numpy()
+    touched = np.unique(g["cat"])
+    untouched = np.setdiff1d(np.arange(g["table"].shape[0]), touched)
+    np.testing.assert_array_equal(got[untouched], g["table"][untouched])                      # lazy: untouched rows stay
+    # Adam's first step is ~ lr * sign(g): compare where the gradient is well above epsilon-scale noise
+    np.testing.assert_allclose(emb.opt_state["m"].cpu().numpy(), st["m"], rtol=5e-3, atol=1e-9)
+    big = np.abs(st["m"]) > 1e-7
+    np.testing.assert_allclose(got[big], table_ref[big], rtol=0, atol=2e-5)
+
+
+def test_deepfm_against_reference_fixture(cuda_lib, golden):
+    from recommender_b200.model import DeepFM, bce_logits
+    from recommender_b200.optimizers import Adam
+    g = golden("deepfm_small")
+    mlp = _mlp(g, "mlp")
+    D, V = g["table"].shape[1], g["table"].shape[0]
+    for fused in (True, False):
+        model = DeepFM(D, V, 13, 26, [W.shape[1] for W, _ in mlp], fused=fused, device="cuda")
+        model.embedding_layer.embeddings.copy_(cu(g["table"]))
+        model.mlp.load_arrays(mlp, "cuda")
+        x = {"cat_features": cu(g["cat"]), "int_features": cu(g["dense"])}
+        prob = model(x)
+        np.testing.assert_allclose(prob.detach().cpu().numpy(), g["prob"], rtol=2e-5, atol=2e-6)   # all fp32
+        loss = bce_logits(model.logits(x), cu(g["label"]))
+        model.embedding_layer.pending.clear()
+        np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+        loss.backward()
+        for i, W in enumerate(model.mlp.kernels):
+            np.testing.assert_allclose(W.grad.cpu().numpy(), g[f"mlp_dW{i}"], rtol=1e-3, atol=1e-6)
+        # table gradient = sum of the three consumers of cat_embedding (ctr/model.py:21,22,25):
+        # apply it with SGD(lr=1) so that table_before - table_after IS the dense table gradient
+        from recommender_b200.optimizers import SGD
+        SGD(1.0).apply_gradients([model.embedding_layer])
+        dtable = g["table"] - model.embedding_layer.embeddings.cpu().numpy()
+        np.testing.assert_allclose(dtable, g["dtable"], rtol=1e-3, atol=2e-8)
+
+
+def test_dlrm_multi_step_training_tracks_the_oracle(cuda_lib, golden):
+    """5 Adam steps on fresh batches: probabilities, loss and the table stay within tolerance of the
+    oracle's DLRM (bf16-operand dot, lazy Adam on the table, Keras Adam on the MLPs)."""
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden("dlrm_uniform")
+    D, V = g["table"].shape[1], g["table"].shape[0]
+    model = _build_dlrm(g)
+    opt = Adam()
+    params = dict(table=g["table"].copy(), bottom=[(W.copy(), b.copy()) for W, b in _mlp(g, "bottom")],
+                  top=[(W.copy(), b.copy()) for W, b in _mlp(g, "top")])
+    st = dict(m=np.zeros_like(params["table"]), v=np.zeros_like(params["table"]))
+    dense_state = {}
+    for step in range(1, 6):
+        cat, dense_x, label = O.synth_batch(128, V, seed=100 + step, dist="zipf")
+        prob = model({"cat_features": cu(cat), "int_features": cu(dense_x)})
+        loss = bce_clipped(prob, cu(label))
+        loss.backward()
+        opt.apply_gradients(model)
+        ref_prob, cache = O.dlrm_forward(params, cat, dense_x, operand_dtype="bf16")
+        ref_loss, dprob = O.bce_clipped(ref_prob, label)
+        grads = O.dlrm_backward(params, cache, dprob, operand_dtype="bf16")
+        O.sparse_backward_update(params["table"], st, cat, grads["dE"], "adam_lazy", step)
+        for name in ("bottom", "top"):
+            for i, ((W, b), (dW, db)) in enumerate(zip(params[name], grads[name])):
+                for tag, p, gr in (("W", W, dW), ("b", b, db)):
+                    m, v = dense_state.setdefault((name, i, tag), (np.zeros_like(p), np.zeros_like(p)))
+                    O.adam_dense_param(p, m, v, gr, step)
+        np.testing.assert_allclose(prob.detach().cpu().numpy(), ref_prob, rtol=0, atol=5e-4 * step)
+        assert abs(loss.item() - float(ref_loss)) <= 5e-4 * step
+    got = model.embedding_layer.embeddings.cpu().numpy()
+    moved = np.abs(params["table"] - g["table"]).max()
+    assert moved > 1e-3                                                       # training did move rows
+    assert np.abs(got - params["table"]).mean() <= 0.02 * moved               # and the two tables agree
+
+
+def test_esmm_style_multi_table_embedding(cuda_lib, golden):
+    """config 5 through the layer classes: one Embedding per feature, bag size 1, concat on the
+    last axis (esmm/esmm.py:15-19), two consumers."""
+    from recommender_b200.layers import Embedding
+    from recommender_b200.optimizers import SGD
+    g = golden("esmm_small")
+    feats = [str(f) for f in g["feats"]]
+    embs = {}
+    for f in feats:
+        W = g[f"W_{f}"]
+        embs[f] = Embedding(W.shape[0], W.shape[1], device="cuda")
+        embs[f].embeddings.copy_(cu(W))
+    inputs = {f: cu(g[f"idx_{f}"]) for f in feats}
+    embedding = torch.cat([embs[f](inputs[f]) for f in feats], dim=-1).squeeze(1)        # esmm/esmm.py:16-18
+    np.testing.assert_array_equal(embedding.detach().cpu().numpy(), g["emb"])
+    rng = np.random.default_rng(3)
+    w1, w2 = (cu(rng.normal(size=g["emb"].shape).astype(np.float32)) for _ in range(2))
+    ((embedding * w1).sum() + (embedding * w2).sum()).backward()                          # ctr and cvr towers
+    SGD(1.0).apply_gradients(list(embs.values()))
+    total = (w1 + w2).cpu().numpy()
+    D = g[f"W_{feats[0]}"].shape[1]
+    for k, f in enumerate(feats):
+        ref = g[f"W_{f}"].copy()
+        O.sparse_backward_update(ref, {}, g[f"idx_{f}"], total[:, None, k * D:(k + 1) * D], "sgd", lr=1.0)
+        np.testing.assert_allclose(embs[f].embeddings.cpu().numpy(), ref, rtol=0, atol=1e-5)
+
+
+def test_dien_style_masked_history(cuda_lib, golden):
+    """config 4 through the layer classes (dien/model.py:14-19,25-31)."""
+    from recommender_b200.layers import Embedding, compute_his_average
+    from recommender_b200.optimizers import SGD
+    g = golden("masked_mean")
+    D = g["W_item"].shape[1]
+    item_emb = Embedding(g["W_item"].shape[0], D, mask_zero=True, device="cuda")
+    cat_emb = Embedding(g["W_cat"].shape[0], D, mask_zero=True, device="cuda")
+    item_emb.embeddings.copy_(cu(g["W_item"]))
+    cat_emb.embeddings.copy_(cu(g["W_cat"]))
+    item, cat = cu(g["item"]), cu(g["cat"])
+    assert torch.equal(item_emb.compute_mask(item), item != 0)
+    avg = torch.cat([compute_his_average(item_emb, item), compute_his_average(cat_emb, cat, mask_idx=item)], dim=-1)
+    np.testing.assert_allclose(avg.detach().cpu().numpy(), g["avg"], rtol=1e-5, atol=1e-7)
+    avg.backward(cu(g["davg"]))
+    SGD(1.0).apply_gradients([item_emb, cat_emb])
+    np.testing.assert_allclose(g["W_item"] - item_emb.embeddings.cpu().numpy(), g["dW_item"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(g["W_cat"] - cat_emb.embeddings.cpu().numpy(), g["dW_cat"], rtol=1e-4, atol=1e-8)
+
+
+# ---- BASELINE config 2 at full size: properties that need no oracle run -------------------------------------
+
+FULL_B, FULL_D, FULL_V, FULL_T = 65536, 64, 1_000_000, 26
+
+
+@pytest.fixture(scope="module")
+def full(cuda_lib):
+    torch.manual_seed(4)
+    W = torch.empty(FULL_V * FULL_T, FULL_D, device="cuda").uniform_(-0.05, 0.05)
+    idx = torch.randint(0, FULL_V, (FULL_B, FULL_T), device="cuda", dtype=torch.int64)
+    idx[torch.rand(FULL_B, FULL_T, device="cuda") < 0.02] = 0                  # OOV -> 0 hot rows per table
+    off = torch.arange(FULL_T, device="cuda", dtype=torch.int64) * FULL_V
+    return W, idx, off
+
+
+def test_full_size_gather_bit_exact(full):
+    from recommender_b200 import ops
+    W, idx, off = full
+    out = ops.gather_fwd(W, idx, L=FULL_T, field_row_offset=off)
+    ref = W[(idx + off[None]).reshape(-1)].reshape(FULL_B, FULL_T, FULL_D)
+    assert torch.equal(out.view(torch.int32), ref.view(torch.int32))
+
+
+def test_full_size_interaction_properties(full):
+    from recommender_b200 import ops
+    W, idx, off = full
+    dv = torch.randn(FULL_B, FULL_D, device="cuda") * 0.1
+    out = ops.dot_interaction_fwd(table=W, idx=idx, field_row_offset=off, dense_vec=dv, tail=True)
+    E = ops.gather_fwd(W, idx, L=FULL_T, field_row_offset=off)
+    out2 = ops.dot_interaction_fwd(E=E, dense_vec=dv, tail=True)
+    assert torch.equal(out, out2)                                              # fused gather == materialised E
+    Z = out[:, :729].reshape(FULL_B, 27, 27)
+    assert (torch.tril(Z) == 0).all()                                          # strict upper triangle kept
+    # power-of-two scaling is exact in bf16 and fp32: Z(2X) == 4 Z(X) bit for bit
+    out4 = ops.dot_interaction_fwd(E=E * 2.0, dense_vec=dv * 2.0, tail=False)
+    assert torch.equal(out4, out[:, :729] * 4.0)
+    # against fp32 cuBLAS on a slice
+    X = torch.cat([E[:4096], dv[:4096, None]], dim=1)
+    ref = torch.triu(torch.bmm(X, X.transpose(1, 2)), diagonal=1)
+    assert (Z[:4096] - ref).abs().max() <= BF16_REL * ref.abs().max()
+
+
+def test_full_size_scatter_counts_and_determinism(full):
+    from recommender_b200 import ops
+    from recommender_b200.ops import GradSource, LookupGroup
+    W, idx, off = full
+    rows = (idx + off[None]).reshape(-1)
+    # SGD(lr=1) with an all-ones gradient subtracts each row's multiplicity: exact integer sums
+    Wc = W.clone()
+    ones = torch.ones(FULL_B, FULL_T, FULL_D, device="cuda")
+    grp = [LookupGroup(idx, FULL_T, GradSource.per_position(ones, FULL_T), field_row_offset=off)]
+    ops.sparse_bwd_update(Wc, None, None, grp, optimizer="sgd", lr=1.0)
+    counts = torch.bincount(rows, minlength=W.shape[0]).to(torch.float32)
+    assert torch.equal(Wc, W - counts[:, None])
+    del Wc, ones
+    # Adam twice from the same state: bit-identical tables (no atomics anywhere)
+    dE = torch.randn(FULL_B, FULL_T, FULL_D, device="cuda") * 1e-3
+    res = []
+    for _ in range(2):
+        Wa, m, v = W.clone(), torch.zeros_like(W), torch.zeros_like(W)
+        ops.sparse_bwd_update(Wa, m, v, [LookupGroup(idx, FULL_T, GradSource.per_position(dE, FULL_T), field_row_offset=off)],
+                              optimizer="adam_lazy", step=1)
+        res.append((Wa, m, v))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    # gradient conservation: sum over rows of m / (1 - beta_1) == sum over lookups of dE (fp64)
+    m = res[0][1]
+    lhs = m.double().sum(0) / (1.0 - np.float32(0.9))
+    rhs = dE.double().sum((0, 1))
+    assert (lhs - rhs).abs().max() <= 1e-4 * dE.double().abs().sum((0, 1)).max()
+    # untouched rows did not move
+    touched = torch.zeros(W.shape[0], dtype=torch.bool, device="cuda")
+    touched[rows] = True
+    assert torch.equal(res[0][0][~touched], W[~touched])
+    ops.check_oob("cuda")

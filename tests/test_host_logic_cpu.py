@@ -1,0 +1,97 @@
+"""Host-side Python logic that needs no GPU: the dense (MLP) mirror, the Keras-form dense
+optimizers, loss forms and shape helpers — each against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+from recommender_b200 import ops
+from recommender_b200.layers import MLP
+from recommender_b200.model import bce_clipped, bce_logits
+from recommender_b200.optimizers import Adagrad, Adam, SGD
+
+
+def test_interaction_ncols():
+    assert ops.interaction_ncols(27, False, True) == 729
+    assert ops.interaction_ncols(27, True, True) == 729
+    assert ops.interaction_ncols(27, False, False) == 351
+    assert ops.interaction_ncols(27, True, False) == 378
+
+
+@pytest.mark.parametrize("act", [None, "relu", "sigmoid"])
+def test_mlp_matches_oracle_hidden_layers_are_linear(act):
+    rng = np.random.default_rng(0)
+    layers = O.init_mlp(rng, 13, [32, 16, 4])
+    x = rng.normal(size=(9, 13)).astype(np.float32)
+    mlp = MLP([32, 16, 4], act)
+    mlp.load_arrays(layers, "cpu")
+    y = mlp(torch.tensor(x)).detach().numpy()
+    ref, _ = O.mlp_forward(x, layers, act)
+    np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_mlp_lazy_build_uses_glorot_uniform():
+    g = torch.Generator().manual_seed(0)
+    mlp = MLP([64, 8], "relu", generator=g)
+    mlp(torch.zeros(2, 20))
+    lim = np.sqrt(6.0 / (20 + 64))
+    W = mlp.kernels[0].detach()
+    assert W.shape == (20, 64) and float(W.abs().max()) <= lim and float(W.abs().max()) > 0.8 * lim
+    assert float(mlp.biases[0].abs().max()) == 0.0
+
+
+def test_dense_adam_is_the_keras_formula(cuda_lib):
+    rng = np.random.default_rng(1)
+    p0 = rng.normal(size=(6, 5)).astype(np.float32)
+    p = torch.nn.Parameter(torch.tensor(p0.copy()))
+    ref, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    opt = Adam()
+    for step in range(1, 4):
+        g = rng.normal(size=p0.shape).astype(np.float32)
+        p.grad = torch.tensor(g)
+        opt.apply_gradients([p])
+        O.adam_dense_param(ref, m, v, g, step)
+        np.testing.assert_allclose(p.detach().numpy(), ref, rtol=2e-6, atol=1e-7)
+    assert opt.iterations == 3 and p.grad is None
+
+
+def test_dense_adagrad_and_sgd(cuda_lib):
+    p0 = np.ones((3, 2), np.float32)
+    g = np.full((3, 2), 0.5, np.float32)
+    p = torch.nn.Parameter(torch.tensor(p0.copy()))
+    p.grad = torch.tensor(g)
+    Adagrad().apply_gradients([p])
+    acc = 0.1 + g * g
+    np.testing.assert_allclose(p.detach().numpy(), p0 - 1e-3 * g / (np.sqrt(acc) + 1e-7), rtol=1e-6)
+    q = torch.nn.Parameter(torch.tensor(p0.copy()))
+    q.grad = torch.tensor(g)
+    SGD(0.1).apply_gradients([q])
+    np.testing.assert_allclose(q.detach().numpy(), p0 - 0.1 * g, rtol=1e-6)
+
+
+def test_loss_forms_match_oracle():
+    rng = np.random.default_rng(2)
+    prob = rng.uniform(0, 1, size=64).astype(np.float32)
+    prob[:2] = [0.0, 1.0]
+    y = (rng.random(64) < 0.3).astype(np.int64)
+    ref, dref = O.bce_clipped(prob, y)
+    pt = torch.tensor(prob, requires_grad=True)
+    loss = bce_clipped(pt, torch.tensor(y))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref, rtol=1e-5)
+    np.testing.assert_allclose(pt.grad.numpy(), dref, rtol=1e-4, atol=1e-7)
+    logit = rng.normal(0, 3, size=64).astype(np.float32)
+    ref, dref = O.bce_logits(logit, y)
+    lt = torch.tensor(logit, requires_grad=True)
+    loss = bce_logits(lt, torch.tensor(y))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref, rtol=1e-5)
+    np.testing.assert_allclose(lt.grad.numpy(), dref, rtol=1e-4, atol=1e-7)
+
+
+def test_embedding_needs_cuda():
+    from recommender_b200.layers import Embedding
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Embedding(10, 4)

@@ -1,0 +1,188 @@
+"""The numpy oracle against the fixtures frozen from the reference's own Python files
+(tests/golden/make_golden.py: ctr/model.py, ctr/layers.py, dien/layers.py, dien/model.py and
+esmm/esmm.py imported byte-for-byte under the tensorflow shim).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ctr_oracle as O
+
+RTOL, ATOL = 2e-5, 2e-6   # fp32 oracle vs fp32 torch-CPU replay of the reference graph
+
+
+def _mlp(g, name):
+    layers, i = [], 0
+    while f"{name}_W{i}" in g:
+        layers.append((g[f"{name}_W{i}"], g[f"{name}_b{i}"]))
+        i += 1
+    return layers
+
+
+@pytest.mark.parametrize("name", ["dlrm_small", "dlrm_uniform"])
+def test_dlrm_forward_backward(golden, name):
+    g = golden(name)
+    params = dict(table=g["table"], bottom=_mlp(g, "bottom"), top=_mlp(g, "top"))
+    prob, cache = O.dlrm_forward(params, g["cat"], g["dense"])
+    np.testing.assert_allclose(prob, g["prob"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(cache["X"], g["X"], rtol=0, atol=0)           # gather + concat: bit-exact
+    np.testing.assert_allclose(cache["inter"], g["inter"], rtol=RTOL, atol=ATOL)
+    loss, dprob = O.bce_clipped(prob, g["label"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-5)
+    grads = O.dlrm_backward(params, cache, dprob)
+    np.testing.assert_allclose(grads["dE"], g["dX"][:, :26], rtol=1e-4, atol=1e-7)
+    for i, (dW, db) in enumerate(grads["top"]):
+        np.testing.assert_allclose(dW, g[f"top_dW{i}"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(db, g[f"top_db{i}"], rtol=1e-3, atol=1e-6)
+    for i, (dW, db) in enumerate(grads["bottom"]):
+        np.testing.assert_allclose(dW, g[f"bottom_dW{i}"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(db, g[f"bottom_db{i}"], rtol=1e-3, atol=1e-6)
+    # dense table gradient == scatter-add of the IndexedSlices (A.1/A.2)
+    rows, summed = O.dedup_indexed_slices(*O.gather_backward(g["cat"], grads["dE"]))
+    dtable = np.zeros_like(g["table"])
+    dtable[rows] = summed
+    np.testing.assert_allclose(dtable, g["dtable"], rtol=1e-4, atol=1e-7)
+
+
+def test_dot_interaction_operand_rounding_is_small(golden):
+    g = golden("dlrm_small")
+    a = O.dot_interaction(g["X"])
+    b = O.dot_interaction(g["X"], operand_dtype="bf16")
+    np.testing.assert_allclose(a, g["inter"], rtol=RTOL, atol=ATOL)
+    scale = np.abs(a).max()
+    assert np.abs(a - b).max() <= 2.0 ** -7 * scale      # two bf16-rounded operands, fp32 accumulate
+
+
+def test_deepfm_forward_backward(golden):
+    g = golden("deepfm_small")
+    params = dict(table=g["table"], mlp=_mlp(g, "mlp"))
+    prob, cache = O.deepfm_forward(params, g["cat"], g["dense"])
+    np.testing.assert_allclose(prob, g["prob"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_array_equal(cache["E"], g["E"])
+    np.testing.assert_allclose(cache["fm"], g["fm"], rtol=1e-4, atol=1e-6)
+    loss, dlogit = O.bce_logits(cache["logit"], g["label"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-5)
+    grads = O.deepfm_backward(params, cache, dlogit)
+    np.testing.assert_allclose(grads["dE"], g["dE"], rtol=1e-4, atol=1e-7)
+    for i, (dW, db) in enumerate(grads["mlp"]):
+        np.testing.assert_allclose(dW, g[f"mlp_dW{i}"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(db, g[f"mlp_db{i}"], rtol=1e-3, atol=1e-6)
+    rows, summed = O.dedup_indexed_slices(*O.gather_backward(g["cat"], grads["dE"]))
+    dtable = np.zeros_like(g["table"])
+    dtable[rows] = summed
+    np.testing.assert_allclose(dtable, g["dtable"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("si", [False, True])
+@pytest.mark.parametrize("sg", [False, True])
+def test_dot_interaction_all_modes(golden, si, sg):
+    g = golden("dot_interaction")
+    tag = f"si{int(si)}_sg{int(sg)}"
+    out = O.dot_interaction(g["X"], si, sg)
+    assert out.shape == g[f"out_{tag}"].shape
+    np.testing.assert_allclose(out, g[f"out_{tag}"], rtol=RTOL, atol=ATOL)
+    dX = O.dot_interaction_backward(g["X"], g[f"dout_{tag}"], si, sg)
+    np.testing.assert_allclose(dX, g[f"dX_{tag}"], rtol=1e-4, atol=1e-5)
+
+
+def test_masked_mean(golden):
+    g = golden("masked_mean")
+    avg = O.masked_mean_lookup(g["W_item"], g["W_cat"], g["item"], g["cat"])
+    np.testing.assert_allclose(avg, g["avg"], rtol=RTOL, atol=ATOL)
+    mask = g["item"] != 0
+    dhis = O.masked_mean_backward(g["davg"], mask)
+    np.testing.assert_allclose(dhis, g["dhis"], rtol=1e-5, atol=1e-9)
+    D = g["W_item"].shape[1]
+    for W, idx, d, key in ((g["W_item"], g["item"], dhis[..., :D], "dW_item"), (g["W_cat"], g["cat"], dhis[..., D:], "dW_cat")):
+        rows, summed = O.dedup_indexed_slices(*O.gather_backward(idx, np.ascontiguousarray(d)))
+        dW = np.zeros_like(W)
+        dW[rows] = summed
+        np.testing.assert_allclose(dW, g[key], rtol=1e-4, atol=1e-8)
+
+
+def test_esmm_multi_table(golden):
+    g = golden("esmm_small")
+    feats = [str(f) for f in g["feats"]]
+    tables = {f: g[f"W_{f}"] for f in feats}
+    inputs = {f: g[f"idx_{f}"] for f in feats}
+    emb = O.compute_embedding_multi(tables, inputs)
+    np.testing.assert_array_equal(emb, g["emb"])
+
+
+# ---- self-checks of the restated TF-internal semantics --------------------
+
+def test_fm_identity_and_finite_difference():
+    rng = np.random.default_rng(0)
+    E = rng.normal(0, 0.3, size=(5, 7, 4))
+    fm = O.fm_second_order_f64(E)
+    pair = sum((E[:, i] * E[:, j]).sum(1) for i in range(7) for j in range(i + 1, 7))
+    np.testing.assert_allclose(fm, pair, rtol=1e-12)
+    g = rng.normal(size=5)
+    dE = O.fm_backward(E.astype(np.float32), g.astype(np.float32))
+    eps = 1e-6
+    for (b, f, d) in [(0, 0, 0), (2, 3, 1), (4, 6, 3)]:
+        Ep, Em = E.copy(), E.copy()
+        Ep[b, f, d] += eps
+        Em[b, f, d] -= eps
+        num = ((O.fm_second_order_f64(Ep) - O.fm_second_order_f64(Em)) * g).sum() / (2 * eps)
+        assert abs(num - dE[b, f, d]) < 1e-4
+
+
+def test_dot_interaction_structure():
+    rng = np.random.default_rng(1)
+    X = rng.normal(size=(3, 27, 8)).astype(np.float32)
+    out = O.dot_interaction(X, False, True)
+    assert out.shape == (3, 729)
+    nz = out.reshape(3, 27, 27) != 0
+    assert nz.sum() == 3 * 351 and not np.tril(nz).any()
+    assert O.dot_interaction(X, False, False).shape == (3, 351)
+    assert O.dot_interaction(X, True, False).shape == (3, 378)
+
+
+def test_dedup_first_occurrence_order_and_input_order_sum():
+    idx = np.array([5, 2, 5, 9, 2, 5], dtype=np.int64)
+    vals = np.array([[1e8], [1.0], [-1e8], [3.0], [2.0], [1.0]], dtype=np.float32)
+    rows, summed = O.dedup_indexed_slices(idx, vals)
+    assert rows.tolist() == [5, 2, 9]
+    # input-order fp32 sum: (1e8 + -1e8) + 1 == 1 ; a different association would give 0
+    assert summed[:, 0].tolist() == [1.0, 3.0, 3.0]
+
+
+def test_adam_lazy_equals_tf_dense_on_step_one_and_differs_later():
+    rng = np.random.default_rng(2)
+    W0 = rng.uniform(-0.05, 0.05, size=(50, 8)).astype(np.float32)
+    idx1 = rng.integers(0, 50, size=(16, 3))
+    idx2 = rng.integers(0, 50, size=(16, 3))
+    d1 = rng.normal(0, 1e-3, size=(16, 3, 8)).astype(np.float32)
+    d2 = rng.normal(0, 1e-3, size=(16, 3, 8)).astype(np.float32)
+    A = dict(W=W0.copy(), m=np.zeros_like(W0), v=np.zeros_like(W0))
+    B = dict(W=W0.copy(), m=np.zeros_like(W0), v=np.zeros_like(W0))
+    O.sparse_backward_update(A["W"], A, idx1, d1, "adam_lazy", 1)
+    O.sparse_backward_update(B["W"], B, idx1, d1, "adam_tf_dense", 1)
+    np.testing.assert_array_equal(A["W"], B["W"])
+    O.sparse_backward_update(A["W"], A, idx2, d2, "adam_lazy", 2)
+    O.sparse_backward_update(B["W"], B, idx2, d2, "adam_tf_dense", 2)
+    untouched = np.setdiff1d(np.unique(idx1), np.unique(idx2))
+    assert untouched.size and not np.array_equal(A["W"][untouched], B["W"][untouched])   # momentum keeps moving them
+
+
+def test_adam_squares_the_summed_gradient():
+    W = np.zeros((4, 2), np.float32)
+    st = dict(m=np.zeros_like(W), v=np.zeros_like(W))
+    idx = np.array([[1, 1]])
+    dE = np.array([[[1.0, 2.0], [3.0, 4.0]]], np.float32)
+    O.sparse_backward_update(W, st, idx, dE, "adam_lazy", 1)
+    np.testing.assert_allclose(st["v"][1], 0.001 * np.array([16.0, 36.0]), rtol=1e-4)   # (1+3)^2, (2+4)^2
+
+
+def test_id_to_row_and_sharding_are_consistent():
+    ids = np.array([-1, 0, 5, 2 ** 40 + 3, 999_999], dtype=np.int64)
+    rows = O.id_to_row(ids, 1000)
+    assert rows.tolist() == [int((2 ** 64 - 1) % 1000), 0, 5, (2 ** 40 + 3) % 1000, 999]
+    owner, local = O.shard_of_row(rows, 8)
+    np.testing.assert_array_equal(local * 8 + owner, rows)
+
+
+def test_bf16_rounding_matches_torch():
+    import torch
+    x = np.random.default_rng(3).normal(size=4096).astype(np.float32)
+    ref = torch.tensor(x).to(torch.bfloat16).float().numpy()
+    np.testing.assert_array_equal(O.round_bf16(x), ref)
