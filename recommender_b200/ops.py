@@ -209,7 +209,6 @@ class GradSource:
                  scale="none", mask_idx=None, count=None, fm_g=None, fm_s=None):
         if not (1 <= len(srcs) <= _lib.RB_MAX_GRAD_SOURCES):
             raise ValueError(f"1..{_lib.RB_MAX_GRAD_SOURCES} gradient sources, got {len(srcs)}")
-        _need_cuda(*srcs, mask_idx, count, fm_g, fm_s)
         for s in srcs:
             if s.dtype != torch.float32:
                 raise TypeError("gradient sources must be float32")
@@ -249,7 +248,6 @@ class LookupGroup:
     """One use of a table inside a step: its index array, bag length and gradient source."""
 
     def __init__(self, idx: torch.Tensor, L: int, grad: GradSource, field_row_offset=None, hash_mod=0):
-        _need_cuda(idx, field_row_offset)
         self.idx = idx.contiguous()
         self.L, self.grad, self.field_row_offset, self.hash_mod = int(L), grad, field_row_offset, int(hash_mod)
 
@@ -280,6 +278,8 @@ def sparse_bwd_update(table, state0, state1, groups: Sequence[LookupGroup], *, o
     """IndexedSlices -> duplicate-row sum -> optimizer row update, in place on table/state
     (rb_sparse_bwd_update_groups; one group = rb_sparse_bwd_update)."""
     _need_cuda(table, state0, state1)
+    for g in groups:
+        _need_cuda(g.idx, g.field_row_offset, *g.grad.srcs, g.grad.mask_idx, g.grad.count, g.grad.fm_g, g.grad.fm_s)
     _f32c(table, "table")
     rows, D = table.shape
     if not (1 <= len(groups) <= _lib.RB_MAX_LOOKUP_GROUPS):

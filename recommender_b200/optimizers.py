@@ -47,6 +47,8 @@ class _Optimizer:
         recorded lookups; then clears them (the reference's `apply_gradients(zip(grads, vars))`,
         dien/train.py:22)."""
         embs, dense = _split(model_or_vars)
+        if hasattr(model_or_vars, "reduce_dense_grads"):
+            model_or_vars.reduce_dense_grads()      # data-parallel replicas (sharded.ShardedDLRM)
         step = self.iterations + 1
         params = [p for p in dense if p.grad is not None]
         if params:
