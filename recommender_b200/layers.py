@@ -235,23 +235,70 @@ class Embedding(nn.Module):
         return n
 
 
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _LinearBF16Fn(torch.autograd.Function):
+    """y = x @ W + b on bf16 tensor cores (cuBLASLt through torch), fp32 master weights.
+
+    x is bf16 [B, Kp] with Kp = in_dim rounded up to 8 (zero pad columns) so that cuBLAS never
+    falls back to its unaligned legacy kernels; W [in_dim, out] and b [out] are the fp32
+    parameters.  Backward: dx = dy W^T (bf16, padded), dW = x^T dy, db = 1^T dy as a skinny GEMM
+    (a column reduction over 65536 rows is ~6x slower as an elementwise reduce kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, need_dx):
+        in_dim, out = W.shape
+        Kp = x.shape[1]
+        Wp = torch.zeros(Kp, out, dtype=torch.bfloat16, device=W.device) if Kp != in_dim else None
+        if Wp is None:
+            Wp = W.to(torch.bfloat16)
+        else:
+            Wp[:in_dim].copy_(W)
+        y = torch.addmm(b.to(torch.bfloat16), x, Wp)
+        ctx.save_for_backward(x, Wp)
+        ctx.in_dim, ctx.need_dx = in_dim, need_dx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wp = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.mm(dy, Wp.t()) if ctx.need_dx else None
+        dW = torch.mm(x.t(), dy)[: ctx.in_dim].float()
+        ones = torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device)
+        db = torch.mm(ones, dy).reshape(-1).float()
+        return dx, dW, db, None
+
+
 class MLP(nn.Module):
     """ctr/layers.py:5-14: Dense layers whose HIDDEN layers are linear; only the last layer has
     `final_activation` (None | 'relu' | 'sigmoid').  Kernels are [in, units] Glorot-uniform, biases
     zero (Keras defaults), built on the first call like Keras does.  Dense and data-parallel:
-    it runs on cuBLAS through torch and is not part of the sparse hot path."""
+    it runs on cuBLAS through torch and is not part of the sparse hot path.
+
+    compute_dtype=torch.bfloat16 runs the GEMMs on bf16 tensor cores with fp32 master weights and
+    fp32 accumulation (activations between layers are bf16; the final activation is applied in
+    fp32).  In that mode the input may arrive already as bf16 with its feature axis zero-padded
+    to a multiple of 8 (what the fused interaction kernel emits)."""
 
     def __init__(self, units: Sequence[int], final_activation=None, *, compute_dtype: Optional[torch.dtype] = None,
                  generator: Optional[torch.Generator] = None):
         super().__init__()
         if final_activation not in (None, "relu", "sigmoid"):
             raise ValueError(final_activation)
+        if compute_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("compute_dtype must be None/float32 or bfloat16")
         self.units, self.final_activation = list(units), final_activation
-        self.compute_dtype, self._generator = compute_dtype, generator
+        self.compute_dtype = None if compute_dtype == torch.float32 else compute_dtype
+        self._generator = generator
+        self.in_dim: Optional[int] = None
         self.kernels = nn.ParameterList()
         self.biases = nn.ParameterList()
 
     def build(self, in_dim: int, device) -> None:
+        self.in_dim = int(in_dim)
         for u in self.units:
             lim = math.sqrt(6.0 / (in_dim + u))
             w = torch.empty(in_dim, u, dtype=torch.float32, device=device).uniform_(-lim, lim, generator=self._generator)
@@ -264,24 +311,43 @@ class MLP(nn.Module):
         parity tests because TF's RNG streams cannot be matched."""
         self.kernels = nn.ParameterList(nn.Parameter(torch.as_tensor(W, dtype=torch.float32).to(device).contiguous()) for W, _ in layers)
         self.biases = nn.ParameterList(nn.Parameter(torch.as_tensor(b, dtype=torch.float32).to(device).contiguous()) for _, b in layers)
+        self.in_dim = int(self.kernels[0].shape[0])
+
+    def padded_in_dim(self) -> int:
+        """Feature count the bf16 path wants its input padded to (multiple of 8)."""
+        return _round_up(self.in_dim, 8)
+
+    def _activate(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.float()
+        if self.final_activation == "relu":
+            x = torch.relu(x)
+        elif self.final_activation == "sigmoid":
+            x = torch.sigmoid(x)
+        return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if len(self.kernels) == 0:
             self.build(x.shape[-1], x.device)
-        cd = self.compute_dtype
-        last = len(self.kernels) - 1
-        for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
-            if cd is not None:
-                x = torch.addmm(b.to(cd), x.to(cd), W.to(cd))
+        if self.compute_dtype is None:
+            last = len(self.kernels) - 1
+            for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
+                x = torch.addmm(b, x.float(), W)
+            return self._activate(x)
+        # bf16 tensor-core path
+        Kp = self.padded_in_dim()
+        need_dx = x.requires_grad
+        if x.dtype != torch.bfloat16 or x.shape[-1] != Kp:
+            if x.shape[-1] != self.in_dim:
+                raise ValueError(f"MLP built for {self.in_dim} input features, got {x.shape[-1]}")
+            xp = torch.zeros(x.shape[0], Kp, dtype=torch.bfloat16, device=x.device) if Kp != self.in_dim else None
+            if xp is None:
+                x = x.to(torch.bfloat16)
             else:
-                x = torch.addmm(b, x, W)
-            if i == last:
-                x = x.float()
-                if self.final_activation == "relu":
-                    x = torch.relu(x)
-                elif self.final_activation == "sigmoid":
-                    x = torch.sigmoid(x)
-        return x
+                xp[:, : self.in_dim] = x              # autograd-aware pad (dense inputs carry no gradient in the models)
+                x = xp
+        for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
+            x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0)
+        return self._activate(x)
 
 
 class DotInteraction(nn.Module):

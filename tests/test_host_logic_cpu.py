@@ -95,3 +95,28 @@ def test_embedding_needs_cuda():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         Embedding(10, 4)
+
+
+def test_mlp_bf16_path_forward_backward_close_to_fp32():
+    rng = np.random.default_rng(5)
+    layers = O.init_mlp(rng, 13, [64, 32, 8])
+    x = rng.normal(size=(128, 13)).astype(np.float32)
+    ref, acts = O.mlp_forward(x, layers, "relu")
+    dy = rng.normal(size=ref.shape).astype(np.float32)
+    _, ref_grads = O.mlp_backward(dy, acts, layers, "relu")
+    mlp = MLP([64, 32, 8], "relu", compute_dtype=torch.bfloat16)
+    mlp.load_arrays(layers, "cpu")
+    assert mlp.padded_in_dim() == 16
+    y = mlp(torch.tensor(x))
+    assert y.dtype == torch.float32
+    np.testing.assert_allclose(y.detach().numpy(), ref, rtol=0, atol=0.03 * np.abs(ref).max())
+    y.backward(torch.tensor(dy))
+    for W, b, (dW, db) in zip(mlp.kernels, mlp.biases, ref_grads):
+        assert W.grad.shape == W.shape and W.grad.dtype == torch.float32
+        assert np.abs(W.grad.numpy() - dW).max() <= 0.05 * np.abs(dW).max()
+        assert np.abs(b.grad.numpy() - db).max() <= 0.05 * np.abs(db).max()
+    # pre-padded bf16 input (what the fused interaction kernel emits) gives the same result
+    xp = torch.zeros(128, 16, dtype=torch.bfloat16)
+    xp[:, :13] = torch.tensor(x)
+    y2 = mlp(xp)
+    np.testing.assert_array_equal(y2.detach().numpy(), y.detach().numpy())
