@@ -1,21 +1,33 @@
 // K3..K6 / K10: DotInteraction forward and backward on bf16 tensor cores (sm_100a).
 //
-// One warp owns one sample.  The F' <= 32 feature rows (F embedding rows — read from E or, in
-// the fused-gather form, straight from the table through idx — plus the optional dense vector)
-// are converted to bf16 into a padded shared tile; Z = X X^T (forward) and dX = (G+G^T) X
-// (backward) run as m16n8k16 bf16 MMAs with fp32 accumulators.  The triangular mask, the
-// zero-fill / compaction, the DLRM concat of the dense vector and the "|| bmlp" tail are all
-// applied in the epilogue, so none of the reference's temporaries exist.
-// The per-sample problem (27x27x64) is far below a tcgen05 128-row tile and the kernel is
-// HBM-bound (9 FLOP/B vs a ridge of ~214); the tcgen05 form lives in interaction_umma.cu.
+// HBM-bound (9 FLOP/B against a ridge of ~214), so the kernels are built around the
+// memory pipeline, not the MMA:
+//   * persistent CTAs (one per SM), every warp owns a private 2-stage ring in shared memory and
+//     walks its samples independently — no CTA-wide barrier anywhere;
+//   * the F' <= 32 feature rows of the NEXT sample (F embedding rows read straight from the
+//     table through idx in the fused-gather form, or from E; plus the optional dense vector)
+//     are fetched with 16-byte cp.async (LDGSTS, L2-only) while the current sample is computed;
+//     the row ids of the sample after that are already in flight (one coalesced load, lane f
+//     owns field f), so no dependent global load sits on the critical path;
+//   * MMA fragments are built directly from the fp32 rows in shared memory (conflict-free
+//     padded stride, cvt.rn.bf16x2 in registers): Z = X X^T needs no separate B operand (the B
+//     fragment of n-tile t is half of the A fragment of m-tile t/2), dX = (G+G^T) X takes its A
+//     operand straight from the staged dOut row through per-lane offsets computed once;
+//   * the triangular mask, zero fill / compaction, the DLRM concat of the dense vector and the
+//     "|| bmlp" tail are applied in the epilogue; the output row is staged
+//     in shared memory and written with aligned 16-byte stores.  fp32 [B, ncols(+D)] is the
+//     reference layout; the bf16 form (row padded to out_stride with zeros) is what the top
+//     MLP's first GEMM consumes, and the backward accepts dOut in the same two forms.
+// The per-sample problem (27x27x64) is far below a tcgen05 128-row tile; m16n8k16 bf16 MMAs keep
+// the tensor work at a few percent of the kernel.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace rb {
 
-constexpr int kIxWarps = 4;  // samples per CTA
-constexpr int kPad = 8;      // bf16 elements of row padding (16 B) -> conflict-free ldmatrix
+constexpr int kIxWarps = 8;    // warps (= samples in flight x2) per CTA
+constexpr int kIxStages = 2;   // ring depth per warp
 
 struct IxArgs {
   const float* E;          // [B,F,D] or null (fused gather)
@@ -31,27 +43,35 @@ struct IxArgs {
   int ncols;               // interaction columns (without tail)
 };
 
+// ---- small PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
+// 16-byte async copy global -> shared, L2 only; src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// kept(i,j) and its position in the compact (skip_gather == 0) layout   (ctr/layers.py:27-42)
+// kept(i,j) and its column in the output row   (ctr/layers.py:27-42)
 __device__ __forceinline__ bool kept(int i, int j, int self_interaction) { return self_interaction ? (j <= i) : (j > i); }
 __device__ __forceinline__ int compact_pos(int i, int j, int Fp, int self_interaction) {
   return self_interaction ? (i * (i + 1) / 2 + j) : (i * Fp - i * (i + 1) / 2 + (j - i - 1));
@@ -60,160 +80,150 @@ __device__ __forceinline__ int out_pos(int i, int j, const IxArgs& a) {
   return a.skip_gather ? (i * a.Fp + j) : compact_pos(i, j, a.Fp, a.self_interaction);
 }
 
-// Load the sample's F' rows (fp32) and park them as bf16 in xs[32][D+kPad]; rows >= F' are zero.
-template <int D>
-__device__ __forceinline__ void load_rows_bf16(const IxArgs& a, int64_t b, __nv_bfloat16* xs, int lane) {
+// ---- output / dOut element types ---------------------------------------------------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static __device__ __forceinline__ float from(float v) { return v; }
+  static __device__ __forceinline__ float to_f32(float v) { return v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+
+// ---- the row ids of one sample: lane f holds the table row of field f (or -1) ------------------------
+__device__ __forceinline__ int64_t load_sample_rows(const IxArgs& a, int64_t b, int lane) {
+  if (a.E != nullptr || lane >= a.F || b >= a.B) return -1;
+  int64_t id = load_raw_index(a.map.idx, a.map.is64, b * a.F + lane);
+  if (a.map.field_row_offset != nullptr) id += __ldg(a.map.field_row_offset + lane);
+  return (id >= 0 && id < a.map.rows) ? id : -1;
+}
+
+// Issue the async copies of sample b's F' rows into xs[32][STRIDE] (fp32).  Rows that do not
+// exist (out-of-range id, TF's GPU kernel semantics: zeros) are zero-filled by the copy itself.
+template <int D, int STRIDE>
+__device__ __forceinline__ void issue_rows(const IxArgs& a, int64_t b, int64_t my_row, float* xs, int lane) {
   constexpr int kLanesPerRow = D / 4;
   constexpr int kRowsPerIter = 32 / kLanesPerRow;
-  constexpr int kIters = 32 / kRowsPerIter;
   const int sub = lane / kLanesPerRow;
   const int c = (lane % kLanesPerRow) * 4;
-  float4 v[kIters];
-#pragma unroll
-  for (int it = 0; it < kIters; ++it) {
-    const int r = it * kRowsPerIter + sub;
-    const float* src = nullptr;
+  for (int r0 = 0; r0 < a.Fp; r0 += kRowsPerIter) {
+    const int r = r0 + sub;
+    const int64_t row = __shfl_sync(0xffffffffu, my_row, r & 31);
+    const float* src = a.dense_vec != nullptr ? a.dense_vec : a.table;  // any valid address for the zero-fill form
+    int bytes = 0;
     if (r < a.F) {
       if (a.E != nullptr) {
-        src = a.E + (b * a.F + r) * D;
-      } else {
-        const int64_t row = map_index(a.map, b * a.F + r);
-        if (row >= 0) src = a.table + row * D;
+        src = a.E + (b * a.F + r) * D + c;
+        bytes = 16;
+      } else if (row >= 0) {
+        src = a.table + row * D + c;
+        bytes = 16;
       }
     } else if (r == a.F && a.dense_vec != nullptr) {
-      src = a.dense_vec + b * D;
+      src = a.dense_vec + b * D + c;
+      bytes = 16;
     }
-    v[it] = (src != nullptr) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int it = 0; it < kIters; ++it) {
-    const int r = it * kRowsPerIter + sub;
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v[it].x, v[it].y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(v[it].z, v[it].w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(xs + r * (D + kPad) + c) = pk;
+    if (r < 32) cp_async16(xs + r * STRIDE + c, src, bytes);
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(kIxWarps * 32)
-dot_interaction_fwd_kernel(IxArgs a, float* __restrict__ out, int64_t out_stride, int out_smem_floats) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
-  if (b >= a.B) return;
-  constexpr int kXsBytes = 32 * (D + kPad) * 2;
-  unsigned char* my = smem + static_cast<size_t>(warp) * (kXsBytes + out_smem_floats * 4);
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(my);
-  float* os = reinterpret_cast<float*>(my + kXsBytes);
-
-  load_rows_bf16<D>(a, b, xs, lane);
-  const int total = a.ncols + (a.tail ? D : 0);
-  if (!a.skip_gather) {
-    // compact layout: every column is written by exactly one kept (i,j); nothing to clear
-  } else {
-    for (int i = lane; i < a.ncols; i += 32) os[i] = 0.f;
-  }
-  __syncwarp();
-
-  float acc[2][4][4];
+// Aligned write of a staged row: smem element (mis + e) <-> global row element e, where mis is the
+// misalignment (in elements) of the global row start from a 16-byte boundary, so that 16-byte
+// chunks line up on both sides.  `width` elements are written.
+template <typename T>
+__device__ __forceinline__ void store_row_aligned(T* __restrict__ grow, const T* os, int mis, int width, int lane) {
+  constexpr int EPC = 16 / static_cast<int>(sizeof(T));
+  const int nchunks = (mis + width + EPC - 1) / EPC;
+  T* gbase = grow - mis;
+  for (int c = lane; c < nchunks; c += 32) {
+    const int e0 = c * EPC;
+    if (e0 >= mis && e0 + EPC <= mis + width) {
+      __stcs(reinterpret_cast<float4*>(gbase + e0), *reinterpret_cast<const float4*>(os + e0));
+    } else {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0.f;
-
-#pragma unroll
-  for (int k0 = 0; k0 < D; k0 += 16) {
-    uint32_t afrag[2][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int row = mt * 16 + (lane % 8) + ((lane / 8) % 2) * 8;
-      const int col = k0 + (lane / 16) * 8;
-      ldmatrix_x4(afrag[mt], smem_addr(xs + row * (D + kPad) + col));
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      uint32_t bfrag[2];
-      const int row = nt * 8 + (lane % 8);
-      const int col = k0 + ((lane / 8) % 2) * 8;
-      ldmatrix_x2(bfrag, smem_addr(xs + row * (D + kPad) + col));
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(acc[mt][nt], afrag[mt], bfrag);
-    }
-  }
-
-  // epilogue: mask + placement into the staged output row
-  const int g = lane / 4, t2 = (lane % 4) * 2;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = mt * 16 + g + (k / 2) * 8;
-        const int j = nt * 8 + t2 + (k % 2);
-        if (i < a.Fp && j < a.Fp && kept(i, j, a.self_interaction)) os[out_pos(i, j, a)] = acc[mt][nt][k];
+      for (int k = 0; k < EPC; ++k) {
+        const int e = e0 + k;
+        if (e >= mis && e < mis + width) gbase[e] = os[e];
       }
-  if (a.tail) {
-    for (int d = lane; d < D; d += 32) os[a.ncols + d] = __ldg(a.dense_vec + b * D + d);
+    }
   }
-  __syncwarp();
-  float* dst = out + b * out_stride;
-  for (int i = lane; i < total; i += 32) __stcs(dst + i, os[i]);
 }
 
-template <int D>
-__global__ void __launch_bounds__(kIxWarps * 32)
-dot_interaction_bwd_kernel(IxArgs a, const float* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
-                           float* __restrict__ d_dense, int out_smem_floats) {
+// Async read of a global row into smem with the same alignment trick (dOut rows of the backward).
+template <typename T>
+__device__ __forceinline__ void load_row_aligned_async(const T* __restrict__ grow, T* gs, int mis, int width, int lane) {
+  constexpr int EPC = 16 / static_cast<int>(sizeof(T));
+  const int nchunks = (mis + width + EPC - 1) / EPC;
+  const T* gbase = grow - mis;
+  for (int c = lane; c < nchunks; c += 32) {
+    const int e0 = c * EPC;
+    if (e0 >= mis && e0 + EPC <= mis + width) {
+      cp_async16(gs + e0, gbase + e0, 16);
+    } else {
+#pragma unroll
+      for (int k = 0; k < EPC; ++k) {
+        const int e = e0 + k;
+        if (e >= mis && e < mis + width) {
+          if constexpr (sizeof(T) == 4) cp_async4(gs + e, gbase + e);
+          else gs[e] = gbase[e];  // bf16 rows are 16 B aligned in practice; plain copy keeps this correct anyway
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ int misalign_elems(const T* p) {
+  return static_cast<int>((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------
+// smem per warp: kIxStages x xs[32][D+8] fp32, then the staged output row (os_elems elements of OUT).
+template <int D, typename OUT>
+__global__ void __launch_bounds__(kIxWarps * 32, 1)
+dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, int write_width, int os_bytes) {
+  constexpr int STRIDE = D + 8;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
+  constexpr int kXsFloats = 32 * STRIDE;
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
+  unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * kXsFloats * 4 + os_bytes);
+  float* xs_base = reinterpret_cast<float*>(my);
+  OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kXsFloats * 4);
+
+  // one-time init: rows >= F' of every stage and the whole output staging (pad columns stay zero)
+  for (int i = lane; i < kIxStages * kXsFloats / 4; i += 32) reinterpret_cast<float4*>(xs_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < os_bytes / 16; i += 32) reinterpret_cast<float4*>(os)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kIxWarps;
+  int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
   if (b >= a.B) return;
-  constexpr int kXsBytes = 32 * (D + kPad) * 2;
-  constexpr int kSsBytes = 32 * (32 + kPad) * 2;
-  unsigned char* my = smem + static_cast<size_t>(warp) * (kXsBytes + kSsBytes + out_smem_floats * 4);
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(my);
-  __nv_bfloat16* ss = reinterpret_cast<__nv_bfloat16*>(my + kXsBytes);
-  float* gs = reinterpret_cast<float*>(my + kXsBytes + kSsBytes);
 
-  // stage the dOut row (interaction columns + tail) with coalesced loads
-  const int total = a.ncols + (a.tail ? D : 0);
-  const float* src = dOut + b * dout_stride;
-  for (int i = lane; i < total; i += 32) gs[i] = __ldcs(src + i);
-  load_rows_bf16<D>(a, b, xs, lane);
-  __syncwarp();
-
-  // S = G + G^T with G = mask (.) dOut, as bf16 [32][32+kPad]; lane owns column j = lane
-  for (int i = 0; i < 32; ++i) {
-    const int j = lane;
-    float sv = 0.f;
-    if (i < a.Fp && j < a.Fp) {
-      if (kept(i, j, a.self_interaction)) sv += gs[out_pos(i, j, a)];
-      if (kept(j, i, a.self_interaction)) sv += gs[out_pos(j, i, a)];
-    }
-    ss[i * (32 + kPad) + j] = __float2bfloat16_rn(sv);
-  }
-  __syncwarp();
-
-  // A = S (two k-steps of 16), fragments kept for all n-chunks
-  uint32_t afrag[2][2][4];  // [mt][kstep]
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int row = mt * 16 + (lane % 8) + ((lane / 8) % 2) * 8;
-      const int col = ks * 16 + (lane / 16) * 8;
-      ldmatrix_x4(afrag[mt][ks], smem_addr(ss + row * (32 + kPad) + col));
-    }
+  int64_t rows_cur = load_sample_rows(a, b, lane);
+  issue_rows<D, STRIDE>(a, b, rows_cur, xs_base, lane);
+  cp_async_commit();
+  int64_t rows_next = load_sample_rows(a, b + nwarps, lane);
 
   const int g = lane / 4, t2 = (lane % 4) * 2;
-#pragma unroll
-  for (int n0 = 0; n0 < D; n0 += 32) {  // chunks of 4 n-tiles bound the accumulator registers
+  const int ntiles = (a.Fp + 7) / 8;   // n-tiles (and half m-tiles) that hold real features
+  const int total = a.ncols + (a.tail ? D : 0);
+  int stage = 0;
+
+  for (; b < a.B; b += nwarps) {
+    const int64_t bn = b + nwarps;
+    float* xs = xs_base + stage * kXsFloats;
+    if (bn < a.B) {
+      issue_rows<D, STRIDE>(a, bn, rows_next, xs_base + (stage ^ 1) * kXsFloats, lane);
+      rows_next = load_sample_rows(a, bn + nwarps, lane);   // in flight during this sample's math
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
     float acc[2][4][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -221,42 +231,199 @@ dot_interaction_bwd_kernel(IxArgs a, const float* __restrict__ dOut, int64_t dou
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0.f;
+
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      if (n0 + nt * 8 < D) {
+    for (int k0 = 0; k0 < D; k0 += 16) {
+      uint32_t af[2][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t bfrag[2];
-          // B[k][n] = X[k][n]: transposed 8x8 loads of X rows k, columns n
-          const int row = ks * 16 + (lane % 8) + ((lane / 8) % 2) * 8;
-          ldmatrix_x2_trans(bfrag, smem_addr(xs + row * (D + kPad) + n0 + nt * 8));
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt * 2 < ntiles) {
+          const float* p = xs + (mt * 16 + g) * STRIDE + k0 + t2;
+          const float2 v0 = *reinterpret_cast<const float2*>(p);
+          const float2 v1 = *reinterpret_cast<const float2*>(p + 8 * STRIDE);
+          const float2 v2 = *reinterpret_cast<const float2*>(p + 8);
+          const float2 v3 = *reinterpret_cast<const float2*>(p + 8 * STRIDE + 8);
+          af[mt][0] = pack_bf16(v0.x, v0.y);
+          af[mt][1] = pack_bf16(v1.x, v1.y);
+          af[mt][2] = pack_bf16(v2.x, v2.y);
+          af[mt][3] = pack_bf16(v3.x, v3.y);
+        } else {
+          af[mt][0] = af[mt][1] = af[mt][2] = af[mt][3] = 0u;
+        }
+      }
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(acc[mt][nt], afrag[mt][ks], bfrag);
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < ntiles) {
+          // B[k][n] = X[n][k]: rows nt*8+g of X are rows (nt&1)*8+g of m-tile nt/2
+          const uint32_t b0 = af[nt / 2][(nt & 1) ? 1 : 0];
+          const uint32_t b1 = af[nt / 2][(nt & 1) ? 3 : 2];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            if (mt * 2 < ntiles) mma_bf16_16816(acc[mt][nt], af[mt], b0, b1);
         }
       }
     }
+
+    // epilogue: mask + placement into the staged output row (element e lives at os[mis + e])
+    OUT* grow = out + b * out_stride;
+    const int mis = misalign_elems(grow);
+    OUT* osr = os + mis;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int col = n0 + nt * 8 + t2;
-        if (col < D) {
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int i = mt * 16 + g + h * 8;
-            float2 v = make_float2(acc[mt][nt][h * 2], acc[mt][nt][h * 2 + 1]);
-            if (i < a.F) {
-              if (dE != nullptr) __stcs(reinterpret_cast<float2*>(dE + (b * a.F + i) * D + col), v);
-            } else if (i == a.F && a.dense_vec != nullptr && d_dense != nullptr) {
-              if (a.tail) {
-                v.x += gs[a.ncols + col];
-                v.y += gs[a.ncols + col + 1];
-              }
-              *reinterpret_cast<float2*>(d_dense + b * D + col) = v;
-            }
+        for (int k = 0; k < 4; ++k) {
+          const int i = mt * 16 + g + (k / 2) * 8;
+          const int j = nt * 8 + t2 + (k % 2);
+          if (i < a.Fp && j < a.Fp) {
+            const bool kp = kept(i, j, a.self_interaction);
+            if (a.skip_gather) osr[i * a.Fp + j] = Elem<OUT>::from(kp ? acc[mt][nt][k] : 0.f);
+            else if (kp) osr[compact_pos(i, j, a.Fp, a.self_interaction)] = Elem<OUT>::from(acc[mt][nt][k]);
           }
         }
+    if (a.tail) {
+      for (int d = lane; d < D; d += 32) osr[a.ncols + d] = Elem<OUT>::from(xs[a.F * STRIDE + d]);
+    }
+    __syncwarp();
+    store_row_aligned<OUT>(grow, os, mis, write_width > total ? write_width : total, lane);
+    __syncwarp();   // os and xs[stage] are free again
+    rows_cur = rows_next;
+    stage ^= 1;
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------
+// smem per warp: kIxStages x { xs[32][D+4] fp32, gs[gs_bytes] staged dOut row }.
+template <int D, typename DOUT>
+__global__ void __launch_bounds__(kIxWarps * 32, 1)
+dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
+                           float* __restrict__ d_dense, int gs_bytes) {
+  constexpr int STRIDE = D + 4;  // floats; 2*(D+4) % 32 == 8 -> conflict-free 32-bit B-fragment loads
+  constexpr int kXsFloats = 32 * STRIDE;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int stage_bytes = kXsFloats * 4 + gs_bytes;
+  unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * stage_bytes);
+
+  for (int i = lane; i < kIxStages * stage_bytes / 16; i += 32) reinterpret_cast<float4*>(my)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kIxWarps;
+  int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
+  if (b >= a.B) return;
+
+  const int g = lane / 4, t2 = (lane % 4) * 2;
+  const int total = a.ncols + (a.tail ? D : 0);
+  const int ktiles = (a.Fp + 15) / 16;   // k-steps (and m-tiles) that hold real features
+
+  // Per-lane offsets of the 32 S = G + G^T elements this lane feeds into the A fragments,
+  // sample-independent: element e = ((mt*2 + ks)*4 + reg)*2 + c  <->  S[i][j] with
+  //   i = mt*16 + g + (reg & 1)*8,  j = ks*16 + t2 + c + (reg >> 1)*8.
+  // off == 0xFFFF: the element is zero.  dbl bit: diagonal of the self-interaction form (G + G^T doubles it).
+  uint32_t offp[16];
+  uint32_t dbl = 0;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int c = e & 1, reg = (e >> 1) & 3, ks = (e >> 3) & 1, mt = e >> 4;
+    const int i = mt * 16 + g + (reg & 1) * 8;
+    const int j = ks * 16 + t2 + c + (reg >> 1) * 8;
+    uint32_t off = 0xFFFFu;
+    if (i < a.Fp && j < a.Fp) {
+      if (i == j) {
+        if (a.self_interaction) {
+          off = static_cast<uint32_t>(out_pos(i, i, a));
+          dbl |= (1u << e);
+        }
+      } else {
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        off = static_cast<uint32_t>(a.self_interaction ? out_pos(hi, lo, a) : out_pos(lo, hi, a));
       }
+    }
+    if (c == 0) offp[e >> 1] = off;
+    else offp[e >> 1] |= off << 16;
+  }
+
+  auto issue = [&](int64_t bb, int64_t rows, int st) {
+    unsigned char* sp = my + st * stage_bytes;
+    issue_rows<D, STRIDE>(a, bb, rows, reinterpret_cast<float*>(sp), lane);
+    const DOUT* grow = dOut + bb * dout_stride;
+    load_row_aligned_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4), misalign_elems(grow), total, lane);
+  };
+
+  int64_t rows_cur = load_sample_rows(a, b, lane);
+  issue(b, rows_cur, 0);
+  cp_async_commit();
+  int64_t rows_next = load_sample_rows(a, b + nwarps, lane);
+  int stage = 0;
+
+  for (; b < a.B; b += nwarps) {
+    const int64_t bn = b + nwarps;
+    unsigned char* sp = my + stage * stage_bytes;
+    const float* xs = reinterpret_cast<const float*>(sp);
+    if (bn < a.B) {
+      issue(bn, rows_next, stage ^ 1);
+      rows_next = load_sample_rows(a, bn + nwarps, lane);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const DOUT* gs = reinterpret_cast<const DOUT*>(sp + kXsFloats * 4) + misalign_elems(dOut + b * dout_stride);
+
+    // A = S as bf16 fragments [mt][ks][4]
+    uint32_t af[2][2][4];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const uint32_t o0 = offp[q] & 0xFFFFu, o1 = offp[q] >> 16;
+      float v0 = (o0 != 0xFFFFu) ? Elem<DOUT>::to_f32(gs[o0]) : 0.f;
+      float v1 = (o1 != 0xFFFFu) ? Elem<DOUT>::to_f32(gs[o1]) : 0.f;
+      if (dbl & (1u << (2 * q))) v0 += v0;
+      if (dbl & (1u << (2 * q + 1))) v1 += v1;
+      af[q >> 3][(q >> 2) & 1][q & 3] = pack_bf16(v0, v1);
+    }
+
+#pragma unroll 2
+    for (int nt = 0; nt < D / 8; ++nt) {
+      float acc[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[mt][k] = 0.f;
+      const int n = nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < ktiles) {
+          // B[k][n] = X[k][n]: two consecutive feature rows per register
+          const float* p = xs + (ks * 16 + t2) * STRIDE + n;
+          const uint32_t b0 = pack_bf16(p[0], p[STRIDE]);
+          const uint32_t b1 = pack_bf16(p[8 * STRIDE], p[9 * STRIDE]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            if (mt < ktiles) mma_bf16_16816(acc[mt], af[mt][ks], b0, b1);
+        }
+      }
+      const int col = nt * 8 + t2;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = mt * 16 + g + h * 8;
+          float2 v = make_float2(acc[mt][h * 2], acc[mt][h * 2 + 1]);
+          if (i < a.F) {
+            if (dE != nullptr) __stcs(reinterpret_cast<float2*>(dE + (b * a.F + i) * D + col), v);
+          } else if (i == a.F && a.dense_vec != nullptr && d_dense != nullptr) {
+            if (a.tail) {
+              v.x += Elem<DOUT>::to_f32(gs[a.ncols + col]);
+              v.y += Elem<DOUT>::to_f32(gs[a.ncols + col + 1]);
+            }
+            *reinterpret_cast<float2*>(d_dense + b * D + col) = v;
+          }
+        }
+    }
+    __syncwarp();   // the stage may be overwritten by the next iteration's copies
+    rows_cur = rows_next;
+    stage ^= 1;
   }
 }
 
@@ -292,7 +459,56 @@ static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) {
+    set_error("dot interaction needs %zu bytes of shared memory per CTA (> 227 KiB)", bytes);
+    return RB_ERR_SHAPE;
+  }
   if (bytes > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  return RB_OK;
+}
+
+static unsigned int persistent_grid(int64_t B) {
+  const int64_t need = (B + kIxWarps - 1) / kIxWarps;
+  return static_cast<unsigned int>(need < kNumSMs ? (need < 1 ? 1 : need) : kNumSMs);
+}
+
+template <typename OUT>
+static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int write_width, cudaStream_t st) {
+  // staged row: up to 15 bytes of misalignment + the widest row written, rounded to 16 B
+  const int total = a.ncols + (a.tail ? D : 0);
+  const int width = write_width > total ? write_width : total;
+  const int os_bytes = ((width * static_cast<int>(sizeof(OUT)) + 15 + 15) / 16) * 16;
+  const unsigned int grid = persistent_grid(a.B);
+  int rc = RB_OK;
+#define LAUNCH(DD)                                                                                                      \
+  {                                                                                                                     \
+    size_t smem = static_cast<size_t>(kIxWarps) * (kIxStages * 32 * (DD + 8) * 4 + os_bytes);                           \
+    rc = set_smem(dot_interaction_fwd_kernel<DD, OUT>, smem);                                                           \
+    if (rc != RB_OK) return rc;                                                                                         \
+    dot_interaction_fwd_kernel<DD, OUT><<<grid, kIxWarps * 32, smem, st>>>(a, out, out_stride, write_width, os_bytes);  \
+  }
+  if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
+#undef LAUNCH
+  RB_LAUNCH_CHECK("dot_interaction_fwd_kernel");
+  return RB_OK;
+}
+
+template <typename DOUT>
+static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_stride, float* dE, float* d_dense, cudaStream_t st) {
+  const int total = a.ncols + (a.tail ? D : 0);
+  const int gs_bytes = ((total * static_cast<int>(sizeof(DOUT)) + 15 + 15) / 16) * 16;
+  const unsigned int grid = persistent_grid(a.B);
+  int rc = RB_OK;
+#define LAUNCH(DD)                                                                                                      \
+  {                                                                                                                     \
+    size_t smem = static_cast<size_t>(kIxWarps) * kIxStages * (32 * (DD + 4) * 4 + gs_bytes);                           \
+    rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT>, smem);                                                          \
+    if (rc != RB_OK) return rc;                                                                                         \
+    dot_interaction_bwd_kernel<DD, DOUT><<<grid, kIxWarps * 32, smem, st>>>(a, dOut, dout_stride, dE, d_dense, gs_bytes); \
+  }
+  if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
+#undef LAUNCH
+  RB_LAUNCH_CHECK("dot_interaction_bwd_kernel");
   return RB_OK;
 }
 
@@ -303,54 +519,45 @@ using namespace rb;
 extern "C" int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows, const void* idx,
                                       int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                       int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
-                                      int32_t tail, float* out, int64_t out_stride, void* stream) {
+                                      int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* stream) {
   IxArgs a;
   int rc = fill_args(&a, E, table, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction,
                      skip_gather, tail);
   if (rc != RB_OK) return rc;
   if (B == 0) return RB_OK;
-  RB_CHECK_ARG(out != nullptr && out_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "out is null or out_stride too small");
-  const int out_floats = (a.ncols + D + 3) / 4 * 4;
+  const int total = a.ncols + (a.tail ? D : 0);
+  RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
+  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned int grid = grid_for(B, kIxWarps);
-#define LAUNCH(DD)                                                                                   \
-  {                                                                                                  \
-    size_t smem = static_cast<size_t>(kIxWarps) * (32 * (DD + kPad) * 2 + out_floats * 4);          \
-    rc = set_smem(dot_interaction_fwd_kernel<DD>, smem);                                             \
-    if (rc != RB_OK) return rc;                                                                      \
-    dot_interaction_fwd_kernel<DD><<<grid, kIxWarps * 32, smem, st>>>(a, out, out_stride, out_floats); \
+  if (out_dtype == RB_F32) {
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 3) == 0, RB_ERR_ALIGN, "out not 4 B aligned");
+    return launch_fwd<float>(a, D, static_cast<float*>(out), out_stride, total, st);
   }
-  if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
-#undef LAUNCH
-  RB_LAUNCH_CHECK("dot_interaction_fwd_kernel");
-  return RB_OK;
+  // bf16: the pad columns [total, out_stride) are written as zeros so a GEMM can consume the padded row
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 1) == 0, RB_ERR_ALIGN, "out not 2 B aligned");
+  RB_CHECK_ARG(out_stride - total < 64, RB_ERR_ARG, "bf16 out_stride pads more than 63 columns");
+  return launch_fwd<__nv_bfloat16>(a, D, static_cast<__nv_bfloat16*>(out), out_stride, static_cast<int>(out_stride), st);
 }
 
 extern "C" int rb_dot_interaction_bwd(const float* E, const float* table, int64_t rows, const void* idx,
                                       int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                       int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
-                                      int32_t tail, const float* dOut, int64_t dout_stride, float* dE, float* d_dense,
-                                      void* stream) {
+                                      int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
+                                      float* d_dense, void* stream) {
   IxArgs a;
   int rc = fill_args(&a, E, table, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction,
                      skip_gather, tail);
   if (rc != RB_OK) return rc;
   if (B == 0) return RB_OK;
   RB_CHECK_ARG(dOut != nullptr && dout_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "dOut is null or stride too small");
+  RB_CHECK_ARG(dout_dtype == RB_F32 || dout_dtype == RB_BF16, RB_ERR_ARG, "bad dout_dtype %d", dout_dtype);
   RB_CHECK_ARG((dE == nullptr || aligned_for(dE, 4)) && (d_dense == nullptr || aligned_for(d_dense, 4)), RB_ERR_ALIGN,
                "dE/d_dense not 16 B aligned");
-  const int out_floats = (a.ncols + D + 3) / 4 * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned int grid = grid_for(B, kIxWarps);
-#define LAUNCH(DD)                                                                                               \
-  {                                                                                                              \
-    size_t smem = static_cast<size_t>(kIxWarps) * (32 * (DD + kPad) * 2 + 32 * (32 + kPad) * 2 + out_floats * 4); \
-    rc = set_smem(dot_interaction_bwd_kernel<DD>, smem);                                                         \
-    if (rc != RB_OK) return rc;                                                                                  \
-    dot_interaction_bwd_kernel<DD><<<grid, kIxWarps * 32, smem, st>>>(a, dOut, dout_stride, dE, d_dense, out_floats); \
+  if (dout_dtype == RB_F32) {
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(dOut) & 3) == 0, RB_ERR_ALIGN, "dOut not 4 B aligned");
+    return launch_bwd<float>(a, D, static_cast<const float*>(dOut), dout_stride, dE, d_dense, st);
   }
-  if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
-#undef LAUNCH
-  RB_LAUNCH_CHECK("dot_interaction_bwd_kernel");
-  return RB_OK;
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(dOut) & 1) == 0, RB_ERR_ALIGN, "dOut not 2 B aligned");
+  return launch_bwd<__nv_bfloat16>(a, D, static_cast<const __nv_bfloat16*>(dOut), dout_stride, dE, d_dense, st);
 }
