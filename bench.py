@@ -357,11 +357,14 @@ def run_b200(args):
     cat0 = resident[0][0]
     rows0 = cat0 if T == 1 else cat0 + (torch.arange(T, device=dev) * V)[None]
     U = int(torch.unique(rows0).numel())
+    # bytes of one interaction row as it crosses HBM: fp32 [F'^2+D], or bf16 padded to 8 columns for the bf16 top MLP
+    width = Fp * Fp + D
+    row_bytes = ((width + 7) // 8 * 8) * 2 if cd == torch.bfloat16 else width * 4
     algo = {
-        # N*idxB + N*D*4 + B*D*4 + B*(F'^2+D)*4
-        "dot_interaction_fwd": N * 8 + N * D * 4 + B * D * 4 + B * (Fp * Fp + D) * 4,
+        # N*idxB + N*D*4 (rows) + B*D*4 (dense vec) + B*row (out)
+        "dot_interaction_fwd": N * 8 + N * D * 4 + B * D * 4 + B * row_bytes,
         # dOut + re-gathered rows + ids + dense vec in; dE + d_dense out
-        "dot_interaction_bwd": B * (Fp * Fp + D) * 4 + N * D * 4 + N * 8 + B * D * 4 + N * D * 4 + B * D * 4,
+        "dot_interaction_bwd": B * row_bytes + N * D * 4 + N * 8 + B * D * 4 + N * D * 4 + B * D * 4,
         # N*D*4 (dE) + N*idxB + U*D*4*6 (read+write of var, m, v)
         "sparse_bwd_update": N * D * 4 + N * 8 + U * D * 4 * 6,
     }

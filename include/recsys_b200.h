@@ -47,6 +47,9 @@ typedef enum rb_status {
 
 typedef enum rb_index_type { RB_I32 = 0, RB_I64 = 1 } rb_index_type;
 
+/* element type of the interaction output / its incoming gradient */
+typedef enum rb_float_type { RB_F32 = 0, RB_BF16 = 1 } rb_float_type;
+
 /* pooling over the L positions of a bag */
 typedef enum rb_pool_mode {
   RB_POOL_SUM = 1,          /* tf.reduce_sum(E, axis=1)              ctr/model.py:21        */
@@ -179,25 +182,30 @@ int rb_gather_fm_fwd(const float* table, int64_t rows, int32_t D,
  *   tail != 0 : dense_vec[b,:] is also copied to out[b, ncols .. ncols+D)   (ctr/model.py:54)
  * E == NULL selects the fused gather: rows are read straight from `table` through idx[B,F]
  * (+field_row_offset), so [B,F,D] never exists in HBM.
- * out row b starts at out + b*out_stride.  Requires F' <= 32, D % 16 == 0, D <= 128.
+ * out row b starts at out + b*out_stride (elements of out_dtype).  out_dtype = RB_F32 is the
+ * reference layout (tf.float32, ctr/layers.py:38).  out_dtype = RB_BF16 rounds the row to bf16
+ * for a bf16 top MLP and ALSO zero-fills the pad columns [ncols(+D), out_stride), so the padded
+ * row can be the K operand of a GEMM (out_stride - width < 64).
+ * Requires F' <= 32, D in {16, 32, 64, 128}.
  */
 int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows,
                            const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                            const float* dense_vec, int64_t B, int32_t F, int32_t D,
                            int32_t self_interaction, int32_t skip_gather, int32_t tail,
-                           float* out, int64_t out_stride, void* stream);
+                           void* out, int32_t out_dtype, int64_t out_stride, void* stream);
 
 /*
  * Backward of the above (TF autodiff of ctr/layers.py:25-42 and ctr/model.py:51-55):
  *   G = mask (.) dOut,  dX = (G + G^T) X;  dE[b,f,:] = dX[b,f,:] (f < F),
  *   d_dense[b,:] = dX[b,F,:] (+ dOut[b, ncols .. ncols+D) when tail != 0).
- * dE row (b,f) is written at dE + (b*F + f)*D.
+ * dE row (b,f) is written at dE + (b*F + f)*D.  dOut is RB_F32 or RB_BF16 (dout_dtype), row b at
+ * dOut + b*dout_stride elements; dE and d_dense are always fp32.
  */
 int rb_dot_interaction_bwd(const float* E, const float* table, int64_t rows,
                            const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                            const float* dense_vec, int64_t B, int32_t F, int32_t D,
                            int32_t self_interaction, int32_t skip_gather, int32_t tail,
-                           const float* dOut, int64_t dout_stride,
+                           const void* dOut, int32_t dout_dtype, int64_t dout_stride,
                            float* dE, float* d_dense, void* stream);
 
 /* ---- K7..K9: backward scatter + sparse optimizer row update ------------------------------- */

@@ -19,6 +19,7 @@ RB_MAX_LOOKUP_GROUPS = 4
 
 # enums (recsys_b200.h)
 RB_I32, RB_I64 = 0, 1
+RB_F32, RB_BF16 = 0, 1
 RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
 RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
 RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2
@@ -58,8 +59,8 @@ SIGNATURES = {
     "rb_gather_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
     "rb_bag_pool_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _i64, _p, _p, _p]),
     "rb_gather_fm_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p]),
-    "rb_dot_interaction_fwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
-    "rb_dot_interaction_bwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p, _p, _p]),
+    "rb_dot_interaction_fwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
+    "rb_dot_interaction_bwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p, _p, _p]),
     "rb_sparse_bwd_update_workspace_bytes": (C.c_size_t, [_i64, _i32, _i64]),
     "rb_sparse_bwd_update": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64,
                                        C.POINTER(RbGradSource), C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),

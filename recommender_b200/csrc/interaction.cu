@@ -26,8 +26,12 @@
 
 namespace rb {
 
-constexpr int kIxWarps = 8;    // warps (= samples in flight x2) per CTA
 constexpr int kIxStages = 2;   // ring depth per warp
+// warps per CTA (each with its own ring): sized so that kIxStages rings + staging fit in 227 KiB
+template <int D>
+struct IxWarps {
+  static constexpr int value = (D <= 64) ? 8 : 4;
+};
 
 struct IxArgs {
   const float* E;          // [B,F,D] or null (fused gather)
@@ -72,7 +76,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 // kept(i,j) and its column in the output row   (ctr/layers.py:27-42)
-__device__ __forceinline__ bool kept(int i, int j, int self_interaction) { return self_interaction ? (j <= i) : (j > i); }
 __device__ __forceinline__ int compact_pos(int i, int j, int Fp, int self_interaction) {
   return self_interaction ? (i * (i + 1) / 2 + j) : (i * Fp - i * (i + 1) / 2 + (j - i - 1));
 }
@@ -94,68 +97,74 @@ struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 };
 
-// ---- the row ids of one sample: lane f holds the table row of field f (or -1) ------------------------
-__device__ __forceinline__ int64_t load_sample_rows(const IxArgs& a, int64_t b, int lane) {
-  if (a.E != nullptr || lane >= a.F || b >= a.B) return -1;
-  int64_t id = load_raw_index(a.map.idx, a.map.is64, b * a.F + lane);
-  if (a.map.field_row_offset != nullptr) id += __ldg(a.map.field_row_offset + lane);
-  return (id >= 0 && id < a.map.rows) ? id : -1;
+// ---- the row ids of one sample: lane f holds the source row of field f -----------------------------
+// Fused gather: row = idx[b,f] (+ field offset), kInvalidRow when out of range (TF's GPU gather
+// writes zeros).  Materialised E: row = b*F + f of E viewed as [B*F, D].
+constexpr uint32_t kInvalidRow = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t load_sample_row(const IxArgs& a, int64_t b, int lane, int64_t lane_off) {
+  if (lane >= a.F || b >= a.B) return kInvalidRow;
+  if (a.E != nullptr) return static_cast<uint32_t>(b * a.F + lane);
+  const int64_t id = load_raw_index(a.map.idx, a.map.is64, b * a.F + lane) + lane_off;
+  return (id >= 0 && id < a.map.rows) ? static_cast<uint32_t>(id) : kInvalidRow;
 }
 
-// Issue the async copies of sample b's F' rows into xs[32][STRIDE] (fp32).  Rows that do not
-// exist (out-of-range id, TF's GPU kernel semantics: zeros) are zero-filled by the copy itself.
+// Issue the async copies of one sample's F rows (+ the dense vector as row F) into xs[32][STRIDE].
+// src_lane = (E or table) + this lane's column offset; dst_lane = xs + sub*STRIDE + column offset.
 template <int D, int STRIDE>
-__device__ __forceinline__ void issue_rows(const IxArgs& a, int64_t b, int64_t my_row, float* xs, int lane) {
-  constexpr int kLanesPerRow = D / 4;
-  constexpr int kRowsPerIter = 32 / kLanesPerRow;
-  const int sub = lane / kLanesPerRow;
-  const int c = (lane % kLanesPerRow) * 4;
-  for (int r0 = 0; r0 < a.Fp; r0 += kRowsPerIter) {
-    const int r = r0 + sub;
-    const int64_t row = __shfl_sync(0xffffffffu, my_row, r & 31);
-    const float* src = a.dense_vec != nullptr ? a.dense_vec : a.table;  // any valid address for the zero-fill form
-    int bytes = 0;
-    if (r < a.F) {
-      if (a.E != nullptr) {
-        src = a.E + (b * a.F + r) * D + c;
-        bytes = 16;
-      } else if (row >= 0) {
-        src = a.table + row * D + c;
-        bytes = 16;
-      }
-    } else if (r == a.F && a.dense_vec != nullptr) {
-      src = a.dense_vec + b * D + c;
-      bytes = 16;
-    }
-    if (r < 32) cp_async16(xs + r * STRIDE + c, src, bytes);
+__device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, uint32_t my_row, int F, float* dst_lane,
+                                           int sub, const float* __restrict__ dense_lane, float* dense_dst) {
+  constexpr int kRowsPerIter = 32 / (D / 4);
+#pragma unroll 4
+  for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
+    const int r = r0 + sub;                                        // <= 31
+    const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+    const bool ok = row != kInvalidRow;
+    const float* src = ok ? src_lane + static_cast<size_t>(row) * D : src_lane;
+    if (r < F) cp_async16(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);   // invalid row: zero-filled by the copy
   }
+  if (dense_lane != nullptr) cp_async16(dense_dst, dense_lane, 16);
 }
 
-// Aligned write of a staged row: smem element (mis + e) <-> global row element e, where mis is the
-// misalignment (in elements) of the global row start from a 16-byte boundary, so that 16-byte
-// chunks line up on both sides.  `width` elements are written.
 template <typename T>
-__device__ __forceinline__ void store_row_aligned(T* __restrict__ grow, const T* os, int mis, int width, int lane) {
+__device__ __forceinline__ int misalign_elems(const T* p) {
+  return static_cast<int>((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
+}
+
+// Write `width` staged elements os[0..width) to the global row `grow` with aligned 16-byte stores.
+// mis = misalignment (elements) of grow from a 16-byte boundary; chunk c covers row elements
+// [c*EPC - mis, (c+1)*EPC - mis).
+template <typename T>
+__device__ __forceinline__ void store_row(T* __restrict__ grow, const T* os, int mis, int width, int lane) {
   constexpr int EPC = 16 / static_cast<int>(sizeof(T));
   const int nchunks = (mis + width + EPC - 1) / EPC;
-  T* gbase = grow - mis;
+  if (mis == 0) {
+    const int full = width / EPC;
+    for (int c = lane; c < full; c += 32) __stcs(reinterpret_cast<float4*>(grow) + c, reinterpret_cast<const float4*>(os)[c]);
+    for (int e = full * EPC + lane; e < width; e += 32) grow[e] = os[e];
+    return;
+  }
   for (int c = lane; c < nchunks; c += 32) {
-    const int e0 = c * EPC;
-    if (e0 >= mis && e0 + EPC <= mis + width) {
-      __stcs(reinterpret_cast<float4*>(gbase + e0), *reinterpret_cast<const float4*>(os + e0));
+    const int e0 = c * EPC - mis;
+    if (e0 >= 0 && e0 + EPC <= width) {
+      if constexpr (sizeof(T) == 4) {
+        __stcs(reinterpret_cast<float4*>(grow + e0), make_float4(os[e0], os[e0 + 1], os[e0 + 2], os[e0 + 3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) grow[e0 + k] = os[e0 + k];
+      }
     } else {
 #pragma unroll
-      for (int k = 0; k < EPC; ++k) {
-        const int e = e0 + k;
-        if (e >= mis && e < mis + width) gbase[e] = os[e];
-      }
+      for (int k = 0; k < EPC; ++k)
+        if (e0 + k >= 0 && e0 + k < width) grow[e0 + k] = os[e0 + k];
     }
   }
 }
 
-// Async read of a global row into smem with the same alignment trick (dOut rows of the backward).
+// Async read of `width` elements of the global row `grow` into gs[mis .. mis+width) (16-byte chunks
+// line up on both sides; ragged ends go element-wise).
 template <typename T>
-__device__ __forceinline__ void load_row_aligned_async(const T* __restrict__ grow, T* gs, int mis, int width, int lane) {
+__device__ __forceinline__ void load_row_async(const T* __restrict__ grow, T* gs, int mis, int width, int lane) {
   constexpr int EPC = 16 / static_cast<int>(sizeof(T));
   const int nchunks = (mis + width + EPC - 1) / EPC;
   const T* gbase = grow - mis;
@@ -169,138 +178,147 @@ __device__ __forceinline__ void load_row_aligned_async(const T* __restrict__ gro
         const int e = e0 + k;
         if (e >= mis && e < mis + width) {
           if constexpr (sizeof(T) == 4) cp_async4(gs + e, gbase + e);
-          else gs[e] = gbase[e];  // bf16 rows are 16 B aligned in practice; plain copy keeps this correct anyway
+          else gs[e] = gbase[e];   // bf16 rows are 16 B aligned and padded in practice; this keeps odd layouts correct
         }
       }
     }
   }
 }
 
-template <typename T>
-__device__ __forceinline__ int misalign_elems(const T* p) {
-  return static_cast<int>((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
-}
-
 // ---- forward -----------------------------------------------------------------------------------------------
-// smem per warp: kIxStages x xs[32][D+8] fp32, then the staged output row (os_elems elements of OUT).
+// Z = X X^T is symmetric: only the 6 tiles (m-tile, n-tile) that touch the upper triangle are
+// computed; the self-interaction form (kept j <= i) reads element (j,i) instead.
+// smem per warp: kIxStages x xs[32][D+8] fp32 | 16 B trash slot | staged output row.
 template <int D, typename OUT>
-__global__ void __launch_bounds__(kIxWarps * 32, 1)
+__global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, int write_width, int os_bytes) {
   constexpr int STRIDE = D + 8;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
   constexpr int kXsFloats = 32 * STRIDE;
+  constexpr int kIxWarps = IxWarps<D>::value;
+  constexpr int kLanesPerRow = D / 4;
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * kXsFloats * 4 + os_bytes);
   float* xs_base = reinterpret_cast<float*>(my);
-  OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kXsFloats * 4);
+  OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kXsFloats * 4 + 16);   // row origin; [-16 B, 0) is the trash slot
 
-  // one-time init: rows >= F' of every stage and the whole output staging (pad columns stay zero)
-  for (int i = lane; i < kIxStages * kXsFloats / 4; i += 32) reinterpret_cast<float4*>(xs_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = lane; i < os_bytes / 16; i += 32) reinterpret_cast<float4*>(os)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // one-time init: rows >= F' of every stage stay zero; masked / pad columns of the staged row stay zero
+  for (int i = lane; i < (kIxStages * kXsFloats * 4 + os_bytes) / 16; i += 32) reinterpret_cast<float4*>(my)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kIxWarps;
   int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
   if (b >= a.B) return;
 
-  int64_t rows_cur = load_sample_rows(a, b, lane);
-  issue_rows<D, STRIDE>(a, b, rows_cur, xs_base, lane);
-  cp_async_commit();
-  int64_t rows_next = load_sample_rows(a, b + nwarps, lane);
-
   const int g = lane / 4, t2 = (lane % 4) * 2;
-  const int ntiles = (a.Fp + 7) / 8;   // n-tiles (and half m-tiles) that hold real features
+  const int F = a.F;
   const int total = a.ncols + (a.tail ? D : 0);
+  const int width = write_width > total ? write_width : total;
+
+  // where each accumulator element goes in the staged row (sample-independent):
+  // tile T = (mt, nt) in {(0,0),(0,1),(0,2),(0,3),(1,2),(1,3)}, element k: i = mt*16+g+(k/2)*8, j = nt*8+t2+(k%2)
+  constexpr int kTileM[6] = {0, 0, 0, 0, 1, 1};
+  constexpr int kTileN[6] = {0, 1, 2, 3, 2, 3};
+  int opos[6][4];
+#pragma unroll
+  for (int T = 0; T < 6; ++T)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = kTileM[T] * 16 + g + (k / 2) * 8;
+      const int j = kTileN[T] * 8 + t2 + (k % 2);
+      int pos = -static_cast<int>(16 / sizeof(OUT));             // trash slot
+      if (i < a.Fp && j < a.Fp) {
+        if (!a.self_interaction) {
+          if (j > i) pos = out_pos(i, j, a);
+        } else if (j >= i) {
+          pos = out_pos(j, i, a);                                // kept (row j, col i): Z[j][i] == Z[i][j]
+        }
+      }
+      opos[T][k] = pos;
+    }
+
+  const float* src_lane = (a.E != nullptr ? a.E : a.table) + (lane % kLanesPerRow) * 4;
+  const int sub = lane / kLanesPerRow;
+  const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
+  const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
+  const int64_t lane_off = (a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
+
+  uint32_t row_next = load_sample_row(a, b, lane, lane_off);
+  issue_rows<D, STRIDE>(src_lane, row_next, F, xs_base + dst_off, sub, dense_lane_on ? a.dense_vec + b * D + lane * 4 : nullptr,
+                        xs_base + F * STRIDE + lane * 4);
+  cp_async_commit();
+  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
     const int64_t bn = b + nwarps;
     float* xs = xs_base + stage * kXsFloats;
     if (bn < a.B) {
-      issue_rows<D, STRIDE>(a, bn, rows_next, xs_base + (stage ^ 1) * kXsFloats, lane);
-      rows_next = load_sample_rows(a, bn + nwarps, lane);   // in flight during this sample's math
+      float* xn = xs_base + (stage ^ 1) * kXsFloats;
+      issue_rows<D, STRIDE>(src_lane, row_next, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bn * D + lane * 4 : nullptr,
+                            xn + F * STRIDE + lane * 4);
+      row_next = load_sample_row(a, bn + nwarps, lane, lane_off);   // in flight during this sample's math
     }
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
 
-    float acc[2][4][4];
+    float acc[6][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int T = 0; T < 6; ++T)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0.f;
+      for (int k = 0; k < 4; ++k) acc[T][k] = 0.f;
 
 #pragma unroll
     for (int k0 = 0; k0 < D; k0 += 16) {
       uint32_t af[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        if (mt * 2 < ntiles) {
-          const float* p = xs + (mt * 16 + g) * STRIDE + k0 + t2;
-          const float2 v0 = *reinterpret_cast<const float2*>(p);
-          const float2 v1 = *reinterpret_cast<const float2*>(p + 8 * STRIDE);
-          const float2 v2 = *reinterpret_cast<const float2*>(p + 8);
-          const float2 v3 = *reinterpret_cast<const float2*>(p + 8 * STRIDE + 8);
-          af[mt][0] = pack_bf16(v0.x, v0.y);
-          af[mt][1] = pack_bf16(v1.x, v1.y);
-          af[mt][2] = pack_bf16(v2.x, v2.y);
-          af[mt][3] = pack_bf16(v3.x, v3.y);
-        } else {
-          af[mt][0] = af[mt][1] = af[mt][2] = af[mt][3] = 0u;
-        }
+        const float* p = xs + (mt * 16 + g) * STRIDE + k0 + t2;
+        const float2 v0 = *reinterpret_cast<const float2*>(p);
+        const float2 v1 = *reinterpret_cast<const float2*>(p + 8 * STRIDE);
+        const float2 v2 = *reinterpret_cast<const float2*>(p + 8);
+        const float2 v3 = *reinterpret_cast<const float2*>(p + 8 * STRIDE + 8);
+        af[mt][0] = pack_bf16(v0.x, v0.y);
+        af[mt][1] = pack_bf16(v1.x, v1.y);
+        af[mt][2] = pack_bf16(v2.x, v2.y);
+        af[mt][3] = pack_bf16(v3.x, v3.y);
       }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt < ntiles) {
-          // B[k][n] = X[n][k]: rows nt*8+g of X are rows (nt&1)*8+g of m-tile nt/2
-          const uint32_t b0 = af[nt / 2][(nt & 1) ? 1 : 0];
-          const uint32_t b1 = af[nt / 2][(nt & 1) ? 3 : 2];
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-            if (mt * 2 < ntiles) mma_bf16_16816(acc[mt][nt], af[mt], b0, b1);
-        }
+      for (int T = 0; T < 6; ++T) {
+        // B[k][n] = X[n][k]: rows nt*8+g of X are rows (nt&1)*8+g of m-tile nt/2
+        const int nt = kTileN[T];
+        mma_bf16_16816(acc[T], af[kTileM[T]], af[nt / 2][(nt & 1) ? 1 : 0], af[nt / 2][(nt & 1) ? 3 : 2]);
       }
     }
 
-    // epilogue: mask + placement into the staged output row (element e lives at os[mis + e])
-    OUT* grow = out + b * out_stride;
-    const int mis = misalign_elems(grow);
-    OUT* osr = os + mis;
+    // epilogue: kept elements to their columns of the staged row; everything else to the trash slot
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int T = 0; T < 6; ++T)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = mt * 16 + g + (k / 2) * 8;
-          const int j = nt * 8 + t2 + (k % 2);
-          if (i < a.Fp && j < a.Fp) {
-            const bool kp = kept(i, j, a.self_interaction);
-            if (a.skip_gather) osr[i * a.Fp + j] = Elem<OUT>::from(kp ? acc[mt][nt][k] : 0.f);
-            else if (kp) osr[compact_pos(i, j, a.Fp, a.self_interaction)] = Elem<OUT>::from(acc[mt][nt][k]);
-          }
-        }
+      for (int k = 0; k < 4; ++k) os[opos[T][k]] = Elem<OUT>::from(acc[T][k]);
     if (a.tail) {
-      for (int d = lane; d < D; d += 32) osr[a.ncols + d] = Elem<OUT>::from(xs[a.F * STRIDE + d]);
+      for (int d = lane; d < D; d += 32) os[a.ncols + d] = Elem<OUT>::from(xs[F * STRIDE + d]);
     }
     __syncwarp();
-    store_row_aligned<OUT>(grow, os, mis, write_width > total ? write_width : total, lane);
+    OUT* grow = out + b * out_stride;
+    store_row<OUT>(grow, os, misalign_elems(grow), width, lane);
     __syncwarp();   // os and xs[stage] are free again
-    rows_cur = rows_next;
     stage ^= 1;
   }
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------
-// smem per warp: kIxStages x { xs[32][D+4] fp32, gs[gs_bytes] staged dOut row }.
-template <int D, typename DOUT>
-__global__ void __launch_bounds__(kIxWarps * 32, 1)
+// dX = (G + G^T) X.  smem per warp: kIxStages x { xs[32][D+4] fp32 | 16 B of zeros | staged dOut row }.
+template <int D, typename DOUT, bool SELF>
+__global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
-                           float* __restrict__ d_dense, int gs_bytes) {
+                           float* __restrict__ d_dense, int copy_width, int gs_bytes) {
   constexpr int STRIDE = D + 4;  // floats; 2*(D+4) % 32 == 8 -> conflict-free 32-bit B-fragment loads
   constexpr int kXsFloats = 32 * STRIDE;
+  constexpr int kIxWarps = IxWarps<D>::value;
+  constexpr int kLanesPerRow = D / 4;
+  constexpr int EPC = 16 / static_cast<int>(sizeof(DOUT));
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int stage_bytes = kXsFloats * 4 + gs_bytes;
@@ -314,47 +332,63 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   if (b >= a.B) return;
 
   const int g = lane / 4, t2 = (lane % 4) * 2;
-  const int total = a.ncols + (a.tail ? D : 0);
-  const int ktiles = (a.Fp + 15) / 16;   // k-steps (and m-tiles) that hold real features
+  const int F = a.F;
 
-  // Per-lane offsets of the 32 S = G + G^T elements this lane feeds into the A fragments,
-  // sample-independent: element e = ((mt*2 + ks)*4 + reg)*2 + c  <->  S[i][j] with
+  // Offsets (elements, relative to the staged row's element 0) of the 32 S = G + G^T values this lane
+  // feeds into the A fragments: element e = ((mt*2 + ks)*4 + reg)*2 + c  <->  S[i][j],
   //   i = mt*16 + g + (reg & 1)*8,  j = ks*16 + t2 + c + (reg >> 1)*8.
-  // off == 0xFFFF: the element is zero.  dbl bit: diagonal of the self-interaction form (G + G^T doubles it).
-  uint32_t offp[16];
-  uint32_t dbl = 0;
+  // Zero entries point at the zero slot (-EPC: 16 B below the row in every alignment).
+  int aoff[32];
+  uint32_t diag = 0;   // SELF only: S[i][i] = 2*G[i][i]
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
     const int c = e & 1, reg = (e >> 1) & 3, ks = (e >> 3) & 1, mt = e >> 4;
     const int i = mt * 16 + g + (reg & 1) * 8;
     const int j = ks * 16 + t2 + c + (reg >> 1) * 8;
-    uint32_t off = 0xFFFFu;
+    int off = -EPC;
     if (i < a.Fp && j < a.Fp) {
       if (i == j) {
-        if (a.self_interaction) {
-          off = static_cast<uint32_t>(out_pos(i, i, a));
-          dbl |= (1u << e);
+        if (SELF) {
+          off = out_pos(i, i, a);
+          diag |= (1u << e);
         }
       } else {
         const int hi = i > j ? i : j, lo = i > j ? j : i;
-        off = static_cast<uint32_t>(a.self_interaction ? out_pos(hi, lo, a) : out_pos(lo, hi, a));
+        off = SELF ? out_pos(hi, lo, a) : out_pos(lo, hi, a);
       }
     }
-    if (c == 0) offp[e >> 1] = off;
-    else offp[e >> 1] |= off << 16;
+    aoff[e] = off;
   }
+  // which of this lane's 4 output rows are embedding rows / the dense row
+  bool is_emb[2][2], is_dense[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = mt * 16 + g + h * 8;
+      is_emb[mt][h] = (i < F) && dE != nullptr;
+      is_dense[mt][h] = (i == F) && a.dense_vec != nullptr && d_dense != nullptr;
+    }
 
-  auto issue = [&](int64_t bb, int64_t rows, int st) {
+  const float* src_lane = (a.E != nullptr ? a.E : a.table) + (lane % kLanesPerRow) * 4;
+  const int sub = lane / kLanesPerRow;
+  const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
+  const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
+  const int64_t lane_off = (a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
+
+  auto issue = [&](int64_t bb, uint32_t row, int st) {
     unsigned char* sp = my + st * stage_bytes;
-    issue_rows<D, STRIDE>(a, bb, rows, reinterpret_cast<float*>(sp), lane);
+    float* xn = reinterpret_cast<float*>(sp);
+    issue_rows<D, STRIDE>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
+                          xn + F * STRIDE + lane * 4);
     const DOUT* grow = dOut + bb * dout_stride;
-    load_row_aligned_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4), misalign_elems(grow), total, lane);
+    load_row_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4 + 16), misalign_elems(grow), copy_width, lane);
   };
 
-  int64_t rows_cur = load_sample_rows(a, b, lane);
-  issue(b, rows_cur, 0);
+  uint32_t row_next = load_sample_row(a, b, lane, lane_off);
+  issue(b, row_next, 0);
   cp_async_commit();
-  int64_t rows_next = load_sample_rows(a, b + nwarps, lane);
+  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
@@ -362,57 +396,54 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
     unsigned char* sp = my + stage * stage_bytes;
     const float* xs = reinterpret_cast<const float*>(sp);
     if (bn < a.B) {
-      issue(bn, rows_next, stage ^ 1);
-      rows_next = load_sample_rows(a, bn + nwarps, lane);
+      issue(bn, row_next, stage ^ 1);
+      row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
     }
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
 
-    const DOUT* gs = reinterpret_cast<const DOUT*>(sp + kXsFloats * 4) + misalign_elems(dOut + b * dout_stride);
+    // staged row element e lives at gs[e]
+    const DOUT* gs = reinterpret_cast<const DOUT*>(sp + kXsFloats * 4 + 16) + misalign_elems(dOut + b * dout_stride);
 
     // A = S as bf16 fragments [mt][ks][4]
     uint32_t af[2][2][4];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const uint32_t o0 = offp[q] & 0xFFFFu, o1 = offp[q] >> 16;
-      float v0 = (o0 != 0xFFFFu) ? Elem<DOUT>::to_f32(gs[o0]) : 0.f;
-      float v1 = (o1 != 0xFFFFu) ? Elem<DOUT>::to_f32(gs[o1]) : 0.f;
-      if (dbl & (1u << (2 * q))) v0 += v0;
-      if (dbl & (1u << (2 * q + 1))) v1 += v1;
+      float v0 = Elem<DOUT>::to_f32(gs[aoff[2 * q]]);
+      float v1 = Elem<DOUT>::to_f32(gs[aoff[2 * q + 1]]);
+      if (SELF) {
+        if (diag & (1u << (2 * q))) v0 += v0;
+        if (diag & (1u << (2 * q + 1))) v1 += v1;
+      }
       af[q >> 3][(q >> 2) & 1][q & 3] = pack_bf16(v0, v1);
     }
 
-#pragma unroll 2
+    float* de_lane = dE != nullptr ? dE + (b * F + g) * D + t2 : nullptr;
+#pragma unroll 4
     for (int nt = 0; nt < D / 8; ++nt) {
       float acc[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[mt][k] = 0.f;
-      const int n = nt * 8 + g;
+      const float* p = xs + t2 * STRIDE + nt * 8 + g;   // B[k][n] = X[k][n]: two consecutive feature rows per register
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        if (ks < ktiles) {
-          // B[k][n] = X[k][n]: two consecutive feature rows per register
-          const float* p = xs + (ks * 16 + t2) * STRIDE + n;
-          const uint32_t b0 = pack_bf16(p[0], p[STRIDE]);
-          const uint32_t b1 = pack_bf16(p[8 * STRIDE], p[9 * STRIDE]);
+        const uint32_t b0 = pack_bf16(p[ks * 16 * STRIDE], p[(ks * 16 + 1) * STRIDE]);
+        const uint32_t b1 = pack_bf16(p[(ks * 16 + 8) * STRIDE], p[(ks * 16 + 9) * STRIDE]);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-            if (mt < ktiles) mma_bf16_16816(acc[mt], af[mt][ks], b0, b1);
-        }
+        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(acc[mt], af[mt][ks], b0, b1);
       }
-      const int col = nt * 8 + t2;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int i = mt * 16 + g + h * 8;
           float2 v = make_float2(acc[mt][h * 2], acc[mt][h * 2 + 1]);
-          if (i < a.F) {
-            if (dE != nullptr) __stcs(reinterpret_cast<float2*>(dE + (b * a.F + i) * D + col), v);
-          } else if (i == a.F && a.dense_vec != nullptr && d_dense != nullptr) {
+          if (is_emb[mt][h]) {
+            __stcs(reinterpret_cast<float2*>(de_lane + (mt * 16 + h * 8) * D + nt * 8), v);
+          } else if (is_dense[mt][h]) {
+            const int col = nt * 8 + t2;
             if (a.tail) {
               v.x += Elem<DOUT>::to_f32(gs[a.ncols + col]);
               v.y += Elem<DOUT>::to_f32(gs[a.ncols + col + 1]);
@@ -422,7 +453,6 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
         }
     }
     __syncwarp();   // the stage may be overwritten by the next iteration's copies
-    rows_cur = rows_next;
     stage ^= 1;
   }
 }
@@ -439,8 +469,10 @@ static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows
     RB_CHECK_ARG(table != nullptr && idx != nullptr && rows > 0, RB_ERR_ARG, "fused gather needs table and idx");
     RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
     RB_CHECK_ARG(aligned_for(table, 4), RB_ERR_ALIGN, "table not 16 B aligned");
+    RB_CHECK_ARG(rows < 0xFFFFFFFFll, RB_ERR_ARG, "dot interaction addresses at most 2^32-2 table rows");
   } else {
     RB_CHECK_ARG(aligned_for(E, 4), RB_ERR_ALIGN, "E not 16 B aligned");
+    RB_CHECK_ARG(B * F < 0xFFFFFFFFll, RB_ERR_ARG, "B*F must be below 2^32-1");
   }
   RB_CHECK_ARG(dense_vec == nullptr || aligned_for(dense_vec, 4), RB_ERR_ALIGN, "dense_vec not 16 B aligned");
   a->E = E;
@@ -467,8 +499,8 @@ static int set_smem(K kernel, size_t bytes) {
   return RB_OK;
 }
 
-static unsigned int persistent_grid(int64_t B) {
-  const int64_t need = (B + kIxWarps - 1) / kIxWarps;
+static unsigned int persistent_grid(int64_t B, int warps) {
+  const int64_t need = (B + warps - 1) / warps;
   return static_cast<unsigned int>(need < kNumSMs ? (need < 1 ? 1 : need) : kNumSMs);
 }
 
@@ -477,15 +509,15 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
   // staged row: up to 15 bytes of misalignment + the widest row written, rounded to 16 B
   const int total = a.ncols + (a.tail ? D : 0);
   const int width = write_width > total ? write_width : total;
-  const int os_bytes = ((width * static_cast<int>(sizeof(OUT)) + 15 + 15) / 16) * 16;
-  const unsigned int grid = persistent_grid(a.B);
+  const int os_bytes = 16 + ((width * static_cast<int>(sizeof(OUT)) + 15) / 16) * 16;   // trash slot + staged row
   int rc = RB_OK;
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
-    size_t smem = static_cast<size_t>(kIxWarps) * (kIxStages * 32 * (DD + 8) * 4 + os_bytes);                           \
+    constexpr int W = IxWarps<DD>::value;                                                                               \
+    size_t smem = static_cast<size_t>(W) * (kIxStages * 32 * (DD + 8) * 4 + os_bytes);                                  \
     rc = set_smem(dot_interaction_fwd_kernel<DD, OUT>, smem);                                                           \
     if (rc != RB_OK) return rc;                                                                                         \
-    dot_interaction_fwd_kernel<DD, OUT><<<grid, kIxWarps * 32, smem, st>>>(a, out, out_stride, write_width, os_bytes);  \
+    dot_interaction_fwd_kernel<DD, OUT><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, out, out_stride, write_width, os_bytes); \
   }
   if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
 #undef LAUNCH
@@ -496,15 +528,27 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
 template <typename DOUT>
 static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_stride, float* dE, float* d_dense, cudaStream_t st) {
   const int total = a.ncols + (a.tail ? D : 0);
-  const int gs_bytes = ((total * static_cast<int>(sizeof(DOUT)) + 15 + 15) / 16) * 16;
-  const unsigned int grid = persistent_grid(a.B);
+  // copy whole 16-byte chunks when the row's padding allows it (no element-wise tail)
+  constexpr int EPC = 16 / static_cast<int>(sizeof(DOUT));
+  const int rounded = (total + EPC - 1) / EPC * EPC;
+  const int copy_width = (dout_stride >= rounded) ? rounded : total;
+  const int gs_bytes = 16 + ((copy_width * static_cast<int>(sizeof(DOUT)) + 15 + 15) / 16) * 16;   // zero slot + row at any alignment
   int rc = RB_OK;
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
-    size_t smem = static_cast<size_t>(kIxWarps) * kIxStages * (32 * (DD + 4) * 4 + gs_bytes);                           \
-    rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT>, smem);                                                          \
-    if (rc != RB_OK) return rc;                                                                                         \
-    dot_interaction_bwd_kernel<DD, DOUT><<<grid, kIxWarps * 32, smem, st>>>(a, dOut, dout_stride, dE, d_dense, gs_bytes); \
+    constexpr int W = IxWarps<DD>::value;                                                                               \
+    size_t smem = static_cast<size_t>(W) * kIxStages * (32 * (DD + 4) * 4 + gs_bytes);                                  \
+    if (a.self_interaction) {                                                                                           \
+      rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, true>, smem);                                                  \
+      if (rc != RB_OK) return rc;                                                                                       \
+      dot_interaction_bwd_kernel<DD, DOUT, true><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
+                                                                                                  d_dense, copy_width, gs_bytes); \
+    } else {                                                                                                            \
+      rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, false>, smem);                                                 \
+      if (rc != RB_OK) return rc;                                                                                       \
+      dot_interaction_bwd_kernel<DD, DOUT, false><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
+                                                                                                   d_dense, copy_width, gs_bytes); \
+    }                                                                                                                   \
   }
   if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
 #undef LAUNCH

@@ -99,12 +99,12 @@ class _InteractFn(torch.autograd.Function):
     """Lookup + DLRM concat + DotInteraction + '|| bmlp' tail in one kernel (ctr/model.py:49-55)."""
 
     @staticmethod
-    def forward(ctx, anchor, emb, idx, dense_vec, self_interaction, skip_gather, tail):
+    def forward(ctx, anchor, emb, idx, dense_vec, self_interaction, skip_gather, tail, out_dtype, pad_to):
         F = idx.shape[1]
         dense_vec = dense_vec.contiguous()
         out = ops.dot_interaction_fwd(table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
                                       dense_vec=dense_vec, self_interaction=self_interaction, skip_gather=skip_gather,
-                                      tail=tail)
+                                      tail=tail, out_dtype=out_dtype, pad_to=pad_to)
         ctx.emb, ctx.idx, ctx.flags = emb, idx, (self_interaction, skip_gather, tail)
         ctx.save_for_backward(dense_vec)
         return out
@@ -121,7 +121,7 @@ class _InteractFn(torch.autograd.Function):
                                               dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail)
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
-        return None, None, None, d_dense, None, None, None
+        return None, None, None, d_dense, None, None, None, None, None
 
 
 class _DotInteractionFn(torch.autograd.Function):
@@ -202,10 +202,13 @@ class Embedding(nn.Module):
         """(E[B,F,D], fm[B]) of ctr/model.py:19-23 in one pass over the rows."""
         return _GatherFMFn.apply(self._anchor, self, idx)
 
-    def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True):
+    def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
+                 out_dtype=torch.float32, pad_to=1):
         """ctr/model.py:49-55 fused: [DotInteraction([E ; dense_vec]) || dense_vec] with E read
-        straight from the table, so [B,F,D] and [B,F+1,D] never exist in HBM."""
-        return _InteractFn.apply(self._anchor, self, idx, dense_vec, self_interaction, skip_gather, tail)
+        straight from the table, so [B,F,D] and [B,F+1,D] never exist in HBM.  out_dtype=bfloat16
+        emits the row in bf16, zero-padded to a multiple of `pad_to` columns (the K operand of a
+        bf16 top MLP); its gradient then comes back in the same padded bf16 form."""
+        return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to)
 
     # -- optimizer side (called by optimizers.*.apply_gradients)
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,

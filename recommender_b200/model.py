@@ -68,6 +68,14 @@ class DLRM(nn.Module):
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :48
         bmlp_output = self.bottom_mlp(int_features)                                     # :50
         if self.fused:
+            width = (self.num_cat_fea + 1) ** 2 + self.embedding_size                                     # :55
+            if self.top_mlp.compute_dtype == torch.bfloat16:
+                # the fused kernel emits the top MLP's K operand directly: bf16, zero-padded to 8 columns
+                if len(self.top_mlp.kernels) == 0:
+                    self.top_mlp.build(width, bmlp_output.device)
+                tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
+                                                           out_dtype=torch.bfloat16, pad_to=8)          # :49,:51-55
+                return self.top_mlp(tmlp_input).squeeze(1)                                              # :56-57
             tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True)   # :49,:51-55
         else:
             cat_embedding = self.embedding_layer(cat_features)                          # :49

@@ -144,9 +144,21 @@ def interaction_ncols(Fp: int, self_interaction: bool, skip_gather: bool) -> int
     return Fp * (Fp + 1) // 2 if self_interaction else Fp * (Fp - 1) // 2
 
 
+def _float_type(dtype) -> int:
+    if dtype == torch.float32:
+        return _lib.RB_F32
+    if dtype == torch.bfloat16:
+        return _lib.RB_BF16
+    raise TypeError(f"interaction rows are float32 or bfloat16, got {dtype}")
+
+
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
-                        self_interaction=False, skip_gather=True, tail=False, out=None, out_stride=None):
-    """rb_dot_interaction_fwd.  Either E[B,F,D] or (table, idx[B,F]) supplies the embedding rows."""
+                        self_interaction=False, skip_gather=True, tail=False, out=None, out_stride=None,
+                        out_dtype=torch.float32, pad_to=1):
+    """rb_dot_interaction_fwd.  Either E[B,F,D] or (table, idx[B,F]) supplies the embedding rows.
+
+    out_dtype=torch.float32 returns the reference layout [B, ncols(+D)].  out_dtype=torch.bfloat16
+    returns [B, round_up(ncols(+D), pad_to)] in bf16 with zero pad columns (a GEMM-ready K operand)."""
     _need_cuda(E, table, idx, field_row_offset, dense_vec, out)
     if E is not None:
         _f32c(E, "E")
@@ -166,11 +178,13 @@ def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, 
     ncols = interaction_ncols(Fp, self_interaction, skip_gather)
     width = ncols + (D if tail else 0)
     if out is None:
-        out = torch.empty(B, width, dtype=torch.float32, device=dev)
-        out_stride = width
+        out_stride = (width + pad_to - 1) // pad_to * pad_to if out_dtype == torch.bfloat16 else width
+        out = torch.empty(B, out_stride, dtype=out_dtype, device=dev)
+    elif out.dtype != out_dtype:
+        raise TypeError("out.dtype must equal out_dtype")
     check(lib.rb_dot_interaction_fwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
-                                     B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(out), int(out_stride),
-                                     _stream()), "rb_dot_interaction_fwd")
+                                     B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(out),
+                                     _float_type(out_dtype), int(out_stride), _stream()), "rb_dot_interaction_fwd")
     return out
 
 
@@ -188,13 +202,14 @@ def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=
         B, F = idx.shape
         rows, D = table.shape
         it, dev = _idx(idx), table.device
-    if dOut.dtype != torch.float32 or dOut.stride(-1) != 1 or dOut.dim() != 2 or dOut.shape[0] != B:
-        raise ValueError("dOut must be float32 [B, cols] with unit inner stride")
+    if dOut.stride(-1) != 1 or dOut.dim() != 2 or dOut.shape[0] != B:
+        raise ValueError("dOut must be [B, cols] (float32 or bfloat16) with unit inner stride")
     dE = torch.empty(B, F, D, dtype=torch.float32, device=dev) if want_dE else None
     d_dense = torch.empty(B, D, dtype=torch.float32, device=dev) if dense_vec is not None else None
     check(lib.rb_dot_interaction_bwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
                                      B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(dOut),
-                                     int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _stream()), "rb_dot_interaction_bwd")
+                                     _float_type(dOut.dtype), int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _stream()),
+          "rb_dot_interaction_bwd")
     return dE, d_dense
 
 

@@ -57,13 +57,19 @@ def _X(E, table, idx, field_row_offset, dense_vec):
 
 
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None, self_interaction=False,
-                        skip_gather=True, tail=False, out=None, out_stride=None):
+                        skip_gather=True, tail=False, out=None, out_stride=None, out_dtype=torch.float32, pad_to=1):
     _launches[0] += 1
     X = _X(E, table, idx, field_row_offset, dense_vec)
     res = O.dot_interaction(X, self_interaction, skip_gather, operand_dtype="bf16")
     if tail:
         res = np.concatenate([res, dense_vec.detach().numpy()], axis=1)
-    return torch.tensor(res)
+    res = torch.tensor(res)
+    if out_dtype == torch.bfloat16:
+        width = res.shape[1]
+        padded = torch.zeros(res.shape[0], (width + pad_to - 1) // pad_to * pad_to, dtype=torch.bfloat16)
+        padded[:, :width] = res.to(torch.bfloat16)
+        return padded
+    return res
 
 
 def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None, self_interaction=False,
@@ -72,7 +78,7 @@ def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=
     X = _X(E, table, idx, field_row_offset, dense_vec)
     Fp = X.shape[1]
     ncols = interaction_ncols(Fp, self_interaction, skip_gather)
-    d = dOut.numpy()
+    d = dOut.float().numpy()
     dX = O.dot_interaction_backward(X, np.ascontiguousarray(d[:, :ncols]), self_interaction, skip_gather, operand_dtype="bf16")
     if dense_vec is None:
         return torch.tensor(dX), None

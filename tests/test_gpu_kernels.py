@@ -192,6 +192,74 @@ def test_dot_interaction_shapes(ops, D, F):
     np.testing.assert_array_equal(out[:, Fp * Fp:], dv)
 
 
+def test_interaction_bf16_rows_for_the_top_mlp(ops, golden):
+    """The bf16 form of the interaction row (what a bf16 top MLP consumes): the same values rounded
+    to bf16, zero pad columns up to a multiple of 8, and a backward that takes the padded bf16 dOut."""
+    g = golden("dlrm_uniform")
+    D = g["table"].shape[1]
+    B = g["cat"].shape[0]
+    bmlp = np.ascontiguousarray(g["X"][:, 26])
+    table, cat, dv = cu(g["table"]), cu(g["cat"]), cu(bmlp)
+    ref32 = ops.dot_interaction_fwd(table=table, idx=cat, dense_vec=dv, tail=True)
+    out = ops.dot_interaction_fwd(table=table, idx=cat, dense_vec=dv, tail=True, out_dtype=torch.bfloat16, pad_to=8)
+    width = 729 + D
+    stride = (width + 7) // 8 * 8
+    assert out.dtype == torch.bfloat16 and out.shape == (B, stride)
+    assert torch.equal(out[:, :width], ref32.to(torch.bfloat16))            # identical arithmetic, one final rounding
+    assert (out[:, width:] == 0).all()                                       # GEMM-ready pad columns
+    # backward with the padded bf16 gradient == backward with the same values in fp32
+    rng = np.random.default_rng(3)
+    dpad = torch.zeros(B, stride, dtype=torch.bfloat16, device="cuda")
+    dpad[:, :width] = cu(rng.normal(0, 1e-2, size=(B, width)).astype(np.float32)).to(torch.bfloat16)
+    dE_b, dd_b = ops.dot_interaction_bwd(dpad, table=table, idx=cat, dense_vec=dv, tail=True)
+    dE_f, dd_f = ops.dot_interaction_bwd(dpad[:, :width].float().contiguous(), table=table, idx=cat, dense_vec=dv, tail=True)
+    assert torch.equal(dE_b, dE_f) and torch.equal(dd_b, dd_f)
+    ref = O.dot_interaction_backward(g["X"], dpad[:, :729].float().cpu().numpy(), False, True, operand_dtype="bf16")
+    np.testing.assert_allclose(dE_b.cpu().numpy(), ref[:, :26], rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("B", [1, 7, 1184 * 2 + 5])
+def test_interaction_ragged_batches_and_unaligned_rows(ops, B):
+    """Persistent-grid edge cases: fewer samples than warps, a ragged last round, and fp32 rows whose
+    start is only 4-byte aligned (width 793 is odd), written into a strided output."""
+    rng = np.random.default_rng(B)
+    V, F, D = 500, 26, 64
+    W = O.init_table(rng, V, D)
+    idx = rng.integers(0, V, size=(B, F)).astype(np.int64)
+    dv = rng.normal(0, 0.1, size=(B, D)).astype(np.float32)
+    X = np.concatenate([W[idx], dv[:, None]], axis=1)
+    ref = O.dot_interaction(X, False, True, operand_dtype="bf16")
+    big = torch.full((B, 801), -7.0, device="cuda")
+    ops.dot_interaction_fwd(table=cu(W), idx=cu(idx), dense_vec=cu(dv), tail=True, out=big, out_stride=801)
+    got = big.cpu().numpy()
+    np.testing.assert_allclose(got[:, :729], ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(got[:, 729:793], dv)
+    assert (got[:, 793:] == -7.0).all()                                      # nothing outside the row is touched
+    dOut = rng.normal(0, 1e-2, size=(B, 793)).astype(np.float32)
+    dE, dd = ops.dot_interaction_bwd(cu(dOut), table=cu(W), idx=cu(idx), dense_vec=cu(dv), tail=True)
+    refd = O.dot_interaction_backward(X, np.ascontiguousarray(dOut[:, :729]), False, True, operand_dtype="bf16")
+    tol = dict(rtol=1e-4, atol=1e-4 * np.abs(refd).max())
+    np.testing.assert_allclose(dE.cpu().numpy(), refd[:, :26], **tol)
+    np.testing.assert_allclose(dd.cpu().numpy(), refd[:, 26] + dOut[:, 729:], **tol)
+
+
+def test_interaction_out_of_range_ids_read_zero_rows(ops):
+    """TF's GPU gather writes zeros for out-of-range ids; the fused form must agree with
+    interaction over the zero-filled E."""
+    rng = np.random.default_rng(9)
+    V, F, D, B = 50, 26, 32, 33
+    W = O.init_table(rng, V, D)
+    idx = rng.integers(0, V, size=(B, F)).astype(np.int64)
+    idx[3, 5], idx[10, 0] = V, -1
+    dv = rng.normal(0, 0.1, size=(B, D)).astype(np.float32)
+    E = ops.gather_fwd(cu(W), cu(idx))
+    torch.cuda.synchronize()
+    ops.oob_flag("cuda").zero_()
+    a = ops.dot_interaction_fwd(table=cu(W), idx=cu(idx), dense_vec=cu(dv), tail=True)
+    b = ops.dot_interaction_fwd(E=E, dense_vec=cu(dv), tail=True)
+    assert torch.equal(a, b)
+
+
 # ---- K7..K9: backward scatter + sparse optimizers -----------------------------------------------------------
 
 def _state(kind, W):
