@@ -11,7 +11,7 @@ import os
 import re
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "librecsys_b200.so")
+LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(PKG, "lib", "librecsys_b200.so")   # RB_LIB_PATH: tuning builds
 HEADER = os.path.join(os.path.dirname(PKG), "include", "recsys_b200.h")
 
 RB_MAX_GRAD_SOURCES = 16

@@ -43,8 +43,32 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines) -> str:
+    """Tuning aid: lib/librecsys_b200_<name>.so compiled with extra -D flags (picked up through the
+    RB_LIB_PATH environment variable by _lib.py).  Not used by the product path."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, f"librecsys_b200_{name}.so")
+    objs, procs = [], []
+    for src in _sources():
+        obj = os.path.join(LIB_DIR, f"{name}_" + os.path.basename(src).replace(".cu", ".o"))
+        procs.append(subprocess.Popen([_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines],
+                                       "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        objs.append(obj)
+    for p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(o)
+    subprocess.run([_nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+                    "-lpthread", "-ldl", "-lrt"], check=True)
+    for o in objs:
+        os.remove(o)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
+    if os.environ.get("RB_LIB_PATH"):
+        return os.environ["RB_LIB_PATH"]
     fp = _fingerprint()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
         return LIB_PATH
@@ -78,5 +102,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", help="name of a tuning build (lib/librecsys_b200_<name>.so)")
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build_variant(a.variant, a.defines) if a.variant else build(a.force, a.verbose))

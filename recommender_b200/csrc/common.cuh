@@ -157,6 +157,33 @@ __device__ __forceinline__ Row<VEC> zero_row() {
   return r;
 }
 
+// ---- cp.async (LDGSTS): global -> shared copies that hold no registers while in flight ----------------
+__device__ __forceinline__ uint32_t smem_u32addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// 16-byte copy, L2 only; src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+}
+// VEC floats per thread (16 / 8 / 4 bytes)
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(float* dst, const float* src) {
+  if constexpr (VEC == 4) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+  } else if constexpr (VEC == 2) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- index decoding --------------------------------------------------------------------------
 // Folds (optional) the id with uint64 mod, adds the per-field row offset, range-checks.
 struct IndexMap {

@@ -27,6 +27,10 @@ constexpr int kTile = 32;         // sorted entries per group
 constexpr int kSegThreads = 256;  // CTA size of the reduction kernels
 constexpr int kChunk = 4;         // gradient rows in flight per group
 constexpr int kLongChain = 64;    // tiles; longer chains go to the CTA-wide kernel
+#ifndef RB_SEG_RING
+#define RB_SEG_RING 3
+#endif
+constexpr int kRing = RB_SEG_RING;  // sorted entries in flight per lane (cp.async ring in shared memory)
 
 struct GradSrcDev {
   int num_src, scale_mode, L, is64;
@@ -54,19 +58,37 @@ struct LongChain {
 };
 
 // ---- gradient row of one lookup position ----------------------------------------------------------
-template <int VEC>
-__device__ __forceinline__ Row<VEC> load_grad(const GradGroupsDev& gg, uint32_t p, uint32_t row, int lane) {
-  int gi = 0;
+// Where position p's gradient lives: which use of the table (group), which bag, which slot of the bag.
+struct GradPos {
+  int gi;
+  uint32_t p, b, l;   // p: position inside the group
+};
+
+__device__ __forceinline__ GradPos decode_pos(const GradGroupsDev& gg, uint32_t p) {
+  GradPos q;
+  q.gi = 0;
 #pragma unroll
-  for (int k = 1; k < RB_MAX_LOOKUP_GROUPS; ++k) gi += (p >= gg.start[k]) ? 1 : 0;
-  const GradSrcDev& g = gg.g[gi];
-  p -= gg.start[gi];
-  const uint32_t b = p / static_cast<uint32_t>(g.L);
-  const uint32_t l = p - b * static_cast<uint32_t>(g.L);
-  const int c = lane * VEC;
-  Row<VEC> r = ld_row_stream<VEC>(g.src[0] + b * g.bag_stride[0] + l * g.pos_stride[0] + c);
+  for (int k = 1; k < RB_MAX_LOOKUP_GROUPS; ++k) q.gi += (p >= gg.start[k]) ? 1 : 0;
+  const uint32_t L = static_cast<uint32_t>(gg.g[q.gi].L);
+  q.p = p - gg.start[q.gi];
+  q.b = q.p / L;
+  q.l = q.p - q.b * L;
+  return q;
+}
+
+// address of the first source's row for this lane's columns (the part fetched by cp.async)
+__device__ __forceinline__ const float* grad_src0(const GradGroupsDev& gg, const GradPos& q, int c) {
+  const GradSrcDev& g = gg.g[q.gi];
+  return g.src[0] + q.b * g.bag_stride[0] + q.l * g.pos_stride[0] + c;
+}
+
+// r = the first source's row (already loaded); adds the other consumers, the mean / masked-mean scaling
+// and the FM term (w = this lane's slice of W[row,:], read before any update of that row)
+template <int VEC>
+__device__ __forceinline__ void finish_grad(const GradGroupsDev& gg, const GradPos& q, int c, Row<VEC>& r, const float* w) {
+  const GradSrcDev& g = gg.g[q.gi];
   for (int k = 1; k < g.num_src; ++k) {  // consumers are added left to right (esmm/esmm.py:23-24)
-    Row<VEC> t = ld_row_stream<VEC>(g.src[k] + b * g.bag_stride[k] + l * g.pos_stride[k] + c);
+    Row<VEC> t = ld_row_stream<VEC>(g.src[k] + q.b * g.bag_stride[k] + q.l * g.pos_stride[k] + c);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], t.v[i]);
   }
@@ -75,19 +97,17 @@ __device__ __forceinline__ Row<VEC> load_grad(const GradGroupsDev& gg, uint32_t 
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = __fdiv_rn(r.v[i], denom);
   } else if (g.scale_mode == RB_SCALE_MASKED_MEAN) {
-    const bool keep = load_raw_index(g.mask_idx, g.is64, p) != 0;
-    const float denom = __ldg(g.count + b);
+    const bool keep = load_raw_index(g.mask_idx, g.is64, q.p) != 0;
+    const float denom = __ldg(g.count + q.b);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = keep ? __fdiv_rn(r.v[i], denom) : 0.f;
   }
   if (g.fm_g != nullptr) {  // dE += g_fm[b] * (s[b,:] - W[row,:])      (ctr/model.py:21-23 backward)
-    const float gb = __ldg(g.fm_g + b);
-    Row<VEC> s = ld_row<VEC>(g.fm_s + static_cast<int64_t>(b) * gg.D + c);
-    Row<VEC> w = ld_row_rw<VEC>(gg.table + static_cast<int64_t>(row) * gg.D + c);
+    const float gb = __ldg(g.fm_g + q.b);
+    Row<VEC> sv = ld_row<VEC>(g.fm_s + static_cast<int64_t>(q.b) * gg.D + c);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(gb, __fsub_rn(s.v[i], w.v[i])));
+    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(gb, __fsub_rn(sv.v[i], w[i])));
   }
-  return r;
 }
 
 // ---- sinks ----------------------------------------------------------------------------------------
@@ -99,11 +119,36 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
   int opt;  // rb_optimizer, RB_OPT_ADAM_TF_DENSE = scatter-add phase only
   float lr, b1, b2, omb1, omb2, eps, alpha;
 
+  static constexpr int kStateRows = 3;  // ring slots per entry after the gradient: W, state0, state1
+
+  // Start the async copies of this lane's slices of W / state rows into its ring slots
+  // (slot k at st + k*kstride).  update: the entry closes a run this tile owns; need_w: FM term.
   template <int VEC>
-  __device__ __forceinline__ void apply(uint32_t row, const Row<VEC>& g, int lane, uint32_t /*seg_first*/) const {
+  __device__ __forceinline__ void issue_state(uint32_t row, int c, bool update, bool need_w, float* st, int kstride) const {
+    const int64_t o = static_cast<int64_t>(row) * D + c;
+    if ((update && opt != RB_OPT_ADAM_TF_DENSE) || need_w) cp_async_vec<VEC>(st, table + o);
+    if (update && opt != RB_OPT_SGD) cp_async_vec<VEC>(st + kstride, s0 + o);
+    if (update && (opt == RB_OPT_ADAM_LAZY || opt == RB_OPT_ADAM_TF_DENSE)) cp_async_vec<VEC>(st + 2 * kstride, s1 + o);
+  }
+
+  // the row update with W / state slices already in shared memory (same arithmetic as apply())
+  template <int VEC>
+  __device__ __forceinline__ void apply_staged(uint32_t row, const Row<VEC>& g, int lane, uint32_t /*seg_first*/, const float* st,
+                                               int kstride) const {
     const int64_t o = static_cast<int64_t>(row) * D + lane * VEC;
+    Row<VEC> w, m, v;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      w.v[i] = st[i];
+      m.v[i] = st[kstride + i];
+      v.v[i] = st[2 * kstride + i];
+    }
+    update_row<VEC>(o, g, w, m, v);
+  }
+
+  template <int VEC>
+  __device__ __forceinline__ void update_row(int64_t o, const Row<VEC>& g, Row<VEC>& w, Row<VEC>& m, Row<VEC>& v) const {
     if (opt == RB_OPT_ADAM_LAZY) {
-      Row<VEC> w = ld_row_rw<VEC>(table + o), m = ld_row_rw<VEC>(s0 + o), v = ld_row_rw<VEC>(s1 + o);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         m.v[i] = __fadd_rn(__fmul_rn(m.v[i], b1), __fmul_rn(g.v[i], omb1));
@@ -114,7 +159,6 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
       st_row<VEC>(s1 + o, v);
       st_row<VEC>(table + o, w);
     } else if (opt == RB_OPT_ADAM_TF_DENSE) {
-      Row<VEC> m = ld_row_rw<VEC>(s0 + o), v = ld_row_rw<VEC>(s1 + o);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], omb1));
@@ -122,21 +166,30 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
       }
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(s1 + o, v);
-    } else if (opt == RB_OPT_ADAGRAD) {
-      Row<VEC> w = ld_row_rw<VEC>(table + o), a = ld_row_rw<VEC>(s0 + o);
+    } else if (opt == RB_OPT_ADAGRAD) {   // accumulator in slot 1 (m)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        a.v[i] = __fadd_rn(a.v[i], __fmul_rn(g.v[i], g.v[i]));
-        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(lr, g.v[i]), __fadd_rn(__fsqrt_rn(a.v[i]), eps)));
+        m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], g.v[i]));
+        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(lr, g.v[i]), __fadd_rn(__fsqrt_rn(m.v[i]), eps)));
       }
-      st_row<VEC>(s0 + o, a);
+      st_row<VEC>(s0 + o, m);
       st_row<VEC>(table + o, w);
     } else {  // SGD
-      Row<VEC> w = ld_row_rw<VEC>(table + o);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) w.v[i] = __fsub_rn(w.v[i], __fmul_rn(lr, g.v[i]));
       st_row<VEC>(table + o, w);
     }
+  }
+
+  // the row update straight from global memory (chain kernels)
+  template <int VEC>
+  __device__ __forceinline__ void apply(uint32_t row, const Row<VEC>& g, int lane, uint32_t /*seg_first*/) const {
+    const int64_t o = static_cast<int64_t>(row) * D + lane * VEC;
+    Row<VEC> w = zero_row<VEC>(), m = zero_row<VEC>(), v = zero_row<VEC>();
+    if (opt != RB_OPT_ADAM_TF_DENSE) w = ld_row_rw<VEC>(table + o);
+    if (opt != RB_OPT_SGD) m = ld_row_rw<VEC>(s0 + o);
+    if (opt == RB_OPT_ADAM_LAZY || opt == RB_OPT_ADAM_TF_DENSE) v = ld_row_rw<VEC>(s1 + o);
+    update_row<VEC>(o, g, w, m, v);
   }
 };
 
@@ -145,6 +198,16 @@ struct DedupSink {  // writes the deduplicated IndexedSlices (rows ascending)
   int64_t* uniq_rows;
   float* uniq_grad;
   int D;
+
+  static constexpr int kStateRows = 0;
+
+  template <int VEC>
+  __device__ __forceinline__ void issue_state(uint32_t, int, bool, bool, float*, int) const {}
+
+  template <int VEC>
+  __device__ __forceinline__ void apply_staged(uint32_t row, const Row<VEC>& g, int lane, uint32_t seg_first, const float*, int) const {
+    apply<VEC>(row, g, lane, seg_first);
+  }
 
   template <int VEC>
   __device__ __forceinline__ void apply(uint32_t row, const Row<VEC>& g, int lane, uint32_t seg_first) const {
@@ -178,14 +241,23 @@ __global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, in
 }
 
 // ---- step 2: tiles -------------------------------------------------------------------------------------
+// Every lane runs a private kRing-deep pipeline over ITS columns of the tile's entries: the gradient
+// row slice (and, for an entry that closes a run owned by this tile, the W / state row slices) are
+// fetched with cp.async into the lane's ring slots, so up to kRing entries x 4 rows are in flight per
+// lane without holding registers; a lane only ever reads back the bytes it copied itself, so no
+// cross-lane synchronisation is needed.  dynamic smem: ring[kRing][1 + Sink::kStateRows][kSegThreads][VEC].
 template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradGroupsDev gsrc,
                         Sink sink, float* __restrict__ head_part, float* __restrict__ tail_part) {
   constexpr int kGroups = kSegThreads / GS;
   constexpr int kEntries = kGroups * kTile;
+  constexpr int kKinds = 1 + Sink::kStateRows;
+  constexpr int kKStride = kSegThreads * VEC;        // floats between the kinds of one ring slot
+  constexpr int kSlotStride = kKinds * kKStride;     // floats between ring slots
   __shared__ uint32_t s_key[kEntries + 2];  // [0] = key before the CTA's range, [kEntries+1] = key after
   __shared__ uint32_t s_pos[kEntries];
+  extern __shared__ __align__(16) float ring[];
 
   const int cta_base = blockIdx.x * kEntries;
   const int cta_cnt = min(kEntries, n - cta_base);
@@ -207,57 +279,77 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
   const int tcnt = min(kTile, cta_cnt - tbase);    // entries of this tile (<= 0: idle group)
   if (tcnt <= 0) return;
   const bool active = lane * VEC < gsrc.D;
+  const int c = lane * VEC;
   const int gbase = cta_base + tbase;              // global sorted index of the tile's first entry
   const int tile_id = gbase / kTile;
   const bool has_prev = gbase > 0;
   const bool has_next = gbase + tcnt < n;
   const uint32_t* tk = s_key + 1 + tbase;          // tk[-1] and tk[tcnt] are the neighbours
   const uint32_t* tp = s_pos + tbase;
+  const uint32_t first_key = tk[0];
+  const bool cont_first = has_prev && (tk[-1] == first_key);   // the leading run started in an earlier tile
+  float* my_ring = ring + threadIdx.x * VEC;
+
+  auto run_ends_at = [&](int j, uint32_t key) {
+    return (j == tcnt - 1) ? !(has_next && tk[tcnt] == key) : (tk[j + 1] != key);
+  };
+  auto issue = [&](int j, int slot) {
+    if (j < tcnt && active) {
+      const uint32_t key = tk[j];
+      const GradPos q = decode_pos(gsrc, tp[j]);
+      float* dst = my_ring + slot * kSlotStride;
+      cp_async_vec<VEC>(dst, grad_src0(gsrc, q, c));
+      if (kKinds > 1) {
+        const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
+        sink.template issue_state<VEC>(key, c, update, gsrc.g[q.gi].fm_g != nullptr, dst + kKStride, kKStride);
+      }
+    }
+    cp_async_commit();   // one group per entry, also when nothing was copied: keeps wait_group uniform
+  };
 
   Row<VEC> acc = zero_row<VEC>();
-  uint32_t cur = tk[0];
+  uint32_t cur = first_key;
   int seg_start = 0;
-  bool continues_prev = has_prev && (tk[-1] == cur);  // the leading run started in an earlier tile
+  bool continues_prev = cont_first;
+#pragma unroll
+  for (int j = 0; j < kRing - 1; ++j) issue(j, j);
 
-  for (int j0 = 0; j0 < tcnt; j0 += kChunk) {
-    Row<VEC> g[kChunk];
-    uint32_t key[kChunk];
+  int slot = 0;
+  for (int j = 0; j < tcnt; ++j) {
+    {
+      int s_issue = slot + (kRing - 1);
+      if (s_issue >= kRing) s_issue -= kRing;
+      issue(j + kRing - 1, s_issue);
+    }
+    cp_async_wait<kRing - 1>();
+    const uint32_t key = tk[j];
+    const float* sl = my_ring + slot * kSlotStride;
+    Row<VEC> g = zero_row<VEC>();
+    if (active) {
 #pragma unroll
-    for (int u = 0; u < kChunk; ++u) {
-      const int j = j0 + u;
-      g[u] = zero_row<VEC>();
-      key[u] = 0;
-      if (j < tcnt) {
-        key[u] = tk[j];
-        if (active) g[u] = load_grad<VEC>(gsrc, tp[j], key[u], lane);
-      }
+      for (int i = 0; i < VEC; ++i) g.v[i] = sl[i];
+      finish_grad<VEC>(gsrc, decode_pos(gsrc, tp[j]), c, g, sl + kKStride);
+    }
+    if (key != cur) {  // previous run was closed below; start a new one
+      cur = key;
+      acc = zero_row<VEC>();
+      seg_start = j;
+      continues_prev = false;
     }
 #pragma unroll
-    for (int u = 0; u < kChunk; ++u) {
-      const int j = j0 + u;
-      if (j < tcnt) {
-        if (key[u] != cur) {  // previous run was closed below; start a new one
-          cur = key[u];
-          acc = zero_row<VEC>();
-          seg_start = j;
-          continues_prev = false;
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], g[u].v[i]);
-        const bool last_in_tile = (j == tcnt - 1);
-        const bool run_ends = last_in_tile ? !(has_next && tk[tcnt] == cur) : (tk[j + 1] != cur);
-        if (run_ends) {
-          if (continues_prev) {
-            if (active) st_row<VEC>(head_part + static_cast<int64_t>(tile_id) * gsrc.D + lane * VEC, acc);
-          } else if (active) {
-            sink.template apply<VEC>(cur, acc, lane, static_cast<uint32_t>(gbase + seg_start));
-          }
-        } else if (last_in_tile && active) {  // run goes on in the next tile
-          float* dst = continues_prev ? head_part : tail_part;
-          st_row<VEC>(dst + static_cast<int64_t>(tile_id) * gsrc.D + lane * VEC, acc);
-        }
+    for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], g.v[i]);
+    const bool last_in_tile = (j == tcnt - 1);
+    if (run_ends_at(j, cur)) {
+      if (continues_prev) {
+        if (active) st_row<VEC>(head_part + static_cast<int64_t>(tile_id) * gsrc.D + c, acc);
+      } else if (active) {
+        sink.template apply_staged<VEC>(cur, acc, lane, static_cast<uint32_t>(gbase + seg_start), sl + kKStride, kKStride);
       }
+    } else if (last_in_tile && active) {  // run goes on in the next tile
+      float* dst = continues_prev ? head_part : tail_part;
+      st_row<VEC>(dst + static_cast<int64_t>(tile_id) * gsrc.D + c, acc);
     }
+    if (++slot == kRing) slot = 0;
   }
 }
 
@@ -465,7 +557,12 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
 #define CALL(V, G)                                                                                                      \
   {                                                                                                                     \
     constexpr int kGroups = kSegThreads / G;                                                                            \
-    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, vals, n, gsrc, sink, head, tail); \
+    const size_t ring_bytes = static_cast<size_t>(kRing) * (1 + Sink::kStateRows) * kSegThreads * V * sizeof(float);   \
+    if (ring_bytes > 40 * 1024)                                                                                         \
+      RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                   static_cast<int>(ring_bytes)));                                                      \
+    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, gsrc, sink, \
+                                                                                                    head, tail);        \
     seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, gsrc.D, sink, head, tail, ll, lc, cap); \
     seg_long_chain_kernel<V, G, Sink><<<2 * kNumSMs, kSegThreads, 0, st>>>(gsrc.D, sink, head, tail, ll, lc, cap);      \
   }

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark at BASELINE config 2 shapes (B=65536, F=26, D=64, 26 x 1M rows): times each
+C-ABI call with CUDA events on the launching stream, inputs larger than L2 (6.7 GB tables, a ring of
+batches).  Used for tuning; `RB_LIB_PATH` selects a variant build (recommender_b200/build.py --variant).
+
+    python scripts/kbench.py [--ops fwd,bwd,update,gather] [--iters 20] [--tables 26] [--dist uniform|zipf]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recommender_b200 import ops  # noqa: E402
+from recommender_b200.ops import GradSource, LookupGroup  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="fwd,bwd,update")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--tables", type=int, default=26)
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--dist", default="uniform")
+    ap.add_argument("--optimizer", default="adam_lazy")
+    ap.add_argument("--tag", default=os.environ.get("RB_LIB_PATH", "default"))
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    B, F, D, V, T = a.batch, 26, a.dim, a.rows, a.tables
+    g = torch.Generator(device=dev).manual_seed(4)
+    table = torch.empty(V * T, D, device=dev).uniform_(-0.05, 0.05, generator=g)
+    m, v = torch.zeros_like(table), torch.zeros_like(table)
+    off = torch.arange(T, device=dev, dtype=torch.int64) * V if T > 1 else None
+    ring = []
+    for i in range(4):
+        if a.dist == "uniform":
+            cat = torch.randint(0, V, (B, F), device=dev, generator=g)
+        else:
+            u = torch.rand(B, F, device=dev, dtype=torch.float64, generator=g).clamp_(min=1e-12)
+            cat = (u.pow(-1.0 / 0.05).clamp_(max=2.0 ** 62).to(torch.int64) % V)
+            cat[torch.rand(B, F, device=dev, generator=g) < 0.02] = 0
+        ring.append(cat)
+    dense = torch.randn(B, D, device=dev, generator=g) * 0.1
+    width = 27 * 27 + D
+    stride = (width + 7) // 8 * 8
+    dout = (torch.randn(B, stride, device=dev, generator=g) * 1e-3).to(torch.bfloat16)
+    dE = torch.randn(B, F, D, device=dev, generator=g) * 1e-3
+    out = torch.empty(B, stride, device=dev, dtype=torch.bfloat16)
+    res = {}
+
+    def timeit(name, fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(a.iters):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        ts = sorted(s.elapsed_time(e) * 1e3 for s, e in evs)
+        res[name] = dict(us_median=ts[len(ts) // 2], us_min=ts[0], us_mean=sum(ts) / len(ts))
+
+    which = a.ops.split(",")
+    if "fwd" in which:
+        timeit("fwd", lambda i: ops.dot_interaction_fwd(table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True,
+                                                        out=out, out_stride=stride, out_dtype=torch.bfloat16))
+    if "bwd" in which:
+        timeit("bwd", lambda i: ops.dot_interaction_bwd(dout, table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True))
+    if "gather" in which:
+        timeit("gather", lambda i: ops.gather_fwd(table, ring[i % 4], L=F, field_row_offset=off))
+    if "update" in which:
+        step = [0]
+
+        def upd(i):
+            step[0] += 1
+            grp = LookupGroup(ring[i % 4], F, GradSource.per_position(dE, F), field_row_offset=off)
+            ops.sparse_bwd_update(table, m, v if a.optimizer.startswith("adam") else None, [grp], optimizer=a.optimizer, step=step[0])
+        timeit("update", upd)
+    print(json.dumps(dict(tag=a.tag, tables=T, dist=a.dist, **res)))
+
+
+if __name__ == "__main__":
+    main()
