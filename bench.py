@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--cpu-sample-batch", type=int, default=8192)
     ap.add_argument("--ref-adam", default="tf_dense", choices=["tf_dense", "lazy"],
                     help="Adam semantics of the CPU reference arm: Keras' dense passes (what the reference runs) or lazy")
@@ -261,9 +262,10 @@ def run_b200(args):
         loss = bce_clipped(prob, label)
         loss.backward()
         opt.apply_gradients(model)
-        return loss
+        return loss.detach()       # no reference to the autograd graph survives the step (CUDA-graph capture needs that)
 
-    timer = CallTimer(ops, ["dot_interaction_fwd", "dot_interaction_bwd", "sparse_bwd_update", "gather_fwd", "bucket_by_owner"])
+    timer = CallTimer(ops, ["dot_interaction_fwd", "dot_interaction_bwd", "sparse_bwd_update", "sparse_bwd_prepare", "sparse_bwd_apply",
+                            "gather_fwd", "bucket_by_owner", "dense_opt_step", "colsum"])
     timer.install()
 
     def barrier():
@@ -283,21 +285,44 @@ def run_b200(args):
     float(loss.item())
     ops.check_oob(dev)
 
+    # ---- eager pass: every C-ABI call bracketed by CUDA events on its launching stream (kernel table, roofline) ----
+    k_eager = min(args.steps, 10)
+    barrier()
+    launches0 = ops.kernel_launches()
+    timer.enabled = True
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(k_eager):
+        loss = train_step(resident[i % args.ring])
+    g1.record()
+    barrier()
+    timer.enabled = False
+    launches_per_step = (ops.kernel_launches() - launches0) / k_eager
+    eager_ms_step = max_over_ranks(g0.elapsed_time(g1)) / k_eager
+
+    # ---- the step as one CUDA graph (single GPU; the sharded step has host-side exchange counts) --------------
+    use_graph = (world == 1) and not args.no_graph
+    if use_graph:
+        from recommender_b200.graph import GraphedTrainStep
+        del loss
+        graphed = GraphedTrainStep(model, opt, bce_clipped, resident[0], warmup=max(args.warmup, 3))
+        train_step = graphed.step
+        for i in range(3):
+            loss = train_step(resident[i % args.ring])
+        float(loss.item())
+
     # ---- value: inputs resident in HBM ---------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     barrier()
-    launches0 = ops.kernel_launches()
-    timer.enabled = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         loss = train_step(resident[i % args.ring])
     e1.record()
     barrier()
-    timer.enabled = False
-    launches = ops.kernel_launches() - launches0
+    launches = int(round(launches_per_step * args.steps))      # the graph replays exactly the eager step's kernels
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -348,7 +373,9 @@ def run_b200(args):
         e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), 0.0)) / args.steps
         e2e = dict(value=B * world / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                    ms_per_step=e2e_ms, wall_ms_per_step=wall_ms / args.steps,
-                   api="DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients on batches staged from pinned host memory")
+                   api=("GraphedTrainStep.step (one CUDA graph: DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients)"
+                        if use_graph else "DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients")
+                       + " on batches staged from pinned host memory")
 
     # ---- roofline of the dominant C-ABI call -------------------------------------------------------------
     calls = timer.summary()
@@ -367,6 +394,8 @@ def run_b200(args):
         "dot_interaction_bwd": B * row_bytes + N * D * 4 + N * 8 + B * D * 4 + N * D * 4 + B * D * 4,
         # N*D*4 (dE) + N*idxB + U*D*4*6 (read+write of var, m, v)
         "sparse_bwd_update": N * D * 4 + N * 8 + U * D * 4 * 6,
+        # the same bytes when keys + radix sort ran ahead on the side stream (rb_sparse_bwd_prepare, overlapped with the forward)
+        "sparse_bwd_apply": N * D * 4 + N * 8 + U * D * 4 * 6,
     }
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -381,18 +410,20 @@ def run_b200(args):
     for name, (ms, cnt) in calls.items():
         if name in algo and world == 1:
             gbs = algo[name] / (ms * 1e-3) / 1e9
-            kernels[name] = dict(ms=ms, calls_per_step=cnt / args.steps, algorithmic_bytes=algo[name], achieved_gbs=gbs,
-                                 frac=gbs / peak, share_of_step=ms * cnt / args.steps / ms_step)
+            kernels[name] = dict(ms=ms, calls_per_step=cnt / k_eager, algorithmic_bytes=algo[name], achieved_gbs=gbs,
+                                 frac=gbs / peak, share_of_step=ms * cnt / k_eager / ms_step)
         else:
-            kernels[name] = dict(ms=ms, calls_per_step=cnt / args.steps, share_of_step=ms * cnt / args.steps / ms_step)
+            kernels[name] = dict(ms=ms, calls_per_step=cnt / k_eager, share_of_step=ms * cnt / k_eager / ms_step)
     roofline = None
     timed = {k: v for k, v in kernels.items() if "achieved_gbs" in v}
     if timed:
         top = max(timed, key=lambda k: timed[k]["ms"] * timed[k]["calls_per_step"])
         roofline = dict(bound="hbm", kernel=top, achieved=timed[top]["achieved_gbs"], peak=peak, unit="GB/s", frac=timed[top]["frac"],
                         traffic=traffic.get(top), peak_source=peak_src, unique_rows=U,
-                        note="achieved = algorithmic bytes of the whole C-ABI call / its CUDA-event time; for sparse_bwd_update the "
-                             "time includes key generation and the radix sort (overhead, not algorithmic bytes)")
+                        note="achieved = algorithmic bytes of the whole C-ABI call / its CUDA-event time on the launching stream. "
+                             "sparse_bwd_apply = segmented reduction + fused Adam row update; its keys + radix sort "
+                             "(sparse_bwd_prepare, overhead, not algorithmic bytes) run on a side stream during the forward; "
+                             "sparse_bwd_update = both phases in one call")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -402,7 +433,8 @@ def run_b200(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 tables/optimizer, bf16 MMA operands (f32 accumulate)",
                     data="synthetic", config=workload_config(args, world), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
-                    kernels=kernels, cpu_baseline=cpu, clocks=clocks, final_loss=final_loss, host_cores=os.cpu_count())
+                    kernels=kernels, cpu_baseline=cpu, clocks=clocks, final_loss=final_loss, host_cores=os.cpu_count(),
+                    launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,6 +35,7 @@ extern "C" {
 #define RB_VERSION 100  /* 0.1.0 */
 #define RB_MAX_GRAD_SOURCES 16
 #define RB_MAX_LOOKUP_GROUPS 4
+#define RB_MAX_DENSE_TENSORS 32
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -72,6 +73,9 @@ typedef struct rb_opt_params {
   float beta_1;        /* 0.9 */
   float beta_2;        /* 0.999 */
   float epsilon;       /* 1e-7 (outside the square root, Keras form) */
+  const float* alpha_t_dev;  /* optional DEVICE f32[1]: when non-NULL, Adam reads alpha_t (rb_adam_alpha_t of the current
+                                step) from here instead of deriving it from `step` — lets a captured CUDA graph be
+                                replayed for successive steps (the host refreshes the value before each replay) */
 } rb_opt_params;
 
 /*
@@ -235,6 +239,19 @@ int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int6
                                 void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
 
 /*
+ * The two phases of rb_sparse_bwd_update_groups as separate calls.  Phase 1 (keys + stable radix sort)
+ * depends only on the ids, which are known when the forward starts: run it on a side stream during
+ * the forward / MLPs and the backward pays for phase 2 only.  `groups[k].grad` is ignored by prepare.
+ * The workspace carries the sorted pairs from prepare to apply and must not be touched in between;
+ * *sorted_sel (host) tells apply which half of the double buffers holds them.
+ */
+int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups,
+                          void* ws, size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, void* stream);
+int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                        const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
+                        void* ws, size_t ws_bytes, int32_t sorted_sel, void* stream);
+
+/*
  * The same sort + segmented reduction WITHOUT the optimizer: writes the unique rows (ascending)
  * and their summed gradients — the deduplicated IndexedSlices itself.  Used by the parity tests
  * and by callers that own their optimizer.
@@ -246,6 +263,35 @@ int rb_sparse_bwd_dedup(int64_t rows, int32_t D,
                         const rb_grad_source* grad,
                         int64_t* uniq_rows, float* uniq_grad, int64_t* num_unique,
                         void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream);
+
+/* ---- dense side of the step ------------------------------------------------- */
+
+/* One dense parameter tensor of the MLPs (ctr/layers.py:5-14) with its gradient and optimizer state. */
+typedef struct rb_dense_slot {
+  float* param;        /* f32[n], updated in place */
+  float* state0;       /* Adam m / Adagrad accumulator / NULL for SGD */
+  float* state1;       /* Adam v / NULL */
+  const float* grad;   /* f32[n] */
+  int64_t n;
+} rb_dense_slot;
+
+/*
+ * Keras `_resource_apply_dense` (Adam: SURVEY A.3, the same formula as the sparse rows; Adagrad: A.4;
+ * SGD) for up to RB_MAX_DENSE_TENSORS tensors in ONE launch — replaces the per-variable
+ * ResourceApplyAdam ops of `optimizer.apply_gradients` (ctr/train.py:80,97; dien/train.py:22).
+ * `slots` is a HOST array.  RB_OPT_ADAM_LAZY and RB_OPT_ADAM_TF_DENSE are the same thing for dense tensors.
+ */
+int rb_dense_opt_step(const rb_dense_slot* slots, int32_t num, const rb_opt_params* opt, void* stream);
+
+size_t rb_colsum_workspace_bytes(int64_t rows, int32_t cols);
+
+/*
+ * out[c] = sum_r x[r, c]: the bias gradient of a Dense layer (TF BiasAddGrad under ctr/layers.py:8-9).
+ * x is RB_F32 or RB_BF16 [rows, cols] with row stride `row_stride` elements; cols % 8 == 0, cols <= 2048.
+ * Deterministic two-stage reduction, fp32 accumulation.
+ */
+int rb_colsum(const void* x, int32_t dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out,
+              void* ws, size_t ws_bytes, void* stream);
 
 /* ---- id -> row map ------------------------------------------------------------------------ */
 

@@ -16,6 +16,7 @@ HEADER = os.path.join(os.path.dirname(PKG), "include", "recsys_b200.h")
 
 RB_MAX_GRAD_SOURCES = 16
 RB_MAX_LOOKUP_GROUPS = 4
+RB_MAX_DENSE_TENSORS = 32
 
 # enums (recsys_b200.h)
 RB_I32, RB_I64 = 0, 1
@@ -32,7 +33,7 @@ SCALE_ENUM = {"none": RB_SCALE_NONE, "mean": RB_SCALE_MEAN, "masked_mean": RB_SC
 
 class RbOptParams(C.Structure):
     _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_float), ("beta_1", C.c_float),
-                ("beta_2", C.c_float), ("epsilon", C.c_float)]
+                ("beta_2", C.c_float), ("epsilon", C.c_float), ("alpha_t_dev", C.c_void_p)]
 
 
 class RbGradSource(C.Structure):
@@ -46,6 +47,10 @@ class RbGradSource(C.Structure):
 class RbLookupGroup(C.Structure):
     _fields_ = [("idx", C.c_void_p), ("idx_type", C.c_int32), ("L", C.c_int32), ("n", C.c_int64),
                 ("field_row_offset", C.c_void_p), ("hash_mod", C.c_int64), ("grad", RbGradSource)]
+
+
+class RbDenseSlot(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("state0", C.c_void_p), ("state1", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_int64)]
 
 
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -66,8 +71,14 @@ SIGNATURES = {
                                        C.POINTER(RbGradSource), C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
     "rb_sparse_bwd_update_groups": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32,
                                               C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
+    "rb_sparse_bwd_prepare": (C.c_int, [_i64, _i32, C.POINTER(RbLookupGroup), _i32, _p, C.c_size_t, _p, C.POINTER(C.c_int32), _p]),
+    "rb_sparse_bwd_apply": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32, C.POINTER(RbOptParams), _p,
+                                      C.c_size_t, _i32, _p]),
     "rb_sparse_bwd_dedup": (C.c_int, [_i64, _i32, _p, _i32, _i64, _i32, _p, _i64, C.POINTER(RbGradSource),
                                       _p, _p, _p, _p, C.c_size_t, _p, _p]),
+    "rb_dense_opt_step": (C.c_int, [C.POINTER(RbDenseSlot), _i32, C.POINTER(RbOptParams), _p]),
+    "rb_colsum_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "rb_colsum": (C.c_int, [_p, _i32, _i64, _i32, _i64, _p, _p, C.c_size_t, _p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

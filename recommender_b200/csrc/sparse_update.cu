@@ -118,6 +118,11 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
   int D;
   int opt;  // rb_optimizer, RB_OPT_ADAM_TF_DENSE = scatter-add phase only
   float lr, b1, b2, omb1, omb2, eps, alpha;
+  const float* alpha_dev;   // optional: alpha_t read from device memory (CUDA-graph replays change it per step)
+
+  __device__ __forceinline__ void prepare() {
+    if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);
+  }
 
   static constexpr int kStateRows = 3;  // ring slots per entry after the gradient: W, state0, state1
 
@@ -200,6 +205,7 @@ struct DedupSink {  // writes the deduplicated IndexedSlices (rows ascending)
   int D;
 
   static constexpr int kStateRows = 0;
+  __device__ __forceinline__ void prepare() {}
 
   template <int VEC>
   __device__ __forceinline__ void issue_state(uint32_t, int, bool, bool, float*, int) const {}
@@ -250,6 +256,7 @@ template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradGroupsDev gsrc,
                         Sink sink, float* __restrict__ head_part, float* __restrict__ tail_part) {
+  sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
   constexpr int kEntries = kGroups * kTile;
   constexpr int kKinds = 1 + Sink::kStateRows;
@@ -370,6 +377,7 @@ __global__ void __launch_bounds__(kSegThreads)
 seg_chain_kernel(const uint32_t* __restrict__ keys, int n, int D, Sink sink, const float* __restrict__ head_part,
                  const float* __restrict__ tail_part, LongChain* __restrict__ long_list, int* __restrict__ long_count,
                  int long_cap) {
+  sink.prepare();
   const int tile_id = blockIdx.x * (kSegThreads / GS) + threadIdx.x / GS;
   const int lane = threadIdx.x % GS;
   const int gbase = tile_id * kTile;
@@ -413,6 +421,7 @@ template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
 seg_long_chain_kernel(int D, Sink sink, const float* __restrict__ head_part, const float* __restrict__ tail_part,
                       const LongChain* __restrict__ long_list, const int* __restrict__ long_count, int long_cap) {
+  sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
   __shared__ float s_part[kGroups * 128];  // D <= 128
   const int group = threadIdx.x / GS, lane = threadIdx.x % GS;
@@ -463,7 +472,8 @@ __global__ void adam_decay_all_kernel(float* __restrict__ m, float* __restrict__
   }
 }
 __global__ void adam_apply_all_kernel(float* __restrict__ w, const float* __restrict__ m, const float* __restrict__ v,
-                                      int64_t count, float alpha, float eps) {
+                                      int64_t count, float alpha, const float* __restrict__ alpha_dev, float eps) {
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     w[i] = __fsub_rn(w[i], __fdiv_rn(__fmul_rn(alpha, m[i]), __fadd_rn(__fsqrt_rn(v[i]), eps)));
@@ -587,15 +597,10 @@ static int check_common(int64_t rows, int D, int64_t n, RowGeom* geo) {
   return RB_OK;
 }
 
-// Validates the groups, fills the device-side description and writes + sorts the (row, position)
-// pairs of all groups; returns pointers to the sorted arrays.
-static int prepare_and_sort(const rb_lookup_group* groups, int num_groups, int64_t rows, int D, const float* table,
-                            const RowGeom& geo, int64_t n, unsigned char* ws, const WsLayout& lay, int* oob_flag,
-                            cudaStream_t st, GradGroupsDev* gg, const uint32_t** keys_out, const uint32_t** vals_out) {
-  gg->num = num_groups;
-  gg->D = D;
-  gg->table = table;
-  for (int k = 0; k <= RB_MAX_LOOKUP_GROUPS; ++k) gg->start[k] = 0xFFFFFFFFu;
+// Phase 1 (depends on the ids only): writes and stably sorts the (row, position) pairs of all groups.
+// *sel_out = which half of the double buffers holds the sorted pairs.
+static int sort_groups(const rb_lookup_group* groups, int num_groups, int64_t rows, int64_t n, unsigned char* ws,
+                       const WsLayout& lay, int* oob_flag, cudaStream_t st, int* sel_out) {
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + lay.keys_a);
   uint32_t* kb = reinterpret_cast<uint32_t*>(ws + lay.keys_b);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + lay.vals_a);
@@ -605,10 +610,6 @@ static int prepare_and_sort(const rb_lookup_group* groups, int num_groups, int64
     const rb_lookup_group& g = groups[k];
     RB_CHECK_ARG(g.idx_type == RB_I32 || g.idx_type == RB_I64, RB_ERR_ARG, "group %d: bad index type", k);
     RB_CHECK_ARG(g.n >= 0 && g.L > 0 && (g.n == 0 || g.idx != nullptr), RB_ERR_ARG, "group %d: bad n/L/idx", k);
-    int rc = fill_grad_src(&gg->g[k], &g.grad, g.L, g.idx_type, g.idx, geo.vec);
-    if (rc != RB_OK) return rc;
-    RB_CHECK_ARG(g.grad.fm_g == nullptr || table != nullptr, RB_ERR_ARG, "the FM term needs the table");
-    gg->start[k] = static_cast<uint32_t>(start);
     if (g.n > 0) {
       IndexMap m = make_index_map(g.idx, g.idx_type, g.field_row_offset, g.hash_mod, rows, g.L);
       make_keys_kernel<<<grid_for(g.n, 256), 256, 0, st>>>(m, g.n, start, ka, va, oob_flag);
@@ -616,12 +617,50 @@ static int prepare_and_sort(const rb_lookup_group* groups, int num_groups, int64
     }
     start += g.n;
   }
-  for (int k = num_groups; k < RB_MAX_LOOKUP_GROUPS; ++k) gg->g[k] = gg->g[0];
   cub::DoubleBuffer<uint32_t> dk(ka, kb), dv(va, vb);
   size_t temp = lay.cub_bytes;
   RB_CUDA(cub::DeviceRadixSort::SortPairs(ws + lay.cub_temp, temp, dk, dv, static_cast<int>(n), 0, key_bits(rows), st));
-  *keys_out = dk.Current();
-  *vals_out = dv.Current();
+  *sel_out = dk.selector;
+  return RB_OK;
+}
+
+static void sorted_pairs(unsigned char* ws, const WsLayout& lay, int sel, const uint32_t** keys, const uint32_t** vals) {
+  *keys = reinterpret_cast<const uint32_t*>(ws + (sel ? lay.keys_b : lay.keys_a));
+  *vals = reinterpret_cast<const uint32_t*>(ws + (sel ? lay.vals_b : lay.vals_a));
+}
+
+// Phase 2 set-up: validates the groups' gradient sources and fills the device-side description.
+static int describe_groups(const rb_lookup_group* groups, int num_groups, int D, const float* table, const RowGeom& geo,
+                           GradGroupsDev* gg) {
+  gg->num = num_groups;
+  gg->D = D;
+  gg->table = table;
+  for (int k = 0; k <= RB_MAX_LOOKUP_GROUPS; ++k) gg->start[k] = 0xFFFFFFFFu;
+  int64_t start = 0;
+  for (int k = 0; k < num_groups; ++k) {
+    const rb_lookup_group& g = groups[k];
+    RB_CHECK_ARG(g.idx_type == RB_I32 || g.idx_type == RB_I64, RB_ERR_ARG, "group %d: bad index type", k);
+    RB_CHECK_ARG(g.n >= 0 && g.L > 0 && (g.n == 0 || g.idx != nullptr), RB_ERR_ARG, "group %d: bad n/L/idx", k);
+    int rc = fill_grad_src(&gg->g[k], &g.grad, g.L, g.idx_type, g.idx, geo.vec);
+    if (rc != RB_OK) return rc;
+    RB_CHECK_ARG(g.grad.fm_g == nullptr || table != nullptr, RB_ERR_ARG, "the FM term needs the table");
+    gg->start[k] = static_cast<uint32_t>(start);
+    start += g.n;
+  }
+  for (int k = num_groups; k < RB_MAX_LOOKUP_GROUPS; ++k) gg->g[k] = gg->g[0];
+  return RB_OK;
+}
+
+static int64_t total_lookups(const rb_lookup_group* groups, int num_groups) {
+  int64_t n = 0;
+  for (int k = 0; k < num_groups; ++k) n += groups[k].n > 0 ? groups[k].n : 0;
+  return n;
+}
+
+static int check_ws(const void* ws, size_t ws_bytes, const WsLayout& lay) {
+  RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", lay.total,
+               ws_bytes);
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
   return RB_OK;
 }
 
@@ -641,13 +680,33 @@ extern "C" float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t s
   return lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
 }
 
-extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
-                                           const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
-                                           void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups, void* ws,
+                                     size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, void* stream) {
   RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
                "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
-  int64_t n = 0;
-  for (int k = 0; k < num_groups; ++k) n += groups[k].n > 0 ? groups[k].n : 0;
+  RB_CHECK_ARG(sorted_sel != nullptr, RB_ERR_ARG, "sorted_sel is null");
+  const int64_t n = total_lookups(groups, num_groups);
+  RowGeom geo;
+  int rc = check_common(rows, D, n, &geo);
+  if (rc != RB_OK) return rc;
+  *sorted_sel = 0;
+  if (n == 0) return RB_OK;
+  const WsLayout lay = ws_layout(n, D, rows);
+  rc = check_ws(ws, ws_bytes, lay);
+  if (rc != RB_OK) return rc;
+  int sel = 0;
+  rc = sort_groups(groups, num_groups, rows, n, static_cast<unsigned char*>(ws), lay, oob_flag, static_cast<cudaStream_t>(stream), &sel);
+  *sorted_sel = sel;
+  return rc;
+}
+
+extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                   const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt, void* ws,
+                                   size_t ws_bytes, int32_t sorted_sel, void* stream) {
+  RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
+               "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
+  RB_CHECK_ARG(sorted_sel == 0 || sorted_sel == 1, RB_ERR_ARG, "sorted_sel must come from rb_sparse_bwd_prepare");
+  const int64_t n = total_lookups(groups, num_groups);
   RowGeom geo;
   int rc = check_common(rows, D, n, &geo);
   if (rc != RB_OK) return rc;
@@ -675,6 +734,7 @@ extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* s
   sink.omb2 = 1.0f - opt->beta_2;
   sink.eps = opt->epsilon;
   sink.alpha = adam ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
+  sink.alpha_dev = adam ? opt->alpha_t_dev : nullptr;
 
   const int64_t count = rows * D;
   if (o == RB_OPT_ADAM_TF_DENSE) {
@@ -683,22 +743,48 @@ extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* s
   }
   if (n > 0) {
     const WsLayout lay = ws_layout(n, D, rows);
-    RB_CHECK_ARG(ws != nullptr && ws_bytes >= lay.total, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
-                 lay.total, ws_bytes);
-    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, RB_ERR_ALIGN, "workspace must be 256 B aligned");
+    rc = check_ws(ws, ws_bytes, lay);
+    if (rc != RB_OK) return rc;
     GradGroupsDev gg;
+    rc = describe_groups(groups, num_groups, D, table, geo, &gg);
+    if (rc != RB_OK) return rc;
     const uint32_t *keys, *vals;
     unsigned char* wsb = static_cast<unsigned char*>(ws);
-    rc = prepare_and_sort(groups, num_groups, rows, D, table, geo, n, wsb, lay, oob_flag, st, &gg, &keys, &vals);
-    if (rc != RB_OK) return rc;
+    sorted_pairs(wsb, lay, sorted_sel, &keys, &vals);
     rc = run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st);
     if (rc != RB_OK) return rc;
   }
   if (o == RB_OPT_ADAM_TF_DENSE) {
-    adam_apply_all_kernel<<<8 * kNumSMs, 256, 0, st>>>(table, state0, state1, count, sink.alpha, sink.eps);
+    adam_apply_all_kernel<<<8 * kNumSMs, 256, 0, st>>>(table, state0, state1, count, sink.alpha, sink.alpha_dev, sink.eps);
     RB_LAUNCH_CHECK("adam_apply_all_kernel");
   }
   return RB_OK;
+}
+
+extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                           const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
+                                           void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {
+  // argument checks that must precede any launch (the two phases repeat the rest)
+  RB_CHECK_ARG(table != nullptr && opt != nullptr, RB_ERR_ARG, "table/opt is null");
+  RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
+               "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
+  const int o = opt->optimizer;
+  RB_CHECK_ARG(o >= RB_OPT_SGD && o <= RB_OPT_ADAM_TF_DENSE, RB_ERR_ARG, "bad optimizer %d", o);
+  const bool adam = (o == RB_OPT_ADAM_LAZY || o == RB_OPT_ADAM_TF_DENSE);
+  RB_CHECK_ARG(!adam || (state0 != nullptr && state1 != nullptr && opt->step >= 1), RB_ERR_ARG, "Adam needs m, v and step >= 1");
+  RB_CHECK_ARG(o != RB_OPT_ADAGRAD || state0 != nullptr, RB_ERR_ARG, "Adagrad needs its accumulator");
+  {
+    RowGeom geo;
+    int rc0 = check_common(rows, D, total_lookups(groups, num_groups), &geo);
+    if (rc0 != RB_OK) return rc0;
+    GradGroupsDev gg;
+    rc0 = describe_groups(groups, num_groups, D, table, geo, &gg);
+    if (rc0 != RB_OK) return rc0;
+  }
+  int32_t sel = 0;
+  int rc = rb_sparse_bwd_prepare(rows, D, groups, num_groups, ws, ws_bytes, oob_flag, &sel, stream);
+  if (rc != RB_OK) return rc;
+  return rb_sparse_bwd_apply(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sel, stream);
 }
 
 extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,
@@ -748,8 +834,12 @@ extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int
   GradGroupsDev gg;
   const uint32_t *keys, *vals;
   unsigned char* wsb = static_cast<unsigned char*>(ws);
-  rc = prepare_and_sort(&g, 1, rows, D, nullptr, geo, n, wsb, lay, oob_flag, st, &gg, &keys, &vals);
+  rc = describe_groups(&g, 1, D, nullptr, geo, &gg);
   if (rc != RB_OK) return rc;
+  int sel = 0;
+  rc = sort_groups(&g, 1, rows, n, wsb, lay, oob_flag, st, &sel);
+  if (rc != RB_OK) return rc;
+  sorted_pairs(wsb, lay, sel, &keys, &vals);
   int32_t* seg = reinterpret_cast<int32_t*>(wsb + lay.seg_incl);
   head_flags_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, static_cast<int>(n), seg);
   RB_LAUNCH_CHECK("head_flags_kernel");

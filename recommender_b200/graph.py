@@ -1,0 +1,69 @@
+"""The whole training step as ONE CUDA graph.
+
+At config-2 sizes a DLRM step is ~140 kernel launches in ~2 ms: launched from Python the GPU waits
+on the host.  `GraphedTrainStep` captures forward + loss + backward + optimizer (dense and sparse,
+including the side-stream radix sort that overlaps the forward) once and replays it; the only
+per-step host work is copying the batch into the graph's static input buffers and refreshing the
+step-dependent Adam scalar (`optimizers.Adam.prepare_step`, read by the kernels from device memory
+through `rb_opt_params.alpha_t_dev`).  The kernels and their order are exactly those of the eager
+path — the graph changes who launches them, not what runs.
+"""
+from __future__ import annotations
+
+import gc
+from typing import Callable, Sequence
+
+import torch
+
+
+class GraphedTrainStep:
+    """step(batch) == { prob = model(inputs); loss = loss_fn(prob, label); loss.backward();
+    optimizer.apply_gradients(model) } with the same results as the eager sequence.
+
+    batch = (cat_features int[B,F], int_features f32[B,13], label) CUDA tensors of the captured shapes.
+    The returned loss is a static device tensor overwritten by every replay."""
+
+    def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, sample_batch: Sequence[torch.Tensor], warmup: int = 3):
+        if not all(t.is_cuda for t in sample_batch):
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
+        self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        self.static = tuple(torch.empty_like(t) for t in sample_batch)
+        if hasattr(optimizer, "enable_device_scalars"):
+            optimizer.enable_device_scalars(sample_batch[0].device)
+        for d, s in zip(self.static, sample_batch):
+            d.copy_(s)
+        # Autograd graphs of earlier eager steps pin their AccumulateGrad nodes to the stream they ran on (the
+        # legacy default stream breaks capture): the caller must not hold such a graph (e.g. a non-detached loss).
+        gc.collect()
+        # warm-up off the default stream (lazy builds, workspaces, cuBLAS handles, autograd threads)
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=sample_batch[0].device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.optimizer.prepare_step()
+                self._body()
+        main.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.optimizer.prepare_step()                       # host half of the captured step
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.steps_run = max(1, warmup) + 1                 # capture itself does not execute: counted when replayed below
+        self.graph.replay()
+
+    def _body(self) -> torch.Tensor:
+        cat, dense, label = self.static
+        prob = self.model({"cat_features": cat, "int_features": dense})
+        loss = self.loss_fn(prob, label)
+        loss.backward()
+        self.optimizer.apply_gradients(self.model)
+        return loss.detach()
+
+    def step(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
+        for d, s in zip(self.static, batch):
+            d.copy_(s, non_blocking=True)
+        self.optimizer.prepare_step()
+        self.graph.replay()
+        self.steps_run += 1
+        return self.loss

@@ -172,6 +172,12 @@ class Embedding(nn.Module):
         self._anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
         self.pending: List[LookupGroup] = []
         self.opt_state = {}
+        # The (row, position) sort of the backward depends on the ids only: it is started on a side stream
+        # when the lookup runs and overlaps the forward / MLPs (rb_sparse_bwd_prepare / _apply).
+        self.presort = True
+        self._side_stream: Optional[torch.cuda.Stream] = None
+        self._sorted = None          # (idx tensor, L, selector, done event) of the sort in flight
+        self._sort_ws: Optional[torch.Tensor] = None
 
     # -- helpers used by the autograd functions
     def row_offset_for(self, L: int):
@@ -184,9 +190,40 @@ class Embedding(nn.Module):
     def _record(self, group: LookupGroup) -> None:
         self.pending.append(group)
 
+    def _presort(self, idx: torch.Tensor, L: int, field_row_offset) -> None:
+        """Start keys + radix sort for this lookup on the side stream (first lookup of the step only;
+        a table used several times per step falls back to the one-call path in apply_pending)."""
+        if not self.embeddings.is_cuda:
+            return
+        if not (self.presort and torch.is_grad_enabled()) or self._sorted is not None or self.pending:
+            if self._sorted is not None and self._sorted[0] is not idx:
+                self._sorted = (None, 0, 0, self._sorted[3])       # a second use: the pre-sort no longer covers the step
+            return
+        n = idx.numel()
+        if n == 0:
+            return
+        rows, D = self.embeddings.shape
+        need = ops.lib.rb_sparse_bwd_update_workspace_bytes(n, D, rows)
+        if self._sort_ws is None or self._sort_ws.numel() < need:
+            self._sort_ws = ops.sparse_workspace(n, D, rows, self.embeddings.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.embeddings.device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        side.wait_stream(main)            # ids are ready; the previous step's apply has released the workspace
+        with torch.cuda.stream(side):
+            sel = ops.sparse_bwd_prepare(rows, D, [LookupGroup(idx, L, None, field_row_offset=field_row_offset, hash_mod=self.hash_mod)],
+                                         self._sort_ws)
+            done = side.record_event()
+        if not torch.cuda.is_current_stream_capturing():
+            idx.record_stream(side)
+        self._sorted = (idx, L, sel, done)
+
     # -- the Keras call surface
     def forward(self, idx: torch.Tensor) -> torch.Tensor:
         """E[..., :] = embeddings[idx[...], :]   (ctr/model.py:19, :49)."""
+        idx = idx.contiguous()
+        L = idx.shape[-1] if idx.dim() >= 1 else 1
+        self._presort(idx, L, self.row_offset_for(L) if self.num_tables > 1 else None)
         return _GatherFn.apply(self._anchor, self, idx)
 
     def compute_mask(self, x, mask=None):
@@ -200,6 +237,8 @@ class Embedding(nn.Module):
 
     def lookup_fm(self, idx: torch.Tensor):
         """(E[B,F,D], fm[B]) of ctr/model.py:19-23 in one pass over the rows."""
+        idx = idx.contiguous()
+        self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return _GatherFMFn.apply(self._anchor, self, idx)
 
     def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
@@ -208,11 +247,13 @@ class Embedding(nn.Module):
         straight from the table, so [B,F,D] and [B,F+1,D] never exist in HBM.  out_dtype=bfloat16
         emits the row in bf16, zero-padded to a multiple of `pad_to` columns (the K operand of a
         bf16 top MLP); its gradient then comes back in the same padded bf16 form."""
+        idx = idx.contiguous()
+        self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to)
 
     # -- optimizer side (called by optimizers.*.apply_gradients)
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
-                      initial_accumulator_value=0.1) -> int:
+                      initial_accumulator_value=0.1, alpha_dev=None) -> int:
         """Runs the fused backward scatter + row update over this step's lookup groups."""
         if not self.pending:
             if kind == "adam_tf_dense":   # Keras moves every row every step, gradient or not
@@ -232,9 +273,17 @@ class Embedding(nn.Module):
         else:
             raise ValueError(kind)
         groups, self.pending = self.pending, []
+        sorted_, self._sorted = self._sorted, None
         n = sum(g.n for g in groups)
-        ops.sparse_bwd_update(self.embeddings, s0, s1, groups, optimizer=kind, step=step, lr=lr, beta_1=beta_1,
-                              beta_2=beta_2, epsilon=epsilon)
+        if sorted_ is not None:
+            torch.cuda.current_stream().wait_event(sorted_[3])     # also orders later reuse of the sort workspace
+        if (sorted_ is not None and sorted_[0] is not None and len(groups) == 1 and groups[0].L == sorted_[1]
+                and groups[0].idx.data_ptr() == sorted_[0].data_ptr() and groups[0].n == sorted_[0].numel()):
+            ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, sorted_[2], optimizer=kind, step=step, lr=lr,
+                                 beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
+        else:
+            ops.sparse_bwd_update(self.embeddings, s0, s1, groups, optimizer=kind, step=step, lr=lr, beta_1=beta_1,
+                                  beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
         return n
 
 
@@ -270,8 +319,11 @@ class _LinearBF16Fn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.mm(dy, Wp.t()) if ctx.need_dx else None
         dW = torch.mm(x.t(), dy)[: ctx.in_dim].float()
-        ones = torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device)
-        db = torch.mm(ones, dy).reshape(-1).float()
+        if dy.is_cuda and dy.shape[1] % 8 == 0:
+            db = ops.colsum(dy)                       # rb_colsum: deterministic fp32 column sums
+        else:
+            ones = torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device)
+            db = torch.mm(ones, dy).reshape(-1).float()
         return dx, dW, db, None
 
 

@@ -262,7 +262,7 @@ class GradSource:
 class LookupGroup:
     """One use of a table inside a step: its index array, bag length and gradient source."""
 
-    def __init__(self, idx: torch.Tensor, L: int, grad: GradSource, field_row_offset=None, hash_mod=0):
+    def __init__(self, idx: torch.Tensor, L: int, grad: Optional[GradSource], field_row_offset=None, hash_mod=0):
         self.idx = idx.contiguous()
         self.L, self.grad, self.field_row_offset, self.hash_mod = int(L), grad, field_row_offset, int(hash_mod)
 
@@ -284,12 +284,60 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def _opt_params(optimizer: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7) -> _lib.RbOptParams:
-    return _lib.RbOptParams(_lib.OPTIMIZER_ENUM[optimizer], int(step), float(lr), float(beta_1), float(beta_2), float(epsilon))
+def _opt_params(optimizer: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None) -> _lib.RbOptParams:
+    return _lib.RbOptParams(_lib.OPTIMIZER_ENUM[optimizer], int(step), float(lr), float(beta_1), float(beta_2), float(epsilon),
+                            _ptr(alpha_dev))
+
+
+def _groups_c(groups, with_grad=True):
+    arr = (_lib.RbLookupGroup * len(groups))()
+    for k, g in enumerate(groups):
+        arr[k].idx = g.idx.data_ptr()
+        arr[k].idx_type = _idx(g.idx)
+        arr[k].L = g.L
+        arr[k].n = g.n
+        arr[k].field_row_offset = _ptr(g.field_row_offset)
+        arr[k].hash_mod = g.hash_mod
+        if with_grad:
+            arr[k].grad = g.grad.to_c()
+    return arr
+
+
+def sparse_workspace(n: int, D: int, rows: int, device) -> torch.Tensor:
+    """A private workspace for the prepare -> apply pair (the shared per-device one may be reused in between)."""
+    nbytes = lib.rb_sparse_bwd_update_workspace_bytes(n, D, rows)
+    if nbytes == 0:
+        raise _lib.RecsysError("rb_sparse_bwd_update_workspace_bytes rejected the problem size")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def sparse_bwd_prepare(rows: int, D: int, groups: Sequence["LookupGroup"], ws: torch.Tensor) -> int:
+    """Phase 1 (rb_sparse_bwd_prepare): keys + stable radix sort of the groups' ids into `ws`, on the
+    current stream.  Returns the selector to hand to sparse_bwd_apply.  Group gradients are not read."""
+    for g in groups:
+        _need_cuda(g.idx, g.field_row_offset)
+    sel = C.c_int32(0)
+    check(lib.rb_sparse_bwd_prepare(int(rows), int(D), _groups_c(groups, with_grad=False), len(groups), _ptr(ws), ws.numel(),
+                                    _ptr(oob_flag(ws.device)), C.byref(sel), _stream()), "rb_sparse_bwd_prepare")
+    return int(sel.value)
+
+
+def sparse_bwd_apply(table, state0, state1, groups: Sequence["LookupGroup"], ws: torch.Tensor, sel: int, *, optimizer="adam_lazy",
+                     step=1, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None) -> None:
+    """Phase 2 (rb_sparse_bwd_apply): segmented reduction + optimizer row update over pairs sorted by
+    sparse_bwd_prepare with the same groups and workspace."""
+    _need_cuda(table, state0, state1)
+    for g in groups:
+        _need_cuda(g.idx, g.field_row_offset, *g.grad.srcs, g.grad.mask_idx, g.grad.count, g.grad.fm_g, g.grad.fm_s)
+    _f32c(table, "table")
+    rows, D = table.shape
+    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+    check(lib.rb_sparse_bwd_apply(_ptr(table), _ptr(state0), _ptr(state1), rows, D, _groups_c(groups), len(groups), C.byref(opt),
+                                  _ptr(ws), ws.numel(), int(sel), _stream()), "rb_sparse_bwd_apply")
 
 
 def sparse_bwd_update(table, state0, state1, groups: Sequence[LookupGroup], *, optimizer="adam_lazy", step=1,
-                      lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7) -> None:
+                      lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None) -> None:
     """IndexedSlices -> duplicate-row sum -> optimizer row update, in place on table/state
     (rb_sparse_bwd_update_groups; one group = rb_sparse_bwd_update)."""
     _need_cuda(table, state0, state1)
@@ -304,16 +352,8 @@ def sparse_bwd_update(table, state0, state1, groups: Sequence[LookupGroup], *, o
     if nbytes == 0:
         raise _lib.RecsysError("rb_sparse_bwd_update_workspace_bytes rejected the problem size")
     ws = _workspace(nbytes, table.device)
-    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon)
-    arr = (_lib.RbLookupGroup * len(groups))()
-    for k, g in enumerate(groups):
-        arr[k].idx = g.idx.data_ptr()
-        arr[k].idx_type = _idx(g.idx)
-        arr[k].L = g.L
-        arr[k].n = g.n
-        arr[k].field_row_offset = _ptr(g.field_row_offset)
-        arr[k].hash_mod = g.hash_mod
-        arr[k].grad = g.grad.to_c()
+    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+    arr = _groups_c(groups)
     check(lib.rb_sparse_bwd_update_groups(_ptr(table), _ptr(state0), _ptr(state1), rows, D, arr, len(groups),
                                           C.byref(opt), _ptr(ws), ws.numel(), _ptr(oob_flag(table.device)), _stream()),
           "rb_sparse_bwd_update_groups")
@@ -335,6 +375,45 @@ def sparse_bwd_dedup(rows: int, D: int, idx, L: int, grad: GradSource, *, field_
                                   _ptr(oob_flag(dev)), _stream()), "rb_sparse_bwd_dedup")
     u = int(num.item())
     return uniq_rows[:u], uniq_grad[:u]
+
+
+# --------------------------------------------------------------------------------------------
+# dense side of the step
+# --------------------------------------------------------------------------------------------
+
+def dense_opt_step(params, grads, state0, state1, *, optimizer="adam_lazy", step=1, lr=1e-3, beta_1=0.9, beta_2=0.999,
+                   epsilon=1e-7, alpha_dev=None) -> None:
+    """Keras `_resource_apply_dense` for a list of fp32 tensors, RB_MAX_DENSE_TENSORS per launch
+    (rb_dense_opt_step).  state0/state1: lists (Adam m, v; Adagrad acc, None) or None (SGD)."""
+    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+    n = len(params)
+    for lo in range(0, n, _lib.RB_MAX_DENSE_TENSORS):
+        hi = min(n, lo + _lib.RB_MAX_DENSE_TENSORS)
+        arr = (_lib.RbDenseSlot * (hi - lo))()
+        for k in range(lo, hi):
+            p, g = params[k], grads[k]
+            _need_cuda(p, g)
+            if p.dtype != torch.float32 or g.dtype != torch.float32 or not p.is_contiguous() or not g.is_contiguous():
+                raise TypeError("dense_opt_step takes contiguous float32 parameters and gradients")
+            arr[k - lo].param = p.data_ptr()
+            arr[k - lo].grad = g.data_ptr()
+            arr[k - lo].state0 = None if state0 is None else state0[k].data_ptr()
+            arr[k - lo].state1 = None if state1 is None else state1[k].data_ptr()
+            arr[k - lo].n = p.numel()
+        check(lib.rb_dense_opt_step(arr, hi - lo, C.byref(opt), _stream()), "rb_dense_opt_step")
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a [rows, cols] float32 / bfloat16 matrix (rb_colsum): a Dense bias gradient."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("colsum takes a [rows, cols] matrix with unit inner stride")
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    ws = _workspace(max(lib.rb_colsum_workspace_bytes(rows, cols), 256), x.device)
+    check(lib.rb_colsum(_ptr(x), _float_type(x.dtype), rows, cols, int(x.stride(0)), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "rb_colsum")
+    return out
 
 
 # --------------------------------------------------------------------------------------------

@@ -34,6 +34,18 @@ class _Optimizer:
     def __init__(self):
         self.iterations = 0
         self._state = {}
+        self._prepared = False      # prepare_step() already advanced `iterations` for the step being applied
+
+    def prepare_step(self) -> None:
+        """Host half of a step whose device half is a captured CUDA graph (graph.GraphedTrainStep): advances
+        `iterations` and refreshes every step-dependent scalar the kernels read from device memory.
+        Call it before each replay; apply_gradients() then must not advance the counter again."""
+        self.iterations += 1
+        self._prepared = True
+        self._refresh_device_scalars()
+
+    def _refresh_device_scalars(self) -> None:
+        pass
 
     def _sparse_kwargs(self):
         raise NotImplementedError
@@ -49,7 +61,7 @@ class _Optimizer:
         embs, dense = _split(model_or_vars)
         if hasattr(model_or_vars, "reduce_dense_grads"):
             model_or_vars.reduce_dense_grads()      # data-parallel replicas (sharded.ShardedDLRM)
-        step = self.iterations + 1
+        step = self.iterations if self._prepared else self.iterations + 1
         params = [p for p in dense if p.grad is not None]
         if params:
             self._dense_step(params, [p.grad for p in params], step)
@@ -58,6 +70,8 @@ class _Optimizer:
         for e in embs:
             e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
         self.iterations = step
+        if not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
+            self._prepared = False      # a captured body is replayed: every replay is preceded by prepare_step()
 
 
 class Adam(_Optimizer):
@@ -71,9 +85,23 @@ class Adam(_Optimizer):
         super().__init__()
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
         self.sparse_kind = {"lazy": "adam_lazy", "tf_dense": "adam_tf_dense"}[sparse]
+        self._alpha_dev = None      # device f32[1] holding alpha_t of the current step (graph replays)
+        self._alpha_host = None
+
+    def enable_device_scalars(self, device) -> None:
+        """alpha_t lives in device memory from now on (rb_opt_params.alpha_t_dev), refreshed by prepare_step()."""
+        if self._alpha_dev is None:
+            self._alpha_dev = torch.zeros(1, dtype=torch.float32, device=device)
+            self._alpha_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def _refresh_device_scalars(self) -> None:
+        if self._alpha_dev is not None:
+            self._alpha_host[0] = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, self.iterations)
+            self._alpha_dev.copy_(self._alpha_host, non_blocking=True)
 
     def _sparse_kwargs(self):
-        return dict(lr=self.learning_rate, beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon)
+        return dict(lr=self.learning_rate, beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon,
+                    alpha_dev=self._alpha_dev if self._prepared else None)
 
     def _dense_step(self, params, grads, step):
         ms, vs = [], []
@@ -83,6 +111,11 @@ class Adam(_Optimizer):
                 st = self._state[p] = (torch.zeros_like(p), torch.zeros_like(p))
             ms.append(st[0])
             vs.append(st[1])
+        if params[0].is_cuda:     # one launch for every dense tensor (rb_dense_opt_step)
+            ops.dense_opt_step(params, grads, ms, vs, optimizer="adam_lazy", step=step, lr=self.learning_rate,
+                               beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon,
+                               alpha_dev=self._alpha_dev if self._prepared else None)
+            return
         alpha = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, step)
         torch._foreach_mul_(ms, self.beta_1)
         torch._foreach_add_(ms, grads, alpha=1.0 - self.beta_1)
@@ -112,6 +145,9 @@ class Adagrad(_Optimizer):
             if st is None:
                 st = self._state[p] = torch.full_like(p, self.initial_accumulator_value)
             accs.append(st)
+        if params[0].is_cuda:
+            ops.dense_opt_step(params, grads, accs, None, optimizer="adagrad", lr=self.learning_rate, epsilon=self.epsilon)
+            return
         torch._foreach_addcmul_(accs, grads, grads, value=1.0)
         denom = torch._foreach_sqrt(accs)
         torch._foreach_add_(denom, self.epsilon)
@@ -130,4 +166,7 @@ class SGD(_Optimizer):
         return dict(lr=self.learning_rate)
 
     def _dense_step(self, params, grads, step):
+        if params[0].is_cuda:
+            ops.dense_opt_step(params, grads, None, None, optimizer="sgd", lr=self.learning_rate)
+            return
         torch._foreach_add_(params, grads, alpha=-self.learning_rate)

@@ -117,7 +117,7 @@ def _group_slices(g: LookupGroup, D):
 
 
 def sparse_bwd_update(table, state0, state1, groups, *, optimizer="adam_lazy", step=1, lr=1e-3, beta_1=0.9, beta_2=0.999,
-                      epsilon=1e-7):
+                      epsilon=1e-7, alpha_dev=None):
     _launches[0] += 1
     D = table.shape[1]
     ind, val = O.concat_indexed_slices([_group_slices(g, D) for g in groups])

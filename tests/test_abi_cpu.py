@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     # plain C layout: 2*int32 + 16 ptr + 16 i64 + 16 i64 + 4 ptr ; group = ptr,2*i32,i64,ptr,i64 + grad
     assert C.sizeof(_lib.RbGradSource) == 8 + 16 * 8 * 3 + 4 * 8
     assert C.sizeof(_lib.RbLookupGroup) == 8 + 8 + 8 + 8 + 8 + C.sizeof(_lib.RbGradSource)
-    assert C.sizeof(_lib.RbOptParams) == 24
+    assert C.sizeof(_lib.RbOptParams) == 32     # 2*int32 + 4*float + 1 pointer
 
 
 def test_version_and_alpha_t(cuda_lib):
@@ -69,7 +69,7 @@ def test_argument_validation_without_a_gpu(cuda_lib):
     gs = _lib.RbGradSource()
     gs.num_src = 1
     gs.src[0] = p
-    opt = _lib.RbOptParams(_lib.RB_OPT_ADAM_LAZY, 1, 1e-3, 0.9, 0.999, 1e-7)
+    opt = _lib.RbOptParams(_lib.RB_OPT_ADAM_LAZY, 1, 1e-3, 0.9, 0.999, 1e-7, None)
     rc = L.rb_sparse_bwd_update(p, p, p, 5000, 16, C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, C.byref(gs), C.byref(opt),
                                 p, 16, None, None)
     assert rc == -4 and b"workspace" in L.rb_last_error()

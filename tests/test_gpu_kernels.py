@@ -455,3 +455,51 @@ def test_bucket_by_owner(ops):
         np.testing.assert_array_equal(local, loc[ref_perm])
         np.testing.assert_array_equal(inv[perm], np.arange(n))
         np.testing.assert_array_equal(counts, np.bincount(owner, minlength=world))
+
+
+# ---- dense side: multi-tensor optimizer step, bias gradient --------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["adam_lazy", "adagrad", "sgd"])
+def test_dense_opt_step_matches_keras_formulas(ops, kind):
+    """rb_dense_opt_step over tensors of very different sizes (1 .. 406016 elements, 40 of them, so two
+    launches) against the oracle's Keras `_resource_apply_dense` restatement — bit for bit."""
+    rng = np.random.default_rng(11)
+    sizes = [1, 7, 512, 2048, 2049, 793 * 512, 64] + [33] * 33
+    P = [rng.normal(0, 0.1, size=n).astype(np.float32) for n in sizes]
+    G = [rng.normal(0, 1e-2, size=n).astype(np.float32) for n in sizes]
+    M = [rng.normal(0, 1e-3, size=n).astype(np.float32) for n in sizes]
+    V = [np.abs(rng.normal(0, 1e-5, size=n)).astype(np.float32) for n in sizes]
+    p, g, m, v = ([cu(a.copy()) for a in L] for L in (P, G, M, V))
+    step = 3
+    if kind == "adam_lazy":
+        ops.dense_opt_step(p, g, m, v, optimizer=kind, step=step)
+        for k in range(len(sizes)):
+            rp, rm, rv = P[k].copy(), M[k].copy(), V[k].copy()
+            O.adam_dense_param(rp, rm, rv, G[k], step)
+            np.testing.assert_array_equal(p[k].cpu().numpy(), rp)
+            np.testing.assert_array_equal(m[k].cpu().numpy(), rm)
+            np.testing.assert_array_equal(v[k].cpu().numpy(), rv)
+    elif kind == "adagrad":
+        acc = [cu(np.full(n, 0.1, np.float32)) for n in sizes]
+        ops.dense_opt_step(p, g, acc, None, optimizer=kind, lr=1e-3)
+        for k in range(len(sizes)):
+            a = np.full(sizes[k], 0.1, np.float32) + G[k] * G[k]
+            ref = P[k] - (np.float32(1e-3) * G[k]) / (np.sqrt(a) + np.float32(1e-7))
+            np.testing.assert_array_equal(acc[k].cpu().numpy(), a)
+            np.testing.assert_array_equal(p[k].cpu().numpy(), ref.astype(np.float32))
+    else:
+        ops.dense_opt_step(p, g, None, None, optimizer=kind, lr=1e-2)
+        for k in range(len(sizes)):
+            np.testing.assert_array_equal(p[k].cpu().numpy(), P[k] - np.float32(1e-2) * G[k])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,cols", [(65536, 512), (1000, 64), (63, 8), (4097, 256), (5, 2048)])
+def test_colsum_bias_gradient(ops, dtype, rows, cols):
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 1e-2).to(dtype)
+    got = ops.colsum(x)
+    ref = x.double().sum(0)
+    scale = x.double().abs().sum(0).max().item()
+    assert (got.double() - ref).abs().max().item() <= 1e-6 * scale + 1e-12
+    assert torch.equal(got, ops.colsum(x))                                   # deterministic

@@ -195,6 +195,49 @@ def test_dien_style_masked_history(cuda_lib, golden):
 FULL_B, FULL_D, FULL_V, FULL_T = 65536, 64, 1_000_000, 26
 
 
+def test_graphed_train_step_equals_eager(cuda_lib, golden):
+    """One CUDA graph per step (graph.GraphedTrainStep: forward + loss + backward + dense and sparse Adam, the
+    radix sort on its side stream) must reproduce the eager step: same kernels, same order, same numbers —
+    including Adam's step-dependent alpha_t, which the graph reads from device memory."""
+    from recommender_b200.graph import GraphedTrainStep
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden("dlrm_uniform")
+    cat, dense_x, label = cu(g["cat"]), cu(g["dense"]), cu(g["label"])
+    batches = [(cat, dense_x, label), (cat.flip(0).contiguous(), dense_x.flip(0).contiguous(), label.flip(0).contiguous())]
+    n_steps = 5
+
+    def run(graphed):
+        torch.manual_seed(0)
+        model = _build_dlrm(g)
+        opt = Adam()
+        losses = []
+        if graphed:
+            gs = GraphedTrainStep(model, opt, bce_clipped, batches[0], warmup=1)    # runs 1 eager + 1 replayed step on batch 0
+            done = gs.steps_run
+            for i in range(n_steps - done):
+                losses.append(float(gs.step(batches[(done + i) % 2]).item()))
+        else:
+            for i in range(n_steps):
+                b = batches[0] if i < 2 else batches[i % 2]
+                prob = model({"cat_features": b[0], "int_features": b[1]})
+                loss = bce_clipped(prob, b[2])
+                loss.backward()
+                opt.apply_gradients(model)
+                losses.append(float(loss.item()))
+            losses = losses[2:]
+        torch.cuda.synchronize()
+        return losses, model.embedding_layer.embeddings.clone(), [p.detach().clone() for p in model.parameters()], opt.iterations
+
+    l_e, t_e, p_e, it_e = run(False)
+    l_g, t_g, p_g, it_g = run(True)
+    assert it_e == it_g == n_steps
+    np.testing.assert_allclose(l_g, l_e, rtol=1e-6)
+    assert torch.equal(t_g, t_e)
+    for a, b in zip(p_g, p_e):
+        assert torch.equal(a, b)
+
+
 @pytest.fixture(scope="module")
 def full(cuda_lib):
     torch.manual_seed(4)
