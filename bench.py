@@ -27,6 +27,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+
 import torch
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -51,6 +53,8 @@ def parse_args():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--sharding", default="row", choices=["row", "table"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: rows/gradients read by the kernels over NVLink peer memory (p2p) or exchanged with NCCL all-to-alls")
     ap.add_argument("--ring", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,7 +189,10 @@ def workload_config(args, world):
                          f"{args.tables} table(s) x {args.rows_per_table} rows, dot interaction, Adam",
                 global_batch=args.batch * world, tables=args.tables, rows_per_table=args.rows_per_table, emb_dim=args.emb_dim,
                 bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
-                sparse_optimizer="adam_lazy", parallelism="single GPU" if world == 1 else f"{args.sharding}-wise sharded tables x{world} + data-parallel MLPs",
+                sparse_optimizer="adam_lazy",
+                parallelism="single GPU" if world == 1 else (
+                    f"row-wise sharded tables x{world}, rows and gradient rows read by the kernels over NVLink peer memory + data-parallel MLPs"
+                    if args.exchange == "p2p" else f"{args.sharding}-wise sharded tables x{world}, NCCL all-to-all + data-parallel MLPs"),
                 l2="inputs larger than L2: tables %.1f GB, ring of %d batches, 436 MB gradient tensor per step" % (
                     args.tables * args.rows_per_table * args.emb_dim * 4 / 1e9, args.ring))
 
@@ -246,6 +253,9 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(4)
     if world == 1:
         model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
+    elif args.exchange == "p2p":
+        from recommender_b200.p2p import P2PShardedDLRM
+        model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
     else:
         from recommender_b200.sharded import ShardedDLRM
         model = ShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
@@ -301,7 +311,7 @@ def run_b200(args):
     eager_ms_step = max_over_ranks(g0.elapsed_time(g1)) / k_eager
 
     # ---- the step as one CUDA graph (single GPU; the sharded step has host-side exchange counts) --------------
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = (world == 1 or args.exchange == "p2p") and not args.no_graph     # the NCCL all-to-all path has host-side counts
     if use_graph:
         from recommender_b200.graph import GraphedTrainStep
         del loss
@@ -437,7 +447,13 @@ def run_b200(args):
                     launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holding NCCL kernels plus peer-mapped buffers makes interpreter teardown unreliable:
+        # meet once more, flush, and leave without running destructors
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

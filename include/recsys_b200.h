@@ -36,6 +36,8 @@ extern "C" {
 #define RB_MAX_GRAD_SOURCES 16
 #define RB_MAX_LOOKUP_GROUPS 4
 #define RB_MAX_DENSE_TENSORS 32
+#define RB_MAX_RANKS 8          /* GPUs of one NVSwitch box */
+#define RB_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -317,6 +319,63 @@ int rb_bucket_by_owner(const void* idx, int32_t idx_type, int64_t n, int32_t L,
                        const int64_t* field_row_offset, int64_t hash_mod, int32_t world,
                        int64_t* local_rows_out, int32_t* perm_out, int32_t* inv_perm_out,
                        int64_t* counts_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- sharded tables over peer memory --------------------------------------------------- */
+/*
+ * One process per GPU; the reference only replicates (MirroredStrategy, ctr/train.py:71-84).  Here the
+ * table is split row-wise (row r -> rank r mod world, local row r div world) and the other GPUs'
+ * shards are read IN the kernels over NVLink/NVSwitch peer pointers — the gather is the collective:
+ * no all-to-all of rows or gradients, no staging copies.
+ *
+ * rb_shared_alloc: cudaMalloc + cudaIpcGetMemHandle (handle_out: RB_IPC_HANDLE_BYTES bytes to ship to the
+ * peers, e.g. with torch.distributed.all_gather_object).  rb_ipc_open maps a peer's buffer into this process.
+ */
+int rb_shared_alloc(size_t bytes, void** ptr_out, void* handle_out);
+int rb_shared_free(void* ptr);
+int rb_ipc_open(const void* handle, void** ptr_out);
+int rb_ipc_close(void* ptr);
+/* single process driving several GPUs: let kernels on the current device dereference `peer_device` memory */
+int rb_enable_peer_access(int32_t peer_device);
+
+/* rb_dot_interaction_fwd / _bwd with the rows fetched from `world` shards in peer memory.
+ * shard_ptrs_dev: DEVICE array of `world` device pointers (own shard included); rows: GLOBAL row count.
+ * x_save (optional, bf16 [B, F', D]): the forward also stores the operand rows rounded to bf16 — exactly
+ * what its MMAs consume — and the backward given the same buffer as x_saved reads them locally instead
+ * of gathering the rows over NVLink a second time (bit-identical results). */
+int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
+                                   const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                                   const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                                   int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                                   void* out, int32_t out_dtype, int64_t out_stride, void* x_save, void* stream);
+int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
+                                   const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                                   const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                                   int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                                   const void* dOut, int32_t dout_dtype, int64_t dout_stride,
+                                   float* dE, float* d_dense, const void* x_saved, void* stream);
+
+/*
+ * Owner side of the sharded backward.  Every rank k publishes its rb_bucket_by_owner outputs (local
+ * rows, perm, counts) in peer memory; owner `me` collects the slices addressed to it as
+ * (key = local row, value = k*n_local + position) pairs into the sparse-backward workspace, padded
+ * to the static `capacity` with a key that sorts last (static shapes: the step can be a CUDA graph).
+ * *n_valid_dev receives the real pair count, *overflow_flag is raised if it exceeds capacity.
+ * The *_ptrs arrays are HOST arrays of `world` device (peer) pointers.  ws: rb_sparse_bwd_update_workspace_bytes(
+ * capacity, D, local_rows + 1).
+ */
+int rb_p2p_collect_keys(int32_t world, int32_t me, int64_t n_local, const void* const* rows_ptrs,
+                        const void* const* perm_ptrs, const void* const* counts_ptrs, int64_t local_rows,
+                        int64_t capacity, void* ws, size_t ws_bytes, int32_t D, int32_t* n_valid_dev,
+                        int32_t* overflow_flag, void* stream);
+/* stable radix sort of the collected pairs (the phase-1 counterpart of rb_sparse_bwd_prepare) */
+int rb_sparse_bwd_prepare_collected(int64_t local_rows, int32_t D, int64_t capacity, void* ws, size_t ws_bytes,
+                                    int32_t* sorted_sel, void* stream);
+/* phase 2: segmented reduction + optimizer row update on the local shard; gradient rows are pulled from
+ * the ranks' dE[B_local, L, D] tensors in peer memory (dE_ptrs: HOST array of `world` device pointers). */
+int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state1, int64_t local_rows, int32_t D, int32_t world,
+                            int64_t n_local, int32_t L, const void* const* dE_ptrs, int64_t capacity,
+                            const int32_t* n_valid_dev, const rb_opt_params* opt, void* ws, size_t ws_bytes,
+                            int32_t sorted_sel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@ HEADER = os.path.join(os.path.dirname(PKG), "include", "recsys_b200.h")
 RB_MAX_GRAD_SOURCES = 16
 RB_MAX_LOOKUP_GROUPS = 4
 RB_MAX_DENSE_TENSORS = 32
+RB_MAX_RANKS = 8
+RB_IPC_HANDLE_BYTES = 64
 
 # enums (recsys_b200.h)
 RB_I32, RB_I64 = 0, 1
@@ -79,6 +81,20 @@ SIGNATURES = {
     "rb_dense_opt_step": (C.c_int, [C.POINTER(RbDenseSlot), _i32, C.POINTER(RbOptParams), _p]),
     "rb_colsum_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_colsum": (C.c_int, [_p, _i32, _i64, _i32, _i64, _p, _p, C.c_size_t, _p]),
+    "rb_shared_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), _p]),
+    "rb_shared_free": (C.c_int, [_p]),
+    "rb_ipc_open": (C.c_int, [_p, C.POINTER(C.c_void_p)]),
+    "rb_ipc_close": (C.c_int, [_p]),
+    "rb_enable_peer_access": (C.c_int, [_i32]),
+    "rb_dot_interaction_fwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p,
+                                                 _p]),
+    "rb_dot_interaction_bwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64,
+                                                 _p, _p, _p, _p]),
+    "rb_p2p_collect_keys": (C.c_int, [_i32, _i32, _i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64, _i64,
+                                      _p, C.c_size_t, _i32, _p, _p, _p]),
+    "rb_sparse_bwd_prepare_collected": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p]),
+    "rb_sparse_bwd_apply_p2p": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i64, _i32, C.POINTER(C.c_void_p), _i64, _p,
+                                          C.POINTER(RbOptParams), _p, C.c_size_t, _i32, _p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

@@ -164,14 +164,21 @@ __device__ __forceinline__ uint32_t smem_u32addr(const void* p) { return static_
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32addr(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
+// 16-byte copy through L1 (.ca): for PEER memory, which bypasses the local L2 — L1 line fills ask NVLink for
+// whole 128-byte lines instead of 32-byte sectors
+__device__ __forceinline__ void cp_async16_ca(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
 }
 // VEC floats per thread (16 / 8 / 4 bytes)
+// through_l1: the source may be PEER memory (see cp_async16_ca)
 template <int VEC>
-__device__ __forceinline__ void cp_async_vec(float* dst, const float* src) {
+__device__ __forceinline__ void cp_async_vec(float* dst, const float* src, bool through_l1 = false) {
   if constexpr (VEC == 4) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+    if (through_l1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
   } else if constexpr (VEC == 2) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32addr(dst)), "l"(src) : "memory");
   } else {
@@ -218,6 +225,9 @@ inline IndexMap make_index_map(const void* idx, int idx_type, const int64_t* off
   m.is64 = (idx_type == RB_I64);
   return m;
 }
+
+// keys / positions input buffers inside a sparse-backward workspace (sparse_update.cu), filled by p2p.cu
+int sparse_ws_key_buffers(int64_t n, int D, int64_t rows, void* ws, uint32_t** keys, uint32_t** vals);
 
 inline unsigned int grid_for(int64_t work_items, int items_per_block) {
   int64_t b = (work_items + items_per_block - 1) / items_per_block;

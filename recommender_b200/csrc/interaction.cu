@@ -26,6 +26,9 @@
 
 namespace rb {
 
+#ifndef RB_PEER_CA
+#define RB_PEER_CA 1
+#endif
 constexpr int kIxStages = 2;   // ring depth per warp
 // warps per CTA (each with its own ring): sized so that kIxStages rings + staging fit in 227 KiB
 template <int D>
@@ -36,6 +39,10 @@ struct IxWarps {
 struct IxArgs {
   const float* E;          // [B,F,D] or null (fused gather)
   const float* table;      // used when E == null
+  const float* const* shards;  // row-wise sharded table: device array of `world` shard pointers (peer memory), or null
+  int world;               // row r lives in shards[r % world] at local row r / world
+  __nv_bfloat16* x_save;        // forward, optional: X[B,F',D] rounded to bf16 (exactly the MMA operands) for the backward
+  const __nv_bfloat16* x_load;  // backward, optional: read X from there instead of gathering the rows again
   IndexMap map;            // idx[B,F]
   const float* dense_vec;  // [B,D] or null
   int64_t B;
@@ -96,17 +103,31 @@ __device__ __forceinline__ uint32_t load_sample_row(const IxArgs& a, int64_t b, 
 
 // Issue the async copies of one sample's F rows (+ the dense vector as row F) into xs[32][STRIDE].
 // src_lane = (E or table) + this lane's column offset; dst_lane = xs + sub*STRIDE + column offset.
+// Sharded table (shard_base != null, smem copy of the peer shard pointers): row r is read from the owner's HBM
+// over NVLink, shard_base[r % world] + (r / world) * D — the gather IS the collective.
 template <int D, int STRIDE>
 __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, uint32_t my_row, int F, float* dst_lane,
-                                           int sub, const float* __restrict__ dense_lane, float* dense_dst) {
+                                           int sub, const float* __restrict__ dense_lane, float* dense_dst,
+                                           const float* const* shard_base, uint32_t world, int col) {
   constexpr int kRowsPerIter = 32 / (D / 4);
 #pragma unroll 4
   for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
     const int r = r0 + sub;                                        // <= 31
     const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
     const bool ok = row != kInvalidRow;
-    const float* src = ok ? src_lane + static_cast<size_t>(row) * D : src_lane;
-    if (r < F) cp_async16(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);   // invalid row: zero-filled by the copy
+    const float* src = src_lane;
+    if (ok) {
+      if (shard_base != nullptr) {
+        const uint32_t local = row / world;
+        src = shard_base[row - local * world] + static_cast<size_t>(local) * D + col;
+      } else {
+        src = src_lane + static_cast<size_t>(row) * D;
+      }
+    }
+    if (r < F) {   // invalid row: zero-filled by the copy
+      if (RB_PEER_CA && shard_base != nullptr) cp_async16_ca(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
+      else cp_async16(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
+    }
   }
   if (dense_lane != nullptr) cp_async16(dense_dst, dense_lane, 16);
 }
@@ -182,7 +203,13 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
   constexpr int kIxWarps = IxWarps<D>::value;
   constexpr int kLanesPerRow = D / 4;
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ const float* s_shards[RB_MAX_RANKS];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (a.shards != nullptr) {
+    if (threadIdx.x < a.world) s_shards[threadIdx.x] = a.shards[threadIdx.x];
+    __syncthreads();
+  }
+  const float* const* shard_base = a.shards != nullptr ? s_shards : nullptr;
   unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * kXsFloats * 4 + os_bytes);
   float* xs_base = reinterpret_cast<float*>(my);
   OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kXsFloats * 4 + 16);   // row origin; [-16 B, 0) is the trash slot
@@ -222,15 +249,16 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
       opos[T][k] = pos;
     }
 
-  const float* src_lane = (a.E != nullptr ? a.E : a.table) + (lane % kLanesPerRow) * 4;
+  const float* src_lane = (a.E != nullptr ? a.E : (a.table != nullptr ? a.table : s_shards[0])) + (lane % kLanesPerRow) * 4;
   const int sub = lane / kLanesPerRow;
   const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
   const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
   const int64_t lane_off = (a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
 
   uint32_t row_next = load_sample_row(a, b, lane, lane_off);
+  const int col = (lane % kLanesPerRow) * 4;
   issue_rows<D, STRIDE>(src_lane, row_next, F, xs_base + dst_off, sub, dense_lane_on ? a.dense_vec + b * D + lane * 4 : nullptr,
-                        xs_base + F * STRIDE + lane * 4);
+                        xs_base + F * STRIDE + lane * 4, shard_base, a.world, col);
   cp_async_commit();
   row_next = load_sample_row(a, b + nwarps, lane, lane_off);
   int stage = 0;
@@ -241,12 +269,28 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
     if (bn < a.B) {
       float* xn = xs_base + (stage ^ 1) * kXsFloats;
       issue_rows<D, STRIDE>(src_lane, row_next, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bn * D + lane * 4 : nullptr,
-                            xn + F * STRIDE + lane * 4);
+                            xn + F * STRIDE + lane * 4, shard_base, a.world, col);
       row_next = load_sample_row(a, bn + nwarps, lane, lane_off);   // in flight during this sample's math
     }
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
+
+    if (a.x_save != nullptr) {   // the sample's operand rows as bf16, contiguous [F', D]: the backward reads them locally
+      constexpr int kChunksPerRow = D / 8;
+      __nv_bfloat16* xrow = a.x_save + b * a.Fp * D;
+      for (int cidx = lane; cidx < a.Fp * kChunksPerRow; cidx += 32) {
+        const int r = cidx / kChunksPerRow, c8 = (cidx % kChunksPerRow) * 8;
+        const float4 lo = *reinterpret_cast<const float4*>(xs + r * STRIDE + c8);
+        const float4 hi = *reinterpret_cast<const float4*>(xs + r * STRIDE + c8 + 4);
+        uint4 pk;
+        pk.x = pack_bf16(lo.x, lo.y);
+        pk.y = pack_bf16(lo.z, lo.w);
+        pk.z = pack_bf16(hi.x, hi.y);
+        pk.w = pack_bf16(hi.z, hi.w);
+        *reinterpret_cast<uint4*>(xrow + r * D + c8) = pk;
+      }
+    }
 
     float acc[6][4];
 #pragma unroll
@@ -305,7 +349,13 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   constexpr int kLanesPerRow = D / 4;
   constexpr int EPC = 16 / static_cast<int>(sizeof(DOUT));
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ const float* s_shards[RB_MAX_RANKS];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (a.shards != nullptr) {
+    if (threadIdx.x < a.world) s_shards[threadIdx.x] = a.shards[threadIdx.x];
+    __syncthreads();
+  }
+  const float* const* shard_base = a.shards != nullptr ? s_shards : nullptr;
   const int stage_bytes = kXsFloats * 4 + gs_bytes;
   unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * stage_bytes);
 
@@ -355,25 +405,36 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
       is_dense[mt][h] = (i == F) && a.dense_vec != nullptr && d_dense != nullptr;
     }
 
-  const float* src_lane = (a.E != nullptr ? a.E : a.table) + (lane % kLanesPerRow) * 4;
+  const float* src_lane = (a.E != nullptr ? a.E : (a.table != nullptr ? a.table : s_shards[0])) + (lane % kLanesPerRow) * 4;
   const int sub = lane / kLanesPerRow;
   const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
   const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
   const int64_t lane_off = (a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
 
+  constexpr int S16 = D + 8;   // bf16 elements per row of the staged X when it comes from x_load
+  const bool xl = a.x_load != nullptr;
   auto issue = [&](int64_t bb, uint32_t row, int st) {
     unsigned char* sp = my + st * stage_bytes;
     float* xn = reinterpret_cast<float*>(sp);
+    if (xl) {
+      constexpr int kChunksPerRow = D / 8;
+      const __nv_bfloat16* xrow = a.x_load + bb * a.Fp * D;
+      __nv_bfloat16* x16 = reinterpret_cast<__nv_bfloat16*>(sp);
+      for (int cidx = lane; cidx < a.Fp * kChunksPerRow; cidx += 32) {
+        const int r = cidx / kChunksPerRow, c8 = (cidx % kChunksPerRow) * 8;
+        cp_async16(x16 + r * S16 + c8, xrow + r * D + c8, 16);
+      }
+    } else
     issue_rows<D, STRIDE>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
-                          xn + F * STRIDE + lane * 4);
+                          xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4);
     const DOUT* grow = dOut + bb * dout_stride;
     load_row_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4 + 16), misalign_elems(grow), copy_width, lane);
   };
 
-  uint32_t row_next = load_sample_row(a, b, lane, lane_off);
+  uint32_t row_next = xl ? kInvalidRow : load_sample_row(a, b, lane, lane_off);
   issue(b, row_next, 0);
   cp_async_commit();
-  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
+  if (!xl) row_next = load_sample_row(a, b + nwarps, lane, lane_off);
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
@@ -382,7 +443,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
     const float* xs = reinterpret_cast<const float*>(sp);
     if (bn < a.B) {
       issue(bn, row_next, stage ^ 1);
-      row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
+      if (!xl) row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -413,10 +474,17 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[mt][k] = 0.f;
       const float* p = xs + t2 * STRIDE + nt * 8 + g;   // B[k][n] = X[k][n]: two consecutive feature rows per register
+      const unsigned short* p16 = reinterpret_cast<const unsigned short*>(sp) + t2 * S16 + nt * 8 + g;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t b0 = pack_bf16(p[ks * 16 * STRIDE], p[(ks * 16 + 1) * STRIDE]);
-        const uint32_t b1 = pack_bf16(p[(ks * 16 + 8) * STRIDE], p[(ks * 16 + 9) * STRIDE]);
+        uint32_t b0, b1;
+        if (xl) {
+          b0 = static_cast<uint32_t>(p16[ks * 16 * S16]) | (static_cast<uint32_t>(p16[(ks * 16 + 1) * S16]) << 16);
+          b1 = static_cast<uint32_t>(p16[(ks * 16 + 8) * S16]) | (static_cast<uint32_t>(p16[(ks * 16 + 9) * S16]) << 16);
+        } else {
+          b0 = pack_bf16(p[ks * 16 * STRIDE], p[(ks * 16 + 1) * STRIDE]);
+          b1 = pack_bf16(p[(ks * 16 + 8) * STRIDE], p[(ks * 16 + 9) * STRIDE]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(acc[mt], af[mt][ks], b0, b1);
       }
@@ -444,13 +512,18 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
 
 static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows, const void* idx, int idx_type,
                      const int64_t* off, const float* dense_vec, int64_t B, int F, int D, int self_interaction,
-                     int skip_gather, int tail) {
+                     int skip_gather, int tail, const float* const* shards = nullptr, int world = 1) {
   RB_CHECK_ARG(B >= 0 && F > 0, RB_ERR_ARG, "bad B/F");
   RB_CHECK_ARG(D == 16 || D == 32 || D == 64 || D == 128, RB_ERR_SHAPE, "dot interaction needs D in {16,32,64,128}, got %d", D);
   const int Fp = F + (dense_vec != nullptr ? 1 : 0);
   RB_CHECK_ARG(Fp <= 32, RB_ERR_SHAPE, "dot interaction supports at most 32 features, got %d", Fp);
   RB_CHECK_ARG(!tail || dense_vec != nullptr, RB_ERR_ARG, "tail requires dense_vec");
-  if (E == nullptr) {
+  RB_CHECK_ARG(shards == nullptr || (E == nullptr && world >= 1 && world <= RB_MAX_RANKS), RB_ERR_ARG,
+               "sharded form: no E, world in [1, %d]", RB_MAX_RANKS);
+  if (E == nullptr && shards != nullptr) {
+    RB_CHECK_ARG(idx != nullptr && rows > 0 && rows < 0xFFFFFFFFll, RB_ERR_ARG, "sharded gather needs idx and rows < 2^32-1");
+    RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
+  } else if (E == nullptr) {
     RB_CHECK_ARG(table != nullptr && idx != nullptr && rows > 0, RB_ERR_ARG, "fused gather needs table and idx");
     RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
     RB_CHECK_ARG(aligned_for(table, 4), RB_ERR_ALIGN, "table not 16 B aligned");
@@ -462,6 +535,10 @@ static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows
   RB_CHECK_ARG(dense_vec == nullptr || aligned_for(dense_vec, 4), RB_ERR_ALIGN, "dense_vec not 16 B aligned");
   a->E = E;
   a->table = table;
+  a->shards = shards;
+  a->world = world;
+  a->x_save = nullptr;
+  a->x_load = nullptr;
   a->map = make_index_map(idx, idx_type, off, 0, rows, F);
   a->dense_vec = dense_vec;
   a->B = B;
@@ -588,5 +665,51 @@ extern "C" int rb_dot_interaction_bwd(const float* E, const float* table, int64_
     return launch_bwd<float>(a, D, static_cast<const float*>(dOut), dout_stride, dE, d_dense, st);
   }
   RB_CHECK_ARG((reinterpret_cast<uintptr_t>(dOut) & 1) == 0, RB_ERR_ALIGN, "dOut not 2 B aligned");
+  return launch_bwd<__nv_bfloat16>(a, D, static_cast<const __nv_bfloat16*>(dOut), dout_stride, dE, d_dense, st);
+}
+
+// Row-wise sharded forms: the table is `world` shards in peer memory (shard_ptrs_dev: DEVICE array of
+// `world` device pointers, this rank's own shard included); `rows` is the GLOBAL row count.
+extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                              int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                              int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                              int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
+                                              void* stream) {
+  RB_CHECK_ARG(shard_ptrs_dev != nullptr, RB_ERR_ARG, "shard_ptrs_dev is null");
+  IxArgs a;
+  int rc = fill_args(&a, nullptr, nullptr, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather,
+                     tail, reinterpret_cast<const float* const*>(shard_ptrs_dev), world);
+  if (rc != RB_OK) return rc;
+  if (B == 0) return RB_OK;
+  RB_CHECK_ARG(x_save == nullptr || (reinterpret_cast<uintptr_t>(x_save) & 15) == 0, RB_ERR_ALIGN, "x_save not 16 B aligned");
+  a.x_save = static_cast<__nv_bfloat16*>(x_save);
+  const int total = a.ncols + (a.tail ? D : 0);
+  RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
+  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == RB_F32) return launch_fwd<float>(a, D, static_cast<float*>(out), out_stride, total, st);
+  RB_CHECK_ARG(out_stride - total < 64, RB_ERR_ARG, "bf16 out_stride pads more than 63 columns");
+  return launch_fwd<__nv_bfloat16>(a, D, static_cast<__nv_bfloat16*>(out), out_stride, static_cast<int>(out_stride), st);
+}
+
+extern "C" int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                              int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                              int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                              int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
+                                              float* d_dense, const void* x_saved, void* stream) {
+  RB_CHECK_ARG(shard_ptrs_dev != nullptr, RB_ERR_ARG, "shard_ptrs_dev is null");
+  IxArgs a;
+  int rc = fill_args(&a, nullptr, nullptr, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather,
+                     tail, reinterpret_cast<const float* const*>(shard_ptrs_dev), world);
+  if (rc != RB_OK) return rc;
+  if (B == 0) return RB_OK;
+  RB_CHECK_ARG(x_saved == nullptr || (reinterpret_cast<uintptr_t>(x_saved) & 15) == 0, RB_ERR_ALIGN, "x_saved not 16 B aligned");
+  a.x_load = static_cast<const __nv_bfloat16*>(x_saved);
+  RB_CHECK_ARG(dOut != nullptr && dout_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "dOut is null or stride too small");
+  RB_CHECK_ARG(dout_dtype == RB_F32 || dout_dtype == RB_BF16, RB_ERR_ARG, "bad dout_dtype %d", dout_dtype);
+  RB_CHECK_ARG((dE == nullptr || aligned_for(dE, 4)) && (d_dense == nullptr || aligned_for(d_dense, 4)), RB_ERR_ALIGN,
+               "dE/d_dense not 16 B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dout_dtype == RB_F32) return launch_bwd<float>(a, D, static_cast<const float*>(dOut), dout_stride, dE, d_dense, st);
   return launch_bwd<__nv_bfloat16>(a, D, static_cast<const __nv_bfloat16*>(dOut), dout_stride, dE, d_dense, st);
 }

@@ -45,12 +45,15 @@ struct GradSrcDev {
 
 // All uses of one table inside a step (their IndexedSlices are concatenated in use
 // order).  Global lookup position p belongs to group k when start[k] <= p < start[k+1].
+constexpr int kMaxGroups = RB_MAX_LOOKUP_GROUPS > RB_MAX_RANKS ? RB_MAX_LOOKUP_GROUPS : RB_MAX_RANKS;
+
 struct GradGroupsDev {
   int num;
   int D;
-  uint32_t start[RB_MAX_LOOKUP_GROUPS + 1];  // unused entries = 0xFFFFFFFF
+  int peer;                                  // gradient rows may live in peer memory (sharded path): copy them through L1
+  uint32_t start[kMaxGroups + 1];            // unused entries = 0xFFFFFFFF
   const float* table;                        // read-only view of the table for the FM term
-  GradSrcDev g[RB_MAX_LOOKUP_GROUPS];
+  GradSrcDev g[kMaxGroups];
 };
 
 struct LongChain {
@@ -68,7 +71,7 @@ __device__ __forceinline__ GradPos decode_pos(const GradGroupsDev& gg, uint32_t 
   GradPos q;
   q.gi = 0;
 #pragma unroll
-  for (int k = 1; k < RB_MAX_LOOKUP_GROUPS; ++k) q.gi += (p >= gg.start[k]) ? 1 : 0;
+  for (int k = 1; k < kMaxGroups; ++k) q.gi += (p >= gg.start[k]) ? 1 : 0;
   const uint32_t L = static_cast<uint32_t>(gg.g[q.gi].L);
   q.p = p - gg.start[q.gi];
   q.b = q.p / L;
@@ -254,8 +257,10 @@ __global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, in
 // cross-lane synchronisation is needed.  dynamic smem: ring[kRing][1 + Sink::kStateRows][kSegThreads][VEC].
 template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
-seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, GradGroupsDev gsrc,
-                        Sink sink, float* __restrict__ head_part, float* __restrict__ tail_part) {
+seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
+                        const __grid_constant__ GradGroupsDev gsrc, Sink sink, float* __restrict__ head_part,
+                        float* __restrict__ tail_part) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));   // padded capacity (sharded path): only the first *n_dev pairs are real
   sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
   constexpr int kEntries = kGroups * kTile;
@@ -268,6 +273,7 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
 
   const int cta_base = blockIdx.x * kEntries;
   const int cta_cnt = min(kEntries, n - cta_base);
+  if (cta_cnt <= 0) return;
   for (int i = threadIdx.x; i < cta_cnt; i += kSegThreads) {
     s_key[i + 1] = keys[cta_base + i];
     s_pos[i] = vals[cta_base + i];
@@ -305,7 +311,7 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
       const uint32_t key = tk[j];
       const GradPos q = decode_pos(gsrc, tp[j]);
       float* dst = my_ring + slot * kSlotStride;
-      cp_async_vec<VEC>(dst, grad_src0(gsrc, q, c));
+      cp_async_vec<VEC>(dst, grad_src0(gsrc, q, c), gsrc.peer != 0);
       if (kKinds > 1) {
         const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
         sink.template issue_state<VEC>(key, c, update, gsrc.g[q.gi].fm_g != nullptr, dst + kKStride, kKStride);
@@ -374,9 +380,10 @@ __device__ __forceinline__ int run_end(const uint32_t* __restrict__ keys, int lo
 
 template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
-seg_chain_kernel(const uint32_t* __restrict__ keys, int n, int D, Sink sink, const float* __restrict__ head_part,
-                 const float* __restrict__ tail_part, LongChain* __restrict__ long_list, int* __restrict__ long_count,
-                 int long_cap) {
+seg_chain_kernel(const uint32_t* __restrict__ keys, int n, const int* __restrict__ n_dev, int D, Sink sink,
+                 const float* __restrict__ head_part, const float* __restrict__ tail_part, LongChain* __restrict__ long_list,
+                 int* __restrict__ long_count, int long_cap) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   sink.prepare();
   const int tile_id = blockIdx.x * (kSegThreads / GS) + threadIdx.x / GS;
   const int lane = threadIdx.x % GS;
@@ -556,7 +563,7 @@ static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_
 
 template <class Sink>
 static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t* vals, int n, const GradGroupsDev& gsrc,
-                        const Sink& sink, unsigned char* ws, const WsLayout& lay, cudaStream_t st) {
+                        const Sink& sink, unsigned char* ws, const WsLayout& lay, cudaStream_t st, const int* n_dev = nullptr) {
   float* head = reinterpret_cast<float*>(ws + lay.head_part);
   float* tail = reinterpret_cast<float*>(ws + lay.tail_part);
   LongChain* ll = reinterpret_cast<LongChain*>(ws + lay.long_list);
@@ -571,9 +578,10 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
     if (ring_bytes > 40 * 1024)                                                                                         \
       RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                    static_cast<int>(ring_bytes)));                                                      \
-    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, gsrc, sink, \
-                                                                                                    head, tail);        \
-    seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, gsrc.D, sink, head, tail, ll, lc, cap); \
+    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, gsrc,   \
+                                                                                                    sink, head, tail);  \
+    seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, n_dev, gsrc.D, sink, head, tail, ll, lc, \
+                                                                                   cap);                                 \
     seg_long_chain_kernel<V, G, Sink><<<2 * kNumSMs, kSegThreads, 0, st>>>(gsrc.D, sink, head, tail, ll, lc, cap);      \
   }
   if (geo.vec == 4) {
@@ -634,8 +642,9 @@ static int describe_groups(const rb_lookup_group* groups, int num_groups, int D,
                            GradGroupsDev* gg) {
   gg->num = num_groups;
   gg->D = D;
+  gg->peer = 0;
   gg->table = table;
-  for (int k = 0; k <= RB_MAX_LOOKUP_GROUPS; ++k) gg->start[k] = 0xFFFFFFFFu;
+  for (int k = 0; k <= kMaxGroups; ++k) gg->start[k] = 0xFFFFFFFFu;
   int64_t start = 0;
   for (int k = 0; k < num_groups; ++k) {
     const rb_lookup_group& g = groups[k];
@@ -647,7 +656,39 @@ static int describe_groups(const rb_lookup_group* groups, int num_groups, int D,
     gg->start[k] = static_cast<uint32_t>(start);
     start += g.n;
   }
-  for (int k = num_groups; k < RB_MAX_LOOKUP_GROUPS; ++k) gg->g[k] = gg->g[0];
+  for (int k = num_groups; k < kMaxGroups; ++k) gg->g[k] = gg->g[0];
+  return RB_OK;
+}
+
+static OptSink make_sink(float* table, float* state0, float* state1, int D, const rb_opt_params* opt) {
+  const int o = opt->optimizer;
+  const bool adam = (o == RB_OPT_ADAM_LAZY || o == RB_OPT_ADAM_TF_DENSE);
+  OptSink sink;
+  sink.table = table;
+  sink.s0 = state0;
+  sink.s1 = state1;
+  sink.D = D;
+  sink.opt = o;
+  sink.lr = opt->lr;
+  sink.b1 = opt->beta_1;
+  sink.b2 = opt->beta_2;
+  sink.omb1 = 1.0f - opt->beta_1;
+  sink.omb2 = 1.0f - opt->beta_2;
+  sink.eps = opt->epsilon;
+  sink.alpha = adam ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
+  sink.alpha_dev = adam ? opt->alpha_t_dev : nullptr;
+  return sink;
+}
+
+static int check_opt(const rb_opt_params* opt, const float* state0, const float* state1, const RowGeom& geo) {
+  RB_CHECK_ARG(opt != nullptr, RB_ERR_ARG, "opt is null");
+  const int o = opt->optimizer;
+  RB_CHECK_ARG(o >= RB_OPT_SGD && o <= RB_OPT_ADAM_TF_DENSE, RB_ERR_ARG, "bad optimizer %d", o);
+  const bool adam = (o == RB_OPT_ADAM_LAZY || o == RB_OPT_ADAM_TF_DENSE);
+  RB_CHECK_ARG(!adam || (state0 != nullptr && state1 != nullptr && opt->step >= 1), RB_ERR_ARG, "Adam needs m, v and step >= 1");
+  RB_CHECK_ARG(o != RB_OPT_ADAGRAD || state0 != nullptr, RB_ERR_ARG, "Adagrad needs its accumulator");
+  RB_CHECK_ARG((state0 == nullptr || aligned_for(state0, geo.vec)) && (state1 == nullptr || aligned_for(state1, geo.vec)),
+               RB_ERR_ALIGN, "optimizer state not aligned for vec=%d", geo.vec);
   return RB_OK;
 }
 
@@ -720,21 +761,7 @@ extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, i
   RB_CHECK_ARG((state0 == nullptr || aligned_for(state0, geo.vec)) && (state1 == nullptr || aligned_for(state1, geo.vec)),
                RB_ERR_ALIGN, "optimizer state not aligned for vec=%d", geo.vec);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-  OptSink sink;
-  sink.table = table;
-  sink.s0 = state0;
-  sink.s1 = state1;
-  sink.D = D;
-  sink.opt = o;
-  sink.lr = opt->lr;
-  sink.b1 = opt->beta_1;
-  sink.b2 = opt->beta_2;
-  sink.omb1 = 1.0f - opt->beta_1;
-  sink.omb2 = 1.0f - opt->beta_2;
-  sink.eps = opt->epsilon;
-  sink.alpha = adam ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
-  sink.alpha_dev = adam ? opt->alpha_t_dev : nullptr;
+  const OptSink sink = make_sink(table, state0, state1, D, opt);
 
   const int64_t count = rows * D;
   if (o == RB_OPT_ADAM_TF_DENSE) {
@@ -849,4 +876,90 @@ extern "C" int rb_sparse_bwd_dedup(int64_t rows, int32_t D, const void* idx, int
   RB_LAUNCH_CHECK("write_num_unique_kernel");
   DedupSink sink{seg, uniq_rows, uniq_grad, D};
   return run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st);
+}
+
+// ---- sharded path: pairs collected from the peers' bucket arrays (p2p.cu) ---------------------------------------
+
+namespace rb {
+int sparse_ws_key_buffers(int64_t n, int D, int64_t rows, void* ws, uint32_t** keys, uint32_t** vals) {
+  const WsLayout lay = ws_layout(n, D, rows);
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  *keys = reinterpret_cast<uint32_t*>(wsb + lay.keys_a);
+  *vals = reinterpret_cast<uint32_t*>(wsb + lay.vals_a);
+  return RB_OK;
+}
+}  // namespace rb
+
+extern "C" int rb_sparse_bwd_prepare_collected(int64_t local_rows, int32_t D, int64_t capacity, void* ws, size_t ws_bytes,
+                                               int32_t* sorted_sel, void* stream) {
+  RB_CHECK_ARG(sorted_sel != nullptr, RB_ERR_ARG, "sorted_sel is null");
+  RowGeom geo;
+  int rc = check_common(local_rows + 1, D, capacity, &geo);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(capacity > 0, RB_ERR_ARG, "capacity must be positive");
+  const WsLayout lay = ws_layout(capacity, D, local_rows + 1);
+  rc = check_ws(ws, ws_bytes, lay);
+  if (rc != RB_OK) return rc;
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  cub::DoubleBuffer<uint32_t> dk(reinterpret_cast<uint32_t*>(wsb + lay.keys_a), reinterpret_cast<uint32_t*>(wsb + lay.keys_b));
+  cub::DoubleBuffer<uint32_t> dv(reinterpret_cast<uint32_t*>(wsb + lay.vals_a), reinterpret_cast<uint32_t*>(wsb + lay.vals_b));
+  size_t temp = lay.cub_bytes;
+  // the padding key is `local_rows` itself: key_bits(local_rows + 1) covers it and it sorts behind every real pair
+  RB_CUDA(cub::DeviceRadixSort::SortPairs(wsb + lay.cub_temp, temp, dk, dv, static_cast<int>(capacity), 0, key_bits(local_rows + 1),
+                                          static_cast<cudaStream_t>(stream)));
+  *sorted_sel = dk.selector;
+  return RB_OK;
+}
+
+extern "C" int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state1, int64_t local_rows, int32_t D, int32_t world,
+                                       int64_t n_local, int32_t L, const void* const* dE_ptrs, int64_t capacity,
+                                       const int32_t* n_valid_dev, const rb_opt_params* opt, void* ws, size_t ws_bytes,
+                                       int32_t sorted_sel, void* stream) {
+  RB_CHECK_ARG(world >= 1 && world <= RB_MAX_RANKS && dE_ptrs != nullptr && n_valid_dev != nullptr, RB_ERR_ARG,
+               "world must be in [1, %d]; dE_ptrs / n_valid_dev must not be null", RB_MAX_RANKS);
+  RB_CHECK_ARG(n_local > 0 && L > 0 && n_local % L == 0 && n_local * world < 0xFFFFFFFFll, RB_ERR_ARG, "bad n_local / L");
+  RB_CHECK_ARG(sorted_sel == 0 || sorted_sel == 1, RB_ERR_ARG, "sorted_sel must come from rb_sparse_bwd_prepare_collected");
+  RowGeom geo;
+  int rc = check_common(local_rows + 1, D, capacity, &geo);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(table != nullptr && aligned_for(table, geo.vec), RB_ERR_ALIGN, "table null or not aligned for vec=%d", geo.vec);
+  rc = check_opt(opt, state0, state1, geo);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(opt->optimizer != RB_OPT_ADAM_TF_DENSE, RB_ERR_ARG, "the sharded apply supports adam_lazy / adagrad / sgd");
+  const WsLayout lay = ws_layout(capacity, D, local_rows + 1);
+  rc = check_ws(ws, ws_bytes, lay);
+  if (rc != RB_OK) return rc;
+  // group k = source rank k: positions [k*n_local, (k+1)*n_local) address rank k's dE[B_local, L, D] (peer memory)
+  GradGroupsDev gg;
+  gg.num = world;
+  gg.D = D;
+  gg.peer = world > 1 ? 1 : 0;
+  gg.table = table;
+  for (int k = 0; k <= kMaxGroups; ++k) gg.start[k] = 0xFFFFFFFFu;
+  for (int k = 0; k < kMaxGroups; ++k) {
+    GradSrcDev& g = gg.g[k];
+    const int src_rank = k < world ? k : 0;
+    RB_CHECK_ARG(dE_ptrs[src_rank] != nullptr && aligned_for(dE_ptrs[src_rank], geo.vec), RB_ERR_ALIGN, "dE of rank %d null or misaligned", src_rank);
+    g.num_src = 1;
+    g.scale_mode = RB_SCALE_NONE;
+    g.L = L;
+    g.is64 = 0;
+    for (int j = 0; j < RB_MAX_GRAD_SOURCES; ++j) {
+      g.src[j] = nullptr;
+      g.bag_stride[j] = g.pos_stride[j] = 0;
+    }
+    g.src[0] = static_cast<const float*>(dE_ptrs[src_rank]);
+    g.bag_stride[0] = static_cast<int64_t>(L) * D;
+    g.pos_stride[0] = D;
+    g.mask_idx = nullptr;
+    g.count = nullptr;
+    g.fm_g = nullptr;
+    g.fm_s = nullptr;
+    if (k < world) gg.start[k] = static_cast<uint32_t>(k * n_local);
+  }
+  const OptSink sink = make_sink(table, state0, state1, D, opt);
+  const uint32_t *keys, *vals;
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  sorted_pairs(wsb, lay, sorted_sel, &keys, &vals);
+  return run_segments(geo, keys, vals, static_cast<int>(capacity), gg, sink, wsb, lay, static_cast<cudaStream_t>(stream), n_valid_dev);
 }

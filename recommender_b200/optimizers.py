@@ -19,12 +19,13 @@ from .layers import Embedding
 
 def _split(model_or_vars):
     if isinstance(model_or_vars, torch.nn.Module):
-        embs = [m for m in model_or_vars.modules() if isinstance(m, Embedding)]
+        # layers.Embedding and the sharded embeddings (sharded.py's local shard, p2p.P2PShardedEmbedding)
+        embs = [m for m in model_or_vars.modules() if hasattr(m, "apply_pending")]
         dense = [p for p in model_or_vars.parameters() if p.requires_grad]
         return embs, dense
     embs, dense = [], []
     for v in model_or_vars:
-        (embs if isinstance(v, Embedding) else dense).append(v)
+        (embs if hasattr(v, "apply_pending") else dense).append(v)
     return embs, dense
 
 

@@ -1,0 +1,403 @@
+"""Row-wise sharded embedding over NVLink/NVSwitch PEER MEMORY: the gather is the collective.
+
+One process per GPU.  Row r of the (T-table) embedding lives on rank r mod G at local row r div G.
+Instead of exchanging rows and gradients with all-to-alls (sharded.py, the NCCL path), every rank
+maps the other ranks' buffers into its address space (CUDA IPC) and the kernels read them directly:
+
+  forward   rb_dot_interaction_fwd_sharded: the interaction kernel's cp.async ring pulls each sample's
+            26 rows from whichever GPU owns them (~(G-1)/G of the reads cross NVLink) while the MMA of
+            the previous sample runs — no all-to-all, no serve-side gather, no staging buffer;
+  backward  rb_dot_interaction_bwd_sharded writes dE[B_local, F, D] into this rank's shared buffer; the
+            OWNER of a row then pulls the gradient rows of all its lookups — from all ranks — inside
+            the segmented reduction (rb_sparse_bwd_apply_p2p), sums duplicates in one deterministic
+            order and applies the fused optimizer update to its shard;
+  routing   rb_bucket_by_owner publishes (local row, position) per owner in peer memory; the owner
+            collects its slices (rb_p2p_collect_keys) into a STATIC-capacity pair list and radix-sorts
+            it on a side stream during the forward.
+
+Only two tiny all-reduces per step order the ranks (after the bucket arrays are published; after all
+backward kernels finished, before any shard is updated), so every shape is static and the whole
+sharded step can be captured as one CUDA graph.  Dense MLPs are data-parallel (sharded.ShardedDLRM).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib, ops
+from ._lib import check, lib
+from .layers import MLP
+
+
+class SharedBuffer:
+    """Device memory allocated by the library (cudaMalloc) with its IPC handle; `.tensor` is a zero-copy torch view."""
+
+    def __init__(self, shape: Sequence[int], dtype: torch.dtype, device: torch.device):
+        self.shape, self.dtype, self.device = tuple(int(s) for s in shape), dtype, device
+        nbytes = max(1, int(torch.tensor([], dtype=dtype).element_size()))
+        for s in self.shape:
+            nbytes *= s
+        self.nbytes = max(nbytes, 256)
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * _lib.RB_IPC_HANDLE_BYTES)()
+        with torch.cuda.device(device):
+            check(lib.rb_shared_alloc(self.nbytes, C.byref(ptr), handle), "rb_shared_alloc")
+        self.ptr, self.handle = int(ptr.value), bytes(handle)
+        typestr = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        self.__cuda_array_interface__ = dict(shape=self.shape, typestr=typestr, data=(self.ptr, False), version=3, strides=None)
+        self.tensor = torch.as_tensor(self, device=device)
+        assert self.tensor.data_ptr() == self.ptr
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            check(lib.rb_shared_free(self.ptr), "rb_shared_free")
+            self.ptr = 0
+
+
+class PeerLink:
+    """How the ranks allocate peer-readable buffers and order themselves.  `alloc(name, shape, dtype)` is a
+    collective: every rank allocates a buffer of the SAME shape and gets back (its tensor, the device
+    pointers of all ranks' buffers — possibly as a callable resolved later); `barrier()` is a
+    stream-ordered rendezvous of all ranks."""
+
+    world: int
+    rank: int
+
+    def alloc(self, name: str, shape: Sequence[int], dtype: torch.dtype):
+        raise NotImplementedError
+
+    def barrier(self) -> None:
+        raise NotImplementedError
+
+
+class DistPeerLink(PeerLink):
+    """Real ranks (one process per GPU).  Buffers are CUDA virtual-memory allocations shared through
+    torch.distributed's symmetric-memory rendezvous (2 MB pages, file-descriptor exchange): a table shard of
+    several GB mapped with legacy cudaIpc handles reads ~20x slower under random access (measured: 27 GB/s
+    against 490 GB/s).  `legacy_ipc=True` keeps the cudaIpc route (rb_shared_alloc / rb_ipc_open) for
+    small buffers or hosts without symmetric memory.  The barrier is a 1-element NCCL all-reduce on the
+    current stream (capturable in a CUDA graph)."""
+
+    def __init__(self, group=None, device=None, legacy_ipc: Optional[bool] = None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.legacy_ipc = bool(int(os.environ.get("RB_P2P_LEGACY_IPC", "0"))) if legacy_ipc is None else legacy_ipc
+        self._keep = []
+
+    def alloc(self, name, shape, dtype):
+        if self.world == 1:
+            buf = SharedBuffer(shape, dtype, self.device)
+            self._keep.append(buf)
+            return buf.tensor, [buf.ptr]
+        if not self.legacy_ipc:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(*[int(x) for x in shape], dtype=dtype, device=self.device)
+            hdl = symm_mem.rendezvous(t, self.group)
+            self._keep.append((t, hdl))
+            return t, [int(p) for p in hdl.buffer_ptrs]
+        buf = SharedBuffer(shape, dtype, self.device)
+        self._keep.append(buf)
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, buf.handle, group=self.group)
+        ptrs = []
+        for k, h in enumerate(handles):
+            if k == self.rank:
+                ptrs.append(buf.ptr)
+                continue
+            p = C.c_void_p()
+            raw = (C.c_ubyte * _lib.RB_IPC_HANDLE_BYTES).from_buffer_copy(h)
+            check(lib.rb_ipc_open(raw, C.byref(p)), f"rb_ipc_open({name}, rank {k})")
+            ptrs.append(int(p.value))
+        return buf.tensor, ptrs
+
+    def barrier(self):
+        dist.all_reduce(self._token, group=self.group)
+        self._token.zero_()
+
+
+class LocalPeerLink(PeerLink):
+    """G emulated ranks inside ONE process on ONE GPU (tests, single-GPU development): pointers are
+    shared directly and the caller runs the ranks' phases in lock-step, so the barrier is a no-op."""
+
+    def __init__(self, world: int, rank: int, registry: Dict[str, List[Optional[SharedBuffer]]], device=None):
+        self.world, self.rank, self.registry = world, rank, registry
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def alloc(self, name, shape, dtype):
+        buf = SharedBuffer(shape, dtype, self.device)
+        slots = self.registry.setdefault(name, [None] * self.world)
+        slots[self.rank] = buf
+        return buf.tensor, (lambda: [b.ptr for b in slots])   # resolved lazily, once every emulated rank has registered
+
+    def barrier(self):
+        pass
+
+
+def _ptr_array(ptrs: Sequence[int]):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+class _P2PInteractFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, emb, idx, dense_vec, flags, out_dtype, pad_to):
+        dense_vec = dense_vec.contiguous()
+        out = emb._interaction_fwd(idx, dense_vec, flags, out_dtype, pad_to)
+        ctx.emb, ctx.idx, ctx.flags = emb, idx, flags
+        ctx.save_for_backward(dense_vec)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        (dense_vec,) = ctx.saved_tensors
+        if dOut.stride(-1) != 1:
+            dOut = dOut.contiguous()
+        d_dense = ctx.emb._interaction_bwd(ctx.idx, dense_vec, ctx.flags, dOut)
+        return None, None, None, d_dense, None, None, None
+
+
+class P2PShardedEmbedding(nn.Module):
+    """`Embedding(input_dim, output_dim, num_tables=T)` row-wise sharded over `link.world` GPUs with the
+    exchange done by the kernels over peer memory.  Call surface used by the models: `interact(...)`,
+    `apply_pending(...)` (driven by optimizers.*), `load_full_table` / `full_row_ids` (tests)."""
+
+    def __init__(self, input_dim: int, output_dim: int, *, num_tables: int = 1, link: PeerLink, device=None,
+                 generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25):
+        super().__init__()
+        self.link = link
+        self.world, self.rank = link.world, link.rank
+        if self.world > _lib.RB_MAX_RANKS:
+            raise ValueError(f"at most {_lib.RB_MAX_RANKS} ranks")
+        self.input_dim, self.output_dim, self.num_tables = int(input_dim), int(output_dim), int(num_tables)
+        self.capacity_factor = float(capacity_factor)
+        self.save_rows = True     # forward keeps the bf16 operand rows so the backward does not cross NVLink again
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        G, total = self.world, self.input_dim * self.num_tables
+        self.total_rows = total
+        self.local_rows = max((total - self.rank + G - 1) // G, 1)       # rows r with r mod G == rank
+        shard_rows = max((total + G - 1) // G, 1)                        # same shape on every rank (rank 0's count)
+        self._shard_full, self._shard_ptrs = link.alloc("shard", (shard_rows, self.output_dim), torch.float32)
+        self.embeddings = self._shard_full[: self.local_rows]
+        self._shard_full.uniform_(-0.05, 0.05, generator=generator)     # Keras default initialiser
+        self._row_offset = (torch.arange(self.num_tables, dtype=torch.int64, device=self.device) * self.input_dim
+                            if self.num_tables > 1 else None)
+        self._anchor = torch.zeros((), dtype=torch.float32, device=self.device, requires_grad=True)
+        self.opt_state: Dict[str, torch.Tensor] = {}
+        self._shape = None           # (B_local, F) the step buffers were built for
+        self._pending = False
+        self._side: Optional[torch.cuda.Stream] = None
+        self._shard_ptr_dev: Optional[torch.Tensor] = None
+        self._routed_by_caller = False
+
+    # ---- lazily built per-shape step buffers -----------------------------------------------------------------
+    def _resolve(self, v):
+        return v() if callable(v) else v
+
+    def _build(self, B: int, F: int) -> None:
+        if self._shape == (B, F):
+            return
+        if self._shape is not None:
+            raise ValueError(f"P2PShardedEmbedding was built for idx {self._shape}, got {(B, F)} (static shapes)")
+        dev, G, D = self.device, self.world, self.output_dim
+        n = B * F
+        self.n_local = n
+        self.capacity = int(n * self.capacity_factor) + 1024
+        self._dE, self._dE_ptrs = self.link.alloc("dE", (n, D), torch.float32)
+        self._b_rows, self._rows_ptrs = self.link.alloc("b_rows", (n,), torch.int64)
+        self._b_perm, self._perm_ptrs = self.link.alloc("b_perm", (n,), torch.int32)
+        self._b_counts, self._counts_ptrs = self.link.alloc("b_counts", (max(G, 8),), torch.int64)
+        self._inv_perm = torch.empty(n, dtype=torch.int32, device=dev)
+        self._bucket_ws = torch.empty(max(lib.rb_bucket_by_owner_workspace_bytes(n, G), 256), dtype=torch.uint8, device=dev)
+        self._sort_ws = ops.sparse_workspace(self.capacity, D, self.local_rows + 1, dev)
+        self._n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._x_saved = torch.empty(B, F + 1, D, dtype=torch.bfloat16, device=dev)    # forward -> backward operand rows
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._shape = (B, F)
+        self._side = torch.cuda.Stream(device=dev)
+
+    def _shard_ptrs_dev(self) -> torch.Tensor:
+        if self._shard_ptr_dev is None:
+            self._shard_ptr_dev = torch.tensor(self._resolve(self._shard_ptrs), dtype=torch.int64, device=self.device)
+        return self._shard_ptr_dev
+
+    # ---- shard <-> full table (tests, checkpoints) ---------------------------------------------------------------
+    def load_full_table(self, full: torch.Tensor) -> None:
+        full = torch.as_tensor(full, dtype=torch.float32)
+        self.embeddings.copy_(full[self.rank::self.world].to(self.device))
+
+    def full_row_ids(self) -> torch.Tensor:
+        return torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank
+
+    # ---- the step, phase by phase (DistPeerLink: called in this order by interact/apply_pending) ---------------------
+    def route(self, idx: torch.Tensor) -> None:
+        """Phase 1: publish this rank's lookups bucketed by owner (peer-readable)."""
+        B, F = idx.shape
+        self._build(B, F)
+        off = self._row_offset if self.num_tables > 1 else None
+        check(lib.rb_bucket_by_owner(idx.data_ptr(), ops._idx(idx), B * F, F, ops._ptr(off), 0, self.world,
+                                     self._b_rows.data_ptr(), self._b_perm.data_ptr(), self._inv_perm.data_ptr(),
+                                     self._b_counts.data_ptr(),
+                                     self._bucket_ws.data_ptr(), self._bucket_ws.numel(), ops._stream()), "rb_bucket_by_owner")
+
+    def collect_and_sort(self) -> None:
+        """Phase 2 (after every rank's route()): gather the pairs addressed to this owner and radix-sort them."""
+        check(lib.rb_p2p_collect_keys(self.world, self.rank, self.n_local, _ptr_array(self._resolve(self._rows_ptrs)),
+                                      _ptr_array(self._resolve(self._perm_ptrs)), _ptr_array(self._resolve(self._counts_ptrs)),
+                                      self.local_rows, self.capacity, self._sort_ws.data_ptr(), self._sort_ws.numel(),
+                                      self.output_dim, self._n_valid.data_ptr(), self.overflow.data_ptr(), ops._stream()),
+              "rb_p2p_collect_keys")
+        sel = C.c_int32(0)
+        check(lib.rb_sparse_bwd_prepare_collected(self.local_rows, self.output_dim, self.capacity, self._sort_ws.data_ptr(),
+                                                  self._sort_ws.numel(), C.byref(sel), ops._stream()), "rb_sparse_bwd_prepare_collected")
+        self._sel = int(sel.value)
+
+    def _interaction_fwd(self, idx, dense_vec, flags, out_dtype, pad_to):
+        si, sg, tail = flags
+        B, F = idx.shape
+        D = self.output_dim
+        Fp = F + 1
+        width = ops.interaction_ncols(Fp, si, sg) + (D if tail else 0)
+        stride = (width + pad_to - 1) // pad_to * pad_to if out_dtype == torch.bfloat16 else width
+        out = torch.empty(B, stride, dtype=out_dtype, device=idx.device)
+        off = self._row_offset if self.num_tables > 1 else None
+        check(lib.rb_dot_interaction_fwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
+                                                 ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
+                                                 int(tail), out.data_ptr(), ops._float_type(out_dtype), stride,
+                                                 self._x_saved.data_ptr() if self.save_rows else None, ops._stream()),
+              "rb_dot_interaction_fwd_sharded")
+        return out
+
+    def _interaction_bwd(self, idx, dense_vec, flags, dOut):
+        si, sg, tail = flags
+        B, F = idx.shape
+        D = self.output_dim
+        d_dense = torch.empty(B, D, dtype=torch.float32, device=idx.device)
+        off = self._row_offset if self.num_tables > 1 else None
+        check(lib.rb_dot_interaction_bwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
+                                                 ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
+                                                 int(tail), dOut.data_ptr(), ops._float_type(dOut.dtype), int(dOut.stride(0)),
+                                                 self._dE.data_ptr(), d_dense.data_ptr(),
+                                                 self._x_saved.data_ptr() if self.save_rows else None, ops._stream()),
+              "rb_dot_interaction_bwd_sharded")
+        self._pending = True
+        return d_dense
+
+    def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
+                 out_dtype=torch.float32, pad_to=1, routed=False) -> torch.Tensor:
+        """ctr/model.py:49-55 on the sharded table.  Unless the caller already ran route()/collect_and_sort()
+        (`routed=True`, lock-step emulation), this also publishes the routing, meets the other ranks and starts
+        the owner-side sort on a side stream so that it overlaps the forward."""
+        idx = idx.contiguous()
+        self._routed_by_caller = bool(routed)
+        if not routed:
+            self.route(idx)
+            self.link.barrier()                  # every rank's bucket arrays are published (and last step's updates are done)
+            if torch.is_grad_enabled():
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self.collect_and_sort()
+                    self._sorted_ev = self._side.record_event()
+        return _P2PInteractFn.apply(self._anchor, self, idx, dense_vec.float(), (self_interaction, skip_gather, tail), out_dtype, pad_to)
+
+    def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                      initial_accumulator_value=0.1, alpha_dev=None) -> int:
+        """Owner-side segmented reduction + optimizer row update, gradient rows pulled from all ranks' dE."""
+        if not self._pending:
+            return 0
+        self._pending = False
+        st = self.opt_state
+        if kind == "adam_lazy":
+            if "m" not in st:
+                st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
+            s0, s1 = st["m"], st["v"]
+        elif kind == "adagrad":
+            if "acc" not in st:
+                st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
+            s0, s1 = st["acc"], None
+        elif kind == "sgd":
+            s0 = s1 = None
+        else:
+            raise ValueError(f"the peer-memory path supports adam_lazy / adagrad / sgd, not {kind}")
+        if not self._routed_by_caller:
+            torch.cuda.current_stream().wait_event(self._sorted_ev)
+            self.link.barrier()                  # every rank's backward has written its dE and stopped reading the shards
+        opt = ops._opt_params(kind, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+        _, F = self._shape
+        check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
+                                          self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
+                                          self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
+                                          self._sel, ops._stream()), "rb_sparse_bwd_apply_p2p")
+        return self.n_local
+
+    def check_overflow(self) -> None:
+        if int(self.overflow.item()) != 0:
+            self.overflow.zero_()
+            raise RuntimeError("an owner received more lookups than its static capacity; raise capacity_factor")
+
+
+class P2PShardedDLRM(nn.Module):
+    """ctr/model.py:34-58 with the table sharded row-wise over peer memory and the MLPs replicated."""
+
+    def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
+                 num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, group=None, link: Optional[PeerLink] = None, device=None,
+                 compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
+                 capacity_factor: float = 1.25):
+        super().__init__()
+        if bottom_mlp_units[-1] != embedding_size:
+            raise ValueError("bottom_mlp_units[-1] must equal embedding_size")       # ctr/model.py:52,55
+        self.group = group
+        self.link = link if link is not None else DistPeerLink(group, device)
+        self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator)
+        self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)
+        self.embedding_layer = P2PShardedEmbedding(vocab_size, embedding_size, num_tables=num_tables, link=self.link, device=device,
+                                                   generator=generator, capacity_factor=capacity_factor)
+        self.num_cat_fea, self.num_int_fea, self.embedding_size = num_cat_fea, num_int_fea, embedding_size
+        self._synced = False
+        self._flat = None
+
+    def sync_dense_parameters(self) -> None:
+        if isinstance(self.link, DistPeerLink) and self.link.world > 1:
+            for p in self.parameters():
+                dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        self._synced = True
+
+    def forward(self, inputs, training=None, mask=None, routed=False):
+        int_features = inputs["int_features"].reshape(-1, self.num_int_fea)
+        cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)
+        bmlp_output = self.bottom_mlp(int_features)
+        width = (self.num_cat_fea + 1) ** 2 + self.embedding_size
+        if len(self.top_mlp.kernels) == 0:
+            self.top_mlp.build(width, bmlp_output.device)
+        if not self._synced:
+            self.sync_dense_parameters()
+        bf16 = self.top_mlp.compute_dtype == torch.bfloat16
+        tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
+                                                   out_dtype=torch.bfloat16 if bf16 else torch.float32, pad_to=8 if bf16 else 1,
+                                                   routed=routed)
+        return self.top_mlp(tmlp_input).squeeze(1)
+
+    def reduce_dense_grads(self) -> None:
+        """SUM over replicas of the MLP gradients in one flat all-reduce (MirroredStrategy with Reduction.NONE
+        losses); called by the optimizers."""
+        if not isinstance(self.link, DistPeerLink) or self.link.world == 1:
+            return
+        params = [p for p in self.parameters() if p.grad is not None]
+        if not params:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        o = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[o:o + n].view_as(p.grad))
+            o += n

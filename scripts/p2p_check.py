@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Multi-process check of the peer-memory sharded path (run under torchrun on >= 2 GPUs of one box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/p2p_check.py
+
+Every rank trains a P2PShardedDLRM for a few steps on its own batches; rank 0 also runs the same global
+problem UNSHARDED (plain DLRM, gradients of the G local losses summed) and compares the reassembled table."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ctr_oracle as O  # noqa: E402  (test infrastructure: initial weights only)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from recommender_b200.model import DLRM, bce_clipped
+    from recommender_b200.optimizers import Adam
+    from recommender_b200.p2p import P2PShardedDLRM
+    V, D, B, T, steps = 5000, 32, 512, 26, 3
+    params = O.init_dlrm(4, [64, D], [64, 1], D, V * T)
+    model = P2PShardedDLRM([64, D], [64, 1], D, V, 26, 13, num_tables=T, device=dev)
+    model.embedding_layer.load_full_table(torch.tensor(params["table"]))
+    model.bottom_mlp.load_arrays(params["bottom"], dev)
+    model.top_mlp.load_arrays(params["top"], dev)
+    opt = Adam()
+    batches = [[O.synth_batch(B, V, seed=100 * s + r, dist="zipf") for r in range(world)] for s in range(steps)]
+    for s in range(steps):
+        cat, dense_x, label = (torch.tensor(a, device=dev) for a in batches[s][rank])
+        loss = bce_clipped(model({"cat_features": cat, "int_features": dense_x}), label)
+        loss.backward()
+        opt.apply_gradients(model)
+    model.embedding_layer.check_overflow()
+    torch.cuda.synchronize()
+    # gather the shards on rank 0
+    emb = model.embedding_layer
+    shards = [torch.empty((V * T - k + world - 1) // world, D, device=dev) for k in range(world)]
+    if rank == 0:
+        shards[0].copy_(emb.embeddings)
+        for k in range(1, world):
+            dist.recv(shards[k], src=k)
+    else:
+        dist.send(emb.embeddings.contiguous(), dst=0)
+    ok = True
+    if rank == 0:
+        full = torch.empty(V * T, D, device=dev)
+        for k in range(world):
+            full[k::world] = shards[k]
+        ref = DLRM([64, D], [64, 1], D, V, 26, 13, num_tables=T, device=dev)
+        ref.embedding_layer.embeddings.copy_(torch.tensor(params["table"]))
+        ref.bottom_mlp.load_arrays(params["bottom"], dev)
+        ref.top_mlp.load_arrays(params["top"], dev)
+        ropt = Adam()
+        for s in range(steps):
+            total = 0
+            for r in range(world):        # MirroredStrategy with Reduction.NONE: the replicas' gradients are summed
+                cat, dense_x, label = (torch.tensor(a, device=dev) for a in batches[s][r])
+                total = total + bce_clipped(ref({"cat_features": cat, "int_features": dense_x}), label)
+            total.backward()
+            ropt.apply_gradients(ref)
+        torch.cuda.synchronize()
+        got, want = full.cpu().numpy(), ref.embedding_layer.embeddings.cpu().numpy()
+        moved = np.abs(want - params["table"]) > 0
+        err = np.abs(got - want).max()
+        print(f"p2p_check: world={world} rows moved={int(moved.any(1).sum())} max|sharded - unsharded|={err:.3e}")
+        ok = bool(err <= 2e-6 and moved.any())
+        print("p2p_check: OK" if ok else "p2p_check: MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
