@@ -244,7 +244,10 @@ def run_b200(args):
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     from recommender_b200 import build, ops
-    build.build()
+    if local_rank == 0:
+        build.build()              # a no-op when the in-tree .so matches the sources
+    if world > 1:
+        dist.barrier()
     from recommender_b200.model import DLRM, bce_clipped
     from recommender_b200.optimizers import Adam
 

@@ -341,12 +341,16 @@ int rb_enable_peer_access(int32_t peer_device);
  * shard_ptrs_dev: DEVICE array of `world` device pointers (own shard included); rows: GLOBAL row count.
  * x_save (optional, bf16 [B, F', D]): the forward also stores the operand rows rounded to bf16 — exactly
  * what its MMAs consume — and the backward given the same buffer as x_saved reads them locally instead
- * of gathering the rows over NVLink a second time (bit-identical results). */
+ * of gathering the rows over NVLink a second time (bit-identical results).
+ * shadow_ptrs_dev (optional, DEVICE array of `world` bf16 shard pointers): bf16 copies of the shards kept in
+ * step by rb_sparse_bwd_apply_p2p(shadow_bf16); the forward then moves 2*D bytes per row over NVLink
+ * instead of 4*D, and since the MMA operands are the rows rounded to bf16 either way, results are unchanged. */
 int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
                                    const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                                    const float* dense_vec, int64_t B, int32_t F, int32_t D,
                                    int32_t self_interaction, int32_t skip_gather, int32_t tail,
-                                   void* out, int32_t out_dtype, int64_t out_stride, void* x_save, void* stream);
+                                   void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
+                                   const void* const* shadow_ptrs_dev, void* stream);
 int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
                                    const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                                    const float* dense_vec, int64_t B, int32_t F, int32_t D,
@@ -375,7 +379,7 @@ int rb_sparse_bwd_prepare_collected(int64_t local_rows, int32_t D, int64_t capac
 int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state1, int64_t local_rows, int32_t D, int32_t world,
                             int64_t n_local, int32_t L, const void* const* dE_ptrs, int64_t capacity,
                             const int32_t* n_valid_dev, const rb_opt_params* opt, void* ws, size_t ws_bytes,
-                            int32_t sorted_sel, void* stream);
+                            int32_t sorted_sel, void* shadow_bf16, void* stream);
 
 #ifdef __cplusplus
 }

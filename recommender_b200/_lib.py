@@ -87,14 +87,14 @@ SIGNATURES = {
     "rb_ipc_close": (C.c_int, [_p]),
     "rb_enable_peer_access": (C.c_int, [_i32]),
     "rb_dot_interaction_fwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p,
-                                                 _p]),
+                                                 _p, _p]),
     "rb_dot_interaction_bwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64,
                                                  _p, _p, _p, _p]),
     "rb_p2p_collect_keys": (C.c_int, [_i32, _i32, _i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64, _i64,
                                       _p, C.c_size_t, _i32, _p, _p, _p]),
     "rb_sparse_bwd_prepare_collected": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p]),
     "rb_sparse_bwd_apply_p2p": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i64, _i32, C.POINTER(C.c_void_p), _i64, _p,
-                                          C.POINTER(RbOptParams), _p, C.c_size_t, _i32, _p]),
+                                          C.POINTER(RbOptParams), _p, C.c_size_t, _i32, _p, _p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

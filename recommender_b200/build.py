@@ -38,7 +38,7 @@ def _fingerprint() -> str:
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(PKG, "..", "include", "recsys_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())     # names, not paths: the GPU box mounts the repo elsewhere
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

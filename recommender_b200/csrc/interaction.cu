@@ -337,6 +337,153 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
   }
 }
 
+// ---- forward, sharded table with a bf16 shadow ---------------------------------------------------------------------
+// The owners keep a bf16 copy of their shard (refreshed by the optimizer row update): the rows cross
+// NVLink as 2*D bytes instead of 4*D and are ALREADY the MMA operands (same values as rounding the fp32
+// row on arrival, so results are bit-identical to the fp32-source kernel).  smem per warp:
+// kIxStages x { x16[32][D+8] bf16 | dense vector fp32[D] } | 16 B trash slot | staged output row.
+template <int D, typename OUT>
+__global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
+dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ shadows, OUT* __restrict__ out, int64_t out_stride,
+                             int write_width, int os_bytes) {
+  constexpr int S16 = D + 8;                    // bf16 elements per tile row: 4*g + t bank pattern, conflict-free
+  constexpr int kTileBytes = 32 * S16 * 2;
+  constexpr int kStageBytes = kTileBytes + D * 4;
+  constexpr int kIxWarps = IxWarps<D>::value;
+  constexpr int kLanesPerRow = D / 8;           // 16-byte chunks per bf16 row
+  constexpr int kRowsPerIter = 32 / kLanesPerRow;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ const __nv_bfloat16* s_shards[RB_MAX_RANKS];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x < a.world) s_shards[threadIdx.x] = shadows[threadIdx.x];
+  __syncthreads();
+  unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * kStageBytes + os_bytes);
+  OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kStageBytes + 16);
+
+  for (int i = lane; i < (kIxStages * kStageBytes + os_bytes) / 16; i += 32) reinterpret_cast<float4*>(my)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kIxWarps;
+  int64_t b = static_cast<int64_t>(blockIdx.x) * kIxWarps + warp;
+  if (b >= a.B) return;
+
+  const int g = lane / 4, t2 = (lane % 4) * 2;
+  const int F = a.F;
+  const int total = a.ncols + (a.tail ? D : 0);
+  const int width = write_width > total ? write_width : total;
+
+  constexpr int kTileM[6] = {0, 0, 0, 0, 1, 1};
+  constexpr int kTileN[6] = {0, 1, 2, 3, 2, 3};
+  int opos[6][4];
+#pragma unroll
+  for (int T = 0; T < 6; ++T)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = kTileM[T] * 16 + g + (k / 2) * 8;
+      const int j = kTileN[T] * 8 + t2 + (k % 2);
+      int pos = -static_cast<int>(16 / sizeof(OUT));
+      if (i < a.Fp && j < a.Fp) {
+        if (!a.self_interaction) {
+          if (j > i) pos = out_pos(i, j, a);
+        } else if (j >= i) {
+          pos = out_pos(j, i, a);
+        }
+      }
+      opos[T][k] = pos;
+    }
+
+  const int sub = lane / kLanesPerRow;
+  const int col = (lane % kLanesPerRow) * 8;
+  const uint32_t world = static_cast<uint32_t>(a.world);
+  const int64_t lane_off = (a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
+  const bool dense_lane_on = a.dense_vec != nullptr && lane < D / 4;
+
+  auto issue = [&](int64_t bb, uint32_t my_row, int st) {
+    unsigned char* sp = my + st * kStageBytes;
+    __nv_bfloat16* x16 = reinterpret_cast<__nv_bfloat16*>(sp);
+#pragma unroll 2
+    for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
+      const int r = r0 + sub;
+      const uint32_t row = __shfl_sync(0xffffffffu, my_row, r & 31);
+      const bool ok = row != kInvalidRow;
+      const __nv_bfloat16* src = s_shards[0];
+      if (ok) {
+        const uint32_t local = row / world;
+        src = s_shards[row - local * world] + static_cast<size_t>(local) * D + col;
+      }
+      if (r < F) cp_async16_ca(x16 + r * S16 + col, src, ok ? 16 : 0);
+    }
+    if (dense_lane_on) cp_async16(sp + kTileBytes + lane * 16, a.dense_vec + bb * D + lane * 4, 16);
+  };
+
+  uint32_t row_next = load_sample_row(a, b, lane, lane_off);
+  issue(b, row_next, 0);
+  cp_async_commit();
+  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
+  int stage = 0;
+
+  for (; b < a.B; b += nwarps) {
+    const int64_t bn = b + nwarps;
+    unsigned char* sp = my + stage * kStageBytes;
+    __nv_bfloat16* x16 = reinterpret_cast<__nv_bfloat16*>(sp);
+    const float* dvec = reinterpret_cast<const float*>(sp + kTileBytes);
+    if (bn < a.B) {
+      issue(bn, row_next, stage ^ 1);
+      row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    if (a.dense_vec != nullptr) {   // the dense vector joins the tile as row F (bf16 operand)
+      for (int d = lane * 2; d < D; d += 64) *reinterpret_cast<uint32_t*>(x16 + F * S16 + d) = pack_bf16(dvec[d], dvec[d + 1]);
+      __syncwarp();
+    }
+    if (a.x_save != nullptr) {
+      __nv_bfloat16* xrow = a.x_save + b * a.Fp * D;
+      for (int cidx = lane; cidx < a.Fp * kLanesPerRow; cidx += 32) {
+        const int r = cidx / kLanesPerRow, c8 = (cidx % kLanesPerRow) * 8;
+        *reinterpret_cast<uint4*>(xrow + r * D + c8) = *reinterpret_cast<const uint4*>(x16 + r * S16 + c8);
+      }
+    }
+
+    float acc[6][4];
+#pragma unroll
+    for (int T = 0; T < 6; ++T)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[T][k] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < D; k0 += 16) {
+      uint32_t af[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const __nv_bfloat16* p = x16 + (mt * 16 + g) * S16 + k0 + t2;
+        af[mt][0] = *reinterpret_cast<const uint32_t*>(p);
+        af[mt][1] = *reinterpret_cast<const uint32_t*>(p + 8 * S16);
+        af[mt][2] = *reinterpret_cast<const uint32_t*>(p + 8);
+        af[mt][3] = *reinterpret_cast<const uint32_t*>(p + 8 * S16 + 8);
+      }
+#pragma unroll
+      for (int T = 0; T < 6; ++T) {
+        const int nt = kTileN[T];
+        mma_bf16_16816(acc[T], af[kTileM[T]], af[nt / 2][(nt & 1) ? 1 : 0], af[nt / 2][(nt & 1) ? 3 : 2]);
+      }
+    }
+#pragma unroll
+    for (int T = 0; T < 6; ++T)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) os[opos[T][k]] = Elem<OUT>::from(acc[T][k]);
+    if (a.tail) {
+      for (int d = lane; d < D; d += 32) os[a.ncols + d] = Elem<OUT>::from(dvec[d]);
+    }
+    __syncwarp();
+    OUT* grow = out + b * out_stride;
+    store_row<OUT>(grow, os, misalign_elems(grow), width, lane);
+    __syncwarp();
+    stage ^= 1;
+  }
+}
+
 // ---- backward ------------------------------------------------------------------------------------------------
 // dX = (G + G^T) X.  smem per warp: kIxStages x { xs[32][D+4] fp32 | 16 B of zeros | staged dOut row }.
 template <int D, typename DOUT, bool SELF>
@@ -587,6 +734,28 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
   return RB_OK;
 }
 
+template <typename OUT>
+static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shadows, OUT* out, int64_t out_stride, int write_width,
+                        cudaStream_t st) {
+  const int total = a.ncols + (a.tail ? D : 0);
+  const int width = write_width > total ? write_width : total;
+  const int os_bytes = 16 + ((width * static_cast<int>(sizeof(OUT)) + 15) / 16) * 16;
+  int rc = RB_OK;
+#define LAUNCH(DD)                                                                                                      \
+  {                                                                                                                     \
+    constexpr int W = IxWarps<DD>::value;                                                                               \
+    size_t smem = static_cast<size_t>(W) * (kIxStages * (32 * (DD + 8) * 2 + DD * 4) + os_bytes);                       \
+    rc = set_smem(dot_interaction_fwd16_kernel<DD, OUT>, smem);                                                         \
+    if (rc != RB_OK) return rc;                                                                                         \
+    dot_interaction_fwd16_kernel<DD, OUT><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, shadows, out, out_stride,   \
+                                                                                           write_width, os_bytes);      \
+  }
+  if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
+#undef LAUNCH
+  RB_LAUNCH_CHECK("dot_interaction_fwd16_kernel");
+  return RB_OK;
+}
+
 template <typename DOUT>
 static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_stride, float* dE, float* d_dense, cudaStream_t st) {
   const int total = a.ncols + (a.tail ? D : 0);
@@ -674,7 +843,7 @@ extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev,
                                               int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                               int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
                                               int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
-                                              void* stream) {
+                                              const void* const* shadow_ptrs_dev, void* stream) {
   RB_CHECK_ARG(shard_ptrs_dev != nullptr, RB_ERR_ARG, "shard_ptrs_dev is null");
   IxArgs a;
   int rc = fill_args(&a, nullptr, nullptr, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather,
@@ -687,8 +856,14 @@ extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev,
   RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
   RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (out_dtype == RB_F32) return launch_fwd<float>(a, D, static_cast<float*>(out), out_stride, total, st);
+  const __nv_bfloat16* const* shadows = reinterpret_cast<const __nv_bfloat16* const*>(shadow_ptrs_dev);
+  if (out_dtype == RB_F32) {
+    if (shadows != nullptr) return launch_fwd16<float>(a, D, shadows, static_cast<float*>(out), out_stride, total, st);
+    return launch_fwd<float>(a, D, static_cast<float*>(out), out_stride, total, st);
+  }
   RB_CHECK_ARG(out_stride - total < 64, RB_ERR_ARG, "bf16 out_stride pads more than 63 columns");
+  if (shadows != nullptr)
+    return launch_fwd16<__nv_bfloat16>(a, D, shadows, static_cast<__nv_bfloat16*>(out), out_stride, static_cast<int>(out_stride), st);
   return launch_fwd<__nv_bfloat16>(a, D, static_cast<__nv_bfloat16*>(out), out_stride, static_cast<int>(out_stride), st);
 }
 

@@ -16,6 +16,8 @@
 //      seg_long_chain_kernel with a fixed split, so the result is run-to-run identical.
 // HBM traffic is the algorithmic minimum: each gradient row once, each touched table/state
 // row read once and written once; sort traffic is 16 B per lookup per pass.
+#include <cuda_bf16.h>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -122,6 +124,23 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
   int opt;  // rb_optimizer, RB_OPT_ADAM_TF_DENSE = scatter-add phase only
   float lr, b1, b2, omb1, omb2, eps, alpha;
   const float* alpha_dev;   // optional: alpha_t read from device memory (CUDA-graph replays change it per step)
+  __nv_bfloat16* shadow;    // optional bf16 copy of the table kept in step with it (what sharded forwards read over NVLink)
+
+  template <int VEC>
+  __device__ __forceinline__ void store_shadow(int64_t o, const Row<VEC>& w) const {
+    if (shadow == nullptr) return;
+    if constexpr (VEC == 4) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(w.v[0], w.v[1]);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(w.v[2], w.v[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(shadow + o) = pk;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) shadow[o + i] = __float2bfloat16_rn(w.v[i]);
+    }
+  }
 
   __device__ __forceinline__ void prepare() {
     if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);
@@ -166,6 +185,7 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(s1 + o, v);
       st_row<VEC>(table + o, w);
+      store_shadow<VEC>(o, w);
     } else if (opt == RB_OPT_ADAM_TF_DENSE) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -182,10 +202,12 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
       }
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(table + o, w);
+      store_shadow<VEC>(o, w);
     } else {  // SGD
 #pragma unroll
       for (int i = 0; i < VEC; ++i) w.v[i] = __fsub_rn(w.v[i], __fmul_rn(lr, g.v[i]));
       st_row<VEC>(table + o, w);
+      store_shadow<VEC>(o, w);
     }
   }
 
@@ -677,6 +699,7 @@ static OptSink make_sink(float* table, float* state0, float* state1, int D, cons
   sink.eps = opt->epsilon;
   sink.alpha = adam ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
   sink.alpha_dev = adam ? opt->alpha_t_dev : nullptr;
+  sink.shadow = nullptr;
   return sink;
 }
 
@@ -914,7 +937,7 @@ extern "C" int rb_sparse_bwd_prepare_collected(int64_t local_rows, int32_t D, in
 extern "C" int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state1, int64_t local_rows, int32_t D, int32_t world,
                                        int64_t n_local, int32_t L, const void* const* dE_ptrs, int64_t capacity,
                                        const int32_t* n_valid_dev, const rb_opt_params* opt, void* ws, size_t ws_bytes,
-                                       int32_t sorted_sel, void* stream) {
+                                       int32_t sorted_sel, void* shadow_bf16, void* stream) {
   RB_CHECK_ARG(world >= 1 && world <= RB_MAX_RANKS && dE_ptrs != nullptr && n_valid_dev != nullptr, RB_ERR_ARG,
                "world must be in [1, %d]; dE_ptrs / n_valid_dev must not be null", RB_MAX_RANKS);
   RB_CHECK_ARG(n_local > 0 && L > 0 && n_local % L == 0 && n_local * world < 0xFFFFFFFFll, RB_ERR_ARG, "bad n_local / L");
@@ -957,7 +980,9 @@ extern "C" int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state
     g.fm_s = nullptr;
     if (k < world) gg.start[k] = static_cast<uint32_t>(k * n_local);
   }
-  const OptSink sink = make_sink(table, state0, state1, D, opt);
+  OptSink sink = make_sink(table, state0, state1, D, opt);
+  RB_CHECK_ARG(shadow_bf16 == nullptr || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0, RB_ERR_ALIGN, "shadow not 8 B aligned");
+  sink.shadow = static_cast<__nv_bfloat16*>(shadow_bf16);
   const uint32_t *keys, *vals;
   unsigned char* wsb = static_cast<unsigned char*>(ws);
   sorted_pairs(wsb, lay, sorted_sel, &keys, &vals);

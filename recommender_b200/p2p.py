@@ -22,6 +22,7 @@ sharded step can be captured as one CUDA graph.  Dense MLPs are data-parallel (s
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -48,9 +49,11 @@ class SharedBuffer:
         with torch.cuda.device(device):
             check(lib.rb_shared_alloc(self.nbytes, C.byref(ptr), handle), "rb_shared_alloc")
         self.ptr, self.handle = int(ptr.value), bytes(handle)
-        typestr = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        typestr = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1", torch.bfloat16: "<i2"}[dtype]
         self.__cuda_array_interface__ = dict(shape=self.shape, typestr=typestr, data=(self.ptr, False), version=3, strides=None)
         self.tensor = torch.as_tensor(self, device=device)
+        if dtype == torch.bfloat16:       # the array interface has no bf16: carried as int16, viewed back
+            self.tensor = self.tensor.view(torch.bfloat16)
         assert self.tensor.data_ptr() == self.ptr
 
     def free(self):
@@ -169,7 +172,7 @@ class P2PShardedEmbedding(nn.Module):
     `apply_pending(...)` (driven by optimizers.*), `load_full_table` / `full_row_ids` (tests)."""
 
     def __init__(self, input_dim: int, output_dim: int, *, num_tables: int = 1, link: PeerLink, device=None,
-                 generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25):
+                 generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25, bf16_shadow: bool = True):
         super().__init__()
         self.link = link
         self.world, self.rank = link.world, link.rank
@@ -181,14 +184,29 @@ class P2PShardedEmbedding(nn.Module):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        G, total = self.world, self.input_dim * self.num_tables
+        G = self.world
+        # Table t starts at global row t * pitch.  pitch is coprime with G so that the SAME id of different tables
+        # (the OOV / padding id 0 is the hottest row of every table, ctr/tfrecord_io.py:61-64) lands on different
+        # ranks instead of piling up on rank 0; costs at most a few unused rows per table.
+        self.pitch = self.input_dim
+        if self.num_tables > 1:
+            while math.gcd(self.pitch, G) != 1:
+                self.pitch += 1
+        total = self.pitch * self.num_tables
         self.total_rows = total
         self.local_rows = max((total - self.rank + G - 1) // G, 1)       # rows r with r mod G == rank
         shard_rows = max((total + G - 1) // G, 1)                        # same shape on every rank (rank 0's count)
         self._shard_full, self._shard_ptrs = link.alloc("shard", (shard_rows, self.output_dim), torch.float32)
         self.embeddings = self._shard_full[: self.local_rows]
         self._shard_full.uniform_(-0.05, 0.05, generator=generator)     # Keras default initialiser
-        self._row_offset = (torch.arange(self.num_tables, dtype=torch.int64, device=self.device) * self.input_dim
+        # bf16 shadow of the shard: what the other ranks' forwards read over NVLink (half the bytes, and exactly the
+        # MMA operands); kept in step by the optimizer row update
+        self.use_shadow = bool(bf16_shadow) and self.world > 1
+        self._shadow_full = self._shadow_ptrs = self._shadow_ptr_dev = None
+        if self.use_shadow:
+            self._shadow_full, self._shadow_ptrs = link.alloc("shadow", (shard_rows, self.output_dim), torch.bfloat16)
+            self.refresh_shadow()
+        self._row_offset = (torch.arange(self.num_tables, dtype=torch.int64, device=self.device) * self.pitch
                             if self.num_tables > 1 else None)
         self._anchor = torch.zeros((), dtype=torch.float32, device=self.device, requires_grad=True)
         self.opt_state: Dict[str, torch.Tensor] = {}
@@ -224,18 +242,46 @@ class P2PShardedEmbedding(nn.Module):
         self._shape = (B, F)
         self._side = torch.cuda.Stream(device=dev)
 
+    def refresh_shadow(self) -> None:
+        """Re-derive the bf16 shadow from the fp32 shard (after loading weights; the optimizer keeps it in step afterwards)."""
+        if self._shadow_full is not None:
+            self._shadow_full.copy_(self._shard_full)
+
+    def _shadow_ptrs_dev(self):
+        if not self.use_shadow:
+            return None
+        if self._shadow_ptr_dev is None:
+            self._shadow_ptr_dev = torch.tensor(self._resolve(self._shadow_ptrs), dtype=torch.int64, device=self.device)
+        return self._shadow_ptr_dev.data_ptr()
+
     def _shard_ptrs_dev(self) -> torch.Tensor:
         if self._shard_ptr_dev is None:
             self._shard_ptr_dev = torch.tensor(self._resolve(self._shard_ptrs), dtype=torch.int64, device=self.device)
         return self._shard_ptr_dev
 
     # ---- shard <-> full table (tests, checkpoints) ---------------------------------------------------------------
-    def load_full_table(self, full: torch.Tensor) -> None:
-        full = torch.as_tensor(full, dtype=torch.float32)
-        self.embeddings.copy_(full[self.rank::self.world].to(self.device))
-
     def full_row_ids(self) -> torch.Tensor:
-        return torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank
+        """For every local shard row: its row in the UNSHARDED [input_dim * num_tables, D] table, or -1 for the
+        pad rows the table pitch introduces."""
+        g = torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank   # global (pitched) row
+        t, i = g // self.pitch, g % self.pitch
+        ok = (i < self.input_dim) & (t < self.num_tables)
+        return torch.where(ok, t * self.input_dim + i, torch.full_like(g, -1))
+
+    def load_full_table(self, full: torch.Tensor) -> None:
+        """Adopt this rank's rows of an unsharded [input_dim * num_tables, D] table."""
+        full = torch.as_tensor(full, dtype=torch.float32).to(self.device)
+        ids = self.full_row_ids()
+        ok = ids >= 0
+        self.embeddings[ok] = full[ids[ok]]
+        self.refresh_shadow()
+
+    def scatter_into_full(self, full: torch.Tensor, local: Optional[torch.Tensor] = None) -> None:
+        """full[unsharded row] = this shard's rows (or `local`, e.g. an optimizer state of the same shape)."""
+        ids = self.full_row_ids()
+        ok = ids >= 0
+        src = self.embeddings if local is None else local
+        full[ids[ok]] = src[ok].to(full.device)
 
     # ---- the step, phase by phase (DistPeerLink: called in this order by interact/apply_pending) ---------------------
     def route(self, idx: torch.Tensor) -> None:
@@ -272,8 +318,8 @@ class P2PShardedEmbedding(nn.Module):
         check(lib.rb_dot_interaction_fwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
                                                  ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
                                                  int(tail), out.data_ptr(), ops._float_type(out_dtype), stride,
-                                                 self._x_saved.data_ptr() if self.save_rows else None, ops._stream()),
-              "rb_dot_interaction_fwd_sharded")
+                                                 self._x_saved.data_ptr() if self.save_rows else None, self._shadow_ptrs_dev(),
+                                                 ops._stream()), "rb_dot_interaction_fwd_sharded")
         return out
 
     def _interaction_bwd(self, idx, dense_vec, flags, dOut):
@@ -336,7 +382,7 @@ class P2PShardedEmbedding(nn.Module):
         check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
                                           self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
                                           self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
-                                          self._sel, ops._stream()), "rb_sparse_bwd_apply_p2p")
+                                          self._sel, ops._ptr(self._shadow_full), ops._stream()), "rb_sparse_bwd_apply_p2p")
         return self.n_local
 
     def check_overflow(self) -> None:
@@ -351,7 +397,7 @@ class P2PShardedDLRM(nn.Module):
     def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
                  num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, group=None, link: Optional[PeerLink] = None, device=None,
                  compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
-                 capacity_factor: float = 1.25):
+                 capacity_factor: float = 1.25, bf16_shadow: bool = True):
         super().__init__()
         if bottom_mlp_units[-1] != embedding_size:
             raise ValueError("bottom_mlp_units[-1] must equal embedding_size")       # ctr/model.py:52,55
@@ -360,7 +406,7 @@ class P2PShardedDLRM(nn.Module):
         self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator)
         self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)
         self.embedding_layer = P2PShardedEmbedding(vocab_size, embedding_size, num_tables=num_tables, link=self.link, device=device,
-                                                   generator=generator, capacity_factor=capacity_factor)
+                                                   generator=generator, capacity_factor=capacity_factor, bf16_shadow=bf16_shadow)
         self.num_cat_fea, self.num_int_fea, self.embedding_size = num_cat_fea, num_int_fea, embedding_size
         self._synced = False
         self._flat = None

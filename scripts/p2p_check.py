@@ -39,20 +39,23 @@ def main():
         opt.apply_gradients(model)
     model.embedding_layer.check_overflow()
     torch.cuda.synchronize()
-    # gather the shards on rank 0
+    # gather the shards on rank 0 as (unsharded row id, row) pairs
     emb = model.embedding_layer
-    shards = [torch.empty((V * T - k + world - 1) // world, D, device=dev) for k in range(world)]
-    if rank == 0:
-        shards[0].copy_(emb.embeddings)
-        for k in range(1, world):
-            dist.recv(shards[k], src=k)
-    else:
-        dist.send(emb.embeddings.contiguous(), dst=0)
+    max_rows = (emb.total_rows + world - 1) // world
+    ids = torch.full((max_rows,), -1, dtype=torch.int64, device=dev)
+    rows = torch.zeros(max_rows, D, device=dev)
+    ids[: emb.local_rows] = emb.full_row_ids()
+    rows[: emb.local_rows] = emb.embeddings
+    all_ids = [torch.empty_like(ids) for _ in range(world)]
+    all_rows = [torch.empty_like(rows) for _ in range(world)]
+    dist.all_gather(all_ids, ids)
+    dist.all_gather(all_rows, rows)
     ok = True
     if rank == 0:
         full = torch.empty(V * T, D, device=dev)
         for k in range(world):
-            full[k::world] = shards[k]
+            okk = all_ids[k] >= 0
+            full[all_ids[k][okk]] = all_rows[k][okk]
         ref = DLRM([64, D], [64, 1], D, V, 26, 13, num_tables=T, device=dev)
         ref.embedding_layer.embeddings.copy_(torch.tensor(params["table"]))
         ref.bottom_mlp.load_arrays(params["bottom"], dev)

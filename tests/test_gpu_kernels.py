@@ -508,8 +508,8 @@ def test_colsum_bias_gradient(ops, dtype, rows, cols):
 # ---- sharded table over peer memory: G emulated ranks on one GPU (p2p.LocalPeerLink) ------------------------------
 
 @pytest.mark.parametrize("G", [2, 4, 8])
-@pytest.mark.parametrize("T", [1, 26])
-def test_peer_memory_sharded_step_equals_unsharded(ops, G, T):
+@pytest.mark.parametrize("T,shadow", [(1, True), (26, True), (26, False)])
+def test_peer_memory_sharded_step_equals_unsharded(ops, G, T, shadow):
     """Row-wise sharding with the exchange done by the kernels (rb_dot_interaction_*_sharded read the rows from
     the owners' shards, rb_sparse_bwd_apply_p2p pulls gradient rows from every rank's dE): interaction
     outputs, dE and the updated table must equal the unsharded kernels bit for bit — same pairs, same
@@ -520,7 +520,8 @@ def test_peer_memory_sharded_step_equals_unsharded(ops, G, T):
     V, D, B, F = (50021 if T == 1 else 2003), 32, 96, 26
     W = O.init_table(rng, V * T, D)
     registry = {}
-    embs = [P2PShardedEmbedding(V, D, num_tables=T, link=LocalPeerLink(G, r, registry), device="cuda", capacity_factor=float(G)) for r in range(G)]
+    embs = [P2PShardedEmbedding(V, D, num_tables=T, link=LocalPeerLink(G, r, registry), device="cuda", capacity_factor=float(G),
+                                bf16_shadow=shadow) for r in range(G)]
     for e in embs:
         e.load_full_table(torch.tensor(W))
     off = cu(np.arange(T, dtype=np.int64) * V) if T > 1 else None
@@ -557,11 +558,19 @@ def test_peer_memory_sharded_step_equals_unsharded(ops, G, T):
         ops.sparse_bwd_update(Wd, m, v, [LookupGroup(rows, 1, GradSource.per_position(dE_all, 1))], optimizer="adam_lazy", step=3)
     # rows hit once are bit-exact; duplicate rows are summed in the same (rank, position) order but the tile
     # boundaries of the segmented reduction fall elsewhere, so long runs may re-associate (fp32)
+    got_W, got_m = torch.zeros_like(Wd), torch.zeros_like(Wd)
     for r in range(G):
-        np.testing.assert_allclose(embs[r].embeddings.cpu().numpy(), Wd[r::G].cpu().numpy(), rtol=0, atol=2e-6)
-        np.testing.assert_allclose(embs[r].opt_state["m"].cpu().numpy(), m[r::G].cpu().numpy(), rtol=1e-5, atol=1e-9)
+        embs[r].scatter_into_full(got_W)
+        embs[r].scatter_into_full(got_m, embs[r].opt_state["m"])
+    np.testing.assert_allclose(got_W.cpu().numpy(), Wd.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got_m.cpu().numpy(), m.cpu().numpy(), rtol=1e-5, atol=1e-9)
     touched = (m.abs().sum(1) > 0)
     assert 0 < int(touched.sum()) < Wd.shape[0]
-    for r in range(G):
-        assert torch.equal((embs[r].opt_state["m"].abs().sum(1) > 0), touched[r::G])     # exactly the same rows moved
+    assert torch.equal(got_m.abs().sum(1) > 0, touched)                                 # exactly the same rows moved
+    if shadow:  # the bf16 shadow the other ranks read stays in step with the fp32 shard
+        for e in embs:
+            assert torch.equal(e._shadow_full[: e.local_rows], e.embeddings.to(torch.bfloat16))
+    if T > 1:   # the table pitch spreads the hot id 0 of the 26 tables over the ranks
+        owners = {int((t * embs[0].pitch) % G) for t in range(T)}
+        assert len(owners) == min(G, T)
     assert int(sum(int(e._n_valid.item()) for e in embs)) == G * B * F
