@@ -34,7 +34,7 @@ extern "C" {
 
 #define RB_VERSION 100  /* 0.1.0 */
 #define RB_MAX_GRAD_SOURCES 16
-#define RB_MAX_LOOKUP_GROUPS 4
+#define RB_MAX_LOOKUP_GROUPS 8
 #define RB_MAX_DENSE_TENSORS 32
 #define RB_MAX_RANKS 8          /* GPUs of one NVSwitch box */
 #define RB_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
@@ -275,6 +275,7 @@ typedef struct rb_dense_slot {
   float* state1;       /* Adam v / NULL */
   const float* grad;   /* f32[n] */
   int64_t n;
+  void* shadow_bf16;   /* optional bf16[n]: receives the updated parameter rounded to bf16 (the operand of bf16 GEMMs) */
 } rb_dense_slot;
 
 /*

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(PKG, "lib", "librecsys_
 HEADER = os.path.join(os.path.dirname(PKG), "include", "recsys_b200.h")
 
 RB_MAX_GRAD_SOURCES = 16
-RB_MAX_LOOKUP_GROUPS = 4
+RB_MAX_LOOKUP_GROUPS = 8
 RB_MAX_DENSE_TENSORS = 32
 RB_MAX_RANKS = 8
 RB_IPC_HANDLE_BYTES = 64
@@ -52,7 +52,8 @@ class RbLookupGroup(C.Structure):
 
 
 class RbDenseSlot(C.Structure):
-    _fields_ = [("param", C.c_void_p), ("state0", C.c_void_p), ("state1", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_int64)]
+    _fields_ = [("param", C.c_void_p), ("state0", C.c_void_p), ("state1", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_int64),
+                ("shadow_bf16", C.c_void_p)]
 
 
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float

@@ -17,6 +17,7 @@ struct DenseSlots {
   float* s0[RB_MAX_DENSE_TENSORS];
   float* s1[RB_MAX_DENSE_TENSORS];
   const float* g[RB_MAX_DENSE_TENSORS];
+  __nv_bfloat16* shadow[RB_MAX_DENSE_TENSORS];   // optional bf16 copy of the parameter (what the bf16 GEMMs read)
   int chunk_start[RB_MAX_DENSE_TENSORS + 1];  // prefix sum of ceil(n / kDenseChunk)
   int64_t n[RB_MAX_DENSE_TENSORS];
 };
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(kDenseThreads) dense_opt_kernel(const __grid_c
   float* __restrict__ v = s.s1[t];
   const float* __restrict__ g = s.g[t];
   const float alpha = s.alpha_dev != nullptr ? __ldg(s.alpha_dev) : s.alpha;
+  __nv_bfloat16* __restrict__ sh = s.shadow[t];
   for (int64_t i = base + threadIdx.x; i < end; i += kDenseThreads) {
     const float gi = g[i];
     if (s.opt == RB_OPT_ADAM_LAZY || s.opt == RB_OPT_ADAM_TF_DENSE) {
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(kDenseThreads) dense_opt_kernel(const __grid_c
     } else {
       p[i] = __fsub_rn(p[i], __fmul_rn(s.lr, gi));
     }
+    if (sh != nullptr) sh[i] = __float2bfloat16_rn(p[i]);
   }
 }
 
@@ -125,28 +128,30 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int cols, int64_t r
 
 // Stage 2: a CTA owns 32 columns; warp w adds partials w, w+8, ... (coalesced 128 B reads, 8 loads in
 // flight), then the 8 warp sums are combined in fixed order.
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
-  __shared__ float s_w[8][32];
+constexpr int kFinalWarps = 32;
+__global__ void __launch_bounds__(kFinalWarps * 32) colsum_final_kernel(const float* __restrict__ partial, int nparts, int cols,
+                                                                         float* __restrict__ out) {
+  __shared__ float s_w[kFinalWarps][32];
   const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + lane;
   float t = 0.f;
   if (c < cols) {
     int p = w;
-    for (; p + 56 < nparts; p += 64) {
+    for (; p + 7 * kFinalWarps < nparts; p += 8 * kFinalWarps) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = partial[static_cast<int64_t>(p + 8 * u) * cols + c];
+      for (int u = 0; u < 8; ++u) v[u] = partial[static_cast<int64_t>(p + kFinalWarps * u) * cols + c];
 #pragma unroll
       for (int u = 0; u < 8; ++u) t += v[u];
     }
-    for (; p < nparts; p += 8) t += partial[static_cast<int64_t>(p) * cols + c];
+    for (; p < nparts; p += kFinalWarps) t += partial[static_cast<int64_t>(p) * cols + c];
   }
   s_w[w][lane] = t;
   __syncthreads();
   if (w == 0 && c < cols) {
     float r = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r += s_w[k][lane];
+    for (int k = 0; k < kFinalWarps; ++k) r += s_w[k][lane];
     out[c] = r;
   }
 }
@@ -191,6 +196,7 @@ extern "C" int rb_dense_opt_step(const rb_dense_slot* slots, int32_t num, const 
     s.s0[t] = d.state0;
     s.s1[t] = d.state1;
     s.g[t] = d.grad;
+    s.shadow[t] = static_cast<__nv_bfloat16*>(d.shadow_bf16);
     s.n[t] = d.n;
     s.chunk_start[t] = chunks;
     chunks += static_cast<int>((d.n + kDenseChunk - 1) / kDenseChunk);
@@ -230,7 +236,7 @@ extern "C" int rb_colsum(const void* x, int32_t dtype, int64_t rows, int32_t col
   else
     colsum_partial_kernel<float><<<parts, kColThreads, 0, st>>>(static_cast<const float*>(x), rows, cols, row_stride, partial);
   RB_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, parts, cols, out);
+  colsum_final_kernel<<<(cols + 31) / 32, kFinalWarps * 32, 0, st>>>(partial, parts, cols, out);
   RB_LAUNCH_CHECK("colsum_final_kernel");
   return RB_OK;
 }

@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t load_sample_row(const IxArgs& a, int64_t b, 
 // src_lane = (E or table) + this lane's column offset; dst_lane = xs + sub*STRIDE + column offset.
 // Sharded table (shard_base != null, smem copy of the peer shard pointers): row r is read from the owner's HBM
 // over NVLink, shard_base[r % world] + (r / world) * D — the gather IS the collective.
-template <int D, int STRIDE>
+template <int D, int STRIDE, bool SHARDED>
 __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, uint32_t my_row, int F, float* dst_lane,
                                            int sub, const float* __restrict__ dense_lane, float* dense_dst,
                                            const float* const* shard_base, uint32_t world, int col) {
@@ -117,7 +117,7 @@ __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, u
     const bool ok = row != kInvalidRow;
     const float* src = src_lane;
     if (ok) {
-      if (shard_base != nullptr) {
+      if constexpr (SHARDED) {
         const uint32_t local = row / world;
         src = shard_base[row - local * world] + static_cast<size_t>(local) * D + col;
       } else {
@@ -125,7 +125,7 @@ __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, u
       }
     }
     if (r < F) {   // invalid row: zero-filled by the copy
-      if (RB_PEER_CA && shard_base != nullptr) cp_async16_ca(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
+      if constexpr (SHARDED && RB_PEER_CA) cp_async16_ca(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
       else cp_async16(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
     }
   }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void load_row_async(const T* __restrict__ grow, T* gs
 // Z = X X^T is symmetric: only the 6 tiles (m-tile, n-tile) that touch the upper triangle are
 // computed; the self-interaction form (kept j <= i) reads element (j,i) instead.
 // smem per warp: kIxStages x xs[32][D+8] fp32 | 16 B trash slot | staged output row.
-template <int D, typename OUT>
+template <int D, typename OUT, bool SHARDED>
 __global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, int write_width, int os_bytes) {
   constexpr int STRIDE = D + 8;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
@@ -205,11 +205,11 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ const float* s_shards[RB_MAX_RANKS];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  if (a.shards != nullptr) {
+  if constexpr (SHARDED) {
     if (threadIdx.x < a.world) s_shards[threadIdx.x] = a.shards[threadIdx.x];
     __syncthreads();
   }
-  const float* const* shard_base = a.shards != nullptr ? s_shards : nullptr;
+  const float* const* shard_base = SHARDED ? s_shards : nullptr;
   unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * kXsFloats * 4 + os_bytes);
   float* xs_base = reinterpret_cast<float*>(my);
   OUT* os = reinterpret_cast<OUT*>(my + kIxStages * kXsFloats * 4 + 16);   // row origin; [-16 B, 0) is the trash slot
@@ -249,7 +249,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
       opos[T][k] = pos;
     }
 
-  const float* src_lane = (a.E != nullptr ? a.E : (a.table != nullptr ? a.table : s_shards[0])) + (lane % kLanesPerRow) * 4;
+  const float* src_lane = (a.E != nullptr ? a.E : (SHARDED ? s_shards[0] : a.table)) + (lane % kLanesPerRow) * 4;
   const int sub = lane / kLanesPerRow;
   const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
   const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
@@ -257,7 +257,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
 
   uint32_t row_next = load_sample_row(a, b, lane, lane_off);
   const int col = (lane % kLanesPerRow) * 4;
-  issue_rows<D, STRIDE>(src_lane, row_next, F, xs_base + dst_off, sub, dense_lane_on ? a.dense_vec + b * D + lane * 4 : nullptr,
+  issue_rows<D, STRIDE, SHARDED>(src_lane, row_next, F, xs_base + dst_off, sub, dense_lane_on ? a.dense_vec + b * D + lane * 4 : nullptr,
                         xs_base + F * STRIDE + lane * 4, shard_base, a.world, col);
   cp_async_commit();
   row_next = load_sample_row(a, b + nwarps, lane, lane_off);
@@ -268,7 +268,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
     float* xs = xs_base + stage * kXsFloats;
     if (bn < a.B) {
       float* xn = xs_base + (stage ^ 1) * kXsFloats;
-      issue_rows<D, STRIDE>(src_lane, row_next, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bn * D + lane * 4 : nullptr,
+      issue_rows<D, STRIDE, SHARDED>(src_lane, row_next, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bn * D + lane * 4 : nullptr,
                             xn + F * STRIDE + lane * 4, shard_base, a.world, col);
       row_next = load_sample_row(a, bn + nwarps, lane, lane_off);   // in flight during this sample's math
     }
@@ -276,7 +276,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
     cp_async_wait<1>();
     __syncwarp();
 
-    if (a.x_save != nullptr) {   // the sample's operand rows as bf16, contiguous [F', D]: the backward reads them locally
+    if (SHARDED && a.x_save != nullptr) {   // the sample's operand rows as bf16, contiguous [F', D]: the backward reads them locally
       constexpr int kChunksPerRow = D / 8;
       __nv_bfloat16* xrow = a.x_save + b * a.Fp * D;
       for (int cidx = lane; cidx < a.Fp * kChunksPerRow; cidx += 32) {
@@ -486,7 +486,9 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
 
 // ---- backward ------------------------------------------------------------------------------------------------
 // dX = (G + G^T) X.  smem per warp: kIxStages x { xs[32][D+4] fp32 | 16 B of zeros | staged dOut row }.
-template <int D, typename DOUT, bool SELF>
+// SRC: where X comes from — 0: rows gathered from E / the local table, 1: rows gathered from the shards in peer
+// memory, 2: the bf16 operand rows the forward saved (x_load)
+template <int D, typename DOUT, bool SELF, int SRC>
 __global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
                            float* __restrict__ d_dense, int copy_width, int gs_bytes) {
@@ -498,11 +500,11 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ const float* s_shards[RB_MAX_RANKS];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  if (a.shards != nullptr) {
+  if constexpr (SRC == 1) {
     if (threadIdx.x < a.world) s_shards[threadIdx.x] = a.shards[threadIdx.x];
     __syncthreads();
   }
-  const float* const* shard_base = a.shards != nullptr ? s_shards : nullptr;
+  const float* const* shard_base = SRC == 1 ? s_shards : nullptr;
   const int stage_bytes = kXsFloats * 4 + gs_bytes;
   unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * stage_bytes);
 
@@ -552,14 +554,14 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
       is_dense[mt][h] = (i == F) && a.dense_vec != nullptr && d_dense != nullptr;
     }
 
-  const float* src_lane = (a.E != nullptr ? a.E : (a.table != nullptr ? a.table : s_shards[0])) + (lane % kLanesPerRow) * 4;
+  const float* src_lane = (a.E != nullptr ? a.E : (SRC == 1 ? s_shards[0] : a.table)) + (lane % kLanesPerRow) * 4;
   const int sub = lane / kLanesPerRow;
   const int dst_off = sub * STRIDE + (lane % kLanesPerRow) * 4;
   const bool dense_lane_on = a.dense_vec != nullptr && lane < kLanesPerRow;
-  const int64_t lane_off = (a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
+  const int64_t lane_off = (SRC != 2 && a.E == nullptr && a.map.field_row_offset != nullptr && lane < F) ? __ldg(a.map.field_row_offset + lane) : 0;
 
   constexpr int S16 = D + 8;   // bf16 elements per row of the staged X when it comes from x_load
-  const bool xl = a.x_load != nullptr;
+  constexpr bool xl = (SRC == 2);
   auto issue = [&](int64_t bb, uint32_t row, int st) {
     unsigned char* sp = my + st * stage_bytes;
     float* xn = reinterpret_cast<float*>(sp);
@@ -572,7 +574,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
         cp_async16(x16 + r * S16 + c8, xrow + r * D + c8, 16);
       }
     } else
-    issue_rows<D, STRIDE>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
+    issue_rows<D, STRIDE, SRC == 1>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
                           xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4);
     const DOUT* grow = dOut + bb * dout_stride;
     load_row_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4 + 16), misalign_elems(grow), copy_width, lane);
@@ -724,9 +726,17 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
   {                                                                                                                     \
     constexpr int W = IxWarps<DD>::value;                                                                               \
     size_t smem = static_cast<size_t>(W) * (kIxStages * 32 * (DD + 8) * 4 + os_bytes);                                  \
-    rc = set_smem(dot_interaction_fwd_kernel<DD, OUT>, smem);                                                           \
-    if (rc != RB_OK) return rc;                                                                                         \
-    dot_interaction_fwd_kernel<DD, OUT><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, out, out_stride, write_width, os_bytes); \
+    if (a.shards != nullptr) {                                                                                          \
+      rc = set_smem(dot_interaction_fwd_kernel<DD, OUT, true>, smem);                                                   \
+      if (rc != RB_OK) return rc;                                                                                       \
+      dot_interaction_fwd_kernel<DD, OUT, true><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, out, out_stride, write_width, \
+                                                                                                 os_bytes);             \
+    } else {                                                                                                            \
+      rc = set_smem(dot_interaction_fwd_kernel<DD, OUT, false>, smem);                                                  \
+      if (rc != RB_OK) return rc;                                                                                       \
+      dot_interaction_fwd_kernel<DD, OUT, false><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, out, out_stride, write_width, \
+                                                                                                  os_bytes);            \
+    }                                                                                                                   \
   }
   if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
 #undef LAUNCH
@@ -756,6 +766,21 @@ static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shad
   return RB_OK;
 }
 
+#define BWD_ONE(DD, SELFV, SRCV)                                                                                        \
+  {                                                                                                                     \
+    rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, SELFV, SRCV>, smem);                                             \
+    if (rc != RB_OK) return rc;                                                                                         \
+    dot_interaction_bwd_kernel<DD, DOUT, SELFV, SRCV><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
+                                                                                                       d_dense, copy_width,  \
+                                                                                                       gs_bytes);       \
+  }
+#define BWD_DISPATCH(DD, MODE)                                                                                          \
+  if (a.self_interaction) {                                                                                             \
+    if (MODE == 2) BWD_ONE(DD, true, 2) else if (MODE == 1) BWD_ONE(DD, true, 1) else BWD_ONE(DD, true, 0)              \
+  } else {                                                                                                              \
+    if (MODE == 2) BWD_ONE(DD, false, 2) else if (MODE == 1) BWD_ONE(DD, false, 1) else BWD_ONE(DD, false, 0)           \
+  }
+
 template <typename DOUT>
 static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_stride, float* dE, float* d_dense, cudaStream_t st) {
   const int total = a.ncols + (a.tail ? D : 0);
@@ -769,17 +794,8 @@ static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_str
   {                                                                                                                     \
     constexpr int W = IxWarps<DD>::value;                                                                               \
     size_t smem = static_cast<size_t>(W) * kIxStages * (32 * (DD + 4) * 4 + gs_bytes);                                  \
-    if (a.self_interaction) {                                                                                           \
-      rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, true>, smem);                                                  \
-      if (rc != RB_OK) return rc;                                                                                       \
-      dot_interaction_bwd_kernel<DD, DOUT, true><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
-                                                                                                  d_dense, copy_width, gs_bytes); \
-    } else {                                                                                                            \
-      rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, false>, smem);                                                 \
-      if (rc != RB_OK) return rc;                                                                                       \
-      dot_interaction_bwd_kernel<DD, DOUT, false><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
-                                                                                                   d_dense, copy_width, gs_bytes); \
-    }                                                                                                                   \
+    const int src_mode = a.x_load != nullptr ? 2 : (a.shards != nullptr ? 1 : 0);                                       \
+    BWD_DISPATCH(DD, src_mode)                                                                                          \
   }
   if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
 #undef LAUNCH

@@ -300,15 +300,25 @@ class _LinearBF16Fn(torch.autograd.Function):
     (a column reduction over 65536 rows is ~6x slower as an elementwise reduce kernel)."""
 
     @staticmethod
+    def _bf16_shadow(p: torch.Tensor, rows: Optional[int] = None) -> torch.Tensor:
+        """bf16 copy of a parameter ([rows, out] zero-padded below for a kernel).  It is cached on the parameter and
+        kept in step by the fused optimizer step (rb_dense_opt_step writes it together with the fp32 value); any
+        torch-side in-place change of the parameter bumps its version and forces a rebuild here."""
+        sh = getattr(p, "_rb_shadow", None)
+        shape = tuple(p.shape) if rows is None else (rows, p.shape[1])
+        if sh is None or sh[1] != p._version or tuple(sh[0].shape) != shape:
+            with torch.no_grad():
+                t = torch.zeros(shape, dtype=torch.bfloat16, device=p.device)
+                t.reshape(-1)[: p.numel()].copy_(p.detach().reshape(-1))
+            p._rb_shadow = sh = (t, p._version)
+        return sh[0]
+
+    @staticmethod
     def forward(ctx, x, W, b, need_dx):
         in_dim, out = W.shape
         Kp = x.shape[1]
-        Wp = torch.zeros(Kp, out, dtype=torch.bfloat16, device=W.device) if Kp != in_dim else None
-        if Wp is None:
-            Wp = W.to(torch.bfloat16)
-        else:
-            Wp[:in_dim].copy_(W)
-        y = torch.addmm(b.to(torch.bfloat16), x, Wp)
+        Wp = _LinearBF16Fn._bf16_shadow(W, Kp)
+        y = torch.addmm(_LinearBF16Fn._bf16_shadow(b), x, Wp)
         ctx.save_for_backward(x, Wp)
         ctx.in_dim, ctx.need_dx = in_dim, need_dx
         return y
@@ -318,7 +328,12 @@ class _LinearBF16Fn(torch.autograd.Function):
         x, Wp = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.mm(dy, Wp.t()) if ctx.need_dx else None
-        dW = torch.mm(x.t(), dy)[: ctx.in_dim].float()
+        if dy.is_cuda:
+            dW = torch.mm(x.t(), dy, out_dtype=torch.float32)[: ctx.in_dim]      # fp32 accumulate AND fp32 result
+            if not dW.is_contiguous():
+                dW = dW.contiguous()
+        else:
+            dW = torch.mm(x.t(), dy)[: ctx.in_dim].float()
         if dy.is_cuda and dy.shape[1] % 8 == 0:
             db = ops.colsum(dy)                       # rb_colsum: deterministic fp32 column sums
         else:

@@ -400,6 +400,8 @@ def dense_opt_step(params, grads, state0, state1, *, optimizer="adam_lazy", step
             arr[k - lo].state0 = None if state0 is None else state0[k].data_ptr()
             arr[k - lo].state1 = None if state1 is None else state1[k].data_ptr()
             arr[k - lo].n = p.numel()
+            sh = getattr(p, "_rb_shadow", None)      # (bf16 tensor whose first n elements mirror p, version it was made at)
+            arr[k - lo].shadow_bf16 = sh[0].data_ptr() if sh is not None and sh[1] == p._version else None
         check(lib.rb_dense_opt_step(arr, hi - lo, C.byref(opt), _stream()), "rb_dense_opt_step")
 
 

@@ -415,17 +415,21 @@ class P2PShardedDLRM(nn.Module):
         if isinstance(self.link, DistPeerLink) and self.link.world > 1:
             for p in self.parameters():
                 dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+                if hasattr(p, "_rb_shadow"):
+                    del p._rb_shadow          # .data writes do not bump the version the bf16 shadow is keyed on
         self._synced = True
 
     def forward(self, inputs, training=None, mask=None, routed=False):
         int_features = inputs["int_features"].reshape(-1, self.num_int_fea)
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)
-        bmlp_output = self.bottom_mlp(int_features)
         width = (self.num_cat_fea + 1) ** 2 + self.embedding_size
-        if len(self.top_mlp.kernels) == 0:
-            self.top_mlp.build(width, bmlp_output.device)
-        if not self._synced:
+        if not self._synced:         # build both towers, then adopt rank 0's weights BEFORE anything is computed from them
+            if len(self.bottom_mlp.kernels) == 0:
+                self.bottom_mlp.build(self.num_int_fea, int_features.device)
+            if len(self.top_mlp.kernels) == 0:
+                self.top_mlp.build(width, int_features.device)
             self.sync_dense_parameters()
+        bmlp_output = self.bottom_mlp(int_features)
         bf16 = self.top_mlp.compute_dtype == torch.bfloat16
         tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
                                                    out_dtype=torch.bfloat16 if bf16 else torch.float32, pad_to=8 if bf16 else 1,

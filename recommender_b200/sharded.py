@@ -245,6 +245,8 @@ class ShardedDLRM(nn.Module):
         """Replicas start from rank 0's MLP weights (MirroredStrategy mirrors variables)."""
         for p in self.parameters():
             dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            if hasattr(p, "_rb_shadow"):
+                del p._rb_shadow              # .data writes do not bump the version the bf16 shadow is keyed on
         self._synced = True
 
     def forward(self, inputs, training=None, mask=None):
