@@ -29,12 +29,26 @@ namespace rb {
 #ifndef RB_PEER_CA
 #define RB_PEER_CA 1
 #endif
-constexpr int kIxStages = 2;   // ring depth per warp
-// warps per CTA (each with its own ring): sized so that kIxStages rings + staging fit in 227 KiB
+#ifndef RB_IX_STAGES
+#define RB_IX_STAGES 2
+#endif
+#ifndef RB_IX_WARPS
+#define RB_IX_WARPS 12
+#endif
+#ifndef RB_IX_FWD_PAD
+#define RB_IX_FWD_PAD 8
+#endif
+constexpr int kIxStages = RB_IX_STAGES;   // ring depth per warp: samples in flight = kIxStages - 1
+// upper bound of warps per CTA (each with its own ring); the launch picks as many as fit in 227 KiB of shared memory
 template <int D>
 struct IxWarps {
-  static constexpr int value = (D <= 64) ? 8 : 4;
+  static constexpr int value = RB_IX_WARPS;
 };
+constexpr size_t kIxSmemLimit = 227 * 1024 - 1024;
+static int warps_that_fit(size_t per_warp_bytes) {
+  int w = static_cast<int>(kIxSmemLimit / per_warp_bytes);
+  return w > RB_IX_WARPS ? RB_IX_WARPS : w;
+}
 
 struct IxArgs {
   const float* E;          // [B,F,D] or null (fused gather)
@@ -198,9 +212,9 @@ __device__ __forceinline__ void load_row_async(const T* __restrict__ grow, T* gs
 template <int D, typename OUT, bool SHARDED>
 __global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, int write_width, int os_bytes) {
-  constexpr int STRIDE = D + 8;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
+  constexpr int STRIDE = D + RB_IX_FWD_PAD;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
   constexpr int kXsFloats = 32 * STRIDE;
-  constexpr int kIxWarps = IxWarps<D>::value;
+  const int kIxWarps = blockDim.x / 32;
   constexpr int kLanesPerRow = D / 4;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ const float* s_shards[RB_MAX_RANKS];
@@ -257,23 +271,32 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
 
   uint32_t row_next = load_sample_row(a, b, lane, lane_off);
   const int col = (lane % kLanesPerRow) * 4;
-  issue_rows<D, STRIDE, SHARDED>(src_lane, row_next, F, xs_base + dst_off, sub, dense_lane_on ? a.dense_vec + b * D + lane * 4 : nullptr,
-                        xs_base + F * STRIDE + lane * 4, shard_base, a.world, col);
-  cp_async_commit();
-  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
+  auto issue = [&](int64_t bb, uint32_t rows, int st) {
+    float* xn = xs_base + st * kXsFloats;
+    issue_rows<D, STRIDE, SHARDED>(src_lane, rows, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
+                                   xn + F * STRIDE + lane * 4, shard_base, a.world, col);
+  };
+  // prologue: the first kIxStages-1 samples of this warp are put in flight
+#pragma unroll
+  for (int s0 = 0; s0 < kIxStages - 1; ++s0) {
+    const int64_t bs = b + s0 * nwarps;
+    if (bs < a.B) issue(bs, row_next, s0);
+    cp_async_commit();
+    row_next = load_sample_row(a, bs + nwarps, lane, lane_off);
+  }
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
-    const int64_t bn = b + nwarps;
+    const int64_t bn = b + (kIxStages - 1) * nwarps;
     float* xs = xs_base + stage * kXsFloats;
     if (bn < a.B) {
-      float* xn = xs_base + (stage ^ 1) * kXsFloats;
-      issue_rows<D, STRIDE, SHARDED>(src_lane, row_next, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bn * D + lane * 4 : nullptr,
-                            xn + F * STRIDE + lane * 4, shard_base, a.world, col);
+      int sa = stage + kIxStages - 1;
+      if (sa >= kIxStages) sa -= kIxStages;
+      issue(bn, row_next, sa);
       row_next = load_sample_row(a, bn + nwarps, lane, lane_off);   // in flight during this sample's math
     }
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<kIxStages - 1>();
     __syncwarp();
 
     if (SHARDED && a.x_save != nullptr) {   // the sample's operand rows as bf16, contiguous [F', D]: the backward reads them locally
@@ -333,7 +356,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
     OUT* grow = out + b * out_stride;
     store_row<OUT>(grow, os, misalign_elems(grow), width, lane);
     __syncwarp();   // os and xs[stage] are free again
-    stage ^= 1;
+    if (++stage == kIxStages) stage = 0;
   }
 }
 
@@ -349,7 +372,7 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
   constexpr int S16 = D + 8;                    // bf16 elements per tile row: 4*g + t bank pattern, conflict-free
   constexpr int kTileBytes = 32 * S16 * 2;
   constexpr int kStageBytes = kTileBytes + D * 4;
-  constexpr int kIxWarps = IxWarps<D>::value;
+  const int kIxWarps = blockDim.x / 32;
   constexpr int kLanesPerRow = D / 8;           // 16-byte chunks per bf16 row
   constexpr int kRowsPerIter = 32 / kLanesPerRow;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -417,22 +440,28 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
   };
 
   uint32_t row_next = load_sample_row(a, b, lane, lane_off);
-  issue(b, row_next, 0);
-  cp_async_commit();
-  row_next = load_sample_row(a, b + nwarps, lane, lane_off);
+#pragma unroll
+  for (int s0 = 0; s0 < kIxStages - 1; ++s0) {
+    const int64_t bs = b + s0 * nwarps;
+    if (bs < a.B) issue(bs, row_next, s0);
+    cp_async_commit();
+    row_next = load_sample_row(a, bs + nwarps, lane, lane_off);
+  }
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
-    const int64_t bn = b + nwarps;
+    const int64_t bn = b + (kIxStages - 1) * nwarps;
     unsigned char* sp = my + stage * kStageBytes;
     __nv_bfloat16* x16 = reinterpret_cast<__nv_bfloat16*>(sp);
     const float* dvec = reinterpret_cast<const float*>(sp + kTileBytes);
     if (bn < a.B) {
-      issue(bn, row_next, stage ^ 1);
+      int sa = stage + kIxStages - 1;
+      if (sa >= kIxStages) sa -= kIxStages;
+      issue(bn, row_next, sa);
       row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
     }
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<kIxStages - 1>();
     __syncwarp();
 
     if (a.dense_vec != nullptr) {   // the dense vector joins the tile as row F (bf16 operand)
@@ -480,7 +509,7 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
     OUT* grow = out + b * out_stride;
     store_row<OUT>(grow, os, misalign_elems(grow), width, lane);
     __syncwarp();
-    stage ^= 1;
+    if (++stage == kIxStages) stage = 0;
   }
 }
 
@@ -494,7 +523,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
                            float* __restrict__ d_dense, int copy_width, int gs_bytes) {
   constexpr int STRIDE = D + 4;  // floats; 2*(D+4) % 32 == 8 -> conflict-free 32-bit B-fragment loads
   constexpr int kXsFloats = 32 * STRIDE;
-  constexpr int kIxWarps = IxWarps<D>::value;
+  const int kIxWarps = blockDim.x / 32;
   constexpr int kLanesPerRow = D / 4;
   constexpr int EPC = 16 / static_cast<int>(sizeof(DOUT));
   extern __shared__ __align__(16) unsigned char smem[];
@@ -581,21 +610,27 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   };
 
   uint32_t row_next = xl ? kInvalidRow : load_sample_row(a, b, lane, lane_off);
-  issue(b, row_next, 0);
-  cp_async_commit();
-  if (!xl) row_next = load_sample_row(a, b + nwarps, lane, lane_off);
+#pragma unroll
+  for (int s0 = 0; s0 < kIxStages - 1; ++s0) {
+    const int64_t bs = b + s0 * nwarps;
+    if (bs < a.B) issue(bs, row_next, s0);
+    cp_async_commit();
+    if (!xl) row_next = load_sample_row(a, bs + nwarps, lane, lane_off);
+  }
   int stage = 0;
 
   for (; b < a.B; b += nwarps) {
-    const int64_t bn = b + nwarps;
+    const int64_t bn = b + (kIxStages - 1) * nwarps;
     unsigned char* sp = my + stage * stage_bytes;
     const float* xs = reinterpret_cast<const float*>(sp);
     if (bn < a.B) {
-      issue(bn, row_next, stage ^ 1);
+      int sa = stage + kIxStages - 1;
+      if (sa >= kIxStages) sa -= kIxStages;
+      issue(bn, row_next, sa);
       if (!xl) row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
     }
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<kIxStages - 1>();
     __syncwarp();
 
     // staged row element e lives at gs[e]
@@ -655,7 +690,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
         }
     }
     __syncwarp();   // the stage may be overwritten by the next iteration's copies
-    stage ^= 1;
+    if (++stage == kIxStages) stage = 0;
   }
 }
 
@@ -724,8 +759,10 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
   int rc = RB_OK;
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
-    constexpr int W = IxWarps<DD>::value;                                                                               \
-    size_t smem = static_cast<size_t>(W) * (kIxStages * 32 * (DD + 8) * 4 + os_bytes);                                  \
+    const size_t per_warp = static_cast<size_t>(kIxStages) * 32 * (DD + RB_IX_FWD_PAD) * 4 + os_bytes;                  \
+    const int W = warps_that_fit(per_warp);                                                                             \
+    RB_CHECK_ARG(W >= 1, RB_ERR_SHAPE, "interaction row does not fit in shared memory");                                \
+    size_t smem = static_cast<size_t>(W) * per_warp;                                                                    \
     if (a.shards != nullptr) {                                                                                          \
       rc = set_smem(dot_interaction_fwd_kernel<DD, OUT, true>, smem);                                                   \
       if (rc != RB_OK) return rc;                                                                                       \
@@ -753,8 +790,10 @@ static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shad
   int rc = RB_OK;
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
-    constexpr int W = IxWarps<DD>::value;                                                                               \
-    size_t smem = static_cast<size_t>(W) * (kIxStages * (32 * (DD + 8) * 2 + DD * 4) + os_bytes);                       \
+    const size_t per_warp = static_cast<size_t>(kIxStages) * (32 * (DD + 8) * 2 + DD * 4) + os_bytes;                   \
+    const int W = warps_that_fit(per_warp);                                                                             \
+    RB_CHECK_ARG(W >= 1, RB_ERR_SHAPE, "interaction row does not fit in shared memory");                                \
+    size_t smem = static_cast<size_t>(W) * per_warp;                                                                    \
     rc = set_smem(dot_interaction_fwd16_kernel<DD, OUT>, smem);                                                         \
     if (rc != RB_OK) return rc;                                                                                         \
     dot_interaction_fwd16_kernel<DD, OUT><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, shadows, out, out_stride,   \
@@ -792,8 +831,10 @@ static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_str
   int rc = RB_OK;
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
-    constexpr int W = IxWarps<DD>::value;                                                                               \
-    size_t smem = static_cast<size_t>(W) * kIxStages * (32 * (DD + 4) * 4 + gs_bytes);                                  \
+    const size_t per_warp = static_cast<size_t>(kIxStages) * (32 * (DD + 4) * 4 + gs_bytes);                            \
+    const int W = warps_that_fit(per_warp);                                                                             \
+    RB_CHECK_ARG(W >= 1, RB_ERR_SHAPE, "interaction row does not fit in shared memory");                                \
+    size_t smem = static_cast<size_t>(W) * per_warp;                                                                    \
     const int src_mode = a.x_load != nullptr ? 2 : (a.shards != nullptr ? 1 : 0);                                       \
     BWD_DISPATCH(DD, src_mode)                                                                                          \
   }
