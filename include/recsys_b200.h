@@ -296,6 +296,16 @@ size_t rb_colsum_workspace_bytes(int64_t rows, int32_t cols);
 int rb_colsum(const void* x, int32_t dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out,
               void* ws, size_t ws_bytes, void* stream);
 
+size_t rb_bce_workspace_bytes(int64_t n);
+
+/*
+ * Loss head of ctr/train.py:85-87 for DLRM: Keras binary_crossentropy on PROBABILITIES (clipped form, SURVEY
+ * Appendix A.5), batch mean, and d loss / d prob in the same pass (dprob_out optional).  prob f32[n];
+ * label f32[n] (label_type 0) or int64[n] (label_type 1).  Deterministic two-stage mean.
+ */
+int rb_bce_clipped(const float* prob, const void* label, int32_t label_type, int64_t n, float* loss_out, float* dprob_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* ---- id -> row map ------------------------------------------------------------------------ */
 
 /* rows_out[p] = uint64(ids[p]) mod vocab  (SURVEY §8c "index hashing"; bit-exact with the oracle).

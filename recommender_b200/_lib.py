@@ -96,6 +96,8 @@ SIGNATURES = {
     "rb_sparse_bwd_prepare_collected": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p]),
     "rb_sparse_bwd_apply_p2p": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i64, _i32, C.POINTER(C.c_void_p), _i64, _p,
                                           C.POINTER(RbOptParams), _p, C.c_size_t, _i32, _p, _p]),
+    "rb_bce_workspace_bytes": (C.c_size_t, [_i64]),
+    "rb_bce_clipped": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, C.c_size_t, _p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

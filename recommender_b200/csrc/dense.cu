@@ -156,6 +156,53 @@ __global__ void __launch_bounds__(kFinalWarps * 32) colsum_final_kernel(const fl
   }
 }
 
+// ---- loss head: Keras binary_crossentropy on probabilities + its gradient, one pass ------------------------
+// ctr/train.py:85 compiles BinaryCrossentropy(from_logits=False); for DLRM (last op Squeeze) Keras evaluates the
+// clipped-probability form:  p <- clip(p, 1e-7, 1-1e-7);  l = -(y log(p+1e-7) + (1-y) log(1-p+1e-7)),
+// batch mean.  dprob = dl/dp / n with the clip's pass-through mask.  Partials per CTA, fixed-order final sum.
+constexpr int kBceThreads = 256;
+
+__global__ void __launch_bounds__(kBceThreads)
+bce_partial_kernel(const float* __restrict__ prob, const void* __restrict__ label, int label_is_i64, int64_t n, float inv_n,
+                   float* __restrict__ dprob, float* __restrict__ partial) {
+  __shared__ float s_red[kBceThreads / 32];
+  const float eps = 1e-7f;
+  float acc = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBceThreads + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * kBceThreads) {
+    const float p = prob[i];
+    const float y = label_is_i64 ? static_cast<float>(static_cast<const int64_t*>(label)[i]) : static_cast<const float*>(label)[i];
+    const float pc = fminf(fmaxf(p, eps), 1.0f - eps);
+    const float a = pc + eps, b = (1.0f - pc) + eps;
+    acc += -(y * logf(a) + (1.0f - y) * logf(b));
+    if (dprob != nullptr) {
+      const bool pass = (p >= eps) && (p <= 1.0f - eps);
+      dprob[i] = pass ? (-(y / a) + (1.0f - y) / b) * inv_n : 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x % 32 == 0) s_red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kBceThreads / 32; ++w) t += s_red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void bce_final_kernel(const float* __restrict__ partial, int nparts, float inv_n, float* __restrict__ loss) {
+  float t = 0.f;
+  for (int i = 0; i < nparts; ++i) t += partial[i];
+  loss[0] = t * inv_n;
+}
+
+static int bce_parts(int64_t n) {
+  int64_t parts = (n + kBceThreads * 4 - 1) / (kBceThreads * 4);
+  if (parts < 1) parts = 1;
+  if (parts > 512) parts = 512;
+  return static_cast<int>(parts);
+}
+
 static int colsum_parts(int64_t rows) {
   int64_t parts = rows / 64;
   if (parts < 1) parts = 1;
@@ -238,5 +285,23 @@ extern "C" int rb_colsum(const void* x, int32_t dtype, int64_t rows, int32_t col
   RB_LAUNCH_CHECK("colsum_partial_kernel");
   colsum_final_kernel<<<(cols + 31) / 32, kFinalWarps * 32, 0, st>>>(partial, parts, cols, out);
   RB_LAUNCH_CHECK("colsum_final_kernel");
+  return RB_OK;
+}
+
+extern "C" size_t rb_bce_workspace_bytes(int64_t n) { return n < 0 ? 0 : static_cast<size_t>(bce_parts(n)) * sizeof(float) + 256; }
+
+extern "C" int rb_bce_clipped(const float* prob, const void* label, int32_t label_type, int64_t n, float* loss_out, float* dprob_out,
+                              void* ws, size_t ws_bytes, void* stream) {
+  RB_CHECK_ARG(n > 0 && prob != nullptr && label != nullptr && loss_out != nullptr, RB_ERR_ARG, "null pointer or n <= 0");
+  RB_CHECK_ARG(label_type == 0 || label_type == 1, RB_ERR_ARG, "label_type: 0 = f32, 1 = i64");
+  RB_CHECK_ARG(ws != nullptr && ws_bytes >= rb_bce_workspace_bytes(n), RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+               rb_bce_workspace_bytes(n), ws_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int parts = bce_parts(n);
+  const float inv_n = 1.0f / static_cast<float>(n);
+  bce_partial_kernel<<<parts, kBceThreads, 0, st>>>(prob, label, label_type, n, inv_n, dprob_out, static_cast<float*>(ws));
+  RB_LAUNCH_CHECK("bce_partial_kernel");
+  bce_final_kernel<<<1, 1, 0, st>>>(static_cast<const float*>(ws), parts, inv_n, loss_out);
+  RB_LAUNCH_CHECK("bce_final_kernel");
   return RB_OK;
 }

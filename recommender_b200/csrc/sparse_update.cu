@@ -36,6 +36,7 @@ constexpr int kRing = RB_SEG_RING;  // sorted entries in flight per lane (cp.asy
 
 struct GradSrcDev {
   int num_src, scale_mode, L, is64;
+  uint32_t L_recip;   // floor(2^32 / L): p / L = umulhi(p, L_recip) (+1 after one correction)
   const float* src[RB_MAX_GRAD_SOURCES];
   int64_t bag_stride[RB_MAX_GRAD_SOURCES];
   int64_t pos_stride[RB_MAX_GRAD_SOURCES];
@@ -76,8 +77,29 @@ __device__ __forceinline__ GradPos decode_pos(const GradGroupsDev& gg, uint32_t 
   for (int k = 1; k < kMaxGroups; ++k) q.gi += (p >= gg.start[k]) ? 1 : 0;
   const uint32_t L = static_cast<uint32_t>(gg.g[q.gi].L);
   q.p = p - gg.start[q.gi];
-  q.b = q.p / L;
+  // q.p / L without the ~20-instruction runtime division: the reciprocal estimate is low by at most one
+  q.b = __umulhi(q.p, gg.g[q.gi].L_recip);
   q.l = q.p - q.b * L;
+  if (q.l >= L) {
+    ++q.b;
+    q.l -= L;
+  }
+  return q;
+}
+
+// SIMPLE gradients (one use of the table, one source tensor, no scaling, no FM term — the DLRM / sharded case):
+// the second half of the work on a gradient row vanishes and the group search is skipped
+__device__ __forceinline__ GradPos decode_pos_simple(const GradGroupsDev& gg, uint32_t p) {
+  GradPos q;
+  q.gi = 0;
+  const uint32_t L = static_cast<uint32_t>(gg.g[0].L);
+  q.p = p;
+  q.b = __umulhi(p, gg.g[0].L_recip);
+  q.l = p - q.b * L;
+  if (q.l >= L) {
+    ++q.b;
+    q.l -= L;
+  }
   return q;
 }
 
@@ -277,7 +299,7 @@ __global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, in
 // fetched with cp.async into the lane's ring slots, so up to kRing entries x 4 rows are in flight per
 // lane without holding registers; a lane only ever reads back the bytes it copied itself, so no
 // cross-lane synchronisation is needed.  dynamic smem: ring[kRing][1 + Sink::kStateRows][kSegThreads][VEC].
-template <int VEC, int GS, class Sink>
+template <int VEC, int GS, class Sink, bool SIMPLE>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
                         const __grid_constant__ GradGroupsDev gsrc, Sink sink, float* __restrict__ head_part,
@@ -331,12 +353,12 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
   auto issue = [&](int j, int slot) {
     if (j < tcnt && active) {
       const uint32_t key = tk[j];
-      const GradPos q = decode_pos(gsrc, tp[j]);
+      const GradPos q = SIMPLE ? decode_pos_simple(gsrc, tp[j]) : decode_pos(gsrc, tp[j]);
       float* dst = my_ring + slot * kSlotStride;
       cp_async_vec<VEC>(dst, grad_src0(gsrc, q, c), gsrc.peer != 0);
       if (kKinds > 1) {
         const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
-        sink.template issue_state<VEC>(key, c, update, gsrc.g[q.gi].fm_g != nullptr, dst + kKStride, kKStride);
+        sink.template issue_state<VEC>(key, c, update, !SIMPLE && gsrc.g[q.gi].fm_g != nullptr, dst + kKStride, kKStride);
       }
     }
     cp_async_commit();   // one group per entry, also when nothing was copied: keeps wait_group uniform
@@ -363,7 +385,7 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
     if (active) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) g.v[i] = sl[i];
-      finish_grad<VEC>(gsrc, decode_pos(gsrc, tp[j]), c, g, sl + kKStride);
+      if constexpr (!SIMPLE) finish_grad<VEC>(gsrc, decode_pos(gsrc, tp[j]), c, g, sl + kKStride);
     }
     if (key != cur) {  // previous run was closed below; start a new one
       cur = key;
@@ -514,6 +536,12 @@ struct WsLayout {
   size_t keys_a, keys_b, vals_a, vals_b, seg_incl, head_part, tail_part, long_list, long_count, cub_temp, cub_bytes, total;
 };
 
+// floor(2^32 / L) clamped to 32 bits (L = 1): umulhi(p, r) is p / L or one less
+static uint32_t recip32(int L) {
+  const uint64_t r = (1ull << 32) / static_cast<uint64_t>(L);
+  return r > 0xFFFFFFFFull ? 0xFFFFFFFFu : static_cast<uint32_t>(r);
+}
+
 static size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 // a chain is "long" when it spans more than kLongChain tiles, so at most this many can exist
@@ -561,6 +589,7 @@ static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_
   d->num_src = g->num_src;
   d->scale_mode = g->scale_mode;
   d->L = L;
+  d->L_recip = recip32(L);
   d->is64 = (idx_type == RB_I64);
   for (int k = 0; k < RB_MAX_GRAD_SOURCES; ++k) {
     d->src[k] = nullptr;
@@ -593,15 +622,25 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
   RB_CUDA(cudaMemsetAsync(lc, 0, sizeof(int), st));
   const int tiles = (n + kTile - 1) / kTile;
   const int cap = long_list_cap(n);
+  const GradSrcDev& g0 = gsrc.g[0];
+  const bool simple = gsrc.num == 1 && g0.num_src == 1 && g0.scale_mode == RB_SCALE_NONE && g0.fm_g == nullptr;
 #define CALL(V, G)                                                                                                      \
   {                                                                                                                     \
     constexpr int kGroups = kSegThreads / G;                                                                            \
     const size_t ring_bytes = static_cast<size_t>(kRing) * (1 + Sink::kStateRows) * kSegThreads * V * sizeof(float);   \
-    if (ring_bytes > 40 * 1024)                                                                                         \
-      RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                   static_cast<int>(ring_bytes)));                                                      \
-    seg_reduce_tiles_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, gsrc,   \
-                                                                                                    sink, head, tail);  \
+    if (simple) {                                                                                                       \
+      if (ring_bytes > 40 * 1024)                                                                                       \
+        RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(ring_bytes)));                                                    \
+      seg_reduce_tiles_kernel<V, G, Sink, true><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, \
+                                                                                                            gsrc, sink, head, tail); \
+    } else {                                                                                                            \
+      if (ring_bytes > 40 * 1024)                                                                                       \
+        RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(ring_bytes)));                                                    \
+      seg_reduce_tiles_kernel<V, G, Sink, false><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, \
+                                                                                                             gsrc, sink, head, tail); \
+    }                                                                                                                   \
     seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, n_dev, gsrc.D, sink, head, tail, ll, lc, \
                                                                                    cap);                                 \
     seg_long_chain_kernel<V, G, Sink><<<2 * kNumSMs, kSegThreads, 0, st>>>(gsrc.D, sink, head, tail, ll, lc, cap);      \
@@ -966,6 +1005,7 @@ extern "C" int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state
     g.num_src = 1;
     g.scale_mode = RB_SCALE_NONE;
     g.L = L;
+    g.L_recip = recip32(L);
     g.is64 = 0;
     for (int j = 0; j < RB_MAX_GRAD_SOURCES; ++j) {
       g.src[j] = nullptr;

@@ -87,9 +87,28 @@ class DLRM(nn.Module):
         return output.squeeze(1)                                                        # :57
 
 
+class _BCEClippedFn(torch.autograd.Function):
+    """Loss and d loss / d prob from one kernel pair (rb_bce_clipped) instead of ~25 elementwise launches."""
+
+    @staticmethod
+    def forward(ctx, prob, label):
+        from . import ops
+        loss, dprob = ops.bce_clipped(prob, label, want_grad=True)
+        ctx.save_for_backward(dprob)
+        ctx.shape = prob.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dprob,) = ctx.saved_tensors
+        return (dprob * g).reshape(ctx.shape), None
+
+
 def bce_clipped(prob: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     """Keras binary_crossentropy on probabilities, batch mean — what compile(loss=BinaryCrossentropy)
     evaluates for DLRM (ctr/train.py:85-87)."""
+    if prob.is_cuda and prob.dtype == torch.float32 and label.dtype in (torch.float32, torch.int64):
+        return _BCEClippedFn.apply(prob, label)
     eps = 1e-7
     y = label.to(prob.dtype)
     p = prob.clamp(eps, 1.0 - eps)

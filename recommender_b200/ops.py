@@ -418,6 +418,22 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def bce_clipped(prob: torch.Tensor, label: torch.Tensor, want_grad: bool = True):
+    """Keras binary_crossentropy on probabilities, batch mean (rb_bce_clipped).  Returns (loss f32[], dloss/dprob f32[n] | None)."""
+    _need_cuda(prob, label)
+    prob = prob.contiguous()
+    label = label.contiguous()
+    if prob.dtype != torch.float32 or label.dtype not in (torch.float32, torch.int64) or label.numel() != prob.numel():
+        raise TypeError("bce_clipped takes float32 probabilities and float32 / int64 labels of the same size")
+    n = prob.numel()
+    loss = torch.empty((), dtype=torch.float32, device=prob.device)
+    dprob = torch.empty_like(prob) if want_grad else None
+    ws = _workspace(max(lib.rb_bce_workspace_bytes(n), 256), prob.device)
+    check(lib.rb_bce_clipped(_ptr(prob), _ptr(label), 1 if label.dtype == torch.int64 else 0, n, _ptr(loss), _ptr(dprob), _ptr(ws),
+                             ws.numel(), _stream()), "rb_bce_clipped")
+    return loss, dprob
+
+
 # --------------------------------------------------------------------------------------------
 # id -> row map, sharding
 # --------------------------------------------------------------------------------------------

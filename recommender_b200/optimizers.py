@@ -66,8 +66,11 @@ class _Optimizer:
         params = [p for p in dense if p.grad is not None]
         if params:
             self._dense_step(params, [p.grad for p in params], step)
-            for p in params:
-                p.grad = None
+            if hasattr(model_or_vars, "reset_dense_grads"):
+                model_or_vars.reset_dense_grads()      # gradients are views of one flat buffer: zero it, keep the views
+            else:
+                for p in params:
+                    p.grad = None
         for e in embs:
             e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
         self.iterations = step

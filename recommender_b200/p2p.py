@@ -429,6 +429,7 @@ class P2PShardedDLRM(nn.Module):
             if len(self.top_mlp.kernels) == 0:
                 self.top_mlp.build(width, int_features.device)
             self.sync_dense_parameters()
+            self._attach_flat_grads()
         bmlp_output = self.bottom_mlp(int_features)
         bf16 = self.top_mlp.compute_dtype == torch.bfloat16
         tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
@@ -436,18 +437,25 @@ class P2PShardedDLRM(nn.Module):
                                                    routed=routed)
         return self.top_mlp(tmlp_input).squeeze(1)
 
-    def reduce_dense_grads(self) -> None:
-        """SUM over replicas of the MLP gradients in one flat all-reduce (MirroredStrategy with Reduction.NONE
-        losses); called by the optimizers."""
-        if not isinstance(self.link, DistPeerLink) or self.link.world == 1:
-            return
-        params = [p for p in self.parameters() if p.grad is not None]
-        if not params:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+    def _attach_flat_grads(self) -> None:
+        """All MLP gradients live in ONE flat buffer (the parameters' .grad are views of it): the replicas' sum is
+        a single all-reduce with no gather / scatter copies around it."""
+        params = [p for p in self.parameters() if p.requires_grad]
+        if self._flat is None or self._flat.numel() != sum(p.numel() for p in params):
+            self._flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
         o = 0
         for p in params:
             n = p.numel()
-            p.grad.copy_(flat[o:o + n].view_as(p.grad))
+            p.grad = self._flat[o:o + n].view_as(p)
             o += n
+
+    def reset_dense_grads(self) -> None:
+        """Called by the optimizers instead of dropping the .grad tensors."""
+        if self._flat is not None:
+            self._flat.zero_()
+
+    def reduce_dense_grads(self) -> None:
+        """SUM over replicas of the MLP gradients (MirroredStrategy with Reduction.NONE losses, SURVEY A.5/A.7);
+        called by the optimizers before the dense step."""
+        if self._flat is not None and isinstance(self.link, DistPeerLink) and self.link.world > 1:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)

@@ -574,3 +574,24 @@ def test_peer_memory_sharded_step_equals_unsharded(ops, G, T, shadow):
         owners = {int((t * embs[0].pitch) % G) for t in range(T)}
         assert len(owners) == min(G, T)
     assert int(sum(int(e._n_valid.item()) for e in embs)) == G * B * F
+
+
+@pytest.mark.parametrize("n", [1, 255, 65536, 100003])
+@pytest.mark.parametrize("ltype", [torch.int64, torch.float32])
+def test_bce_clipped_head(ops, n, ltype):
+    """rb_bce_clipped against the oracle's Keras clipped-probability BCE and torch autograd of the same expression,
+    including probabilities at and beyond the clip points."""
+    rng = np.random.default_rng(n)
+    p = rng.random(n).astype(np.float32)
+    p[: min(n, 4)] = np.array([0.0, 1.0, 1e-9, 1.0 - 1e-9], np.float32)[: min(n, 4)]
+    y = (rng.random(n) < 0.25)
+    ref_loss, ref_d = O.bce_clipped(p, y.astype(np.int64))
+    loss, dprob = ops.bce_clipped(cu(p), cu(y).to(ltype))
+    assert abs(float(loss) - float(ref_loss)) <= 1e-6 * max(1.0, abs(float(ref_loss)))
+    np.testing.assert_allclose(dprob.cpu().numpy(), ref_d, rtol=1e-5, atol=1e-12)
+    pt = cu(p).requires_grad_()
+    yt = cu(y).float()
+    e = 1e-7
+    pc = pt.clamp(e, 1 - e)
+    (-(yt * torch.log(pc + e) + (1 - yt) * torch.log(1 - pc + e))).mean().backward()
+    np.testing.assert_allclose(dprob.cpu().numpy(), pt.grad.cpu().numpy(), rtol=1e-5, atol=1e-12)
