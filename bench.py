@@ -213,6 +213,13 @@ class CallTimer:
             self._orig[n] = getattr(self.ops, n)
             setattr(self.ops, n, self._wrap(n, self._orig[n]))
 
+    def install_on(self, obj, methods, prefix):
+        """Also time bound methods of `obj` (the peer-memory embedding calls the library directly)."""
+        for m in methods:
+            name = prefix + m
+            self.records[name] = []
+            setattr(obj, m, self._wrap(name, getattr(obj, m)))
+
     def _wrap(self, name, fn):
         def timed(*a, **k):
             if not self.enabled:
@@ -280,6 +287,8 @@ def run_b200(args):
     timer = CallTimer(ops, ["dot_interaction_fwd", "dot_interaction_bwd", "sparse_bwd_update", "sparse_bwd_prepare", "sparse_bwd_apply",
                             "gather_fwd", "bucket_by_owner", "dense_opt_step", "colsum"])
     timer.install()
+    if world > 1 and args.exchange == "p2p":
+        timer.install_on(model.embedding_layer, ["route", "collect_and_sort", "_interaction_fwd", "_interaction_bwd", "apply_pending"], "p2p.")
 
     def barrier():
         if world > 1:
@@ -427,6 +436,13 @@ def run_b200(args):
                                  frac=gbs / peak, share_of_step=ms * cnt / k_eager / ms_step)
         else:
             kernels[name] = dict(ms=ms, calls_per_step=cnt / k_eager, share_of_step=ms * cnt / k_eager / ms_step)
+    if world > 1 and args.exchange == "p2p":
+        # bytes each rank pulls over NVLink per step: (G-1)/G of the rows (bf16 shadow) in the forward, of the fp32 gradient rows in the apply
+        remote = (world - 1) / world
+        for name, nbytes in (("p2p._interaction_fwd", N * D * 2 * remote), ("p2p.apply_pending", N * D * 4 * remote)):
+            if name in kernels:
+                kernels[name]["nvlink_bytes"] = int(nbytes)
+                kernels[name]["nvlink_gbs_if_alone"] = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
     roofline = None
     timed = {k: v for k, v in kernels.items() if "achieved_gbs" in v}
     if timed:

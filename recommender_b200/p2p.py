@@ -94,6 +94,13 @@ class DistPeerLink(PeerLink):
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.legacy_ipc = bool(int(os.environ.get("RB_P2P_LEGACY_IPC", "0"))) if legacy_ipc is None else legacy_ipc
         self._keep = []
+        # Rendezvous of the ranks on the stream: a device-side barrier over symmetric-memory signal pads (a few
+        # microseconds, one kernel, capturable) instead of a 1-element NCCL all-reduce (45-75 us at 8 GPUs).
+        self._bar = None
+        if self.world > 1 and not self.legacy_ipc and os.environ.get("RB_P2P_BARRIER", "symm") == "symm":
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(64, dtype=torch.float32, device=self.device)
+            self._bar = (t, symm_mem.rendezvous(t, self.group))
 
     def alloc(self, name, shape, dtype):
         if self.world == 1:
@@ -122,6 +129,9 @@ class DistPeerLink(PeerLink):
         return buf.tensor, ptrs
 
     def barrier(self):
+        if self._bar is not None:
+            self._bar[1].barrier(channel=0)
+            return
         dist.all_reduce(self._token, group=self.group)
         self._token.zero_()
 
