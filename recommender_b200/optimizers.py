@@ -61,8 +61,13 @@ class _Optimizer:
         dien/train.py:22)."""
         embs, dense = _split(model_or_vars)
         if hasattr(model_or_vars, "reduce_dense_grads"):
-            model_or_vars.reduce_dense_grads()      # data-parallel replicas (sharded.ShardedDLRM)
+            model_or_vars.reduce_dense_grads()      # data-parallel replicas (sharded.ShardedDLRM, p2p.P2PShardedDLRM)
         step = self.iterations if self._prepared else self.iterations + 1
+        overlap = hasattr(model_or_vars, "wait_dense_grads")
+        if overlap:      # the replicas' all-reduce runs on a side stream: do the sparse tables first, then join it
+            for e in embs:
+                e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+            model_or_vars.wait_dense_grads()
         params = [p for p in dense if p.grad is not None]
         if params:
             self._dense_step(params, [p.grad for p in params], step)
@@ -71,8 +76,9 @@ class _Optimizer:
             else:
                 for p in params:
                     p.grad = None
-        for e in embs:
-            e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+        if not overlap:
+            for e in embs:
+                e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
         self.iterations = step
         if not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
             self._prepared = False      # a captured body is replayed: every replay is preceded by prepare_step()

@@ -75,7 +75,7 @@ class PeerLink:
     def alloc(self, name: str, shape: Sequence[int], dtype: torch.dtype):
         raise NotImplementedError
 
-    def barrier(self) -> None:
+    def barrier(self, channel: int = 0) -> None:
         raise NotImplementedError
 
 
@@ -128,9 +128,9 @@ class DistPeerLink(PeerLink):
             ptrs.append(int(p.value))
         return buf.tensor, ptrs
 
-    def barrier(self):
+    def barrier(self, channel: int = 0):
         if self._bar is not None:
-            self._bar[1].barrier(channel=0)
+            self._bar[1].barrier(channel=channel)
             return
         dist.all_reduce(self._token, group=self.group)
         self._token.zero_()
@@ -150,7 +150,7 @@ class LocalPeerLink(PeerLink):
         slots[self.rank] = buf
         return buf.tensor, (lambda: [b.ptr for b in slots])   # resolved lazily, once every emulated rank has registered
 
-    def barrier(self):
+    def barrier(self, channel: int = 0):
         pass
 
 
@@ -225,6 +225,7 @@ class P2PShardedEmbedding(nn.Module):
         self._side: Optional[torch.cuda.Stream] = None
         self._shard_ptr_dev: Optional[torch.Tensor] = None
         self._routed_by_caller = False
+        self._begun = None
 
     # ---- lazily built per-shape step buffers -----------------------------------------------------------------
     def _resolve(self, v):
@@ -347,22 +348,37 @@ class P2PShardedEmbedding(nn.Module):
         self._pending = True
         return d_dense
 
+    def begin_step(self, idx: torch.Tensor) -> None:
+        """Start this step's routing on the side stream as soon as the ids exist (the model calls it before the
+        bottom MLP, which needs no embeddings): publish the bucket arrays, meet the other ranks, then collect and
+        sort the pairs this rank owns.  interact() waits for the rendezvous, apply_pending() for the sort."""
+        idx = idx.contiguous()
+        B, F = idx.shape
+        self._build(B, F)
+        main, side = torch.cuda.current_stream(), self._side
+        side.wait_stream(main)                   # ids are ready; last step's apply (on main) precedes this rank's arrival
+        with torch.cuda.stream(side):
+            self.route(idx)
+            self.link.barrier(0)                 # every rank's bucket arrays are published and last step's updates are done
+            self._routed_ev = side.record_event()
+            if torch.is_grad_enabled():
+                self.collect_and_sort()
+            self._sorted_ev = side.record_event()
+        if not torch.cuda.is_current_stream_capturing():
+            idx.record_stream(side)
+        self._begun = idx
+
     def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
                  out_dtype=torch.float32, pad_to=1, routed=False) -> torch.Tensor:
         """ctr/model.py:49-55 on the sharded table.  Unless the caller already ran route()/collect_and_sort()
-        (`routed=True`, lock-step emulation), this also publishes the routing, meets the other ranks and starts
-        the owner-side sort on a side stream so that it overlaps the forward."""
+        (`routed=True`, lock-step emulation) the step's routing runs on the side stream (begin_step)."""
         idx = idx.contiguous()
         self._routed_by_caller = bool(routed)
         if not routed:
-            self.route(idx)
-            self.link.barrier()                  # every rank's bucket arrays are published (and last step's updates are done)
-            if torch.is_grad_enabled():
-                main = torch.cuda.current_stream()
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    self.collect_and_sort()
-                    self._sorted_ev = self._side.record_event()
+            if self._begun is None or self._begun.data_ptr() != idx.data_ptr():
+                self.begin_step(idx)
+            self._begun = None
+            torch.cuda.current_stream().wait_event(self._routed_ev)
         return _P2PInteractFn.apply(self._anchor, self, idx, dense_vec.float(), (self_interaction, skip_gather, tail), out_dtype, pad_to)
 
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
@@ -386,7 +402,7 @@ class P2PShardedEmbedding(nn.Module):
             raise ValueError(f"the peer-memory path supports adam_lazy / adagrad / sgd, not {kind}")
         if not self._routed_by_caller:
             torch.cuda.current_stream().wait_event(self._sorted_ev)
-            self.link.barrier()                  # every rank's backward has written its dE and stopped reading the shards
+            self.link.barrier(1)                 # every rank's backward has written its dE and stopped reading the shards
         opt = ops._opt_params(kind, step, lr, beta_1, beta_2, epsilon, alpha_dev)
         _, F = self._shape
         check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
@@ -420,6 +436,8 @@ class P2PShardedDLRM(nn.Module):
         self.num_cat_fea, self.num_int_fea, self.embedding_size = num_cat_fea, num_int_fea, embedding_size
         self._synced = False
         self._flat = None
+        self._reduce_stream = None
+        self._reduce_ev = None
 
     def sync_dense_parameters(self) -> None:
         if isinstance(self.link, DistPeerLink) and self.link.world > 1:
@@ -440,6 +458,8 @@ class P2PShardedDLRM(nn.Module):
                 self.top_mlp.build(width, int_features.device)
             self.sync_dense_parameters()
             self._attach_flat_grads()
+        if not routed:
+            self.embedding_layer.begin_step(cat_features)      # routing + rendezvous overlap the bottom MLP
         bmlp_output = self.bottom_mlp(int_features)
         bf16 = self.top_mlp.compute_dtype == torch.bfloat16
         tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
@@ -465,7 +485,20 @@ class P2PShardedDLRM(nn.Module):
             self._flat.zero_()
 
     def reduce_dense_grads(self) -> None:
-        """SUM over replicas of the MLP gradients (MirroredStrategy with Reduction.NONE losses, SURVEY A.5/A.7);
-        called by the optimizers before the dense step."""
+        """SUM over replicas of the MLP gradients (MirroredStrategy with Reduction.NONE losses).
+        Started on a side stream so that it overlaps the sparse apply; wait_dense_grads() joins it before the
+        dense optimizer step (the optimizers call both)."""
+        self._reduce_ev = None
         if self._flat is not None and isinstance(self.link, DistPeerLink) and self.link.world > 1:
-            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self._reduce_stream is None:
+                self._reduce_stream = torch.cuda.Stream(device=self._flat.device)
+            main = torch.cuda.current_stream()
+            self._reduce_stream.wait_stream(main)
+            with torch.cuda.stream(self._reduce_stream):
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+                self._reduce_ev = self._reduce_stream.record_event()
+
+    def wait_dense_grads(self) -> None:
+        if self._reduce_ev is not None:
+            torch.cuda.current_stream().wait_event(self._reduce_ev)
+            self._reduce_ev = None
