@@ -236,6 +236,30 @@ class CallTimer:
         return {n: (sum(s.elapsed_time(e) for s, e in r) / len(r), len(r)) for n, r in self.records.items() if r}
 
 
+def peer_memory_usable(args, dev) -> bool:
+    """Pre-flight for the peer-memory path: every rank tries a tiny symmetric-memory allocation + rendezvous; unless ALL
+    succeed, all ranks fall back to the NCCL all-to-all path together (a one-sided failure would deadlock later)."""
+    import torch.distributed as dist
+    if args.exchange != "p2p":
+        return False
+    ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(64, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+        hdl.barrier(channel=0)
+        torch.cuda.synchronize()
+    except Exception as e:                                        # noqa: BLE001 - any failure means "not usable here"
+        print(f"# peer-memory pre-flight failed on rank {dist.get_rank()}: {type(e).__name__}: {e}", file=sys.stderr)
+        ok = 0
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    usable = bool(int(flag.item()))
+    if not usable:
+        args.exchange = "nccl"
+    return usable
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,7 +287,7 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(4)
     if world == 1:
         model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
-    elif args.exchange == "p2p":
+    elif peer_memory_usable(args, dev):
         from recommender_b200.p2p import P2PShardedDLRM
         model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
     else:
@@ -454,6 +478,26 @@ def run_b200(args):
                              "(sparse_bwd_prepare, overhead, not algorithmic bytes) run on a side stream during the forward; "
                              "sparse_bwd_update = both phases in one call")
 
+    # ---- the second half of BASELINE.json's metric: embedding-gather HBM GB/s (un-pooled lookup, rb_gather_fwd) ----------
+    gather = None
+    if world == 1:
+        table = model.embedding_layer.embeddings
+        off = model.embedding_layer.row_offset_for(F_CAT)
+        gout = torch.empty(B, F_CAT, D, dtype=torch.float32, device=dev)
+        for i in range(3):
+            ops.gather_fwd(table, resident[i % args.ring][0], L=F_CAT, field_row_offset=off, out=gout, out_stride=D)
+        gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gs_.record()
+        for i in range(20):
+            ops.gather_fwd(table, resident[i % args.ring][0], L=F_CAT, field_row_offset=off, out=gout, out_stride=D)
+        ge_.record()
+        torch.cuda.synchronize()
+        g_ms = gs_.elapsed_time(ge_) / 20
+        g_bytes = N * D * 4 * 2 + N * 8        # rows + ids + output
+        gather = dict(metric="embedding-gather HBM GB/s", ms=g_ms, algorithmic_bytes=g_bytes, achieved_gbs=g_bytes / (g_ms * 1e-3) / 1e9,
+                      frac=g_bytes / (g_ms * 1e-3) / 1e9 / peak, peak=peak, lookups=N, emb_dim=D)
+        del gout
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = time_cpu_reference(args, steps=2, warmup=1, budget_s=90)
@@ -463,7 +507,7 @@ def run_b200(args):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 tables/optimizer, bf16 MMA operands (f32 accumulate)",
                     data="synthetic", config=workload_config(args, world), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
                     kernels=kernels, cpu_baseline=cpu, clocks=clocks, final_loss=final_loss, host_cores=os.cpu_count(),
-                    launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step)
+                    launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step, embedding_gather=gather)
         print(json.dumps(line), flush=True)
     if world > 1:
         # a captured graph holding NCCL kernels plus peer-mapped buffers makes interpreter teardown unreliable:
