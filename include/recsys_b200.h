@@ -51,7 +51,12 @@ typedef enum rb_status {
 typedef enum rb_index_type { RB_I32 = 0, RB_I64 = 1 } rb_index_type;
 
 /* element type of the interaction output / its incoming gradient */
-typedef enum rb_float_type { RB_F32 = 0, RB_BF16 = 1 } rb_float_type;
+typedef enum rb_float_type {
+  RB_F32 = 0,
+  RB_BF16 = 1,
+  RB_BF16_ONES = 2  /* output rows only: bf16 whose FIRST pad column holds 1.0 (the others 0): a consumer Dense layer
+                       whose padded kernel has a zero row there reads its bias gradient off its weight-gradient GEMM */
+} rb_float_type;
 
 /* pooling over the L positions of a bag */
 typedef enum rb_pool_mode {

@@ -22,7 +22,7 @@ RB_IPC_HANDLE_BYTES = 64
 
 # enums (recsys_b200.h)
 RB_I32, RB_I64 = 0, 1
-RB_F32, RB_BF16 = 0, 1
+RB_F32, RB_BF16, RB_BF16_ONES = 0, 1, 2
 RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
 RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
 RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2

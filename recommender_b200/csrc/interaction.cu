@@ -66,6 +66,7 @@ struct IxArgs {
   int skip_gather;
   int tail;
   int ncols;               // interaction columns (without tail)
+  int pad_one;             // bf16 output rows: first pad column = 1.0 (RB_BF16_ONES)
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------
@@ -240,6 +241,7 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
   const int F = a.F;
   const int total = a.ncols + (a.tail ? D : 0);
   const int width = write_width > total ? write_width : total;
+  if (a.pad_one && width > total && lane == 0) os[total] = Elem<OUT>::from(1.0f);   // pad columns are written once: they never change
 
   // where each accumulator element goes in the staged row (sample-independent):
   // tile T = (mt, nt) in {(0,0),(0,1),(0,2),(0,3),(1,2),(1,3)}, element k: i = mt*16+g+(k/2)*8, j = nt*8+t2+(k%2)
@@ -394,6 +396,7 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
   const int F = a.F;
   const int total = a.ncols + (a.tail ? D : 0);
   const int width = write_width > total ? write_width : total;
+  if (a.pad_one && width > total && lane == 0) os[total] = Elem<OUT>::from(1.0f);
 
   constexpr int kTileM[6] = {0, 0, 0, 0, 1, 1};
   constexpr int kTileN[6] = {0, 1, 2, 3, 2, 3};
@@ -732,6 +735,7 @@ static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows
   a->skip_gather = skip_gather ? 1 : 0;
   a->tail = tail ? 1 : 0;
   a->ncols = skip_gather ? Fp * Fp : (self_interaction ? Fp * (Fp + 1) / 2 : Fp * (Fp - 1) / 2);
+  a->pad_one = 0;
   return RB_OK;
 }
 
@@ -859,7 +863,9 @@ extern "C" int rb_dot_interaction_fwd(const float* E, const float* table, int64_
   if (B == 0) return RB_OK;
   const int total = a.ncols + (a.tail ? D : 0);
   RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
-  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
+  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16 || out_dtype == RB_BF16_ONES, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
+  RB_CHECK_ARG(out_dtype != RB_BF16_ONES || out_stride > total, RB_ERR_ARG, "RB_BF16_ONES needs at least one pad column");
+  a.pad_one = (out_dtype == RB_BF16_ONES);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == RB_F32) {
     RB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 3) == 0, RB_ERR_ALIGN, "out not 4 B aligned");
@@ -911,7 +917,9 @@ extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev,
   a.x_save = static_cast<__nv_bfloat16*>(x_save);
   const int total = a.ncols + (a.tail ? D : 0);
   RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
-  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
+  RB_CHECK_ARG(out_dtype == RB_F32 || out_dtype == RB_BF16 || out_dtype == RB_BF16_ONES, RB_ERR_ARG, "bad out_dtype %d", out_dtype);
+  RB_CHECK_ARG(out_dtype != RB_BF16_ONES || out_stride > total, RB_ERR_ARG, "RB_BF16_ONES needs at least one pad column");
+  a.pad_one = (out_dtype == RB_BF16_ONES);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* const* shadows = reinterpret_cast<const __nv_bfloat16* const*>(shadow_ptrs_dev);
   if (out_dtype == RB_F32) {

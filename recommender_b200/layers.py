@@ -99,12 +99,12 @@ class _InteractFn(torch.autograd.Function):
     """Lookup + DLRM concat + DotInteraction + '|| bmlp' tail in one kernel (ctr/model.py:49-55)."""
 
     @staticmethod
-    def forward(ctx, anchor, emb, idx, dense_vec, self_interaction, skip_gather, tail, out_dtype, pad_to):
+    def forward(ctx, anchor, emb, idx, dense_vec, self_interaction, skip_gather, tail, out_dtype, pad_to, ones_col=False):
         F = idx.shape[1]
         dense_vec = dense_vec.contiguous()
         out = ops.dot_interaction_fwd(table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
                                       dense_vec=dense_vec, self_interaction=self_interaction, skip_gather=skip_gather,
-                                      tail=tail, out_dtype=out_dtype, pad_to=pad_to)
+                                      tail=tail, out_dtype=out_dtype, pad_to=pad_to, ones_col=ones_col)
         ctx.emb, ctx.idx, ctx.flags = emb, idx, (self_interaction, skip_gather, tail)
         ctx.save_for_backward(dense_vec)
         return out
@@ -121,7 +121,7 @@ class _InteractFn(torch.autograd.Function):
                                               dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail)
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
-        return None, None, None, d_dense, None, None, None, None, None
+        return None, None, None, d_dense, None, None, None, None, None, None
 
 
 class _DotInteractionFn(torch.autograd.Function):
@@ -242,14 +242,15 @@ class Embedding(nn.Module):
         return _GatherFMFn.apply(self._anchor, self, idx)
 
     def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
-                 out_dtype=torch.float32, pad_to=1):
+                 out_dtype=torch.float32, pad_to=1, ones_col=False):
         """ctr/model.py:49-55 fused: [DotInteraction([E ; dense_vec]) || dense_vec] with E read
         straight from the table, so [B,F,D] and [B,F+1,D] never exist in HBM.  out_dtype=bfloat16
         emits the row in bf16, zero-padded to a multiple of `pad_to` columns (the K operand of a
         bf16 top MLP); its gradient then comes back in the same padded bf16 form."""
         idx = idx.contiguous()
         self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
-        return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to)
+        return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to,
+                                 ones_col)
 
     # -- optimizer side (called by optimizers.*.apply_gradients)
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
@@ -314,13 +315,15 @@ class _LinearBF16Fn(torch.autograd.Function):
         return sh[0]
 
     @staticmethod
-    def forward(ctx, x, W, b, need_dx):
+    def forward(ctx, x, W, b, need_dx, ones_col=False):
+        """ones_col: the caller set pad column `in_dim` of x to 1.0 (the matching row of the padded kernel is zero,
+        so the output is unchanged); then row `in_dim` of x^T dy IS the bias gradient and no column sum runs."""
         in_dim, out = W.shape
         Kp = x.shape[1]
         Wp = _LinearBF16Fn._bf16_shadow(W, Kp)
         y = torch.addmm(_LinearBF16Fn._bf16_shadow(b), x, Wp)
         ctx.save_for_backward(x, Wp)
-        ctx.in_dim, ctx.need_dx = in_dim, need_dx
+        ctx.in_dim, ctx.need_dx, ctx.ones_col = in_dim, need_dx, bool(ones_col) and Kp > in_dim
         return y
 
     @staticmethod
@@ -329,17 +332,18 @@ class _LinearBF16Fn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.mm(dy, Wp.t()) if ctx.need_dx else None
         if dy.is_cuda:
-            dW = torch.mm(x.t(), dy, out_dtype=torch.float32)[: ctx.in_dim]      # fp32 accumulate AND fp32 result
-            if not dW.is_contiguous():
-                dW = dW.contiguous()
+            dW_full = torch.mm(x.t(), dy, out_dtype=torch.float32)               # fp32 accumulate AND fp32 result
         else:
-            dW = torch.mm(x.t(), dy)[: ctx.in_dim].float()
+            dW_full = torch.mm(x.t(), dy).float()
+        dW = dW_full[: ctx.in_dim]
+        if ctx.ones_col:
+            return dx, dW, dW_full[ctx.in_dim].clone(), None, None               # bias gradient came with the GEMM
         if dy.is_cuda and dy.shape[1] % 8 == 0:
             db = ops.colsum(dy)                       # rb_colsum: deterministic fp32 column sums
         else:
             ones = torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device)
             db = torch.mm(ones, dy).reshape(-1).float()
-        return dx, dW, db, None
+        return dx, dW, db, None, None
 
 
 class MLP(nn.Module):
@@ -395,7 +399,9 @@ class MLP(nn.Module):
             x = torch.sigmoid(x)
         return x
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, ones_col: bool = False) -> torch.Tensor:
+        """ones_col=True: x arrives bf16, padded, with pad column `in_dim` already set to 1.0 (the fused interaction
+        kernel does that), which lets the first layer read its bias gradient off the weight-gradient GEMM."""
         if len(self.kernels) == 0:
             self.build(x.shape[-1], x.device)
         if self.compute_dtype is None:
@@ -414,9 +420,11 @@ class MLP(nn.Module):
                 x = x.to(torch.bfloat16)
             else:
                 xp[:, : self.in_dim] = x              # autograd-aware pad (dense inputs carry no gradient in the models)
+                xp[:, self.in_dim] = 1.0              # ones column: the bias gradient falls out of the dW GEMM
                 x = xp
+                ones_col = True
         for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
-            x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0)
+            x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0, ones_col and i == 0)
         return self._activate(x)
 
 

@@ -73,9 +73,10 @@ class DLRM(nn.Module):
                 # the fused kernel emits the top MLP's K operand directly: bf16, zero-padded to 8 columns
                 if len(self.top_mlp.kernels) == 0:
                     self.top_mlp.build(width, bmlp_output.device)
+                ones = width % 8 != 0          # a spare pad column exists: it carries 1.0 so that db comes with the dW GEMM
                 tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
-                                                           out_dtype=torch.bfloat16, pad_to=8)          # :49,:51-55
-                return self.top_mlp(tmlp_input).squeeze(1)                                              # :56-57
+                                                           out_dtype=torch.bfloat16, pad_to=8, ones_col=ones)   # :49,:51-55
+                return self.top_mlp(tmlp_input, ones_col=ones).squeeze(1)                               # :56-57
             tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True)   # :49,:51-55
         else:
             cat_embedding = self.embedding_layer(cat_features)                          # :49

@@ -154,11 +154,12 @@ def _float_type(dtype) -> int:
 
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
                         self_interaction=False, skip_gather=True, tail=False, out=None, out_stride=None,
-                        out_dtype=torch.float32, pad_to=1):
+                        out_dtype=torch.float32, pad_to=1, ones_col=False):
     """rb_dot_interaction_fwd.  Either E[B,F,D] or (table, idx[B,F]) supplies the embedding rows.
 
     out_dtype=torch.float32 returns the reference layout [B, ncols(+D)].  out_dtype=torch.bfloat16
-    returns [B, round_up(ncols(+D), pad_to)] in bf16 with zero pad columns (a GEMM-ready K operand)."""
+    returns [B, round_up(ncols(+D), pad_to)] in bf16 with zero pad columns (a GEMM-ready K operand); ones_col=True
+    sets the FIRST pad column to 1.0 instead (the consumer's bias gradient then falls out of its dW GEMM)."""
     _need_cuda(E, table, idx, field_row_offset, dense_vec, out)
     if E is not None:
         _f32c(E, "E")
@@ -184,7 +185,8 @@ def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, 
         raise TypeError("out.dtype must equal out_dtype")
     check(lib.rb_dot_interaction_fwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
                                      B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(out),
-                                     _float_type(out_dtype), int(out_stride), _stream()), "rb_dot_interaction_fwd")
+                                     _lib.RB_BF16_ONES if (ones_col and out_dtype == torch.bfloat16 and out_stride > width)
+                                     else _float_type(out_dtype), int(out_stride), _stream()), "rb_dot_interaction_fwd")
     return out
 
 

@@ -160,9 +160,9 @@ def _ptr_array(ptrs: Sequence[int]):
 
 class _P2PInteractFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, emb, idx, dense_vec, flags, out_dtype, pad_to):
+    def forward(ctx, anchor, emb, idx, dense_vec, flags, out_dtype, pad_to, ones_col=False):
         dense_vec = dense_vec.contiguous()
-        out = emb._interaction_fwd(idx, dense_vec, flags, out_dtype, pad_to)
+        out = emb._interaction_fwd(idx, dense_vec, flags, out_dtype, pad_to, ones_col)
         ctx.emb, ctx.idx, ctx.flags = emb, idx, flags
         ctx.save_for_backward(dense_vec)
         return out
@@ -173,7 +173,7 @@ class _P2PInteractFn(torch.autograd.Function):
         if dOut.stride(-1) != 1:
             dOut = dOut.contiguous()
         d_dense = ctx.emb._interaction_bwd(ctx.idx, dense_vec, ctx.flags, dOut)
-        return None, None, None, d_dense, None, None, None
+        return None, None, None, d_dense, None, None, None, None
 
 
 class P2PShardedEmbedding(nn.Module):
@@ -317,7 +317,7 @@ class P2PShardedEmbedding(nn.Module):
                                                   self._sort_ws.numel(), C.byref(sel), ops._stream()), "rb_sparse_bwd_prepare_collected")
         self._sel = int(sel.value)
 
-    def _interaction_fwd(self, idx, dense_vec, flags, out_dtype, pad_to):
+    def _interaction_fwd(self, idx, dense_vec, flags, out_dtype, pad_to, ones_col=False):
         si, sg, tail = flags
         B, F = idx.shape
         D = self.output_dim
@@ -328,7 +328,9 @@ class P2PShardedEmbedding(nn.Module):
         off = self._row_offset if self.num_tables > 1 else None
         check(lib.rb_dot_interaction_fwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
                                                  ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
-                                                 int(tail), out.data_ptr(), ops._float_type(out_dtype), stride,
+                                                 int(tail), out.data_ptr(),
+                                                 _lib.RB_BF16_ONES if (ones_col and out_dtype == torch.bfloat16 and stride > width)
+                                                 else ops._float_type(out_dtype), stride,
                                                  self._x_saved.data_ptr() if self.save_rows else None, self._shadow_ptrs_dev(),
                                                  ops._stream()), "rb_dot_interaction_fwd_sharded")
         return out
@@ -369,7 +371,7 @@ class P2PShardedEmbedding(nn.Module):
         self._begun = idx
 
     def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
-                 out_dtype=torch.float32, pad_to=1, routed=False) -> torch.Tensor:
+                 out_dtype=torch.float32, pad_to=1, routed=False, ones_col=False) -> torch.Tensor:
         """ctr/model.py:49-55 on the sharded table.  Unless the caller already ran route()/collect_and_sort()
         (`routed=True`, lock-step emulation) the step's routing runs on the side stream (begin_step)."""
         idx = idx.contiguous()
@@ -379,7 +381,8 @@ class P2PShardedEmbedding(nn.Module):
                 self.begin_step(idx)
             self._begun = None
             torch.cuda.current_stream().wait_event(self._routed_ev)
-        return _P2PInteractFn.apply(self._anchor, self, idx, dense_vec.float(), (self_interaction, skip_gather, tail), out_dtype, pad_to)
+        return _P2PInteractFn.apply(self._anchor, self, idx, dense_vec.float(), (self_interaction, skip_gather, tail), out_dtype, pad_to,
+                                    ones_col)
 
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
                       initial_accumulator_value=0.1, alpha_dev=None) -> int:
@@ -462,10 +465,11 @@ class P2PShardedDLRM(nn.Module):
             self.embedding_layer.begin_step(cat_features)      # routing + rendezvous overlap the bottom MLP
         bmlp_output = self.bottom_mlp(int_features)
         bf16 = self.top_mlp.compute_dtype == torch.bfloat16
+        ones = bf16 and width % 8 != 0     # a spare pad column carries 1.0: the first top layer's bias gradient comes with its dW GEMM
         tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
                                                    out_dtype=torch.bfloat16 if bf16 else torch.float32, pad_to=8 if bf16 else 1,
-                                                   routed=routed)
-        return self.top_mlp(tmlp_input).squeeze(1)
+                                                   routed=routed, ones_col=ones)
+        return (self.top_mlp(tmlp_input, ones_col=True) if ones else self.top_mlp(tmlp_input)).squeeze(1)
 
     def _attach_flat_grads(self) -> None:
         """All MLP gradients live in ONE flat buffer (the parameters' .grad are views of it): the replicas' sum is

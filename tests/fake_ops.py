@@ -57,7 +57,7 @@ def _X(E, table, idx, field_row_offset, dense_vec):
 
 
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None, self_interaction=False,
-                        skip_gather=True, tail=False, out=None, out_stride=None, out_dtype=torch.float32, pad_to=1):
+                        skip_gather=True, tail=False, out=None, out_stride=None, out_dtype=torch.float32, pad_to=1, ones_col=False):
     _launches[0] += 1
     X = _X(E, table, idx, field_row_offset, dense_vec)
     res = O.dot_interaction(X, self_interaction, skip_gather, operand_dtype="bf16")
@@ -68,6 +68,8 @@ def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, 
         width = res.shape[1]
         padded = torch.zeros(res.shape[0], (width + pad_to - 1) // pad_to * pad_to, dtype=torch.bfloat16)
         padded[:, :width] = res.to(torch.bfloat16)
+        if ones_col and padded.shape[1] > width:
+            padded[:, width] = 1.0
         return padded
     return res
 

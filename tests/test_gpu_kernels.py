@@ -207,6 +207,10 @@ def test_interaction_bf16_rows_for_the_top_mlp(ops, golden):
     assert out.dtype == torch.bfloat16 and out.shape == (B, stride)
     assert torch.equal(out[:, :width], ref32.to(torch.bfloat16))            # identical arithmetic, one final rounding
     assert (out[:, width:] == 0).all()                                       # GEMM-ready pad columns
+    ones = ops.dot_interaction_fwd(table=table, idx=cat, dense_vec=dv, tail=True, out_dtype=torch.bfloat16, pad_to=8, ones_col=True)
+    assert torch.equal(ones[:, :width], out[:, :width])
+    if stride > width:                                                       # first pad column carries 1.0, the rest stay 0
+        assert (ones[:, width] == 1).all() and (ones[:, width + 1:] == 0).all()
     # backward with the padded bf16 gradient == backward with the same values in fp32
     rng = np.random.default_rng(3)
     dpad = torch.zeros(B, stride, dtype=torch.bfloat16, device="cuda")
