@@ -9,12 +9,9 @@ One optimizer object drives both kinds of variables of a model:
 """
 from __future__ import annotations
 
-from typing import Iterable
-
 import torch
 
 from . import ops
-from .layers import Embedding
 
 
 def _split(model_or_vars):

@@ -24,7 +24,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
