@@ -75,6 +75,31 @@ def main():
         timeit("bwd", lambda i: ops.dot_interaction_bwd(dout, table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True))
     if "gather" in which:
         timeit("gather", lambda i: ops.gather_fwd(table, ring[i % 4], L=F, field_row_offset=off))
+    if "pool" in which:      # BASELINE config 4: masked mean over a behaviour history, L = 100, D = 32, item table of 400k rows
+        Lh, Dh, Vh = 100, 32, 400_000
+        wt = torch.empty(Vh, Dh, device=dev).uniform_(-0.05, 0.05, generator=g)
+        lens = torch.randint(1, Lh + 1, (B, 1), device=dev, generator=g)
+        hist = torch.randint(1, Vh, (B, Lh), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+        hist = torch.where(torch.arange(Lh, device=dev)[None] < lens, hist, torch.zeros_like(hist))     # trailing pads (dien/data_loader.py:44)
+        pout = torch.empty(B, Dh, device=dev)
+        timeit("pool_masked_mean", lambda i: ops.bag_pool_fwd(wt, hist, "masked_mean", out=pout, out_stride=Dh))
+        valid = int((hist != 0).sum())
+        res["pool_masked_mean"]["algorithmic_bytes"] = valid * Dh * 4 + B * Lh * 4 + B * Dh * 4
+        dpool = torch.randn(B, Dh, device=dev, generator=g) * 1e-3
+        cnt = (hist != 0).sum(1).float()
+        mh, vh = torch.zeros_like(wt), torch.zeros_like(wt)
+        hstep = [0]
+
+        def hupd(i):
+            hstep[0] += 1
+            grp = LookupGroup(hist, Lh, GradSource.per_bag([dpool], scale="masked_mean", mask_idx=hist, count=cnt))
+            ops.sparse_bwd_update(wt, mh, vh, [grp], optimizer="adam_lazy", step=hstep[0])
+        timeit("pool_masked_mean_bwd_update", hupd)
+    if "fm" in which:        # DeepFM front end (ctr/model.py:19-23) at D = 16, one shared 1M-row table
+        wf = torch.empty(1_000_000, 16, device=dev).uniform_(-0.05, 0.05, generator=g)
+        catf = torch.randint(0, 1_000_000, (B, F), device=dev, generator=g)
+        timeit("gather_fm_fwd", lambda i: ops.gather_fm_fwd(wf, catf))
+        res["gather_fm_fwd"]["algorithmic_bytes"] = B * F * 16 * 4 * 2 + B * F * 8 + B * 16 * 4 + B * 4
     if "update" in which:
         step = [0]
 
@@ -83,6 +108,9 @@ def main():
             grp = LookupGroup(ring[i % 4], F, GradSource.per_position(dE, F), field_row_offset=off)
             ops.sparse_bwd_update(table, m, v if a.optimizer.startswith("adam") else None, [grp], optimizer=a.optimizer, step=step[0])
         timeit("update", upd)
+    for v_ in res.values():
+        if "algorithmic_bytes" in v_:
+            v_["gbs"] = round(v_["algorithmic_bytes"] / v_["us_median"] / 1e3, 1)
     print(json.dumps(dict(tag=a.tag, tables=T, dist=a.dist, **res)))
 
 

@@ -81,6 +81,41 @@ def test_argument_validation_without_a_gpu(cuda_lib):
     assert L.rb_bucket_by_owner(C.addressof(idx), _lib.RB_I64, 4, 1, None, 0, 0, p, p, p, p, p, 1 << 20, None) == -1
 
 
+def test_argument_validation_of_the_dense_and_peer_memory_entry_points(cuda_lib):
+    """Status codes of the later additions, all decided before any CUDA call."""
+    L = cuda_lib
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    opt = _lib.RbOptParams(_lib.RB_OPT_ADAM_LAZY, 1, 1e-3, 0.9, 0.999, 1e-7, None)
+    # dense step: too many tensors / Adam without state
+    slots = (_lib.RbDenseSlot * 1)()
+    slots[0].param, slots[0].grad, slots[0].n = p, p, 8
+    assert L.rb_dense_opt_step(slots, _lib.RB_MAX_DENSE_TENSORS + 1, C.byref(opt), None) == -1
+    assert L.rb_dense_opt_step(slots, 1, C.byref(opt), None) == -1 and b"Adam" in L.rb_last_error()
+    assert L.rb_dense_opt_step(slots, 0, C.byref(opt), None) == 0
+    # column sum: cols must be a multiple of 8; workspace is checked
+    assert L.rb_colsum(p, _lib.RB_F32, 4, 12, 12, p, p, 1 << 20, None) == -2
+    assert L.rb_colsum_workspace_bytes(65536, 512) >= 512 * 4
+    assert L.rb_colsum(p, _lib.RB_F32, 4, 16, 16, p, p, 8, None) == -4
+    # loss head
+    assert L.rb_bce_clipped(None, p, 0, 8, p, None, p, 1 << 20, None) == -1
+    assert L.rb_bce_clipped(p, p, 7, 8, p, None, p, 1 << 20, None) == -1
+    # interaction: RB_BF16_ONES needs a pad column
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 16, 0, 1, 0, p, _lib.RB_BF16_ONES, 729, None) == -1
+    # peer-memory path: world size and null checks
+    ptrs = (C.c_void_p * 9)(*([p] * 9))
+    nv = (C.c_int32 * 1)()
+    assert L.rb_p2p_collect_keys(9, 0, 100, ptrs, ptrs, ptrs, 50, 200, p, 1 << 30, 16, nv, None, None) == -1
+    assert L.rb_p2p_collect_keys(2, 5, 100, ptrs, ptrs, ptrs, 50, 200, p, 1 << 30, 16, nv, None, None) == -1
+    assert L.rb_p2p_collect_keys(2, 0, 100, ptrs, ptrs, ptrs, 50, 200, p, 16, 16, nv, None, None) == -4
+    sel = C.c_int32(0)
+    assert L.rb_sparse_bwd_prepare_collected(50, 16, 200, p, 16, C.byref(sel), None) == -4
+    assert L.rb_sparse_bwd_apply_p2p(p, p, p, 50, 16, 9, 100, 4, ptrs, 200, nv, C.byref(opt), p, 1 << 30, 0, None, None) == -1
+    assert L.rb_sparse_bwd_apply_p2p(p, p, p, 50, 16, 2, 100, 3, ptrs, 200, nv, C.byref(opt), p, 1 << 30, 0, None, None) == -1   # n_local % L
+    assert L.rb_dot_interaction_fwd_sharded(None, 2, 100, p, 1, None, None, 1, 26, 16, 0, 1, 0, p, 0, 676, None, None, None) == -1
+    assert L.rb_ipc_open(None, None) == -1 and L.rb_shared_alloc(0, None, None) == -1
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     from recommender_b200 import ops
