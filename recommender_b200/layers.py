@@ -121,6 +121,7 @@ class _InteractFn(torch.autograd.Function):
                                               dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail)
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
+        emb._grad_ready = torch.cuda.current_stream().record_event()    # dE is complete here: the row update may start
         return None, None, None, d_dense, None, None, None, None, None, None
 
 
@@ -178,6 +179,12 @@ class Embedding(nn.Module):
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._sorted = None          # (idx tensor, L, selector, done event) of the sort in flight
         self._sort_ws: Optional[torch.Tensor] = None
+        # The row update only needs the sorted pairs and dE: it is launched on the side stream as soon as the
+        # interaction backward has written dE, so it overlaps the rest of the backward (bottom MLP) and the dense
+        # optimizer step; join() brings the streams back together.
+        self._grad_ready: Optional[torch.cuda.Event] = None
+        self._apply_done: Optional[torch.cuda.Event] = None
+        self._inflight = None
 
     # -- helpers used by the autograd functions
     def row_offset_for(self, L: int):
@@ -252,6 +259,13 @@ class Embedding(nn.Module):
         return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to,
                                  ones_col)
 
+    def join(self) -> None:
+        """Wait (on the current stream) for a row update launched on the side stream."""
+        if self._apply_done is not None:
+            torch.cuda.current_stream().wait_event(self._apply_done)
+            self._apply_done = None
+        self._inflight = None
+
     # -- optimizer side (called by optimizers.*.apply_gradients)
     def apply_pending(self, kind: str, step: int, lr: float, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
                       initial_accumulator_value=0.1, alpha_dev=None) -> int:
@@ -261,13 +275,16 @@ class Embedding(nn.Module):
                 raise NotImplementedError("adam_tf_dense with no lookup in the step")
             return 0
         st = self.opt_state
+        fresh_state = False           # state tensors created just now on the current stream: the side stream must see them
         if kind in ("adam_lazy", "adam_tf_dense"):
             if "m" not in st:
                 st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
+                fresh_state = True
             s0, s1 = st["m"], st["v"]
         elif kind == "adagrad":
             if "acc" not in st:
                 st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
+                fresh_state = True
             s0, s1 = st["acc"], None
         elif kind == "sgd":
             s0 = s1 = None
@@ -278,8 +295,21 @@ class Embedding(nn.Module):
         n = sum(g.n for g in groups)
         if sorted_ is not None:
             torch.cuda.current_stream().wait_event(sorted_[3])     # also orders later reuse of the sort workspace
+        grad_ready, self._grad_ready = self._grad_ready, None
         if (sorted_ is not None and sorted_[0] is not None and len(groups) == 1 and groups[0].L == sorted_[1]
                 and groups[0].idx.data_ptr() == sorted_[0].data_ptr() and groups[0].n == sorted_[0].numel()):
+            if grad_ready is not None and self._side_stream is not None:
+                side = self._side_stream
+                if fresh_state:
+                    side.wait_stream(torch.cuda.current_stream())
+                else:
+                    side.wait_event(grad_ready)
+                with torch.cuda.stream(side):
+                    ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, sorted_[2], optimizer=kind, step=step,
+                                         lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
+                    self._apply_done = side.record_event()
+                self._inflight = groups          # keeps dE alive until join(): the allocator must not hand it out meanwhile
+                return n
             ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, sorted_[2], optimizer=kind, step=step, lr=lr,
                                  beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
         else:

@@ -60,10 +60,11 @@ class _Optimizer:
         if hasattr(model_or_vars, "reduce_dense_grads"):
             model_or_vars.reduce_dense_grads()      # data-parallel replicas (sharded.ShardedDLRM, p2p.P2PShardedDLRM)
         step = self.iterations if self._prepared else self.iterations + 1
-        overlap = hasattr(model_or_vars, "wait_dense_grads")
-        if overlap:      # the replicas' all-reduce runs on a side stream: do the sparse tables first, then join it
-            for e in embs:
-                e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+        # sparse tables first: their row updates run on side streams (layers.Embedding, p2p.P2PShardedEmbedding) and overlap
+        # the replicas' all-reduce and the dense step below; join() brings the streams back together
+        for e in embs:
+            e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+        if hasattr(model_or_vars, "wait_dense_grads"):
             model_or_vars.wait_dense_grads()
         params = [p for p in dense if p.grad is not None]
         if params:
@@ -73,9 +74,9 @@ class _Optimizer:
             else:
                 for p in params:
                     p.grad = None
-        if not overlap:
-            for e in embs:
-                e.apply_pending(self.sparse_kind, step, **self._sparse_kwargs())
+        for e in embs:
+            if hasattr(e, "join"):
+                e.join()
         self.iterations = step
         if not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
             self._prepared = False      # a captured body is replayed: every replay is preceded by prepare_step()

@@ -226,6 +226,8 @@ class P2PShardedEmbedding(nn.Module):
         self._shard_ptr_dev: Optional[torch.Tensor] = None
         self._routed_by_caller = False
         self._begun = None
+        self._grad_ready = None
+        self._apply_done = None
 
     # ---- lazily built per-shape step buffers -----------------------------------------------------------------
     def _resolve(self, v):
@@ -348,6 +350,7 @@ class P2PShardedEmbedding(nn.Module):
                                                  self._x_saved.data_ptr() if self.save_rows else None, ops._stream()),
               "rb_dot_interaction_bwd_sharded")
         self._pending = True
+        self._grad_ready = torch.cuda.current_stream().record_event()
         return d_dense
 
     def begin_step(self, idx: torch.Tensor) -> None:
@@ -391,28 +394,51 @@ class P2PShardedEmbedding(nn.Module):
             return 0
         self._pending = False
         st = self.opt_state
+        fresh_state = False
         if kind == "adam_lazy":
             if "m" not in st:
                 st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
+                fresh_state = True
             s0, s1 = st["m"], st["v"]
         elif kind == "adagrad":
             if "acc" not in st:
                 st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
+                fresh_state = True
             s0, s1 = st["acc"], None
         elif kind == "sgd":
             s0 = s1 = None
         else:
             raise ValueError(f"the peer-memory path supports adam_lazy / adagrad / sgd, not {kind}")
-        if not self._routed_by_caller:
-            torch.cuda.current_stream().wait_event(self._sorted_ev)
-            self.link.barrier(1)                 # every rank's backward has written its dE and stopped reading the shards
         opt = ops._opt_params(kind, step, lr, beta_1, beta_2, epsilon, alpha_dev)
         _, F = self._shape
-        check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
-                                          self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
-                                          self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
-                                          self._sel, ops._ptr(self._shadow_full), ops._stream()), "rb_sparse_bwd_apply_p2p")
+
+        def launch():
+            check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
+                                              self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
+                                              self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
+                                              self._sel, ops._ptr(self._shadow_full), ops._stream()), "rb_sparse_bwd_apply_p2p")
+
+        if self._routed_by_caller:
+            launch()
+            return self.n_local
+        # on the side stream (which already holds this step's sort): start as soon as this rank's dE is written, meet the
+        # other ranks, update — overlapping the rest of the backward, the dense all-reduce and the dense step
+        side = self._side
+        if self._grad_ready is not None and not fresh_state:
+            side.wait_event(self._grad_ready)
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+        self._grad_ready = None
+        with torch.cuda.stream(side):
+            self.link.barrier(1)                 # every rank's backward has written its dE and stopped reading the shards
+            launch()
+            self._apply_done = side.record_event()
         return self.n_local
+
+    def join(self) -> None:
+        if self._apply_done is not None:
+            torch.cuda.current_stream().wait_event(self._apply_done)
+            self._apply_done = None
 
     def check_overflow(self) -> None:
         if int(self.overflow.item()) != 0:
