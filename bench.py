@@ -330,6 +330,8 @@ def run_b200(args):
         loss = train_step(resident[i % args.ring])
     float(loss.item())
     ops.check_oob(dev)
+    if hasattr(model.embedding_layer, "check_overflow"):
+        model.embedding_layer.check_overflow()       # static per-owner capacity of the peer-memory path
 
     # ---- eager pass: every C-ABI call bracketed by CUDA events on its launching stream (kernel table, roofline) ----
     k_eager = min(args.steps, 10)
@@ -374,6 +376,8 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
     final_loss = float(loss.item())
+    if hasattr(model.embedding_layer, "check_overflow"):
+        model.embedding_layer.check_overflow()
 
     # ---- e2e: pinned host buffers -> H2D copies, loss read back, all inside the timed region ---------------
     e2e = None

@@ -153,22 +153,35 @@ class Embedding(nn.Module):
 
     `embeddings` f32[input_dim, output_dim] ~ U(-0.05, 0.05) (the Keras default initialiser).
     `num_tables` > 1 stores that many input_dim-row tables back to back and routes position f of
-    a [B, num_tables] index array to table f (the T = 26 form of BASELINE config 2).
+    a [B, num_tables] index array to table f (the T = 26 form of BASELINE config 2).  `table_rows`
+    gives every table its own row count instead (BASELINE config 3: capped Criteo-Terabyte
+    cardinalities from 3 to 40M rows); `cap_ids(ids)` folds raw ids into each table's range.
     `hash_mod` folds ids with uint64 mod before the lookup (capped tables).
     """
 
     def __init__(self, input_dim: int, output_dim: int, mask_zero: bool = False, *, num_tables: int = 1,
-                 hash_mod: int = 0, device=None, generator: Optional[torch.Generator] = None):
+                 hash_mod: int = 0, table_rows: Optional[Sequence[int]] = None, device=None,
+                 generator: Optional[torch.Generator] = None):
         super().__init__()
         dev = _default_device(device)
         self.input_dim, self.output_dim, self.mask_zero = int(input_dim), int(output_dim), bool(mask_zero)
         self.num_tables, self.hash_mod = int(num_tables), int(hash_mod)
-        rows = self.input_dim * self.num_tables
+        self.table_rows = None if table_rows is None else [int(r) for r in table_rows]
+        if self.table_rows is not None:
+            if min(self.table_rows) < 1:
+                raise ValueError("every table needs at least one row")
+            self.num_tables = len(self.table_rows)
+        rows = self.input_dim * self.num_tables if self.table_rows is None else sum(self.table_rows)
         w = torch.empty(rows, self.output_dim, dtype=torch.float32, device=dev)
         w.uniform_(-0.05, 0.05, generator=generator)
         self.register_buffer("embeddings", w)
-        self.register_buffer("_row_offset", torch.arange(self.num_tables, dtype=torch.int64, device=dev) * self.input_dim
-                             if self.num_tables > 1 else None, persistent=False)
+        if self.table_rows is not None:
+            starts = torch.tensor([0] + self.table_rows[:-1], dtype=torch.int64).cumsum(0)
+            self.register_buffer("_row_offset", starts.to(dev), persistent=False)
+            self.register_buffer("_table_rows_dev", torch.tensor(self.table_rows, dtype=torch.int64, device=dev), persistent=False)
+        else:
+            self.register_buffer("_row_offset", torch.arange(self.num_tables, dtype=torch.int64, device=dev) * self.input_dim
+                                 if self.num_tables > 1 else None, persistent=False)
         # makes autograd call the lookups' backward although the table itself is not a leaf
         self._anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
         self.pending: List[LookupGroup] = []
@@ -187,8 +200,15 @@ class Embedding(nn.Module):
         self._inflight = None
 
     # -- helpers used by the autograd functions
+    def cap_ids(self, ids: torch.Tensor) -> torch.Tensor:
+        """row-in-table = id mod rows(table) for non-negative raw ids [B, num_tables] (the MLPerf-DLRM capping of the
+        Criteo-Terabyte cardinalities)."""
+        if self.table_rows is None:
+            return ids % self.input_dim
+        return ids % self._table_rows_dev[None].to(ids.dtype)
+
     def row_offset_for(self, L: int):
-        if self.num_tables == 1:
+        if self.num_tables == 1 and self.table_rows is None:
             return None
         if L != self.num_tables:
             raise ValueError(f"a {self.num_tables}-table embedding takes [B, {self.num_tables}] indices, got last dim {L}")

@@ -182,7 +182,8 @@ class P2PShardedEmbedding(nn.Module):
     `apply_pending(...)` (driven by optimizers.*), `load_full_table` / `full_row_ids` (tests)."""
 
     def __init__(self, input_dim: int, output_dim: int, *, num_tables: int = 1, link: PeerLink, device=None,
-                 generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25, bf16_shadow: bool = True):
+                 generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25, bf16_shadow: bool = True,
+                 table_rows: Optional[Sequence[int]] = None):
         super().__init__()
         self.link = link
         self.world, self.rank = link.world, link.rank
@@ -198,11 +199,27 @@ class P2PShardedEmbedding(nn.Module):
         # Table t starts at global row t * pitch.  pitch is coprime with G so that the SAME id of different tables
         # (the OOV / padding id 0 is the hottest row of every table, ctr/tfrecord_io.py:61-64) lands on different
         # ranks instead of piling up on rank 0; costs at most a few unused rows per table.
-        self.pitch = self.input_dim
-        if self.num_tables > 1:
-            while math.gcd(self.pitch, G) != 1:
-                self.pitch += 1
-        total = self.pitch * self.num_tables
+        self.table_rows = None if table_rows is None else [int(r) for r in table_rows]
+        if self.table_rows is not None:
+            # per-table row counts (BASELINE config 3): table t starts at the first row >= the previous table's end whose
+            # owner is rank t mod G — the same staggering of the tables' hot id 0
+            self.num_tables = len(self.table_rows)
+            starts, end = [], 0
+            for t, r in enumerate(self.table_rows):
+                s0 = end + ((t % G) - end % G) % G
+                starts.append(s0)
+                end = s0 + r
+            self._starts = starts
+            self.pitch = None
+            total = end
+        else:
+            self.pitch = self.input_dim
+            if self.num_tables > 1:
+                while math.gcd(self.pitch, G) != 1:
+                    self.pitch += 1
+            self._starts = [t * self.pitch for t in range(self.num_tables)]
+            self.table_rows = [self.input_dim] * self.num_tables
+            total = self.pitch * self.num_tables
         self.total_rows = total
         self.local_rows = max((total - self.rank + G - 1) // G, 1)       # rows r with r mod G == rank
         shard_rows = max((total + G - 1) // G, 1)                        # same shape on every rank (rank 0's count)
@@ -216,8 +233,10 @@ class P2PShardedEmbedding(nn.Module):
         if self.use_shadow:
             self._shadow_full, self._shadow_ptrs = link.alloc("shadow", (shard_rows, self.output_dim), torch.bfloat16)
             self.refresh_shadow()
-        self._row_offset = (torch.arange(self.num_tables, dtype=torch.int64, device=self.device) * self.pitch
-                            if self.num_tables > 1 else None)
+        self._row_offset = (torch.tensor(self._starts, dtype=torch.int64, device=self.device) if self.num_tables > 1 else None)
+        self._starts_dev = torch.tensor(self._starts, dtype=torch.int64, device=self.device)
+        self._rows_dev = torch.tensor(self.table_rows, dtype=torch.int64, device=self.device)
+        self._unsharded_starts = torch.tensor([0] + self.table_rows[:-1], dtype=torch.int64, device=self.device).cumsum(0)
         self._anchor = torch.zeros((), dtype=torch.float32, device=self.device, requires_grad=True)
         self.opt_state: Dict[str, torch.Tensor] = {}
         self._shape = None           # (B_local, F) the step buffers were built for
@@ -276,13 +295,18 @@ class P2PShardedEmbedding(nn.Module):
     def full_row_ids(self) -> torch.Tensor:
         """For every local shard row: its row in the UNSHARDED [input_dim * num_tables, D] table, or -1 for the
         pad rows the table pitch introduces."""
-        g = torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank   # global (pitched) row
-        t, i = g // self.pitch, g % self.pitch
-        ok = (i < self.input_dim) & (t < self.num_tables)
-        return torch.where(ok, t * self.input_dim + i, torch.full_like(g, -1))
+        g = torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank   # global (staggered) row
+        t = torch.searchsorted(self._starts_dev, g, right=True) - 1
+        i = g - self._starts_dev[t]
+        ok = i < self._rows_dev[t]
+        return torch.where(ok, self._unsharded_starts[t] + i, torch.full_like(g, -1))
+
+    def cap_ids(self, ids: torch.Tensor) -> torch.Tensor:
+        """row-in-table = id mod rows(table) for non-negative raw ids [B, num_tables]."""
+        return ids % self._rows_dev[None].to(ids.dtype)
 
     def load_full_table(self, full: torch.Tensor) -> None:
-        """Adopt this rank's rows of an unsharded [input_dim * num_tables, D] table."""
+        """Adopt this rank's rows of an unsharded [sum(table_rows), D] table."""
         full = torch.as_tensor(full, dtype=torch.float32).to(self.device)
         ids = self.full_row_ids()
         ok = ids >= 0

@@ -577,6 +577,59 @@ def test_peer_memory_sharded_step_equals_unsharded(ops, G, T, shadow):
     if T > 1:   # the table pitch spreads the hot id 0 of the 26 tables over the ranks
         owners = {int((t * embs[0].pitch) % G) for t in range(T)}
         assert len(owners) == min(G, T)
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_peer_memory_sharding_of_unequal_tables(ops, G):
+    """BASELINE config 3 in miniature: 26 tables with capped Criteo-Terabyte-like cardinalities from 3 rows to a few
+    thousand, raw ids folded per table (cap_ids), row-wise sharded over G emulated ranks — against the unsharded
+    Embedding(table_rows=...) on the same ids."""
+    from recommender_b200.layers import Embedding
+    from recommender_b200.ops import GradSource, LookupGroup
+    from recommender_b200.p2p import LocalPeerLink, P2PShardedEmbedding
+    rng = np.random.default_rng(G)
+    cards = [3989, 391, 173, 75, 203, 3, 72, 16, 63, 3854, 2954, 404, 10, 23, 120, 155, 4, 976, 14, 3998, 2565, 3967, 586, 130, 108, 36]
+    D, B, F = 32, 128, 26
+    ref = Embedding(0, D, table_rows=cards, device="cuda")
+    W = ref.embeddings.clone()
+    registry = {}
+    embs = [P2PShardedEmbedding(0, D, link=LocalPeerLink(G, r, registry), device="cuda", capacity_factor=float(G), table_rows=cards)
+            for r in range(G)]
+    for e in embs:
+        e.load_full_table(W)
+        assert int((e.full_row_ids() >= 0).sum()) > 0
+    assert sum(int((e.full_row_ids() >= 0).sum()) for e in embs) == sum(cards)
+    raw = [cu(rng.integers(0, 2 ** 40, size=(B, F)).astype(np.int64)) for _ in range(G)]
+    idx = [ref.cap_ids(r_) for r_ in raw]
+    for r in range(G):
+        assert torch.equal(embs[r].cap_ids(raw[r]), idx[r])
+    dense = [cu(rng.normal(0, 0.1, size=(B, D)).astype(np.float32)) for _ in range(G)]
+    dOut = [cu(rng.normal(0, 1e-2, size=(B, 27 * 27 + D)).astype(np.float32)) for _ in range(G)]
+    off = ref.row_offset_for(F)
+    for r in range(G):
+        embs[r].route(idx[r])
+    for r in range(G):
+        embs[r].collect_and_sort()
+    groups = []
+    for r in range(G):
+        out = embs[r]._interaction_fwd(idx[r], dense[r], (False, True, True), torch.float32, 1)
+        assert torch.equal(out, ops.dot_interaction_fwd(table=W, idx=idx[r], field_row_offset=off, dense_vec=dense[r], tail=True))
+        embs[r]._interaction_bwd(idx[r], dense[r], (False, True, True), dOut[r])
+        dE_ref, _ = ops.dot_interaction_bwd(dOut[r], table=W, idx=idx[r], field_row_offset=off, dense_vec=dense[r], tail=True)
+        assert torch.equal(embs[r]._dE.view(B, F, D), dE_ref)
+        groups.append((idx[r], dE_ref))
+    for r in range(G):
+        embs[r]._routed_by_caller = True
+        embs[r].apply_pending("adam_lazy", 1, 1e-3)
+        embs[r].check_overflow()
+    rows = torch.cat([(i_ + off[None]).reshape(-1) for i_, _ in groups])
+    dE_all = torch.cat([d_.reshape(-1, D) for _, d_ in groups])
+    Wd, m, v = W.clone(), torch.zeros_like(W), torch.zeros_like(W)
+    ops.sparse_bwd_update(Wd, m, v, [LookupGroup(rows, 1, GradSource.per_position(dE_all, 1))], optimizer="adam_lazy", step=1)
+    got = torch.zeros_like(Wd)
+    for e in embs:
+        e.scatter_into_full(got)
+    np.testing.assert_allclose(got.cpu().numpy(), Wd.cpu().numpy(), rtol=0, atol=2e-6)   # 3-row tables: runs of ~B*G/3 duplicates
     assert int(sum(int(e._n_valid.item()) for e in embs)) == G * B * F
 
 
