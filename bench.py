@@ -38,6 +38,9 @@ METRIC = "train samples/s, DLRM Criteo-shape"
 UNIT = "samples/s"
 BOTTOM, TOP = [512, 256, 64], [512, 256, 1]
 F_CAT, F_INT = 26, 13
+# MLPerf-DLRM capping (row = id mod 40M) of the Criteo-Terabyte cardinalities: 187.8M rows in 26 tables
+CRITEO_TB_ROWS = [39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546, 403346, 10, 2208, 11938, 155, 4, 976, 14,
+                  39979771, 25641295, 39664984, 585935, 12972, 108, 36]
 
 
 def parse_args():
@@ -58,6 +61,8 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--criteo-tb", action="store_true",
+                    help="BASELINE config 3 (N > 1 only): 26 tables with the capped Criteo-Terabyte cardinalities (187.8M rows), row-wise sharded")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--cpu-sample-batch", type=int, default=8192)
     ap.add_argument("--ref-adam", default="tf_dense", choices=["tf_dense", "lazy"],
@@ -69,11 +74,15 @@ def parse_args():
 # synthetic Criteo-shaped data: seed 4 (+rank), uniform or Zipf(1.05)+2% id 0
 # ---------------------------------------------------------------------------------------------------
 
-def synth_batches(n, B, V, dist, seed, pin):
+def synth_batches(n, B, V, dist, seed, pin, table_rows=None):
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
-        if dist == "uniform":
+        if table_rows is not None:       # uniform inside every table's own cardinality
+            cards = torch.tensor(table_rows, dtype=torch.float64)
+            cat = (torch.rand(B, F_CAT, generator=g, dtype=torch.float64) * cards[None]).to(torch.int64)
+            cat = torch.minimum(cat, (cards[None] - 1).to(torch.int64))
+        elif dist == "uniform":
             cat = torch.randint(0, V, (B, F_CAT), generator=g, dtype=torch.int64)
         else:
             u = torch.rand(B, F_CAT, generator=g, dtype=torch.float64).clamp_(min=1e-12)
@@ -185,8 +194,13 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return dict(workload=f"DLRM Criteo-shape (BASELINE config 2): emb dim {args.emb_dim}, batch {args.batch} per GPU, "
-                         f"{args.tables} table(s) x {args.rows_per_table} rows, dot interaction, Adam",
+    if getattr(args, "criteo_tb", False):
+        what = (f"DLRM Criteo-Terabyte-shape (BASELINE config 3): emb dim {args.emb_dim}, batch {args.batch} per GPU, 26 tables with the capped "
+                f"Criteo-Terabyte cardinalities ({sum(CRITEO_TB_ROWS)} rows, 3 .. 39979771 per table), dot interaction, Adam")
+    else:
+        what = (f"DLRM Criteo-shape (BASELINE config 2): emb dim {args.emb_dim}, batch {args.batch} per GPU, "
+                f"{args.tables} table(s) x {args.rows_per_table} rows, dot interaction, Adam")
+    return dict(workload=what,
                 global_batch=args.batch * world, tables=args.tables, rows_per_table=args.rows_per_table, emb_dim=args.emb_dim,
                 bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
                 sparse_optimizer="adam_lazy",
@@ -289,14 +303,17 @@ def run_b200(args):
         model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
     elif peer_memory_usable(args, dev):
         from recommender_b200.p2p import P2PShardedDLRM
-        model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
+        model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
+                               table_rows=CRITEO_TB_ROWS if args.criteo_tb else None, capacity_factor=2.0 if args.criteo_tb else 1.25)
     else:
         from recommender_b200.sharded import ShardedDLRM
         model = ShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
                             sharding=args.sharding)
     opt = Adam()
 
-    host = synth_batches(args.ring, B, V, args.dist, seed=4 + rank, pin=True)
+    if args.criteo_tb and not (world > 1 and args.exchange == "p2p"):
+        raise SystemExit("--criteo-tb needs the peer-memory sharded path (N > 1)")
+    host = synth_batches(args.ring, B, V, args.dist, seed=4 + rank, pin=True, table_rows=CRITEO_TB_ROWS if args.criteo_tb else None)
     resident = [tuple(t.to(dev) for t in b) for b in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 

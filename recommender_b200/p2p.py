@@ -476,7 +476,7 @@ class P2PShardedDLRM(nn.Module):
     def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
                  num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, group=None, link: Optional[PeerLink] = None, device=None,
                  compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
-                 capacity_factor: float = 1.25, bf16_shadow: bool = True):
+                 capacity_factor: float = 1.25, bf16_shadow: bool = True, table_rows: Optional[Sequence[int]] = None):
         super().__init__()
         if bottom_mlp_units[-1] != embedding_size:
             raise ValueError("bottom_mlp_units[-1] must equal embedding_size")       # ctr/model.py:52,55
@@ -485,7 +485,8 @@ class P2PShardedDLRM(nn.Module):
         self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator)
         self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)
         self.embedding_layer = P2PShardedEmbedding(vocab_size, embedding_size, num_tables=num_tables, link=self.link, device=device,
-                                                   generator=generator, capacity_factor=capacity_factor, bf16_shadow=bf16_shadow)
+                                                   generator=generator, capacity_factor=capacity_factor, bf16_shadow=bf16_shadow,
+                                                   table_rows=table_rows)
         self.num_cat_fea, self.num_int_fea, self.embedding_size = num_cat_fea, num_int_fea, embedding_size
         self._synced = False
         self._flat = None
