@@ -13,7 +13,33 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import ctr_oracle as O  # noqa: E402  (test infrastructure: initial weights only)
+
+
+def init_params(seed, bottom, top, D, rows, num_int=13, num_cat=26):
+    """Keras-default initial weights (table U(-0.05, 0.05), Dense Glorot-uniform, zero bias) from one seeded generator,
+    identical on every rank."""
+    rng = np.random.default_rng(seed)
+
+    def mlp(in_dim, units):
+        layers = []
+        for u in units:
+            lim = np.sqrt(6.0 / (in_dim + u))
+            layers.append((rng.uniform(-lim, lim, size=(in_dim, u)).astype(np.float32), np.zeros(u, np.float32)))
+            in_dim = u
+        return layers
+
+    return dict(table=rng.uniform(-0.05, 0.05, size=(rows, D)).astype(np.float32), bottom=mlp(num_int, bottom),
+                top=mlp((num_cat + 1) ** 2 + D, top))
+
+
+def synth_batch(B, V, seed, num_cat=26, num_int=13):
+    """Zipf-like ids with 2 % forced id 0 (hot OOV row), log1p dense features, ~25 % positives."""
+    rng = np.random.default_rng(seed)
+    cat = (rng.pareto(1.05, size=(B, num_cat)) * 3).astype(np.int64) % V
+    cat[rng.random((B, num_cat)) < 0.02] = 0
+    dense = np.log1p(rng.integers(0, 1000, size=(B, num_int))).astype(np.float32)
+    label = (rng.random(B) < 0.25).astype(np.int64)
+    return cat, dense, label
 
 
 def main():
@@ -25,13 +51,13 @@ def main():
     from recommender_b200.optimizers import Adam
     from recommender_b200.p2p import P2PShardedDLRM
     V, D, B, T, steps = 5000, 32, 512, 26, 3
-    params = O.init_dlrm(4, [64, D], [64, 1], D, V * T)
+    params = init_params(4, [64, D], [64, 1], D, V * T)
     model = P2PShardedDLRM([64, D], [64, 1], D, V, 26, 13, num_tables=T, device=dev)
     model.embedding_layer.load_full_table(torch.tensor(params["table"]))
     model.bottom_mlp.load_arrays(params["bottom"], dev)
     model.top_mlp.load_arrays(params["top"], dev)
     opt = Adam()
-    batches = [[O.synth_batch(B, V, seed=100 * s + r, dist="zipf") for r in range(world)] for s in range(steps)]
+    batches = [[synth_batch(B, V, seed=100 * s + r) for r in range(world)] for s in range(steps)]
     for s in range(steps):
         cat, dense_x, label = (torch.tensor(a, device=dev) for a in batches[s][rank])
         loss = bce_clipped(model({"cat_features": cat, "int_features": dense_x}), label)
