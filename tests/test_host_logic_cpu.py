@@ -120,3 +120,27 @@ def test_mlp_bf16_path_forward_backward_close_to_fp32():
     xp[:, :13] = torch.tensor(x)
     y2 = mlp(xp)
     np.testing.assert_array_equal(y2.detach().numpy(), y.detach().numpy())
+
+
+def test_prepare_step_advances_the_counter_exactly_once():
+    """graph.GraphedTrainStep calls Adam.prepare_step() before every replay and apply_gradients() inside the captured
+    body: together they must advance `iterations` by one, and the dense update must use that step's alpha_t."""
+    import torch
+    from recommender_b200.optimizers import Adam
+    rng = np.random.default_rng(0)
+    w0 = rng.normal(size=(4, 3)).astype(np.float32)
+    g = rng.normal(size=(4, 3)).astype(np.float32)
+    a, b = torch.nn.Parameter(torch.tensor(w0)), torch.nn.Parameter(torch.tensor(w0))
+    opt_a, opt_b = Adam(), Adam()
+    for _ in range(3):
+        a.grad = torch.tensor(g)
+        opt_a.apply_gradients([a])                     # plain: the call advances the counter itself
+        b.grad = torch.tensor(g)
+        opt_b.prepare_step()                           # graph style: host half first ...
+        opt_b.apply_gradients([b])                     # ... then the (captured) device half
+    assert opt_a.iterations == opt_b.iterations == 3
+    assert torch.equal(a.detach(), b.detach())
+    ref, m, v = w0.copy(), np.zeros_like(w0), np.zeros_like(w0)
+    for t in (1, 2, 3):
+        O.adam_dense_param(ref, m, v, g, t)
+    np.testing.assert_allclose(a.detach().numpy(), ref, rtol=1e-6, atol=1e-7)
