@@ -271,8 +271,15 @@ struct DedupSink {  // writes the deduplicated IndexedSlices (rows ascending)
 };
 
 // ---- step 1: keys ------------------------------------------------------------------------------------
+// drop_mask != null (masked-mean pooling, dien/layers.py:13): a masked position carries an exactly-zero gradient row.
+// TF still lists it in the IndexedSlices, so its row counts as touched — but one zero pair per row says that as well as
+// fifty.  A masked position whose predecessor in the same bag is masked too and maps to the same row gets `invalid_key`,
+// sorts behind every real pair and is cut off by the device-side pair count; the first pad of each run stays.  The sums
+// are unchanged bit for bit (x + 0 == x), every optimizer sees the same touched rows, and the trailing pads of a
+// behaviour history (dien/data_loader.py:44) no longer form one run of B*L/2 pairs on row 0.
 __global__ void make_keys_kernel(IndexMap m, int64_t n, int64_t start, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals, int* __restrict__ oob_flag) {
+                                 uint32_t* __restrict__ vals, int* __restrict__ oob_flag, const void* __restrict__ drop_mask,
+                                 uint32_t invalid_key) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= n) return;
   int64_t row = map_index(m, p);
@@ -280,8 +287,26 @@ __global__ void make_keys_kernel(IndexMap m, int64_t n, int64_t start, uint32_t*
     if (oob_flag != nullptr) *oob_flag = 1;
     row = 0;
   }
-  keys[start + p] = static_cast<uint32_t>(row);
+  uint32_t key = static_cast<uint32_t>(row);
+  if (drop_mask != nullptr && (p % m.L) != 0 && load_raw_index(drop_mask, m.is64, p) == 0 &&
+      load_raw_index(drop_mask, m.is64, p - 1) == 0) {
+    int64_t prev = map_index(m, p - 1);
+    if (prev < 0) prev = 0;
+    if (prev == row) key = invalid_key;
+  }
+  keys[start + p] = key;
   vals[start + p] = static_cast<uint32_t>(start + p);  // global position over the concatenated groups
+}
+
+// number of real pairs = first sorted position holding invalid_key
+__global__ void count_valid_kernel(const uint32_t* __restrict__ keys, int n, uint32_t invalid_key, int* __restrict__ n_valid) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    if (keys[mid] < invalid_key) lo = mid + 1;
+    else hi = mid;
+  }
+  *n_valid = lo;
 }
 
 __global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ flags) {
@@ -574,7 +599,7 @@ static WsLayout ws_layout(int64_t n, int D, int64_t rows) {
   w.long_count = take(256);
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, static_cast<int>(n), 0, key_bits(rows));
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, static_cast<int>(n), 0, key_bits(rows + 1));
   cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
                                 static_cast<int>(n));
   w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
@@ -669,7 +694,9 @@ static int check_common(int64_t rows, int D, int64_t n, RowGeom* geo) {
 // Phase 1 (depends on the ids only): writes and stably sorts the (row, position) pairs of all groups.
 // *sel_out = which half of the double buffers holds the sorted pairs.
 static int sort_groups(const rb_lookup_group* groups, int num_groups, int64_t rows, int64_t n, unsigned char* ws,
-                       const WsLayout& lay, int* oob_flag, cudaStream_t st, int* sel_out) {
+                       const WsLayout& lay, int* oob_flag, cudaStream_t st, int* sel_out, bool drop_masked = false,
+                       bool* dropped_out = nullptr) {
+  bool dropped = false;
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + lay.keys_a);
   uint32_t* kb = reinterpret_cast<uint32_t*>(ws + lay.keys_b);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + lay.vals_a);
@@ -681,15 +708,28 @@ static int sort_groups(const rb_lookup_group* groups, int num_groups, int64_t ro
     RB_CHECK_ARG(g.n >= 0 && g.L > 0 && (g.n == 0 || g.idx != nullptr), RB_ERR_ARG, "group %d: bad n/L/idx", k);
     if (g.n > 0) {
       IndexMap m = make_index_map(g.idx, g.idx_type, g.field_row_offset, g.hash_mod, rows, g.L);
-      make_keys_kernel<<<grid_for(g.n, 256), 256, 0, st>>>(m, g.n, start, ka, va, oob_flag);
+      const void* mask = nullptr;
+      if (drop_masked && g.grad.scale_mode == RB_SCALE_MASKED_MEAN && rows < 0xFFFFFFFFll) {
+        mask = g.grad.mask_idx != nullptr ? g.grad.mask_idx : g.idx;
+        dropped = true;
+      }
+      make_keys_kernel<<<grid_for(g.n, 256), 256, 0, st>>>(m, g.n, start, ka, va, oob_flag, mask, static_cast<uint32_t>(rows));
       RB_LAUNCH_CHECK("make_keys_kernel");
     }
     start += g.n;
   }
   cub::DoubleBuffer<uint32_t> dk(ka, kb), dv(va, vb);
   size_t temp = lay.cub_bytes;
-  RB_CUDA(cub::DeviceRadixSort::SortPairs(ws + lay.cub_temp, temp, dk, dv, static_cast<int>(n), 0, key_bits(rows), st));
+  // the padding key is `rows` itself: one more key bit when pairs were dropped
+  const int bits = dropped ? key_bits(rows + 1) : key_bits(rows);
+  RB_CUDA(cub::DeviceRadixSort::SortPairs(ws + lay.cub_temp, temp, dk, dv, static_cast<int>(n), 0, bits, st));
   *sel_out = dk.selector;
+  if (dropped) {
+    int* n_valid = reinterpret_cast<int*>(ws + lay.long_count) + 1;
+    count_valid_kernel<<<1, 1, 0, st>>>(dk.Current(), static_cast<int>(n), static_cast<uint32_t>(rows), n_valid);
+    RB_LAUNCH_CHECK("count_valid_kernel");
+  }
+  if (dropped_out != nullptr) *dropped_out = dropped;
   return RB_OK;
 }
 
@@ -803,9 +843,10 @@ extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_gr
   return rc;
 }
 
-extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
-                                   const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt, void* ws,
-                                   size_t ws_bytes, int32_t sorted_sel, void* stream) {
+// n_dev != null: only the first *n_dev sorted pairs are real (masked pads collapsed by sort_groups)
+static int apply_sorted(float* table, float* state0, float* state1, int64_t rows, int32_t D, const rb_lookup_group* groups,
+                        int32_t num_groups, const rb_opt_params* opt, void* ws, size_t ws_bytes, int32_t sorted_sel,
+                        void* stream, const int* n_dev) {
   RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
                "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
   RB_CHECK_ARG(sorted_sel == 0 || sorted_sel == 1, RB_ERR_ARG, "sorted_sel must come from rb_sparse_bwd_prepare");
@@ -840,7 +881,7 @@ extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, i
     const uint32_t *keys, *vals;
     unsigned char* wsb = static_cast<unsigned char*>(ws);
     sorted_pairs(wsb, lay, sorted_sel, &keys, &vals);
-    rc = run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st);
+    rc = run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st, n_dev);
     if (rc != RB_OK) return rc;
   }
   if (o == RB_OPT_ADAM_TF_DENSE) {
@@ -848,6 +889,12 @@ extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, i
     RB_LAUNCH_CHECK("adam_apply_all_kernel");
   }
   return RB_OK;
+}
+
+extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                   const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt, void* ws,
+                                   size_t ws_bytes, int32_t sorted_sel, void* stream) {
+  return apply_sorted(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sorted_sel, stream, nullptr);
 }
 
 extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
@@ -870,10 +917,22 @@ extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* s
     rc0 = describe_groups(groups, num_groups, D, table, geo, &gg);
     if (rc0 != RB_OK) return rc0;
   }
-  int32_t sel = 0;
-  int rc = rb_sparse_bwd_prepare(rows, D, groups, num_groups, ws, ws_bytes, oob_flag, &sel, stream);
-  if (rc != RB_OK) return rc;
-  return rb_sparse_bwd_apply(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sel, stream);
+  // The one-call form knows the gradient sources while it sorts, so masked-mean pads are collapsed (make_keys_kernel);
+  // the two-phase form (rb_sparse_bwd_prepare reads ids only) keeps every pair.
+  const int64_t n = total_lookups(groups, num_groups);
+  int sel = 0;
+  const int* n_dev = nullptr;
+  if (n > 0) {
+    const WsLayout lay = ws_layout(n, D, rows);
+    int rc = check_ws(ws, ws_bytes, lay);
+    if (rc != RB_OK) return rc;
+    bool dropped = false;
+    rc = sort_groups(groups, num_groups, rows, n, static_cast<unsigned char*>(ws), lay, oob_flag, static_cast<cudaStream_t>(stream),
+                     &sel, true, &dropped);
+    if (rc != RB_OK) return rc;
+    if (dropped) n_dev = reinterpret_cast<const int*>(static_cast<unsigned char*>(ws) + lay.long_count) + 1;
+  }
+  return apply_sorted(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sel, stream, n_dev);
 }
 
 extern "C" int rb_sparse_bwd_update(float* table, float* state0, float* state1, int64_t rows, int32_t D,

@@ -95,6 +95,17 @@ def main():
             grp = LookupGroup(hist, Lh, GradSource.per_bag([dpool], scale="masked_mean", mask_idx=hist, count=cnt))
             ops.sparse_bwd_update(wt, mh, vh, [grp], optimizer="adam_lazy", step=hstep[0])
         timeit("pool_masked_mean_bwd_update", hupd)
+        res["pool_masked_mean_bwd_update"]["pairs"] = int(valid + (hist[:, :1] == 0).sum()
+                                                          + ((hist[:, 1:] == 0) & (hist[:, :-1] != 0)).sum())   # one pad per run survives
+        hws = ops.sparse_workspace(B * Lh, Dh, Vh, dev)
+
+        def hupd_all(i):       # the two-phase form sorts ids only and keeps every pad pair: the "before" of the collapse
+            hstep[0] += 1
+            grp = LookupGroup(hist, Lh, GradSource.per_bag([dpool], scale="masked_mean", mask_idx=hist, count=cnt))
+            sel = ops.sparse_bwd_prepare(Vh, Dh, [grp], hws)
+            ops.sparse_bwd_apply(wt, mh, vh, [grp], hws, sel, optimizer="adam_lazy", step=hstep[0])
+        timeit("pool_masked_mean_bwd_update_all_pairs", hupd_all)
+        res["pool_masked_mean_bwd_update_all_pairs"]["pairs"] = B * Lh
     if "fm" in which:        # DeepFM front end (ctr/model.py:19-23) at D = 16, one shared 1M-row table
         wf = torch.empty(1_000_000, 16, device=dev).uniform_(-0.05, 0.05, generator=g)
         catf = torch.randint(0, 1_000_000, (B, F), device=dev, generator=g)

@@ -446,6 +446,44 @@ def test_two_uses_of_one_table_are_concatenated(ops):
     np.testing.assert_allclose(v.cpu().numpy(), st["v"], rtol=1e-3, atol=1e-12)
 
 
+@pytest.mark.parametrize("optimizer", ["adam_lazy", "adam_tf_dense", "adagrad"])
+def test_masked_pads_collapse_keeps_touched_rows(ops, optimizer):
+    """config 4 over several steps: the one-call update collapses each run of masked pads into one zero pair
+    (make_keys_kernel).  TF lists every pad in the IndexedSlices (dien/layers.py:13 multiplies, it does not drop), so
+    the pad row stays *touched*: with lazy Adam its moments decay and the row moves although its gradient is zero.  The
+    cat table is masked by the item ids (dien/model.py:25) and its pad row 0 also occurs at valid positions, so the row
+    carries state when the pads touch it.  Interior (non-trailing) masks are in the batch."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    rng = np.random.default_rng(21)
+    V_item, V_cat, D, B, L = 300, 7, 32, 96, 100
+    W = O.init_table(rng, V_cat, D)
+    st = _state(optimizer, W)
+    Wt = cu(W)
+    s0 = cu(st["m"] if "m" in st else st["acc"]) if st else None
+    s1 = cu(st["v"]) if "v" in st else None
+    for step in (1, 2, 3):
+        lens = rng.integers(1, L + 1, size=(B, 1))
+        item = rng.integers(1, V_item, size=(B, L)).astype(np.int32)
+        cat = rng.integers(0, V_cat, size=(B, L)).astype(np.int32)
+        valid = np.arange(L)[None] < lens
+        item, cat = item * valid, cat * valid                   # trailing zeros (dien/data_loader.py:44)
+        item[3, 2:5] = 0                                        # interior pads; their cat rows differ from one another
+        item[5, 1:] = 0                                         # one valid position, 99 masked ones with random cat rows
+        if step == 2:
+            cat[cat == 0] = 1                                   # row 0 is reached through pads only in this step
+            cat = cat * valid
+        mask = item != 0
+        d_avg = rng.normal(0, 1e-3, size=(B, D)).astype(np.float32)
+        count = cu(mask.sum(1).astype(np.float32))
+        grp = LookupGroup(cu(cat), L, GradSource.per_bag([cu(d_avg)], scale="masked_mean", mask_idx=cu(item), count=count))
+        ops.sparse_bwd_update(Wt, s0, s1, [grp], optimizer=optimizer, step=step)
+        ops.check_oob("cuda")
+        O.sparse_backward_update(W, st, cat, O.masked_mean_backward(d_avg, mask), optimizer, step=step)
+        np.testing.assert_allclose(Wt.cpu().numpy(), W, rtol=0, atol=3e-6, err_msg=f"step {step}")
+    if s1 is not None:
+        np.testing.assert_allclose(s1.cpu().numpy(), st["v"], rtol=1e-3, atol=1e-12)
+
+
 def test_bucket_by_owner(ops):
     rng = np.random.default_rng(11)
     n, V = 10007, 1000
