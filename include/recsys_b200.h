@@ -397,6 +397,59 @@ int rb_sparse_bwd_apply_p2p(float* table, float* state0, float* state1, int64_t 
                             const int32_t* n_valid_dev, const rb_opt_params* opt, void* ws, size_t ws_bytes,
                             int32_t sorted_sel, void* shadow_bf16, void* stream);
 
+/* ---- input side: Criteo TSV -> batch ------------------------------------------------ */
+/*
+ * Replaces the per-line Python of ctr/tfrecord_io.py: build_vocab (:15-35), the body of write_tfrecord (:43-66)
+ * and what read_tfrecord (:78-96) hands to the model — ({'int_features' f32[13], 'cat_features' int64[26]}, label).
+ * The TFRecord container itself is not reproduced: the text goes from HBM straight to the batch.
+ *
+ * text: the file (or a chunk of whole lines, < 2 GiB) resident in HBM, 16-byte aligned, its allocation readable up to
+ * the next multiple of 16 bytes.  One line = label \t I1..I13 \t C1..C26, '\n'-terminated (the last line may lack it).
+ *
+ * Dictionary keys.  The reference keys ONE dictionary for all 26 columns by Python strings (:24-33); this library keys
+ * by the token's bytes packed little-endian into a uint64 — the same identity for tokens of 1..8 ASCII bytes (Criteo's
+ * are 8 hex digits).  Two quirks are kept: (1) str.split leaves the line's newline attached to C26, so its tokens are
+ * different keys from the same bytes in another column — carried as bit 63; (2) an empty column ('' or '\n', :21/:55)
+ * is imputed with a per-column token — key (column + 1) << 8, whose low byte no real token has.
+ *
+ * error_flag (optional int32*, OR-ed): 1 = a line with fewer than 40 columns (the reference raises IndexError),
+ * 2 = a label / integer column int() would reject or of more than 18 digits (int() accepts blanks and underscores;
+ * this parser takes an optional sign and digits), 4 = a categorical token longer than 8 bytes, 8 = a non-ASCII byte
+ * in a token, 16 = a line longer than 1024 bytes.  Offending values are written as 0 / truncated; outputs of other
+ * lines are unaffected.
+ */
+size_t rb_criteo_index_workspace_bytes(int64_t nbytes);
+/* line_start[i] = byte offset of line i (i < min(*num_lines_dev, max_lines)); `for line in f` semantics: a final
+ * newline does not open an empty last line.  *num_lines_dev is the true count even when it exceeds max_lines. */
+int rb_criteo_index_lines(const uint8_t* text, int64_t nbytes, int64_t max_lines, int64_t* line_start,
+                          int64_t* num_lines_dev, void* ws, size_t ws_bytes, void* stream);
+/*
+ * One warp per line.  label int64[n] (:66), int_features f32[n,13] = log(float32(max(x, 0)) + 1), '' -> 0 (:45-53),
+ * cat_tokens (optional) uint64[n,26] the dictionary keys in scan order (input of rb_vocab_build),
+ * cat_features (optional) int64[n,26] = vocabulary id, 0 when absent (:58-65) — needs the table of
+ * rb_vocab_table_build.  num_lines is a HOST value (read *num_lines_dev back, or know the chunk).
+ */
+int rb_criteo_parse(const uint8_t* text, int64_t nbytes, const int64_t* line_start, int64_t num_lines,
+                    int64_t* label, float* int_features, uint64_t* cat_tokens, int64_t* cat_features,
+                    const uint64_t* vocab_table_keys, const int32_t* vocab_table_vals, int64_t vocab_capacity,
+                    int32_t* error_flag, void* stream);
+/*
+ * build_vocab (:15-35) over n tokens in scan order (line-major, column-minor): a token is kept when it occurs more
+ * than min_count times (10 in the reference) and ids are dense from 0 in first-seen order, which is what iterating
+ * the reference's insertion-ordered dict yields.  vocab_keys_out[id] = key for id < min(*num_vocab_dev, max_vocab);
+ * *num_vocab_dev is the true size.  Stream-ordered, no host round trip.  n < 2^31 tokens per call.
+ */
+size_t rb_vocab_build_workspace_bytes(int64_t n);
+int rb_vocab_build(const uint64_t* tokens, int64_t n, int32_t min_count, uint64_t* vocab_keys_out, int64_t max_vocab,
+                   int64_t* num_vocab_dev, void* ws, size_t ws_bytes, void* stream);
+/* key -> id table in HBM: open addressing, linear probing, slot = splitmix64(key) & (capacity - 1);
+ * capacity: a power of two > num_vocab (2x or more keeps probes short).  vocab_keys must be distinct. */
+int rb_vocab_table_build(const uint64_t* vocab_keys, int64_t num_vocab, uint64_t* table_keys, int32_t* table_vals,
+                         int64_t capacity, void* stream);
+/* ids_out[i] = id of tokens[i], 0 when absent (:61-64: OOV shares id 0 with the first vocabulary entry) */
+int rb_vocab_lookup(const uint64_t* tokens, int64_t n, const uint64_t* table_keys, const int32_t* table_vals,
+                    int64_t capacity, int64_t* ids_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ import torch as _t
 
 from . import keras  # noqa: F401  (`from tensorflow import keras`)
 from . import linalg, nn  # noqa: F401
+from . import io, train  # noqa: F401  (ctr/tfrecord_io.py's writer side)
 
 float32 = _t.float32
 int32 = _t.int32

@@ -101,6 +101,13 @@ SIGNATURES = {
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "rb_criteo_index_workspace_bytes": (C.c_size_t, [_i64]),
+    "rb_criteo_index_lines": (C.c_int, [_p, _i64, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "rb_criteo_parse": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
+    "rb_vocab_build_workspace_bytes": (C.c_size_t, [_i64]),
+    "rb_vocab_build": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, C.c_size_t, _p]),
+    "rb_vocab_table_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
+    "rb_vocab_lookup": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
 }
 
 

@@ -1,0 +1,233 @@
+"""Input side of the CTR models: Criteo TSV -> batches, on the GPU (mirror of /root/reference/ctr/tfrecord_io.py).
+
+The reference goes text -> Python dict vocabulary -> TFRecord of serialized tensors -> tf.data (`build_vocab` :15-35,
+`write_tfrecord` :38-75, `read_tfrecord` :78-96) and is bound by that Python loop.  Here the text is
+copied to HBM once and every step of that chain is a kernel of librecsys_b200.so (csrc/criteo_input.cu):
+
+    vocab = build_vocab(train_file)                        # same name, same rule: count > 10, ids in first-seen order
+    for features, label in read_tfrecord(raw_file, vocab, batch_size):
+        model(features)                                    # {'int_features' f32[B,13], 'cat_features' i64[B,26]}
+
+`read_tfrecord` takes the RAW text file: the TFRecord container in between is not reproduced, its content is.
+torch only carries the device memory; there is no CPU path (a missing library raises).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .ops import _need_cuda, _ptr, _stream
+
+num_int = 13        # ctr/tfrecord_io.py:8
+num_cat = 26        # :9
+total_cols = 40     # :10
+MIN_COUNT = 10      # :31
+
+ERROR_BITS = {1: "a line with fewer than 40 columns", 2: "a label / integer column that is not an integer",
+              4: "a categorical token longer than 8 bytes", 8: "a non-ASCII byte in a categorical token",
+              16: "a line longer than 1024 bytes"}
+
+
+class CriteoFormatError(ValueError):
+    pass
+
+
+def _device(device) -> torch.device:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.RecsysError("recommender_b200.tfrecord_io runs on a CUDA device only (there is no CPU path)")
+    return dev
+
+
+def to_device(text, device=None) -> torch.Tensor:
+    """bytes / uint8 array / uint8 tensor -> uint8 tensor in HBM, padded so that the parser's 128-bit loads stay inside
+    the allocation.  Returns a view of exactly len(text) bytes."""
+    dev = _device(device)
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        host = torch.frombuffer(bytearray(text), dtype=torch.uint8) if len(text) else torch.empty(0, dtype=torch.uint8)
+    elif isinstance(text, np.ndarray):
+        host = torch.from_numpy(np.ascontiguousarray(text, dtype=np.uint8))
+    else:
+        host = text
+    n = host.numel()
+    buf = torch.zeros((n + 15) // 16 * 16 + 16, dtype=torch.uint8, device=dev)
+    buf[:n].copy_(host, non_blocking=True)
+    return buf[:n]
+
+
+def index_lines(text: torch.Tensor, max_lines: Optional[int] = None) -> torch.Tensor:
+    """int64[num_lines] byte offsets of the lines of `text` (rb_criteo_index_lines).  Synchronises once to learn the
+    count; room is sized for well-formed lines (39 tabs and a label: more than 40 bytes) and the call is repeated with
+    the exact count for a file of shorter ones."""
+    _need_cuda(text)
+    nbytes = text.numel()
+    nbytes_ws = lib.rb_criteo_index_workspace_bytes(nbytes)
+    if nbytes_ws == 0:
+        raise _lib.RecsysError("rb_criteo_index_workspace_bytes rejected the size: feed the file in chunks below 2 GiB")
+    ws = torch.empty(nbytes_ws, dtype=torch.uint8, device=text.device)
+    count = torch.zeros(1, dtype=torch.int64, device=text.device)
+    room = nbytes // total_cols + 1 if max_lines is None else int(max_lines)
+    while True:
+        starts = torch.empty(room, dtype=torch.int64, device=text.device)
+        check(lib.rb_criteo_index_lines(_ptr(text), nbytes, room, _ptr(starts), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+              "rb_criteo_index_lines")
+        n = int(count.item())
+        if n <= room:
+            return starts[:n]
+        if max_lines is not None:
+            raise _lib.RecsysError(f"{n} lines but room for {max_lines}")
+        room = n
+
+
+def check_errors(flag: torch.Tensor) -> None:
+    bits = int(flag.item())
+    if bits:
+        flag.zero_()
+        raise CriteoFormatError("malformed Criteo text: " + "; ".join(msg for b, msg in ERROR_BITS.items() if bits & b))
+
+
+class Vocab:
+    """The reference's `cat_fea_vocab` dict (:28-33) as device arrays: `keys` uint64-as-int64[V] in id order and the
+    open-addressing table the parser probes."""
+
+    def __init__(self, keys: torch.Tensor):
+        _need_cuda(keys)
+        self.keys = keys.contiguous()
+        n = self.keys.numel()
+        cap = 16
+        while cap < 2 * n + 1:
+            cap *= 2
+        self.capacity = cap
+        self.table_keys = torch.empty(cap, dtype=torch.int64, device=keys.device)
+        self.table_vals = torch.empty(cap, dtype=torch.int32, device=keys.device)
+        check(lib.rb_vocab_table_build(_ptr(self.keys), n, _ptr(self.table_keys), _ptr(self.table_vals), cap, _stream()),
+              "rb_vocab_table_build")
+
+    def __len__(self) -> int:
+        return self.keys.numel()
+
+    def lookup(self, tokens: torch.Tensor) -> torch.Tensor:
+        """ids of packed token keys, 0 when absent (:61-64)."""
+        _need_cuda(tokens)
+        tokens = tokens.contiguous()
+        out = torch.empty(tokens.shape, dtype=torch.int64, device=tokens.device)
+        check(lib.rb_vocab_lookup(_ptr(tokens), tokens.numel(), _ptr(self.table_keys), _ptr(self.table_vals), self.capacity,
+                                  _ptr(out), _stream()), "rb_vocab_lookup")
+        return out
+
+    def save(self, path: str) -> None:
+        """Stands in for the pickle of :34-35 (keys in id order)."""
+        np.save(path, self.keys.cpu().numpy().view(np.uint64))
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "Vocab":
+        return cls(torch.from_numpy(np.load(path).view(np.int64)).to(_device(device)))
+
+
+def parse(text: torch.Tensor, vocab: Optional[Vocab] = None, *, line_start: Optional[torch.Tensor] = None, want_tokens=False,
+          raise_on_error=True):
+    """The body of `write_tfrecord` (:43-66) for every line of `text`, as one kernel (rb_criteo_parse).
+
+    Returns ({'int_features': f32[n,13], 'cat_features': i64[n,26]}, label i64[n]); with vocab=None or want_tokens the
+    dict also carries 'cat_tokens' (the packed dictionary keys, i64 bit patterns of uint64)."""
+    _need_cuda(text)
+    if line_start is None:
+        line_start = index_lines(text)
+    n = line_start.numel()
+    dev = text.device
+    label = torch.empty(n, dtype=torch.int64, device=dev)
+    ints = torch.empty(n, num_int, dtype=torch.float32, device=dev)
+    tokens = torch.empty(n, num_cat, dtype=torch.int64, device=dev) if (want_tokens or vocab is None) else None
+    cats = torch.empty(n, num_cat, dtype=torch.int64, device=dev) if vocab is not None else None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.rb_criteo_parse(_ptr(text), text.numel(), _ptr(line_start), n, _ptr(label), _ptr(ints), _ptr(tokens), _ptr(cats),
+                              _ptr(vocab.table_keys) if vocab is not None else None,
+                              _ptr(vocab.table_vals) if vocab is not None else None,
+                              vocab.capacity if vocab is not None else 0, _ptr(flag), _stream()), "rb_criteo_parse")
+    features = {"int_features": ints}
+    if raise_on_error:
+        check_errors(flag)               # synchronises
+    else:
+        features["error_flag"] = flag    # the caller reads the bits (ERROR_BITS) when it chooses to synchronise
+    if cats is not None:
+        features["cat_features"] = cats
+    if tokens is not None:
+        features["cat_tokens"] = tokens
+    return features, label
+
+
+def vocab_from_tokens(tokens: torch.Tensor, min_count: int = MIN_COUNT) -> Vocab:
+    """`build_vocab`'s counting and numbering (:24-33) over packed tokens in scan order (rb_vocab_build)."""
+    _need_cuda(tokens)
+    tokens = tokens.contiguous()
+    n = tokens.numel()
+    nbytes = lib.rb_vocab_build_workspace_bytes(n)
+    if nbytes == 0:
+        raise _lib.RecsysError("rb_vocab_build_workspace_bytes rejected the size (2^31 tokens per call)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=tokens.device)
+    out = torch.empty(max(n // (min_count + 1), 1), dtype=torch.int64, device=tokens.device)   # a kept token occurs > min_count times
+    count = torch.zeros(1, dtype=torch.int64, device=tokens.device)
+    check(lib.rb_vocab_build(_ptr(tokens), n, int(min_count), _ptr(out), out.numel(), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+          "rb_vocab_build")
+    return Vocab(out[: int(count.item())].clone())
+
+
+def _chunks(path: str, chunk_bytes: int) -> Iterator[bytes]:
+    """Whole-line chunks of a text file."""
+    with open(path, "rb") as fh:
+        rest = b""
+        while True:
+            block = fh.read(chunk_bytes)
+            if not block:
+                break
+            block = rest + block
+            cut = block.rfind(b"\n") + 1
+            if cut == 0:
+                rest = block
+                continue
+            yield block[:cut]
+            rest = block[cut:]
+        if rest:
+            yield rest
+
+
+def build_vocab(train_file: str, *, device=None, chunk_bytes: int = 1 << 30, min_count: int = MIN_COUNT,
+                save_to: Optional[str] = None) -> Vocab:
+    """ctr/tfrecord_io.py:15-35.  The file is parsed chunk by chunk; the packed tokens of all chunks stay in HBM
+    (8 bytes x 26 per line) and are counted in one pass."""
+    dev = _device(device)
+    parts = []
+    for block in _chunks(train_file, chunk_bytes):
+        features, _ = parse(to_device(block, dev), None)
+        parts.append(features["cat_tokens"])
+    tokens = torch.cat(parts) if parts else torch.empty(0, num_cat, dtype=torch.int64, device=dev)
+    vocab = vocab_from_tokens(tokens, min_count)
+    if save_to is not None:
+        os.makedirs(os.path.dirname(os.path.abspath(save_to)), exist_ok=True)
+        vocab.save(save_to)
+    return vocab
+
+
+def read_tfrecord(raw_file: str, vocab: Vocab, batch_size: int, *, device=None, chunk_bytes: int = 1 << 28,
+                  drop_remainder: bool = False) -> Iterator[Tuple[dict, torch.Tensor]]:
+    """`read_tfrecord(write_tfrecord(raw_file)).batch(batch_size)` (:38-96) without the file in between: yields
+    ({'int_features': f32[B,13], 'cat_features': i64[B,26]}, label i64[B]) in file order."""
+    dev = _device(device)
+    carry = None
+    for block in _chunks(raw_file, chunk_bytes):
+        features, label = parse(to_device(block, dev), vocab)
+        ints, cats = features["int_features"], features["cat_features"]
+        if carry is not None:
+            ints, cats, label = torch.cat([carry[0], ints]), torch.cat([carry[1], cats]), torch.cat([carry[2], label])
+        n = label.numel()
+        full = n // batch_size * batch_size
+        for s in range(0, full, batch_size):
+            yield {"int_features": ints[s:s + batch_size], "cat_features": cats[s:s + batch_size]}, label[s:s + batch_size]
+        carry = (ints[full:], cats[full:], label[full:]) if full < n else None
+    if carry is not None and not drop_remainder:
+        yield {"int_features": carry[0], "cat_features": carry[1]}, carry[2]
