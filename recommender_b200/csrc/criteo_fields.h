@@ -4,6 +4,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RB_HD __host__ __device__ __forceinline__
@@ -27,10 +28,55 @@ constexpr int kErrLongToken = 4;   // a categorical token longer than 8 bytes ha
 constexpr int kErrNonAscii = 8;    // a byte >= 0x80 inside a categorical token
 constexpr int kErrLongLine = 16;   // a line longer than the parser's staging buffer
 
+// The 8 bytes at s (any alignment), little-endian: byte i of the result is s[i].  Bytes behind the column are garbage
+// the caller masks off; the caller guarantees that 11 bytes behind s are readable (the parser's line buffer has slack).
+RB_HD uint64_t load8(const uint8_t* s) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const unsigned sh = static_cast<unsigned>(a & 3) * 8;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32) | __funnelshift_r(w0, w1, sh);
+#else
+  uint64_t v;
+  memcpy(&v, s, 8);  // little-endian hosts (x86-64, aarch64)
+  return v;
+#endif
+}
+
+// 1..8 decimal digits held in the low `len` bytes of `chunk` (first character in byte 0), all at once: pad with
+// leading '0's, check every byte is a digit, then three multiply-shift steps combine pairs, quads and the two halves.
+RB_HD bool parse_digits8(uint64_t chunk, int len, int64_t* out) {
+  const int pad = 8 * (8 - len);
+  uint64_t v = pad ? ((chunk << pad) | (0x3030303030303030ull >> (64 - pad))) : chunk;
+  if (((v & 0xF0F0F0F0F0F0F0F0ull) | (((v + 0x0606060606060606ull) & 0xF0F0F0F0F0F0F0F0ull) >> 4)) != 0x3333333333333333ull)
+    return false;
+  v = ((v & 0x0F0F0F0F0F0F0F0Full) * 2561) >> 8;
+  v = ((v & 0x00FF00FF00FF00FFull) * 6553601) >> 16;
+  *out = static_cast<int64_t>(((v & 0x0000FFFF0000FFFFull) * 42949672960001ull) >> 32);
+  return true;
+}
+
 // `int(s)` for the label and the 13 integer columns: optional sign, decimal digits.  '' is the caller's business
 // (:46-47 turns it into '0' for the integer columns; the label is never empty).  Returns false when int() would raise
-// (or the value does not fit: more than 18 digits).
+// (or the value does not fit: more than 18 digits).  Up to 8 digits go through parse_digits8; longer ones and
+// anything odd through the byte loop.
 RB_HD bool parse_int(const uint8_t* s, int len, int64_t* out) {
+  if (len >= 1 && len <= 8) {
+    uint64_t c = load8(s);
+    int l = len;
+    const unsigned first = static_cast<unsigned>(c & 0xFF);
+    const bool sign = first == '-' || first == '+';
+    if (sign) {
+      c >>= 8;
+      l -= 1;
+    }
+    int64_t v;
+    if (l >= 1 && parse_digits8(c, l, &v)) {
+      *out = first == '-' ? -v : v;
+      return true;
+    }
+  }
   int i = 0;
   bool neg = false;
   if (len > 0 && (s[0] == '-' || s[0] == '+')) {
@@ -73,11 +119,11 @@ RB_HD uint64_t token_key(const uint8_t* s, int len, bool trailing_newline, int f
     *err |= kErrLongToken;
     len = 8;
   }
-  uint64_t k = 0;
-  for (int i = 0; i < len; ++i) {
-    const uint64_t c = s[i];
-    if (c >= 0x80) *err |= kErrNonAscii;
-    k |= (c & 0x7F) << (8 * i);
+  uint64_t k = load8(s);
+  if (len < 8) k &= (1ull << (8 * len)) - 1;
+  if (k & 0x8080808080808080ull) {
+    *err |= kErrNonAscii;
+    k &= 0x7F7F7F7F7F7F7F7Full;
   }
   return trailing_newline ? (k | kNewlineBit) : k;
 }

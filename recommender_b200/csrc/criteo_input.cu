@@ -23,7 +23,8 @@ using namespace criteo;
 constexpr int kTileThreads = 256;
 constexpr int kTileBytes = kTileThreads * 16;  // one 128-bit load per thread
 constexpr int kMaxLine = 1024;                 // bytes of one line without its newline (Criteo lines are < 450)
-constexpr int kLineBuf = kMaxLine + 16;        // the copy starts at the 16-byte boundary below the line
+constexpr int kLineBuf = kMaxLine + 32;        // the copy starts at the 16-byte boundary below the line; 16 B of slack
+                                               // behind it for load8 (criteo_fields.h)
 constexpr int kParseWarps = 8;
 
 __device__ __forceinline__ unsigned newline_mask(uint32_t w) { return __vcmpeq4(w, 0x0A0A0A0Au) & 0x01010101u; }

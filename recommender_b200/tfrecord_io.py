@@ -8,7 +8,10 @@ copied to HBM once and every step of that chain is a kernel of librecsys_b200.so
     for features, label in read_tfrecord(raw_file, vocab, batch_size):
         model(features)                                    # {'int_features' f32[B,13], 'cat_features' i64[B,26]}
 
-`read_tfrecord` takes the RAW text file: the TFRecord container in between is not reproduced, its content is.
+    write_tfrecord(raw_file, output_file, vocab)           # optional, once: 268-byte binary records instead of text
+    for features, label in read_tfrecord(output_file, batch_size=65536): ...
+
+`read_tfrecord` takes the raw text or the record file.  The TFRecord/protobuf container is not reproduced, its content is.
 torch only carries the device memory; there is no CPU path (a missing library raises).
 """
 from __future__ import annotations
@@ -49,9 +52,9 @@ def to_device(text, device=None) -> torch.Tensor:
     the allocation.  Returns a view of exactly len(text) bytes."""
     dev = _device(device)
     if isinstance(text, (bytes, bytearray, memoryview)):
-        host = torch.frombuffer(bytearray(text), dtype=torch.uint8) if len(text) else torch.empty(0, dtype=torch.uint8)
+        host = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()) if len(text) else torch.empty(0, dtype=torch.uint8)
     elif isinstance(text, np.ndarray):
-        host = torch.from_numpy(np.ascontiguousarray(text, dtype=np.uint8))
+        host = torch.from_numpy(np.array(text, dtype=np.uint8))      # a copy: fixtures come in read-only
     else:
         host = text
     n = host.numel()
@@ -177,23 +180,48 @@ def vocab_from_tokens(tokens: torch.Tensor, min_count: int = MIN_COUNT) -> Vocab
     return Vocab(out[: int(count.item())].clone())
 
 
-def _chunks(path: str, chunk_bytes: int) -> Iterator[bytes]:
-    """Whole-line chunks of a text file."""
-    with open(path, "rb") as fh:
-        rest = b""
-        while True:
-            block = fh.read(chunk_bytes)
-            if not block:
-                break
-            block = rest + block
-            cut = block.rfind(b"\n") + 1
+def _fill_chunks(fh, view: np.ndarray) -> Iterator[int]:
+    """Host half of the chunked reader: fills `view` (uint8) from the binary file `fh` and yields `cut`, the number of
+    leading bytes that form whole lines.  When the consumer comes back the unfinished tail is moved to the front and
+    reading continues behind it.  The file's last line may lack its newline."""
+    rest = 0
+    while True:
+        got = fh.readinto(memoryview(view)[rest:]) or 0
+        total = rest + got
+        if total == 0:
+            return
+        if got == 0:
+            cut = total                                       # end of file: a last line without its newline
+        else:
+            cut, lo, step = 0, total, 1 << 16
+            while cut == 0 and lo > 0:                        # last newline, searched backwards a block at a time
+                lo = max(0, lo - step)
+                hits = np.flatnonzero(view[lo:min(lo + step, total)] == 10)
+                if hits.size:
+                    cut = lo + int(hits[-1]) + 1
             if cut == 0:
-                rest = block
+                if total == view.size:
+                    raise CriteoFormatError(f"a line longer than chunk_bytes = {view.size}")
+                rest = total                                  # no complete line yet: keep reading
                 continue
-            yield block[:cut]
-            rest = block[cut:]
+        yield cut
+        rest = total - cut
         if rest:
-            yield rest
+            view[:rest] = view[cut:total].copy()
+        if got == 0:
+            return
+
+
+def _device_chunks(path: str, chunk_bytes: int, dev: torch.device) -> Iterator[torch.Tensor]:
+    """Whole-line chunks of a text file as uint8 tensors in HBM: the file is read straight into ONE pinned staging
+    buffer (no intermediate bytes objects) and copied from there."""
+    size = max(1, min(int(chunk_bytes), os.path.getsize(path)))
+    stage = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+    with open(path, "rb") as fh:
+        for cut in _fill_chunks(fh, stage.numpy()):
+            out = to_device(stage[:cut], dev)
+            torch.cuda.current_stream(dev).synchronize()      # the staging buffer is about to be overwritten
+            yield out
 
 
 def build_vocab(train_file: str, *, device=None, chunk_bytes: int = 1 << 30, min_count: int = MIN_COUNT,
@@ -202,8 +230,8 @@ def build_vocab(train_file: str, *, device=None, chunk_bytes: int = 1 << 30, min
     (8 bytes x 26 per line) and are counted in one pass."""
     dev = _device(device)
     parts = []
-    for block in _chunks(train_file, chunk_bytes):
-        features, _ = parse(to_device(block, dev), None)
+    for block in _device_chunks(train_file, chunk_bytes, dev):
+        features, _ = parse(block, None)
         parts.append(features["cat_tokens"])
     tokens = torch.cat(parts) if parts else torch.empty(0, num_cat, dtype=torch.int64, device=dev)
     vocab = vocab_from_tokens(tokens, min_count)
@@ -213,14 +241,93 @@ def build_vocab(train_file: str, *, device=None, chunk_bytes: int = 1 << 30, min
     return vocab
 
 
-def read_tfrecord(raw_file: str, vocab: Vocab, batch_size: int, *, device=None, chunk_bytes: int = 1 << 28,
-                  drop_remainder: bool = False) -> Iterator[Tuple[dict, torch.Tensor]]:
-    """`read_tfrecord(write_tfrecord(raw_file)).batch(batch_size)` (:38-96) without the file in between: yields
-    ({'int_features': f32[B,13], 'cat_features': i64[B,26]}, label i64[B]) in file order."""
+# ---- the preprocessed record file (stands in for the TFRecord of ctr/tfrecord_io.py:38-75) -----------------------------
+# One fixed-size record per line, in file order: label i64 | int_features f32[13] | cat_features i64[26] = 268 bytes,
+# behind a 64-byte header.  Same content as the reference's tf.train.Example (two serialized tensors and the label,
+# :66-73), without the protobuf framing.  The host never touches a record: records move disk -> pinned -> HBM as
+# bytes and are split into the three tensors on the GPU.
+
+RECORD_MAGIC = b"RBCRITEO"
+RECORD_HEADER = 64
+RECORD_BYTES = 8 + 4 * num_int + 8 * num_cat
+
+
+def _record_header() -> bytes:
+    head = RECORD_MAGIC + np.array([1, num_int, num_cat, RECORD_BYTES], dtype="<i4").tobytes()
+    return head + b"\0" * (RECORD_HEADER - len(head))
+
+
+def _split_records(raw: torch.Tensor):
+    """uint8[n, 268] in HBM -> ({'int_features', 'cat_features'}, label)."""
+    label = raw[:, :8].contiguous().view(torch.int64).reshape(-1)
+    ints = raw[:, 8:8 + 4 * num_int].contiguous().view(torch.float32)
+    cats = raw[:, 8 + 4 * num_int:].contiguous().view(torch.int64)
+    return {"int_features": ints, "cat_features": cats}, label
+
+
+def write_tfrecord(raw_file: str, output_file: str, vocab: Vocab, *, device=None, chunk_bytes: int = 1 << 28) -> int:
+    """ctr/tfrecord_io.py:38-75: raw Criteo text -> the preprocessed record file, once, so that every epoch reads
+    268-byte records instead of parsing text.  Returns the number of records."""
     dev = _device(device)
+    n = 0
+    with open(output_file, "wb") as out:
+        out.write(_record_header())
+        for block in _device_chunks(raw_file, chunk_bytes, dev):
+            features, label = parse(block, vocab)
+            rows = label.numel()
+            raw = torch.cat([label.view(torch.uint8).reshape(rows, 8),
+                             features["int_features"].view(torch.uint8).reshape(rows, 4 * num_int),
+                             features["cat_features"].view(torch.uint8).reshape(rows, 8 * num_cat)], dim=1)
+            out.write(raw.cpu().numpy().tobytes())
+            n += rows
+    return n
+
+
+def _is_record_file(path: str) -> bool:
+    with open(path, "rb") as fh:
+        return fh.read(len(RECORD_MAGIC)) == RECORD_MAGIC
+
+
+def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder: bool):
+    size = os.path.getsize(path) - RECORD_HEADER
+    if size < 0 or size % RECORD_BYTES:
+        raise CriteoFormatError(f"{path}: truncated record file")
+    n = size // RECORD_BYTES
+    if n == 0:
+        return
+    records = np.memmap(path, dtype=np.uint8, mode="r", offset=RECORD_HEADER, shape=(n, RECORD_BYTES))
+    stage = [torch.empty(batch_size, RECORD_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    done = [None, None]                                       # the H2D copy that last read each staging buffer
+    for k, s in enumerate(range(0, n, batch_size)):
+        e = min(s + batch_size, n)
+        if e - s < batch_size and drop_remainder:
+            return
+        buf = stage[k % 2]
+        if done[k % 2] is not None:
+            done[k % 2].synchronize()
+        buf.numpy()[: e - s] = records[s:e]
+        raw = buf[: e - s].to(dev, non_blocking=True)
+        done[k % 2] = torch.cuda.Event()
+        done[k % 2].record()
+        yield _split_records(raw)
+
+
+def read_tfrecord(tfrecord_file: str, vocab: Optional[Vocab] = None, batch_size: int = 1024, *, device=None,
+                  chunk_bytes: int = 1 << 28, drop_remainder: bool = False) -> Iterator[Tuple[dict, torch.Tensor]]:
+    """ctr/tfrecord_io.py:78-96 followed by `.batch(batch_size)` (ctr/train.py:59-61): yields
+    ({'int_features': f32[B,13], 'cat_features': i64[B,26]}, label i64[B]) in file order.
+
+    `tfrecord_file` is either a record file written by `write_tfrecord`, or the RAW Criteo text itself (then `vocab`
+    is required and the text is parsed on the fly: `read_tfrecord(write_tfrecord(raw))` without the file in between)."""
+    dev = _device(device)
+    if _is_record_file(tfrecord_file):
+        yield from _read_records(tfrecord_file, int(batch_size), dev, drop_remainder)
+        return
+    if vocab is None:
+        raise ValueError("reading raw Criteo text needs the vocabulary (build_vocab)")
     carry = None
-    for block in _chunks(raw_file, chunk_bytes):
-        features, label = parse(to_device(block, dev), vocab)
+    for block in _device_chunks(tfrecord_file, chunk_bytes, dev):
+        features, label = parse(block, vocab)
         ints, cats = features["int_features"], features["cat_features"]
         if carry is not None:
             ints, cats, label = torch.cat([carry[0], ints]), torch.cat([carry[1], cats]), torch.cat([carry[2], label])

@@ -114,18 +114,38 @@ def main():
     assert int(flag.item()) == 0
     res["oov_or_id0_fraction"] = float((cats == 0).float().mean())
     # the user-facing chain: index + parse + lookup with allocation and the count read-back (one host sync) inside
+    for _ in range(2):
+        io.parse(text, vocab)                             # the caching allocator now holds the output buffers
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(a.iters):
         io.parse(text, vocab)
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / a.iters * 1e3
     res["parse_api_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3, text_gbs=nbytes / ms / 1e6)
-    # host text -> device -> batch, H2D from pageable memory inside the timed region
-    t0 = time.perf_counter()
-    io.parse(io.to_device(text_host, dev), vocab)
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3
-    res["host_to_batch_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3, h2d_bytes=nbytes)
+    # the file on disk (page cache) -> pinned staging -> HBM -> batches of 65536: what `read_tfrecord` delivers end to end
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "day.txt")
+        with open(path, "wb") as fh:
+            fh.write(text_host)
+        for _ in io.read_tfrecord(path, vocab, 65536):    # warm-up: page cache, pinned buffer, allocator
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seen = 0
+        for feats, lab in io.read_tfrecord(path, vocab, 65536):
+            seen += lab.numel()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        assert seen == n_lines
+        res["read_tfrecord_file_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3, h2d_bytes=nbytes, batch=65536)
+        t0 = time.perf_counter()
+        v2 = io.build_vocab(path)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        assert len(v2) == len(vocab)
+        res["build_vocab_file_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3)
     if a.cpu_lines > 0:
         from oracle import criteo_oracle as CO           # the CPU leg only: restated ctr/tfrecord_io.py:43-66
         sample = CO.split_lines(block)[: a.cpu_lines]

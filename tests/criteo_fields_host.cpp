@@ -2,13 +2,19 @@
 // field-level functions the parse kernel calls, driven by a scalar walk over one line.  TEST INFRASTRUCTURE.
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <vector>
 
 #include "../recommender_b200/csrc/criteo_fields.h"
 
 using namespace rb::criteo;
 
 // line[0..len): one line WITHOUT its newline; has_nl: the newline was there.  Returns the error bits.
-extern "C" int t_parse_line(const uint8_t* line, int len, int has_nl, int64_t* label, float* ints, uint64_t* keys) {
+extern "C" int t_parse_line(const uint8_t* text, int len, int has_nl, int64_t* label, float* ints, uint64_t* keys) {
+  std::vector<uint8_t> padded(static_cast<size_t>(len) + 16, 0xAB);   // load8 reads up to 11 bytes behind a column
+  memcpy(padded.data(), text, static_cast<size_t>(len));
+  const uint8_t* line = padded.data();
   int16_t tab[kCols];
   int ntabs = 0;
   for (int p = 0; p < len; ++p)
@@ -57,4 +63,11 @@ extern "C" void t_table_build(const uint64_t* vocab_keys, int64_t n, uint64_t* t
     tkeys[slot] = vocab_keys[i];
     tvals[slot] = static_cast<int32_t>(i);
   }
+}
+
+extern "C" int t_parse_int(const uint8_t* text, int len, int64_t* out) {
+  uint8_t padded[64];
+  memset(padded, 0xAB, sizeof(padded));
+  memcpy(padded, text, static_cast<size_t>(len < 40 ? len : 40));
+  return parse_int(padded, len, out) ? 1 : 0;
 }

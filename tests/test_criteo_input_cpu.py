@@ -162,3 +162,55 @@ def test_host_error_bits_and_quirks(host, g):
     e[30] = "123456789"
     assert _host_parse(host, "\t".join(e) + "\n")[0] == 4                           # no 64-bit key
     assert _host_parse(host, "\t" + "\t".join(cols[1:]) + "\n")[0] == 2             # int('') for the label
+
+
+# ---- host half of the chunked file reader ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("final_newline", [True, False])
+@pytest.mark.parametrize("chunk", [64, 100, 257, 4096, 1 << 20])
+def test_fill_chunks_yields_whole_lines(tmp_path, chunk, final_newline):
+    """recommender_b200.tfrecord_io._fill_chunks: every chunk ends on a line boundary, nothing is lost or repeated,
+    whatever the chunk size (here down to barely more than one line)."""
+    from recommender_b200.tfrecord_io import CriteoFormatError, _fill_chunks
+    rng = np.random.default_rng(chunk)
+    lines = [b"x" * int(rng.integers(0, 60)) for _ in range(200)]
+    text = b"\n".join(lines) + (b"\n" if final_newline else b"")
+    path = tmp_path / "f.txt"
+    path.write_bytes(text)
+    view = np.empty(min(chunk, len(text)), dtype=np.uint8)
+    got = []
+    with open(path, "rb") as fh:
+        for cut in _fill_chunks(fh, view):
+            piece = view[:cut].tobytes()
+            got.append(piece)
+    assert b"".join(got) == text
+    assert all(p.endswith(b"\n") for p in got[:-1])
+    assert all(len(p) <= chunk for p in got)
+    if chunk >= len(text):
+        assert len(got) == 1
+    # a line that does not fit the buffer is an error, not a silent split
+    path.write_bytes(b"y" * 300 + b"\n")
+    with open(path, "rb") as fh, pytest.raises(CriteoFormatError):
+        list(_fill_chunks(fh, np.empty(128, dtype=np.uint8)))
+    path.write_bytes(b"")
+    with open(path, "rb") as fh:
+        assert list(_fill_chunks(fh, np.empty(16, dtype=np.uint8))) == []
+
+
+def test_host_parse_int_matches_python_int(host):
+    """parse_int (SWAR path for up to 8 digits, byte loop beyond) against Python's int() on what Criteo files hold."""
+    host.t_parse_int.restype = C.c_int
+    host.t_parse_int.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(3)
+    cases = ["0", "7", "-1", "+5", "00012", "99999999", "-9999999", "123456789", "-123456789012345678", "999999999999999999"]
+    for digits in range(1, 19):
+        for _ in range(40):
+            v = int(rng.integers(0, 10 ** digits))
+            cases += [str(v), str(-v), str(v).zfill(digits)]
+    for text in cases:
+        out = C.c_int64(0)
+        assert host.t_parse_int(text.encode(), len(text), C.byref(out)) == 1, text
+        assert out.value == int(text), text
+    for text in ["", "-", "+", "12x", "x12", "1 2", "1.5", "--1", "1-", "12345678x", "1" * 19, "\t1", "1e3", "0x10", ":", "/"]:
+        out = C.c_int64(0)
+        assert host.t_parse_int(text.encode(), len(text), C.byref(out)) == 0, text

@@ -188,3 +188,33 @@ def test_arguments_are_validated(io):
         io.parse(text[1:], None)                                                 # not 16-byte aligned
     with pytest.raises(RecsysError):
         io.to_device(b"abc", device="cpu")
+
+
+def test_record_file_round_trip(io, g, tmp_path):
+    """write_tfrecord (ctr/tfrecord_io.py:38-75) -> read_tfrecord (:78-96): the preprocessed record file delivers the
+    reference's records bit for bit (the int_features are stored, not recomputed), in any batch size."""
+    train, test = tmp_path / "train.txt", tmp_path / "test.txt"
+    train.write_bytes(g["train_tsv"].tobytes())
+    test.write_bytes(g["test_tsv"].tobytes())
+    vocab = io.build_vocab(str(train))
+    for path, split in ((train, "train"), (test, "test")):
+        out = tmp_path / f"{split}.tfrecord"
+        n = io.write_tfrecord(str(path), str(out), vocab, chunk_bytes=20_000)
+        assert n == len(g[f"{split}_label"]) and out.stat().st_size == 64 + 268 * n
+        direct = io.parse(io.to_device(path.read_bytes()), vocab)
+        for B in (1, 7, 64, 10_000):
+            batches = list(io.read_tfrecord(str(out), batch_size=B))
+            assert [len(b[1]) for b in batches] == [B] * (n // B) + ([n % B] if n % B else [])
+            cats = torch.cat([b[0]["cat_features"] for b in batches])
+            ints = torch.cat([b[0]["int_features"] for b in batches])
+            label = torch.cat([b[1] for b in batches])
+            np.testing.assert_array_equal(cats.cpu().numpy(), g[f"{split}_cat_features"])
+            np.testing.assert_array_equal(label.cpu().numpy(), g[f"{split}_label"])
+            assert torch.equal(ints, direct[0]["int_features"])                      # stored bits = parsed bits
+            assert cats.dtype == torch.int64 and ints.dtype == torch.float32 and label.dtype == torch.int64
+        assert len(list(io.read_tfrecord(str(out), batch_size=10, drop_remainder=True))) == n // 10
+    (tmp_path / "bad.tfrecord").write_bytes((tmp_path / "test.tfrecord").read_bytes()[:-5])
+    with pytest.raises(io.CriteoFormatError):
+        list(io.read_tfrecord(str(tmp_path / "bad.tfrecord"), batch_size=4))
+    with pytest.raises(ValueError):
+        list(io.read_tfrecord(str(test), batch_size=4))                              # raw text needs the vocabulary
