@@ -259,9 +259,14 @@ def _record_header() -> bytes:
 
 def _split_records(raw: torch.Tensor):
     """uint8[n, 268] in HBM -> ({'int_features', 'cat_features'}, label)."""
-    label = raw[:, :8].contiguous().view(torch.int64).reshape(-1)
-    ints = raw[:, 8:8 + 4 * num_int].contiguous().view(torch.float32)
-    cats = raw[:, 8 + 4 * num_int:].contiguous().view(torch.int64)
+    def cols(a: int, b: int, dtype) -> torch.Tensor:
+        out = torch.empty(raw.shape[0], b - a, dtype=torch.uint8, device=raw.device)     # fresh, so the dtype view is aligned
+        out.copy_(raw[:, a:b])
+        return out.view(dtype)
+
+    label = cols(0, 8, torch.int64).reshape(-1)
+    ints = cols(8, 8 + 4 * num_int, torch.float32)
+    cats = cols(8 + 4 * num_int, RECORD_BYTES, torch.int64)
     return {"int_features": ints, "cat_features": cats}, label
 
 
