@@ -293,7 +293,20 @@ def _is_record_file(path: str) -> bool:
         return fh.read(len(RECORD_MAGIC)) == RECORD_MAGIC
 
 
-def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder: bool):
+def _batch_ranges(n: int, batch_size: int, rank: int, world: int, drop_remainder: bool):
+    """Record ranges [s, e) of the batches rank `rank` of `world` reads: batch k of the file goes to rank k mod world
+    (data-parallel replicas see disjoint batches, no exchange).  With drop_remainder the ranks also get EQUAL batch
+    counts — a trailing group of fewer than `world` batches is dropped — so collectives in the step stay matched."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    total = n // batch_size if drop_remainder else -(-n // batch_size)
+    if drop_remainder:
+        total -= total % world
+    for k in range(rank, total, world):
+        yield k * batch_size, min((k + 1) * batch_size, n)
+
+
+def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder: bool, rank: int = 0, world: int = 1):
     size = os.path.getsize(path) - RECORD_HEADER
     if size < 0 or size % RECORD_BYTES:
         raise CriteoFormatError(f"{path}: truncated record file")
@@ -303,10 +316,7 @@ def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder:
     records = np.memmap(path, dtype=np.uint8, mode="r", offset=RECORD_HEADER, shape=(n, RECORD_BYTES))
     stage = [torch.empty(batch_size, RECORD_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     done = [None, None]                                       # the H2D copy that last read each staging buffer
-    for k, s in enumerate(range(0, n, batch_size)):
-        e = min(s + batch_size, n)
-        if e - s < batch_size and drop_remainder:
-            return
+    for k, (s, e) in enumerate(_batch_ranges(n, batch_size, rank, world, drop_remainder)):
         buf = stage[k % 2]
         if done[k % 2] is not None:
             done[k % 2].synchronize()
@@ -318,18 +328,24 @@ def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder:
 
 
 def read_tfrecord(tfrecord_file: str, vocab: Optional[Vocab] = None, batch_size: int = 1024, *, device=None,
-                  chunk_bytes: int = 1 << 28, drop_remainder: bool = False) -> Iterator[Tuple[dict, torch.Tensor]]:
+                  chunk_bytes: int = 1 << 28, drop_remainder: bool = False, rank: int = 0,
+                  world: int = 1) -> Iterator[Tuple[dict, torch.Tensor]]:
     """ctr/tfrecord_io.py:78-96 followed by `.batch(batch_size)` (ctr/train.py:59-61): yields
     ({'int_features': f32[B,13], 'cat_features': i64[B,26]}, label i64[B]) in file order.
 
     `tfrecord_file` is either a record file written by `write_tfrecord`, or the RAW Criteo text itself (then `vocab`
-    is required and the text is parsed on the fly: `read_tfrecord(write_tfrecord(raw))` without the file in between)."""
+    is required and the text is parsed on the fly: `read_tfrecord(write_tfrecord(raw))` without the file in between).
+    One process per GPU: rank r of `world` gets batches r, r + world, ... of a record file (no exchange between the
+    replicas); raw text is a single-process format."""
     dev = _device(device)
+    batch_size = int(batch_size)
     if _is_record_file(tfrecord_file):
-        yield from _read_records(tfrecord_file, int(batch_size), dev, drop_remainder)
+        yield from _read_records(tfrecord_file, batch_size, dev, drop_remainder, rank, world)
         return
     if vocab is None:
         raise ValueError("reading raw Criteo text needs the vocabulary (build_vocab)")
+    if world != 1:
+        raise NotImplementedError("raw text is read by one process; convert it once with write_tfrecord for several ranks")
     carry = None
     for block in _device_chunks(tfrecord_file, chunk_bytes, dev):
         features, label = parse(block, vocab)

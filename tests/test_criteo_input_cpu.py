@@ -214,3 +214,22 @@ def test_host_parse_int_matches_python_int(host):
     for text in ["", "-", "+", "12x", "x12", "1 2", "1.5", "--1", "1-", "12345678x", "1" * 19, "\t1", "1e3", "0x10", ":", "/"]:
         out = C.c_int64(0)
         assert host.t_parse_int(text.encode(), len(text), C.byref(out)) == 0, text
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("n,B", [(0, 4), (3, 4), (64, 8), (70, 8), (1000, 64)])
+def test_batch_ranges_shard_the_file_across_ranks(n, B, world):
+    """recommender_b200.tfrecord_io._batch_ranges: the ranks' batches are disjoint, cover the file in order, and with
+    drop_remainder every rank sees the same number of full batches (matched collectives in a data-parallel step)."""
+    from recommender_b200.tfrecord_io import _batch_ranges
+    per_rank = [list(_batch_ranges(n, B, r, world, False)) for r in range(world)]
+    merged = sorted(x for pr in per_rank for x in pr)
+    assert merged == [(s, min(s + B, n)) for s in range(0, n, B)]
+    for r, pr in enumerate(per_rank):
+        assert all((s // B) % world == r for s, _ in pr)
+    full = [list(_batch_ranges(n, B, r, world, True)) for r in range(world)]
+    assert len({len(f) for f in full}) == 1
+    assert all(e - s == B for f in full for s, e in f)
+    assert sum(len(f) for f in full) == (n // B) - (n // B) % world
+    with pytest.raises(ValueError):
+        list(_batch_ranges(n, B, world, world, False))

@@ -213,6 +213,13 @@ def test_record_file_round_trip(io, g, tmp_path):
             assert torch.equal(ints, direct[0]["int_features"])                      # stored bits = parsed bits
             assert cats.dtype == torch.int64 and ints.dtype == torch.float32 and label.dtype == torch.int64
         assert len(list(io.read_tfrecord(str(out), batch_size=10, drop_remainder=True))) == n // 10
+        # one process per GPU: rank r of 2 reads batches r, r + 2, ... — disjoint, together the whole file
+        halves = [list(io.read_tfrecord(str(out), batch_size=16, rank=r, world=2)) for r in (0, 1)]
+        order = [halves[k % 2][k // 2] for k in range(len(halves[0]) + len(halves[1]))]
+        np.testing.assert_array_equal(torch.cat([b[1] for b in order]).cpu().numpy(), g[f"{split}_label"])
+        np.testing.assert_array_equal(torch.cat([b[0]["cat_features"] for b in order]).cpu().numpy(), g[f"{split}_cat_features"])
+        even = [list(io.read_tfrecord(str(out), batch_size=16, rank=r, world=2, drop_remainder=True)) for r in (0, 1)]
+        assert len(even[0]) == len(even[1]) == (n // 16) // 2
     (tmp_path / "bad.tfrecord").write_bytes((tmp_path / "test.tfrecord").read_bytes()[:-5])
     with pytest.raises(io.CriteoFormatError):
         list(io.read_tfrecord(str(tmp_path / "bad.tfrecord"), batch_size=4))
