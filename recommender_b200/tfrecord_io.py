@@ -17,6 +17,8 @@ torch only carries the device memory; there is no CPU path (a missing library ra
 from __future__ import annotations
 
 import os
+import queue
+import threading
 from typing import Iterator, Optional, Tuple
 
 import numpy as np
@@ -306,7 +308,28 @@ def _batch_ranges(n: int, batch_size: int, rank: int, world: int, drop_remainder
         yield k * batch_size, min((k + 1) * batch_size, n)
 
 
+def _pinned(*shape) -> torch.Tensor:
+    return torch.empty(*shape, dtype=torch.uint8, pin_memory=True)
+
+
+class _CopyDone:
+    """Marks the point on the current stream after which a staging buffer may be overwritten."""
+
+    def __init__(self):
+        self._ev = torch.cuda.Event()
+        self._ev.record()
+
+    def wait(self):
+        self._ev.synchronize()
+
+
+_STAGES = 3       # pinned staging buffers of the record reader: one being filled, one in flight to the GPU, one spare
+
+
 def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder: bool, rank: int = 0, world: int = 1):
+    """Record file -> batches.  A reader thread copies each batch's records from the page cache (np.memmap) into a
+    pinned staging buffer while the caller's thread issues the H2D copy of the previous one and splits it on the GPU;
+    a buffer goes back to the reader once the copy that read it has completed."""
     size = os.path.getsize(path) - RECORD_HEADER
     if size < 0 or size % RECORD_BYTES:
         raise CriteoFormatError(f"{path}: truncated record file")
@@ -314,17 +337,45 @@ def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder:
     if n == 0:
         return
     records = np.memmap(path, dtype=np.uint8, mode="r", offset=RECORD_HEADER, shape=(n, RECORD_BYTES))
-    stage = [torch.empty(batch_size, RECORD_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    done = [None, None]                                       # the H2D copy that last read each staging buffer
-    for k, (s, e) in enumerate(_batch_ranges(n, batch_size, rank, world, drop_remainder)):
-        buf = stage[k % 2]
-        if done[k % 2] is not None:
-            done[k % 2].synchronize()
-        buf.numpy()[: e - s] = records[s:e]
-        raw = buf[: e - s].to(dev, non_blocking=True)
-        done[k % 2] = torch.cuda.Event()
-        done[k % 2].record()
-        yield _split_records(raw)
+    stage = [_pinned(batch_size, RECORD_BYTES) for _ in range(_STAGES)]
+    free_q: "queue.Queue" = queue.Queue()
+    full_q: "queue.Queue" = queue.Queue()
+    for i in range(_STAGES):
+        free_q.put(i)
+
+    def reader():
+        try:
+            for s, e in _batch_ranges(n, batch_size, rank, world, drop_remainder):
+                i = free_q.get()
+                if i is None:                                 # the consumer went away
+                    return
+                stage[i].numpy()[: e - s] = records[s:e]      # numpy releases the GIL for the copy
+                full_q.put((i, e - s))
+            full_q.put(None)
+        except BaseException as exc:                          # surfaces in the consumer's thread
+            full_q.put(exc)
+
+    thread = threading.Thread(target=reader, name="rb-record-reader", daemon=True)
+    thread.start()
+    in_flight = []                                            # (buffer, copy-done marker), oldest first
+    try:
+        while True:
+            item = full_q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            i, rows = item
+            raw = stage[i][:rows].to(dev, non_blocking=True)
+            in_flight.append((i, _CopyDone()))
+            if len(in_flight) >= _STAGES - 1:
+                j, done = in_flight.pop(0)
+                done.wait()
+                free_q.put(j)
+            yield _split_records(raw)
+    finally:
+        free_q.put(None)
+        thread.join(timeout=5)
 
 
 def read_tfrecord(tfrecord_file: str, vocab: Optional[Vocab] = None, batch_size: int = 1024, *, device=None,

@@ -140,6 +140,23 @@ def main():
         ms = (time.perf_counter() - t0) * 1e3
         assert seen == n_lines
         res["read_tfrecord_file_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3, h2d_bytes=nbytes, batch=65536)
+        # the same content as a preprocessed record file (write_tfrecord once, read every epoch)
+        rec = os.path.join(tmp, "day.tfrecord")
+        t0 = time.perf_counter()
+        assert io.write_tfrecord(path, rec, vocab) == n_lines
+        res["write_tfrecord_wall"] = dict(ms=(time.perf_counter() - t0) * 1e3, record_bytes=io.RECORD_BYTES)
+        for _ in io.read_tfrecord(rec, batch_size=65536):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seen = 0
+        for feats, lab in io.read_tfrecord(rec, batch_size=65536):
+            seen += lab.numel()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        assert seen == n_lines
+        res["read_tfrecord_records_wall"] = dict(ms=ms, lines_per_s=n_lines / ms * 1e3, h2d_bytes=n_lines * io.RECORD_BYTES,
+                                                 host_gbs=n_lines * io.RECORD_BYTES / ms / 1e6, batch=65536)
         t0 = time.perf_counter()
         v2 = io.build_vocab(path)
         torch.cuda.synchronize()

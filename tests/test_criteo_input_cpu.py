@@ -233,3 +233,46 @@ def test_batch_ranges_shard_the_file_across_ranks(n, B, world):
     assert sum(len(f) for f in full) == (n // B) - (n // B) % world
     with pytest.raises(ValueError):
         list(_batch_ranges(n, B, world, world, False))
+
+
+def test_record_reader_thread_on_cpu(tmp_path, monkeypatch):
+    """recommender_b200.tfrecord_io._read_records with its two CUDA touch points (pinned allocation, copy-done event)
+    replaced: the reader thread, the staging-buffer hand-back and early close of the generator, without a GPU."""
+    import threading
+    import torch
+    from recommender_b200 import tfrecord_io as io
+
+    class Done:
+        def wait(self):
+            pass
+    monkeypatch.setattr(io, "_pinned", lambda *shape: torch.empty(*shape, dtype=torch.uint8))
+    monkeypatch.setattr(io, "_CopyDone", Done)
+    n = 1003
+    g = torch.Generator().manual_seed(0)
+    label = torch.randint(0, 2, (n,), generator=g)
+    ints = torch.randn(n, 13, generator=g)
+    cats = torch.randint(0, 1 << 40, (n, 26), generator=g)
+    raw = torch.cat([label.view(torch.uint8).reshape(n, 8), ints.view(torch.uint8).reshape(n, 52),
+                     cats.view(torch.uint8).reshape(n, 208)], dim=1)
+    path = tmp_path / "x.tfrecord"
+    path.write_bytes(io._record_header() + raw.numpy().tobytes())
+    assert io._is_record_file(str(path))
+    cpu = torch.device("cpu")
+    for B in (1, 7, 64, 1003, 5000):
+        batches = list(io._read_records(str(path), B, cpu, False))
+        assert [len(b[1]) for b in batches] == [B] * (n // B) + ([n % B] if n % B else [])
+        assert torch.equal(torch.cat([b[1] for b in batches]), label)
+        assert torch.equal(torch.cat([b[0]["cat_features"] for b in batches]), cats)
+        assert torch.equal(torch.cat([b[0]["int_features"] for b in batches]), ints)
+    parts = [list(io._read_records(str(path), 16, cpu, False, r, 4)) for r in range(4)]
+    order = [parts[k % 4][k // 4] for k in range(sum(len(p) for p in parts))]
+    assert torch.equal(torch.cat([b[1] for b in order]), label)
+    # closing the generator early stops the reader thread
+    before = threading.active_count()
+    it = io._read_records(str(path), 8, cpu, False)
+    next(it)
+    it.close()
+    assert threading.active_count() <= before
+    (tmp_path / "bad").write_bytes(io._record_header() + b"123")
+    with pytest.raises(io.CriteoFormatError):
+        list(io._read_records(str(tmp_path / "bad"), 4, cpu, False))
