@@ -29,6 +29,16 @@ constexpr int kParseWarps = 8;
 
 __device__ __forceinline__ unsigned newline_mask(uint32_t w) { return __vcmpeq4(w, 0x0A0A0A0Au) & 0x01010101u; }
 
+// 16-bit mask of the tab bytes of v (bit j = byte j).  Per word: 0xFF where the byte matches, one bit per byte kept,
+// and a multiply gathers bits 0, 8, 16, 24 into one nibble (no two partial products share a bit, so no carries).
+__device__ __forceinline__ uint32_t tab_mask16(const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m |= (((__vcmpeq4(w[k], 0x09090909u) & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+  return m;
+}
+
 // newline bytes among the first `valid` (1..16) bytes of v
 __device__ __forceinline__ int count_newlines(const uint4& v, int valid) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -138,21 +148,37 @@ __global__ void __launch_bounds__(kParseWarps * 32) parse_lines_kernel(ParseArgs
     const int shift = static_cast<int>(beg - abeg);
     const int n16 = (shift + len + 15) >> 4;
     __syncwarp();                                   // the previous line's readers are done with buf / tab
-    for (int k = lane; k < n16; k += 32)
-      reinterpret_cast<uint4*>(buf)[k] = __ldg(reinterpret_cast<const uint4*>(a.text + abeg) + k);
-    __syncwarp();
+    // Each lane moves 16 bytes to shared memory and, from the same registers, finds the tabs among them; a warp
+    // prefix sum numbers them in line order.  Tab k closes column k.
     const uint8_t* line = buf + shift;
-    // ---- tab k closes column k
     int ntabs = 0;
-    for (int base = 0; base < len; base += 32) {
-      const int pos = base + lane;
-      const bool t = pos < len && line[pos] == '\t';
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, t);
-      if (t) {
-        const int k = ntabs + __popc(m & ((1u << lane) - 1u));
-        if (k < kCols) tab[k] = static_cast<int16_t>(pos);
+    for (int k0 = 0; k0 < n16; k0 += 32) {
+      const int k = k0 + lane;
+      uint32_t tm = 0;                              // bit j: byte j of this lane's 16 is a tab inside the line
+      if (k < n16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.text + abeg) + k);
+        reinterpret_cast<uint4*>(buf)[k] = v;
+        tm = tab_mask16(v);
+        const int lo = shift - 16 * k;              // bytes before the line (first 16 only) ...
+        const int hi = shift + len - 16 * k;        // ... and behind it are not part of it
+        if (lo > 0) tm &= ~((1u << lo) - 1u);
+        if (hi < 16) tm &= (1u << (hi > 0 ? hi : 0)) - 1u;
       }
-      ntabs += __popc(m);
+      const int c = __popc(tm);
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int idx = ntabs + incl - c;
+      while (tm != 0) {
+        const int j = __ffs(tm) - 1;
+        tm &= tm - 1;
+        if (idx < kCols) tab[idx] = static_cast<int16_t>(16 * k + j - shift);
+        ++idx;
+      }
+      ntabs += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     __syncwarp();
     const bool short_line = ntabs < kCols - 1;      // line.split('\t')[39] raises IndexError in the reference

@@ -8,7 +8,7 @@ copied to HBM once and every step of that chain is a kernel of librecsys_b200.so
     for features, label in read_tfrecord(raw_file, vocab, batch_size):
         model(features)                                    # {'int_features' f32[B,13], 'cat_features' i64[B,26]}
 
-    write_tfrecord(raw_file, output_file, vocab)           # optional, once: 268-byte binary records instead of text
+    write_tfrecord(raw_file, output_file, vocab)           # optional, once: 160-byte binary records instead of text
     for features, label in read_tfrecord(output_file, batch_size=65536): ...
 
 `read_tfrecord` takes the raw text or the record file.  The TFRecord/protobuf container is not reproduced, its content is.
@@ -244,55 +244,70 @@ def build_vocab(train_file: str, *, device=None, chunk_bytes: int = 1 << 30, min
 
 
 # ---- the preprocessed record file (stands in for the TFRecord of ctr/tfrecord_io.py:38-75) -----------------------------
-# One fixed-size record per line, in file order: label i64 | int_features f32[13] | cat_features i64[26] = 268 bytes,
+# One fixed-size record per line, in file order: label i32 | int_features f32[13] | cat_features i32[26] = 160 bytes,
 # behind a 64-byte header.  Same content as the reference's tf.train.Example (two serialized tensors and the label,
-# :66-73), without the protobuf framing.  The host never touches a record: records move disk -> pinned -> HBM as
-# bytes and are split into the three tensors on the GPU.
+# :66-73) without the protobuf framing; ids and labels are stored in 32 bits (a dictionary has fewer than 2^31
+# entries) and widened to the reference's int64 (:82, :88) on the GPU.  The host never touches a record: records move
+# disk -> pinned -> HBM as bytes and are split into the three tensors on the GPU.
 
 RECORD_MAGIC = b"RBCRITEO"
+RECORD_VERSION = 2
 RECORD_HEADER = 64
-RECORD_BYTES = 8 + 4 * num_int + 8 * num_cat
+RECORD_BYTES = 4 + 4 * num_int + 4 * num_cat
 
 
 def _record_header() -> bytes:
-    head = RECORD_MAGIC + np.array([1, num_int, num_cat, RECORD_BYTES], dtype="<i4").tobytes()
+    head = RECORD_MAGIC + np.array([RECORD_VERSION, num_int, num_cat, RECORD_BYTES], dtype="<i4").tobytes()
     return head + b"\0" * (RECORD_HEADER - len(head))
 
 
+def _pack_records(label: torch.Tensor, ints: torch.Tensor, cats: torch.Tensor) -> torch.Tensor:
+    """(label i64[n], int_features f32[n,13], cat_features i64[n,26]) -> uint8[n, 160] on the same device."""
+    n = label.numel()
+    if n and (int(label.abs().max()) >= 2 ** 31 or int(cats.max()) >= 2 ** 31 or int(cats.min()) < 0):
+        raise CriteoFormatError("a label or id does not fit the record file's 32-bit fields")
+    return torch.cat([label.to(torch.int32).reshape(n, 1).view(torch.uint8),
+                      ints.contiguous().view(torch.uint8).reshape(n, 4 * num_int),
+                      cats.to(torch.int32).view(torch.uint8).reshape(n, 4 * num_cat)], dim=1)
+
+
 def _split_records(raw: torch.Tensor):
-    """uint8[n, 268] in HBM -> ({'int_features', 'cat_features'}, label)."""
+    """uint8[n, 160] in HBM -> ({'int_features' f32, 'cat_features' i64}, label i64)."""
     def cols(a: int, b: int, dtype) -> torch.Tensor:
         out = torch.empty(raw.shape[0], b - a, dtype=torch.uint8, device=raw.device)     # fresh, so the dtype view is aligned
         out.copy_(raw[:, a:b])
         return out.view(dtype)
 
-    label = cols(0, 8, torch.int64).reshape(-1)
-    ints = cols(8, 8 + 4 * num_int, torch.float32)
-    cats = cols(8 + 4 * num_int, RECORD_BYTES, torch.int64)
+    label = cols(0, 4, torch.int32).reshape(-1).to(torch.int64)
+    ints = cols(4, 4 + 4 * num_int, torch.float32)
+    cats = cols(4 + 4 * num_int, RECORD_BYTES, torch.int32).to(torch.int64)
     return {"int_features": ints, "cat_features": cats}, label
 
 
 def write_tfrecord(raw_file: str, output_file: str, vocab: Vocab, *, device=None, chunk_bytes: int = 1 << 28) -> int:
     """ctr/tfrecord_io.py:38-75: raw Criteo text -> the preprocessed record file, once, so that every epoch reads
-    268-byte records instead of parsing text.  Returns the number of records."""
+    160-byte records instead of parsing text.  Returns the number of records."""
     dev = _device(device)
     n = 0
     with open(output_file, "wb") as out:
         out.write(_record_header())
         for block in _device_chunks(raw_file, chunk_bytes, dev):
             features, label = parse(block, vocab)
-            rows = label.numel()
-            raw = torch.cat([label.view(torch.uint8).reshape(rows, 8),
-                             features["int_features"].view(torch.uint8).reshape(rows, 4 * num_int),
-                             features["cat_features"].view(torch.uint8).reshape(rows, 8 * num_cat)], dim=1)
-            out.write(raw.cpu().numpy().tobytes())
-            n += rows
+            raw = _pack_records(label, features["int_features"], features["cat_features"])
+            out.write(raw.cpu().numpy())              # the array's buffer goes to the file as is
+            n += label.numel()
     return n
 
 
 def _is_record_file(path: str) -> bool:
     with open(path, "rb") as fh:
-        return fh.read(len(RECORD_MAGIC)) == RECORD_MAGIC
+        head = fh.read(len(RECORD_MAGIC) + 16)
+    if head[: len(RECORD_MAGIC)] != RECORD_MAGIC:
+        return False
+    fields = np.frombuffer(head[len(RECORD_MAGIC):], dtype="<i4")
+    if fields.size != 4 or fields.tolist() != [RECORD_VERSION, num_int, num_cat, RECORD_BYTES]:
+        raise CriteoFormatError(f"{path}: record file of another version / layout")
+    return True
 
 
 def _batch_ranges(n: int, batch_size: int, rank: int, world: int, drop_remainder: bool):

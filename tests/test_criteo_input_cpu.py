@@ -251,9 +251,11 @@ def test_record_reader_thread_on_cpu(tmp_path, monkeypatch):
     g = torch.Generator().manual_seed(0)
     label = torch.randint(0, 2, (n,), generator=g)
     ints = torch.randn(n, 13, generator=g)
-    cats = torch.randint(0, 1 << 40, (n, 26), generator=g)
-    raw = torch.cat([label.view(torch.uint8).reshape(n, 8), ints.view(torch.uint8).reshape(n, 52),
-                     cats.view(torch.uint8).reshape(n, 208)], dim=1)
+    cats = torch.randint(0, 1 << 31, (n, 26), generator=g)
+    raw = io._pack_records(label, ints, cats)
+    assert raw.shape == (n, io.RECORD_BYTES) and io.RECORD_BYTES == 160
+    with pytest.raises(io.CriteoFormatError):
+        io._pack_records(label + 2 ** 31, ints, cats)                       # does not fit the 32-bit field
     path = tmp_path / "x.tfrecord"
     path.write_bytes(io._record_header() + raw.numpy().tobytes())
     assert io._is_record_file(str(path))
@@ -276,3 +278,8 @@ def test_record_reader_thread_on_cpu(tmp_path, monkeypatch):
     (tmp_path / "bad").write_bytes(io._record_header() + b"123")
     with pytest.raises(io.CriteoFormatError):
         list(io._read_records(str(tmp_path / "bad"), 4, cpu, False))
+    (tmp_path / "old").write_bytes(io.RECORD_MAGIC + np.array([1, 13, 26, 268], dtype="<i4").tobytes() + b"\0" * 40)
+    with pytest.raises(io.CriteoFormatError):
+        io._is_record_file(str(tmp_path / "old"))                            # another layout is refused, not misread
+    (tmp_path / "text").write_bytes(b"1\t2\t3\n")
+    assert not io._is_record_file(str(tmp_path / "text"))

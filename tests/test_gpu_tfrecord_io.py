@@ -200,7 +200,7 @@ def test_record_file_round_trip(io, g, tmp_path):
     for path, split in ((train, "train"), (test, "test")):
         out = tmp_path / f"{split}.tfrecord"
         n = io.write_tfrecord(str(path), str(out), vocab, chunk_bytes=20_000)
-        assert n == len(g[f"{split}_label"]) and out.stat().st_size == 64 + 268 * n
+        assert n == len(g[f"{split}_label"]) and out.stat().st_size == 64 + io.RECORD_BYTES * n
         direct = io.parse(io.to_device(path.read_bytes()), vocab)
         for B in (1, 7, 64, 10_000):
             batches = list(io.read_tfrecord(str(out), batch_size=B))
