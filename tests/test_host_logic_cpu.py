@@ -144,3 +144,30 @@ def test_prepare_step_advances_the_counter_exactly_once():
     for t in (1, 2, 3):
         O.adam_dense_param(ref, m, v, g, t)
     np.testing.assert_allclose(a.detach().numpy(), ref, rtol=1e-6, atol=1e-7)
+
+
+def test_keras_style_auc_and_accuracy():
+    """recommender_b200.train.AUC / BinaryAccuracy restate tf.keras.metrics.AUC() / BinaryAccuracy() with their defaults
+    (ctr/train.py:86): 200 thresholds, confusion matrices accumulated over batches, trapezoids over the ROC points."""
+    from recommender_b200.train import AUC, BinaryAccuracy
+    rng = np.random.default_rng(0)
+    y = (rng.random(5000) < 0.3).astype(np.int64)
+    p = np.clip(0.3 * y + rng.random(5000) * 0.7, 0, 1).astype(np.float32)
+    p[:5] = [0.0, 1.0, 0.5, 1 / 199, 198 / 199]                                   # values that sit ON thresholds
+    auc, acc = AUC(), BinaryAccuracy()
+    for s in range(0, 5000, 777):
+        auc.update_state(torch.from_numpy(y[s:s + 777]), torch.from_numpy(p[s:s + 777]))
+        acc.update_state(torch.from_numpy(y[s:s + 777]), torch.from_numpy(p[s:s + 777]))
+    th = np.array([-1e-7] + [(i + 1) / 199 for i in range(198)] + [1 + 1e-7], dtype=np.float32)
+    tpr = np.array([((p > t) & (y == 1)).sum() for t in th], float) / (y == 1).sum()
+    fpr = np.array([((p > t) & (y == 0)).sum() for t in th], float) / (y == 0).sum()
+    ref = ((fpr[:-1] - fpr[1:]) * (tpr[:-1] + tpr[1:]) / 2).sum()
+    assert abs(auc.result() - ref) < 1e-12
+    order = np.argsort(p, kind="stable")
+    ranks = np.empty(5000)
+    ranks[order] = np.arange(1, 5001)
+    n1 = y.sum()
+    exact = (ranks[y == 1].sum() - n1 * (n1 + 1) / 2) / (n1 * (5000 - n1))
+    assert abs(auc.result() - exact) < 5e-3                                       # the 200-threshold curve is close to the exact AUC
+    assert acc.result() == ((p > 0.5) == (y > 0)).mean()
+    assert AUC().result() == 0.0                                                  # no samples: div_no_nan
