@@ -13,5 +13,14 @@ its arithmetic lives in the un-vendored ``tensorflow~=2.2.0`` wheel
 ``tensorflow`` shim (oracle/tf_shim) and their forward outputs + autograd
 gradients are frozen as fixtures in tests/golden/ (tests/golden/make_golden.py).
 The TF-internal pieces (IndexedSlices dedup, Keras Adam/Adagrad, BCE form,
-SURVEY Appendix A) are restated from the published Keras semantics.
+SURVEY Appendix A) are restated from the published Keras semantics; the Adam
+formula and the first-occurrence dedup order are additionally cross-checked
+against two independent implementations of the same definitions that ARE in
+this image (scikit-learn's AdamOptimizer, pandas.factorize:
+tests/test_oracle_golden.py) — known-answer checks, not the reference itself.
+
+PINNED: the input side.  oracle/criteo_oracle.py reproduces bit for bit what
+the reference's own ``build_vocab`` / ``write_tfrecord`` (ctr/tfrecord_io.py,
+imported byte-for-byte under the shim) produce on synthetic Criteo files
+(tests/golden/criteo_tsv.npz, tests/golden/make_golden_criteo.py).
 """

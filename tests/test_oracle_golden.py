@@ -186,3 +186,63 @@ def test_bf16_rounding_matches_torch():
     x = np.random.default_rng(3).normal(size=4096).astype(np.float32)
     ref = torch.tensor(x).to(torch.bfloat16).float().numpy()
     np.testing.assert_array_equal(O.round_bf16(x), ref)
+
+
+# ---- independent cross-checks of the TF-internal restatements --------------------------------------
+# TensorFlow is absent, so these pieces cannot be pinned on the reference's own run.  Two implementations that ARE in
+# this image follow the same published definitions and serve as known-answer checks of the oracle: scikit-learn's
+# AdamOptimizer (Kingma & Ba's "epsilon-hat" form, the one Keras OptimizerV2.Adam uses: alpha_t = lr*sqrt(1-b2^t)/(1-b1^t),
+# var -= alpha_t * m / (sqrt(v) + eps)) and pandas.factorize (uniques in first-occurrence order, as tf.unique).
+
+def test_keras_adam_formula_against_sklearn_adam():
+    from sklearn.neural_network._stochastic_optimizers import AdamOptimizer
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(0, 0.05, size=(37, 16))
+    sk_params = [p0.astype(np.float64).copy()]
+    sk = AdamOptimizer(sk_params, learning_rate_init=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+    p = p0.astype(np.float32).copy()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    for step in range(1, 8):
+        g = rng.normal(0, 1e-2, size=p.shape)
+        sk.update_params(sk_params, [g.astype(np.float64)])
+        O.adam_dense_param(p, m, v, g.astype(np.float32), step)
+        np.testing.assert_allclose(p, sk_params[0], rtol=2e-6, atol=2e-8, err_msg=f"step {step}")   # fp32 vs fp64: a few ULP of 0.05
+
+
+def test_keras_sparse_adam_is_dense_adam_on_the_scattered_gradient():
+    """A.3: Keras Adam._resource_apply_sparse decays m and v and moves var on EVERY row; rows without a gradient see
+    g = 0.  That is dense Adam on the scattered gradient — checked against scikit-learn's Adam over several steps, with
+    duplicate ids (summed first, A.2)."""
+    from sklearn.neural_network._stochastic_optimizers import AdamOptimizer
+    rng = np.random.default_rng(5)
+    V, D = 50, 8
+    W0 = O.init_table(rng, V, D)
+    sk_params = [W0.astype(np.float64).copy()]
+    sk = AdamOptimizer(sk_params, learning_rate_init=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+    W = W0.copy()
+    st = dict(m=np.zeros_like(W), v=np.zeros_like(W))
+    for step in range(1, 6):
+        idx = rng.integers(0, V, size=(12, 3))
+        dE = rng.normal(0, 1e-2, size=(12, 3, D)).astype(np.float32)
+        dense_g = np.zeros((V, D))
+        np.add.at(dense_g, idx.reshape(-1), dE.reshape(-1, D).astype(np.float64))
+        sk.update_params(sk_params, [dense_g])
+        O.sparse_backward_update(W, st, idx, dE, "adam_tf_dense", step=step)
+        np.testing.assert_allclose(W, sk_params[0], rtol=5e-6, atol=2e-8, err_msg=f"step {step}")
+    untouched = np.setdiff1d(np.arange(V), idx.reshape(-1))
+    assert untouched.size and not np.array_equal(W[untouched], W0[untouched])      # rows without a gradient moved too
+
+
+def test_dedup_order_against_pandas_factorize():
+    """A.2: tf.unique returns the unique ids in FIRST-OCCURRENCE order; pandas.factorize has the same contract."""
+    import pandas as pd
+    rng = np.random.default_rng(9)
+    ids = rng.integers(0, 40, size=500).astype(np.int64)
+    vals = rng.normal(0, 1, size=(500, 4)).astype(np.float32)
+    rows, summed = O.dedup_indexed_slices(ids, vals)
+    codes, uniques = pd.factorize(ids)
+    np.testing.assert_array_equal(rows, uniques)
+    ref = np.zeros((uniques.size, 4), np.float32)
+    for k in range(500):                                                          # unsorted_segment_sum, input order
+        ref[codes[k]] += vals[k]
+    np.testing.assert_array_equal(summed, ref)
