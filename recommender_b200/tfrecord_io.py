@@ -327,6 +327,18 @@ def _pinned(*shape) -> torch.Tensor:
     return torch.empty(*shape, dtype=torch.uint8, pin_memory=True)
 
 
+_stage_pool: dict = {}        # (rows, bytes per row) -> idle pinned staging buffers; page-locking costs milliseconds apiece
+
+
+def _take_stages(rows: int, count: int):
+    idle = _stage_pool.setdefault((rows, RECORD_BYTES), [])
+    return [idle.pop() if idle else _pinned(rows, RECORD_BYTES) for _ in range(count)]
+
+
+def _return_stages(rows: int, stages) -> None:
+    _stage_pool.setdefault((rows, RECORD_BYTES), []).extend(stages)
+
+
 class _CopyDone:
     """Marks the point on the current stream after which a staging buffer may be overwritten."""
 
@@ -342,17 +354,16 @@ _STAGES = 3       # pinned staging buffers of the record reader: one being fille
 
 
 def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder: bool, rank: int = 0, world: int = 1):
-    """Record file -> batches.  A reader thread copies each batch's records from the page cache (np.memmap) into a
+    """Record file -> batches.  A reader thread reads each batch's records from the file (page cache) straight into a
     pinned staging buffer while the caller's thread issues the H2D copy of the previous one and splits it on the GPU;
-    a buffer goes back to the reader once the copy that read it has completed."""
+    a buffer goes back to the reader once the copy that read it has completed, and to a pool when the epoch ends."""
     size = os.path.getsize(path) - RECORD_HEADER
     if size < 0 or size % RECORD_BYTES:
         raise CriteoFormatError(f"{path}: truncated record file")
     n = size // RECORD_BYTES
     if n == 0:
         return
-    records = np.memmap(path, dtype=np.uint8, mode="r", offset=RECORD_HEADER, shape=(n, RECORD_BYTES))
-    stage = [_pinned(batch_size, RECORD_BYTES) for _ in range(_STAGES)]
+    stage = _take_stages(batch_size, _STAGES)
     free_q: "queue.Queue" = queue.Queue()
     full_q: "queue.Queue" = queue.Queue()
     for i in range(_STAGES):
@@ -360,12 +371,23 @@ def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder:
 
     def reader():
         try:
-            for s, e in _batch_ranges(n, batch_size, rank, world, drop_remainder):
-                i = free_q.get()
-                if i is None:                                 # the consumer went away
-                    return
-                stage[i].numpy()[: e - s] = records[s:e]      # numpy releases the GIL for the copy
-                full_q.put((i, e - s))
+            with open(path, "rb", buffering=0) as fh:
+                at = -1
+                for s, e in _batch_ranges(n, batch_size, rank, world, drop_remainder):
+                    i = free_q.get()
+                    if i is None:                             # the consumer went away
+                        return
+                    if at != s:
+                        fh.seek(RECORD_HEADER + s * RECORD_BYTES)
+                    view = memoryview(stage[i].numpy()).cast("B")[: (e - s) * RECORD_BYTES]
+                    got = 0
+                    while got < len(view):                    # read() releases the GIL; short reads are legal
+                        k = fh.readinto(view[got:])
+                        if not k:
+                            raise CriteoFormatError(f"{path}: file shrank while it was being read")
+                        got += k
+                    at = e
+                    full_q.put((i, e - s))
             full_q.put(None)
         except BaseException as exc:                          # surfaces in the consumer's thread
             full_q.put(exc)
@@ -391,6 +413,10 @@ def _read_records(path: str, batch_size: int, dev: torch.device, drop_remainder:
     finally:
         free_q.put(None)
         thread.join(timeout=5)
+        for _, done in in_flight:
+            done.wait()
+        if not thread.is_alive():
+            _return_stages(batch_size, stage)
 
 
 def read_tfrecord(tfrecord_file: str, vocab: Optional[Vocab] = None, batch_size: int = 1024, *, device=None,

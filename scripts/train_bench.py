@@ -24,6 +24,7 @@ from recommender_b200.train import train  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lines", type=int, default=1_000_000)
+    ap.add_argument("--only", default="", help="comma-separated configuration tags to run (default: all)")
     a = ap.parse_args()
     block = synth_block(20_000)
     res = {"lines": a.lines}
@@ -43,12 +44,15 @@ def main():
         res["write_tfrecord_s"] = time.perf_counter() - t0
         del vocab
         torch.cuda.empty_cache()
-        for tag, extra in (("dlrm_b1024_reference_defaults", ["--train_batch_size", "1024"]),
-                           ("dlrm_b65536", ["--train_batch_size", "65536"]),
-                           ("dlrm_b65536_emb64", ["--train_batch_size", "65536", "--embedding_size", "64"]),
-                           ("deepfm_b1024_reference_defaults", ["--model_type", "DeepFM", "--train_batch_size", "1024"]),
-                           ("dlrm_b65536_raw_text", ["--train_batch_size", "65536", "--train_file", raw, "--test_file", test_raw,
-                                                     "--vocab", os.path.join(tmp, "vocab.npy")])):
+        configs = [("dlrm_b1024_reference_defaults", ["--train_batch_size", "1024"]),
+                   ("dlrm_b65536", ["--train_batch_size", "65536"]),
+                   ("dlrm_b65536_emb64", ["--train_batch_size", "65536", "--embedding_size", "64"]),
+                   ("deepfm_b1024_reference_defaults", ["--model_type", "DeepFM", "--train_batch_size", "1024"]),
+                   ("dlrm_b65536_raw_text", ["--train_batch_size", "65536", "--train_file", raw, "--test_file", test_raw,
+                                             "--vocab", os.path.join(tmp, "vocab.npy")])]
+        for tag, extra in configs:
+            if a.only and tag not in a.only.split(","):
+                continue
             args = ["--train_file", os.path.join(tmp, "train.tfrecord"), "--test_file", os.path.join(tmp, "test.tfrecord"),
                     "--epochs", "2", "--ckpt_path", os.path.join(tmp, "ckpts")] + extra
             hist = train(args)
