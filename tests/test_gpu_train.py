@@ -35,9 +35,10 @@ def test_train_from_raw_text(files, model_type):
     assert any(k.endswith("embeddings") for k in state)
 
 
-def test_eager_and_record_file_agree_with_each_other(files):
-    """The record file written once by write_tfrecord feeds the same batches as the raw text, and the step launched
-    from Python computes what the captured graph computes (batch 1 aside, which capture applies twice)."""
+def test_record_file_and_raw_text_train_identically(files):
+    """The record file written once by write_tfrecord feeds the same batches as the raw text: two eager runs, one per
+    format, produce the same losses and metrics.  (Graph replay == eager step is tests/test_gpu_models.py's business;
+    the graphed trainer applies its first batch twice while capturing, so whole runs are not comparable.)"""
     from recommender_b200 import tfrecord_io as io
     vocab = io.build_vocab(str(files / "train.txt"))
     for name in ("train", "test"):
@@ -46,8 +47,6 @@ def test_eager_and_record_file_agree_with_each_other(files):
     eager_rec = _run(files, "DLRM", "--no_graph", "--seed", "4", train="train.tfrecord", test="test.tfrecord")
     for a, b in zip(eager_text, eager_rec):
         assert abs(a["loss"] - b["loss"]) <= 1e-6 and abs(a["val_loss"] - b["val_loss"]) <= 1e-6 and abs(a["val_auc"] - b["val_auc"]) <= 1e-6
-    graph = _run(files, "DLRM")
-    assert abs(graph[1]["val_loss"] - eager_text[1]["val_loss"]) < 0.05
 
 
 def test_keras_style_metrics_on_device():
