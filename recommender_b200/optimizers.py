@@ -100,12 +100,18 @@ class Adam(_Optimizer):
         """alpha_t lives in device memory from now on (rb_opt_params.alpha_t_dev), refreshed by prepare_step()."""
         if self._alpha_dev is None:
             self._alpha_dev = torch.zeros(1, dtype=torch.float32, device=device)
-            self._alpha_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            # A ring of pinned slots, one per step in flight: the copy below is asynchronous and a replay loop that does
+            # not read anything back runs many steps ahead of the GPU; a single slot would be overwritten with a later
+            # step's alpha before the DMA of an earlier step has read it.
+            self._alpha_host = torch.zeros(self._ALPHA_SLOTS, dtype=torch.float32).pin_memory()
+
+    _ALPHA_SLOTS = 4096      # far beyond the launches the driver queues ahead
 
     def _refresh_device_scalars(self) -> None:
         if self._alpha_dev is not None:
-            self._alpha_host[0] = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, self.iterations)
-            self._alpha_dev.copy_(self._alpha_host, non_blocking=True)
+            slot = self.iterations % self._ALPHA_SLOTS
+            self._alpha_host[slot] = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, self.iterations)
+            self._alpha_dev.copy_(self._alpha_host[slot:slot + 1], non_blocking=True)
 
     def _sparse_kwargs(self):
         return dict(lr=self.learning_rate, beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon,

@@ -171,3 +171,21 @@ def test_keras_style_auc_and_accuracy():
     assert abs(auc.result() - exact) < 5e-3                                       # the 200-threshold curve is close to the exact AUC
     assert acc.result() == ((p > 0.5) == (y > 0)).mean()
     assert AUC().result() == 0.0                                                  # no samples: div_no_nan
+
+
+def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight():
+    """optimizers.Adam._refresh_device_scalars: alpha_t of step k is staged in pinned slot k mod 4096 before its
+    asynchronous copy to the device, so a replay loop running many steps ahead of the GPU cannot overwrite the value a
+    still-queued copy is going to read (emulated here with plain host tensors)."""
+    opt = Adam()
+    opt._alpha_dev = torch.zeros(1)
+    opt._alpha_host = torch.zeros(opt._ALPHA_SLOTS)
+    seen = {}
+    for k in range(1, opt._ALPHA_SLOTS + 50):
+        opt.iterations = k
+        opt._refresh_device_scalars()
+        slot = k % opt._ALPHA_SLOTS
+        assert float(opt._alpha_dev) == float(opt._alpha_host[slot]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, k)
+        seen[slot] = k
+    assert len(seen) == opt._ALPHA_SLOTS                                          # every slot used before any is reused
+    assert float(opt._alpha_host[5]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, 5)      # untouched since step 5
