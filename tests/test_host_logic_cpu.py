@@ -188,4 +188,5 @@ def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight():
         assert float(opt._alpha_dev) == float(opt._alpha_host[slot]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, k)
         seen[slot] = k
     assert len(seen) == opt._ALPHA_SLOTS                                          # every slot used before any is reused
-    assert float(opt._alpha_host[5]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, 5)      # untouched since step 5
+    assert float(opt._alpha_host[60]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, 60)    # untouched for 4096 steps
+    assert float(opt._alpha_host[5]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, opt._ALPHA_SLOTS + 5)   # reused one lap later
