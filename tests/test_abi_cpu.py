@@ -132,3 +132,37 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fresh.load()
+
+
+def test_argument_validation_of_the_input_side_entry_points(cuda_lib):
+    """rb_criteo_* / rb_vocab_*: bad arguments come back as status codes before anything is launched."""
+    L = cuda_lib
+    buf = (C.c_uint8 * 4096)()
+    p = (C.addressof(buf) + 255) & ~255                      # 256-byte aligned inside the buffer
+    out = (C.c_int64 * 64)()
+    q = C.addressof(out)
+    # line index
+    assert L.rb_criteo_index_workspace_bytes(1 << 20) > 0
+    assert L.rb_criteo_index_workspace_bytes(1 << 31) == 0                       # chunks stay below 2 GiB
+    assert L.rb_criteo_index_lines(p, 1 << 31, 8, q, q, p, 1 << 20, None) == -1
+    assert L.rb_criteo_index_lines(p, 100, 8, q, None, p, 1 << 20, None) == -1   # num_lines_dev is required
+    assert L.rb_criteo_index_lines(p + 1, 100, 8, q, q, p, 1 << 20, None) == -3  # text must be 16-byte aligned
+    assert L.rb_criteo_index_lines(p, 100, 8, q, q, p, 16, None) == -4 and b"workspace" in L.rb_last_error()
+    assert L.rb_criteo_index_lines(p, 100, 8, q, q, p + 8, 1 << 20, None) == -3  # workspace alignment
+    # parse
+    assert L.rb_criteo_parse(p, 100, q, 0, q, q, q, None, None, None, 0, None, None) == 0          # no lines: nothing to do
+    assert L.rb_criteo_parse(p, 100, q, 2, q, q, None, None, None, None, 0, None, None) == -1      # neither keys nor ids asked for
+    assert L.rb_criteo_parse(p, 100, q, 2, q, q, None, q, None, None, 0, None, None) == -1         # ids need the table
+    assert L.rb_criteo_parse(p, 100, q, 2, q, q, None, q, q, q, 1000, None, None) == -1            # capacity not a power of two
+    assert L.rb_criteo_parse(p + 4, 100, q, 2, q, q, q, None, None, None, 0, None, None) == -3
+    assert L.rb_criteo_parse(None, 100, q, 2, q, q, q, None, None, None, 0, None, None) == -1
+    # dictionary
+    assert L.rb_vocab_build_workspace_bytes(1000) > 1000 * 8 * 2
+    assert L.rb_vocab_build_workspace_bytes(1 << 31) == 0
+    assert L.rb_vocab_build(q, 1000, 10, q, 10, q, p, 64, None) == -4
+    assert L.rb_vocab_build(q, 1000, -1, q, 10, q, p, 1 << 30, None) == -1
+    assert L.rb_vocab_build(None, 1000, 10, q, 10, q, p, 1 << 30, None) == -1
+    assert L.rb_vocab_table_build(q, 10, q, q, 10, None) == -1                    # capacity must be a power of two ...
+    assert L.rb_vocab_table_build(q, 16, q, q, 16, None) == -1                    # ... and leave an empty slot
+    assert L.rb_vocab_lookup(q, 0, q, q, 16, q, None) == 0
+    assert L.rb_vocab_lookup(q, 4, q, q, 12, q, None) == -1
