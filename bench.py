@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: rows/gradients read by the kernels over NVLink peer memory (p2p) or exchanged with NCCL all-to-alls")
     ap.add_argument("--ring", type=int, default=8, help="distinct synthetic batches cycled through")
+    ap.add_argument("--collapse-mlp", action="store_true",
+                    help="single GPU, opt-in: evaluate each tower (linear hidden layers, ctr/layers.py:8) as one affine map "
+                         "(layers._CollapsedAffineFn); the default runs the layers one GEMM at a time like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--criteo-tb", action="store_true",
@@ -204,6 +207,8 @@ def workload_config(args, world):
                 global_batch=args.batch * world, tables=args.tables, rows_per_table=args.rows_per_table, emb_dim=args.emb_dim,
                 bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
                 sparse_optimizer="adam_lazy",
+                mlp_evaluation="collapsed affine map per tower (opt-in)" if getattr(args, "collapse_mlp", False) and world == 1
+                else "layer by layer",
                 parallelism="single GPU" if world == 1 else (
                     f"row-wise sharded tables x{world}, rows and gradient rows read by the kernels over NVLink peer memory + data-parallel MLPs"
                     if args.exchange == "p2p" else f"{args.sharding}-wise sharded tables x{world}, NCCL all-to-all + data-parallel MLPs"),
@@ -300,7 +305,8 @@ def run_b200(args):
     cd = torch.bfloat16 if args.mlp_dtype == "bf16" else None
     gen = torch.Generator(device=dev).manual_seed(4)
     if world == 1:
-        model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen)
+        model = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
+                     collapse_linear=args.collapse_mlp)
     elif peer_memory_usable(args, dev):
         from recommender_b200.p2p import P2PShardedDLRM
         model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,

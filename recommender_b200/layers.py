@@ -396,6 +396,69 @@ class _LinearBF16Fn(torch.autograd.Function):
         return dx, dW, db, None, None
 
 
+class _CollapsedAffineFn(torch.autograd.Function):
+    """The affine part of an MLP whose hidden layers are linear (ctr/layers.py:8 builds them without activation):
+
+        z = ((x W1 + b1) W2 + b2) ... Wn + bn  =  x A_n + c_n,     A_k = W1 ... Wk,   c_k = c_{k-1} W_k + b_k.
+
+    Opt-in (MLP(collapse_linear=True)); the default path runs the layers one GEMM at a time like the reference.  Only
+    three passes touch the batch: z = x A_n + c_n, G = x^T dz (+ s = 1^T dz) and dx = dz A_n^T.  Every layer's own
+    gradient follows from G and s in weight space, with S_k = W_{k+1} ... W_n:
+
+        dW_k = (A_{k-1}^T G + c_{k-1} s^T) S_k^T,      db_k = S_k s            (A_0 = I, c_0 = 0, S_n = I)
+
+    which is H_{k-1}^T (dz S_k^T) with H_{k-1} = x A_{k-1} + 1 c_{k-1}^T written out.  Same function, same parameters,
+    same gradients in exact arithmetic; in floating point the products are associated differently (weight-space
+    products in fp32).  x may be bf16, zero-padded to Kp columns, with column in_dim set to 1.0 (ones_col): the padded
+    rows of A_n are zero, so the pads do not contribute, and row in_dim of x^T dz is s."""
+
+    @staticmethod
+    def forward(ctx, x, in_dim, need_dx, ones_col, *params):
+        Ws, bs = params[0::2], params[1::2]
+        A, c = [Ws[0]], [bs[0]]
+        for W, b in zip(Ws[1:], bs[1:]):
+            A.append(A[-1] @ W)
+            c.append(torch.addmv(b, W.t(), c[-1]))
+        Kp = x.shape[1]
+        Ap = A[-1]
+        if Kp != in_dim:
+            Ap = torch.zeros(Kp, Ap.shape[1], dtype=Ap.dtype, device=Ap.device)
+            Ap[:in_dim] = A[-1]
+        Ax = Ap.to(x.dtype)
+        z = torch.addmm(c[-1].to(x.dtype), x, Ax)
+        ctx.save_for_backward(x, Ax, *A[:-1], *c[:-1], *Ws)
+        ctx.n, ctx.in_dim, ctx.need_dx, ctx.ones_col = len(Ws), in_dim, need_dx, bool(ones_col) and Kp > in_dim
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        x, Ax = saved[0], saved[1]
+        A, c, Ws = saved[2:2 + n - 1], saved[2 + n - 1:2 + 2 * (n - 1)], saved[2 + 2 * (n - 1):]
+        dz = dz.contiguous()
+        if dz.is_cuda:
+            G_full = torch.mm(x.t(), dz, out_dtype=torch.float32)                # fp32 accumulate AND fp32 result
+        else:
+            G_full = torch.mm(x.t(), dz).float()
+        G = G_full[: ctx.in_dim]
+        if ctx.ones_col:
+            s = G_full[ctx.in_dim]
+        elif dz.is_cuda and dz.shape[1] % 8 == 0:
+            s = ops.colsum(dz)
+        else:
+            s = dz.float().sum(0)
+        dx = torch.mm(dz, Ax.t()) if ctx.need_dx else None
+        grads = [None] * (2 * n)
+        S = None                                                                # S_k, starting from S_n = I
+        for k in range(n - 1, -1, -1):
+            left = G if k == 0 else torch.addmm(torch.outer(c[k - 1], s), A[k - 1].t(), G)
+            grads[2 * k] = left if S is None else left @ S.t()
+            grads[2 * k + 1] = s.clone() if S is None else S @ s
+            S = Ws[k] if S is None else Ws[k] @ S
+        return (dx, None, None, None, *grads)
+
+
 class MLP(nn.Module):
     """ctr/layers.py:5-14: Dense layers whose HIDDEN layers are linear; only the last layer has
     `final_activation` (None | 'relu' | 'sigmoid').  Kernels are [in, units] Glorot-uniform, biases
@@ -408,8 +471,9 @@ class MLP(nn.Module):
     to a multiple of 8 (what the fused interaction kernel emits)."""
 
     def __init__(self, units: Sequence[int], final_activation=None, *, compute_dtype: Optional[torch.dtype] = None,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, collapse_linear: bool = False):
         super().__init__()
+        self.collapse_linear = bool(collapse_linear)     # opt-in: evaluate the linear stack as ONE affine map (_CollapsedAffineFn)
         if final_activation not in (None, "relu", "sigmoid"):
             raise ValueError(final_activation)
         if compute_dtype not in (None, torch.float32, torch.bfloat16):
@@ -454,8 +518,11 @@ class MLP(nn.Module):
         kernel does that), which lets the first layer read its bias gradient off the weight-gradient GEMM."""
         if len(self.kernels) == 0:
             self.build(x.shape[-1], x.device)
+        collapse = self.collapse_linear and len(self.kernels) >= 2
         if self.compute_dtype is None:
-            last = len(self.kernels) - 1
+            if collapse:
+                flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
+                return self._activate(_CollapsedAffineFn.apply(x.float(), self.in_dim, x.requires_grad, False, *flat))
             for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
                 x = torch.addmm(b, x.float(), W)
             return self._activate(x)
@@ -473,6 +540,9 @@ class MLP(nn.Module):
                 xp[:, self.in_dim] = 1.0              # ones column: the bias gradient falls out of the dW GEMM
                 x = xp
                 ones_col = True
+        if collapse:
+            flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
+            return self._activate(_CollapsedAffineFn.apply(x, self.in_dim, need_dx, ones_col, *flat))
         for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
             x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0, ones_col and i == 0)
         return self._activate(x)

@@ -21,10 +21,10 @@ class DeepFM(nn.Module):
 
     def __init__(self, embedding_size: int, vocab_size: int, num_int_fea: int, num_cat_fea: int, mlp_units: Sequence[int],
                  *, num_tables: int = 1, fused: bool = True, device=None, compute_dtype: Optional[torch.dtype] = None,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, collapse_linear: bool = False):
         super().__init__()
         self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :10
-        self.mlp = MLP(mlp_units, None, compute_dtype=compute_dtype, generator=generator)                                      # :11
+        self.mlp = MLP(mlp_units, None, compute_dtype=compute_dtype, generator=generator, collapse_linear=collapse_linear)     # :11
         self.num_int_fea, self.num_cat_fea, self.fused = num_int_fea, num_cat_fea, fused
 
     def logits(self, inputs):
@@ -52,13 +52,18 @@ class DLRM(nn.Module):
 
     def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
                  num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, fused: bool = True, device=None,
-                 compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None):
+                 compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
+                 collapse_linear: bool = False):
         super().__init__()
         if bottom_mlp_units[-1] != embedding_size:
             # ctr/model.py:52,55: the concat and the shape-asserting reshape need equal widths
             raise ValueError("bottom_mlp_units[-1] must equal embedding_size")
-        self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator)      # :38
-        self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)         # :39
+        # collapse_linear (opt-in): the hidden layers are linear (ctr/layers.py:8), so each tower is one affine map
+        # followed by its last activation; layers._CollapsedAffineFn evaluates it that way, gradients per layer intact
+        self.bottom_mlp = MLP(bottom_mlp_units, "relu", compute_dtype=compute_dtype, generator=generator,
+                              collapse_linear=collapse_linear)                                                 # :38
+        self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator,
+                           collapse_linear=collapse_linear)                                                    # :39
         self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :42
         self.interaction = DotInteraction(False, True)                                                          # :43
         self.num_cat_fea, self.num_int_fea, self.embedding_size, self.fused = num_cat_fea, num_int_fea, embedding_size, fused

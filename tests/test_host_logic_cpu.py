@@ -190,3 +190,57 @@ def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight():
     assert len(seen) == opt._ALPHA_SLOTS                                          # every slot used before any is reused
     assert float(opt._alpha_host[60]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, 60)    # untouched for 4096 steps
     assert float(opt._alpha_host[5]) == ops.adam_alpha_t(1e-3, 0.9, 0.999, opt._ALPHA_SLOTS + 5)   # reused one lap later
+
+
+@pytest.mark.parametrize("units,act,in_dim", [([512, 256, 64], "relu", 13), ([512, 256, 1], "sigmoid", 793), ([32, 1], None, 429),
+                                              ([24, 16, 8, 4], "relu", 10)])
+def test_collapsed_affine_mlp_matches_the_layerwise_oracle(units, act, in_dim):
+    """MLP(collapse_linear=True): the linear hidden layers (ctr/layers.py:8) make each tower ONE affine map followed by
+    the last activation; output, input gradient and every layer's own dW / db must equal the oracle's layer-by-layer
+    forward / backward to fp32 re-association accuracy."""
+    rng = np.random.default_rng(in_dim)
+    layers = O.init_mlp(rng, in_dim, units)
+    layers = [(W, rng.normal(0, 0.1, size=b.shape).astype(np.float32)) for W, b in layers]       # non-zero biases
+    x = rng.normal(0, 0.5, size=(129, in_dim)).astype(np.float32)
+    dy = rng.normal(size=(129, units[-1])).astype(np.float32)
+    y_ref, acts = O.mlp_forward(x, layers, act)
+    dx_ref, grads_ref = O.mlp_backward(dy, acts, layers, act)
+    mlp = MLP(units, act, collapse_linear=True)
+    mlp.load_arrays(layers, "cpu")
+    xt = torch.tensor(x, requires_grad=True)
+    y = mlp(xt)
+    (y * torch.tensor(dy)).sum().backward()
+
+    def close(a, b):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5 * max(np.abs(b).max(), 1e-6))
+    close(y.detach().numpy(), y_ref)
+    close(xt.grad.numpy(), dx_ref)
+    for W, b, (dW, db) in zip(mlp.kernels, mlp.biases, grads_ref):
+        close(W.grad.numpy(), dW)
+        close(b.grad.numpy(), db)
+
+
+def test_collapsed_affine_mlp_bf16_path_with_padding_and_ones_column():
+    """The bf16 form the fused interaction kernel feeds: input padded to a multiple of 8 columns, pad column in_dim = 1.
+    The padded rows of the collapsed kernel are zero, and the bias-gradient vector s is read off row in_dim of x^T dz.
+    No worse than the layer-by-layer bf16 path against the fp32 oracle."""
+    rng = np.random.default_rng(7)
+    in_dim, units = 13, [64, 32, 8]
+    layers = O.init_mlp(rng, in_dim, units)
+    layers = [(W, rng.normal(0, 0.1, size=b.shape).astype(np.float32)) for W, b in layers]
+    x = rng.normal(0, 0.5, size=(200, in_dim)).astype(np.float32)
+    dy = rng.normal(size=(200, units[-1])).astype(np.float32)
+    y_ref, acts = O.mlp_forward(x, layers, "relu")
+    _, grads_ref = O.mlp_backward(dy, acts, layers, "relu")
+    errs = {}
+    for collapse in (False, True):
+        mlp = MLP(units, "relu", compute_dtype=torch.bfloat16, collapse_linear=collapse)
+        mlp.load_arrays(layers, "cpu")
+        y = mlp(torch.tensor(x))
+        (y * torch.tensor(dy)).sum().backward()
+        e = [np.abs(y.detach().numpy() - y_ref).max() / np.abs(y_ref).max()]
+        for W, b, (dW, db) in zip(mlp.kernels, mlp.biases, grads_ref):
+            e.append(np.abs(W.grad.numpy() - dW).max() / np.abs(dW).max())
+            e.append(np.abs(b.grad.numpy() - db).max() / np.abs(db).max())
+        errs[collapse] = max(e)
+    assert errs[True] < 0.05 and errs[True] <= 1.5 * errs[False]
