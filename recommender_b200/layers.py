@@ -437,15 +437,16 @@ class _CollapsedAffineFn(torch.autograd.Function):
         x, Ax = saved[0], saved[1]
         A, c, Ws = saved[2:2 + n - 1], saved[2 + n - 1:2 + 2 * (n - 1)], saved[2 + 2 * (n - 1):]
         dz = dz.contiguous()
-        if dz.is_cuda:
+        bf16_cuda = dz.is_cuda and dz.dtype == torch.bfloat16                    # the cases _LinearBF16Fn runs on the GPU
+        if bf16_cuda:
             G_full = torch.mm(x.t(), dz, out_dtype=torch.float32)                # fp32 accumulate AND fp32 result
         else:
             G_full = torch.mm(x.t(), dz).float()
         G = G_full[: ctx.in_dim]
         if ctx.ones_col:
             s = G_full[ctx.in_dim]
-        elif dz.is_cuda and dz.shape[1] % 8 == 0:
-            s = ops.colsum(dz)
+        elif bf16_cuda and dz.shape[1] % 8 == 0:
+            s = ops.colsum(dz)                                                    # rb_colsum: deterministic fp32 column sums
         else:
             s = dz.float().sum(0)
         dx = torch.mm(dz, Ax.t()) if ctx.need_dx else None
