@@ -9,6 +9,9 @@ tail -c 600 gpurun_out/bench_zipf.json
 # 2. the same with one shared table (the reference's layout, T = 1): chains of duplicates are ~26x longer
 timeout 200 python bench.py --tables 1 --dist zipf --no-cpu-baseline --no-e2e > gpurun_out/bench_zipf_t1.json 2> gpurun_out/bench_zipf_t1.err
 tail -c 600 gpurun_out/bench_zipf_t1.json
+# 2b. opt-in collapsed towers (linear hidden layers => one affine map): same step, MLP GEMMs replaced by three passes
+timeout 200 python bench.py --collapse-mlp --no-cpu-baseline > gpurun_out/bench_collapse_mlp.json 2> gpurun_out/bench_collapse_mlp.err
+tail -c 600 gpurun_out/bench_collapse_mlp.json
 # 3. why the trainer loop runs at 6.9 ms per step at B = 65536: launch list of one short run (shares, not absolutes)
 timeout 120 python scripts/train_bench.py --lines 1000000 --only dlrm_b65536 > gpurun_out/train_b65536.json 2> gpurun_out/train_b65536.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_train_b65536.csv \
