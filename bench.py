@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--tables", type=int, default=26, choices=[1, 26])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mlp-backend", default="tcgen05", choices=["tcgen05", "cublas"],
+                    help="bf16 towers on the hand-written tcgen05 Dense kernels (csrc/mlp.cu) or on torch / cuBLASLt (the round-1 path, for A/B)")
     ap.add_argument("--sharding", default="row", choices=["row", "table"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: rows/gradients read by the kernels over NVLink peer memory (p2p) or exchanged with NCCL all-to-alls")
@@ -206,6 +208,8 @@ def workload_config(args, world):
     return dict(workload=what,
                 global_batch=args.batch * world, tables=args.tables, rows_per_table=args.rows_per_table, emb_dim=args.emb_dim,
                 bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
+                mlp_backend=("tcgen05 Dense kernels (csrc/mlp.cu)" if getattr(args, "mlp_backend", "tcgen05") == "tcgen05" else "torch / cuBLASLt")
+                if args.mlp_dtype == "bf16" else "torch fp32",
                 sparse_optimizer="adam_lazy",
                 mlp_evaluation="collapsed affine map per tower (opt-in)" if getattr(args, "collapse_mlp", False) and world == 1
                 else "layer by layer",
@@ -315,6 +319,9 @@ def run_b200(args):
         from recommender_b200.sharded import ShardedDLRM
         model = ShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
                             sharding=args.sharding)
+    for m in model.modules():
+        if hasattr(m, "backend"):
+            m.backend = args.mlp_backend
     opt = Adam()
 
     if args.criteo_tb and not (world > 1 and args.exchange == "p2p"):

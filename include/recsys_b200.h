@@ -311,6 +311,53 @@ size_t rb_bce_workspace_bytes(int64_t n);
 int rb_bce_clipped(const float* prob, const void* label, int32_t label_type, int64_t n, float* loss_out, float* dprob_out,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Dense layers of the towers (ctr/layers.py:5-14) on tcgen05 tensor cores ------------------
+ *
+ * `MLP.call` (ctr/layers.py:11-14) is a chain of keras.layers.Dense; DLRM builds 13 -> 512 -> 256 -> 64 (relu) and
+ * 793 -> 512 -> 256 -> 1 (sigmoid), DeepFM 429 -> 512 -> 256 -> 1 (ctr/train.py:74-75,82; ctr/model.py:27,50,56).  These
+ * entry points are the three products of one Dense layer and its Dense(1) head, replacing TF's MatMul / BiasAdd /
+ * Relu / Sigmoid ops and their gradients.  Operands are bf16 (fp32 accumulation in tensor memory); every matrix is
+ * row-major with a leading dimension in ELEMENTS; base pointers and row strides must be 16-byte aligned; `in_dim` and
+ * `units` must be multiples of 8 (the callers zero-pad the feature axis: 13 -> 16, 793 -> 800).
+ */
+typedef enum rb_activation { RB_ACT_NONE = 0, RB_ACT_RELU = 1, RB_ACT_SIGMOID = 2 } rb_activation;
+
+/* y = activation(x . W + bias)   — Dense.call (ctr/layers.py:8-9,12-13).
+ * x bf16 [rows, in_dim] (ldx), w bf16 [in_dim, units] (ldw), bias f32 [units] or NULL, y RB_BF16 or RB_F32 [rows, units] (ldy). */
+int rb_dense_fwd(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, int32_t units, int64_t ldw,
+                 const float* bias, int32_t activation, void* y, int32_t y_type, int64_t ldy, void* stream);
+
+/* dx = dy . W^T   — the MatMul gradient w.r.t. the layer input.  dy bf16 [rows, units], w bf16 [in_dim, units], dx bf16 [rows, in_dim]. */
+int rb_dense_bwd_input(const void* dy, int64_t rows, int32_t units, int64_t lddy, const void* w, int32_t in_dim, int64_t ldw,
+                       void* dx, int64_t lddx, void* stream);
+
+size_t rb_dense_bwd_weight_workspace_bytes(int64_t rows, int32_t in_dim, int32_t units);
+
+/* dW = x^T . dy (f32 [in_dim, units], lddw)   — the MatMul gradient w.r.t. the kernel.  The batch axis is split over the
+ * SMs; partial tiles are summed in split order (deterministic).  When x carries a ones column (rb_dense_pack_input,
+ * RB_BF16_ONES rows of rb_dot_interaction_fwd) the matching row of dW is the bias gradient (BiasAddGrad). */
+int rb_dense_bwd_weight(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* dy, int32_t units, int64_t lddy,
+                        float* dw, int64_t lddw, void* ws, size_t ws_bytes, void* stream);
+
+/* Dense(1) head: out[r] = activation(sum_k x[r,k] * w[k] + bias[0])   (the last unit of [512, 256, 1]).  x, w bf16; out f32 [rows]. */
+int rb_dense_head_fwd(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, const float* bias, int32_t activation,
+                      float* out, void* stream);
+
+size_t rb_dense_head_bwd_workspace_bytes(int64_t rows, int32_t in_dim);
+
+/* Backward of the head: dz = dout * activation'(out);  dx[r,:] = bf16(dz[r] * w[:]) (optional);  dw[k] = sum_r x[r,k] * dz[r];
+ * db[0] = sum_r dz[r].  Deterministic two-stage sums. */
+int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, const void* x, int64_t rows, int32_t in_dim, int64_t ldx,
+                      const void* w, void* dx, int64_t lddx, float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+
+/* out_bf16[i] = bf16(dy[i] * activation'(y[i])) over n contiguous f32 elements: the ReluGrad / SigmoidGrad in front of the
+ * last layer's gradient GEMMs. */
+int rb_dense_act_bwd(const float* dy, const float* y, int32_t activation, int64_t n, void* out_bf16, void* stream);
+
+/* out_bf16[rows, ld_out] = [x (f32 [rows, in_dim], ldx) | 1.0 if ones_col | 0 ...]: the padded bf16 K operand of a first Dense layer. */
+int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim, int64_t ldx, void* out_bf16, int32_t ld_out, int32_t ones_col,
+                        void* stream);
+
 /* ---- id -> row map ------------------------------------------------------------------------ */
 
 /* rows_out[p] = uint64(ids[p]) mod vocab  (SURVEY §8c "index hashing"; bit-exact with the oracle).

@@ -134,28 +134,50 @@ def sigmoid(x):
     return (F32(1) / (F32(1) + np.exp(-x.astype(F32)))).astype(F32)
 
 
-def mlp_forward(x, layers, final_activation):
-    """ctr/layers.py:5-14: hidden Dense layers are linear, only the last has an activation."""
+def mlp_forward(x, layers, final_activation, operand_dtype=None):
+    """ctr/layers.py:5-14: hidden Dense layers are linear, only the last has an activation.
+
+    operand_dtype='bf16' restates the rounding points of the CUDA towers (csrc/mlp.cu): every GEMM reads its input
+    activations and its kernel rounded to bfloat16, accumulates in fp32, adds the fp32 bias; hidden activations are
+    stored in bf16; the last layer's activation acts on the fp32 accumulator.  acts[i] is what layer i's GEMMs read."""
+    if operand_dtype != "bf16":
+        acts = [x]
+        for i, (W, b) in enumerate(layers):
+            x = dense(x, W, b, final_activation if i == len(layers) - 1 else None)
+            acts.append(x)
+        return x, acts
+    x = round_bf16(x)
     acts = [x]
     for i, (W, b) in enumerate(layers):
-        x = dense(x, W, b, final_activation if i == len(layers) - 1 else None)
+        last = i == len(layers) - 1
+        x = dense(x, round_bf16(W), b, final_activation if last else None)
+        if not last:
+            x = round_bf16(x)
         acts.append(x)
     return x, acts
 
 
-def mlp_backward(dy, acts, layers, final_activation):
-    """Returns dx and [(dW, db)] for mlp_forward."""
+def mlp_backward(dy, acts, layers, final_activation, operand_dtype=None):
+    """Returns dx and [(dW, db)] for mlp_forward.  operand_dtype='bf16': activation gradients travel between layers in
+    bf16 (a Dense(1) last layer keeps its fp32 dz for dW / db, as rb_dense_head_bwd does)."""
     y = acts[-1]
     if final_activation == "relu":
         dy = dy * (y > 0)
     elif final_activation == "sigmoid":
         dy = dy * y * (F32(1) - y)
+    bf16 = operand_dtype == "bf16"
     grads = []
     for i in range(len(layers) - 1, -1, -1):
         W, _ = layers[i]
         x = acts[i]
+        if bf16:
+            W = round_bf16(W)
+            if not (i == len(layers) - 1 and W.shape[1] == 1):
+                dy = round_bf16(dy)
         grads.append(((x.T @ dy).astype(F32), dy.sum(0, dtype=F32)))
         dy = (dy @ W.T).astype(F32)
+    if bf16:
+        dy = round_bf16(dy)
     return dy, grads[::-1]
 
 
@@ -190,31 +212,32 @@ def deepfm_backward(params, cache, dlogit, num_cat_fea=26):
 
 
 def dlrm_forward(params, cat_features, int_features, num_int_fea=13, num_cat_fea=26,
-                 operand_dtype=None):
-    """ctr/model.py:45-58.  params: {'table', 'bottom': [...], 'top': [...]}."""
+                 operand_dtype=None, mlp_dtype=None):
+    """ctr/model.py:45-58.  params: {'table', 'bottom': [...], 'top': [...]}.  mlp_dtype='bf16': the towers' GEMMs read
+    bf16 operands (mlp_forward), the configuration bench.py times."""
     int_features = np.reshape(int_features, (-1, num_int_fea)).astype(F32)           # :47
     cat_features = np.reshape(cat_features, (-1, num_cat_fea))                      # :48
     E = embedding_lookup(params["table"], cat_features)                             # :49
-    bmlp, bacts = mlp_forward(int_features, params["bottom"], "relu")               # :50
+    bmlp, bacts = mlp_forward(int_features, params["bottom"], "relu", mlp_dtype)    # :50
     X = np.concatenate([E, bmlp[:, None, :]], axis=1)                               # :51-52
     inter = dot_interaction(X, False, True, operand_dtype)                          # :53
     tmlp_input = np.concatenate([inter, bmlp], axis=1)                              # :54
     D = E.shape[2]
     tmlp_input = tmlp_input.reshape(-1, (num_cat_fea + 1) ** 2 + D)                 # :55
-    out, tacts = mlp_forward(tmlp_input, params["top"], "sigmoid")                  # :56
+    out, tacts = mlp_forward(tmlp_input, params["top"], "sigmoid", mlp_dtype)       # :56
     prob = out[:, 0]                                                                # :57
     return prob, dict(E=E, X=X, bacts=bacts, tacts=tacts, idx=cat_features, inter=inter)
 
 
-def dlrm_backward(params, cache, dprob, num_cat_fea=26, operand_dtype=None):
+def dlrm_backward(params, cache, dprob, num_cat_fea=26, operand_dtype=None, mlp_dtype=None):
     X = cache["X"]
     Fp = num_cat_fea + 1
-    dtin, top_grads = mlp_backward(dprob[:, None].astype(F32), cache["tacts"], params["top"], "sigmoid")
+    dtin, top_grads = mlp_backward(dprob[:, None].astype(F32), cache["tacts"], params["top"], "sigmoid", mlp_dtype)
     dinter, dbmlp_direct = dtin[:, : Fp * Fp], dtin[:, Fp * Fp:]
     dX = dot_interaction_backward(X, dinter, False, True, operand_dtype)
     dE = dX[:, :num_cat_fea]
     dbmlp = dX[:, num_cat_fea] + dbmlp_direct
-    _, bottom_grads = mlp_backward(dbmlp.astype(F32), cache["bacts"], params["bottom"], "relu")
+    _, bottom_grads = mlp_backward(dbmlp.astype(F32), cache["bacts"], params["bottom"], "relu", mlp_dtype)
     return dict(dE=np.ascontiguousarray(dE, dtype=F32), top=top_grads, bottom=bottom_grads)
 
 

@@ -26,6 +26,8 @@ RB_F32, RB_BF16, RB_BF16_ONES = 0, 1, 2
 RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
 RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
 RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2
+RB_ACT_NONE, RB_ACT_RELU, RB_ACT_SIGMOID = 0, 1, 2
+ACT_ENUM = {None: RB_ACT_NONE, "relu": RB_ACT_RELU, "sigmoid": RB_ACT_SIGMOID}
 
 OPTIMIZER_ENUM = {"sgd": RB_OPT_SGD, "adagrad": RB_OPT_ADAGRAD, "adam_lazy": RB_OPT_ADAM_LAZY,
                   "adam_tf_dense": RB_OPT_ADAM_TF_DENSE}
@@ -98,6 +100,15 @@ SIGNATURES = {
                                           C.POINTER(RbOptParams), _p, C.c_size_t, _i32, _p, _p]),
     "rb_bce_workspace_bytes": (C.c_size_t, [_i64]),
     "rb_bce_clipped": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "rb_dense_fwd": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i64, _p, _i32, _p, _i32, _i64, _p]),
+    "rb_dense_bwd_input": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i64, _p, _i64, _p]),
+    "rb_dense_bwd_weight_workspace_bytes": (C.c_size_t, [_i64, _i32, _i32]),
+    "rb_dense_bwd_weight": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i64, _p, _i64, _p, C.c_size_t, _p]),
+    "rb_dense_head_fwd": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i32, _p, _p]),
+    "rb_dense_head_bwd_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "rb_dense_head_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "rb_dense_act_bwd": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "rb_dense_pack_input": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i32, _p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

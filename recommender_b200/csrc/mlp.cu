@@ -1,0 +1,759 @@
+// the Dense layers around the embedding path (ctr/layers.py:5-14, called at ctr/model.py:27,50,56;
+// shapes ctr/train.py:74-75,82) as hand-written sm_100a GEMMs: TMA (cp.async.bulk.tensor, 128-byte swizzle) stages the
+// bf16 operands in shared memory, one thread issues tcgen05.mma (M = 128, N <= 256, K = 16 per instruction) with fp32
+// accumulators in tensor memory, four epilogue warps read them back with tcgen05.ld, fuse bias / activation / the bf16
+// cast and hand 128-byte-wide slabs to TMA stores.  Persistent, warp-specialised, one CTA per SM:
+//
+//   warp 0   TMA producer     ring of kStages {A tile 128x64, B tile Nx64} stages, full/empty mbarriers
+//   warp 1   MMA issuer       4 x tcgen05.mma per stage, tcgen05.commit frees the stage / publishes the accumulator
+//   warp 2   TMEM allocator   512 columns = two accumulators (the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 4-7 epilogue         TMEM lane quarter q = warp % 4: thread = one row of the 128-row tile
+//
+// One kernel serves the three products of a Dense layer; they differ only in which operand is "K-major" (reduction
+// index contiguous in memory) and which is "MN-major" (row / column index contiguous), which the shared-memory
+// descriptors and the instruction descriptor express directly — nothing is transposed in memory:
+//
+//   forward       y  = x . W         A = x  [rows, in]    K-major    B = W  [in, units]   MN-major   reduce over in
+//   input grad    dx = dy . W^T      A = dy [rows, units] K-major    B = W  [in, units]   K-major    reduce over units
+//   weight grad   dW = x^T . dy      A = x  [rows, in]    MN-major   B = dy [rows, units] MN-major   reduce over rows
+//
+// The weight gradient reduces over the batch: its few output tiles are split along the batch over all SMs, every split
+// writes an fp32 partial tile, and a second kernel adds the partials in split order (deterministic, no float atomics).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rb {
+namespace mlp {
+
+constexpr int kBlockM = 128;                       // rows of C per tile = TMEM lanes
+constexpr int kBlockK = 64;                        // reduction elements per stage: 64 bf16 = one 128-byte swizzle span
+constexpr int kMaxN = 256;                         // columns of C per tile (tcgen05.mma N <= 256)
+constexpr int kStages = 4;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
+constexpr int kBStageBytes = kMaxN * kBlockK * 2;      // 32 KiB
+constexpr int kSlabBytes = kBlockM * 128;              // an output slab: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
+constexpr int kSlabs = 2;
+constexpr int kAtomBytes = 64 * kBlockK * 2;           // MN-major operands: one 64-wide box of 64 reduction rows = 8 KiB
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kSlabs * kSlabBytes + 256 /* barriers */ + kMaxN * 4 /* bias */ +
+                           1024 /* alignment */;
+
+struct GemmArgs {
+  int32_t M, N, K;             // C[M, N] = sum_k A[m, k] * B[n, k]
+  int32_t block_n;             // columns per tile: multiple of 64, <= 256
+  int32_t a_mn, b_mn;          // 1: the operand is MN-major in memory
+  int32_t m_blocks, n_blocks, splits, k_blocks, k_blocks_per_split;
+  int32_t out_f32;             // 0: bf16 C;  1: fp32 C (split s writes rows [s * m_blocks * 128, ...) of the output map)
+  int32_t activation;          // rb_activation, applied after the bias
+  const float* bias;           // f32[N] or null
+};
+
+// ---- PTX: mbarrier, TMA, tcgen05 ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t saddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(saddr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A wait that cannot hang the GPU: a protocol error (a phase that never completes) traps after ~2 s instead of
+// spinning until the watchdog resets the device for everybody.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {
+        printf("rb::mlp: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(saddr(dst)),
+               "l"(map), "r"(saddr(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(saddr(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulate; one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(bar)) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane (asynchronous: tmem_ld_wait() before the registers are read)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (tcgen05), 128-byte swizzle.  Offsets are in bytes, encoded without their 4 LSBs.
+//   K-major operand:  rows of 128 bytes (64 bf16 of the reduction axis), 8-row groups 1024 bytes apart (SBO); one
+//                     instruction consumes 32 bytes of every row -> the start address advances by 32 per k-step.
+//   MN-major operand: boxes of 64 reduction rows x 128 bytes (64 bf16 of the M/N axis); 8-row groups 1024 bytes apart
+//                     (SBO), the next 64 columns of M/N one box (8 KiB) further (LBO); one instruction consumes 16 rows
+//                     -> the start address advances by 2048 per k-step.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  d |= 2ull << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float apply_activation(float x, int act) {
+  if (act == RB_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == RB_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
+  return x;
+}
+
+// 32 accumulator columns of one row -> (+ bias, activation) -> 128 bytes of fp32 or 64 bytes of bf16 in the swizzled slab row.
+// `chunk0` is the first 16-byte chunk of the row these columns occupy; s_bias points at their 32 biases in shared memory.
+template <bool F32, int ACT>
+__device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const float* s_bias, uint8_t* srow, int chunk0, int sw) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(s_bias + 4 * j);      // same address in every lane: a broadcast
+    const float f0 = apply_activation(__uint_as_float(v[4 * j]) + b.x, ACT), f1 = apply_activation(__uint_as_float(v[4 * j + 1]) + b.y, ACT);
+    const float f2 = apply_activation(__uint_as_float(v[4 * j + 2]) + b.z, ACT), f3 = apply_activation(__uint_as_float(v[4 * j + 3]) + b.w, ACT);
+    if constexpr (F32) {
+      *reinterpret_cast<float4*>(srow + (((chunk0 + j) ^ sw) << 4)) = make_float4(f0, f1, f2, f3);
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
+      // two columns quads make one 16-byte chunk: even j fills its low half, odd j the high half
+      *reinterpret_cast<uint2*>(srow + (((chunk0 + (j >> 1)) ^ sw) << 4) + ((j & 1) << 3)) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
+template <bool F32, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kStages * kAStageBytes;
+  uint8_t* smem_out = smem_b + kStages * kBStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_out + kSlabs * kSlabBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem_out + kSlabs * kSlabBytes + 256);   // the tile's kMaxN biases
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);     // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total = g.m_blocks * g.n_blocks * g.splits;
+
+  if (warp == 0) {
+    // ===== TMA producer ========================================================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
+        const int m0 = m_blk * kBlockM, n0 = n_blk * g.block_n;
+        const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
+        // a tile that hangs over the right edge of C loads (MN-major B) and multiplies only the columns that exist
+        const int b_boxes = (min(g.block_n, g.N - n0) + 63) / 64;
+        const uint32_t stage_bytes = kAStageBytes + (g.b_mn ? static_cast<uint32_t>(b_boxes) * kAtomBytes : static_cast<uint32_t>(g.block_n) * 128u);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], stage_bytes);
+          const int k0 = kb * kBlockK;
+          uint8_t* a_dst = smem_a + stage * kAStageBytes;
+          uint8_t* b_dst = smem_b + stage * kBStageBytes;
+          if (!g.a_mn) {
+            tma_load_2d(a_dst, &map_a, &full[stage], k0, m0);
+          } else {
+            tma_load_2d(a_dst, &map_a, &full[stage], m0, k0);
+            tma_load_2d(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(b_dst, &map_b, &full[stage], k0, n0);
+          } else {
+            for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kAtomBytes, &map_b, &full[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ==========================================================================================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, majors, N >> 3, M >> 4
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.a_mn) << 15) |
+                              (static_cast<uint32_t>(g.b_mn) << 16) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
+      const uint32_t a_lbo = g.a_mn ? kAtomBytes : 16, b_lbo = g.b_mn ? kAtomBytes : 16;
+      const uint32_t a_step = g.a_mn ? 2048 : 32, b_step = g.b_mn ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int split = w / (g.n_blocks * g.m_blocks);
+        const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
+        const int n_valid = min(g.block_n, g.N - (w % g.n_blocks) * g.block_n);
+        const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((n_valid + 15) / 16 * 16) >> 3) << 17);   // N of this tile's MMAs
+        const int acc = it & 1;
+        mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const int k_valid = min(kBlockK, g.K - kb * kBlockK);
+          const int k_steps = (k_valid + 15) / 16;
+          const uint32_t a_addr = saddr(smem_a + stage * kAStageBytes), b_addr = saddr(smem_b + stage * kBStageBytes);
+          for (int k = 0; k < k_steps; ++k) {
+            umma_bf16(tmem_d, smem_desc(a_addr + k * a_step, a_lbo, 1024), smem_desc(b_addr + k * b_step, b_lbo, 1024), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                           // the stage is free once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);                            // the accumulator is complete
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===== epilogue: TMEM -> registers -> (bias, activation, cast) -> swizzled smem slab -> TMA store ===========
+    const int q = warp - kEpilogueWarp0;                        // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - kEpilogueWarp0 * 32;
+    constexpr int cols_per_slab = F32 ? 32 : 64;
+    const int n_slabs = g.block_n / cols_per_slab;
+    uint32_t slab_count = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
+      const int n0 = n_blk * g.block_n;
+      const int out_row0 = (F32 ? split * g.m_blocks * kBlockM : 0) + m_blk * kBlockM;
+      const int acc = it & 1;
+      // the tile's biases -> shared memory (zeros without a bias / past the edge of C); ordered before their first use by the
+      // bar.sync that opens the first slab, and after the previous tile's last use by the bar.sync that closed its last slab
+      for (int c = etid; c < g.block_n; c += 128) s_bias[c] = (g.bias != nullptr && n0 + c < g.N) ? __ldg(g.bias + n0 + c) : 0.f;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxN);
+      for (int s = 0; s < n_slabs; ++s) {
+        const int c0 = n0 + s * cols_per_slab;                  // first output column of the slab
+        if (c0 >= g.N) break;                                   // uniform over the CTA: the tile hangs over the edge of C
+        uint8_t* slab = smem_out + (slab_count & 1) * kSlabBytes;
+        ++slab_count;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab), v0);          // in flight across the waits below
+        if constexpr (!F32) tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab + 32), v1);
+        if (etid == 0) tma_store_wait_read<1>();                // the store that last read this slab buffer is done with it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* srow = slab + row * 128;
+        const int sw = row & 7;
+        tmem_ld_wait();
+        store_columns<F32, ACT>(v0, s_bias + s * cols_per_slab, srow, 0, sw);
+        if constexpr (!F32) store_columns<F32, ACT>(v1, s_bias + s * cols_per_slab + 32, srow, 4, sw);
+        fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          tma_store_2d(&map_c, slab, c0, out_row0);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);              // this warp's quarter of the accumulator is drained
+    }
+    if (etid == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dW[m, n] = sum over splits (in split order) of the fp32 partial tiles
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N, float* __restrict__ out, int64_t ldo) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int nv = N / 4;
+  if (i >= static_cast<int64_t>(M) * nv) return;
+  const int m = static_cast<int>(i / nv), n = static_cast<int>(i % nv) * 4;
+  const float* p = part + static_cast<int64_t>(m) * N + n;
+  float4 acc = *reinterpret_cast<const float4*>(p);
+  for (int s = 1; s < splits; ++s) {
+    const float4 t = *reinterpret_cast<const float4*>(p + s * split_stride);
+    acc.x += t.x;
+    acc.y += t.y;
+    acc.z += t.z;
+    acc.w += t.w;
+  }
+  *reinterpret_cast<float4*>(out + static_cast<int64_t>(m) * ldo + n) = acc;
+}
+
+// ---- the Dense(1) head (ctr/train.py:75,82: the last unit of [512, 256, 1]) on CUDA cores: a row dot product ----------
+// z[r] = sum_k x[r, k] * w[k] + b;  out[r] = act(z[r]).  One warp per row, 16-byte loads, fp32 accumulation.
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                const float* __restrict__ bias, int act, float* __restrict__ out) {
+  const int lane = threadIdx.x % 32;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + threadIdx.x / 32;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int k = lane * 8; k < in_dim; k += 256) {
+    const uint4 xv = __ldcs(reinterpret_cast<const uint4*>(x + r * ldx + k));
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + k));
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc = fmaf(__uint_as_float(xs[j] << 16), __uint_as_float(ws[j] << 16), acc);
+      acc = fmaf(__uint_as_float(xs[j] & 0xFFFF0000u), __uint_as_float(ws[j] & 0xFFFF0000u), acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[r] = apply_activation(acc + (bias != nullptr ? __ldg(bias) : 0.f), act);
+}
+
+// Backward of the head.  dz[r] = dout[r] * act'(out[r]);  dx[r, :] = bf16(dz[r] * w[:]);  partial sums of
+// dW[k] = sum_r x[r, k] * dz[r] and db = sum_r dz[r] per CTA (slab of rows), reduced in CTA order by head_bwd_final_kernel.
+constexpr int kHeadBwdThreads = 256;
+__global__ void __launch_bounds__(kHeadBwdThreads)
+head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int act, const __nv_bfloat16* __restrict__ x, int64_t rows,
+                int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t lddx,
+                float* __restrict__ partial /* [grid, in_dim + 1] */) {
+  // thread = (row lane rl, vector column vc): vc covers 8 consecutive columns
+  const int vcols = in_dim / 8;
+  const int row_lanes = kHeadBwdThreads / vcols;
+  const int vc = threadIdx.x % vcols, rl = threadIdx.x / vcols;
+  __shared__ float s_red[kHeadBwdThreads * 8];
+  __shared__ float s_db[kHeadBwdThreads];
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  float db = 0.f;
+  if (rl < row_lanes) {
+    float wf[8];
+    {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + vc * 8));
+      const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wf[2 * j] = __uint_as_float(ws[j] << 16);
+        wf[2 * j + 1] = __uint_as_float(ws[j] & 0xFFFF0000u);
+      }
+    }
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * per, r1 = min(r0 + per, rows);
+    for (int64_t r = r0 + rl; r < r1; r += row_lanes) {
+      float dz = dout[r];
+      const float o = out[r];
+      if (act == RB_ACT_SIGMOID) dz = dz * o * (1.0f - o);
+      else if (act == RB_ACT_RELU) dz = o > 0.f ? dz : 0.f;
+      if (vc == 0) db += dz;
+      const uint4 xv = __ldcs(reinterpret_cast<const uint4*>(x + r * ldx + vc * 8));
+      const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] = fmaf(__uint_as_float(xs[j] << 16), dz, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(__uint_as_float(xs[j] & 0xFFFF0000u), dz, acc[2 * j + 1]);
+        __nv_bfloat162 h = __floats2bfloat162_rn(dz * wf[2 * j], dz * wf[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (dx != nullptr) __stcs(reinterpret_cast<uint4*>(dx + r * lddx + vc * 8), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = acc[k];
+  s_db[threadIdx.x] = db;
+  __syncthreads();
+  for (int c = threadIdx.x; c < in_dim; c += kHeadBwdThreads) {
+    float t = 0.f;
+    for (int l = 0; l < row_lanes; ++l) t += s_red[(l * vcols + c / 8) * 8 + (c % 8)];
+    partial[static_cast<int64_t>(blockIdx.x) * (in_dim + 1) + c] = t;
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int l = 0; l < row_lanes; ++l) t += s_db[l * vcols];
+    partial[static_cast<int64_t>(blockIdx.x) * (in_dim + 1) + in_dim] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c > in_dim) return;
+  float t = 0.f;
+  for (int p = 0; p < parts; ++p) t += partial[static_cast<int64_t>(p) * (in_dim + 1) + c];
+  if (c < in_dim) dW[c] = t;
+  else db[0] = t;
+}
+
+// dy_pre[r, c] = bf16(dy[r, c] * act'(y[r, c])): the activation's backward in front of the last layer's GEMMs
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, int64_t n4, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 d = __ldcs(reinterpret_cast<const float4*>(dy) + i);
+  float v[4] = {d.x, d.y, d.z, d.w};
+  if (act != RB_ACT_NONE) {
+    const float4 o = __ldcs(reinterpret_cast<const float4*>(y) + i);
+    const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = act == RB_ACT_RELU ? (ov[k] > 0.f ? v[k] : 0.f) : v[k] * ov[k] * (1.0f - ov[k]);
+  }
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// x f32[rows, in_dim] -> bf16[rows, ld] = [x | 1 | 0 ...]: the K operand of the first Dense layer; the ones column makes
+// row in_dim of that layer's weight-gradient GEMM its bias gradient
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, __nv_bfloat16* __restrict__ out, int ld, int ones_col) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t r = i / ld;
+  const int c = static_cast<int>(i % ld);
+  float v = 0.f;
+  if (c < in_dim) v = x[r * ldx + c];
+  else if (c == in_dim && ones_col) v = 1.0f;
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D row-major matrix [outer, inner] with row stride `ld` elements; box = [box_outer, box_inner]; 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  EncodeTiledFn fn = encode_tiled();
+  RB_CHECK_ARG(fn != nullptr, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const size_t esz = f32 ? 4 : 2;
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esz) % 16 == 0, RB_ERR_ALIGN,
+               "Dense operands need 16-byte aligned base pointers and row strides (ld * %zu bytes)", esz);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RB_CHECK_ARG(r == CUDA_SUCCESS, RB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (inner %lld outer %lld ld %lld)", static_cast<int>(r),
+               static_cast<long long>(inner), static_cast<long long>(outer), static_cast<long long>(ld));
+  return RB_OK;
+}
+
+struct Operand {
+  const void* p;
+  int64_t rows, cols, ld;   // row-major [rows, cols]
+  bool mn_major;            // true: `cols` is the M / N axis of the product and `rows` the reduction axis
+};
+
+static int block_n_for(int N) {
+  int bn = (std::min(N, kMaxN) + 63) / 64 * 64;
+  return bn;
+}
+
+static void plan_splits(int tiles, int k_blocks, bool allow_split, int* splits, int* kbps) {
+  int s = 1;
+  if (allow_split && tiles < kNumSMs) s = std::max(1, std::min(kNumSMs / tiles, k_blocks));
+  const int per = (k_blocks + s - 1) / s;
+  *kbps = per;
+  *splits = (k_blocks + per - 1) / per;
+}
+
+// C[M, N] = A . B^T over K.  `c` is bf16 [M, N] / f32 [M, N] (splits == 1) or the f32 partial buffer.
+static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, void* c, bool c_f32, int64_t ldc, bool split_k, const float* bias,
+                       int activation, void* ws, size_t ws_bytes, cudaStream_t st, int* splits_out, int64_t* split_stride_out) {
+  GemmArgs g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.block_n = block_n_for(N);
+  g.a_mn = a.mn_major;
+  g.b_mn = b.mn_major;
+  g.m_blocks = (M + kBlockM - 1) / kBlockM;
+  g.n_blocks = (N + g.block_n - 1) / g.block_n;
+  g.k_blocks = (K + kBlockK - 1) / kBlockK;
+  plan_splits(g.m_blocks * g.n_blocks, g.k_blocks, split_k, &g.splits, &g.k_blocks_per_split);
+  g.out_f32 = c_f32;
+  g.activation = activation;
+  g.bias = bias;
+  CUtensorMap ma, mb, mc;
+  int rc;
+  // K-major operand [MN, K]: box = 64 reduction elements x (128 | block_n) rows.  MN-major operand [K, MN]: box = 64 x 64.
+  if (!a.mn_major) rc = make_map(&ma, a.p, false, K, M, a.ld, kBlockK, kBlockM);
+  else rc = make_map(&ma, a.p, false, M, K, a.ld, 64, kBlockK);
+  if (rc != RB_OK) return rc;
+  if (!b.mn_major) rc = make_map(&mb, b.p, false, K, N, b.ld, kBlockK, g.block_n);
+  else rc = make_map(&mb, b.p, false, N, K, b.ld, 64, kBlockK);
+  if (rc != RB_OK) return rc;
+  void* out = c;
+  int64_t out_rows = M, out_ld = ldc;
+  if (split_k) {
+    const int64_t split_stride = static_cast<int64_t>(g.m_blocks) * kBlockM * N;
+    const size_t need = static_cast<size_t>(g.splits) * split_stride * sizeof(float);
+    RB_CHECK_ARG(ws != nullptr && ws_bytes >= need, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    out = ws;
+    out_rows = static_cast<int64_t>(g.splits) * g.m_blocks * kBlockM;
+    out_ld = N;
+    *splits_out = g.splits;
+    *split_stride_out = split_stride;
+  }
+  rc = make_map(&mc, out, c_f32, N, out_rows, out_ld, c_f32 ? 32 : 64, kBlockM);
+  if (rc != RB_OK) return rc;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
+  static const KernelFn kernels[2][3] = {
+      {dense_gemm_kernel<false, RB_ACT_NONE>, dense_gemm_kernel<false, RB_ACT_RELU>, dense_gemm_kernel<false, RB_ACT_SIGMOID>},
+      {dense_gemm_kernel<true, RB_ACT_NONE>, dense_gemm_kernel<true, RB_ACT_RELU>, dense_gemm_kernel<true, RB_ACT_SIGMOID>}};
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (int f = 0; f < 2; ++f)
+      for (int a = 0; a < 3; ++a) RB_CUDA(cudaFuncSetAttribute(kernels[f][a], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int total = g.m_blocks * g.n_blocks * g.splits;
+  kernels[c_f32 ? 1 : 0][activation]<<<std::min(total, kNumSMs), kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
+  RB_LAUNCH_CHECK("dense_gemm_kernel");
+  return RB_OK;
+}
+
+static size_t weight_ws_bytes(int64_t rows, int in_dim, int units) {
+  const int bn = block_n_for(units);
+  const int m_blocks = (in_dim + kBlockM - 1) / kBlockM, n_blocks = (units + bn - 1) / bn;
+  const int k_blocks = static_cast<int>((rows + kBlockK - 1) / kBlockK);
+  int splits, kbps;
+  plan_splits(m_blocks * n_blocks, k_blocks, true, &splits, &kbps);
+  return static_cast<size_t>(splits) * m_blocks * kBlockM * units * sizeof(float) + 256;
+}
+
+static bool dims_ok(int64_t rows, int a, int b) { return rows > 0 && rows < (1ll << 31) && a > 0 && b > 0 && a % 8 == 0 && b % 8 == 0; }
+
+}  // namespace mlp
+}  // namespace rb
+
+using namespace rb;
+using namespace rb::mlp;
+
+extern "C" int rb_dense_fwd(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, int32_t units, int64_t ldw,
+                            const float* bias, int32_t activation, void* y, int32_t y_type, int64_t ldy, void* stream) {
+  RB_CHECK_ARG(x != nullptr && w != nullptr && y != nullptr, RB_ERR_ARG, "x / w / y is null");
+  RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
+  RB_CHECK_ARG(y_type == RB_F32 || y_type == RB_BF16, RB_ERR_ARG, "y_type must be RB_F32 or RB_BF16");
+  RB_CHECK_ARG(dims_ok(rows, in_dim, units), RB_ERR_SHAPE, "Dense needs rows > 0 and in_dim, units multiples of 8 (got %lld, %d, %d)",
+               static_cast<long long>(rows), in_dim, units);
+  RB_CHECK_ARG(ldx >= in_dim && ldw >= units && ldy >= units, RB_ERR_ARG, "a leading dimension is smaller than its row");
+  Operand a{x, rows, in_dim, ldx, false}, b{w, in_dim, units, ldw, true};
+  return launch_gemm(a, b, static_cast<int>(rows), units, in_dim, y, y_type == RB_F32, ldy, false, bias, activation, nullptr, 0,
+                     static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+extern "C" int rb_dense_bwd_input(const void* dy, int64_t rows, int32_t units, int64_t lddy, const void* w, int32_t in_dim, int64_t ldw,
+                                  void* dx, int64_t lddx, void* stream) {
+  RB_CHECK_ARG(dy != nullptr && w != nullptr && dx != nullptr, RB_ERR_ARG, "dy / w / dx is null");
+  RB_CHECK_ARG(dims_ok(rows, in_dim, units), RB_ERR_SHAPE, "Dense needs rows > 0 and in_dim, units multiples of 8 (got %lld, %d, %d)",
+               static_cast<long long>(rows), in_dim, units);
+  RB_CHECK_ARG(lddy >= units && ldw >= units && lddx >= in_dim, RB_ERR_ARG, "a leading dimension is smaller than its row");
+  // dx[r, i] = sum_u dy[r, u] * W[i, u]: both operands have the reduction index u contiguous
+  Operand a{dy, rows, units, lddy, false}, b{w, in_dim, units, ldw, false};
+  return launch_gemm(a, b, static_cast<int>(rows), in_dim, units, dx, false, lddx, false, nullptr, RB_ACT_NONE, nullptr, 0,
+                     static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+extern "C" size_t rb_dense_bwd_weight_workspace_bytes(int64_t rows, int32_t in_dim, int32_t units) {
+  if (!dims_ok(rows, in_dim, units)) return 0;
+  return weight_ws_bytes(rows, in_dim, units);
+}
+
+extern "C" int rb_dense_bwd_weight(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* dy, int32_t units, int64_t lddy,
+                                   float* dw, int64_t lddw, void* ws, size_t ws_bytes, void* stream) {
+  RB_CHECK_ARG(x != nullptr && dy != nullptr && dw != nullptr, RB_ERR_ARG, "x / dy / dw is null");
+  RB_CHECK_ARG(dims_ok(rows, in_dim, units), RB_ERR_SHAPE, "Dense needs rows > 0 and in_dim, units multiples of 8 (got %lld, %d, %d)",
+               static_cast<long long>(rows), in_dim, units);
+  RB_CHECK_ARG(ldx >= in_dim && lddy >= units && lddw >= units && lddw % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0, RB_ERR_ARG,
+               "bad leading dimension / dw alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // dW[i, u] = sum_r x[r, i] * dy[r, u]: the reduction index r is the slow axis of both operands (MN-major)
+  Operand a{x, rows, in_dim, ldx, true}, b{dy, rows, units, lddy, true};
+  int splits = 1;
+  int64_t split_stride = 0;
+  int rc = launch_gemm(a, b, in_dim, units, static_cast<int>(rows), nullptr, true, 0, true, nullptr, RB_ACT_NONE, ws, ws_bytes, st, &splits,
+                       &split_stride);
+  if (rc != RB_OK) return rc;
+  const int64_t work = static_cast<int64_t>(in_dim) * (units / 4);
+  reduce_splits_kernel<<<grid_for(work, 256), 256, 0, st>>>(static_cast<const float*>(ws), splits, split_stride, in_dim, units, dw, lddw);
+  RB_LAUNCH_CHECK("reduce_splits_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_dense_head_fwd(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, const float* bias, int32_t activation,
+                                 float* out, void* stream) {
+  RB_CHECK_ARG(x != nullptr && w != nullptr && out != nullptr, RB_ERR_ARG, "x / w / out is null");
+  RB_CHECK_ARG(rows > 0 && in_dim > 0 && in_dim % 8 == 0 && ldx % 8 == 0 && ldx >= in_dim, RB_ERR_SHAPE, "head: in_dim and ldx must be multiples of 8");
+  RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, RB_ERR_ALIGN, "head: x / w not 16-byte aligned");
+  RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
+  head_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
+                                                                                  static_cast<const __nv_bfloat16*>(w), bias, activation, out);
+  RB_LAUNCH_CHECK("head_fwd_kernel");
+  return RB_OK;
+}
+
+static int head_parts(int64_t rows) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(4 * kNumSMs, rows / 64))); }
+
+extern "C" size_t rb_dense_head_bwd_workspace_bytes(int64_t rows, int32_t in_dim) {
+  if (rows <= 0 || in_dim <= 0) return 0;
+  return static_cast<size_t>(head_parts(rows)) * (in_dim + 1) * sizeof(float) + 256;
+}
+
+extern "C" int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, const void* x, int64_t rows, int32_t in_dim, int64_t ldx,
+                                 const void* w, void* dx, int64_t lddx, float* dw, float* db, void* ws, size_t ws_bytes, void* stream) {
+  RB_CHECK_ARG(dout != nullptr && x != nullptr && w != nullptr && dw != nullptr && db != nullptr, RB_ERR_ARG, "a required pointer is null");
+  RB_CHECK_ARG(activation == RB_ACT_NONE || out != nullptr, RB_ERR_ARG, "the activation's backward needs the forward output");
+  RB_CHECK_ARG(rows > 0 && in_dim > 0 && in_dim % 8 == 0 && in_dim <= 8 * kHeadBwdThreads && ldx % 8 == 0 && ldx >= in_dim &&
+                   (dx == nullptr || (lddx % 8 == 0 && lddx >= in_dim)),
+               RB_ERR_SHAPE, "head: in_dim (<= %d) and the leading dimensions must be multiples of 8", 8 * kHeadBwdThreads);
+  RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0, RB_ERR_ALIGN,
+               "head: x / w / dx not 16-byte aligned");
+  RB_CHECK_ARG(ws != nullptr && ws_bytes >= rb_dense_head_bwd_workspace_bytes(rows, in_dim), RB_ERR_WORKSPACE,
+               "workspace too small: need %zu bytes, got %zu", rb_dense_head_bwd_workspace_bytes(rows, in_dim), ws_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int parts = head_parts(rows);
+  head_bwd_kernel<<<parts, kHeadBwdThreads, 0, st>>>(dout, out, activation, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
+                                                     static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(dx), lddx,
+                                                     static_cast<float*>(ws));
+  RB_LAUNCH_CHECK("head_bwd_kernel");
+  head_bwd_final_kernel<<<(in_dim + 1 + 255) / 256, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, dw, db);
+  RB_LAUNCH_CHECK("head_bwd_final_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_dense_act_bwd(const float* dy, const float* y, int32_t activation, int64_t n, void* out_bf16, void* stream) {
+  RB_CHECK_ARG(dy != nullptr && out_bf16 != nullptr && (activation == RB_ACT_NONE || y != nullptr), RB_ERR_ARG, "a required pointer is null");
+  RB_CHECK_ARG(n > 0 && n % 4 == 0, RB_ERR_SHAPE, "act_bwd: element count must be a positive multiple of 4");
+  RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
+               RB_ERR_ALIGN, "act_bwd: pointers not aligned");
+  RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
+  act_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, activation, n / 4, static_cast<__nv_bfloat16*>(out_bf16));
+  RB_LAUNCH_CHECK("act_bwd_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim, int64_t ldx, void* out_bf16, int32_t ld_out, int32_t ones_col,
+                                   void* stream) {
+  RB_CHECK_ARG(x != nullptr && out_bf16 != nullptr, RB_ERR_ARG, "x / out is null");
+  RB_CHECK_ARG(rows > 0 && in_dim > 0 && ld_out >= in_dim + (ones_col ? 1 : 0) && ldx >= in_dim, RB_ERR_SHAPE, "pack_input: bad sizes");
+  pack_input_kernel<<<grid_for(rows * ld_out, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, in_dim, ldx,
+                                                                                              static_cast<__nv_bfloat16*>(out_bf16), ld_out, ones_col);
+  RB_LAUNCH_CHECK("pack_input_kernel");
+  return RB_OK;
+}

@@ -396,6 +396,75 @@ class _LinearBF16Fn(torch.autograd.Function):
         return dx, dW, db, None, None
 
 
+class _DenseStackFn(torch.autograd.Function):
+    """The whole MLP of ctr/layers.py:5-14 on the tcgen05 Dense kernels (csrc/mlp.cu): hidden layers linear, bf16 operands with
+    fp32 accumulation, fp32 master weights, the last layer's activation applied on the fp32 accumulator.
+
+    x is either the padded bf16 K operand [B, Kp] (what the fused interaction kernel emits; `ones_col` says its column
+    `in_dim` holds 1.0) or the raw f32 [B, in_dim] features, which are packed here (rb_dense_pack_input).  One C-ABI call
+    per product: y = x W + b (rb_dense_fwd), dx = dy W^T (rb_dense_bwd_input), dW = x^T dy (rb_dense_bwd_weight; with the
+    ones column its row `in_dim` is the bias gradient), and the Dense(1) head as a row dot product (rb_dense_head_*)."""
+
+    @staticmethod
+    def forward(ctx, x, in_dim, Kp, ones_col, final_activation, need_dx, *params):
+        Ws, bs = params[0::2], params[1::2]
+        n = len(Ws)
+        raw = x.dtype != torch.bfloat16
+        if raw:
+            ones_col = Kp > in_dim
+            x = ops.dense_pack_input(x.float(), Kp, ones_col)
+        acts = [x]
+        shadows = []
+        h = x
+        for i, (W, b) in enumerate(zip(Ws, bs)):
+            last = i == n - 1
+            Wp = _LinearBF16Fn._bf16_shadow(W, Kp if i == 0 else None)
+            shadows.append(Wp)
+            if last and W.shape[1] == 1:
+                out = ops.dense_head_fwd(h, Wp.reshape(-1), b, final_activation).reshape(-1, 1)
+            elif last:
+                out = ops.dense_fwd(h, Wp, b, final_activation, torch.float32)
+            else:
+                h = ops.dense_fwd(h, Wp, b, None, torch.bfloat16)
+                acts.append(h)
+        ctx.save_for_backward(out, *acts, *shadows)
+        ctx.n, ctx.in_dim, ctx.ones_col, ctx.act, ctx.need_dx, ctx.raw = n, in_dim, bool(ones_col) and Kp > in_dim, final_activation, need_dx, raw
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        out, acts, shadows = saved[0], saved[1:1 + n], saved[1 + n:]
+        grads = [None] * (2 * n)
+        dout = dout.contiguous().float()
+        h, Wp = acts[n - 1], shadows[n - 1]
+        want_dx = n > 1 or ctx.need_dx
+        if Wp.shape[1] == 1:
+            dy, dw, db = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), ctx.act, h, Wp.reshape(-1), want_dx=want_dx)
+            dW_full = dw.reshape(-1, 1)
+        else:
+            dyp = ops.dense_act_bwd(dout, out, ctx.act)
+            dW_full = ops.dense_bwd_weight(h, dyp)
+            db = ops.colsum(dyp)
+            dy = ops.dense_bwd_input(dyp, Wp) if want_dx else None
+        for i in range(n - 1, -1, -1):
+            if i < n - 1:
+                h, Wp = acts[i], shadows[i]
+                dW_full = ops.dense_bwd_weight(h, dy)
+                db = None if (i == 0 and ctx.ones_col) else ops.colsum(dy)
+                dy = ops.dense_bwd_input(dy, Wp) if (i > 0 or ctx.need_dx) else None
+            if i == 0:
+                grads[0] = dW_full[: ctx.in_dim]
+                grads[1] = dW_full[ctx.in_dim].clone() if db is None else db
+            else:
+                grads[2 * i], grads[2 * i + 1] = dW_full, db
+        dx = dy
+        if dx is not None and ctx.raw:
+            dx = dx[:, : ctx.in_dim].float()
+        return (dx if ctx.need_dx else None, None, None, None, None, None, *grads)
+
+
 class _CollapsedAffineFn(torch.autograd.Function):
     """The affine part of an MLP whose hidden layers are linear (ctr/layers.py:8 builds them without activation):
 
@@ -475,6 +544,7 @@ class MLP(nn.Module):
                  generator: Optional[torch.Generator] = None, collapse_linear: bool = False):
         super().__init__()
         self.collapse_linear = bool(collapse_linear)     # opt-in: evaluate the linear stack as ONE affine map (_CollapsedAffineFn)
+        self.backend = "tcgen05"                          # bf16 mode: csrc/mlp.cu kernels; "cublas" = torch.addmm / mm
         if final_activation not in (None, "relu", "sigmoid"):
             raise ValueError(final_activation)
         if compute_dtype not in (None, torch.float32, torch.bfloat16):
@@ -501,6 +571,17 @@ class MLP(nn.Module):
         self.kernels = nn.ParameterList(nn.Parameter(torch.as_tensor(W, dtype=torch.float32).to(device).contiguous()) for W, _ in layers)
         self.biases = nn.ParameterList(nn.Parameter(torch.as_tensor(b, dtype=torch.float32).to(device).contiguous()) for _, b in layers)
         self.in_dim = int(self.kernels[0].shape[0])
+
+    def _tcgen05_ok(self, x: torch.Tensor) -> bool:
+        """The hand-written tcgen05 Dense kernels serve CUDA inputs when every hidden width is a multiple of 8 (16-byte row
+        strides for TMA) and the last layer is either such a width or the Dense(1) head; `backend='cublas'` keeps the
+        torch / cuBLASLt path (the round-1 implementation, used as the A/B baseline in bench.py --mlp-backend)."""
+        if self.backend != "tcgen05" or not x.is_cuda or x.dim() != 2:
+            return False
+        us = [int(k.shape[1]) for k in self.kernels]
+        if any(u % 8 for u in us[:-1]) or (us[-1] != 1 and us[-1] % 8):
+            return False
+        return not (us[-1] == 1 and int(self.kernels[-1].shape[0]) % 8)
 
     def padded_in_dim(self) -> int:
         """Feature count the bf16 path wants its input padded to (multiple of 8)."""
@@ -530,6 +611,12 @@ class MLP(nn.Module):
         # bf16 tensor-core path
         Kp = self.padded_in_dim()
         need_dx = x.requires_grad
+        collapse_ = self.collapse_linear and len(self.kernels) >= 2
+        if not collapse_ and self._tcgen05_ok(x) and (x.dtype != torch.bfloat16 or x.shape[-1] != Kp):
+            if x.shape[-1] != self.in_dim:
+                raise ValueError(f"MLP built for {self.in_dim} input features, got {x.shape[-1]}")
+            flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
+            return _DenseStackFn.apply(x.float(), self.in_dim, Kp, False, self.final_activation, need_dx, *flat)   # packed inside
         if x.dtype != torch.bfloat16 or x.shape[-1] != Kp:
             if x.shape[-1] != self.in_dim:
                 raise ValueError(f"MLP built for {self.in_dim} input features, got {x.shape[-1]}")
@@ -544,6 +631,9 @@ class MLP(nn.Module):
         if collapse:
             flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
             return self._activate(_CollapsedAffineFn.apply(x, self.in_dim, need_dx, ones_col, *flat))
+        if self._tcgen05_ok(x):
+            flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
+            return _DenseStackFn.apply(x, self.in_dim, Kp, ones_col, self.final_activation, need_dx, *flat)
         for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
             x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0, ones_col and i == 0)
         return self._activate(x)

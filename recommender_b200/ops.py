@@ -274,6 +274,7 @@ class LookupGroup:
 
 
 _workspaces = {}
+_retired = []
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -281,6 +282,8 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     key = torch.device(device).index or 0
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)      # a captured CUDA graph may hold its address: outgrown buffers are kept, never freed
         ws = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, device=f"cuda:{key}")
         _workspaces[key] = ws
     return ws
@@ -434,6 +437,109 @@ def bce_clipped(prob: torch.Tensor, label: torch.Tensor, want_grad: bool = True)
     check(lib.rb_bce_clipped(_ptr(prob), _ptr(label), 1 if label.dtype == torch.int64 else 0, n, _ptr(loss), _ptr(dprob), _ptr(ws),
                              ws.numel(), _stream()), "rb_bce_clipped")
     return loss, dprob
+
+
+# --------------------------------------------------------------------------------------------
+# Dense layers of the towers on tcgen05 tensor cores (csrc/mlp.cu; ctr/layers.py:5-14)
+# --------------------------------------------------------------------------------------------
+
+def _bf16m(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+        raise TypeError(f"{name} must be a bfloat16 matrix with unit inner stride, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    return t
+
+
+def dense_fwd(x, w, bias=None, activation=None, out_dtype=torch.bfloat16, out=None):
+    """y = activation(x @ w + bias) (rb_dense_fwd).  x bf16 [rows, in_dim], w bf16 [in_dim, units], bias f32 [units];
+    y bf16 or f32 [rows, units]."""
+    _need_cuda(x, w, bias, out)
+    _bf16m(x, "x"), _bf16m(w, "w")
+    rows, in_dim = x.shape
+    units = w.shape[1]
+    if w.shape[0] != in_dim:
+        raise ValueError(f"x has {in_dim} features, w has {w.shape[0]} rows")
+    if out is None:
+        out = torch.empty(rows, units, dtype=out_dtype, device=x.device)
+    check(lib.rb_dense_fwd(_ptr(x), rows, in_dim, x.stride(0), _ptr(w), units, w.stride(0), _ptr(bias), _lib.ACT_ENUM[activation],
+                           _ptr(out), _float_type(out.dtype), out.stride(0), _stream()), "rb_dense_fwd")
+    return out
+
+
+def dense_bwd_input(dy, w, out=None):
+    """dx = dy @ w.T (rb_dense_bwd_input).  dy bf16 [rows, units], w bf16 [in_dim, units] -> dx bf16 [rows, in_dim]."""
+    _need_cuda(dy, w, out)
+    _bf16m(dy, "dy"), _bf16m(w, "w")
+    rows, units = dy.shape
+    in_dim = w.shape[0]
+    if out is None:
+        out = torch.empty(rows, in_dim, dtype=torch.bfloat16, device=dy.device)
+    check(lib.rb_dense_bwd_input(_ptr(dy), rows, units, dy.stride(0), _ptr(w), in_dim, w.stride(0), _ptr(out), out.stride(0), _stream()),
+          "rb_dense_bwd_input")
+    return out
+
+
+def dense_bwd_weight(x, dy, out=None):
+    """dW = x.T @ dy in fp32 (rb_dense_bwd_weight), deterministic split over the batch.  x bf16 [rows, in_dim], dy bf16 [rows, units]."""
+    _need_cuda(x, dy, out)
+    _bf16m(x, "x"), _bf16m(dy, "dy")
+    rows, in_dim = x.shape
+    units = dy.shape[1]
+    if out is None:
+        out = torch.empty(in_dim, units, dtype=torch.float32, device=x.device)
+    nbytes = lib.rb_dense_bwd_weight_workspace_bytes(rows, in_dim, units)
+    if nbytes == 0:
+        raise _lib.RecsysError(f"rb_dense_bwd_weight rejected the problem size ({rows}, {in_dim}, {units})")
+    ws = _workspace(nbytes, x.device)
+    check(lib.rb_dense_bwd_weight(_ptr(x), rows, in_dim, x.stride(0), _ptr(dy), units, dy.stride(0), _ptr(out), out.stride(0), _ptr(ws),
+                                  ws.numel(), _stream()), "rb_dense_bwd_weight")
+    return out
+
+
+def dense_head_fwd(x, w, bias=None, activation=None):
+    """out[r] = activation(x[r] . w + bias) for a Dense(1) layer (rb_dense_head_fwd).  x bf16 [rows, in_dim], w bf16 [in_dim]."""
+    _need_cuda(x, w, bias)
+    _bf16m(x, "x")
+    rows, in_dim = x.shape
+    out = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(lib.rb_dense_head_fwd(_ptr(x), rows, in_dim, x.stride(0), _ptr(w), _ptr(bias), _lib.ACT_ENUM[activation], _ptr(out), _stream()),
+          "rb_dense_head_fwd")
+    return out
+
+
+def dense_head_bwd(dout, out, activation, x, w, want_dx=True):
+    """Backward of the Dense(1) head (rb_dense_head_bwd): returns (dx bf16 [rows, in_dim] | None, dW f32 [in_dim], db f32 [1])."""
+    _need_cuda(dout, out, x, w)
+    _bf16m(x, "x")
+    rows, in_dim = x.shape
+    dx = torch.empty(rows, in_dim, dtype=torch.bfloat16, device=x.device) if want_dx else None
+    dw = torch.empty(in_dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = _workspace(max(lib.rb_dense_head_bwd_workspace_bytes(rows, in_dim), 256), x.device)
+    check(lib.rb_dense_head_bwd(_ptr(_f32c(dout, "dout")), _ptr(out), _lib.ACT_ENUM[activation], _ptr(x), rows, in_dim, x.stride(0), _ptr(w),
+                                _ptr(dx), in_dim, _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()), "rb_dense_head_bwd")
+    return dx, dw, db
+
+
+def dense_act_bwd(dy, y, activation):
+    """bf16(dy * activation'(y)) (rb_dense_act_bwd); dy, y f32 of the same contiguous shape."""
+    _need_cuda(dy, y)
+    _f32c(dy, "dy")
+    if y is not None:
+        _f32c(y, "y")
+    out = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    check(lib.rb_dense_act_bwd(_ptr(dy), _ptr(y), _lib.ACT_ENUM[activation], dy.numel(), _ptr(out), _stream()), "rb_dense_act_bwd")
+    return out
+
+
+def dense_pack_input(x, ld: int, ones_col: bool = True):
+    """bf16 [rows, ld] = [x | 1 | 0...] from f32 x [rows, in_dim] (rb_dense_pack_input)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise TypeError("pack_input takes a float32 matrix with unit inner stride")
+    rows, in_dim = x.shape
+    out = torch.empty(rows, ld, dtype=torch.bfloat16, device=x.device)
+    check(lib.rb_dense_pack_input(_ptr(x), rows, in_dim, x.stride(0), _ptr(out), ld, int(bool(ones_col)), _stream()), "rb_dense_pack_input")
+    return out
 
 
 # --------------------------------------------------------------------------------------------
