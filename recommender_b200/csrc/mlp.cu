@@ -7,7 +7,8 @@
 //   warp 0   TMA producer     ring of kStages {A tile 128x64, B tile Nx64} stages, full/empty mbarriers
 //   warp 1   MMA issuer       4 x tcgen05.mma per stage, tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2   TMEM allocator   512 columns = two accumulators (the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warp 4-7 epilogue         TMEM lane quarter q = warp % 4: thread = one row of the 128-row tile
+//   warp 4-11 epilogue        TMEM lane quarter q = warp % 4: thread = one row of the 128-row tile; two groups of four
+//                             warps drain alternate 128-byte-wide column slabs
 //
 // One kernel serves the three products of a Dense layer; they differ only in which operand is "K-major" (reduction
 // index contiguous in memory) and which is "MN-major" (row / column index contiguous), which the shared-memory
@@ -33,16 +34,17 @@ constexpr int kBlockM = 128;                       // rows of C per tile = TMEM 
 constexpr int kBlockK = 64;                        // reduction elements per stage: 64 bf16 = one 128-byte swizzle span
 constexpr int kMaxN = 256;                         // columns of C per tile (tcgen05.mma N <= 256)
 constexpr int kStages = 4;
+constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueGroups = 2;                   // groups of four warps (one per TMEM lane quarter)
+constexpr int kThreads = (kEpilogueWarp0 + 4 * kEpilogueGroups) * 32;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
 constexpr int kBStageBytes = kMaxN * kBlockK * 2;      // 32 KiB
 constexpr int kSlabBytes = kBlockM * 128;              // an output slab: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
-constexpr int kSlabs = 2;
+constexpr int kSlabs = kEpilogueGroups;
 constexpr int kAtomBytes = 64 * kBlockK * 2;           // MN-major operands: one 64-wide box of 64 reduction rows = 8 KiB
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 256;
-constexpr int kEpilogueWarp0 = 4;
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kSlabs * kSlabBytes + 256 /* barriers */ + kMaxN * 4 /* bias */ +
-                           1024 /* alignment */;
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kSlabs * kSlabBytes + 256 /* barriers */ + kEpilogueGroups * kMaxN * 4 /* bias */;
+static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory of the Dense kernel exceeds the 227 KiB a CTA may own");
 
 struct GemmArgs {
   int32_t M, N, K;             // C[M, N] = sum_k A[m, k] * B[n, k]
@@ -181,6 +183,7 @@ __device__ __forceinline__ float apply_activation(float x, int act) {
 // `chunk0` is the first 16-byte chunk of the row these columns occupy; s_bias points at their 32 biases in shared memory.
 template <bool F32, int ACT>
 __device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const float* s_bias, uint8_t* srow, int chunk0, int sw) {
+  uint32_t pk[2];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 b = *reinterpret_cast<const float4*>(s_bias + 4 * j);      // same address in every lane: a broadcast
@@ -190,9 +193,13 @@ __device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const flo
       *reinterpret_cast<float4*>(srow + (((chunk0 + j) ^ sw) << 4)) = make_float4(f0, f1, f2, f3);
     } else {
       __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
-      // two columns quads make one 16-byte chunk: even j fills its low half, odd j the high half
-      *reinterpret_cast<uint2*>(srow + (((chunk0 + (j >> 1)) ^ sw) << 4) + ((j & 1) << 3)) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      if ((j & 1) == 0) {       // two column quads make one 16-byte chunk
+        pk[0] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[1] = *reinterpret_cast<uint32_t*>(&hi);
+      } else {
+        *reinterpret_cast<uint4*>(srow + (((chunk0 + (j >> 1)) ^ sw) << 4)) =
+            make_uint4(pk[0], pk[1], *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
     }
   }
 }
@@ -201,8 +208,8 @@ template <bool F32, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // 128-byte-swizzled tiles need 1024-byte aligned bases
+  if ((saddr(smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kStages * kAStageBytes;
   uint8_t* smem_out = smem_b + kStages * kBStageBytes;
@@ -227,7 +234,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);     // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], 4 * kEpilogueGroups);     // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -316,41 +323,46 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp >= kEpilogueWarp0) {
     // ===== epilogue: TMEM -> registers -> (bias, activation, cast) -> swizzled smem slab -> TMA store ===========
-    const int q = warp - kEpilogueWarp0;                        // == warp % 4: the TMEM lane quarter this warp may read
+    // Two groups of four warps; group g drains the slabs of parity g of every tile through its own slab buffer, bias copy
+    // and named barrier, so two slabs are in flight per tile.
+    const int ew = warp - kEpilogueWarp0;
+    const int q = ew & 3;                                       // == warp % 4: the TMEM lane quarter this warp may read
+    const int grp = ew >> 2;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - kEpilogueWarp0 * 32;
+    const int etid = q * 32 + lane;                             // thread index inside the group
+    const int bar_id = 1 + grp;
+    float* bias_g = s_bias + grp * kMaxN;
+    uint8_t* slab = smem_out + grp * kSlabBytes;
+    uint8_t* srow = slab + row * 128;
+    const int sw = row & 7;
     constexpr int cols_per_slab = F32 ? 32 : 64;
     const int n_slabs = g.block_n / cols_per_slab;
-    uint32_t slab_count = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
       const int n0 = n_blk * g.block_n;
       const int out_row0 = (F32 ? split * g.m_blocks * kBlockM : 0) + m_blk * kBlockM;
       const int acc = it & 1;
-      // the tile's biases -> shared memory (zeros without a bias / past the edge of C); ordered before their first use by the
-      // bar.sync that opens the first slab, and after the previous tile's last use by the bar.sync that closed its last slab
-      for (int c = etid; c < g.block_n; c += 128) s_bias[c] = (g.bias != nullptr && n0 + c < g.N) ? __ldg(g.bias + n0 + c) : 0.f;
+      // the tile's biases -> this group's shared-memory copy (zeros without a bias / past the edge of C); ordered before their
+      // first use by the bar.sync that opens the group's first slab, and after the previous tile's last use by the bar.sync
+      // that closed its last slab
+      for (int c = etid; c < g.block_n; c += 128) bias_g[c] = (g.bias != nullptr && n0 + c < g.N) ? __ldg(g.bias + n0 + c) : 0.f;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxN);
-      for (int s = 0; s < n_slabs; ++s) {
+      for (int s = grp; s < n_slabs; s += kEpilogueGroups) {
         const int c0 = n0 + s * cols_per_slab;                  // first output column of the slab
-        if (c0 >= g.N) break;                                   // uniform over the CTA: the tile hangs over the edge of C
-        uint8_t* slab = smem_out + (slab_count & 1) * kSlabBytes;
-        ++slab_count;
+        if (c0 >= g.N) break;                                   // uniform over the group: the tile hangs over the edge of C
         uint32_t v0[32], v1[32];
         tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab), v0);          // in flight across the waits below
         if constexpr (!F32) tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab + 32), v1);
-        if (etid == 0) tma_store_wait_read<1>();                // the store that last read this slab buffer is done with it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint8_t* srow = slab + row * 128;
-        const int sw = row & 7;
+        if (etid == 0) tma_store_wait_read<0>();                // the group's previous store is done reading the slab buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         tmem_ld_wait();
-        store_columns<F32, ACT>(v0, s_bias + s * cols_per_slab, srow, 0, sw);
-        if constexpr (!F32) store_columns<F32, ACT>(v1, s_bias + s * cols_per_slab + 32, srow, 4, sw);
+        store_columns<F32, ACT>(v0, bias_g + s * cols_per_slab, srow, 0, sw);
+        if constexpr (!F32) store_columns<F32, ACT>(v1, bias_g + s * cols_per_slab + 32, srow, 4, sw);
         fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (etid == 0) {
           tma_store_2d(&map_c, slab, c0, out_row0);
           tma_store_commit();
@@ -358,7 +370,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);              // this warp's quarter of the accumulator is drained
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);              // this warp's share of the accumulator is drained
     }
     if (etid == 0) tma_store_wait_all();
   }

@@ -21,6 +21,10 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rb {
@@ -435,6 +439,174 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
   }
 }
 
+// ---- step 2, row-granular form: one bulk async copy (TMA 1-D, SASS UBLKCP) per row ---------------------------------------
+// Same tiles, same order of additions, same sink arithmetic as seg_reduce_tiles_kernel — what changes is who moves the bytes.
+// There, every lane issues one 16-byte cp.async per row kind and entry (4 LDGSTS per entry and lane): at config 2 the
+// LSU / MIO queues saturate before HBM does (ncu r1_15: mio_throttle + short_scoreboard = 41 % of the stalls at 73 % DRAM
+// utilisation).  Here lane 0 of a group issues ONE cp.async.bulk per row — the gradient row, and for an entry that closes
+// a run this tile owns the W / m / v rows — into the group's ring slot, completion counted in bytes by the slot's mbarrier;
+// the lanes then read their 16-byte slices.  Applies to plain gradients (one source tensor per use of the table, no
+// scaling, no FM term: DLRM, and the per-rank dE buffers of the sharded path) with rows that are multiples of 16 bytes.
+constexpr int kBulkRing = 4;       // entries in flight per group
+
+__device__ __forceinline__ uint32_t su_saddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void su_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(su_saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void su_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su_saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void su_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su_saddr(dst)), "l"(src),
+               "r"(bytes), "r"(su_saddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void su_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(su_saddr(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();     // a byte count that never completes must not hang the device
+  } while (!ok);
+}
+
+template <int VEC, int GS>
+__global__ void __launch_bounds__(kSegThreads)
+seg_reduce_tiles_bulk_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
+                             const __grid_constant__ GradGroupsDev gsrc, OptSink sink, float* __restrict__ head_part,
+                             float* __restrict__ tail_part) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
+  sink.prepare();
+  constexpr int kGroups = kSegThreads / GS;
+  constexpr int kEntries = kGroups * kTile;
+  constexpr int kKinds = 4;                            // gradient, W, state0, state1
+  __shared__ uint32_t s_key[kEntries + 2];
+  __shared__ uint32_t s_pos[kEntries];
+  __shared__ __align__(8) uint64_t s_bar[kGroups * kBulkRing];
+  extern __shared__ __align__(16) float ring[];        // [kGroups][kBulkRing][kKinds][D]
+
+  const int D = gsrc.D;
+  const uint32_t row_bytes = static_cast<uint32_t>(D) * 4u;
+  const int cta_base = blockIdx.x * kEntries;
+  const int cta_cnt = min(kEntries, n - cta_base);
+  if (cta_cnt <= 0) return;
+  for (int i = threadIdx.x; i < cta_cnt; i += kSegThreads) {
+    s_key[i + 1] = keys[cta_base + i];
+    s_pos[i] = vals[cta_base + i];
+  }
+  if (threadIdx.x == 0) {
+    s_key[0] = (cta_base > 0) ? keys[cta_base - 1] : 0u;
+    s_key[cta_cnt + 1] = (cta_base + cta_cnt < n) ? keys[cta_base + cta_cnt] : 0u;
+  }
+  if (threadIdx.x < kGroups * kBulkRing) su_mbar_init(&s_bar[threadIdx.x], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int group = threadIdx.x / GS;
+  const int lane = threadIdx.x % GS;
+  const int tbase = group * kTile;
+  const int tcnt = min(kTile, cta_cnt - tbase);
+  if (tcnt <= 0) return;
+  const unsigned gmask = (GS == 32) ? 0xFFFFFFFFu : (((1u << GS) - 1u) << ((threadIdx.x % 32) / GS * GS));
+  const bool active = lane * VEC < D;
+  const int c = lane * VEC;
+  const int gbase = cta_base + tbase;
+  const int tile_id = gbase / kTile;
+  const bool has_prev = gbase > 0;
+  const bool has_next = gbase + tcnt < n;
+  const uint32_t* tk = s_key + 1 + tbase;
+  const uint32_t* tp = s_pos + tbase;
+  const uint32_t first_key = tk[0];
+  const bool cont_first = has_prev && (tk[-1] == first_key);
+  float* my_ring = ring + static_cast<size_t>(group) * kBulkRing * kKinds * D;
+  uint64_t* my_bar = s_bar + group * kBulkRing;
+  const int opt = sink.opt;
+  const bool ld_w = opt != RB_OPT_ADAM_TF_DENSE, ld_s0 = opt != RB_OPT_SGD, ld_s1 = (opt == RB_OPT_ADAM_LAZY || opt == RB_OPT_ADAM_TF_DENSE);
+  const uint32_t state_bytes = row_bytes * (static_cast<uint32_t>(ld_w) + static_cast<uint32_t>(ld_s0) + static_cast<uint32_t>(ld_s1));
+
+  auto run_ends_at = [&](int j, uint32_t key) {
+    return (j == tcnt - 1) ? !(has_next && tk[tcnt] == key) : (tk[j + 1] != key);
+  };
+  auto issue = [&](int j, int slot) {            // lane 0 of the group only
+    if (j >= tcnt) return;
+    const uint32_t key = tk[j];
+    const GradPos q = decode_pos(gsrc, tp[j]);
+    float* dst = my_ring + slot * kKinds * D;
+    uint64_t* bar = my_bar + slot;
+    const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
+    su_mbar_expect_tx(bar, row_bytes + (update ? state_bytes : 0u));
+    su_bulk_g2s(dst, grad_src0(gsrc, q, 0), row_bytes, bar);
+    if (update) {
+      const int64_t o = static_cast<int64_t>(key) * D;
+      if (ld_w) su_bulk_g2s(dst + D, sink.table + o, row_bytes, bar);
+      if (ld_s0) su_bulk_g2s(dst + 2 * D, sink.s0 + o, row_bytes, bar);
+      if (ld_s1) su_bulk_g2s(dst + 3 * D, sink.s1 + o, row_bytes, bar);
+    }
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kBulkRing; ++j) issue(j, j);
+  }
+  Row<VEC> acc = zero_row<VEC>();
+  uint32_t cur = first_key;
+  int seg_start = 0;
+  bool continues_prev = cont_first;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int j = 0; j < tcnt; ++j) {
+    su_mbar_wait(my_bar + slot, parity);
+    const uint32_t key = tk[j];
+    const float* sl = my_ring + slot * kKinds * D;
+    Row<VEC> g = zero_row<VEC>(), w = zero_row<VEC>(), m = zero_row<VEC>(), v = zero_row<VEC>();
+    if (key != cur) {
+      cur = key;
+      acc = zero_row<VEC>();
+      seg_start = j;
+      continues_prev = false;
+    }
+    const bool ends = run_ends_at(j, cur);
+    const bool update = ends && !continues_prev;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g.v[i] = sl[c + i];
+      if (update) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          w.v[i] = sl[D + c + i];
+          m.v[i] = sl[2 * D + c + i];
+          v.v[i] = sl[3 * D + c + i];
+        }
+      }
+    }
+    __syncwarp(gmask);                           // every lane of the group has read the slot: it may be refilled
+    if (lane == 0) issue(j + kBulkRing, slot);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], g.v[i]);
+    if (ends) {
+      if (continues_prev) {
+        if (active) st_row<VEC>(head_part + static_cast<int64_t>(tile_id) * D + c, acc);
+      } else if (active) {
+        sink.template update_row<VEC>(static_cast<int64_t>(cur) * D + c, acc, w, m, v);
+      }
+    } else if (j == tcnt - 1 && active) {
+      float* dst = continues_prev ? head_part : tail_part;
+      st_row<VEC>(dst + static_cast<int64_t>(tile_id) * D + c, acc);
+    }
+    if (++slot == kBulkRing) {
+      slot = 0;
+      parity ^= 1;
+    }
+  }
+}
+
 // ---- step 3: runs that cross tile borders -------------------------------------------------------------------
 __device__ __forceinline__ int run_end(const uint32_t* __restrict__ keys, int lo, int n, uint32_t key) {
   // first index in [lo, n) whose key differs from `key` (keys are sorted, keys[lo-1] == key)
@@ -637,6 +809,24 @@ static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_
   return RB_OK;
 }
 
+// RB_SEG_BULK=0 in the environment keeps the per-lane cp.async kernel (A/B measurements)
+static bool bulk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RB_SEG_BULK");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+// gradient rows in PEER memory (sharded path): opt-in until measured over NVLink
+static bool bulk_peer_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RB_SEG_BULK_PEER");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 template <class Sink>
 static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t* vals, int n, const GradGroupsDev& gsrc,
                         const Sink& sink, unsigned char* ws, const WsLayout& lay, cudaStream_t st, const int* n_dev = nullptr) {
@@ -649,11 +839,27 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
   const int cap = long_list_cap(n);
   const GradSrcDev& g0 = gsrc.g[0];
   const bool simple = gsrc.num == 1 && g0.num_src == 1 && g0.scale_mode == RB_SCALE_NONE && g0.fm_g == nullptr;
+  // plain gradient rows (every use of the table: one source tensor, no scaling, no FM term) of 16-byte multiples, all
+  // 16-byte aligned: the row-granular bulk-copy kernel
+  bool bulk = std::is_same<Sink, OptSink>::value && geo.vec == 4 && bulk_enabled() && (gsrc.peer == 0 || bulk_peer_enabled());
+  for (int k = 0; k < gsrc.num && bulk; ++k) {
+    const GradSrcDev& gk = gsrc.g[k];
+    bulk = gk.num_src == 1 && gk.scale_mode == RB_SCALE_NONE && gk.fm_g == nullptr && gk.bag_stride[0] % 4 == 0 && gk.pos_stride[0] % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(gk.src[0]) & 15) == 0;
+  }
 #define CALL(V, G)                                                                                                      \
   {                                                                                                                     \
     constexpr int kGroups = kSegThreads / G;                                                                            \
     const size_t ring_bytes = static_cast<size_t>(kRing) * (1 + Sink::kStateRows) * kSegThreads * V * sizeof(float);   \
-    if (simple) {                                                                                                       \
+    if (bulk) {                                                                                                         \
+      const size_t bulk_bytes = static_cast<size_t>(kGroups) * kBulkRing * 4 * gsrc.D * sizeof(float);                  \
+      if constexpr (std::is_same<Sink, OptSink>::value) {                                                               \
+        RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     static_cast<int>(bulk_bytes)));                                                    \
+        seg_reduce_tiles_bulk_kernel<V, G><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, gsrc, \
+                                                                                                      sink, head, tail); \
+      }                                                                                                                 \
+    } else if (simple) {                                                                                                \
       if (ring_bytes > 40 * 1024)                                                                                       \
         RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      static_cast<int>(ring_bytes)));                                                    \

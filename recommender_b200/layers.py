@@ -403,12 +403,18 @@ class _DenseStackFn(torch.autograd.Function):
     x is either the padded bf16 K operand [B, Kp] (what the fused interaction kernel emits; `ones_col` says its column
     `in_dim` holds 1.0) or the raw f32 [B, in_dim] features, which are packed here (rb_dense_pack_input).  One C-ABI call
     per product: y = x W + b (rb_dense_fwd), dx = dy W^T (rb_dense_bwd_input), dW = x^T dy (rb_dense_bwd_weight; with the
-    ones column its row `in_dim` is the bias gradient), and the Dense(1) head as a row dot product (rb_dense_head_*)."""
+    ones column its row `in_dim` is the bias gradient), and the Dense(1) head as a row dot product (rb_dense_head_*).
+
+    Backward: only the dx chain is on the step's critical path (it feeds the interaction backward and, through it, the
+    sparse row update).  The weight and bias gradients run on the module's own stream beside it and are written straight
+    into the parameters' .grad; the streams meet again when the backward pass ends (`MLP._join_wgrad`, queued as an
+    autograd-engine callback), so readers of .grad on the caller's stream see finished values."""
 
     @staticmethod
-    def forward(ctx, x, in_dim, Kp, ones_col, final_activation, need_dx, *params):
+    def forward(ctx, x, mlp, Kp, ones_col, need_dx, *params):
         Ws, bs = params[0::2], params[1::2]
         n = len(Ws)
+        in_dim, final_activation = mlp.in_dim, mlp.final_activation
         raw = x.dtype != torch.bfloat16
         if raw:
             ones_col = Kp > in_dim
@@ -428,41 +434,67 @@ class _DenseStackFn(torch.autograd.Function):
                 h = ops.dense_fwd(h, Wp, b, None, torch.bfloat16)
                 acts.append(h)
         ctx.save_for_backward(out, *acts, *shadows)
-        ctx.n, ctx.in_dim, ctx.ones_col, ctx.act, ctx.need_dx, ctx.raw = n, in_dim, bool(ones_col) and Kp > in_dim, final_activation, need_dx, raw
+        ctx.mlp, ctx.n, ctx.ones_col, ctx.need_dx, ctx.raw = mlp, n, bool(ones_col) and Kp > in_dim, need_dx, raw
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        n = ctx.n
+        n, mlp = ctx.n, ctx.mlp
+        in_dim, act = mlp.in_dim, mlp.final_activation
         saved = ctx.saved_tensors
         out, acts, shadows = saved[0], saved[1:1 + n], saved[1 + n:]
-        grads = [None] * (2 * n)
+        Ws, bs = list(mlp.kernels), list(mlp.biases)
         dout = dout.contiguous().float()
+        main = torch.cuda.current_stream()
+        wg, ws = mlp._wgrad_begin(acts, shadows)
+
+        def assign(p, g):           # runs inside the wgrad stream context
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+
+        def wgrad(i, x_i, dy_i, have_db=None):
+            """dW_i (and db_i) on the wgrad stream, from operands the main stream has just produced."""
+            W, b = Ws[i], bs[i]
+            dW_full = torch.empty(x_i.shape[1], W.shape[1], dtype=torch.float32, device=x_i.device)
+            db = torch.empty(W.shape[1], dtype=torch.float32, device=x_i.device) if not (i == 0 and ctx.ones_col) else None
+            wg.wait_event(main.record_event())
+            mlp._wgrad_keep.extend((x_i, dy_i, dW_full, db))
+            with torch.cuda.stream(wg):
+                ops.dense_bwd_weight(x_i, dy_i, out=dW_full, ws=ws)
+                if db is not None:
+                    ops.colsum(dy_i, out=db, ws=ws)
+                if i == 0:
+                    assign(W, dW_full[:in_dim])
+                    assign(b, dW_full[in_dim] if db is None else db)
+                else:
+                    assign(W, dW_full)
+                    assign(b, db)
+
         h, Wp = acts[n - 1], shadows[n - 1]
         want_dx = n > 1 or ctx.need_dx
         if Wp.shape[1] == 1:
-            dy, dw, db = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), ctx.act, h, Wp.reshape(-1), want_dx=want_dx)
-            dW_full = dw.reshape(-1, 1)
+            dy, dw, db = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), act, h, Wp.reshape(-1), want_dx=want_dx)
+            dw = dw[:in_dim] if n == 1 else dw
+            for p_, g_ in ((Ws[n - 1], dw.reshape(-1, 1)), (bs[n - 1], db)):
+                if p_.grad is None:
+                    p_.grad = g_
+                else:
+                    p_.grad.add_(g_)
         else:
-            dyp = ops.dense_act_bwd(dout, out, ctx.act)
-            dW_full = ops.dense_bwd_weight(h, dyp)
-            db = ops.colsum(dyp)
+            dyp = ops.dense_act_bwd(dout, out, act)
             dy = ops.dense_bwd_input(dyp, Wp) if want_dx else None
-        for i in range(n - 1, -1, -1):
-            if i < n - 1:
-                h, Wp = acts[i], shadows[i]
-                dW_full = ops.dense_bwd_weight(h, dy)
-                db = None if (i == 0 and ctx.ones_col) else ops.colsum(dy)
-                dy = ops.dense_bwd_input(dy, Wp) if (i > 0 or ctx.need_dx) else None
-            if i == 0:
-                grads[0] = dW_full[: ctx.in_dim]
-                grads[1] = dW_full[ctx.in_dim].clone() if db is None else db
-            else:
-                grads[2 * i], grads[2 * i + 1] = dW_full, db
+            wgrad(n - 1, h, dyp)
+        for i in range(n - 2, -1, -1):
+            dy_i = dy
+            dy = ops.dense_bwd_input(dy_i, shadows[i]) if (i > 0 or ctx.need_dx) else None
+            wgrad(i, acts[i], dy_i)
+        mlp._wgrad_end()
         dx = dy
         if dx is not None and ctx.raw:
-            dx = dx[:, : ctx.in_dim].float()
-        return (dx if ctx.need_dx else None, None, None, None, None, None, *grads)
+            dx = dx[:, :in_dim].float()
+        return (dx if ctx.need_dx else None, None, None, None, None, *([None] * (2 * n)))
 
 
 class _CollapsedAffineFn(torch.autograd.Function):
@@ -545,6 +577,11 @@ class MLP(nn.Module):
         super().__init__()
         self.collapse_linear = bool(collapse_linear)     # opt-in: evaluate the linear stack as ONE affine map (_CollapsedAffineFn)
         self.backend = "tcgen05"                          # bf16 mode: csrc/mlp.cu kernels; "cublas" = torch.addmm / mm
+        self._wgrad_stream: Optional[torch.cuda.Stream] = None
+        self._wgrad_ws: Optional[torch.Tensor] = None
+        self._wgrad_done: Optional[torch.cuda.Event] = None
+        self._wgrad_keep: list = []
+        self._wgrad_join_queued = False
         if final_activation not in (None, "relu", "sigmoid"):
             raise ValueError(final_activation)
         if compute_dtype not in (None, torch.float32, torch.bfloat16):
@@ -571,6 +608,36 @@ class MLP(nn.Module):
         self.kernels = nn.ParameterList(nn.Parameter(torch.as_tensor(W, dtype=torch.float32).to(device).contiguous()) for W, _ in layers)
         self.biases = nn.ParameterList(nn.Parameter(torch.as_tensor(b, dtype=torch.float32).to(device).contiguous()) for _, b in layers)
         self.in_dim = int(self.kernels[0].shape[0])
+
+    # -- weight gradients beside the dx chain (see _DenseStackFn) -------------------------------------------------------
+    def _wgrad_begin(self, acts, shadows):
+        dev = acts[0].device
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(device=dev)
+        rows = acts[0].shape[0]
+        need = 256
+        for a, w in zip(acts, shadows):
+            if w.shape[1] > 1:
+                need = max(need, ops.dense_bwd_weight_workspace_bytes(rows, a.shape[1], w.shape[1]),
+                           int(ops.lib.rb_colsum_workspace_bytes(rows, w.shape[1])))
+        if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
+            self._wgrad_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._wgrad_keep.append(self._wgrad_ws)
+        return self._wgrad_stream, self._wgrad_ws
+
+    def _wgrad_end(self) -> None:
+        self._wgrad_done = self._wgrad_stream.record_event()
+        if not self._wgrad_join_queued:
+            self._wgrad_join_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._join_wgrad)
+
+    def _join_wgrad(self) -> None:
+        """The caller's stream waits for the weight gradients; operands the wgrad stream was reading may be freed after that."""
+        self._wgrad_join_queued = False
+        if self._wgrad_done is not None:
+            torch.cuda.current_stream().wait_event(self._wgrad_done)
+            self._wgrad_done = None
+        self._wgrad_keep.clear()
 
     def _tcgen05_ok(self, x: torch.Tensor) -> bool:
         """The hand-written tcgen05 Dense kernels serve CUDA inputs when every hidden width is a multiple of 8 (16-byte row
@@ -616,7 +683,7 @@ class MLP(nn.Module):
             if x.shape[-1] != self.in_dim:
                 raise ValueError(f"MLP built for {self.in_dim} input features, got {x.shape[-1]}")
             flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
-            return _DenseStackFn.apply(x.float(), self.in_dim, Kp, False, self.final_activation, need_dx, *flat)   # packed inside
+            return _DenseStackFn.apply(x.float(), self, Kp, False, need_dx, *flat)   # packed inside
         if x.dtype != torch.bfloat16 or x.shape[-1] != Kp:
             if x.shape[-1] != self.in_dim:
                 raise ValueError(f"MLP built for {self.in_dim} input features, got {x.shape[-1]}")
@@ -633,7 +700,7 @@ class MLP(nn.Module):
             return self._activate(_CollapsedAffineFn.apply(x, self.in_dim, need_dx, ones_col, *flat))
         if self._tcgen05_ok(x):
             flat = [t for Wb in zip(self.kernels, self.biases) for t in Wb]
-            return _DenseStackFn.apply(x, self.in_dim, Kp, ones_col, self.final_activation, need_dx, *flat)
+            return _DenseStackFn.apply(x, self, Kp, ones_col, need_dx, *flat)
         for i, (W, b) in enumerate(zip(self.kernels, self.biases)):
             x = _LinearBF16Fn.apply(x, W, b, need_dx or i > 0, ones_col and i == 0)
         return self._activate(x)

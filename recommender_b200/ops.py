@@ -410,14 +410,16 @@ def dense_opt_step(params, grads, state0, state1, *, optimizer="adam_lazy", step
         check(lib.rb_dense_opt_step(arr, hi - lo, C.byref(opt), _stream()), "rb_dense_opt_step")
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+def colsum(x: torch.Tensor, out=None, ws=None) -> torch.Tensor:
     """fp32 column sums of a [rows, cols] float32 / bfloat16 matrix (rb_colsum): a Dense bias gradient."""
     _need_cuda(x)
     if x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("colsum takes a [rows, cols] matrix with unit inner stride")
     rows, cols = x.shape
-    out = torch.empty(cols, dtype=torch.float32, device=x.device)
-    ws = _workspace(max(lib.rb_colsum_workspace_bytes(rows, cols), 256), x.device)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    if ws is None:
+        ws = _workspace(max(lib.rb_colsum_workspace_bytes(rows, cols), 256), x.device)
     check(lib.rb_colsum(_ptr(x), _float_type(x.dtype), rows, cols, int(x.stride(0)), _ptr(out), _ptr(ws), ws.numel(), _stream()),
           "rb_colsum")
     return out
@@ -478,18 +480,24 @@ def dense_bwd_input(dy, w, out=None):
     return out
 
 
-def dense_bwd_weight(x, dy, out=None):
-    """dW = x.T @ dy in fp32 (rb_dense_bwd_weight), deterministic split over the batch.  x bf16 [rows, in_dim], dy bf16 [rows, units]."""
+def dense_bwd_weight_workspace_bytes(rows: int, in_dim: int, units: int) -> int:
+    nbytes = lib.rb_dense_bwd_weight_workspace_bytes(rows, in_dim, units)
+    if nbytes == 0:
+        raise _lib.RecsysError(f"rb_dense_bwd_weight rejected the problem size ({rows}, {in_dim}, {units})")
+    return int(nbytes)
+
+
+def dense_bwd_weight(x, dy, out=None, ws=None):
+    """dW = x.T @ dy in fp32 (rb_dense_bwd_weight), deterministic split over the batch.  x bf16 [rows, in_dim], dy bf16 [rows, units].
+    `ws`: a private workspace (a call on a stream other than the one the shared per-device workspace serves)."""
     _need_cuda(x, dy, out)
     _bf16m(x, "x"), _bf16m(dy, "dy")
     rows, in_dim = x.shape
     units = dy.shape[1]
     if out is None:
         out = torch.empty(in_dim, units, dtype=torch.float32, device=x.device)
-    nbytes = lib.rb_dense_bwd_weight_workspace_bytes(rows, in_dim, units)
-    if nbytes == 0:
-        raise _lib.RecsysError(f"rb_dense_bwd_weight rejected the problem size ({rows}, {in_dim}, {units})")
-    ws = _workspace(nbytes, x.device)
+    if ws is None:
+        ws = _workspace(dense_bwd_weight_workspace_bytes(rows, in_dim, units), x.device)
     check(lib.rb_dense_bwd_weight(_ptr(x), rows, in_dim, x.stride(0), _ptr(dy), units, dy.stride(0), _ptr(out), out.stride(0), _ptr(ws),
                                   ws.numel(), _stream()), "rb_dense_bwd_weight")
     return out

@@ -99,9 +99,21 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--only", default="fwd,bwd_input,bwd_weight,head")
     ap.add_argument("--quick", action="store_true", help="the two smallest cases of each product only")
+    ap.add_argument("--profile", action="store_true", help="no checks: 3 launches of each product at 65536 x 800 x 512 (for ncu)")
     a = ap.parse_args()
     only = a.only.split(",")
     ok = True
+    if a.profile:
+        B, i, u = 65536, 800, 512
+        x, w, dy = rnd(B, i), rnd(i, u, scale=i ** -0.5), rnd(B, u)
+        bias = torch.zeros(u, device=dev)
+        for _ in range(3):
+            ops.dense_fwd(x, w, bias, None)
+            ops.dense_bwd_input(dy, w)
+            ops.dense_bwd_weight(x, dy)
+        torch.cuda.synchronize()
+        print("profiled")
+        return
     if "fwd" in only:
         cases = [(128, 64, 64), (256, 128, 256), (300, 800, 512), (1000, 16, 512), (128, 512, 256), (4096, 512, 256)]
         for rows, i, u in cases[:2] if a.quick else cases:
