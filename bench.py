@@ -69,7 +69,10 @@ def parse_args():
     ap.add_argument("--criteo-tb", action="store_true",
                     help="BASELINE config 3 (N > 1 only): 26 tables with the capped Criteo-Terabyte cardinalities (187.8M rows), row-wise sharded")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
-    ap.add_argument("--cpu-sample-batch", type=int, default=8192)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="batch of the CPU reference arm; 0 = the GPU arm's batch (its Keras dense-Adam passes cost the same whatever the batch)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the second, sustained timed region (value_sustained)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short lines of the other BASELINE configs / id distributions (extra)")
     ap.add_argument("--ref-adam", default="tf_dense", choices=["tf_dense", "lazy"],
                     help="Adam semantics of the CPU reference arm: Keras' dense passes (what the reference runs) or lazy")
     return ap.parse_args()
@@ -163,7 +166,7 @@ def time_cpu_reference(args, steps, warmup, budget_s=None):
     from oracle.torch_cpu_ref import DLRMRef
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = args.cpu_sample_batch
+    B = args.cpu_sample_batch or args.batch
     ref = DLRMRef(BOTTOM[:-1] + [args.emb_dim], TOP, args.emb_dim, args.rows_per_table, num_tables=args.tables, seed=4,
                   adam=args.ref_adam)
     batches = synth_batches(2, B, args.rows_per_table, args.dist, seed=4, pin=False)
@@ -180,7 +183,7 @@ def time_cpu_reference(args, steps, warmup, budget_s=None):
         if budget_s and time.perf_counter() - t_start > budget_s:
             break
     sec = sum(times) / len(times)
-    sample = (f"{len(times)} steps of B={B} (1/{max(1, args.batch // B)} of the GPU batch) on the same DLRM "
+    sample = (f"{len(times)} steps of B={B} ({'the GPU batch' if B == args.batch else f'1/{max(1, args.batch // B)} of the GPU batch'}) on the same DLRM "
               f"({args.tables}x{args.rows_per_table}-row tables, D={args.emb_dim}); torch-CPU restatement of ctr/model.py + "
               f"Keras Adam ({args.ref_adam}), TensorFlow absent")
     return dict(value=B / sec, unit=UNIT, cores=cores, kind="port", sample=sample), sec * 1e3, len(times)
@@ -210,7 +213,8 @@ def workload_config(args, world):
                 bottom_mlp=BOTTOM[:-1] + [args.emb_dim], top_mlp=TOP, ids=args.dist, mlp_dtype=args.mlp_dtype,
                 mlp_backend=("tcgen05 Dense kernels (csrc/mlp.cu)" if getattr(args, "mlp_backend", "tcgen05") == "tcgen05" else "torch / cuBLASLt")
                 if args.mlp_dtype == "bf16" else "torch fp32",
-                sparse_optimizer="adam_lazy",
+                sparse_optimizer="adam_lazy (Keras Adam formula on the touched rows; the CPU arm runs Keras' dense passes, tf_dense: "
+                                 "the two agree on step 1 from zero state and differ afterwards, tests/test_gpu_kernels.py)",
                 mlp_evaluation="collapsed affine map per tower (opt-in)" if getattr(args, "collapse_mlp", False) and world == 1
                 else "layer by layer",
                 parallelism="single GPU" if world == 1 else (
@@ -218,6 +222,141 @@ def workload_config(args, world):
                     if args.exchange == "p2p" else f"{args.sharding}-wise sharded tables x{world}, NCCL all-to-all + data-parallel MLPs"),
                 l2="inputs larger than L2: tables %.1f GB, ring of %d batches, 436 MB gradient tensor per step" % (
                     args.tables * args.rows_per_table * args.emb_dim * 4 / 1e9, args.ring))
+
+
+# ---------------------------------------------------------------------------------------------------
+# short lines for the other BASELINE configs and id distributions (N = 1; the `extra` object of the JSON line)
+# ---------------------------------------------------------------------------------------------------
+
+ESMM_VOCAB = [238635, 98, 14, 3, 8, 4, 4, 3, 5, 467298, 6929, 263942, 106399, 5888, 104830, 51878, 37148, 4]      # esmm/train.py:197-215
+
+
+def _time_loop(fn, iters, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def extra_lines(args, dev, model, graphed_step, peak):
+    """SURVEY §8d asks for both id distributions and for T = 1 as well as T = 26; BASELINE configs 1, 4 and 5 get one short
+    line each.  Everything here is a few dozen launches; inputs larger than L2 wherever the config is."""
+    from recommender_b200 import ops
+    from recommender_b200.graph import GraphedTrainStep
+    from recommender_b200.model import DLRM, DeepFM, bce_clipped, bce_logits
+    from recommender_b200.ops import GradSource, LookupGroup
+    from recommender_b200.optimizers import Adam
+    D, V, B = args.emb_dim, args.rows_per_table, args.batch
+    cd = torch.bfloat16 if args.mlp_dtype == "bf16" else None
+    out = {}
+
+    def dlrm_line(tables, dist, step_fn=None):
+        if step_fn is None:
+            g = torch.Generator(device=dev).manual_seed(4)
+            m = DLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=tables, device=dev, compute_dtype=cd, generator=g)
+            for mod in m.modules():
+                if hasattr(mod, "backend"):
+                    mod.backend = args.mlp_backend
+            first = [tuple(t.to(dev) for t in b) for b in synth_batches(1, B, V, dist, seed=4, pin=False)]
+            step_fn = GraphedTrainStep(m, Adam(), bce_clipped, first[0], warmup=3).step
+        batches = [tuple(t.to(dev) for t in b) for b in synth_batches(4, B, V, dist, seed=5, pin=False)]
+        ms = _time_loop(lambda i: step_fn(batches[i % 4]), 20)
+        rows0 = batches[0][0] if tables == 1 else batches[0][0] + (torch.arange(tables, device=dev) * V)[None]
+        return dict(ms_per_step=ms, samples_per_s=B / ms * 1e3, unique_rows=int(torch.unique(rows0).numel()), tables=tables, ids=dist)
+
+    if graphed_step is not None and args.dist != "zipf":
+        out[f"dlrm_cfg2_T{args.tables}_zipf"] = dlrm_line(args.tables, "zipf", graphed_step)      # the headline model, skewed ids
+    other_t = 1 if args.tables == 26 else 26
+    if other_t == 1:      # one shared 1M-row table: the reference's own layout (ctr/model.py:42)
+        out["dlrm_cfg2_T1_uniform"] = dlrm_line(1, "uniform")
+        out["dlrm_cfg2_T1_zipf"] = dlrm_line(1, "zipf")
+
+    # BASELINE config 1: DeepFM through ctr/train.py's constants, B = 1024, D = 16, one shared 1M-row table, MLP 512-256-1
+    class _Logits(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, inputs):
+            return self.m.logits(inputs)
+
+    g = torch.Generator(device=dev).manual_seed(4)
+    B1 = 1024
+    fm = _Logits(DeepFM(16, 1_000_000, 13, 26, [512, 256, 1], device=dev, generator=g, compute_dtype=cd))
+    ring = [tuple(t.to(dev) for t in b) for b in synth_batches(4, B1, 1_000_000, "uniform", seed=4, pin=False)]
+    ring = [(c, d, l.float()) for c, d, l in ring]
+    gs = GraphedTrainStep(fm, Adam(), bce_logits, ring[0], warmup=3)
+    ms = _time_loop(lambda i: gs.step(ring[i % 4]), 50)
+    out["deepfm_cfg1_B1024"] = dict(ms_per_step=ms, samples_per_s=B1 / ms * 1e3, launch_mode="cuda_graph",
+                                    note="launch-latency-bound on a B200 (SURVEY §8d): 3.6 MB of gather per step")
+    del fm, gs
+
+    # BASELINE config 4: masked mean over a behaviour history (dien/layers.py:5-17), L = 100, D = 32, item table of 400k rows
+    Lh, Dh, Vh = 100, 32, 400_000
+    g = torch.Generator(device=dev).manual_seed(4)
+    wt = torch.empty(Vh, Dh, device=dev).uniform_(-0.05, 0.05, generator=g)
+    lens = torch.randint(1, Lh + 1, (B, 1), device=dev, generator=g)
+    hist = torch.randint(1, Vh, (B, Lh), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+    hist = torch.where(torch.arange(Lh, device=dev)[None] < lens, hist, torch.zeros_like(hist))     # trailing pads (dien/data_loader.py:44)
+    pout = torch.empty(B, Dh, device=dev)
+    ms_f = _time_loop(lambda i: ops.bag_pool_fwd(wt, hist, "masked_mean", out=pout, out_stride=Dh), 20)
+    valid = int((hist != 0).sum())
+    fbytes = valid * Dh * 4 + B * Lh * 4 + B * Dh * 4
+    dpool = torch.randn(B, Dh, device=dev, generator=g) * 1e-3
+    cnt = (hist != 0).sum(1).float()
+    mh, vh = torch.zeros_like(wt), torch.zeros_like(wt)
+    stp = [0]
+
+    def hupd(i):
+        stp[0] += 1
+        grp = LookupGroup(hist, Lh, GradSource.per_bag([dpool], scale="masked_mean", mask_idx=hist, count=cnt))
+        ops.sparse_bwd_update(wt, mh, vh, [grp], optimizer="adam_lazy", step=stp[0])
+    ms_b = _time_loop(hupd, 10)
+    out["dien_cfg4_masked_mean"] = dict(batch=B, history=Lh, emb_dim=Dh, valid_positions=valid, fwd_ms=ms_f, fwd_algorithmic_bytes=fbytes,
+                                        fwd_gbs=fbytes / ms_f / 1e6, fwd_frac=fbytes / ms_f / 1e6 / peak, bwd_update_ms=ms_b,
+                                        samples_per_s_fwd_bwd=B / (ms_f + ms_b) * 1e3)
+    del wt, mh, vh, hist
+
+    # BASELINE config 5: 26 tables (vocab sizes cycled from esmm/train.py:197-215), D = 32, bag size 1, gradients of 2 (ESMM) and
+    # 10 (MMOE) consumers added inside the scatter (esmm/esmm.py:15-24)
+    D5, T5 = 32, 26
+    vocab = [ESMM_VOCAB[k % len(ESMM_VOCAB)] for k in range(T5)]
+    g = torch.Generator(device=dev).manual_seed(4)
+    tabs = [torch.empty(v, D5, device=dev).uniform_(-0.05, 0.05, generator=g) for v in vocab]
+    ms_ = [(torch.zeros_like(t), torch.zeros_like(t)) for t in tabs]
+    idx5 = [torch.randint(0, v, (B, 1), device=dev, generator=g, dtype=torch.int64).to(torch.int32) for v in vocab]
+    width = D5 * T5
+    emb = torch.empty(B, width, device=dev)
+
+    def fwd5(i):
+        for k in range(T5):
+            ops.gather_fwd(tabs[k], idx5[k][:, 0], out=emb[:, k * D5:], out_stride=width)
+    ms_f5 = _time_loop(fwd5, 10)
+    res5 = dict(batch=B, tables=T5, emb_dim=D5, vocab_min=min(vocab), vocab_max=max(vocab), gather_concat_ms=ms_f5,
+                gather_algorithmic_bytes=B * T5 * (D5 * 4 * 2 + 4), gather_gbs=B * T5 * (D5 * 4 * 2 + 4) / ms_f5 / 1e6)
+    for nc in (2, 10):
+        cons = [torch.randn(B, width, device=dev, generator=g) * 1e-3 for _ in range(nc)]
+        stp5 = [0]
+
+        def upd5(i):
+            stp5[0] += 1
+            for k in range(T5):
+                src = GradSource([c[:, k * D5:] for c in cons], [width] * nc, [0] * nc)
+                ops.sparse_bwd_update(tabs[k], ms_[k][0], ms_[k][1], [LookupGroup(idx5[k], 1, src)], optimizer="adam_lazy", step=stp5[0])
+        ms_u = _time_loop(upd5, 5, warm=2)
+        uniq = sum(int(torch.unique(ix).numel()) for ix in idx5)
+        ubytes = B * T5 * (nc * D5 * 4 + 4) + uniq * D5 * 4 * 6
+        res5[f"scatter_adam_{nc}_consumers_ms"] = ms_u
+        res5[f"scatter_adam_{nc}_consumers_gbs"] = ubytes / ms_u / 1e6
+        del cons
+    out["esmm_cfg5_multi_table"] = res5
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -342,7 +481,10 @@ def run_b200(args):
                             "gather_fwd", "bucket_by_owner", "dense_opt_step", "colsum"])
     timer.install()
     if world > 1 and args.exchange == "p2p":
-        timer.install_on(model.embedding_layer, ["route", "collect_and_sort", "_interaction_fwd", "_interaction_bwd", "apply_pending"], "p2p.")
+        # every one of these runs with the stream it launches on as torch's current stream (route / collect_and_sort / _apply_rows
+        # inside `with torch.cuda.stream(side)`), so the bracketing events sit on the launching stream; the rendezvous barriers
+        # are outside the brackets
+        timer.install_on(model.embedding_layer, ["route", "collect_and_sort", "_interaction_fwd", "_interaction_bwd", "_apply_rows"], "p2p.")
 
     def barrier():
         if world > 1:
@@ -408,6 +550,36 @@ def run_b200(args):
     final_loss = float(loss.item())
     if hasattr(model.embedding_layer, "check_overflow"):
         model.embedding_layer.check_overflow()
+
+    # ---- the same loop for >= --sustain-seconds: the number a long job sees (clocks settle under the power cap) ----------
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / ms_step) + 1)
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for i in range(n_sus):
+            loss = train_step(resident[i % args.ring])
+        u1.record()
+        barrier()
+        sus_ms = max_over_ranks(u0.elapsed_time(u1))
+        sustained = dict(value=B * world * n_sus / (sus_ms / 1e3), unit=UNIT, steps=n_sus, seconds=sus_ms / 1e3, ms_per_step=sus_ms / n_sus,
+                         clocks=sampler2.stop() if rank == 0 else None)
+
+    # ---- N > 1: real-rank parity of the sharded path against the unsharded model (small problem, untimed) ---------------
+    parity = None
+    if world > 1 and args.exchange == "p2p":
+        from recommender_b200 import p2p_selfcheck
+        parity = {}
+        for tag, dt in (("fp32_towers", None), ("bf16_towers", torch.bfloat16)):
+            try:
+                parity[tag] = p2p_selfcheck.run(dev, compute_dtype=dt)
+            except Exception as e:                               # noqa: BLE001 - reported in the line, never hidden
+                parity[tag] = dict(error=f"{type(e).__name__}: {e}")
+                break
 
     # ---- e2e: pinned host buffers -> H2D copies, loss read back, all inside the timed region ---------------
     e2e = None
@@ -494,23 +666,36 @@ def run_b200(args):
                                  frac=gbs / peak, share_of_step=ms * cnt / k_eager / ms_step)
         else:
             kernels[name] = dict(ms=ms, calls_per_step=cnt / k_eager, share_of_step=ms * cnt / k_eager / ms_step)
-    if world > 1 and args.exchange == "p2p":
-        # bytes each rank pulls over NVLink per step: (G-1)/G of the rows (bf16 shadow) in the forward, of the fp32 gradient rows in the apply
-        remote = (world - 1) / world
-        for name, nbytes in (("p2p._interaction_fwd", N * D * 2 * remote), ("p2p.apply_pending", N * D * 4 * remote)):
-            if name in kernels:
-                kernels[name]["nvlink_bytes"] = int(nbytes)
-                kernels[name]["nvlink_gbs_if_alone"] = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
     roofline = None
     timed = {k: v for k, v in kernels.items() if "achieved_gbs" in v}
     if timed:
         top = max(timed, key=lambda k: timed[k]["ms"] * timed[k]["calls_per_step"])
         roofline = dict(bound="hbm", kernel=top, achieved=timed[top]["achieved_gbs"], peak=peak, unit="GB/s", frac=timed[top]["frac"],
                         traffic=traffic.get(top), peak_source=peak_src, unique_rows=U,
+                        frac_of_nominal_8tbs=timed[top]["achieved_gbs"] / 8000.0,
                         note="achieved = algorithmic bytes of the whole C-ABI call / its CUDA-event time on the launching stream. "
                              "sparse_bwd_apply = segmented reduction + fused Adam row update; its keys + radix sort "
                              "(sparse_bwd_prepare, overhead, not algorithmic bytes) run on a side stream during the forward; "
                              "sparse_bwd_update = both phases in one call")
+    if world > 1 and args.exchange == "p2p":
+        # Bytes each rank pulls over NVLink per step: (G-1)/G of the rows (bf16 shadow, 2 B per element) inside the forward kernel,
+        # (G-1)/G of the fp32 gradient rows inside the owner-side apply.  Both calls are bracketed by events on the stream they run on.
+        remote = (world - 1) / world
+        nv_peak, nv_measured = 900.0, 770.0      # nominal per direction per GPU; peer-copy rate measured on this pool (B200_PROFILING.md)
+        nv = {}
+        for name, nbytes in (("p2p._interaction_fwd", N * D * 2 * remote), ("p2p._apply_rows", N * D * 4 * remote)):
+            if name in kernels:
+                gbs = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
+                kernels[name].update(nvlink_bytes=int(nbytes), nvlink_gbs=gbs, nvlink_frac=gbs / nv_peak)
+                nv[name] = kernels[name]
+        if nv:
+            top = max(nv, key=lambda k: nv[k]["ms"])
+            roofline = dict(bound="nvlink", kernel=top, achieved=nv[top]["nvlink_gbs"], peak=nv_peak, unit="GB/s", frac=nv[top]["nvlink_frac"],
+                            traffic=None, peak_source="nominal NVLink 5, 900 GB/s per direction per GPU",
+                            frac_of_measured_peer_copy=nv[top]["nvlink_gbs"] / nv_measured,
+                            note="achieved = bytes this rank's kernel reads from PEER memory over NVLink ((G-1)/G of its rows: bf16 shadow rows "
+                                 "in the forward, fp32 gradient rows in the owner-side apply) / the CUDA-event time of that C call on its "
+                                 "launching stream; the same kernels also move their local HBM share in that time")
 
     # ---- the second half of BASELINE.json's metric: embedding-gather HBM GB/s (un-pooled lookup, rb_gather_fwd) ----------
     gather = None
@@ -532,8 +717,17 @@ def run_b200(args):
                       frac=g_bytes / (g_ms * 1e-3) / 1e9 / peak, peak=peak, lookups=N, emb_dim=D)
         del gout
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            extra = extra_lines(args, dev, model, train_step if use_graph else None, peak)
+        except Exception as e:                                   # noqa: BLE001 - the headline line must still be printed
+            extra = dict(error=f"{type(e).__name__}: {e}")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del resident
+        torch.cuda.empty_cache()
         cpu, _, _ = time_cpu_reference(args, steps=2, warmup=1, budget_s=90)
 
     if rank == 0:
@@ -541,7 +735,8 @@ def run_b200(args):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 tables/optimizer, bf16 MMA operands (f32 accumulate)",
                     data="synthetic", config=workload_config(args, world), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
                     kernels=kernels, cpu_baseline=cpu, clocks=clocks, final_loss=final_loss, host_cores=os.cpu_count(),
-                    launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step, embedding_gather=gather)
+                    launch_mode="cuda_graph" if use_graph else "eager", eager_ms_per_step=eager_ms_step, embedding_gather=gather,
+                    value_sustained=None if sustained is None else sustained["value"], sustained=sustained, parity=parity, extra=extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         # a captured graph holding NCCL kernels plus peer-mapped buffers makes interpreter teardown unreliable:

@@ -346,9 +346,11 @@ int rb_dense_head_fwd(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, 
 size_t rb_dense_head_bwd_workspace_bytes(int64_t rows, int32_t in_dim);
 
 /* Backward of the head: dz = dout * activation'(out);  dx[r,:] = bf16(dz[r] * w[:]) (optional);  dw[k] = sum_r x[r,k] * dz[r];
- * db[0] = sum_r dz[r].  Deterministic two-stage sums. */
+ * db[0] = sum_r dz[r];  dx_colsum[k] = sum_r dx[r,k] (optional, f32 [in_dim]: the bias gradient of the layer below, which
+ * would otherwise re-read dx).  Deterministic two-stage sums. */
 int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, const void* x, int64_t rows, int32_t in_dim, int64_t ldx,
-                      const void* w, void* dx, int64_t lddx, float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+                      const void* w, void* dx, int64_t lddx, float* dw, float* db, float* dx_colsum, void* ws, size_t ws_bytes,
+                      void* stream);
 
 /* out_bf16[i] = bf16(dy[i] * activation'(y[i])) over n contiguous f32 elements: the ReluGrad / SigmoidGrad in front of the
  * last layer's gradient GEMMs. */
@@ -357,6 +359,12 @@ int rb_dense_act_bwd(const float* dy, const float* y, int32_t activation, int64_
 /* out_bf16[rows, ld_out] = [x (f32 [rows, in_dim], ldx) | 1.0 if ones_col | 0 ...]: the padded bf16 K operand of a first Dense layer. */
 int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim, int64_t ldx, void* out_bf16, int32_t ld_out, int32_t ones_col,
                         void* stream);
+
+/* Diagnostic: when `device_buf` (u64 [8 * 148], zeroed by the caller) is non-NULL, every following Dense GEMM launch of this
+ * process records per CTA the cycles its roles spent waiting: [0] MMA issuer on operand stages, [1] MMA issuer on a drained
+ * accumulator, [2] MMA issuer total, [3] TMA producer on free stages, [4] producer total, [5] epilogue on a finished
+ * accumulator, [6] epilogue total.  NULL switches it off.  Tuning aid (scripts/mlp_check.py --stats); not thread-safe. */
+int rb_dense_debug_stats(void* device_buf);
 
 /* ---- id -> row map ------------------------------------------------------------------------ */
 

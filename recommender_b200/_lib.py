@@ -106,9 +106,10 @@ SIGNATURES = {
     "rb_dense_bwd_weight": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i64, _p, _i64, _p, C.c_size_t, _p]),
     "rb_dense_head_fwd": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i32, _p, _p]),
     "rb_dense_head_bwd_workspace_bytes": (C.c_size_t, [_i64, _i32]),
-    "rb_dense_head_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "rb_dense_head_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
     "rb_dense_act_bwd": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
     "rb_dense_pack_input": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i32, _p]),
+    "rb_dense_debug_stats": (C.c_int, [_p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),

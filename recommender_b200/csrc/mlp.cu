@@ -21,6 +21,7 @@
 // The weight gradient reduces over the batch: its few output tiles are split along the batch over all SMs, every split
 // writes an fp32 partial tile, and a second kernel adds the partials in split order (deterministic, no float atomics).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cuda_bf16.h>
@@ -54,6 +55,7 @@ struct GemmArgs {
   int32_t out_f32;             // 0: bf16 C;  1: fp32 C (split s writes rows [s * m_blocks * 128, ...) of the output map)
   int32_t activation;          // rb_activation, applied after the bias
   const float* bias;           // f32[N] or null
+  unsigned long long* stats;   // diagnostic (rb_dense_debug_stats): per CTA, cycles each role spent waiting; null = off
 };
 
 // ---- PTX: mbarrier, TMA, tcgen05 ----------------------------------------------------------------------------------
@@ -204,23 +206,86 @@ __device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const flo
   }
 }
 
-template <bool F32, int ACT>
-__global__ void __launch_bounds__(kThreads, 1)
-dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmArgs g) {
+// ---- the 2-CTA form (cta_group::2) ---------------------------------------------------------------------------------------
+// A CTA pair (the two SMs of a TPC, a cluster of 2) computes a 256 x N tile: CTA r owns rows [128 r, 128 r + 128) of A and of
+// the accumulator, and stages HALF of the B tile (N / 2 of its rows / columns); the leader's tcgen05.mma.cta_group::2 reads
+// both halves, so every byte of B crosses L2 -> SM once per 256 rows of C instead of once per 128.  At 128 x 256 tiles one
+// CTA alone needs 96 B / clk of operand fill against ~3000 cycles of L2 / DRAM latency — more bytes in flight than its
+// shared memory holds (ncu r2_04: tensor pipe 55 % busy, HBM 32 %, L2 35 %: waiting on data); the pair needs 64 B / clk.
+//   * both producers issue cp.async.bulk.tensor ... .cta_group::2 whose completion bytes land on the LEADER's full barrier;
+//     the leader's producer arms it with the bytes of both CTAs;
+//   * the leader's tcgen05.commit ... .multicast::cluster frees the stage / publishes the accumulator in BOTH CTAs;
+//   * both CTAs' epilogue warps arrive on the leader's acc_empty barrier (remote arrive through mapa).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the pair's even (leader) CTA
+
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(saddr(dst)),
+      "l"(map), "r"(saddr(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(saddr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(saddr(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+// CG = CTAs per tile (1, or 2 = a cta_group::2 pair launched as a cluster of 2)
+template <int CG, bool F32, int ACT>
+__device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_c,
+                                                const GemmArgs& g) {
+  constexpr int kNumStages = CG == 2 ? 6 : kStages;
+  constexpr int kBBytes = kBStageBytes / CG;              // this CTA's share of a B stage
   extern __shared__ __align__(1024) uint8_t smem[];      // 128-byte-swizzled tiles need 1024-byte aligned bases
   if ((saddr(smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + kStages * kAStageBytes;
-  uint8_t* smem_out = smem_b + kStages * kBStageBytes;
+  uint8_t* smem_b = smem_a + kNumStages * kAStageBytes;
+  uint8_t* smem_out = smem_b + kNumStages * kBBytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_out + kSlabs * kSlabBytes);
-  uint64_t* empty = full + kStages;
-  uint64_t* acc_full = empty + kStages;
+  uint64_t* empty = full + kNumStages;
+  uint64_t* acc_full = empty + kNumStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(smem_out + kSlabs * kSlabBytes + 256);   // the tile's kMaxN biases
+  float* s_bias = reinterpret_cast<float*>(smem_out + kSlabs * kSlabBytes + 256);   // the tile's kMaxN biases, one copy per group
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile_id0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
@@ -228,19 +293,23 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     prefetch_tensormap(&map_c);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNumStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4 * kEpilogueGroups);     // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], 4 * kEpilogueGroups * CG);     // one arrival per epilogue warp of the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything is signalled on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -251,74 +320,127 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      long long t_empty = 0;
+      const long long t_begin = clock64();
+      for (int w = tile_id0; w < total; w += tile_stride) {
         const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
-        const int m0 = m_blk * kBlockM, n0 = n_blk * g.block_n;
+        const int m0 = m_blk * (kBlockM * CG) + rank * kBlockM, n0 = n_blk * g.block_n;
         const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
-        // a tile that hangs over the right edge of C loads (MN-major B) and multiplies only the columns that exist
-        const int b_boxes = (min(g.block_n, g.N - n0) + 63) / 64;
-        const uint32_t stage_bytes = kAStageBytes + (g.b_mn ? static_cast<uint32_t>(b_boxes) * kAtomBytes : static_cast<uint32_t>(g.block_n) * 128u);
+        // a tile that hangs over the right edge of C multiplies only the columns that exist (rounded up to the MMA's N step);
+        // this CTA stages share `rank` of them
+        const int n_eff = min(g.block_n, (g.N - n0 + 16 * CG - 1) / (16 * CG) * (16 * CG));
+        const int n_mine = n_eff / CG, nb0 = n0 + rank * n_mine;
+        const int b_boxes = (n_mine + 63) / 64;
+        const uint32_t my_bytes = kAStageBytes + (g.b_mn ? static_cast<uint32_t>(b_boxes) * kAtomBytes : static_cast<uint32_t>(g.block_n / CG) * 128u);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long t0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], stage_bytes);
+          t_empty += clock64() - t0;
           const int k0 = kb * kBlockK;
           uint8_t* a_dst = smem_a + stage * kAStageBytes;
-          uint8_t* b_dst = smem_b + stage * kBStageBytes;
-          if (!g.a_mn) {
-            tma_load_2d(a_dst, &map_a, &full[stage], k0, m0);
+          uint8_t* b_dst = smem_b + stage * kBBytes;
+          if constexpr (CG == 2) {
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * my_bytes);      // both CTAs stage the same number of bytes
+            if (!g.a_mn) {
+              tma_load_2d_pair(a_dst, &map_a, &full[stage], k0, m0);
+            } else {
+              tma_load_2d_pair(a_dst, &map_a, &full[stage], m0, k0);
+              tma_load_2d_pair(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
+            }
+            if (!g.b_mn) {
+              tma_load_2d_pair(b_dst, &map_b, &full[stage], k0, nb0);
+            } else {
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
+            }
           } else {
-            tma_load_2d(a_dst, &map_a, &full[stage], m0, k0);
-            tma_load_2d(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
+            mbar_expect_tx(&full[stage], my_bytes);
+            if (!g.a_mn) {
+              tma_load_2d(a_dst, &map_a, &full[stage], k0, m0);
+            } else {
+              tma_load_2d(a_dst, &map_a, &full[stage], m0, k0);
+              tma_load_2d(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
+            }
+            if (!g.b_mn) {
+              tma_load_2d(b_dst, &map_b, &full[stage], k0, nb0);
+            } else {
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
+            }
           }
-          if (!g.b_mn) {
-            tma_load_2d(b_dst, &map_b, &full[stage], k0, n0);
-          } else {
-            for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kAtomBytes, &map_b, &full[stage], n0 + 64 * j, k0);
-          }
-          if (++stage == kStages) {
+          if (++stage == kNumStages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
+      if (g.stats != nullptr) {
+        g.stats[blockIdx.x * 8 + 3] = t_empty;
+        g.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer ==========================================================================================
-    if (lane == 0) {
+    // ===== MMA issuer (the pair's leader only) =====================================================================
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D fp32, A/B bf16, majors, N >> 3, M >> 4
       const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.a_mn) << 15) |
-                              (static_cast<uint32_t>(g.b_mn) << 16) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
+                              (static_cast<uint32_t>(g.b_mn) << 16) | (static_cast<uint32_t>((kBlockM * CG) >> 4) << 24);
       const uint32_t a_lbo = g.a_mn ? kAtomBytes : 16, b_lbo = g.b_mn ? kAtomBytes : 16;
-      const uint32_t a_step = g.a_mn ? 2048 : 32, b_step = g.b_mn ? 2048 : 32;
+      // descriptors of k-step 0 of stage 0; a k-step advances the 14-bit start-address field (16-byte units) by 2 (K-major:
+      // 32 bytes along the swizzled row) or 128 (MN-major: 16 rows of 128 bytes), a stage by its size
+      const uint64_t a_desc0 = smem_desc(saddr(smem_a), a_lbo, 1024), b_desc0 = smem_desc(saddr(smem_b), b_lbo, 1024);
+      const uint32_t a_kstep = g.a_mn ? 128u : 2u, b_kstep = g.b_mn ? 128u : 2u;
+      long long t_full = 0, t_acc = 0;
+      const long long t_begin = clock64();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (int w = tile_id0; w < total; w += tile_stride, ++it) {
         const int split = w / (g.n_blocks * g.m_blocks);
         const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
-        const int n_valid = min(g.block_n, g.N - (w % g.n_blocks) * g.block_n);
-        const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((n_valid + 15) / 16 * 16) >> 3) << 17);   // N of this tile's MMAs
+        const int n_eff = min(g.block_n, (g.N - (w % g.n_blocks) * g.block_n + 16 * CG - 1) / (16 * CG) * (16 * CG));
+        const uint32_t idesc = idesc0 | (static_cast<uint32_t>(n_eff >> 3) << 17);   // N of this tile's MMAs
         const int acc = it & 1;
+        long long t0 = clock64();
         mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
+        t_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxN);
         for (int kb = kb0; kb < kb1; ++kb) {
+          t0 = clock64();
           mbar_wait(&full[stage], phase);
+          t_full += clock64() - t0;
           tc_fence_after();
-          const int k_valid = min(kBlockK, g.K - kb * kBlockK);
-          const int k_steps = (k_valid + 15) / 16;
-          const uint32_t a_addr = saddr(smem_a + stage * kAStageBytes), b_addr = saddr(smem_b + stage * kBStageBytes);
-          for (int k = 0; k < k_steps; ++k) {
-            umma_bf16(tmem_d, smem_desc(a_addr + k * a_step, a_lbo, 1024), smem_desc(b_addr + k * b_step, b_lbo, 1024), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+          const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * (kAStageBytes >> 4));
+          const uint64_t bd = b_desc0 + static_cast<uint64_t>(stage * (kBBytes >> 4));
+          const int k_valid = g.K - kb * kBlockK;
+          if (k_valid >= kBlockK) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          } else {                                              // the ragged end of the reduction axis
+            const int k_steps = (k_valid + 15) / 16;
+            for (int k = 0; k < k_steps; ++k) {
+              if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty[stage]);                           // the stage is free once these MMAs have read it
-          if (++stage == kStages) {
+          // the stage is free (in both CTAs) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_pair(&empty[stage]);
+          else umma_commit(&empty[stage]);
+          if (++stage == kNumStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);                            // the accumulator is complete
+        // the accumulator (each CTA's 128 rows of it) is complete
+        if constexpr (CG == 2) umma_commit_pair(&acc_full[acc]);
+        else umma_commit(&acc_full[acc]);
+      }
+      if (g.stats != nullptr) {
+        g.stats[blockIdx.x * 8 + 0] = t_full;
+        g.stats[blockIdx.x * 8 + 1] = t_acc;
+        g.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;
       }
     }
   } else if (warp >= kEpilogueWarp0) {
@@ -337,17 +459,21 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int sw = row & 7;
     constexpr int cols_per_slab = F32 ? 32 : 64;
     const int n_slabs = g.block_n / cols_per_slab;
+    long long t_wait = 0;
+    const long long t_begin = clock64();
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (int w = tile_id0; w < total; w += tile_stride, ++it) {
       const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
       const int n0 = n_blk * g.block_n;
-      const int out_row0 = (F32 ? split * g.m_blocks * kBlockM : 0) + m_blk * kBlockM;
+      const int out_row0 = (F32 ? split * g.m_blocks * (kBlockM * CG) : 0) + m_blk * (kBlockM * CG) + rank * kBlockM;
       const int acc = it & 1;
       // the tile's biases -> this group's shared-memory copy (zeros without a bias / past the edge of C); ordered before their
       // first use by the bar.sync that opens the group's first slab, and after the previous tile's last use by the bar.sync
       // that closed its last slab
       for (int c = etid; c < g.block_n; c += 128) bias_g[c] = (g.bias != nullptr && n0 + c < g.N) ? __ldg(g.bias + n0 + c) : 0.f;
+      const long long t0 = clock64();
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      t_wait += clock64() - t0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxN);
       for (int s = grp; s < n_slabs; s += kEpilogueGroups) {
@@ -370,20 +496,43 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);              // this warp's share of the accumulator is drained
+      if (lane == 0) {                                          // this warp's share of the accumulator is drained
+        if constexpr (CG == 2) mbar_arrive_leader(&acc_empty[acc]);
+        else mbar_arrive(&acc_empty[acc]);
+      }
     }
     if (etid == 0) tma_store_wait_all();
+    if (g.stats != nullptr && etid == 0 && grp == 0) {
+      g.stats[blockIdx.x * 8 + 5] = t_wait;
+      g.stats[blockIdx.x * 8 + 6] = clock64() - t_begin;
+    }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // no CTA leaves while its peer may still read its shared memory or signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-// dW[m, n] = sum over splits (in split order) of the fp32 partial tiles
+template <bool F32, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmArgs g) {
+  dense_gemm_body<1, F32, ACT>(map_a, map_b, map_c, g);
+}
+
+template <bool F32, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+dense_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmArgs g) {
+  dense_gemm_body<2, F32, ACT>(map_a, map_b, map_c, g);
+}
+
+// dW[m, n] = sum over splits (in split order) of the fp32 partial tiles; eight loads in flight per thread
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N, float* __restrict__ out, int64_t ldo) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
@@ -391,13 +540,19 @@ reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_s
   if (i >= static_cast<int64_t>(M) * nv) return;
   const int m = static_cast<int>(i / nv), n = static_cast<int>(i % nv) * 4;
   const float* p = part + static_cast<int64_t>(m) * N + n;
-  float4 acc = *reinterpret_cast<const float4*>(p);
-  for (int s = 1; s < splits; ++s) {
-    const float4 t = *reinterpret_cast<const float4*>(p + s * split_stride);
-    acc.x += t.x;
-    acc.y += t.y;
-    acc.z += t.z;
-    acc.w += t.w;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < splits; s0 += 8) {
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = (s0 + u < splits) ? __ldcs(reinterpret_cast<const float4*>(p + (s0 + u) * split_stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += t[u].x;
+      acc.y += t[u].y;
+      acc.z += t[u].z;
+      acc.w += t[u].w;
+    }
   }
   *reinterpret_cast<float4*>(out + static_cast<int64_t>(m) * ldo + n) = acc;
 }
@@ -432,16 +587,17 @@ constexpr int kHeadBwdThreads = 256;
 __global__ void __launch_bounds__(kHeadBwdThreads)
 head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int act, const __nv_bfloat16* __restrict__ x, int64_t rows,
                 int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t lddx,
-                float* __restrict__ partial /* [grid, in_dim + 1] */) {
+                float* __restrict__ partial /* [grid, 2 * in_dim + 1]: dW | db | column sums of dx */) {
   // thread = (row lane rl, vector column vc): vc covers 8 consecutive columns
   const int vcols = in_dim / 8;
   const int row_lanes = kHeadBwdThreads / vcols;
   const int vc = threadIdx.x % vcols, rl = threadIdx.x / vcols;
   __shared__ float s_red[kHeadBwdThreads * 8];
   __shared__ float s_db[kHeadBwdThreads];
-  float acc[8];
+  const int pstride = 2 * in_dim + 1;
+  float acc[8], cs[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 8; ++k) acc[k] = cs[k] = 0.f;
   float db = 0.f;
   if (rl < row_lanes) {
     float wf[8];
@@ -471,6 +627,8 @@ head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, i
         acc[2 * j + 1] = fmaf(__uint_as_float(xs[j] & 0xFFFF0000u), dz, acc[2 * j + 1]);
         __nv_bfloat162 h = __floats2bfloat162_rn(dz * wf[2 * j], dz * wf[2 * j + 1]);
         pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        cs[2 * j] += __uint_as_float(pk[j] << 16);            // what the next layer's bias gradient sums: the ROUNDED dx
+        cs[2 * j + 1] += __uint_as_float(pk[j] & 0xFFFF0000u);
       }
       if (dx != nullptr) __stcs(reinterpret_cast<uint4*>(dx + r * lddx + vc * 8), make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
@@ -482,23 +640,39 @@ head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, i
   for (int c = threadIdx.x; c < in_dim; c += kHeadBwdThreads) {
     float t = 0.f;
     for (int l = 0; l < row_lanes; ++l) t += s_red[(l * vcols + c / 8) * 8 + (c % 8)];
-    partial[static_cast<int64_t>(blockIdx.x) * (in_dim + 1) + c] = t;
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + c] = t;
   }
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int l = 0; l < row_lanes; ++l) t += s_db[l * vcols];
-    partial[static_cast<int64_t>(blockIdx.x) * (in_dim + 1) + in_dim] = t;
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + in_dim] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = cs[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < in_dim; c += kHeadBwdThreads) {
+    float t = 0.f;
+    for (int l = 0; l < row_lanes; ++l) t += s_red[(l * vcols + c / 8) * 8 + (c % 8)];
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + in_dim + 1 + c] = t;
   }
 }
 
+// one warp per output column: lane l adds partials l, l + 32, ... (independent loads), then a fixed shuffle tree
 __global__ void __launch_bounds__(256)
-head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c > in_dim) return;
+head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db,
+                      float* __restrict__ dx_colsum) {
+  const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int pstride = 2 * in_dim + 1;
+  if (c >= pstride) return;
   float t = 0.f;
-  for (int p = 0; p < parts; ++p) t += partial[static_cast<int64_t>(p) * (in_dim + 1) + c];
+  for (int p = lane; p < parts; p += 32) t += partial[static_cast<int64_t>(p) * pstride + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane != 0) return;
   if (c < in_dim) dW[c] = t;
-  else db[0] = t;
+  else if (c == in_dim) db[0] = t;
+  else if (dx_colsum != nullptr) dx_colsum[c - in_dim - 1] = t;
 }
 
 // dy_pre[r, c] = bf16(dy[r, c] * act'(y[r, c])): the activation's backward in front of the last layer's GEMMs
@@ -576,48 +750,103 @@ static int block_n_for(int N) {
   return bn;
 }
 
-static void plan_splits(int tiles, int k_blocks, bool allow_split, int* splits, int* kbps) {
+static unsigned long long* g_debug_stats = nullptr;    // rb_dense_debug_stats
+
+// RB_DENSE_PAIR=0 in the environment keeps every product on single-CTA tiles (A/B measurements)
+static bool pair_enabled() {
+  const char* e = getenv("RB_DENSE_PAIR");
+  return e == nullptr || e[0] != '0';
+}
+
+static int max_pair_clusters() {
+  static const int n = [] {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kNumSMs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int c = 0;
+    if (cudaFuncSetAttribute(dense_gemm_pair_kernel<false, RB_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&c, dense_gemm_pair_kernel<false, RB_ACT_NONE>, &cfg) != cudaSuccess)
+      c = 0;
+    (void)cudaGetLastError();
+    return std::min(c, kNumSMs / 2);
+  }();
+  return n;
+}
+
+// How a product is cut into work items: tiles of (128 * cg) x block_n, the reduction split over `splits` workers
+struct Plan {
+  int cg;          // CTAs per tile: 2 = cta_group::2 pairs
+  int block_n, m_blocks, n_blocks, k_blocks, splits, kbps, workers;
+};
+
+static Plan make_plan(int M, int N, int K, bool split_k, bool use_pairs) {
+  Plan p;
+  p.block_n = block_n_for(N);
+  p.workers = kNumSMs;
+  p.cg = 1;
+  if (use_pairs && p.block_n % 128 == 0 && M >= 2 * kBlockM) {
+    p.cg = 2;
+    p.workers = kNumSMs / 2;
+  }
+  p.m_blocks = (M + kBlockM * p.cg - 1) / (kBlockM * p.cg);
+  p.n_blocks = (N + p.block_n - 1) / p.block_n;
+  p.k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int tiles = p.m_blocks * p.n_blocks;
   int s = 1;
-  if (allow_split && tiles < kNumSMs) s = std::max(1, std::min(kNumSMs / tiles, k_blocks));
-  const int per = (k_blocks + s - 1) / s;
-  *kbps = per;
-  *splits = (k_blocks + per - 1) / per;
+  if (split_k && tiles < p.workers) s = std::max(1, std::min(p.workers / tiles, p.k_blocks));
+  p.kbps = (p.k_blocks + s - 1) / s;
+  p.splits = (p.k_blocks + p.kbps - 1) / p.kbps;
+  return p;
 }
 
 // C[M, N] = A . B^T over K.  `c` is bf16 [M, N] / f32 [M, N] (splits == 1) or the f32 partial buffer.
 static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, void* c, bool c_f32, int64_t ldc, bool split_k, const float* bias,
                        int activation, void* ws, size_t ws_bytes, cudaStream_t st, int* splits_out, int64_t* split_stride_out) {
+  Plan pl = make_plan(M, N, K, split_k, pair_enabled());
+  if (pl.cg == 2 && max_pair_clusters() < 1) pl = make_plan(M, N, K, split_k, false);
   GemmArgs g;
   g.M = M;
   g.N = N;
   g.K = K;
-  g.block_n = block_n_for(N);
+  g.block_n = pl.block_n;
   g.a_mn = a.mn_major;
   g.b_mn = b.mn_major;
-  g.m_blocks = (M + kBlockM - 1) / kBlockM;
-  g.n_blocks = (N + g.block_n - 1) / g.block_n;
-  g.k_blocks = (K + kBlockK - 1) / kBlockK;
-  plan_splits(g.m_blocks * g.n_blocks, g.k_blocks, split_k, &g.splits, &g.k_blocks_per_split);
+  g.m_blocks = pl.m_blocks;
+  g.n_blocks = pl.n_blocks;
+  g.k_blocks = pl.k_blocks;
+  g.splits = pl.splits;
+  g.k_blocks_per_split = pl.kbps;
   g.out_f32 = c_f32;
   g.activation = activation;
   g.bias = bias;
+  g.stats = g_debug_stats;
+  const int tile_m = kBlockM * pl.cg;
   CUtensorMap ma, mb, mc;
   int rc;
-  // K-major operand [MN, K]: box = 64 reduction elements x (128 | block_n) rows.  MN-major operand [K, MN]: box = 64 x 64.
+  // K-major operand [MN, K]: box = 64 reduction elements x (128 | this CTA's share of block_n) rows.
+  // MN-major operand [K, MN]: box = 64 x 64.
   if (!a.mn_major) rc = make_map(&ma, a.p, false, K, M, a.ld, kBlockK, kBlockM);
   else rc = make_map(&ma, a.p, false, M, K, a.ld, 64, kBlockK);
   if (rc != RB_OK) return rc;
-  if (!b.mn_major) rc = make_map(&mb, b.p, false, K, N, b.ld, kBlockK, g.block_n);
+  if (!b.mn_major) rc = make_map(&mb, b.p, false, K, N, b.ld, kBlockK, g.block_n / pl.cg);
   else rc = make_map(&mb, b.p, false, N, K, b.ld, 64, kBlockK);
   if (rc != RB_OK) return rc;
   void* out = c;
   int64_t out_rows = M, out_ld = ldc;
   if (split_k) {
-    const int64_t split_stride = static_cast<int64_t>(g.m_blocks) * kBlockM * N;
+    const int64_t split_stride = static_cast<int64_t>(g.m_blocks) * tile_m * N;
     const size_t need = static_cast<size_t>(g.splits) * split_stride * sizeof(float);
     RB_CHECK_ARG(ws != nullptr && ws_bytes >= need, RB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     out = ws;
-    out_rows = static_cast<int64_t>(g.splits) * g.m_blocks * kBlockM;
+    out_rows = static_cast<int64_t>(g.splits) * g.m_blocks * tile_m;
     out_ld = N;
     *splits_out = g.splits;
     *split_stride_out = split_stride;
@@ -625,28 +854,33 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   rc = make_map(&mc, out, c_f32, N, out_rows, out_ld, c_f32 ? 32 : 64, kBlockM);
   if (rc != RB_OK) return rc;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
-  static const KernelFn kernels[2][3] = {
-      {dense_gemm_kernel<false, RB_ACT_NONE>, dense_gemm_kernel<false, RB_ACT_RELU>, dense_gemm_kernel<false, RB_ACT_SIGMOID>},
-      {dense_gemm_kernel<true, RB_ACT_NONE>, dense_gemm_kernel<true, RB_ACT_RELU>, dense_gemm_kernel<true, RB_ACT_SIGMOID>}};
+  static const KernelFn kernels[2][2][3] = {
+      {{dense_gemm_kernel<false, RB_ACT_NONE>, dense_gemm_kernel<false, RB_ACT_RELU>, dense_gemm_kernel<false, RB_ACT_SIGMOID>},
+       {dense_gemm_kernel<true, RB_ACT_NONE>, dense_gemm_kernel<true, RB_ACT_RELU>, dense_gemm_kernel<true, RB_ACT_SIGMOID>}},
+      {{dense_gemm_pair_kernel<false, RB_ACT_NONE>, dense_gemm_pair_kernel<false, RB_ACT_RELU>, dense_gemm_pair_kernel<false, RB_ACT_SIGMOID>},
+       {dense_gemm_pair_kernel<true, RB_ACT_NONE>, dense_gemm_pair_kernel<true, RB_ACT_RELU>, dense_gemm_pair_kernel<true, RB_ACT_SIGMOID>}}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int f = 0; f < 2; ++f)
-      for (int a = 0; a < 3; ++a) RB_CUDA(cudaFuncSetAttribute(kernels[f][a], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    for (int q = 0; q < 2; ++q)
+      for (int f = 0; f < 2; ++f)
+        for (int t = 0; t < 3; ++t) RB_CUDA(cudaFuncSetAttribute(kernels[q][f][t], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int total = g.m_blocks * g.n_blocks * g.splits;
-  kernels[c_f32 ? 1 : 0][activation]<<<std::min(total, kNumSMs), kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
+  const int workers = pl.cg == 2 ? std::min(pl.workers, max_pair_clusters()) : pl.workers;
+  kernels[pl.cg - 1][c_f32 ? 1 : 0][activation]<<<std::min(total, workers) * pl.cg, kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
   RB_LAUNCH_CHECK("dense_gemm_kernel");
   return RB_OK;
 }
 
+// the larger of the two plans' partial buffers: the workspace query does not know which form will run
 static size_t weight_ws_bytes(int64_t rows, int in_dim, int units) {
-  const int bn = block_n_for(units);
-  const int m_blocks = (in_dim + kBlockM - 1) / kBlockM, n_blocks = (units + bn - 1) / bn;
-  const int k_blocks = static_cast<int>((rows + kBlockK - 1) / kBlockK);
-  int splits, kbps;
-  plan_splits(m_blocks * n_blocks, k_blocks, true, &splits, &kbps);
-  return static_cast<size_t>(splits) * m_blocks * kBlockM * units * sizeof(float) + 256;
+  size_t need = 0;
+  for (int pairs = 0; pairs < 2; ++pairs) {
+    const Plan pl = make_plan(in_dim, units, static_cast<int>(std::min<int64_t>(rows, 0x7FFFFFFF)), true, pairs != 0);
+    need = std::max(need, static_cast<size_t>(pl.splits) * pl.m_blocks * kBlockM * pl.cg * units * sizeof(float));
+  }
+  return need + 256;
 }
 
 static bool dims_ok(int64_t rows, int a, int b) { return rows > 0 && rows < (1ll << 31) && a > 0 && b > 0 && a % 8 == 0 && b % 8 == 0; }
@@ -724,11 +958,12 @@ static int head_parts(int64_t rows) { return static_cast<int>(std::max<int64_t>(
 
 extern "C" size_t rb_dense_head_bwd_workspace_bytes(int64_t rows, int32_t in_dim) {
   if (rows <= 0 || in_dim <= 0) return 0;
-  return static_cast<size_t>(head_parts(rows)) * (in_dim + 1) * sizeof(float) + 256;
+  return static_cast<size_t>(head_parts(rows)) * (2 * in_dim + 1) * sizeof(float) + 256;
 }
 
 extern "C" int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, const void* x, int64_t rows, int32_t in_dim, int64_t ldx,
-                                 const void* w, void* dx, int64_t lddx, float* dw, float* db, void* ws, size_t ws_bytes, void* stream) {
+                                 const void* w, void* dx, int64_t lddx, float* dw, float* db, float* dx_colsum, void* ws, size_t ws_bytes,
+                                 void* stream) {
   RB_CHECK_ARG(dout != nullptr && x != nullptr && w != nullptr && dw != nullptr && db != nullptr, RB_ERR_ARG, "a required pointer is null");
   RB_CHECK_ARG(activation == RB_ACT_NONE || out != nullptr, RB_ERR_ARG, "the activation's backward needs the forward output");
   RB_CHECK_ARG(rows > 0 && in_dim > 0 && in_dim % 8 == 0 && in_dim <= 8 * kHeadBwdThreads && ldx % 8 == 0 && ldx >= in_dim &&
@@ -744,7 +979,7 @@ extern "C" int rb_dense_head_bwd(const float* dout, const float* out, int32_t ac
                                                      static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(dx), lddx,
                                                      static_cast<float*>(ws));
   RB_LAUNCH_CHECK("head_bwd_kernel");
-  head_bwd_final_kernel<<<(in_dim + 1 + 255) / 256, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, dw, db);
+  head_bwd_final_kernel<<<(2 * in_dim + 1 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, dw, db, dx_colsum);
   RB_LAUNCH_CHECK("head_bwd_final_kernel");
   return RB_OK;
 }
@@ -767,5 +1002,10 @@ extern "C" int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim,
   pack_input_kernel<<<grid_for(rows * ld_out, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, in_dim, ldx,
                                                                                               static_cast<__nv_bfloat16*>(out_bf16), ld_out, ones_col);
   RB_LAUNCH_CHECK("pack_input_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_dense_debug_stats(void* device_buf) {
+  g_debug_stats = static_cast<unsigned long long*>(device_buf);
   return RB_OK;
 }

@@ -27,6 +27,7 @@ class GraphedTrainStep:
         if not all(t.is_cuda for t in sample_batch):
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        self._pollers = [m for m in model.modules() if hasattr(m, "poll_overflow")]
         self.static = tuple(torch.empty_like(t) for t in sample_batch)
         if hasattr(optimizer, "enable_device_scalars"):
             optimizer.enable_device_scalars(sample_batch[0].device)
@@ -64,6 +65,8 @@ class GraphedTrainStep:
         for d, s in zip(self.static, batch):
             d.copy_(s, non_blocking=True)
         self.optimizer.prepare_step()
+        for m in self._pollers:
+            m.poll_overflow()            # a sharded table that dropped gradient rows in an earlier replay (p2p.poll_overflow)
         self.graph.replay()
         self.steps_run += 1
         return self.loss

@@ -381,18 +381,15 @@ class _LinearBF16Fn(torch.autograd.Function):
         x, Wp = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.mm(dy, Wp.t()) if ctx.need_dx else None
-        if dy.is_cuda:
-            dW_full = torch.mm(x.t(), dy, out_dtype=torch.float32)               # fp32 accumulate AND fp32 result
-        else:
-            dW_full = torch.mm(x.t(), dy).float()
+        dW_full = ops.mm_f32_out(x.t(), dy)                                       # fp32 accumulate AND fp32 result
         dW = dW_full[: ctx.in_dim]
         if ctx.ones_col:
             return dx, dW, dW_full[ctx.in_dim].clone(), None, None               # bias gradient came with the GEMM
-        if dy.is_cuda and dy.shape[1] % 8 == 0:
+        if dy.shape[1] % 8 == 0 and dy.shape[1] <= 2048:
             db = ops.colsum(dy)                       # rb_colsum: deterministic fp32 column sums
         else:
             ones = torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device)
-            db = torch.mm(ones, dy).reshape(-1).float()
+            db = ops.mm_f32_out(ones, dy).reshape(-1)
         return dx, dW, db, None, None
 
 
@@ -458,12 +455,13 @@ class _DenseStackFn(torch.autograd.Function):
             """dW_i (and db_i) on the wgrad stream, from operands the main stream has just produced."""
             W, b = Ws[i], bs[i]
             dW_full = torch.empty(x_i.shape[1], W.shape[1], dtype=torch.float32, device=x_i.device)
-            db = torch.empty(W.shape[1], dtype=torch.float32, device=x_i.device) if not (i == 0 and ctx.ones_col) else None
+            need_db = not (i == 0 and ctx.ones_col) and have_db is None
+            db = torch.empty(W.shape[1], dtype=torch.float32, device=x_i.device) if need_db else have_db
             wg.wait_event(main.record_event())
             mlp._wgrad_keep.extend((x_i, dy_i, dW_full, db))
             with torch.cuda.stream(wg):
                 ops.dense_bwd_weight(x_i, dy_i, out=dW_full, ws=ws)
-                if db is not None:
+                if need_db:
                     ops.colsum(dy_i, out=db, ws=ws)
                 if i == 0:
                     assign(W, dW_full[:in_dim])
@@ -474,8 +472,13 @@ class _DenseStackFn(torch.autograd.Function):
 
         h, Wp = acts[n - 1], shadows[n - 1]
         want_dx = n > 1 or ctx.need_dx
+        head_cs = None
         if Wp.shape[1] == 1:
-            dy, dw, db = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), act, h, Wp.reshape(-1), want_dx=want_dx)
+            # the head also sums the columns of the dx it writes: the bias gradient of the layer below, without re-reading dx
+            want_cs = n > 1 and not (n == 2 and ctx.ones_col)
+            res = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), act, h, Wp.reshape(-1), want_dx=want_dx, want_dx_colsum=want_cs)
+            dy, dw, db = res[:3]
+            head_cs = res[3] if want_cs else None
             dw = dw[:in_dim] if n == 1 else dw
             for p_, g_ in ((Ws[n - 1], dw.reshape(-1, 1)), (bs[n - 1], db)):
                 if p_.grad is None:
@@ -489,7 +492,7 @@ class _DenseStackFn(torch.autograd.Function):
         for i in range(n - 2, -1, -1):
             dy_i = dy
             dy = ops.dense_bwd_input(dy_i, shadows[i]) if (i > 0 or ctx.need_dx) else None
-            wgrad(i, acts[i], dy_i)
+            wgrad(i, acts[i], dy_i, head_cs if i == n - 2 else None)
         mlp._wgrad_end()
         dx = dy
         if dx is not None and ctx.raw:
@@ -538,15 +541,12 @@ class _CollapsedAffineFn(torch.autograd.Function):
         x, Ax = saved[0], saved[1]
         A, c, Ws = saved[2:2 + n - 1], saved[2 + n - 1:2 + 2 * (n - 1)], saved[2 + 2 * (n - 1):]
         dz = dz.contiguous()
-        bf16_cuda = dz.is_cuda and dz.dtype == torch.bfloat16                    # the cases _LinearBF16Fn runs on the GPU
-        if bf16_cuda:
-            G_full = torch.mm(x.t(), dz, out_dtype=torch.float32)                # fp32 accumulate AND fp32 result
-        else:
-            G_full = torch.mm(x.t(), dz).float()
+        bf16 = dz.dtype == torch.bfloat16
+        G_full = ops.mm_f32_out(x.t(), dz) if bf16 else torch.mm(x.t(), dz)      # fp32 accumulate AND fp32 result
         G = G_full[: ctx.in_dim]
         if ctx.ones_col:
             s = G_full[ctx.in_dim]
-        elif bf16_cuda and dz.shape[1] % 8 == 0:
+        elif bf16 and dz.shape[1] % 8 == 0 and dz.shape[1] <= 2048:
             s = ops.colsum(dz)                                                    # rb_colsum: deterministic fp32 column sums
         else:
             s = dz.float().sum(0)

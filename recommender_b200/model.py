@@ -12,6 +12,7 @@ from typing import Optional, Sequence
 import torch
 from torch import nn
 
+from . import ops
 from .layers import MLP, DotInteraction, Embedding
 
 
@@ -98,7 +99,6 @@ class _BCEClippedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, prob, label):
-        from . import ops
         loss, dprob = ops.bce_clipped(prob, label, want_grad=True)
         ctx.save_for_backward(dprob)
         ctx.shape = prob.shape
@@ -113,12 +113,9 @@ class _BCEClippedFn(torch.autograd.Function):
 def bce_clipped(prob: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     """Keras binary_crossentropy on probabilities, batch mean — what compile(loss=BinaryCrossentropy)
     evaluates for DLRM (ctr/train.py:85-87)."""
-    if prob.is_cuda and prob.dtype == torch.float32 and label.dtype in (torch.float32, torch.int64):
-        return _BCEClippedFn.apply(prob, label)
-    eps = 1e-7
-    y = label.to(prob.dtype)
-    p = prob.clamp(eps, 1.0 - eps)
-    return (-(y * torch.log(p + eps) + (1.0 - y) * torch.log(1.0 - p + eps))).mean()
+    if label.dtype not in (torch.float32, torch.int64):
+        label = label.to(torch.float32)
+    return _BCEClippedFn.apply(prob.float(), label)          # rb_bce_clipped: loss and d loss / d prob in one pass
 
 
 def bce_logits(logit: torch.Tensor, label: torch.Tensor) -> torch.Tensor:

@@ -410,6 +410,13 @@ def dense_opt_step(params, grads, state0, state1, *, optimizer="adam_lazy", step
         check(lib.rb_dense_opt_step(arr, hi - lo, C.byref(opt), _stream()), "rb_dense_opt_step")
 
 
+def mm_f32_out(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b with fp32 accumulation AND an fp32 result from bf16 operands: the weight-gradient GEMM of the cuBLASLt A/B path
+    (layers._LinearBF16Fn; the default path is rb_dense_bwd_weight)."""
+    _need_cuda(a, b)
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
 def colsum(x: torch.Tensor, out=None, ws=None) -> torch.Tensor:
     """fp32 column sums of a [rows, cols] float32 / bfloat16 matrix (rb_colsum): a Dense bias gradient."""
     _need_cuda(x)
@@ -514,18 +521,20 @@ def dense_head_fwd(x, w, bias=None, activation=None):
     return out
 
 
-def dense_head_bwd(dout, out, activation, x, w, want_dx=True):
-    """Backward of the Dense(1) head (rb_dense_head_bwd): returns (dx bf16 [rows, in_dim] | None, dW f32 [in_dim], db f32 [1])."""
+def dense_head_bwd(dout, out, activation, x, w, want_dx=True, want_dx_colsum=False):
+    """Backward of the Dense(1) head (rb_dense_head_bwd): returns (dx bf16 [rows, in_dim] | None, dW f32 [in_dim], db f32 [1])
+    and, with want_dx_colsum, the f32 column sums of dx (the bias gradient of the layer below) as a fourth value."""
     _need_cuda(dout, out, x, w)
     _bf16m(x, "x")
     rows, in_dim = x.shape
     dx = torch.empty(rows, in_dim, dtype=torch.bfloat16, device=x.device) if want_dx else None
     dw = torch.empty(in_dim, dtype=torch.float32, device=x.device)
     db = torch.empty(1, dtype=torch.float32, device=x.device)
+    cs = torch.empty(in_dim, dtype=torch.float32, device=x.device) if want_dx_colsum else None
     ws = _workspace(max(lib.rb_dense_head_bwd_workspace_bytes(rows, in_dim), 256), x.device)
     check(lib.rb_dense_head_bwd(_ptr(_f32c(dout, "dout")), _ptr(out), _lib.ACT_ENUM[activation], _ptr(x), rows, in_dim, x.stride(0), _ptr(w),
-                                _ptr(dx), in_dim, _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()), "rb_dense_head_bwd")
-    return dx, dw, db
+                                _ptr(dx), in_dim, _ptr(dw), _ptr(db), _ptr(cs), _ptr(ws), ws.numel(), _stream()), "rb_dense_head_bwd")
+    return (dx, dw, db, cs) if want_dx_colsum else (dx, dw, db)
 
 
 def dense_act_bwd(dy, y, activation):

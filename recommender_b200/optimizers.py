@@ -1,9 +1,9 @@
 """Mirrors of the Keras optimizers the reference builds (`Adam()` at ctr/train.py:80,84).
 
 One optimizer object drives both kinds of variables of a model:
-  * dense parameters (the MLPs) — the Keras formula restated with torch foreach ops
-    (`_resource_apply_dense`; note Keras' epsilon placement differs from
-    torch.optim.Adam, which is why torch's own Adam is not used);
+  * dense parameters (the MLPs) — the Keras formula (`_resource_apply_dense`; its epsilon
+    placement differs from torch.optim.Adam, which is why torch's own Adam is not used) for ALL tensors in one launch
+    (rb_dense_opt_step);
   * embedding tables — ONE fused CUDA call per table (`Embedding.apply_pending`): sort of the
     (row, position) pairs, duplicate-row sum, optimizer row update (A.1-A.4).
 """
@@ -125,19 +125,10 @@ class Adam(_Optimizer):
                 st = self._state[p] = (torch.zeros_like(p), torch.zeros_like(p))
             ms.append(st[0])
             vs.append(st[1])
-        if params[0].is_cuda:     # one launch for every dense tensor (rb_dense_opt_step)
-            ops.dense_opt_step(params, grads, ms, vs, optimizer="adam_lazy", step=step, lr=self.learning_rate,
-                               beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon,
-                               alpha_dev=self._alpha_dev if self._prepared else None)
-            return
-        alpha = ops.adam_alpha_t(self.learning_rate, self.beta_1, self.beta_2, step)
-        torch._foreach_mul_(ms, self.beta_1)
-        torch._foreach_add_(ms, grads, alpha=1.0 - self.beta_1)
-        torch._foreach_mul_(vs, self.beta_2)
-        torch._foreach_addcmul_(vs, grads, grads, value=1.0 - self.beta_2)
-        denom = torch._foreach_sqrt(vs)
-        torch._foreach_add_(denom, self.epsilon)
-        torch._foreach_addcdiv_(params, ms, denom, value=-alpha)
+        # one launch for every dense tensor (rb_dense_opt_step)
+        ops.dense_opt_step(params, grads, ms, vs, optimizer="adam_lazy", step=step, lr=self.learning_rate,
+                           beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon,
+                           alpha_dev=self._alpha_dev if self._prepared else None)
 
 
 class Adagrad(_Optimizer):
@@ -159,13 +150,7 @@ class Adagrad(_Optimizer):
             if st is None:
                 st = self._state[p] = torch.full_like(p, self.initial_accumulator_value)
             accs.append(st)
-        if params[0].is_cuda:
-            ops.dense_opt_step(params, grads, accs, None, optimizer="adagrad", lr=self.learning_rate, epsilon=self.epsilon)
-            return
-        torch._foreach_addcmul_(accs, grads, grads, value=1.0)
-        denom = torch._foreach_sqrt(accs)
-        torch._foreach_add_(denom, self.epsilon)
-        torch._foreach_addcdiv_(params, grads, denom, value=-self.learning_rate)
+        ops.dense_opt_step(params, grads, accs, None, optimizer="adagrad", lr=self.learning_rate, epsilon=self.epsilon)
 
 
 class SGD(_Optimizer):
@@ -180,7 +165,4 @@ class SGD(_Optimizer):
         return dict(lr=self.learning_rate)
 
     def _dense_step(self, params, grads, step):
-        if params[0].is_cuda:
-            ops.dense_opt_step(params, grads, None, None, optimizer="sgd", lr=self.learning_rate)
-            return
-        torch._foreach_add_(params, grads, alpha=-self.learning_rate)
+        ops.dense_opt_step(params, grads, None, None, optimizer="sgd", lr=self.learning_rate)

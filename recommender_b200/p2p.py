@@ -271,6 +271,9 @@ class P2PShardedEmbedding(nn.Module):
         self._n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
         self._x_saved = torch.empty(B, F + 1, D, dtype=torch.bfloat16, device=dev)    # forward -> backward operand rows
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        # the flag is mirrored into pinned host memory behind every collect (an async copy on the side stream, capturable),
+        # so that the NEXT step's host code can notice an overflow without synchronising (poll_overflow)
+        self._overflow_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._shape = (B, F)
         self._side = torch.cuda.Stream(device=dev)
 
@@ -342,6 +345,7 @@ class P2PShardedEmbedding(nn.Module):
         check(lib.rb_sparse_bwd_prepare_collected(self.local_rows, self.output_dim, self.capacity, self._sort_ws.data_ptr(),
                                                   self._sort_ws.numel(), C.byref(sel), ops._stream()), "rb_sparse_bwd_prepare_collected")
         self._sel = int(sel.value)
+        self._overflow_host.copy_(self.overflow, non_blocking=True)
 
     def _interaction_fwd(self, idx, dense_vec, flags, out_dtype, pad_to, ones_col=False):
         si, sg, tail = flags
@@ -383,6 +387,8 @@ class P2PShardedEmbedding(nn.Module):
         sort the pairs this rank owns.  interact() waits for the rendezvous, apply_pending() for the sort."""
         idx = idx.contiguous()
         B, F = idx.shape
+        if not torch.cuda.is_current_stream_capturing():
+            self.poll_overflow()
         self._build(B, F)
         main, side = torch.cuda.current_stream(), self._side
         side.wait_stream(main)                   # ids are ready; last step's apply (on main) precedes this rank's arrival
@@ -434,13 +440,9 @@ class P2PShardedEmbedding(nn.Module):
         else:
             raise ValueError(f"the peer-memory path supports adam_lazy / adagrad / sgd, not {kind}")
         opt = ops._opt_params(kind, step, lr, beta_1, beta_2, epsilon, alpha_dev)
-        _, F = self._shape
 
         def launch():
-            check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
-                                              self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
-                                              self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
-                                              self._sel, ops._ptr(self._shadow_full), ops._stream()), "rb_sparse_bwd_apply_p2p")
+            self._apply_rows(s0, s1, opt)
 
         if self._routed_by_caller:
             launch()
@@ -459,14 +461,35 @@ class P2PShardedEmbedding(nn.Module):
             self._apply_done = side.record_event()
         return self.n_local
 
+    def _apply_rows(self, s0, s1, opt) -> None:
+        """The C call of the apply phase, on the current (side) stream: what bench.py brackets with CUDA events."""
+        _, F = self._shape
+        check(lib.rb_sparse_bwd_apply_p2p(self.embeddings.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.local_rows, self.output_dim,
+                                          self.world, self.n_local, F, _ptr_array(self._resolve(self._dE_ptrs)), self.capacity,
+                                          self._n_valid.data_ptr(), C.byref(opt), self._sort_ws.data_ptr(), self._sort_ws.numel(),
+                                          self._sel, ops._ptr(self._shadow_full), ops._stream()), "rb_sparse_bwd_apply_p2p")
+
     def join(self) -> None:
         if self._apply_done is not None:
             torch.cuda.current_stream().wait_event(self._apply_done)
             self._apply_done = None
 
+    def poll_overflow(self) -> None:
+        """Non-blocking: raises if an EARLIER step's collect saw more lookups addressed to this owner than the static
+        capacity (`capacity_factor` x the per-rank lookups + 1024; the mean load is 1.0 x).  The pairs beyond the capacity
+        were cut off, i.e. their gradients were NOT applied — training must not continue silently.  Called at the start
+        of every step (begin_step) and by graph.GraphedTrainStep before each replay; check_overflow() is the synchronising form.
+        Skewed ids concentrate on few owners (a 3-row table sends all its lookups to 3 ranks): BASELINE config 3 runs with
+        capacity_factor = 2.0."""
+        if self._shape is not None and int(self._overflow_host[0]) != 0:
+            self._overflow_host.zero_()
+            raise RuntimeError("an owner received more lookups than its static capacity in an earlier step and dropped the excess "
+                               "gradient rows; raise capacity_factor (p2p.P2PShardedEmbedding)")
+
     def check_overflow(self) -> None:
         if int(self.overflow.item()) != 0:
             self.overflow.zero_()
+            self._overflow_host.zero_()
             raise RuntimeError("an owner received more lookups than its static capacity; raise capacity_factor")
 
 

@@ -252,10 +252,13 @@ class ShardedDLRM(nn.Module):
     def forward(self, inputs, training=None, mask=None):
         int_features = inputs["int_features"].reshape(-1, self.num_int_fea)
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)
-        bmlp_output = self.bottom_mlp(int_features)
-        if not self._synced:
-            self.top_mlp.build((self.num_cat_fea + 1) ** 2 + self.embedding_size, bmlp_output.device) if len(self.top_mlp.kernels) == 0 else None
+        if not self._synced:         # build both towers, then adopt rank 0's weights BEFORE anything is computed from them
+            if len(self.bottom_mlp.kernels) == 0:
+                self.bottom_mlp.build(self.num_int_fea, int_features.device)
+            if len(self.top_mlp.kernels) == 0:
+                self.top_mlp.build((self.num_cat_fea + 1) ** 2 + self.embedding_size, int_features.device)
             self.sync_dense_parameters()
+        bmlp_output = self.bottom_mlp(int_features)
         tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True, plan=inputs.get("plan"))
         output = self.top_mlp(tmlp_input)
         return output.squeeze(1)

@@ -99,10 +99,32 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--only", default="fwd,bwd_input,bwd_weight,head")
     ap.add_argument("--quick", action="store_true", help="the two smallest cases of each product only")
+    ap.add_argument("--stats", action="store_true", help="per-role wait cycles of the three products at 65536 x 800 x 512")
     ap.add_argument("--profile", action="store_true", help="no checks: 3 launches of each product at 65536 x 800 x 512 (for ncu)")
     a = ap.parse_args()
     only = a.only.split(",")
     ok = True
+    if a.stats:
+        from recommender_b200._lib import lib
+        B, i, u = 65536, 800, 512
+        x, w, dy = rnd(B, i), rnd(i, u, scale=i ** -0.5), rnd(B, u)
+        bias = torch.zeros(u, device=dev)
+        buf = torch.zeros(8 * 148, dtype=torch.int64, device=dev)
+        names = ["mma_wait_operands", "mma_wait_accumulator", "mma_total", "producer_wait_stage", "producer_total", "epilogue_wait_acc", "epilogue_total"]
+        for label, fn in (("fwd", lambda: ops.dense_fwd(x, w, bias, None)), ("bwd_input", lambda: ops.dense_bwd_input(dy, w)),
+                          ("bwd_weight", lambda: ops.dense_bwd_weight(x, dy))):
+            fn()
+            torch.cuda.synchronize()
+            buf.zero_()
+            lib.rb_dense_debug_stats(buf.data_ptr())
+            fn()
+            torch.cuda.synchronize()
+            lib.rb_dense_debug_stats(None)
+            t = buf.reshape(148, 8).double()
+            lead = t[t[:, 2] > 0]
+            print(label, {n: int(lead[:, k].mean().item()) if lead.numel() else 0 for k, n in enumerate(names)},
+                  "epilogue(all CTAs):", {n: int(t[:, k].mean().item()) for k, n in enumerate(names) if k >= 5}, flush=True)
+        return
     if a.profile:
         B, i, u = 65536, 800, 512
         x, w, dy = rnd(B, i), rnd(i, u, scale=i ** -0.5), rnd(B, u)

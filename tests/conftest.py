@@ -51,3 +51,16 @@ def cuda_lib():
     build.build()
     _lib.lib.load()
     return _lib.lib
+
+
+@pytest.fixture
+def fake_kernels(monkeypatch):
+    """Host-logic tests on torch-CPU: the C-ABI calls of layers / model / optimizers are served by tests/fake_ops.py (numpy
+    oracle + torch-CPU).  The product itself has no CPU path."""
+    import tests.fake_ops as fake
+    import recommender_b200.layers as layers
+    import recommender_b200.model as model
+    import recommender_b200.optimizers as optimizers
+    for mod in (layers, model, optimizers):
+        monkeypatch.setattr(mod, "ops", fake)
+    return fake

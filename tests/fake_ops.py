@@ -133,3 +133,44 @@ def sparse_bwd_update(table, state0, state1, groups, *, optimizer="adam_lazy", s
         O.adagrad(W, state0.numpy(), rows, gsum, lr, epsilon)
     else:
         O.sgd(W, rows, gsum, lr)
+
+
+# ---- dense side of the step (host-logic tests run the towers, the loss and the dense optimizers on torch-CPU) ------------
+
+def mm_f32_out(a, b):
+    return a.float() @ b.float()
+
+
+def colsum(x, out=None, ws=None):
+    r = x.float().sum(0)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def bce_clipped(prob, label, want_grad=True):
+    loss, dprob = O.bce_clipped(prob.detach().numpy().astype(np.float32), label.numpy())
+    return torch.tensor(np.float32(loss)), (torch.tensor(dprob) if want_grad else None)
+
+
+def dense_opt_step(params, grads, state0, state1, *, optimizer="adam_lazy", step=1, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                   alpha_dev=None):
+    """Keras `_resource_apply_dense` with torch foreach ops."""
+    _launches[0] += 1
+    if optimizer in ("adam_lazy", "adam_tf_dense"):
+        alpha = adam_alpha_t(lr, beta_1, beta_2, step)
+        torch._foreach_mul_(state0, beta_1)
+        torch._foreach_add_(state0, grads, alpha=1.0 - beta_1)
+        torch._foreach_mul_(state1, beta_2)
+        torch._foreach_addcmul_(state1, grads, grads, value=1.0 - beta_2)
+        denom = torch._foreach_sqrt(state1)
+        torch._foreach_add_(denom, epsilon)
+        torch._foreach_addcdiv_(params, state0, denom, value=-alpha)
+    elif optimizer == "adagrad":
+        torch._foreach_addcmul_(state0, grads, grads, value=1.0)
+        denom = torch._foreach_sqrt(state0)
+        torch._foreach_add_(denom, epsilon)
+        torch._foreach_addcdiv_(params, grads, denom, value=-lr)
+    else:
+        torch._foreach_add_(params, grads, alpha=-lr)

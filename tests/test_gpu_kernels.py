@@ -617,6 +617,34 @@ def test_peer_memory_sharded_step_equals_unsharded(ops, G, T, shadow):
         assert len(owners) == min(G, T)
 
 
+def test_peer_memory_capacity_overflow_is_loud(ops):
+    """Every lookup of both emulated ranks addressed to owner 0 (id 0 of one shared table): twice the mean load against a
+    capacity factor of 1.25.  The collect must raise the flag, the synchronising check and the non-blocking poll (pinned
+    mirror of the flag, read by the next step) must both raise, and a run with room must not."""
+    from recommender_b200.p2p import LocalPeerLink, P2PShardedEmbedding
+    G, V, D, B, F = 2, 4096, 32, 1024, 26
+    for factor, expect in ((1.25, True), (2.0, False)):
+        registry = {}
+        embs = [P2PShardedEmbedding(V, D, link=LocalPeerLink(G, r, registry), device="cuda", capacity_factor=factor) for r in range(G)]
+        idx = [torch.zeros(B, F, dtype=torch.int64, device="cuda") for _ in range(G)]
+        for r in range(G):
+            embs[r].route(idx[r])
+        for r in range(G):
+            embs[r].collect_and_sort()
+        torch.cuda.synchronize()
+        if expect:
+            with pytest.raises(RuntimeError, match="capacity"):
+                embs[0].poll_overflow()
+            embs[0]._overflow_host.fill_(1)
+            with pytest.raises(RuntimeError, match="capacity"):
+                embs[0].check_overflow()
+        else:
+            embs[0].poll_overflow()
+            embs[0].check_overflow()
+        embs[1].poll_overflow()          # owner 1 received nothing
+        embs[1].check_overflow()
+
+
 @pytest.mark.parametrize("G", [2, 8])
 def test_peer_memory_sharding_of_unequal_tables(ops, G):
     """BASELINE config 3 in miniature: 26 tables with capped Criteo-Terabyte-like cardinalities from 3 rows to a few

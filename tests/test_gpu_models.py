@@ -308,3 +308,20 @@ def test_full_size_scatter_counts_and_determinism(full):
     touched[rows] = True
     assert torch.equal(res[0][0][~touched], W[~touched])
     ops.check_oob("cuda")
+
+
+def test_two_real_ranks_sharded_equals_unsharded(cuda_lib):
+    """The peer-memory sharded step on REAL ranks (two processes, two GPUs, NVLink peer reads, device-side barriers)
+    against the unsharded model on rank 0 (scripts/p2p_check.py).  Needs two visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(repo, "scripts", "p2p_check.py")], capture_output=True, text=True, timeout=600,
+                       env=env, cwd=repo)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") >= 2

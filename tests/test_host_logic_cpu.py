@@ -40,7 +40,7 @@ def test_mlp_lazy_build_uses_glorot_uniform():
     assert float(mlp.biases[0].abs().max()) == 0.0
 
 
-def test_dense_adam_is_the_keras_formula(cuda_lib):
+def test_dense_adam_is_the_keras_formula(cuda_lib, fake_kernels):
     rng = np.random.default_rng(1)
     p0 = rng.normal(size=(6, 5)).astype(np.float32)
     p = torch.nn.Parameter(torch.tensor(p0.copy()))
@@ -55,7 +55,7 @@ def test_dense_adam_is_the_keras_formula(cuda_lib):
     assert opt.iterations == 3 and p.grad is None
 
 
-def test_dense_adagrad_and_sgd(cuda_lib):
+def test_dense_adagrad_and_sgd(cuda_lib, fake_kernels):
     p0 = np.ones((3, 2), np.float32)
     g = np.full((3, 2), 0.5, np.float32)
     p = torch.nn.Parameter(torch.tensor(p0.copy()))
@@ -69,7 +69,7 @@ def test_dense_adagrad_and_sgd(cuda_lib):
     np.testing.assert_allclose(q.detach().numpy(), p0 - 0.1 * g, rtol=1e-6)
 
 
-def test_loss_forms_match_oracle():
+def test_loss_forms_match_oracle(fake_kernels):
     rng = np.random.default_rng(2)
     prob = rng.uniform(0, 1, size=64).astype(np.float32)
     prob[:2] = [0.0, 1.0]
@@ -97,7 +97,7 @@ def test_embedding_needs_cuda():
         Embedding(10, 4)
 
 
-def test_mlp_bf16_path_forward_backward_close_to_fp32():
+def test_mlp_bf16_path_forward_backward_close_to_fp32(fake_kernels):
     rng = np.random.default_rng(5)
     layers = O.init_mlp(rng, 13, [64, 32, 8])
     x = rng.normal(size=(128, 13)).astype(np.float32)
@@ -122,7 +122,7 @@ def test_mlp_bf16_path_forward_backward_close_to_fp32():
     np.testing.assert_array_equal(y2.detach().numpy(), y.detach().numpy())
 
 
-def test_prepare_step_advances_the_counter_exactly_once():
+def test_prepare_step_advances_the_counter_exactly_once(fake_kernels):
     """graph.GraphedTrainStep calls Adam.prepare_step() before every replay and apply_gradients() inside the captured
     body: together they must advance `iterations` by one, and the dense update must use that step's alpha_t."""
     import torch
@@ -173,7 +173,7 @@ def test_keras_style_auc_and_accuracy():
     assert AUC().result() == 0.0                                                  # no samples: div_no_nan
 
 
-def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight():
+def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight(fake_kernels):
     """optimizers.Adam._refresh_device_scalars: alpha_t of step k is staged in pinned slot k mod 4096 before its
     asynchronous copy to the device, so a replay loop running many steps ahead of the GPU cannot overwrite the value a
     still-queued copy is going to read (emulated here with plain host tensors)."""
@@ -194,7 +194,7 @@ def test_adam_device_scalar_ring_never_reuses_a_slot_in_flight():
 
 @pytest.mark.parametrize("units,act,in_dim", [([512, 256, 64], "relu", 13), ([512, 256, 1], "sigmoid", 793), ([32, 1], None, 429),
                                               ([24, 16, 8, 4], "relu", 10)])
-def test_collapsed_affine_mlp_matches_the_layerwise_oracle(units, act, in_dim):
+def test_collapsed_affine_mlp_matches_the_layerwise_oracle(units, act, in_dim, fake_kernels):
     """MLP(collapse_linear=True): the linear hidden layers (ctr/layers.py:8) make each tower ONE affine map followed by
     the last activation; output, input gradient and every layer's own dW / db must equal the oracle's layer-by-layer
     forward / backward to fp32 re-association accuracy."""
@@ -220,7 +220,7 @@ def test_collapsed_affine_mlp_matches_the_layerwise_oracle(units, act, in_dim):
         close(b.grad.numpy(), db)
 
 
-def test_collapsed_affine_mlp_bf16_path_with_padding_and_ones_column():
+def test_collapsed_affine_mlp_bf16_path_with_padding_and_ones_column(fake_kernels):
     """The bf16 form the fused interaction kernel feeds: input padded to a multiple of 8 columns, pad column in_dim = 1.
     The padded rows of the collapsed kernel are zero, and the bias-gradient vector s is read off row in_dim of x^T dz.
     No worse than the layer-by-layer bf16 path against the fp32 oracle."""

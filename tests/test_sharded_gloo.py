@@ -60,7 +60,8 @@ def _worker(rank, port, sharding, num_tables, steps, out):
         import recommender_b200.layers as layers
         import recommender_b200.optimizers as optimizers
         import recommender_b200.sharded as sharded
-        layers.ops = sharded.ops = optimizers.ops = fake                      # inject the CPU kernels
+        import recommender_b200.model as model_mod
+        layers.ops = sharded.ops = optimizers.ops = model_mod.ops = fake      # inject the CPU kernels
         from recommender_b200.model import bce_clipped
         params = O.init_dlrm(4, BOTTOM, TOP, D, V * num_tables)
         model = sharded.ShardedDLRM(BOTTOM, TOP, D, V, 26, 13, num_tables=num_tables, sharding=sharding, device="cpu")
