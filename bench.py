@@ -67,7 +67,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--criteo-tb", action="store_true",
-                    help="BASELINE config 3 (N > 1 only): 26 tables with the capped Criteo-Terabyte cardinalities (187.8M rows), row-wise sharded")
+                    help="BASELINE config 3 (N > 1 only): 26 tables with the capped Criteo-Terabyte cardinalities (187.8M rows), row-wise "
+                         "sharded.  This is the default workload of every N > 1 run on the peer-memory path")
+    ap.add_argument("--config2-sharded", action="store_true",
+                    help="N > 1: keep BASELINE config 2 (26 x 1M-row tables) row-wise sharded instead of config 3")
+    ap.add_argument("--capacity-factor", type=float, default=0.0,
+                    help="static per-owner pair capacity of the sharded table in units of the per-rank lookups (0 = 2.0 for config 3, 1.25 otherwise)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="batch of the CPU reference arm; 0 = the GPU arm's batch (its Keras dense-Adam passes cost the same whatever the batch)")
@@ -86,10 +91,14 @@ def synth_batches(n, B, V, dist, seed, pin, table_rows=None):
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
-        if table_rows is not None:       # uniform inside every table's own cardinality
+        if table_rows is not None and dist == "uniform":       # uniform inside every table's own cardinality
             cards = torch.tensor(table_rows, dtype=torch.float64)
             cat = (torch.rand(B, F_CAT, generator=g, dtype=torch.float64) * cards[None]).to(torch.int64)
             cat = torch.minimum(cat, (cards[None] - 1).to(torch.int64))
+        elif table_rows is not None:     # Zipf(1.05) folded into every table's cardinality + 2 % forced id 0
+            u = torch.rand(B, F_CAT, generator=g, dtype=torch.float64).clamp_(min=1e-12)
+            cat = u.pow(-1.0 / 0.05).clamp_(max=2.0 ** 62).to(torch.int64) % torch.tensor(table_rows, dtype=torch.int64)[None]
+            cat[torch.rand(B, F_CAT, generator=g) < 0.02] = 0
         elif dist == "uniform":
             cat = torch.randint(0, V, (B, F_CAT), generator=g, dtype=torch.int64)
         else:
@@ -324,37 +333,39 @@ def extra_lines(args, dev, model, graphed_step, peak):
     del wt, mh, vh, hist
 
     # BASELINE config 5: 26 tables (vocab sizes cycled from esmm/train.py:197-215), D = 32, bag size 1, gradients of 2 (ESMM) and
-    # 10 (MMOE) consumers added inside the scatter (esmm/esmm.py:15-24)
+    # 10 (MMOE) consumers added inside the scatter (esmm/esmm.py:15-24).  The tables live back to back in ONE tensor
+    # (layers.Embedding(table_rows=...)): the 26 lookups + concat are one rb_gather_fwd over [B, 26] ids with per-field row
+    # offsets, and the 26 sparse Adam applies one rb_sparse_bwd_update whose gradient source lists the consumers.
     D5, T5 = 32, 26
     vocab = [ESMM_VOCAB[k % len(ESMM_VOCAB)] for k in range(T5)]
     g = torch.Generator(device=dev).manual_seed(4)
-    tabs = [torch.empty(v, D5, device=dev).uniform_(-0.05, 0.05, generator=g) for v in vocab]
-    ms_ = [(torch.zeros_like(t), torch.zeros_like(t)) for t in tabs]
-    idx5 = [torch.randint(0, v, (B, 1), device=dev, generator=g, dtype=torch.int64).to(torch.int32) for v in vocab]
+    rows5 = sum(vocab)
+    tab = torch.empty(rows5, D5, device=dev).uniform_(-0.05, 0.05, generator=g)
+    m5, v5 = torch.zeros_like(tab), torch.zeros_like(tab)
+    off5 = torch.tensor([0] + vocab[:-1], dtype=torch.int64, device=dev).cumsum(0)
+    idx5 = torch.stack([torch.randint(0, v, (B,), device=dev, generator=g, dtype=torch.int64) for v in vocab], dim=1).to(torch.int32).contiguous()
     width = D5 * T5
-    emb = torch.empty(B, width, device=dev)
-
-    def fwd5(i):
-        for k in range(T5):
-            ops.gather_fwd(tabs[k], idx5[k][:, 0], out=emb[:, k * D5:], out_stride=width)
-    ms_f5 = _time_loop(fwd5, 10)
-    res5 = dict(batch=B, tables=T5, emb_dim=D5, vocab_min=min(vocab), vocab_max=max(vocab), gather_concat_ms=ms_f5,
-                gather_algorithmic_bytes=B * T5 * (D5 * 4 * 2 + 4), gather_gbs=B * T5 * (D5 * 4 * 2 + 4) / ms_f5 / 1e6)
+    emb = torch.empty(B, T5, D5, device=dev)
+    ms_f5 = _time_loop(lambda i: ops.gather_fwd(tab, idx5, L=T5, field_row_offset=off5, out=emb, out_stride=D5), 20)
+    gbytes = B * T5 * (D5 * 4 * 2 + 4)
+    res5 = dict(batch=B, tables=T5, emb_dim=D5, vocab_min=min(vocab), vocab_max=max(vocab), rows=rows5, gather_concat_ms=ms_f5,
+                gather_algorithmic_bytes=gbytes, gather_gbs=gbytes / ms_f5 / 1e6, gather_frac=gbytes / ms_f5 / 1e6 / peak)
+    uniq = int(torch.unique(idx5.to(torch.int64) + off5[None]).numel())
     for nc in (2, 10):
         cons = [torch.randn(B, width, device=dev, generator=g) * 1e-3 for _ in range(nc)]
         stp5 = [0]
 
         def upd5(i):
             stp5[0] += 1
-            for k in range(T5):
-                src = GradSource([c[:, k * D5:] for c in cons], [width] * nc, [0] * nc)
-                ops.sparse_bwd_update(tabs[k], ms_[k][0], ms_[k][1], [LookupGroup(idx5[k], 1, src)], optimizer="adam_lazy", step=stp5[0])
-        ms_u = _time_loop(upd5, 5, warm=2)
-        uniq = sum(int(torch.unique(ix).numel()) for ix in idx5)
+            src = GradSource(cons, [width] * nc, [D5] * nc)
+            ops.sparse_bwd_update(tab, m5, v5, [LookupGroup(idx5, T5, src, field_row_offset=off5)], optimizer="adam_lazy", step=stp5[0])
+        ms_u = _time_loop(upd5, 10, warm=2)
         ubytes = B * T5 * (nc * D5 * 4 + 4) + uniq * D5 * 4 * 6
         res5[f"scatter_adam_{nc}_consumers_ms"] = ms_u
+        res5[f"scatter_adam_{nc}_consumers_algorithmic_bytes"] = ubytes
         res5[f"scatter_adam_{nc}_consumers_gbs"] = ubytes / ms_u / 1e6
         del cons
+    res5["unique_rows"] = uniq
     out["esmm_cfg5_multi_table"] = res5
     return out
 
@@ -445,6 +456,9 @@ def run_b200(args):
     from recommender_b200.optimizers import Adam
 
     D, V, T, B = args.emb_dim, args.rows_per_table, args.tables, args.batch
+    if world > 1 and args.exchange == "p2p" and not args.config2_sharded and T == 26:
+        args.criteo_tb = True          # BASELINE's multi-GPU workload (config 3) is what an N > 1 run measures
+    cap_factor = args.capacity_factor or (2.0 if args.criteo_tb else 1.25)
     cd = torch.bfloat16 if args.mlp_dtype == "bf16" else None
     gen = torch.Generator(device=dev).manual_seed(4)
     if world == 1:
@@ -453,9 +467,10 @@ def run_b200(args):
     elif peer_memory_usable(args, dev):
         from recommender_b200.p2p import P2PShardedDLRM
         model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
-                               table_rows=CRITEO_TB_ROWS if args.criteo_tb else None, capacity_factor=2.0 if args.criteo_tb else 1.25)
+                               table_rows=CRITEO_TB_ROWS if args.criteo_tb else None, capacity_factor=cap_factor)
     else:
         from recommender_b200.sharded import ShardedDLRM
+        args.criteo_tb = False           # the NCCL all-to-all fallback runs config 2 sharded
         model = ShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
                             sharding=args.sharding)
     for m in model.modules():
@@ -716,6 +731,28 @@ def run_b200(args):
         gather = dict(metric="embedding-gather HBM GB/s", ms=g_ms, algorithmic_bytes=g_bytes, achieved_gbs=g_bytes / (g_ms * 1e-3) / 1e9,
                       frac=g_bytes / (g_ms * 1e-3) / 1e9 / peak, peak=peak, lookups=N, emb_dim=D)
         del gout
+        # the dominant call once more with nothing else on the GPU (in the step its events also count the time its CTAs queue behind
+        # kernels of the other streams)
+        if roofline is not None and roofline.get("kernel") == "sparse_bwd_apply" and "m" in model.embedding_layer.opt_state:
+            from recommender_b200.ops import GradSource, LookupGroup
+            st = model.embedding_layer.opt_state
+            dE = torch.randn(B, F_CAT, D, device=dev) * 1e-3
+            ws = ops.sparse_workspace(N, D, table.shape[0], dev)
+            ts = []
+            for i in range(8):
+                grp = [LookupGroup(resident[i % args.ring][0], F_CAT, GradSource.per_position(dE, F_CAT), field_row_offset=off)]
+                sel = ops.sparse_bwd_prepare(table.shape[0], D, grp, ws)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                ops.sparse_bwd_apply(table, st["m"], st["v"], grp, ws, sel, optimizer="adam_lazy", step=1000 + i)
+                a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            ts.sort()
+            alone_ms = ts[len(ts) // 2]
+            alone_gbs = algo["sparse_bwd_apply"] / (alone_ms * 1e-3) / 1e9
+            roofline.update(alone_ms=alone_ms, achieved_alone=alone_gbs, frac_alone=alone_gbs / peak, frac_alone_of_nominal_8tbs=alone_gbs / 8000.0)
+            del dE, ws
 
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:

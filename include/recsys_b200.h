@@ -58,6 +58,11 @@ typedef enum rb_float_type {
                        whose padded kernel has a zero row there reads its bias gradient off its weight-gradient GEMM */
 } rb_float_type;
 
+/* how the fused lookup of rb_dot_interaction_fwd / _bwd copies table rows: past L1 (best for ids that rarely repeat), through L1
+ * (best when few rows take most of the lookups: Zipf ids, the OOV row of a shared table), or decided on the device from a flag
+ * that rb_sparse_bwd_prepare derives from the sorted ids of the step */
+typedef enum rb_row_cache { RB_ROW_CACHE_L2 = 0, RB_ROW_CACHE_L1 = 1, RB_ROW_CACHE_AUTO = 2 } rb_row_cache;
+
 /* pooling over the L positions of a bag */
 typedef enum rb_pool_mode {
   RB_POOL_SUM = 1,          /* tf.reduce_sum(E, axis=1)              ctr/model.py:21        */
@@ -181,6 +186,18 @@ int rb_gather_fm_fwd(const float* table, int64_t rows, int32_t D,
                      const int64_t* field_row_offset, int64_t hash_mod,
                      float* E, float* s, float* fm, int32_t* oob_flag, void* stream);
 
+/*
+ * The same pass also writing DeepFM's deep input (ctr/model.py:25-26: tf.reshape(cat_embedding, (-1, F*D)) and the
+ * tf.concat with int_features) as the bf16 K operand of the MLP's first Dense layer:
+ *   deep[b, :] = [ E[b,0,:] ... E[b,F-1,:] | dense[b, 0..num_dense) | 1.0 | 0 ... ]   (ld_deep columns; the 1.0 only if a
+ * column is left: it turns that layer's bias gradient into a row of its weight-gradient GEMM).  E, s may be NULL.
+ */
+int rb_gather_fm_deep_fwd(const float* table, int64_t rows, int32_t D,
+                          const void* idx, int32_t idx_type, int64_t B, int32_t F,
+                          const int64_t* field_row_offset, int64_t hash_mod,
+                          const float* dense, int32_t num_dense, int64_t dense_ld, void* deep_bf16, int32_t ld_deep,
+                          float* E, float* s, float* fm, int32_t* oob_flag, void* stream);
+
 /* ---- K3..K6, K10: DotInteraction ------------------------------------------------------------ */
 
 /*
@@ -203,7 +220,10 @@ int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows,
                            const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                            const float* dense_vec, int64_t B, int32_t F, int32_t D,
                            int32_t self_interaction, int32_t skip_gather, int32_t tail,
-                           void* out, int32_t out_dtype, int64_t out_stride, void* stream);
+                           void* out, int32_t out_dtype, int64_t out_stride,
+                           int32_t row_cache, const int32_t* row_cache_hint, void* stream);
+/* row_cache (rb_row_cache) applies to the fused gather (E == NULL); row_cache_hint: the DEVICE flag of RB_ROW_CACHE_AUTO
+ * (NULL reads as 0).  The choice changes only which cache level serves the row copies, never a result. */
 
 /*
  * Backward of the above (TF autodiff of ctr/layers.py:25-42 and ctr/model.py:51-55):
@@ -217,7 +237,7 @@ int rb_dot_interaction_bwd(const float* E, const float* table, int64_t rows,
                            const float* dense_vec, int64_t B, int32_t F, int32_t D,
                            int32_t self_interaction, int32_t skip_gather, int32_t tail,
                            const void* dOut, int32_t dout_dtype, int64_t dout_stride,
-                           float* dE, float* d_dense, void* stream);
+                           float* dE, float* d_dense, int32_t row_cache, const int32_t* row_cache_hint, void* stream);
 
 /* ---- K7..K9: backward scatter + sparse optimizer row update ------------------------------- */
 
@@ -253,7 +273,10 @@ int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int6
  * *sorted_sel (host) tells apply which half of the double buffers holds them.
  */
 int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups,
-                          void* ws, size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, void* stream);
+                          void* ws, size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, int32_t* hot_rows_flag,
+                          void* stream);
+/* hot_rows_flag (optional DEVICE int32[1]): set to 1 when rows that take >= 64 lookups each account for more than a quarter of
+ * the step's lookups (Zipf ids, the OOV row), else 0 — the RB_ROW_CACHE_AUTO input of rb_dot_interaction_fwd / _bwd. */
 int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
                         const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
                         void* ws, size_t ws_bytes, int32_t sorted_sel, void* stream);

@@ -186,8 +186,9 @@ def mlp_backward(dy, acts, layers, final_activation, operand_dtype=None):
 # --------------------------------------------------------------------------------------
 
 
-def deepfm_forward(params, cat_features, int_features, num_int_fea=13, num_cat_fea=26):
-    """ctr/model.py:15-31.  params: {'table', 'mlp': [(W,b)...]}.  Returns (prob[B], cache)."""
+def deepfm_forward(params, cat_features, int_features, num_int_fea=13, num_cat_fea=26, mlp_dtype=None):
+    """ctr/model.py:15-31.  params: {'table', 'mlp': [(W,b)...]}.  Returns (prob[B], cache).  mlp_dtype='bf16': the MLP's
+    GEMMs read bf16 operands (mlp_forward)."""
     int_features = np.reshape(int_features, (-1, num_int_fea)).astype(F32)           # :17
     cat_features = np.reshape(cat_features, (-1, num_cat_fea))                      # :18
     E = embedding_lookup(params["table"], cat_features)                             # :19
@@ -195,18 +196,18 @@ def deepfm_forward(params, cat_features, int_features, num_int_fea=13, num_cat_f
     D = E.shape[2]
     deep_cat_input = E.reshape(-1, num_cat_fea * D)                                 # :25
     deep_input = np.concatenate([deep_cat_input, int_features], axis=1)             # :26
-    dense_output, acts = mlp_forward(deep_input, params["mlp"], None)               # :27
+    dense_output, acts = mlp_forward(deep_input, params["mlp"], None, mlp_dtype)    # :27
     logit = interaction + dense_output[:, 0]                                        # :28-29
     prob = sigmoid(logit)                                                           # :30
     return prob, dict(E=E, acts=acts, logit=logit, idx=cat_features, fm=interaction)
 
 
-def deepfm_backward(params, cache, dlogit, num_cat_fea=26):
+def deepfm_backward(params, cache, dlogit, num_cat_fea=26, mlp_dtype=None):
     """Gradients for deepfm_forward given dL/dlogit.  Table grad = sum of the three consumers
     of cat_embedding (ctr/model.py:21, :22, :25)."""
     E = cache["E"]
     B, Fc, D = E.shape
-    dx, mlp_grads = mlp_backward(dlogit[:, None].astype(F32), cache["acts"], params["mlp"], None)
+    dx, mlp_grads = mlp_backward(dlogit[:, None].astype(F32), cache["acts"], params["mlp"], None, mlp_dtype)
     dE = dx[:, : Fc * D].reshape(B, Fc, D) + fm_backward(E, dlogit.astype(F32))
     return dict(dE=dE.astype(F32), mlp=mlp_grads)
 

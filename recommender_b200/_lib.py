@@ -26,6 +26,8 @@ RB_F32, RB_BF16, RB_BF16_ONES = 0, 1, 2
 RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
 RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
 RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2
+RB_ROW_CACHE_L2, RB_ROW_CACHE_L1, RB_ROW_CACHE_AUTO = 0, 1, 2
+ROW_CACHE_ENUM = {False: RB_ROW_CACHE_L2, True: RB_ROW_CACHE_L1, "auto": RB_ROW_CACHE_AUTO, None: RB_ROW_CACHE_L2}
 RB_ACT_NONE, RB_ACT_RELU, RB_ACT_SIGMOID = 0, 1, 2
 ACT_ENUM = {None: RB_ACT_NONE, "relu": RB_ACT_RELU, "sigmoid": RB_ACT_SIGMOID}
 
@@ -69,14 +71,16 @@ SIGNATURES = {
     "rb_gather_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
     "rb_bag_pool_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _i64, _p, _p, _p]),
     "rb_gather_fm_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p]),
-    "rb_dot_interaction_fwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
-    "rb_dot_interaction_bwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p, _p, _p]),
+    "rb_gather_fm_deep_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p]),
+    "rb_dot_interaction_fwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _i32, _p, _p]),
+    "rb_dot_interaction_bwd": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p, _p, _i32, _p,
+                                         _p]),
     "rb_sparse_bwd_update_workspace_bytes": (C.c_size_t, [_i64, _i32, _i64]),
     "rb_sparse_bwd_update": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64,
                                        C.POINTER(RbGradSource), C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
     "rb_sparse_bwd_update_groups": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32,
                                               C.POINTER(RbOptParams), _p, C.c_size_t, _p, _p]),
-    "rb_sparse_bwd_prepare": (C.c_int, [_i64, _i32, C.POINTER(RbLookupGroup), _i32, _p, C.c_size_t, _p, C.POINTER(C.c_int32), _p]),
+    "rb_sparse_bwd_prepare": (C.c_int, [_i64, _i32, C.POINTER(RbLookupGroup), _i32, _p, C.c_size_t, _p, C.POINTER(C.c_int32), _p, _p]),
     "rb_sparse_bwd_apply": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32, C.POINTER(RbOptParams), _p,
                                       C.c_size_t, _i32, _p]),
     "rb_sparse_bwd_dedup": (C.c_int, [_i64, _i32, _p, _i32, _i64, _i32, _p, _i64, C.POINTER(RbGradSource),

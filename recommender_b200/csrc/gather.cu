@@ -4,9 +4,19 @@
 // accesses, so a warp request covers whole 32 B sectors of each row.  The un-pooled gather
 // stages its index block in shared memory with one bulk async copy (cp.async.bulk + mbarrier,
 // the 1-D TMA path: SASS UBLKCP) so that the dependent row loads are issued from on-chip data.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rb {
+
+// The DeepFM deep input row (ctr/model.py:25-26) as the bf16 K operand of the MLP's first Dense layer:
+// [flatten(E) | int_features | 1.0 | 0 ...] of `ld` columns, written by the kernel that gathers E.
+struct DeepRow {
+  __nv_bfloat16* out;      // [B, ld] or null
+  const float* dense;      // [B, num_dense] (row stride dense_ld)
+  int num_dense, dense_ld, ld;
+};
 
 // ---- mbarrier / bulk-copy PTX (1-D TMA) ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -192,7 +202,7 @@ bag_pool_kernel(const float* __restrict__ table, IndexMap m, int64_t B, int L, i
 template <int VEC, int GS>
 __global__ void __launch_bounds__(kPoolThreads)
 gather_fm_kernel(const float* __restrict__ table, IndexMap m, int64_t B, int F, int D, float* __restrict__ E,
-                 float* __restrict__ s_out, float* __restrict__ fm_out, int* __restrict__ oob_flag) {
+                 float* __restrict__ s_out, float* __restrict__ fm_out, int* __restrict__ oob_flag, DeepRow deep) {
   const int64_t b = static_cast<int64_t>(blockIdx.x) * (kPoolThreads / GS) + threadIdx.x / GS;
   const int lane = threadIdx.x % GS;
   const bool b_ok = b < B;
@@ -225,6 +235,11 @@ gather_fm_kernel(const float* __restrict__ table, IndexMap m, int64_t B, int F, 
         if (row[u] != -2) {
           oob |= (row[u] == -1);
           if (active && E != nullptr) st_row_stream<VEC>(E + (p0 + f0 + j0 + u) * D + lane * VEC, val[u]);
+          if (active && deep.out != nullptr) {
+            __nv_bfloat16* dst = deep.out + b * deep.ld + (f0 + j0 + u) * D + lane * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) dst[k] = __float2bfloat16_rn(val[u].v[k]);
+          }
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
             s.v[k] += val[u].v[k];
@@ -244,6 +259,14 @@ gather_fm_kernel(const float* __restrict__ table, IndexMap m, int64_t B, int F, 
 #pragma unroll
   for (int o = GS / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, GS);
   if (b_ok && lane == 0 && fm_out != nullptr) fm_out[b] = 0.5f * part;
+  if (b_ok && deep.out != nullptr) {      // the tail of the deep row: dense features, the ones column, zero pads
+    const int c0 = F * D;
+    for (int c = c0 + lane; c < deep.ld; c += GS) {
+      const int j = c - c0;
+      const float v = j < deep.num_dense ? __ldg(deep.dense + b * deep.dense_ld + j) : (j == deep.num_dense ? 1.0f : 0.f);
+      deep.out[b * deep.ld + c] = __float2bfloat16_rn(v);
+    }
+  }
   if (oob && oob_flag != nullptr) *oob_flag = 1;
 }
 
@@ -356,8 +379,34 @@ extern "C" int rb_gather_fm_fwd(const float* table, int64_t rows, int32_t D, con
                "E/s pointer not aligned for vec=%d", g.vec);
   IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, F);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeepRow deep{nullptr, nullptr, 0, 0, 0};
 #define CALL(V, G) \
-  gather_fm_kernel<V, G><<<grid_for(B, kPoolThreads / G), kPoolThreads, 0, st>>>(table, m, B, F, D, E, s, fm, oob_flag)
+  gather_fm_kernel<V, G><<<grid_for(B, kPoolThreads / G), kPoolThreads, 0, st>>>(table, m, B, F, D, E, s, fm, oob_flag, deep)
+  RB_DISPATCH_GEOM(g, CALL);
+#undef CALL
+  RB_LAUNCH_CHECK("gather_fm_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_gather_fm_deep_fwd(const float* table, int64_t rows, int32_t D, const void* idx, int32_t idx_type, int64_t B, int32_t F,
+                                     const int64_t* field_row_offset, int64_t hash_mod, const float* dense, int32_t num_dense,
+                                     int64_t dense_ld, void* deep_bf16, int32_t ld_deep, float* E, float* s, float* fm, int32_t* oob_flag,
+                                     void* stream) {
+  RowGeom g;
+  int rc = check_table(table, rows, D, &g);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(B >= 0 && F > 0 && (idx_type == RB_I32 || idx_type == RB_I64), RB_ERR_ARG, "bad B/F or index type");
+  if (B == 0) return RB_OK;
+  RB_CHECK_ARG(idx != nullptr && deep_bf16 != nullptr, RB_ERR_ARG, "idx / deep row is null");
+  RB_CHECK_ARG(num_dense >= 0 && (num_dense == 0 || (dense != nullptr && dense_ld >= num_dense)), RB_ERR_ARG, "bad dense features");
+  RB_CHECK_ARG(ld_deep >= F * D + num_dense, RB_ERR_SHAPE, "deep row of %d columns cannot hold %d x %d + %d values", ld_deep, F, D, num_dense);
+  RB_CHECK_ARG((E == nullptr || aligned_for(E, g.vec)) && (s == nullptr || aligned_for(s, g.vec)), RB_ERR_ALIGN,
+               "E/s pointer not aligned for vec=%d", g.vec);
+  IndexMap m = make_index_map(idx, idx_type, field_row_offset, hash_mod, rows, F);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeepRow deep{static_cast<__nv_bfloat16*>(deep_bf16), dense, num_dense, static_cast<int>(dense_ld), ld_deep};
+#define CALL(V, G) \
+  gather_fm_kernel<V, G><<<grid_for(B, kPoolThreads / G), kPoolThreads, 0, st>>>(table, m, B, F, D, E, s, fm, oob_flag, deep)
   RB_DISPATCH_GEOM(g, CALL);
 #undef CALL
   RB_LAUNCH_CHECK("gather_fm_kernel");

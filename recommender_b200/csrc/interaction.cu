@@ -67,7 +67,19 @@ struct IxArgs {
   int tail;
   int ncols;               // interaction columns (without tail)
   int pad_one;             // bf16 output rows: first pad column = 1.0 (RB_BF16_ONES)
+  int row_cache;           // rb_row_cache: copy table rows through L1 (hot rows: Zipf ids, the OOV row) or past it (uniform ids)
+  const int32_t* row_cache_hint;   // RB_ROW_CACHE_AUTO: device flag written by rb_sparse_bwd_prepare of this / the previous step
 };
+
+// Hot rows.  Under Zipf ids on ONE shared table (the reference's layout, ctr/model.py:42) a tenth of all lookups read the
+// same row: through L2 only (cp.async.cg) every SM queues on the one L2 slice that holds the line and the forward runs 3.3x
+// slower than with uniform ids (r2_00: 376 us against 132 us); through L1 (cp.async.ca) each SM keeps the handful of hot
+// rows itself (r2_10: 105 us).  With uniform ids the L1 pass costs ~20 % (107 -> 130 us): nothing is re-used and every
+// row allocates two lines.  So the choice is made per step from the ids themselves (RB_ROW_CACHE_AUTO).
+__device__ __forceinline__ bool rows_through_l1(const IxArgs& a) {
+  if (a.row_cache == RB_ROW_CACHE_AUTO) return a.row_cache_hint != nullptr && __ldg(a.row_cache_hint) != 0;
+  return a.row_cache == RB_ROW_CACHE_L1;
+}
 
 // ---- small PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -123,7 +135,7 @@ __device__ __forceinline__ uint32_t load_sample_row(const IxArgs& a, int64_t b, 
 template <int D, int STRIDE, bool SHARDED>
 __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, uint32_t my_row, int F, float* dst_lane,
                                            int sub, const float* __restrict__ dense_lane, float* dense_dst,
-                                           const float* const* shard_base, uint32_t world, int col) {
+                                           const float* const* shard_base, uint32_t world, int col, bool l1) {
   constexpr int kRowsPerIter = 32 / (D / 4);
 #pragma unroll 4
   for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
@@ -140,7 +152,7 @@ __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, u
       }
     }
     if (r < F) {   // invalid row: zero-filled by the copy
-      if constexpr (SHARDED && RB_PEER_CA) cp_async16_ca(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
+      if ((SHARDED && RB_PEER_CA) || l1) cp_async16_ca(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
       else cp_async16(dst_lane + r0 * STRIDE, src, ok ? 16 : 0);
     }
   }
@@ -273,10 +285,11 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
 
   uint32_t row_next = load_sample_row(a, b, lane, lane_off);
   const int col = (lane % kLanesPerRow) * 4;
+  const bool l1 = rows_through_l1(a);
   auto issue = [&](int64_t bb, uint32_t rows, int st) {
     float* xn = xs_base + st * kXsFloats;
     issue_rows<D, STRIDE, SHARDED>(src_lane, rows, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
-                                   xn + F * STRIDE + lane * 4, shard_base, a.world, col);
+                                   xn + F * STRIDE + lane * 4, shard_base, a.world, col, l1);
   };
   // prologue: the first kIxStages-1 samples of this warp are put in flight
 #pragma unroll
@@ -594,6 +607,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
 
   constexpr int S16 = D + 8;   // bf16 elements per row of the staged X when it comes from x_load
   constexpr bool xl = (SRC == 2);
+  const bool l1 = rows_through_l1(a);
   auto issue = [&](int64_t bb, uint32_t row, int st) {
     unsigned char* sp = my + st * stage_bytes;
     float* xn = reinterpret_cast<float*>(sp);
@@ -607,7 +621,7 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
       }
     } else
     issue_rows<D, STRIDE, SRC == 1>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
-                          xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4);
+                          xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4, l1);
     const DOUT* grow = dOut + bb * dout_stride;
     load_row_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4 + 16), misalign_elems(grow), copy_width, lane);
   };
@@ -700,6 +714,8 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
 static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows, const void* idx, int idx_type,
                      const int64_t* off, const float* dense_vec, int64_t B, int F, int D, int self_interaction,
                      int skip_gather, int tail, const float* const* shards = nullptr, int world = 1) {
+  a->row_cache = RB_ROW_CACHE_L2;
+  a->row_cache_hint = nullptr;
   RB_CHECK_ARG(B >= 0 && F > 0, RB_ERR_ARG, "bad B/F");
   RB_CHECK_ARG(D == 16 || D == 32 || D == 64 || D == 128, RB_ERR_SHAPE, "dot interaction needs D in {16,32,64,128}, got %d", D);
   const int Fp = F + (dense_vec != nullptr ? 1 : 0);
@@ -855,11 +871,15 @@ using namespace rb;
 extern "C" int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows, const void* idx,
                                       int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                       int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
-                                      int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* stream) {
+                                      int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, int32_t row_cache,
+                                      const int32_t* row_cache_hint, void* stream) {
   IxArgs a;
   int rc = fill_args(&a, E, table, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction,
                      skip_gather, tail);
   if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(row_cache >= RB_ROW_CACHE_L2 && row_cache <= RB_ROW_CACHE_AUTO, RB_ERR_ARG, "bad row_cache %d", row_cache);
+  a.row_cache = row_cache;
+  a.row_cache_hint = row_cache_hint;
   if (B == 0) return RB_OK;
   const int total = a.ncols + (a.tail ? D : 0);
   RB_CHECK_ARG(out != nullptr && out_stride >= total, RB_ERR_ARG, "out is null or out_stride too small");
@@ -881,11 +901,14 @@ extern "C" int rb_dot_interaction_bwd(const float* E, const float* table, int64_
                                       int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                       int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
                                       int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
-                                      float* d_dense, void* stream) {
+                                      float* d_dense, int32_t row_cache, const int32_t* row_cache_hint, void* stream) {
   IxArgs a;
   int rc = fill_args(&a, E, table, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction,
                      skip_gather, tail);
   if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(row_cache >= RB_ROW_CACHE_L2 && row_cache <= RB_ROW_CACHE_AUTO, RB_ERR_ARG, "bad row_cache %d", row_cache);
+  a.row_cache = row_cache;
+  a.row_cache_hint = row_cache_hint;
   if (B == 0) return RB_OK;
   RB_CHECK_ARG(dOut != nullptr && dout_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "dOut is null or stride too small");
   RB_CHECK_ARG(dout_dtype == RB_F32 || dout_dtype == RB_BF16, RB_ERR_ARG, "bad dout_dtype %d", dout_dtype);

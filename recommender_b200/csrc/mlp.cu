@@ -40,7 +40,7 @@ constexpr int kEpilogueGroups = 2;                   // groups of four warps (on
 constexpr int kThreads = (kEpilogueWarp0 + 4 * kEpilogueGroups) * 32;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
 constexpr int kBStageBytes = kMaxN * kBlockK * 2;      // 32 KiB
-constexpr int kSlabBytes = kBlockM * 128;              // an output slab: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
+constexpr int kSlabBytes = kBlockM * 128;              // per epilogue group: one fp32 slab (128 rows x 128 bytes) or two bf16 slabs (x 64 bytes)
 constexpr int kSlabs = kEpilogueGroups;
 constexpr int kAtomBytes = 64 * kBlockK * 2;           // MN-major operands: one 64-wide box of 64 reduction rows = 8 KiB
 constexpr int kTmemCols = 512;
@@ -51,6 +51,9 @@ struct GemmArgs {
   int32_t M, N, K;             // C[M, N] = sum_k A[m, k] * B[n, k]
   int32_t block_n;             // columns per tile: multiple of 64, <= 256
   int32_t a_mn, b_mn;          // 1: the operand is MN-major in memory
+  int32_t a_atoms, b_atoms;    // MN-major operand whose M / N extent is a multiple of 64: its map is 3-D {64, K, extent / 64} and ONE
+                               // TMA instruction stages all 64-column boxes of the tile (a single thread issues ~1 TMA per 130 cycles:
+                               // five per stage starved the MMAs, stats r2_09); 0: one 2-D box per instruction
   int32_t m_blocks, n_blocks, splits, k_blocks, k_blocks_per_split;
   int32_t out_f32;             // 0: bf16 C;  1: fp32 C (split s writes rows [s * m_blocks * 128, ...) of the output map)
   int32_t activation;          // rb_activation, applied after the bias
@@ -105,6 +108,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(saddr(dst)),
                "l"(map), "r"(saddr(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(saddr(dst)),
+               "l"(map), "r"(saddr(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1) {
@@ -181,10 +189,12 @@ __device__ __forceinline__ float apply_activation(float x, int act) {
   return x;
 }
 
-// 32 accumulator columns of one row -> (+ bias, activation) -> 128 bytes of fp32 or 64 bytes of bf16 in the swizzled slab row.
-// `chunk0` is the first 16-byte chunk of the row these columns occupy; s_bias points at their 32 biases in shared memory.
+// 32 accumulator columns of one row -> (+ bias, activation) -> the slab row in shared memory: 128 bytes of fp32 (128-byte
+// swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)) or 64 bytes of bf16 (64-byte swizzle: chunk c ^ ((r >> 1) & 3)).
+// `sw` is that row term; s_bias points at the 32 biases in shared memory.
 template <bool F32, int ACT>
-__device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const float* s_bias, uint8_t* srow, int chunk0, int sw) {
+__device__ __forceinline__ void store_columns(const uint32_t (&v)[32], const float* s_bias, uint8_t* srow, int sw) {
+  constexpr int chunk0 = 0;
   uint32_t pk[2];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -231,6 +241,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(saddr(dst)),
       "l"(map), "r"(saddr(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          saddr(dst)),
+      "l"(map), "r"(saddr(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
@@ -328,10 +345,12 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
         const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
         // a tile that hangs over the right edge of C multiplies only the columns that exist (rounded up to the MMA's N step);
         // this CTA stages share `rank` of them
-        const int n_eff = min(g.block_n, (g.N - n0 + 16 * CG - 1) / (16 * CG) * (16 * CG));
+        const int n_round = (g.b_atoms ? 64 : 16) * CG;
+        const int n_eff = min(g.block_n, (g.N - n0 + n_round - 1) / n_round * n_round);
         const int n_mine = n_eff / CG, nb0 = n0 + rank * n_mine;
         const int b_boxes = (n_mine + 63) / 64;
-        const uint32_t my_bytes = kAStageBytes + (g.b_mn ? static_cast<uint32_t>(b_boxes) * kAtomBytes : static_cast<uint32_t>(g.block_n / CG) * 128u);
+        const uint32_t my_bytes = kAStageBytes + ((g.b_mn && !g.b_atoms) ? static_cast<uint32_t>(b_boxes) * kAtomBytes
+                                                                         : static_cast<uint32_t>(g.block_n / CG) * 128u);
         for (int kb = kb0; kb < kb1; ++kb) {
           const long long t0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
@@ -343,12 +362,16 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * my_bytes);      // both CTAs stage the same number of bytes
             if (!g.a_mn) {
               tma_load_2d_pair(a_dst, &map_a, &full[stage], k0, m0);
+            } else if (g.a_atoms) {
+              tma_load_3d_pair(a_dst, &map_a, &full[stage], 0, k0, m0 / 64);
             } else {
               tma_load_2d_pair(a_dst, &map_a, &full[stage], m0, k0);
               tma_load_2d_pair(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
             }
             if (!g.b_mn) {
               tma_load_2d_pair(b_dst, &map_b, &full[stage], k0, nb0);
+            } else if (g.b_atoms) {
+              tma_load_3d_pair(b_dst, &map_b, &full[stage], 0, k0, nb0 / 64);
             } else {
               for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
             }
@@ -356,12 +379,16 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
             mbar_expect_tx(&full[stage], my_bytes);
             if (!g.a_mn) {
               tma_load_2d(a_dst, &map_a, &full[stage], k0, m0);
+            } else if (g.a_atoms) {
+              tma_load_3d(a_dst, &map_a, &full[stage], 0, k0, m0 / 64);
             } else {
               tma_load_2d(a_dst, &map_a, &full[stage], m0, k0);
               tma_load_2d(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
             }
             if (!g.b_mn) {
               tma_load_2d(b_dst, &map_b, &full[stage], k0, nb0);
+            } else if (g.b_atoms) {
+              tma_load_3d(b_dst, &map_b, &full[stage], 0, k0, nb0 / 64);
             } else {
               for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
             }
@@ -396,7 +423,8 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       for (int w = tile_id0; w < total; w += tile_stride, ++it) {
         const int split = w / (g.n_blocks * g.m_blocks);
         const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
-        const int n_eff = min(g.block_n, (g.N - (w % g.n_blocks) * g.block_n + 16 * CG - 1) / (16 * CG) * (16 * CG));
+        const int n_round = (g.b_atoms ? 64 : 16) * CG;
+        const int n_eff = min(g.block_n, (g.N - (w % g.n_blocks) * g.block_n + n_round - 1) / n_round * n_round);
         const uint32_t idesc = idesc0 | (static_cast<uint32_t>(n_eff >> 3) << 17);   // N of this tile's MMAs
         const int acc = it & 1;
         long long t0 = clock64();
@@ -454,10 +482,14 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
     const int etid = q * 32 + lane;                             // thread index inside the group
     const int bar_id = 1 + grp;
     float* bias_g = s_bias + grp * kMaxN;
-    uint8_t* slab = smem_out + grp * kSlabBytes;
-    uint8_t* srow = slab + row * 128;
-    const int sw = row & 7;
-    constexpr int cols_per_slab = F32 ? 32 : 64;
+    // a slab = 32 output columns of the tile's 128 rows: fp32 -> 128-byte rows (16 KiB, one buffer per group), bf16 -> 64-byte rows
+    // (8 KiB, TWO buffers per group: the TMA store of one slab drains while the next is written)
+    constexpr int cols_per_slab = 32;
+    constexpr int kRowBytes = F32 ? 128 : 64;
+    constexpr int kBufs = F32 ? 1 : 2;
+    uint8_t* slab0 = smem_out + grp * kSlabBytes;
+    const int sw = F32 ? (row & 7) : ((row >> 1) & 3);
+    uint32_t slab_seq = 0;
     const int n_slabs = g.block_n / cols_per_slab;
     long long t_wait = 0;
     const long long t_begin = clock64();
@@ -479,14 +511,14 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       for (int s = grp; s < n_slabs; s += kEpilogueGroups) {
         const int c0 = n0 + s * cols_per_slab;                  // first output column of the slab
         if (c0 >= g.N) break;                                   // uniform over the group: the tile hangs over the edge of C
-        uint32_t v0[32], v1[32];
+        uint32_t v0[32];
         tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab), v0);          // in flight across the waits below
-        if constexpr (!F32) tmem_ld32(t_row + static_cast<uint32_t>(s * cols_per_slab + 32), v1);
-        if (etid == 0) tma_store_wait_read<0>();                // the group's previous store is done reading the slab buffer
+        uint8_t* slab = slab0 + (slab_seq % kBufs) * (kBlockM * kRowBytes);
+        ++slab_seq;
+        if (etid == 0) tma_store_wait_read<kBufs - 1>();        // the store that last read this slab buffer is done with it
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         tmem_ld_wait();
-        store_columns<F32, ACT>(v0, bias_g + s * cols_per_slab, srow, 0, sw);
-        if constexpr (!F32) store_columns<F32, ACT>(v1, bias_g + s * cols_per_slab + 32, srow, 4, sw);
+        store_columns<F32, ACT>(v0, bias_g + s * cols_per_slab, slab + row * kRowBytes, sw);
         fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA engine
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (etid == 0) {
@@ -721,7 +753,8 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // 2-D row-major matrix [outer, inner] with row stride `ld` elements; box = [box_outer, box_inner]; 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled();
   RB_CHECK_ARG(fn != nullptr, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const size_t esz = f32 ? 4 : 2;
@@ -732,10 +765,28 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner,
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RB_CHECK_ARG(r == CUDA_SUCCESS, RB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (inner %lld outer %lld ld %lld)", static_cast<int>(r),
                static_cast<long long>(inner), static_cast<long long>(outer), static_cast<long long>(ld));
+  return RB_OK;
+}
+
+// MN-major operand [K, MN] (row stride ld) with MN a multiple of 64, seen as {64, K, MN / 64}: a box of `atoms` 64-column slabs
+// of 64 reduction rows lands in shared memory slab after slab, exactly the layout the per-box loads produce
+static int make_map_atoms(CUtensorMap* map, const void* base, int64_t mn, int64_t k, int64_t ld, int atoms) {
+  EncodeTiledFn fn = encode_tiled();
+  RB_CHECK_ARG(fn != nullptr, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, RB_ERR_ALIGN,
+               "Dense operands need 16-byte aligned base pointers and row strides");
+  cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(mn / 64)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(atoms)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RB_CHECK_ARG(r == CUDA_SUCCESS, RB_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with %d (mn %lld k %lld ld %lld)", static_cast<int>(r),
+               static_cast<long long>(mn), static_cast<long long>(k), static_cast<long long>(ld));
   return RB_OK;
 }
 
@@ -755,6 +806,12 @@ static unsigned long long* g_debug_stats = nullptr;    // rb_dense_debug_stats
 // RB_DENSE_PAIR=0 in the environment keeps every product on single-CTA tiles (A/B measurements)
 static bool pair_enabled() {
   const char* e = getenv("RB_DENSE_PAIR");
+  return e == nullptr || e[0] != '0';
+}
+
+// RB_DENSE_ATOMS=0: MN-major operands are staged one 64-column box per TMA instruction (A/B measurements)
+static bool atoms_enabled() {
+  const char* e = getenv("RB_DENSE_ATOMS");
   return e == nullptr || e[0] != '0';
 }
 
@@ -833,10 +890,14 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   int rc;
   // K-major operand [MN, K]: box = 64 reduction elements x (128 | this CTA's share of block_n) rows.
   // MN-major operand [K, MN]: box = 64 x 64.
+  g.a_atoms = (a.mn_major && M % 64 == 0 && atoms_enabled()) ? 2 : 0;
+  g.b_atoms = (b.mn_major && N % 64 == 0 && atoms_enabled()) ? g.block_n / 64 / pl.cg : 0;
   if (!a.mn_major) rc = make_map(&ma, a.p, false, K, M, a.ld, kBlockK, kBlockM);
+  else if (g.a_atoms) rc = make_map_atoms(&ma, a.p, M, K, a.ld, g.a_atoms);
   else rc = make_map(&ma, a.p, false, M, K, a.ld, 64, kBlockK);
   if (rc != RB_OK) return rc;
   if (!b.mn_major) rc = make_map(&mb, b.p, false, K, N, b.ld, kBlockK, g.block_n / pl.cg);
+  else if (g.b_atoms) rc = make_map_atoms(&mb, b.p, N, K, b.ld, g.b_atoms);
   else rc = make_map(&mb, b.p, false, N, K, b.ld, 64, kBlockK);
   if (rc != RB_OK) return rc;
   void* out = c;
@@ -851,7 +912,7 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
     *splits_out = g.splits;
     *split_stride_out = split_stride;
   }
-  rc = make_map(&mc, out, c_f32, N, out_rows, out_ld, c_f32 ? 32 : 64, kBlockM);
+  rc = make_map(&mc, out, c_f32, N, out_rows, out_ld, 32, kBlockM, c_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != RB_OK) return rc;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
   static const KernelFn kernels[2][2][3] = {

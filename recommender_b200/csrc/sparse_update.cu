@@ -1029,8 +1029,22 @@ extern "C" float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t s
   return lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
 }
 
+// Hot-row census over the sorted keys: position i starts a window of kHotRun equal keys <=> its row takes at least kHotRun of
+// the step's lookups.  The count is (run length - kHotRun + 1) summed over such rows; when it exceeds a quarter of the
+// lookups the flag says "copy table rows through L1" to the fused lookups that follow (RB_ROW_CACHE_AUTO).
+constexpr int kHotRun = 64;
+__global__ void __launch_bounds__(256) hot_rows_count_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ count) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool hot = (i + kHotRun - 1 < n) && keys[i] == keys[i + kHotRun - 1];
+  const unsigned m = __ballot_sync(0xffffffffu, hot);
+  if (threadIdx.x % 32 == 0 && m != 0) atomicAdd(count, __popc(m));        // integer count: order-independent
+}
+__global__ void hot_rows_flag_kernel(int* __restrict__ count, int n, int32_t* __restrict__ flag) {
+  *flag = (static_cast<int64_t>(*count) * 4 > n) ? 1 : 0;
+}
+
 extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups, void* ws,
-                                     size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, void* stream) {
+                                     size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, int32_t* hot_rows_flag, void* stream) {
   RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
                "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
   RB_CHECK_ARG(sorted_sel != nullptr, RB_ERR_ARG, "sorted_sel is null");
@@ -1046,6 +1060,17 @@ extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_gr
   int sel = 0;
   rc = sort_groups(groups, num_groups, rows, n, static_cast<unsigned char*>(ws), lay, oob_flag, static_cast<cudaStream_t>(stream), &sel);
   *sorted_sel = sel;
+  if (rc == RB_OK && hot_rows_flag != nullptr) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t *keys, *vals;
+    sorted_pairs(static_cast<unsigned char*>(ws), lay, sel, &keys, &vals);
+    int* count = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + lay.long_count) + 2;     // [0] long chains, [1] valid pairs
+    RB_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    hot_rows_count_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, static_cast<int>(n), count);
+    RB_LAUNCH_CHECK("hot_rows_count_kernel");
+    hot_rows_flag_kernel<<<1, 1, 0, st>>>(count, static_cast<int>(n), hot_rows_flag);
+    RB_LAUNCH_CHECK("hot_rows_flag_kernel");
+  }
   return rc;
 }
 

@@ -95,6 +95,33 @@ class _GatherFMFn(torch.autograd.Function):
         return None, None, None
 
 
+class _GatherFMDeepFn(torch.autograd.Function):
+    """ctr/model.py:19-26 in one pass: fm, and the deep input [flatten(E) | int_features | 1 | 0...] as the bf16 K operand
+    of the MLP's first layer; E itself is never written.  Backward: the MLP's dx (bf16) carries the gradient of E through
+    the reshape / concat; the FM term is added inside the scatter (fm_g, fm_s)."""
+
+    @staticmethod
+    def forward(ctx, anchor, emb, idx, dense, ld):
+        F = idx.shape[1]
+        deep, s, fm = ops.gather_fm_deep_fwd(emb.embeddings, idx, dense, ld, field_row_offset=emb.row_offset_for(F), hash_mod=emb.hash_mod)
+        ctx.emb, ctx.idx, ctx.s = emb, idx, s
+        ctx.mark_non_differentiable(s)
+        return deep, fm
+
+    @staticmethod
+    def backward(ctx, d_deep, dfm):
+        emb = ctx.emb
+        B, F = ctx.idx.shape
+        D = emb.output_dim
+        if d_deep is None:
+            src, bs, ps = torch.zeros(D, dtype=torch.float32, device=ctx.idx.device), 0, 0
+        else:
+            src, bs, ps = d_deep[:, : F * D].float().contiguous(), F * D, D
+        grad = GradSource([src], [bs], [ps], fm_g=None if dfm is None else dfm.contiguous(), fm_s=ctx.s)
+        emb._record(LookupGroup(ctx.idx, F, grad, field_row_offset=emb.row_offset_for(F), hash_mod=emb.hash_mod))
+        return None, None, None, None, None
+
+
 class _InteractFn(torch.autograd.Function):
     """Lookup + DLRM concat + DotInteraction + '|| bmlp' tail in one kernel (ctr/model.py:49-55)."""
 
@@ -104,7 +131,8 @@ class _InteractFn(torch.autograd.Function):
         dense_vec = dense_vec.contiguous()
         out = ops.dot_interaction_fwd(table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
                                       dense_vec=dense_vec, self_interaction=self_interaction, skip_gather=skip_gather,
-                                      tail=tail, out_dtype=out_dtype, pad_to=pad_to, ones_col=ones_col)
+                                      tail=tail, out_dtype=out_dtype, pad_to=pad_to, ones_col=ones_col,
+                                      row_cache=emb.row_cache, row_cache_hint=emb._hot_rows)
         ctx.emb, ctx.idx, ctx.flags = emb, idx, (self_interaction, skip_gather, tail)
         ctx.save_for_backward(dense_vec)
         return out
@@ -118,7 +146,8 @@ class _InteractFn(torch.autograd.Function):
         if dOut.stride(-1) != 1:
             dOut = dOut.contiguous()
         dE, d_dense = ops.dot_interaction_bwd(dOut, table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
-                                              dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail)
+                                              dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail,
+                                              row_cache=emb.row_cache, row_cache_hint=emb._hot_rows)
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
         emb._grad_ready = torch.cuda.current_stream().record_event()    # dE is complete here: the row update may start
@@ -189,6 +218,10 @@ class Embedding(nn.Module):
         # The (row, position) sort of the backward depends on the ids only: it is started on a side stream
         # when the lookup runs and overlaps the forward / MLPs (rb_sparse_bwd_prepare / _apply).
         self.presort = True
+        # How the fused lookups copy table rows (rb_row_cache): "auto" lets the device decide per step from the hot-row census
+        # the pre-sort takes of the ids (rows with >= 64 lookups holding more than a quarter of them: through L1)
+        self.row_cache = "auto"
+        self._hot_rows = torch.zeros(1, dtype=torch.int32, device=dev)
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._sorted = None          # (idx tensor, L, selector, done event) of the sort in flight
         self._sort_ws: Optional[torch.Tensor] = None
@@ -239,7 +272,7 @@ class Embedding(nn.Module):
         side.wait_stream(main)            # ids are ready; the previous step's apply has released the workspace
         with torch.cuda.stream(side):
             sel = ops.sparse_bwd_prepare(rows, D, [LookupGroup(idx, L, None, field_row_offset=field_row_offset, hash_mod=self.hash_mod)],
-                                         self._sort_ws)
+                                         self._sort_ws, hot_rows_flag=self._hot_rows)
             done = side.record_event()
         if not torch.cuda.is_current_stream_capturing():
             idx.record_stream(side)
@@ -267,6 +300,13 @@ class Embedding(nn.Module):
         idx = idx.contiguous()
         self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return _GatherFMFn.apply(self._anchor, self, idx)
+
+    def lookup_fm_deep(self, idx: torch.Tensor, dense: torch.Tensor, ld: int):
+        """(deep bf16 [B, ld], fm [B]) of ctr/model.py:19-26: the lookup, the FM second order and the MLP's padded input row
+        [flatten(E) | dense | 1 | 0...] in one pass over the rows (rb_gather_fm_deep_fwd)."""
+        idx = idx.contiguous()
+        self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
+        return _GatherFMDeepFn.apply(self._anchor, self, idx, dense.float().contiguous(), int(ld))
 
     def interact(self, idx: torch.Tensor, dense_vec: torch.Tensor, self_interaction=False, skip_gather=True, tail=True,
                  out_dtype=torch.float32, pad_to=1, ones_col=False):

@@ -31,6 +31,16 @@ class DeepFM(nn.Module):
     def logits(self, inputs):
         int_features = inputs["int_features"].reshape(-1, self.num_int_fea)            # :17
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :18
+        if self.fused and self.mlp.compute_dtype == torch.bfloat16 and cat_features.is_cuda:
+            # :19-27 with the deep input written by the gather itself as the MLP's bf16 K operand: no E tensor, no reshape,
+            # no concat, no pad copy
+            D = self.embedding_layer.output_dim
+            if len(self.mlp.kernels) == 0:
+                self.mlp.build(self.num_cat_fea * D + self.num_int_fea, cat_features.device)
+            Kp = self.mlp.padded_in_dim()
+            deep_input, interaction = self.embedding_layer.lookup_fm_deep(cat_features, int_features, Kp)       # :19-26
+            dense_output = self.mlp(deep_input, ones_col=Kp > self.mlp.in_dim)                                    # :27
+            return interaction + dense_output.squeeze(1)                                                          # :28-29
         if self.fused:
             cat_embedding, interaction = self.embedding_layer.lookup_fm(cat_features)  # :19-23 in one pass
         else:

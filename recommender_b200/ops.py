@@ -134,6 +134,26 @@ def gather_fm_fwd(table, idx, *, field_row_offset=None, hash_mod=0, want_E=True,
     return E, s, fm
 
 
+def gather_fm_deep_fwd(table, idx, dense, ld_deep: int, *, field_row_offset=None, hash_mod=0):
+    """DeepFM front end emitting the MLP's padded bf16 input row (rb_gather_fm_deep_fwd):
+    returns (deep bf16 [B, ld_deep] = [flatten(E) | dense | 1 | 0...], s f32 [B, D], fm f32 [B])."""
+    _need_cuda(table, idx, dense, field_row_offset)
+    _f32c(table, "table")
+    idx = idx.contiguous()
+    B, F = idx.shape
+    rows, D = table.shape
+    dev = table.device
+    if dense.dtype != torch.float32 or dense.dim() != 2 or dense.stride(1) != 1 or dense.shape[0] != B:
+        raise TypeError("dense features must be float32 [B, num_dense] with unit inner stride")
+    deep = torch.empty(B, ld_deep, dtype=torch.bfloat16, device=dev)
+    s = torch.empty(B, D, dtype=torch.float32, device=dev)
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    check(lib.rb_gather_fm_deep_fwd(_ptr(table), rows, D, _ptr(idx), _idx(idx), B, F, _ptr(field_row_offset), int(hash_mod),
+                                    _ptr(dense), dense.shape[1], dense.stride(0), _ptr(deep), int(ld_deep), None, _ptr(s), _ptr(fm),
+                                    _ptr(oob_flag(dev)), _stream()), "rb_gather_fm_deep_fwd")
+    return deep, s, fm
+
+
 # --------------------------------------------------------------------------------------------
 # K3..K6, K10: DotInteraction
 # --------------------------------------------------------------------------------------------
@@ -154,7 +174,7 @@ def _float_type(dtype) -> int:
 
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
                         self_interaction=False, skip_gather=True, tail=False, out=None, out_stride=None,
-                        out_dtype=torch.float32, pad_to=1, ones_col=False):
+                        out_dtype=torch.float32, pad_to=1, ones_col=False, row_cache=False, row_cache_hint=None):
     """rb_dot_interaction_fwd.  Either E[B,F,D] or (table, idx[B,F]) supplies the embedding rows.
 
     out_dtype=torch.float32 returns the reference layout [B, ncols(+D)].  out_dtype=torch.bfloat16
@@ -186,12 +206,13 @@ def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, 
     check(lib.rb_dot_interaction_fwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
                                      B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(out),
                                      _lib.RB_BF16_ONES if (ones_col and out_dtype == torch.bfloat16 and out_stride > width)
-                                     else _float_type(out_dtype), int(out_stride), _stream()), "rb_dot_interaction_fwd")
+                                     else _float_type(out_dtype), int(out_stride), _lib.ROW_CACHE_ENUM[row_cache], _ptr(row_cache_hint),
+                                     _stream()), "rb_dot_interaction_fwd")
     return out
 
 
 def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None,
-                        self_interaction=False, skip_gather=True, tail=False, want_dE=True):
+                        self_interaction=False, skip_gather=True, tail=False, want_dE=True, row_cache=False, row_cache_hint=None):
     """rb_dot_interaction_bwd.  Returns (dE[B,F,D] | None, d_dense[B,D] | None)."""
     _need_cuda(dOut, E, table, idx, field_row_offset, dense_vec)
     if E is not None:
@@ -210,8 +231,8 @@ def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=
     d_dense = torch.empty(B, D, dtype=torch.float32, device=dev) if dense_vec is not None else None
     check(lib.rb_dot_interaction_bwd(_ptr(E), _ptr(table), rows, _ptr(idx), it, _ptr(field_row_offset), _ptr(dense_vec),
                                      B, F, D, int(self_interaction), int(skip_gather), int(tail), _ptr(dOut),
-                                     _float_type(dOut.dtype), int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _stream()),
-          "rb_dot_interaction_bwd")
+                                     _float_type(dOut.dtype), int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _lib.ROW_CACHE_ENUM[row_cache],
+                                     _ptr(row_cache_hint), _stream()), "rb_dot_interaction_bwd")
     return dE, d_dense
 
 
@@ -316,14 +337,14 @@ def sparse_workspace(n: int, D: int, rows: int, device) -> torch.Tensor:
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def sparse_bwd_prepare(rows: int, D: int, groups: Sequence["LookupGroup"], ws: torch.Tensor) -> int:
+def sparse_bwd_prepare(rows: int, D: int, groups: Sequence["LookupGroup"], ws: torch.Tensor, hot_rows_flag=None) -> int:
     """Phase 1 (rb_sparse_bwd_prepare): keys + stable radix sort of the groups' ids into `ws`, on the
     current stream.  Returns the selector to hand to sparse_bwd_apply.  Group gradients are not read."""
     for g in groups:
         _need_cuda(g.idx, g.field_row_offset)
     sel = C.c_int32(0)
     check(lib.rb_sparse_bwd_prepare(int(rows), int(D), _groups_c(groups, with_grad=False), len(groups), _ptr(ws), ws.numel(),
-                                    _ptr(oob_flag(ws.device)), C.byref(sel), _stream()), "rb_sparse_bwd_prepare")
+                                    _ptr(oob_flag(ws.device)), C.byref(sel), _ptr(hot_rows_flag), _stream()), "rb_sparse_bwd_prepare")
     return int(sel.value)
 
 

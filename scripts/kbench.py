@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--dist", default="uniform")
     ap.add_argument("--optimizer", default="adam_lazy")
+    ap.add_argument("--row-cache", default="l2", choices=["l2", "l1"], help="how the fused lookups copy table rows (rb_row_cache)")
     ap.add_argument("--tag", default=os.environ.get("RB_LIB_PATH", "default"))
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -68,11 +69,13 @@ def main():
         res[name] = dict(us_median=ts[len(ts) // 2], us_min=ts[0], us_mean=sum(ts) / len(ts))
 
     which = a.ops.split(",")
+    rc = a.row_cache == "l1"
     if "fwd" in which:
         timeit("fwd", lambda i: ops.dot_interaction_fwd(table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True,
-                                                        out=out, out_stride=stride, out_dtype=torch.bfloat16))
+                                                        out=out, out_stride=stride, out_dtype=torch.bfloat16, row_cache=rc))
     if "bwd" in which:
-        timeit("bwd", lambda i: ops.dot_interaction_bwd(dout, table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True))
+        timeit("bwd", lambda i: ops.dot_interaction_bwd(dout, table=table, idx=ring[i % 4], field_row_offset=off, dense_vec=dense, tail=True,
+                                                        row_cache=rc))
     if "gather" in which:
         timeit("gather", lambda i: ops.gather_fwd(table, ring[i % 4], L=F, field_row_offset=off))
     if "pool" in which:      # BASELINE config 4: masked mean over a behaviour history, L = 100, D = 32, item table of 400k rows
@@ -122,7 +125,7 @@ def main():
     for v_ in res.values():
         if "algorithmic_bytes" in v_:
             v_["gbs"] = round(v_["algorithmic_bytes"] / v_["us_median"] / 1e3, 1)
-    print(json.dumps(dict(tag=a.tag, tables=T, dist=a.dist, **res)))
+    print(json.dumps(dict(tag=a.tag, tables=T, dist=a.dist, row_cache=a.row_cache, **res)))
 
 
 if __name__ == "__main__":

@@ -57,7 +57,8 @@ def _X(E, table, idx, field_row_offset, dense_vec):
 
 
 def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None, self_interaction=False,
-                        skip_gather=True, tail=False, out=None, out_stride=None, out_dtype=torch.float32, pad_to=1, ones_col=False):
+                        skip_gather=True, tail=False, out=None, out_stride=None, out_dtype=torch.float32, pad_to=1, ones_col=False,
+                        row_cache=False, row_cache_hint=None):
     _launches[0] += 1
     X = _X(E, table, idx, field_row_offset, dense_vec)
     res = O.dot_interaction(X, self_interaction, skip_gather, operand_dtype="bf16")
@@ -75,7 +76,7 @@ def dot_interaction_fwd(*, E=None, table=None, idx=None, field_row_offset=None, 
 
 
 def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=None, dense_vec=None, self_interaction=False,
-                        skip_gather=True, tail=False, want_dE=True):
+                        skip_gather=True, tail=False, want_dE=True, row_cache=False, row_cache_hint=None):
     _launches[0] += 1
     X = _X(E, table, idx, field_row_offset, dense_vec)
     Fp = X.shape[1]

@@ -58,10 +58,10 @@ def test_argument_validation_without_a_gpu(cuda_lib):
     assert L.rb_gather_fwd(p, 10, 16, None, _lib.RB_I64, 0, 1, None, 0, None, 16, None, None) == 0
     assert L.rb_bag_pool_fwd(p, 10, 16, None, _lib.RB_I32, 0, 5, None, 0, _lib.RB_POOL_SUM, None, None, 16, None, None, None) == 0
     # interaction: too many features / bad D
-    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 33, 16, 0, 1, 0, p, 0, 33 * 33, None) == -2
-    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 24, 0, 1, 0, p, 0, 729, None) == -2
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 33, 16, 0, 1, 0, p, 0, 33 * 33, 0, None, None) == -2
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 24, 0, 1, 0, p, 0, 729, 0, None, None) == -2
     # tail without a dense vector
-    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 26, 16, 0, 1, 1, p, 0, 800, None) == -1
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 26, 16, 0, 1, 1, p, 0, 800, 0, None, None) == -1
     # sparse update: workspace too small is reported with the needed size
     need = L.rb_sparse_bwd_update_workspace_bytes(1000, 16, 5000)
     assert need > 1000 * 16
@@ -101,7 +101,8 @@ def test_argument_validation_of_the_dense_and_peer_memory_entry_points(cuda_lib)
     assert L.rb_bce_clipped(None, p, 0, 8, p, None, p, 1 << 20, None) == -1
     assert L.rb_bce_clipped(p, p, 7, 8, p, None, p, 1 << 20, None) == -1
     # interaction: RB_BF16_ONES needs a pad column
-    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 16, 0, 1, 0, p, _lib.RB_BF16_ONES, 729, None) == -1
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 16, 0, 1, 0, p, _lib.RB_BF16_ONES, 729, 0, None, None) == -1
+    assert L.rb_dot_interaction_fwd(p, None, 0, None, 0, None, None, 1, 27, 16, 0, 1, 0, p, 0, 729, 7, None, None) == -1      # bad row_cache
     # peer-memory path: world size and null checks
     ptrs = (C.c_void_p * 9)(*([p] * 9))
     nv = (C.c_int32 * 1)()

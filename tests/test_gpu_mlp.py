@@ -242,3 +242,38 @@ def test_the_benchmarked_dlrm_tracks_the_oracle(cuda_lib, golden, graphed):
         for i, W in enumerate(mlp.kernels):
             rW = params[name][i][0]
             assert np.abs(W.detach().cpu().numpy() - rW).mean() <= 0.02 * np.abs(rW - _mlp(g, name)[i][0]).max() + 1e-7
+
+
+def test_deepfm_with_the_fused_deep_input_row_tracks_the_oracle(cuda_lib, golden):
+    """BASELINE config 1's model in the bf16 configuration: rb_gather_fm_deep_fwd writes [flatten(E) | int | 1 | 0...] as the
+    MLP's bf16 K operand (ctr/model.py:19-27 without E, reshape, concat or pad copy); prob, loss, the MLP gradients and the
+    table gradient (three consumers of E: MLP, sum-square, square-sum) against the oracle with the same rounding points."""
+    from recommender_b200.model import DeepFM, bce_logits
+    from recommender_b200.optimizers import SGD
+    g = golden("deepfm_small")
+    mlp = _mlp(g, "mlp")
+    D, V = g["table"].shape[1], g["table"].shape[0]
+    params = dict(table=g["table"].copy(), mlp=mlp)
+    rprob, cache = O.deepfm_forward(params, g["cat"], g["dense"], mlp_dtype="bf16")
+    rloss, dlogit = O.bce_logits(cache["logit"], g["label"])
+    rg = O.deepfm_backward(params, cache, dlogit, mlp_dtype="bf16")
+    model = DeepFM(D, V, 13, 26, [W.shape[1] for W, _ in mlp], fused=True, device="cuda", compute_dtype=torch.bfloat16)
+    model.embedding_layer.embeddings.copy_(cu(g["table"]))
+    model.mlp.load_arrays(mlp, "cuda")
+    x = {"cat_features": cu(g["cat"]), "int_features": cu(g["dense"])}
+    logit = model.logits(x)
+    np.testing.assert_allclose(torch.sigmoid(logit).detach().cpu().numpy(), rprob, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(torch.sigmoid(logit).detach().cpu().numpy(), g["prob"], rtol=0, atol=2e-2)      # the fp32 reference run
+    loss = bce_logits(logit, cu(g["label"]))
+    assert abs(loss.item() - float(rloss)) <= 2e-3
+    loss.backward()
+    tol = 2.0 ** -6
+    for i, (W, b) in enumerate(zip(model.mlp.kernels, model.mlp.biases)):
+        rW, rb = rg["mlp"][i]
+        assert np.abs(W.grad.cpu().numpy() - rW).max() <= tol * np.abs(rW).max() + 1e-9, i
+        assert np.abs(b.grad.cpu().numpy() - rb).max() <= tol * np.abs(rb).max() + 1e-9, i
+    SGD(1.0).apply_gradients([model.embedding_layer])
+    dtable = g["table"] - model.embedding_layer.embeddings.cpu().numpy()
+    ref = np.zeros_like(g["table"])
+    np.add.at(ref, g["cat"].reshape(-1), rg["dE"].reshape(-1, D))
+    assert np.abs(dtable - ref).max() <= tol * np.abs(ref).max() + 1e-9
