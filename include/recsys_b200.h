@@ -275,8 +275,8 @@ int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int6
 int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups,
                           void* ws, size_t ws_bytes, int32_t* oob_flag, int32_t* sorted_sel, int32_t* hot_rows_flag,
                           void* stream);
-/* hot_rows_flag (optional DEVICE int32[1]): set to 1 when rows that take >= 64 lookups each account for more than a quarter of
- * the step's lookups (Zipf ids, the OOV row), else 0 — the RB_ROW_CACHE_AUTO input of rb_dot_interaction_fwd / _bwd. */
+/* hot_rows_flag (optional DEVICE int32[1]): set to 1 when rows that take >= 4096 lookups each hold more than 1/16 of the step's
+ * lookups beyond their first 4095 (Zipf ids on a shared table, an OOV row), else 0 — the RB_ROW_CACHE_AUTO input of rb_dot_interaction_fwd / _bwd. */
 int rb_sparse_bwd_apply(float* table, float* state0, float* state1, int64_t rows, int32_t D,
                         const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
                         void* ws, size_t ws_bytes, int32_t sorted_sel, void* stream);

@@ -36,6 +36,7 @@ constexpr int kBlockK = 64;                        // reduction elements per sta
 constexpr int kMaxN = 256;                         // columns of C per tile (tcgen05.mma N <= 256)
 constexpr int kStages = 4;
 constexpr int kEpilogueWarp0 = 4;
+constexpr int kPrefetchAhead = 8;                    // stages the L2 prefetch warp runs ahead of the TMA producer
 constexpr int kEpilogueGroups = 2;                   // groups of four warps (one per TMEM lane quarter)
 constexpr int kThreads = (kEpilogueWarp0 + 4 * kEpilogueGroups) * 32;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
@@ -57,6 +58,8 @@ struct GemmArgs {
   int32_t m_blocks, n_blocks, splits, k_blocks, k_blocks_per_split;
   int32_t out_f32;             // 0: bf16 C;  1: fp32 C (split s writes rows [s * m_blocks * 128, ...) of the output map)
   int32_t activation;          // rb_activation, applied after the bias
+  int32_t pf_a, pf_b;          // opt-in experiment (RB_DENSE_PREFETCH=1): a spare warp prefetches the operand's boxes into L2
+                               // kPrefetchAhead stages ahead of the TMA loads; see prefetch_enabled() for why it is off
   const float* bias;           // f32[N] or null
   unsigned long long* stats;   // diagnostic (rb_dense_debug_stats): per CTA, cycles each role spent waiting; null = off
 };
@@ -114,6 +117,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(saddr(dst)),
                "l"(map), "r"(saddr(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(saddr(src)), "r"(c0), "r"(c1)
@@ -298,6 +307,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
   uint64_t* acc_full = empty + kNumStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* produced = reinterpret_cast<volatile int*>(tmem_slot + 1);      // stages the TMA producer has issued (paces the prefetch warp)
   float* s_bias = reinterpret_cast<float*>(smem_out + kSlabs * kSlabBytes + 256);   // the tile's kMaxN biases, one copy per group
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -314,6 +324,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    *produced = 0;
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 4 * kEpilogueGroups * CG);     // one arrival per epilogue warp of the tile
@@ -338,6 +349,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       int stage = 0;
       uint32_t phase = 0;
       long long t_empty = 0;
+      int issued = 0;
       const long long t_begin = clock64();
       for (int w = tile_id0; w < total; w += tile_stride) {
         const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
@@ -397,11 +409,44 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
             stage = 0;
             phase ^= 1;
           }
+          *produced = ++issued;
         }
       }
       if (g.stats != nullptr) {
         g.stats[blockIdx.x * 8 + 3] = t_empty;
         g.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
+    }
+  } else if (warp == 3) {
+    // ===== L2 prefetch of the streamed operands, kPrefetchAhead stages ahead of the TMA loads ===================================
+    if (lane == 0 && (g.pf_a || g.pf_b)) {
+      int ahead = 0;
+      for (int w = tile_id0; w < total; w += tile_stride) {
+        const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
+        const int m0 = m_blk * (kBlockM * CG) + rank * kBlockM, n0 = n_blk * g.block_n;
+        const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
+        const int n_round = (g.b_atoms ? 64 : 16) * CG;
+        const int n_eff = min(g.block_n, (g.N - n0 + n_round - 1) / n_round * n_round);
+        const int n_mine = n_eff / CG, nb0 = n0 + rank * n_mine;
+        const int b_boxes = (n_mine + 63) / 64;
+        for (int kb = kb0; kb < kb1; ++kb, ++ahead) {
+          while (ahead >= *produced + kPrefetchAhead) __nanosleep(64);
+          const int k0 = kb * kBlockK;
+          if (g.pf_a) {
+            if (!g.a_mn) tma_prefetch_2d(&map_a, k0, m0);
+            else if (g.a_atoms) tma_prefetch_3d(&map_a, 0, k0, m0 / 64);
+            else {
+              tma_prefetch_2d(&map_a, m0, k0);
+              tma_prefetch_2d(&map_a, m0 + 64, k0);
+            }
+          }
+          if (g.pf_b) {
+            if (!g.b_mn) tma_prefetch_2d(&map_b, k0, nb0);
+            else if (g.b_atoms) tma_prefetch_3d(&map_b, 0, k0, nb0 / 64);
+            else
+              for (int j = 0; j < b_boxes; ++j) tma_prefetch_2d(&map_b, nb0 + 64 * j, k0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -803,16 +848,28 @@ static int block_n_for(int N) {
 
 static unsigned long long* g_debug_stats = nullptr;    // rb_dense_debug_stats
 
-// RB_DENSE_PAIR=0 in the environment keeps every product on single-CTA tiles (A/B measurements)
+// RB_DENSE_PAIR=1 in the environment runs the products whose tiles allow it on cta_group::2 pairs.  Measured (r2_11, 65536 x 800
+// x 512): forward 51.8 us against 52.9 us single-CTA, input gradient 62.0 against 59.5, weight gradient 62.5 against 59.5; the
+// whole step 1.374 ms against 1.343 ms — the single-CTA form is the default.
 static bool pair_enabled() {
   const char* e = getenv("RB_DENSE_PAIR");
-  return e == nullptr || e[0] != '0';
+  return e != nullptr && e[0] == '1';
 }
 
 // RB_DENSE_ATOMS=0: MN-major operands are staged one 64-column box per TMA instruction (A/B measurements)
 static bool atoms_enabled() {
   const char* e = getenv("RB_DENSE_ATOMS");
   return e == nullptr || e[0] != '0';
+}
+
+// RB_DENSE_PREFETCH=1: a spare warp prefetches the streamed operand's boxes into L2 ahead of the TMA loads.  Off by default:
+// measured (r2_12) it makes every product SLOWER (forward 53.2 -> 55.8 us, weight gradient 59.5 -> 67.6 us) and the MMA
+// issuer waits on operands MORE, not less — the wait is not DRAM latency but the SM's L2 -> shared-memory ingest rate (a
+// 128 x 256 tile needs 96 B / clk of operand fill), which extra TMA requests only load further.  What relieves it is the
+// 2-CTA form (64 B / clk per SM): there the wait halves (stats r2_11), but its other costs cancel the gain.
+static bool prefetch_enabled() {
+  const char* e = getenv("RB_DENSE_PREFETCH");
+  return e != nullptr && e[0] == '1';
 }
 
 static int max_pair_clusters() {
@@ -885,6 +942,9 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   g.activation = activation;
   g.bias = bias;
   g.stats = g_debug_stats;
+  const bool pf = prefetch_enabled();
+  g.pf_a = pf && static_cast<int64_t>(M) * K * 2 > (8ll << 20);
+  g.pf_b = pf && static_cast<int64_t>(N) * K * 2 > (8ll << 20);
   const int tile_m = kBlockM * pl.cg;
   CUtensorMap ma, mb, mc;
   int rc;

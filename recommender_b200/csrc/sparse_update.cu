@@ -1030,9 +1030,13 @@ extern "C" float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t s
 }
 
 // Hot-row census over the sorted keys: position i starts a window of kHotRun equal keys <=> its row takes at least kHotRun of
-// the step's lookups.  The count is (run length - kHotRun + 1) summed over such rows; when it exceeds a quarter of the
-// lookups the flag says "copy table rows through L1" to the fused lookups that follow (RB_ROW_CACHE_AUTO).
-constexpr int kHotRun = 64;
+// the step's lookups.  The count is (run length - kHotRun + 1) summed over such rows; when it exceeds 1/16 of the lookups
+// the flag says "copy table rows through L1" to the fused lookups that follow (RB_ROW_CACHE_AUTO).  Calibration (B = 65536,
+// F = 26, kbench r2_10 / r2_11, bench r2_12): the bench's Zipf ids (P(id >= x) = x^-0.05, + 2 % id 0) on ONE shared table put
+// 11 % of the lookups into such windows (18 rows with >= 4096 lookups each) — forward 347 -> 105 us, backward 447 -> 193 us
+// through L1; the same ids over 26 tables (the hottest row of a table takes ~2.2k lookups: census 0) run 6 % SLOWER through
+// L1 (111 -> 118 us) and uniform ids 20 % slower: both stay on L2.
+constexpr int kHotRun = 4096;
 __global__ void __launch_bounds__(256) hot_rows_count_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ count) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   const bool hot = (i + kHotRun - 1 < n) && keys[i] == keys[i + kHotRun - 1];
@@ -1040,7 +1044,7 @@ __global__ void __launch_bounds__(256) hot_rows_count_kernel(const uint32_t* __r
   if (threadIdx.x % 32 == 0 && m != 0) atomicAdd(count, __popc(m));        // integer count: order-independent
 }
 __global__ void hot_rows_flag_kernel(int* __restrict__ count, int n, int32_t* __restrict__ flag) {
-  *flag = (static_cast<int64_t>(*count) * 4 > n) ? 1 : 0;
+  *flag = (static_cast<int64_t>(*count) * 16 > n) ? 1 : 0;
 }
 
 extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_group* groups, int32_t num_groups, void* ws,

@@ -246,3 +246,38 @@ def test_dedup_order_against_pandas_factorize():
     for k in range(500):                                                          # unsorted_segment_sum, input order
         ref[codes[k]] += vals[k]
     np.testing.assert_array_equal(summed, ref)
+
+
+def test_bf16_operand_mlp_mode_restates_the_cuda_rounding_points():
+    """oracle.mlp_forward / mlp_backward(operand_dtype='bf16') (the restatement of csrc/mlp.cu's arithmetic used by the GPU
+    parity tests): every GEMM operand is a bf16 value, hidden activations and travelling gradients are bf16 values, the last
+    activation sees the fp32 accumulator, a Dense(1) head keeps its fp32 dz for dW / db; and the whole thing stays within
+    bf16 rounding of the fp32 layers."""
+    rng = np.random.default_rng(11)
+    layers = O.init_mlp(rng, 24, [64, 32, 1])
+    x = rng.normal(size=(50, 24)).astype(np.float32)
+    y32, a32 = O.mlp_forward(x, layers, "sigmoid")
+    y16, a16 = O.mlp_forward(x, layers, "sigmoid", "bf16")
+    for a in a16[:-1]:
+        np.testing.assert_array_equal(a, O.round_bf16(a))            # what the GEMMs read is representable in bf16
+    assert not np.array_equal(a16[-1], O.round_bf16(a16[-1]))         # the output is the fp32 activation of the fp32 accumulator
+    assert np.abs(y16 - y32).max() <= 2.0 ** -6
+    dy = rng.normal(size=y32.shape).astype(np.float32)
+    dx32, g32 = O.mlp_backward(dy, a32, layers, "sigmoid")
+    dx16, g16 = O.mlp_backward(dy, a16, layers, "sigmoid", "bf16")
+    np.testing.assert_array_equal(dx16, O.round_bf16(dx16))
+    assert np.abs(dx16 - dx32).max() <= 2.0 ** -5 * np.abs(dx32).max()
+    for (W16, b16), (W32, b32) in zip(g16, g32):
+        assert np.abs(W16 - W32).max() <= 2.0 ** -5 * np.abs(W32).max()
+        assert np.abs(b16 - b32).max() <= 2.0 ** -5 * np.abs(b32).max()
+    # the head's bias gradient is the fp32 sum of dz, not of a rounded dz
+    dz = dy * y16 * (1 - y16)
+    np.testing.assert_allclose(g16[-1][1], dz.sum(0), rtol=1e-6)
+    # DLRM / DeepFM accept the mode end to end
+    p = O.init_dlrm(4, [32, 16], [32, 1], 16, 500)
+    cat, dx, lab = O.synth_batch(32, 500, seed=4)
+    prob, c = O.dlrm_forward(p, cat, dx, operand_dtype="bf16", mlp_dtype="bf16")
+    ref, _ = O.dlrm_forward(p, cat, dx, operand_dtype="bf16")
+    assert np.abs(prob - ref).max() <= 2.0 ** -6
+    g = O.dlrm_backward(p, c, O.bce_clipped(prob, lab)[1], operand_dtype="bf16", mlp_dtype="bf16")
+    assert g["dE"].shape == (32, 26, 16) and np.isfinite(g["dE"]).all()
