@@ -22,6 +22,10 @@
 // the tensor work at a few percent of the kernel.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace rb {
@@ -801,6 +805,15 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
   return RB_OK;
 }
 
+// The sharded forward waits on NVLink, not on its SM: with fewer warps (less shared memory) per CTA the radix sort of the
+// owner's pairs, which runs beside it on the side stream, finds room on the same SMs instead of queueing behind it.
+// RB_IX16_WARPS caps the warps per CTA (tuning; default: as many as fit).
+static int sharded_fwd_warp_cap() {
+  const char* e = getenv("RB_IX16_WARPS");
+  const int v = e != nullptr ? atoi(e) : 0;
+  return v > 0 ? v : 64;
+}
+
 template <typename OUT>
 static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shadows, OUT* out, int64_t out_stride, int write_width,
                         cudaStream_t st) {
@@ -811,7 +824,7 @@ static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shad
 #define LAUNCH(DD)                                                                                                      \
   {                                                                                                                     \
     const size_t per_warp = static_cast<size_t>(kIxStages) * (32 * (DD + 8) * 2 + DD * 4) + os_bytes;                   \
-    const int W = warps_that_fit(per_warp);                                                                             \
+    const int W = std::min(warps_that_fit(per_warp), sharded_fwd_warp_cap());                                           \
     RB_CHECK_ARG(W >= 1, RB_ERR_SHAPE, "interaction row does not fit in shared memory");                                \
     size_t smem = static_cast<size_t>(W) * per_warp;                                                                    \
     rc = set_smem(dot_interaction_fwd16_kernel<DD, OUT>, smem);                                                         \
