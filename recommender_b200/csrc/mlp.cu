@@ -41,6 +41,7 @@ constexpr int kEpilogueGroups = 2;                   // groups of four warps (on
 constexpr int kThreads = (kEpilogueWarp0 + 4 * kEpilogueGroups) * 32;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
 constexpr int kBStageBytes = kMaxN * kBlockK * 2;      // 32 KiB
+constexpr int kBResidentBytes = kStages * kBStageBytes;   // 128 KiB: the B ring's shared memory, used as one resident panel
 constexpr int kSlabBytes = kBlockM * 128;              // per epilogue group: one fp32 slab (128 rows x 128 bytes) or two bf16 slabs (x 64 bytes)
 constexpr int kSlabs = kEpilogueGroups;
 constexpr int kAtomBytes = 64 * kBlockK * 2;           // MN-major operands: one 64-wide box of 64 reduction rows = 8 KiB
@@ -58,6 +59,8 @@ struct GemmArgs {
   int32_t m_blocks, n_blocks, splits, k_blocks, k_blocks_per_split;
   int32_t out_f32;             // 0: bf16 C;  1: fp32 C (split s writes rows [s * m_blocks * 128, ...) of the output map)
   int32_t activation;          // rb_activation, applied after the bias
+  int32_t b_resident;          // the whole B panel of the CTA's column block (K x block_n, <= kBResidentBytes) is loaded ONCE and stays in
+                               // shared memory; only A streams through the ring (single-CTA form, no split): small-K products
   int32_t pf_a, pf_b;          // opt-in experiment (RB_DENSE_PREFETCH=1): a spare warp prefetches the operand's boxes into L2
                                // kPrefetchAhead stages ahead of the TMA loads; see prefetch_enabled() for why it is off
   const float* bias;           // f32[N] or null
@@ -306,7 +309,8 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
   uint64_t* empty = full + kNumStages;
   uint64_t* acc_full = empty + kNumStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* b_full = acc_empty + 2;                     // B-resident form: the panel has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   volatile int* produced = reinterpret_cast<volatile int*>(tmem_slot + 1);      // stages the TMA producer has issued (paces the prefetch warp)
   float* s_bias = reinterpret_cast<float*>(smem_out + kSlabs * kSlabBytes + 256);   // the tile's kMaxN biases, one copy per group
 
@@ -325,6 +329,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       mbar_init(&empty[s], 1);
     }
     *produced = 0;
+    mbar_init(b_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 4 * kEpilogueGroups * CG);     // one arrival per epilogue warp of the tile
@@ -351,6 +356,20 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       long long t_empty = 0;
       int issued = 0;
       const long long t_begin = clock64();
+      if (CG == 1 && g.b_resident) {
+        // every tile of this CTA has the same column block (the grid is a multiple of n_blocks): its B panel is loaded once,
+        // k-block after k-block, in the layout a stage would have
+        const int n0 = (tile_id0 % g.n_blocks) * g.block_n;
+        const uint32_t tile_bytes = static_cast<uint32_t>(g.block_n) * 128u;
+        mbar_expect_tx(b_full, tile_bytes * static_cast<uint32_t>(g.k_blocks));
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          uint8_t* dst = smem_b + static_cast<size_t>(kb) * tile_bytes;
+          if (!g.b_mn) tma_load_2d(dst, &map_b, b_full, kb * kBlockK, n0);
+          else if (g.b_atoms) tma_load_3d(dst, &map_b, b_full, 0, kb * kBlockK, n0 / 64);
+          else
+            for (int j = 0; j < g.block_n / 64; ++j) tma_load_2d(dst + j * kAtomBytes, &map_b, b_full, n0 + 64 * j, kb * kBlockK);
+        }
+      }
       for (int w = tile_id0; w < total; w += tile_stride) {
         const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
         const int m0 = m_blk * (kBlockM * CG) + rank * kBlockM, n0 = n_blk * g.block_n;
@@ -388,7 +407,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
               for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
             }
           } else {
-            mbar_expect_tx(&full[stage], my_bytes);
+            mbar_expect_tx(&full[stage], g.b_resident ? static_cast<uint32_t>(kAStageBytes) : my_bytes);
             if (!g.a_mn) {
               tma_load_2d(a_dst, &map_a, &full[stage], k0, m0);
             } else if (g.a_atoms) {
@@ -397,7 +416,9 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
               tma_load_2d(a_dst, &map_a, &full[stage], m0, k0);
               tma_load_2d(a_dst + kAtomBytes, &map_a, &full[stage], m0 + 64, k0);
             }
-            if (!g.b_mn) {
+            if (g.b_resident) {
+              // B is already there
+            } else if (!g.b_mn) {
               tma_load_2d(b_dst, &map_b, &full[stage], k0, nb0);
             } else if (g.b_atoms) {
               tma_load_3d(b_dst, &map_b, &full[stage], 0, k0, nb0 / 64);
@@ -465,6 +486,11 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t b_tile16 = static_cast<uint32_t>(g.block_n) * 128u >> 4;      // B-resident: k-block stride of the panel
+      if (CG == 1 && g.b_resident) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
       for (int w = tile_id0; w < total; w += tile_stride, ++it) {
         const int split = w / (g.n_blocks * g.m_blocks);
         const int kb0 = split * g.k_blocks_per_split, kb1 = min(kb0 + g.k_blocks_per_split, g.k_blocks);
@@ -483,7 +509,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
           t_full += clock64() - t0;
           tc_fence_after();
           const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * (kAStageBytes >> 4));
-          const uint64_t bd = b_desc0 + static_cast<uint64_t>(stage * (kBBytes >> 4));
+          const uint64_t bd = b_desc0 + static_cast<uint64_t>(g.b_resident ? (kb - kb0) * b_tile16 : stage * (kBBytes >> 4));
           const int k_valid = g.K - kb * kBlockK;
           if (k_valid >= kBlockK) {
 #pragma unroll
@@ -899,7 +925,18 @@ static int max_pair_clusters() {
 struct Plan {
   int cg;          // CTAs per tile: 2 = cta_group::2 pairs
   int block_n, m_blocks, n_blocks, k_blocks, splits, kbps, workers;
+  int resident;    // B panel resident in shared memory (small K): grid is a multiple of n_blocks
 };
+
+// RB_DENSE_RESIDENT: 0 (default) = never, 1 = when every CTA gets at least two tiles, 2 = whenever the panel fits (tests).
+// Off by default — measured (r2_18, B = 65536): no product gets faster and the ones whose column block has to shrink to fit
+// the panel get much slower (800 -> 512 forward with 64-column blocks 53.9 -> 139 us, 512 -> 800 input gradient with 128-column
+// blocks 59.8 -> 85.7 us, 512 -> 256 forward 25.3 -> 30.2 us): one thread issues one tcgen05.mma per ~130 cycles, so an MMA must
+// be N = 256 wide (128 cycles of tensor work) to keep the pipe busy; halving N halves the work per issue slot.
+static int resident_mode() {
+  const char* e = getenv("RB_DENSE_RESIDENT");
+  return e == nullptr ? 0 : atoi(e);
+}
 
 static Plan make_plan(int M, int N, int K, bool split_k, bool use_pairs) {
   Plan p;
@@ -918,6 +955,26 @@ static Plan make_plan(int M, int N, int K, bool split_k, bool use_pairs) {
   if (split_k && tiles < p.workers) s = std::max(1, std::min(p.workers / tiles, p.k_blocks));
   p.kbps = (p.k_blocks + s - 1) / s;
   p.splits = (p.k_blocks + p.kbps - 1) / p.kbps;
+  // Small reduction axis (K <= 512: every product of the towers but the 800-wide ones): the operand B (the layer's kernel) of a
+  // column block is at most 128 KiB and the same for every row tile — keep it in shared memory and stream A alone.  A 128 x 256
+  // tile then needs 32 B / clk of operand fill instead of 96 (the SM ingests ~64): at K = 512 the column block shrinks to 128 so
+  // that the panel fits.
+  p.resident = 0;
+  const int mode = resident_mode();
+  if (mode > 0 && p.cg == 1 && !split_k && p.splits == 1) {
+    const int k_pad = p.k_blocks * kBlockK;
+    int bn = 0;
+    for (int cand : {256, 192, 128, 64})
+      if (bn == 0 && cand <= p.block_n && static_cast<int64_t>(k_pad) * cand * 2 <= kBResidentBytes) bn = cand;
+    if (bn != 0) {
+      const int nb = (N + bn - 1) / bn;
+      if (nb <= kNumSMs && (mode >= 2 || static_cast<int64_t>(p.m_blocks) * nb >= 2 * kNumSMs)) {
+        p.resident = 1;
+        p.block_n = bn;
+        p.n_blocks = nb;
+      }
+    }
+  }
   return p;
 }
 
@@ -940,6 +997,7 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   g.k_blocks_per_split = pl.kbps;
   g.out_f32 = c_f32;
   g.activation = activation;
+  g.b_resident = pl.resident;
   g.bias = bias;
   g.stats = g_debug_stats;
   const bool pf = prefetch_enabled();
@@ -989,7 +1047,9 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   }
   const int total = g.m_blocks * g.n_blocks * g.splits;
   const int workers = pl.cg == 2 ? std::min(pl.workers, max_pair_clusters()) : pl.workers;
-  kernels[pl.cg - 1][c_f32 ? 1 : 0][activation]<<<std::min(total, workers) * pl.cg, kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
+  int grid = std::min(total, workers) * pl.cg;
+  if (pl.resident) grid = std::min(workers / g.n_blocks, g.m_blocks) * g.n_blocks;      // a CTA keeps its column block
+  kernels[pl.cg - 1][c_f32 ? 1 : 0][activation]<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
   RB_LAUNCH_CHECK("dense_gemm_kernel");
   return RB_OK;
 }

@@ -718,3 +718,112 @@ def test_bce_clipped_head(ops, n, ltype):
     pc = pt.clamp(e, 1 - e)
     (-(yt * torch.log(pc + e) + (1 - yt) * torch.log(1 - pc + e))).mean().backward()
     np.testing.assert_allclose(dprob.cpu().numpy(), pt.grad.cpu().numpy(), rtol=1e-5, atol=1e-12)
+
+
+# ---- stand-in for compute-sanitizer (closed on this pool, profiles/r2_16_compute_sanitizer_closed.md) -------------------
+
+CANARY = 0x5A
+
+
+def _framed(shape, dtype, pad=4096):
+    """A tensor of `shape` carved out of the middle of a byte buffer whose margins hold a canary pattern."""
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    buf = torch.full((pad + n + pad,), CANARY, dtype=torch.uint8, device="cuda")
+    return buf, buf[pad:pad + n].view(dtype).reshape(shape)
+
+
+def _intact(buf, n_inner, pad=4096):
+    return bool((buf[:pad] == CANARY).all()) and bool((buf[pad + n_inner:] == CANARY).all())
+
+
+def test_kernels_stay_inside_their_outputs_and_repeat_bit_for_bit(ops):
+    """Every hot-path entry point writes into the interior of canary-framed buffers (the margins must survive) and gives
+    bit-identical results when repeated on the same inputs (a race would show as run-to-run differences)."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    g = torch.Generator(device="cuda").manual_seed(9)
+    V, D, B, F = 5003, 64, 333, 26                 # odd sizes: ragged chunks, partial tiles
+    W = torch.empty(V, D, device="cuda").uniform_(-0.05, 0.05, generator=g)
+    idx = torch.randint(0, V, (B, F), device="cuda", generator=g)
+    idx[torch.rand(B, F, device="cuda", generator=g) < 0.1] = 0
+    dv = torch.randn(B, D, device="cuda", generator=g) * 0.1
+
+    def thrice(fn):
+        outs = [fn() for _ in range(3)]
+        for o in outs[1:]:
+            for a, b in zip(outs[0], o):
+                assert torch.equal(a, b)
+        return outs[0]
+
+    # un-pooled gather into a framed [B, F, D]
+    def gather():
+        buf, E = _framed((B, F, D), torch.float32)
+        ops.gather_fwd(W, idx, L=F, out=E, out_stride=D)
+        torch.cuda.synchronize()
+        assert _intact(buf, E.numel() * 4)
+        return (E.clone(),)
+    thrice(gather)
+
+    # fused interaction forward (bf16 padded row with ones column) and backward
+    width = 27 * 27 + D
+    stride = (width + 7) // 8 * 8
+
+    def ifwd():
+        buf, out = _framed((B, stride), torch.bfloat16)
+        ops.dot_interaction_fwd(table=W, idx=idx, dense_vec=dv, tail=True, out=out, out_stride=stride, out_dtype=torch.bfloat16, ones_col=True)
+        torch.cuda.synchronize()
+        assert _intact(buf, out.numel() * 2)
+        return (out.clone(),)
+    (row,) = thrice(ifwd)
+    dout = (torch.randn(B, stride, device="cuda", generator=g) * 1e-2).to(torch.bfloat16)
+    thrice(lambda: ops.dot_interaction_bwd(dout, table=W, idx=idx, dense_vec=dv, tail=True))
+
+    # one-call sparse update (sort + segmented reduction + Adam) from identical state
+    dE = torch.randn(B, F, D, device="cuda", generator=g) * 1e-3
+
+    def update():
+        bw, Wc = _framed((V, D), torch.float32)
+        bm, m = _framed((V, D), torch.float32)
+        bv, v = _framed((V, D), torch.float32)
+        Wc.copy_(W)
+        m.zero_()
+        v.zero_()
+        ops.sparse_bwd_update(Wc, m, v, [LookupGroup(idx, F, GradSource.per_position(dE, F))], optimizer="adam_lazy", step=2)
+        torch.cuda.synchronize()
+        assert _intact(bw, V * D * 4) and _intact(bm, V * D * 4) and _intact(bv, V * D * 4)
+        return Wc.clone(), m.clone(), v.clone()
+    thrice(update)
+
+    # the three Dense products and the head, odd row counts
+    rows, in_dim, units = 333, 800, 520
+    x = (torch.randn(rows, in_dim, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(in_dim, units, device="cuda", generator=g) * in_dim ** -0.5).to(torch.bfloat16)
+    dy = (torch.randn(rows, units, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(units, device="cuda", generator=g)
+
+    def dfwd():
+        buf, y = _framed((rows, units), torch.bfloat16)
+        ops.dense_fwd(x, w, bias, None, out=y)
+        torch.cuda.synchronize()
+        assert _intact(buf, y.numel() * 2)
+        return (y.clone(),)
+    thrice(dfwd)
+
+    def dbwd_in():
+        buf, dx = _framed((rows, in_dim), torch.bfloat16)
+        ops.dense_bwd_input(dy, w, out=dx)
+        torch.cuda.synchronize()
+        assert _intact(buf, dx.numel() * 2)
+        return (dx.clone(),)
+    thrice(dbwd_in)
+
+    def dbwd_w():
+        buf, dw = _framed((in_dim, units), torch.float32)
+        ops.dense_bwd_weight(x, dy, out=dw)
+        torch.cuda.synchronize()
+        assert _intact(buf, dw.numel() * 4)
+        return (dw.clone(),)
+    thrice(dbwd_w)
+    wv = (torch.randn(in_dim, device="cuda", generator=g) * in_dim ** -0.5).to(torch.bfloat16)
+    out = ops.dense_head_fwd(x, wv, bias[:1], "sigmoid")
+    dout1 = torch.randn(rows, device="cuda", generator=g)
+    thrice(lambda: tuple(t for t in ops.dense_head_bwd(dout1, out, "sigmoid", x, wv, want_dx_colsum=True)))

@@ -325,3 +325,87 @@ def test_two_real_ranks_sharded_equals_unsharded(cuda_lib):
                        env=env, cwd=repo)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") >= 2
+
+
+# ---- BASELINE config 2 at full size AGAINST THE NUMPY ORACLE (not only properties) ----------------------------------------
+
+def _full_ids(dist, tables, rng):
+    """[B, 26] ids at config 2's size: uniform, or Zipf(1.05) folded mod V + 2 % forced id 0."""
+    if dist == "uniform":
+        ids = rng.integers(0, FULL_V, size=(FULL_B, 26), dtype=np.int64)
+    else:
+        ids = (rng.zipf(1.05, size=(FULL_B, 26)).astype(np.uint64) % np.uint64(FULL_V)).astype(np.int64)
+        ids[rng.random((FULL_B, 26)) < 0.02] = 0
+    return ids
+
+
+@pytest.mark.parametrize("dist", ["uniform", "zipf"])
+@pytest.mark.parametrize("tables", [26, 1])
+def test_full_size_interaction_and_sparse_update_against_the_oracle(cuda_lib, dist, tables):
+    """B = 65536, D = 64, 1M-row tables, T = 26 and T = 1, uniform and Zipf + 2 % id 0 ids.
+    (a) the fused lookup + interaction row of ALL 65536 samples against oracle.dot_interaction in its bf16-operand mode
+        (same arithmetic: 1e-5 of the largest entry; the bf16 output row: one bf16 rounding);
+    (b) the deterministic backward — sort, duplicate-row sum in input order, fused lazy Adam — on >= 10 000 sampled
+        touched rows (the hottest rows included) against oracle.dedup_indexed_slices + oracle.adam_lazy run on exactly
+        the lookups that hit those rows: rows hit once bit-exact, summed rows to fp32 re-association."""
+    from recommender_b200 import ops
+    from recommender_b200.ops import GradSource, LookupGroup
+    rng = np.random.default_rng(7 + tables + (dist == "zipf"))
+    T, V, D, B, F = tables, FULL_V, FULL_D, FULL_B, 26
+    torch.manual_seed(11)
+    W = torch.empty(V * T, D, device="cuda").uniform_(-0.05, 0.05)
+    ids = _full_ids(dist, T, rng)
+    idx = cu(ids)
+    off = torch.arange(T, device="cuda", dtype=torch.int64) * V if T > 1 else None
+    rows = ids + (np.arange(T, dtype=np.int64) * V)[None] if T > 1 else ids
+    dv = torch.randn(B, D, device="cuda") * 0.1
+    # ---- (a) interaction, all samples
+    out = ops.dot_interaction_fwd(table=W, idx=idx, field_row_offset=off, dense_vec=dv, tail=True)
+    Wn, dvn = W.cpu().numpy(), dv.cpu().numpy()
+    worst = 0.0
+    for lo in range(0, B, 8192):                                   # the oracle in slabs: 8192 x 27 x 64 floats at a time
+        hi = lo + 8192
+        X = np.concatenate([Wn[rows[lo:hi]], dvn[lo:hi, None, :]], axis=1)
+        ref = np.concatenate([O.dot_interaction(X, False, True, operand_dtype="bf16"), dvn[lo:hi]], axis=1)
+        got = out[lo:hi].cpu().numpy()
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+    assert worst <= 1e-5, worst
+    out16 = ops.dot_interaction_fwd(table=W, idx=idx, field_row_offset=off, dense_vec=dv, tail=True, out_dtype=torch.bfloat16, pad_to=8,
+                                    ones_col=True)
+    assert (out16[:, 793] == 1).all() and (out16[:, 794:] == 0).all()
+    assert (out16[:, :793].float() - out).abs().max().item() <= 2.0 ** -8 * out.abs().max().item()
+    # ---- (b) backward scatter + lazy Adam on sampled touched rows
+    dE = torch.randn(B, F, D, device="cuda") * 1e-3
+    m, v = torch.zeros_like(W), torch.zeros_like(W)
+    W0 = Wn                                                         # the table before the update (host copy)
+    ops.sparse_bwd_update(W, m, v, [LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=off)], optimizer="adam_lazy", step=3)
+    flat = rows.reshape(-1)
+    uniq, counts = np.unique(flat, return_counts=True)
+    hot = uniq[np.argsort(-counts)[:64]]                            # the longest chains (id 0 / the Zipf head)
+    sample = np.unique(np.concatenate([hot, rng.choice(uniq, size=min(10_000, uniq.size), replace=False)]))
+    assert sample.size >= min(10_000, uniq.size)
+    sel = np.isin(flat, sample)
+    pos = np.nonzero(sel)[0]                                        # ascending = input order
+    dEn = dE.reshape(-1, D).cpu().numpy()
+    r_rows, r_g = O.dedup_indexed_slices(flat[pos], dEn[pos])
+    ref_W, ref_m, ref_v = W0.copy(), np.zeros_like(W0), np.zeros_like(W0)
+    O.adam_lazy(ref_W, ref_m, ref_v, r_rows, r_g, 3)
+    got_W, got_m, got_v = W[sample].cpu().numpy(), m[sample].cpu().numpy(), v[sample].cpu().numpy()
+    cnt = counts[np.searchsorted(uniq, sample)]
+    once = cnt == 1
+    if once.any():                                                  # no summation involved: bit-exact
+        np.testing.assert_array_equal(got_m[once], ref_m[sample][once])
+        np.testing.assert_array_equal(got_v[once], ref_v[sample][once])
+        np.testing.assert_array_equal(got_W[once], ref_W[sample][once])
+    # fp32 re-association of the duplicate sums: a hot row adds ~2000 gradients of magnitude 1e-3 whose sum nearly cancels,
+    # so the error scales with sum |g| (~2) x 2^-24 x (1 - beta_1), not with the result
+    # (one shared table under Zipf ids: the hottest row sums ~170 000 gradients, relative error of the sum ~1e-4)
+    np.testing.assert_allclose(got_m, ref_m[sample], rtol=5e-4, atol=5e-8)
+    np.testing.assert_allclose(got_v, ref_v[sample], rtol=1e-3, atol=1e-12)
+    # Adam's update is ~ alpha * m / sqrt(v): compare where the row moved at all, at a tolerance far below one lr step
+    np.testing.assert_allclose(got_W, ref_W[sample], rtol=0, atol=2e-5)
+    # rows outside the batch did not move
+    probe = rng.integers(0, V * T, size=4096)
+    probe = probe[~np.isin(probe, uniq)]
+    assert torch.equal(W[probe].cpu(), torch.tensor(W0[probe]))
+    ops.check_oob("cuda")
