@@ -111,6 +111,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp.  The producer and the MMA issuer run their loops with all 32 lanes and predicate only the
+// TMA / tcgen05 instructions on the elected lane: operands that are warp-uniform then live in uniform registers.  (Under
+// `if (lane == 0)` the compiler wraps every UTCHMMA / UTMALDG in an ELECT retry loop fed by R2UR moves — ~130 cycles per
+// issue, SASS of r2_18 — which made a 128-cycle MMA issue-bound.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(saddr(dst)),
                "l"(map), "r"(saddr(bar)), "r"(c0), "r"(c1)
@@ -349,8 +365,9 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
   const int total = g.m_blocks * g.n_blocks * g.splits;
 
   if (warp == 0) {
-    // ===== TMA producer ========================================================================================
-    if (lane == 0) {
+    // ===== TMA producer (converged warp, one elected lane issues) ================================================
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       long long t_empty = 0;
@@ -361,14 +378,17 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
         // k-block after k-block, in the layout a stage would have
         const int n0 = (tile_id0 % g.n_blocks) * g.block_n;
         const uint32_t tile_bytes = static_cast<uint32_t>(g.block_n) * 128u;
-        mbar_expect_tx(b_full, tile_bytes * static_cast<uint32_t>(g.k_blocks));
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
-          uint8_t* dst = smem_b + static_cast<size_t>(kb) * tile_bytes;
-          if (!g.b_mn) tma_load_2d(dst, &map_b, b_full, kb * kBlockK, n0);
-          else if (g.b_atoms) tma_load_3d(dst, &map_b, b_full, 0, kb * kBlockK, n0 / 64);
-          else
-            for (int j = 0; j < g.block_n / 64; ++j) tma_load_2d(dst + j * kAtomBytes, &map_b, b_full, n0 + 64 * j, kb * kBlockK);
+        if (leader) {
+          mbar_expect_tx(b_full, tile_bytes * static_cast<uint32_t>(g.k_blocks));
+          for (int kb = 0; kb < g.k_blocks; ++kb) {
+            uint8_t* dst = smem_b + static_cast<size_t>(kb) * tile_bytes;
+            if (!g.b_mn) tma_load_2d(dst, &map_b, b_full, kb * kBlockK, n0);
+            else if (g.b_atoms) tma_load_3d(dst, &map_b, b_full, 0, kb * kBlockK, n0 / 64);
+            else
+              for (int j = 0; j < g.block_n / 64; ++j) tma_load_2d(dst + j * kAtomBytes, &map_b, b_full, n0 + 64 * j, kb * kBlockK);
+          }
         }
+        __syncwarp();
       }
       for (int w = tile_id0; w < total; w += tile_stride) {
         const int n_blk = w % g.n_blocks, m_blk = (w / g.n_blocks) % g.m_blocks, split = w / (g.n_blocks * g.m_blocks);
@@ -389,6 +409,7 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
           const int k0 = kb * kBlockK;
           uint8_t* a_dst = smem_a + stage * kAStageBytes;
           uint8_t* b_dst = smem_b + stage * kBBytes;
+          if (leader) {
           if constexpr (CG == 2) {
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * my_bytes);      // both CTAs stage the same number of bytes
             if (!g.a_mn) {
@@ -426,14 +447,17 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
               for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * kAtomBytes, &map_b, &full[stage], nb0 + 64 * j, k0);
             }
           }
+          }
+          __syncwarp();
           if (++stage == kNumStages) {
             stage = 0;
             phase ^= 1;
           }
-          *produced = ++issued;
+          ++issued;
+          if (leader) *produced = issued;
         }
       }
-      if (g.stats != nullptr) {
+      if (g.stats != nullptr && leader) {
         g.stats[blockIdx.x * 8 + 3] = t_empty;
         g.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
@@ -471,8 +495,9 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (the pair's leader only) =====================================================================
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (the pair's leader CTA only; converged warp, one elected lane issues) ==========================
+    if (rank == 0) {
+      const bool leader = elect_one();
       // instruction descriptor: D fp32, A/B bf16, majors, N >> 3, M >> 4
       const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.a_mn) << 15) |
                               (static_cast<uint32_t>(g.b_mn) << 16) | (static_cast<uint32_t>((kBlockM * CG) >> 4) << 24);
@@ -511,32 +536,38 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
           const uint64_t ad = a_desc0 + static_cast<uint64_t>(stage * (kAStageBytes >> 4));
           const uint64_t bd = b_desc0 + static_cast<uint64_t>(g.b_resident ? (kb - kb0) * b_tile16 : stage * (kBBytes >> 4));
           const int k_valid = g.K - kb * kBlockK;
-          if (k_valid >= kBlockK) {
+          if (leader) {
+            if (k_valid >= kBlockK) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+            } else {                                              // the ragged end of the reduction axis
+              const int k_steps = (k_valid + 15) / 16;
+              for (int k = 0; k < k_steps; ++k) {
+                if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
             }
-          } else {                                              // the ragged end of the reduction axis
-            const int k_steps = (k_valid + 15) / 16;
-            for (int k = 0; k < k_steps; ++k) {
-              if constexpr (CG == 2) umma_bf16_pair(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            // the stage is free (in both CTAs) once these MMAs have read it
+            if constexpr (CG == 2) umma_commit_pair(&empty[stage]);
+            else umma_commit(&empty[stage]);
           }
-          // the stage is free (in both CTAs) once these MMAs have read it
-          if constexpr (CG == 2) umma_commit_pair(&empty[stage]);
-          else umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == kNumStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // the accumulator (each CTA's 128 rows of it) is complete
-        if constexpr (CG == 2) umma_commit_pair(&acc_full[acc]);
-        else umma_commit(&acc_full[acc]);
+        if (leader) {
+          if constexpr (CG == 2) umma_commit_pair(&acc_full[acc]);
+          else umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
       }
-      if (g.stats != nullptr) {
+      if (g.stats != nullptr && leader) {
         g.stats[blockIdx.x * 8 + 0] = t_full;
         g.stats[blockIdx.x * 8 + 1] = t_acc;
         g.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;

@@ -818,6 +818,15 @@ static bool bulk_enabled() {
   return on;
 }
 
+// RB_SEG_PAD_KB=n adds n KiB to the bulk kernel's dynamic shared memory (occupancy experiments: fewer resident CTAs per SM)
+static size_t bulk_pad_bytes() {
+  static const size_t pad = [] {
+    const char* e = getenv("RB_SEG_PAD_KB");
+    return e == nullptr ? size_t(0) : static_cast<size_t>(atoi(e)) * 1024;
+  }();
+  return pad;
+}
+
 // gradient rows in PEER memory (sharded path): opt-in until measured over NVLink
 static bool bulk_peer_enabled() {
   static const bool on = [] {
@@ -852,7 +861,7 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
     constexpr int kGroups = kSegThreads / G;                                                                            \
     const size_t ring_bytes = static_cast<size_t>(kRing) * (1 + Sink::kStateRows) * kSegThreads * V * sizeof(float);   \
     if (bulk) {                                                                                                         \
-      const size_t bulk_bytes = static_cast<size_t>(kGroups) * kBulkRing * 4 * gsrc.D * sizeof(float);                  \
+      const size_t bulk_bytes = static_cast<size_t>(kGroups) * kBulkRing * 4 * gsrc.D * sizeof(float) + bulk_pad_bytes(); \
       if constexpr (std::is_same<Sink, OptSink>::value) {                                                               \
         RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                      static_cast<int>(bulk_bytes)));                                                    \

@@ -11,6 +11,7 @@ path — the graph changes who launches them, not what runs.
 from __future__ import annotations
 
 import gc
+import os
 from typing import Callable, Sequence
 
 import torch
@@ -48,7 +49,12 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self.optimizer.prepare_step()                       # host half of the captured step
-        with torch.cuda.graph(self.graph):
+        # Stream priorities are recorded into the captured kernel nodes.  The step's critical chain runs at the highest one,
+        # the weight-gradient stream below it (layers.MLP), the sort + row-update stream at the default: when the HBM-bound
+        # row update and the towers' backward are runnable together, the Dense CTAs are placed first and the update fills the
+        # SMs around them (timeline r2_19: the bottom tower's backward moved from behind the update to beside it)
+        capture_stream = torch.cuda.Stream(device=sample_batch[0].device, priority=int(os.environ.get("RB_PRIO_MAIN", "-2")))
+        with torch.cuda.graph(self.graph, stream=capture_stream):
             self.loss = self._body()
         self.steps_run = max(1, warmup) + 1                 # capture itself does not execute: counted when replayed below
         self.graph.replay()

@@ -24,6 +24,13 @@ from . import ops
 from .ops import GradSource, LookupGroup
 
 
+def _stream_priority(env: str, default: int = 0) -> int:
+    """CUDA stream priority of a helper stream (0 = default, negative = higher), overridable for scheduling experiments."""
+    import os
+    v = os.environ.get(env)
+    return default if v is None else int(v)
+
+
 def _default_device(device=None) -> torch.device:
     if device is not None:
         return torch.device(device)
@@ -151,6 +158,8 @@ class _InteractFn(torch.autograd.Function):
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
         emb._grad_ready = torch.cuda.current_stream().record_event()    # dE is complete here: the row update may start
+        for hook in emb.after_grad_hooks:
+            hook(emb._grad_ready)
         return None, None, None, d_dense, None, None, None, None, None, None
 
 
@@ -218,6 +227,8 @@ class Embedding(nn.Module):
         # The (row, position) sort of the backward depends on the ids only: it is started on a side stream
         # when the lookup runs and overlaps the forward / MLPs (rb_sparse_bwd_prepare / _apply).
         self.presort = True
+        import os
+        self.presort_at = os.environ.get("RB_PRESORT_AT", "start")      # "start": DLRM starts the sort before its bottom MLP
         # How the fused lookups copy table rows (rb_row_cache): "auto" lets the device decide per step from the hot-row census
         # the pre-sort takes of the ids (rows with >= 64 lookups holding more than a quarter of them: through L1)
         self.row_cache = "auto"
@@ -229,6 +240,7 @@ class Embedding(nn.Module):
         # interaction backward has written dE, so it overlaps the rest of the backward (bottom MLP) and the dense
         # optimizer step; join() brings the streams back together.
         self._grad_ready: Optional[torch.cuda.Event] = None
+        self.after_grad_hooks: list = []      # called with the event above once the fused lookup's backward is queued
         self._apply_done: Optional[torch.cuda.Event] = None
         self._inflight = None
 
@@ -267,7 +279,7 @@ class Embedding(nn.Module):
         if self._sort_ws is None or self._sort_ws.numel() < need:
             self._sort_ws = ops.sparse_workspace(n, D, rows, self.embeddings.device)
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=self.embeddings.device)
+            self._side_stream = torch.cuda.Stream(device=self.embeddings.device, priority=_stream_priority("RB_PRIO_SIDE"))
         main, side = torch.cuda.current_stream(), self._side_stream
         side.wait_stream(main)            # ids are ready; the previous step's apply has released the workspace
         with torch.cuda.stream(side):
@@ -277,6 +289,20 @@ class Embedding(nn.Module):
         if not torch.cuda.is_current_stream_capturing():
             idx.record_stream(side)
         self._sorted = (idx, L, sel, done)
+
+    def start_presort(self, idx: torch.Tensor) -> torch.Tensor:
+        if self.presort_at == "after_lookup":
+            return idx.contiguous()
+        return self._start_presort(idx)
+
+    def _start_presort(self, idx: torch.Tensor) -> torch.Tensor:
+        """Start the backward's (row, position) sort for `idx` NOW on the side stream — a model calls this before work that
+        does not depend on the ids (DLRM's bottom MLP) so that the sort runs under it instead of beside the lookup.  Returns
+        the (contiguous) index tensor the later lookup must be given."""
+        idx = idx.contiguous()
+        L = idx.shape[-1] if idx.dim() >= 1 else 1
+        self._presort(idx, L, self.row_offset_for(L))
+        return idx
 
     # -- the Keras call surface
     def forward(self, idx: torch.Tensor) -> torch.Tensor:
@@ -315,9 +341,14 @@ class Embedding(nn.Module):
         emits the row in bf16, zero-padded to a multiple of `pad_to` columns (the K operand of a
         bf16 top MLP); its gradient then comes back in the same padded bf16 form."""
         idx = idx.contiguous()
-        self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
-        return _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to,
-                                 ones_col)
+        late = self.presort_at == "after_lookup"
+        if not late:
+            self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
+        out = _InteractFn.apply(self._anchor, self, idx, dense_vec.float(), self_interaction, skip_gather, tail, out_dtype, pad_to,
+                                ones_col)
+        if late:        # the sort's HBM passes start once the lookup kernel is queued ahead of them
+            self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
+        return out
 
     def join(self) -> None:
         """Wait (on the current stream) for a row update launched on the side stream."""
@@ -497,9 +528,9 @@ class _DenseStackFn(torch.autograd.Function):
             dW_full = torch.empty(x_i.shape[1], W.shape[1], dtype=torch.float32, device=x_i.device)
             need_db = not (i == 0 and ctx.ones_col) and have_db is None
             db = torch.empty(W.shape[1], dtype=torch.float32, device=x_i.device) if need_db else have_db
-            wg.wait_event(main.record_event())
             mlp._wgrad_keep.extend((x_i, dy_i, dW_full, db))
-            with torch.cuda.stream(wg):
+
+            def launch():
                 ops.dense_bwd_weight(x_i, dy_i, out=dW_full, ws=ws)
                 if need_db:
                     ops.colsum(dy_i, out=db, ws=ws)
@@ -509,6 +540,13 @@ class _DenseStackFn(torch.autograd.Function):
                 else:
                     assign(W, dW_full)
                     assign(b, db)
+
+            if mlp.defer_wgrad:
+                mlp._wgrad_deferred.append(launch)      # launched by flush_wgrad(): after the caller's critical kernels are queued
+                return
+            wg.wait_event(main.record_event())
+            with torch.cuda.stream(wg):
+                launch()
 
         h, Wp = acts[n - 1], shadows[n - 1]
         want_dx = n > 1 or ctx.need_dx
@@ -622,6 +660,8 @@ class MLP(nn.Module):
         self._wgrad_done: Optional[torch.cuda.Event] = None
         self._wgrad_keep: list = []
         self._wgrad_join_queued = False
+        self.defer_wgrad = False                          # hold the weight-gradient products back until flush_wgrad()
+        self._wgrad_deferred: list = []
         if final_activation not in (None, "relu", "sigmoid"):
             raise ValueError(final_activation)
         if compute_dtype not in (None, torch.float32, torch.bfloat16):
@@ -653,7 +693,7 @@ class MLP(nn.Module):
     def _wgrad_begin(self, acts, shadows):
         dev = acts[0].device
         if self._wgrad_stream is None:
-            self._wgrad_stream = torch.cuda.Stream(device=dev)
+            self._wgrad_stream = torch.cuda.Stream(device=dev, priority=_stream_priority("RB_PRIO_WGRAD", -1))
         rows = acts[0].shape[0]
         need = 256
         for a, w in zip(acts, shadows):
@@ -671,9 +711,25 @@ class MLP(nn.Module):
             self._wgrad_join_queued = True
             torch.autograd.Variable._execution_engine.queue_callback(self._join_wgrad)
 
+    def flush_wgrad(self, after: Optional[torch.cuda.Event] = None) -> None:
+        """Launch the weight-gradient products held back by `defer_wgrad` on the wgrad stream, ordered after `after` (default:
+        everything queued on the current stream so far).  DLRM defers the top tower's products until the interaction backward
+        is queued: the persistent Dense CTAs would otherwise occupy the SMs just when that kernel becomes ready (r2_19
+        timeline: an 18 us hole in front of it), and under the HBM-bound row update they cost next to nothing."""
+        if not self._wgrad_deferred:
+            return
+        todo, self._wgrad_deferred = self._wgrad_deferred, []
+        wg = self._wgrad_stream
+        wg.wait_event(after if after is not None else torch.cuda.current_stream().record_event())
+        with torch.cuda.stream(wg):
+            for launch in todo:
+                launch()
+        self._wgrad_done = wg.record_event()
+
     def _join_wgrad(self) -> None:
         """The caller's stream waits for the weight gradients; operands the wgrad stream was reading may be freed after that."""
         self._wgrad_join_queued = False
+        self.flush_wgrad()
         if self._wgrad_done is not None:
             torch.cuda.current_stream().wait_event(self._wgrad_done)
             self._wgrad_done = None

@@ -77,11 +77,18 @@ class DLRM(nn.Module):
                            collapse_linear=collapse_linear)                                                    # :39
         self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :42
         self.interaction = DotInteraction(False, True)                                                          # :43
+        if fused:
+            # the top tower's weight gradients wait until the interaction backward is queued (MLP.flush_wgrad)
+            self.top_mlp.defer_wgrad = True
+            self.embedding_layer.after_grad_hooks.append(self.top_mlp.flush_wgrad)
         self.num_cat_fea, self.num_int_fea, self.embedding_size, self.fused = num_cat_fea, num_int_fea, embedding_size, fused
 
     def forward(self, inputs, training=None, mask=None):
         int_features = inputs["int_features"].reshape(-1, self.num_int_fea)            # :47
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :48
+        if self.fused and torch.is_grad_enabled():
+            # the backward's sort of (row, position) pairs depends on the ids only: start it under the bottom MLP
+            cat_features = self.embedding_layer.start_presort(cat_features)
         bmlp_output = self.bottom_mlp(int_features)                                     # :50
         if self.fused:
             width = (self.num_cat_fea + 1) ** 2 + self.embedding_size                                     # :55

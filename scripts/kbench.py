@@ -122,6 +122,23 @@ def main():
             grp = LookupGroup(ring[i % 4], F, GradSource.per_position(dE, F), field_row_offset=off)
             ops.sparse_bwd_update(table, m, v if a.optimizer.startswith("adam") else None, [grp], optimizer=a.optimizer, step=step[0])
         timeit("update", upd)
+    if "apply" in which:     # the segmented reduction + row update alone (keys + sort outside the timed region, as in the step)
+        ws = ops.sparse_workspace(B * F, D, V * T, dev)
+        step = [0]
+        evs = []
+        for i in range(a.iters + 3):
+            step[0] += 1
+            grp = LookupGroup(ring[i % 4], F, GradSource.per_position(dE, F), field_row_offset=off)
+            sel = ops.sparse_bwd_prepare(V * T, D, [grp], ws)
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            ops.sparse_bwd_apply(table, m, v, [grp], ws, sel, optimizer=a.optimizer, step=step[0])
+            e_.record()
+            if i >= 3:
+                evs.append((s_, e_))
+        torch.cuda.synchronize()
+        ts = sorted(s_.elapsed_time(e_) * 1e3 for s_, e_ in evs)
+        res["apply"] = dict(us_median=ts[len(ts) // 2], us_min=ts[0], us_mean=sum(ts) / len(ts))
     for v_ in res.values():
         if "algorithmic_bytes" in v_:
             v_["gbs"] = round(v_["algorithmic_bytes"] / v_["us_median"] / 1e3, 1)
