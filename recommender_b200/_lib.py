@@ -83,6 +83,11 @@ SIGNATURES = {
     "rb_sparse_bwd_prepare": (C.c_int, [_i64, _i32, C.POINTER(RbLookupGroup), _i32, _p, C.c_size_t, _p, C.POINTER(C.c_int32), _p, _p]),
     "rb_sparse_bwd_apply": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32, C.POINTER(RbOptParams), _p,
                                       C.c_size_t, _i32, _p]),
+    "rb_sparse_bwd_apply_ex": (C.c_int, [_p, _p, _p, _i64, _i32, C.POINTER(RbLookupGroup), _i32, C.POINTER(RbOptParams), _p,
+                                         C.c_size_t, _i32, _i32, _p]),
+    "rb_sparse_bwd_mark_singletons": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p, _p]),
+    "rb_dot_interaction_bwd_update": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p, _p,
+                                                _p, _p, _p, C.POINTER(RbOptParams), _i32, _p, _p]),
     "rb_sparse_bwd_dedup": (C.c_int, [_i64, _i32, _p, _i32, _i64, _i32, _p, _i64, C.POINTER(RbGradSource),
                                       _p, _p, _p, _p, C.c_size_t, _p, _p]),
     "rb_dense_opt_step": (C.c_int, [C.POINTER(RbDenseSlot), _i32, C.POINTER(RbOptParams), _p]),

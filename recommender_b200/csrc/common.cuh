@@ -157,6 +157,41 @@ __device__ __forceinline__ Row<VEC> zero_row() {
   return r;
 }
 
+// ---- the optimizers' row arithmetic, every op explicitly rounded (no FMA contraction) so that
+// every kernel that updates a row — the segmented reduction's sink and the interaction backward's fused update of rows a
+// step touches once — produces the same bits as the numpy oracle
+struct OptMath {
+  int opt;  // rb_optimizer
+  float lr, b1, b2, omb1, omb2, eps, alpha;
+};
+
+template <int VEC>
+__device__ __forceinline__ void opt_row_math(const OptMath& p, const Row<VEC>& g, Row<VEC>& w, Row<VEC>& m, Row<VEC>& v) {
+  if (p.opt == RB_OPT_ADAM_LAZY) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      m.v[i] = __fadd_rn(__fmul_rn(m.v[i], p.b1), __fmul_rn(g.v[i], p.omb1));
+      v.v[i] = __fadd_rn(__fmul_rn(v.v[i], p.b2), __fmul_rn(__fmul_rn(g.v[i], g.v[i]), p.omb2));
+      w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(p.alpha, m.v[i]), __fadd_rn(__fsqrt_rn(v.v[i]), p.eps)));
+    }
+  } else if (p.opt == RB_OPT_ADAM_TF_DENSE) {   // scatter-add phase only: the decay / apply passes cover every row
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], p.omb1));
+      v.v[i] = __fadd_rn(v.v[i], __fmul_rn(__fmul_rn(g.v[i], g.v[i]), p.omb2));
+    }
+  } else if (p.opt == RB_OPT_ADAGRAD) {         // accumulator in m
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], g.v[i]));
+      w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(p.lr, g.v[i]), __fadd_rn(__fsqrt_rn(m.v[i]), p.eps)));
+    }
+  } else {                                      // SGD
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) w.v[i] = __fsub_rn(w.v[i], __fmul_rn(p.lr, g.v[i]));
+  }
+}
+
 // ---- cp.async (LDGSTS): global -> shared copies that hold no registers while in flight ----------------
 __device__ __forceinline__ uint32_t smem_u32addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 

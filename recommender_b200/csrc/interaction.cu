@@ -75,6 +75,17 @@ struct IxArgs {
   const int32_t* row_cache_hint;   // RB_ROW_CACHE_AUTO: device flag written by rb_sparse_bwd_prepare of this / the previous step
 };
 
+// Fused optimizer update of the rows a step touches once (rb_dot_interaction_bwd_update): the backward kernel applies the
+// optimizer to such a row where its gradient row is produced instead of writing the gradient to dE.
+struct IxUpdate {
+  const uint8_t* single;   // [B*F]: 1 = the row of this lookup position occurs once among the step's lookups
+  float* table;            // the table, writable
+  float* s0;               // optimizer state rows (Adam m / Adagrad accumulator) or null
+  float* s1;               // Adam v or null
+  OptMath math;
+  const float* alpha_dev;  // optional device alpha_t (graph replays)
+};
+
 // Hot rows.  Under Zipf ids on ONE shared table (the reference's layout, ctr/model.py:42) a tenth of all lookups read the
 // same row: through L2 only (cp.async.cg) every SM queues on the one L2 slice that holds the line and the forward runs 3.3x
 // slower than with uniform ids (r2_00: 376 us against 132 us); through L1 (cp.async.ca) each SM keeps the handful of hot
@@ -537,11 +548,19 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
 // dX = (G + G^T) X.  smem per warp: kIxStages x { xs[32][D+4] fp32 | 16 B of zeros | staged dOut row }.
 // SRC: where X comes from — 0: rows gathered from E / the local table, 1: rows gathered from the shards in peer
 // memory, 2: the bf16 operand rows the forward saved (x_load)
-template <int D, typename DOUT, bool SELF, int SRC>
-__global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
+// UPD (SRC == 0 only): rows flagged in u.single get their optimizer update here.  Per warp, next to the ring: the m / v rows of
+// the CURRENT sample's flagged rows (cp.async, issued while the sample's X rows are still landing) and, per stage, the row ids
+// and flags of the sample staged there.  The epilogue updates W (the fp32 row already in the stage), m and v in place in
+// shared memory, column block by column block — columns of X are dead as MMA operands once their block is done — and the
+// finished rows go back to the table / state with full-row 16-byte stores.
+constexpr int kIxUpdWarps = 8;     // the fused-update form: more shared memory and more registers per warp
+template <int D, typename DOUT, bool SELF, int SRC, bool UPD = false>
+__global__ void __launch_bounds__(UPD ? kIxUpdWarps * 32 : IxWarps<D>::value * 32, 1)
 dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
-                           float* __restrict__ d_dense, int copy_width, int gs_bytes) {
+                           float* __restrict__ d_dense, int copy_width, int gs_bytes, IxUpdate u = IxUpdate{}) {
+  static_assert(!UPD || SRC == 0, "the fused row update reads fp32 rows of the local table");
   constexpr int STRIDE = D + 4;  // floats; 2*(D+4) % 32 == 8 -> conflict-free 32-bit B-fragment loads
+  constexpr int MS = D + 8;      // floats per staged m / v row: conflict-free 64-bit accesses of the epilogue
   constexpr int kXsFloats = 32 * STRIDE;
   const int kIxWarps = blockDim.x / 32;
   constexpr int kLanesPerRow = D / 4;
@@ -555,7 +574,15 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   }
   const float* const* shard_base = SRC == 1 ? s_shards : nullptr;
   const int stage_bytes = kXsFloats * 4 + gs_bytes;
-  unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * stage_bytes);
+  const int upd_bytes = UPD ? (2 * a.F * MS * 4 + kIxStages * 256) : 0;
+  unsigned char* my = smem + static_cast<size_t>(warp) * (kIxStages * stage_bytes + upd_bytes);
+  float* mvm = reinterpret_cast<float*>(my + kIxStages * stage_bytes);            // [F][MS] state0 rows of the current sample
+  float* mvv = mvm + a.F * MS;                                                     // [F][MS] state1 rows
+  uint32_t* st_rows = reinterpret_cast<uint32_t*>(mvv + a.F * MS);                 // [kIxStages][32] row ids of the staged sample
+  uint32_t* st_single = st_rows + kIxStages * 32;                                  // [kIxStages][32] its flags
+  if constexpr (UPD) {
+    if (u.alpha_dev != nullptr) u.math.alpha = __ldg(u.alpha_dev);
+  }
 
   for (int i = lane; i < kIxStages * stage_bytes / 16; i += 32) reinterpret_cast<float4*>(my)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
@@ -612,9 +639,18 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   constexpr int S16 = D + 8;   // bf16 elements per row of the staged X when it comes from x_load
   constexpr bool xl = (SRC == 2);
   const bool l1 = rows_through_l1(a);
+  uint32_t single_next = 0;
+  auto load_single = [&](int64_t bb) -> uint32_t {
+    if constexpr (UPD) return (lane < F && bb < a.B) ? static_cast<uint32_t>(__ldg(u.single + bb * F + lane)) : 0u;
+    return 0u;
+  };
   auto issue = [&](int64_t bb, uint32_t row, int st) {
     unsigned char* sp = my + st * stage_bytes;
     float* xn = reinterpret_cast<float*>(sp);
+    if constexpr (UPD) {
+      st_rows[st * 32 + lane] = row;
+      st_single[st * 32 + lane] = (row != kInvalidRow) ? single_next : 0u;
+    }
     if (xl) {
       constexpr int kChunksPerRow = D / 8;
       const __nv_bfloat16* xrow = a.x_load + bb * a.Fp * D;
@@ -631,12 +667,14 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
   };
 
   uint32_t row_next = xl ? kInvalidRow : load_sample_row(a, b, lane, lane_off);
+  single_next = load_single(b);
 #pragma unroll
   for (int s0 = 0; s0 < kIxStages - 1; ++s0) {
     const int64_t bs = b + s0 * nwarps;
     if (bs < a.B) issue(bs, row_next, s0);
     cp_async_commit();
     if (!xl) row_next = load_sample_row(a, bs + nwarps, lane, lane_off);
+    single_next = load_single(bs + nwarps);
   }
   int stage = 0;
 
@@ -644,14 +682,36 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
     const int64_t bn = b + (kIxStages - 1) * nwarps;
     unsigned char* sp = my + stage * stage_bytes;
     const float* xs = reinterpret_cast<const float*>(sp);
+    uint32_t rowc = kInvalidRow, smask = 0;
+    if constexpr (UPD) {
+      // this sample's rows and flags (stored when its stage was issued); the state rows of its flagged rows start
+      // moving now, ahead of the stage issued below
+      __syncwarp();
+      rowc = st_rows[stage * 32 + lane];
+      smask = __ballot_sync(0xffffffffu, st_single[stage * 32 + lane] != 0);
+      constexpr int kRowsPerIter = 32 / kLanesPerRow;
+      const int colq = (lane % kLanesPerRow) * 4;
+#pragma unroll 4
+      for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
+        const int r = r0 + sub;
+        const uint32_t row = __shfl_sync(0xffffffffu, rowc, r);
+        if (r < F && ((smask >> r) & 1u)) {
+          const size_t o = static_cast<size_t>(row) * D + colq;
+          if (u.s0 != nullptr) cp_async16(mvm + r * MS + colq, u.s0 + o, 16);
+          if (u.s1 != nullptr) cp_async16(mvv + r * MS + colq, u.s1 + o, 16);
+        }
+      }
+      cp_async_commit();
+    }
     if (bn < a.B) {
       int sa = stage + kIxStages - 1;
       if (sa >= kIxStages) sa -= kIxStages;
       issue(bn, row_next, sa);
       if (!xl) row_next = load_sample_row(a, bn + nwarps, lane, lane_off);
+      single_next = load_single(bn + nwarps);
     }
     cp_async_commit();
-    cp_async_wait<kIxStages - 1>();
+    cp_async_wait<UPD ? kIxStages : kIxStages - 1>();     // UPD: the state-row group and the next stage may still be in flight
     __syncwarp();
 
     // staged row element e lives at gs[e]
@@ -671,6 +731,11 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
     }
 
     float* de_lane = dE != nullptr ? dE + (b * F + g) * D + t2 : nullptr;
+    if constexpr (UPD) {
+      cp_async_wait<1>();       // the state rows have landed (the next stage may still be in flight)
+      __syncwarp();
+    }
+    float* xw = reinterpret_cast<float*>(sp);
 #pragma unroll 4
     for (int nt = 0; nt < D / 8; ++nt) {
       float acc[2][4];
@@ -693,12 +758,49 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(acc[mt], af[mt][ks], b0, b1);
       }
+      if constexpr (UPD) {
+        // The four rows this lane holds two columns of, all at once and branch-free: eight independent chains of the
+        // optimizer arithmetic (its IEEE divisions and square roots are long dependent sequences) instead of four
+        // divergent branches of two.  Rows that are not flagged compute on whatever the buffers hold and store nothing here.
+        Row<8> gr, wr, mr, vr;
+        float2* wp[4];
+        float2* mp[4];
+        float2* vp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = (q >> 1) * 16 + g + (q & 1) * 8;
+          const int ic = i < F ? i : F - 1;                       // the m / v buffers hold F rows
+          wp[q] = reinterpret_cast<float2*>(xw + i * STRIDE + nt * 8 + t2);
+          mp[q] = reinterpret_cast<float2*>(mvm + ic * MS + nt * 8 + t2);
+          vp[q] = reinterpret_cast<float2*>(mvv + ic * MS + nt * 8 + t2);
+          const float2 w2 = *wp[q], m2 = *mp[q], v2 = *vp[q];
+          // the row's only gradient this step: its summed gradient is 0 + g, exactly as the segmented reduction forms it
+          gr.v[2 * q] = __fadd_rn(0.f, acc[q >> 1][(q & 1) * 2]);
+          gr.v[2 * q + 1] = __fadd_rn(0.f, acc[q >> 1][(q & 1) * 2 + 1]);
+          wr.v[2 * q] = w2.x; wr.v[2 * q + 1] = w2.y;
+          mr.v[2 * q] = m2.x; mr.v[2 * q + 1] = m2.y;
+          vr.v[2 * q] = v2.x; vr.v[2 * q + 1] = v2.y;
+        }
+        opt_row_math<8>(u.math, gr, wr, mr, vr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int mt = q >> 1, h = q & 1;
+          const int i = mt * 16 + g + h * 8;
+          if (is_emb[mt][h] && ((smask >> i) & 1u)) {
+            *wp[q] = make_float2(wr.v[2 * q], wr.v[2 * q + 1]);
+            *mp[q] = make_float2(mr.v[2 * q], mr.v[2 * q + 1]);
+            *vp[q] = make_float2(vr.v[2 * q], vr.v[2 * q + 1]);
+          }
+        }
+      }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float2 v = make_float2(acc[mt][h * 2], acc[mt][h * 2 + 1]);
-          if (is_emb[mt][h]) {
+          if (UPD && is_emb[mt][h] && ((smask >> (mt * 16 + g + h * 8)) & 1u)) {
+            // updated above
+          } else if (is_emb[mt][h]) {
             __stcs(reinterpret_cast<float2*>(de_lane + (mt * 16 + h * 8) * D + nt * 8), v);
           } else if (is_dense[mt][h]) {
             const int col = nt * 8 + t2;
@@ -709,6 +811,23 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
             *reinterpret_cast<float2*>(d_dense + b * D + col) = v;
           }
         }
+    }
+    if constexpr (UPD) {
+      // finished rows back to the table and its optimizer state: 16 bytes per lane, a full row per kLanesPerRow lanes
+      __syncwarp();
+      constexpr int kRowsPerIter = 32 / kLanesPerRow;
+      const int colq = (lane % kLanesPerRow) * 4;
+#pragma unroll 4
+      for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
+        const int r = r0 + sub;
+        const uint32_t row = __shfl_sync(0xffffffffu, rowc, r);
+        if (r < F && ((smask >> r) & 1u)) {
+          const size_t o = static_cast<size_t>(row) * D + colq;
+          *reinterpret_cast<float4*>(u.table + o) = *reinterpret_cast<const float4*>(xw + r * STRIDE + colq);
+          if (u.s0 != nullptr) *reinterpret_cast<float4*>(u.s0 + o) = *reinterpret_cast<const float4*>(mvm + r * MS + colq);
+          if (u.s1 != nullptr) *reinterpret_cast<float4*>(u.s1 + o) = *reinterpret_cast<const float4*>(mvv + r * MS + colq);
+        }
+      }
     }
     __syncwarp();   // the stage may be overwritten by the next iteration's copies
     if (++stage == kIxStages) stage = 0;
@@ -877,9 +996,88 @@ static int launch_bwd(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_str
   return RB_OK;
 }
 
+// the fused-update form: local table, fp32 rows (SRC == 0)
+template <typename DOUT>
+static int launch_bwd_update(const IxArgs& a, int D, const DOUT* dOut, int64_t dout_stride, float* dE, float* d_dense, const IxUpdate& u,
+                             cudaStream_t st) {
+  const int total = a.ncols + (a.tail ? D : 0);
+  constexpr int EPC = 16 / static_cast<int>(sizeof(DOUT));
+  const int rounded = (total + EPC - 1) / EPC * EPC;
+  const int copy_width = (dout_stride >= rounded) ? rounded : total;
+  const int gs_bytes = 16 + ((copy_width * static_cast<int>(sizeof(DOUT)) + 15 + 15) / 16) * 16;
+  int rc = RB_OK;
+#define LAUNCH_U(DD, SELFV)                                                                                             \
+  {                                                                                                                     \
+    const size_t per_warp = static_cast<size_t>(kIxStages) * (32 * (DD + 4) * 4 + gs_bytes) + 2 * a.F * (DD + 8) * 4 + kIxStages * 256; \
+    const int W = std::min(warps_that_fit(per_warp), kIxUpdWarps);                                                      \
+    RB_CHECK_ARG(W >= 1, RB_ERR_SHAPE, "interaction row does not fit in shared memory");                                \
+    const size_t smem = static_cast<size_t>(W) * per_warp;                                                              \
+    rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, SELFV, 0, true>, smem);                                          \
+    if (rc != RB_OK) return rc;                                                                                         \
+    dot_interaction_bwd_kernel<DD, DOUT, SELFV, 0, true><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
+                                                                                                          d_dense, copy_width, \
+                                                                                                          gs_bytes, u); \
+  }
+#define LAUNCH_UD(DD)                                                                                                   \
+  if (a.self_interaction) LAUNCH_U(DD, true) else LAUNCH_U(DD, false)
+  if (D == 16) LAUNCH_UD(16) else if (D == 32) LAUNCH_UD(32) else if (D == 64) LAUNCH_UD(64) else LAUNCH_UD(128)
+#undef LAUNCH_UD
+#undef LAUNCH_U
+  RB_LAUNCH_CHECK("dot_interaction_bwd_kernel (fused row update)");
+  return RB_OK;
+}
+
 }  // namespace rb
 
 using namespace rb;
+
+extern "C" int rb_dot_interaction_bwd_update(float* table, int64_t rows, const void* idx, int32_t idx_type,
+                                             const int64_t* field_row_offset, const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                                             int32_t self_interaction, int32_t skip_gather, int32_t tail, const void* dOut,
+                                             int32_t dout_dtype, int64_t dout_stride, float* dE, float* d_dense,
+                                             const uint8_t* single, float* state0, float* state1, const rb_opt_params* opt,
+                                             int32_t row_cache, const int32_t* row_cache_hint, void* stream) {
+  IxArgs a;
+  int rc = fill_args(&a, nullptr, table, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather, tail);
+  if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(row_cache >= RB_ROW_CACHE_L2 && row_cache <= RB_ROW_CACHE_AUTO, RB_ERR_ARG, "bad row_cache %d", row_cache);
+  a.row_cache = row_cache;
+  a.row_cache_hint = row_cache_hint;
+  if (B == 0) return RB_OK;
+  RB_CHECK_ARG(dOut != nullptr && dout_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "dOut is null or stride too small");
+  RB_CHECK_ARG(dout_dtype == RB_F32 || dout_dtype == RB_BF16, RB_ERR_ARG, "bad dout_dtype %d", dout_dtype);
+  RB_CHECK_ARG(dE != nullptr && aligned_for(dE, 4) && (d_dense == nullptr || aligned_for(d_dense, 4)), RB_ERR_ALIGN,
+               "dE (required: rows the step touches more than once still go through it) / d_dense not 16 B aligned");
+  RB_CHECK_ARG(single != nullptr && opt != nullptr, RB_ERR_ARG, "single / opt is null");
+  const int o = opt->optimizer;
+  RB_CHECK_ARG(o == RB_OPT_SGD || o == RB_OPT_ADAGRAD || o == RB_OPT_ADAM_LAZY, RB_ERR_ARG,
+               "the fused row update serves the row-sparse optimizers (SGD, Adagrad, lazy Adam), got %d", o);
+  RB_CHECK_ARG(o != RB_OPT_ADAM_LAZY || (state0 != nullptr && state1 != nullptr && opt->step >= 1), RB_ERR_ARG, "Adam needs m, v and step >= 1");
+  RB_CHECK_ARG(o != RB_OPT_ADAGRAD || state0 != nullptr, RB_ERR_ARG, "Adagrad needs its accumulator");
+  RB_CHECK_ARG((state0 == nullptr || aligned_for(state0, 4)) && (state1 == nullptr || aligned_for(state1, 4)), RB_ERR_ALIGN,
+               "optimizer state not 16 B aligned");
+  IxUpdate u;
+  u.single = single;
+  u.table = table;
+  u.s0 = o == RB_OPT_SGD ? nullptr : state0;
+  u.s1 = o == RB_OPT_ADAM_LAZY ? state1 : nullptr;
+  u.math.opt = o;
+  u.math.lr = opt->lr;
+  u.math.b1 = opt->beta_1;
+  u.math.b2 = opt->beta_2;
+  u.math.omb1 = 1.0f - opt->beta_1;
+  u.math.omb2 = 1.0f - opt->beta_2;
+  u.math.eps = opt->epsilon;
+  u.math.alpha = o == RB_OPT_ADAM_LAZY ? rb_adam_alpha_t(opt->lr, opt->beta_1, opt->beta_2, opt->step) : 0.f;
+  u.alpha_dev = o == RB_OPT_ADAM_LAZY ? opt->alpha_t_dev : nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dout_dtype == RB_F32) {
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(dOut) & 3) == 0, RB_ERR_ALIGN, "dOut not 4 B aligned");
+    return launch_bwd_update<float>(a, D, static_cast<const float*>(dOut), dout_stride, dE, d_dense, u, st);
+  }
+  RB_CHECK_ARG((reinterpret_cast<uintptr_t>(dOut) & 1) == 0, RB_ERR_ALIGN, "dOut not 2 B aligned");
+  return launch_bwd_update<__nv_bfloat16>(a, D, static_cast<const __nv_bfloat16*>(dOut), dout_stride, dE, d_dense, u, st);
+}
 
 extern "C" int rb_dot_interaction_fwd(const float* E, const float* table, int64_t rows, const void* idx,
                                       int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,

@@ -199,39 +199,24 @@ struct OptSink {  // fused optimizer row update; every op explicitly rounded (no
     update_row<VEC>(o, g, w, m, v);
   }
 
+  __device__ __forceinline__ OptMath math() const { return OptMath{opt, lr, b1, b2, omb1, omb2, eps, alpha}; }
+
   template <int VEC>
   __device__ __forceinline__ void update_row(int64_t o, const Row<VEC>& g, Row<VEC>& w, Row<VEC>& m, Row<VEC>& v) const {
+    opt_row_math<VEC>(math(), g, w, m, v);
     if (opt == RB_OPT_ADAM_LAZY) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        m.v[i] = __fadd_rn(__fmul_rn(m.v[i], b1), __fmul_rn(g.v[i], omb1));
-        v.v[i] = __fadd_rn(__fmul_rn(v.v[i], b2), __fmul_rn(__fmul_rn(g.v[i], g.v[i]), omb2));
-        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(alpha, m.v[i]), __fadd_rn(__fsqrt_rn(v.v[i]), eps)));
-      }
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(s1 + o, v);
       st_row<VEC>(table + o, w);
       store_shadow<VEC>(o, w);
     } else if (opt == RB_OPT_ADAM_TF_DENSE) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], omb1));
-        v.v[i] = __fadd_rn(v.v[i], __fmul_rn(__fmul_rn(g.v[i], g.v[i]), omb2));
-      }
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(s1 + o, v);
     } else if (opt == RB_OPT_ADAGRAD) {   // accumulator in slot 1 (m)
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        m.v[i] = __fadd_rn(m.v[i], __fmul_rn(g.v[i], g.v[i]));
-        w.v[i] = __fsub_rn(w.v[i], __fdiv_rn(__fmul_rn(lr, g.v[i]), __fadd_rn(__fsqrt_rn(m.v[i]), eps)));
-      }
       st_row<VEC>(s0 + o, m);
       st_row<VEC>(table + o, w);
       store_shadow<VEC>(o, w);
     } else {  // SGD
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) w.v[i] = __fsub_rn(w.v[i], __fmul_rn(lr, g.v[i]));
       st_row<VEC>(table + o, w);
       store_shadow<VEC>(o, w);
     }
@@ -537,9 +522,9 @@ seg_reduce_tiles_bulk_kernel(const uint32_t* __restrict__ keys, const uint32_t* 
   auto issue = [&](int j, int slot) {            // lane 0 of the group only
     if (j >= tcnt) return;
     const uint32_t key = tk[j];
+    uint64_t* bar = my_bar + slot;
     const GradPos q = decode_pos(gsrc, tp[j]);
     float* dst = my_ring + slot * kKinds * D;
-    uint64_t* bar = my_bar + slot;
     const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
     su_mbar_expect_tx(bar, row_bytes + (update ? state_bytes : 0u));
     su_bulk_g2s(dst, grad_src0(gsrc, q, 0), row_bytes, bar);
@@ -1090,7 +1075,7 @@ extern "C" int rb_sparse_bwd_prepare(int64_t rows, int32_t D, const rb_lookup_gr
 // n_dev != null: only the first *n_dev sorted pairs are real (masked pads collapsed by sort_groups)
 static int apply_sorted(float* table, float* state0, float* state1, int64_t rows, int32_t D, const rb_lookup_group* groups,
                         int32_t num_groups, const rb_opt_params* opt, void* ws, size_t ws_bytes, int32_t sorted_sel,
-                        void* stream, const int* n_dev) {
+                        void* stream, const int* n_dev, int32_t flags = 0) {
   RB_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= RB_MAX_LOOKUP_GROUPS, RB_ERR_ARG,
                "1..%d lookup groups, got %d", RB_MAX_LOOKUP_GROUPS, num_groups);
   RB_CHECK_ARG(sorted_sel == 0 || sorted_sel == 1, RB_ERR_ARG, "sorted_sel must come from rb_sparse_bwd_prepare");
@@ -1125,6 +1110,10 @@ static int apply_sorted(float* table, float* state0, float* state1, int64_t rows
     const uint32_t *keys, *vals;
     unsigned char* wsb = static_cast<unsigned char*>(ws);
     sorted_pairs(wsb, lay, sorted_sel, &keys, &vals);
+    RB_CHECK_ARG((flags & RB_APPLY_SKIP_SINGLETONS) == 0 || (o != RB_OPT_ADAM_TF_DENSE && num_groups == 1), RB_ERR_ARG,
+                 "RB_APPLY_SKIP_SINGLETONS: one lookup group, row-sparse optimizers only");
+    // the pairs of rows touched once were compacted away by rb_sparse_bwd_mark_singletons: the survivors' count is on the device
+    if (flags & RB_APPLY_SKIP_SINGLETONS) n_dev = reinterpret_cast<const int*>(wsb + lay.long_count) + 1;
     rc = run_segments(geo, keys, vals, static_cast<int>(n), gg, sink, wsb, lay, st, n_dev);
     if (rc != RB_OK) return rc;
   }
@@ -1139,6 +1128,71 @@ extern "C" int rb_sparse_bwd_apply(float* table, float* state0, float* state1, i
                                    const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt, void* ws,
                                    size_t ws_bytes, int32_t sorted_sel, void* stream) {
   return apply_sorted(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sorted_sel, stream, nullptr);
+}
+
+extern "C" int rb_sparse_bwd_apply_ex(float* table, float* state0, float* state1, int64_t rows, int32_t D,
+                                      const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt, void* ws,
+                                      size_t ws_bytes, int32_t sorted_sel, int32_t flags, void* stream) {
+  RB_CHECK_ARG((flags & ~RB_APPLY_SKIP_SINGLETONS) == 0, RB_ERR_ARG, "unknown flags 0x%x", flags);
+  return apply_sorted(table, state0, state1, rows, D, groups, num_groups, opt, ws, ws_bytes, sorted_sel, stream, nullptr, flags);
+}
+
+// single[p] = 1 when the row of lookup position p occurs exactly once among the step's sorted pairs; keep[i] = 1 for the sorted
+// pairs of every other row
+__global__ void __launch_bounds__(256)
+mark_singletons_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, uint8_t* __restrict__ single,
+                       int32_t* __restrict__ keep) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  const bool alone = (i == 0 || keys[i - 1] != k) && (i == n - 1 || keys[i + 1] != k);
+  single[vals[i]] = alone ? 1 : 0;
+  keep[i] = alone ? 0 : 1;
+}
+
+// stable compaction of the kept pairs (incl = inclusive scan of keep) into the other half of the double buffers
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int32_t* __restrict__ incl,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int* __restrict__ n_kept) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = incl[i];
+  if (c != (i > 0 ? incl[i - 1] : 0)) {
+    keys_out[c - 1] = keys[i];
+    vals_out[c - 1] = vals[i];
+  }
+  if (i == n - 1) *n_kept = c;
+}
+
+extern "C" int rb_sparse_bwd_mark_singletons(int64_t rows, int32_t D, int64_t n, void* ws, size_t ws_bytes, int32_t* sorted_sel,
+                                             uint8_t* single, void* stream) {
+  RB_CHECK_ARG(sorted_sel != nullptr && (*sorted_sel == 0 || *sorted_sel == 1), RB_ERR_ARG, "sorted_sel must come from rb_sparse_bwd_prepare");
+  RB_CHECK_ARG(single != nullptr, RB_ERR_ARG, "single is null");
+  RowGeom geo;
+  int rc = check_common(rows, D, n, &geo);
+  if (rc != RB_OK) return rc;
+  if (n == 0) return RB_OK;
+  const WsLayout lay = ws_layout(n, D, rows);
+  rc = check_ws(ws, ws_bytes, lay);
+  if (rc != RB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  const uint32_t *keys, *vals;
+  sorted_pairs(wsb, lay, *sorted_sel, &keys, &vals);
+  int32_t* keep = reinterpret_cast<int32_t*>(wsb + lay.seg_incl);
+  mark_singletons_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, vals, static_cast<int>(n), single, keep);
+  RB_LAUNCH_CHECK("mark_singletons_kernel");
+  size_t temp = lay.cub_bytes;
+  RB_CUDA(cub::DeviceScan::InclusiveSum(wsb + lay.cub_temp, temp, keep, keep, static_cast<int>(n), st));
+  const int other = 1 - *sorted_sel;
+  uint32_t* keys_out = reinterpret_cast<uint32_t*>(wsb + (other ? lay.keys_b : lay.keys_a));
+  uint32_t* vals_out = reinterpret_cast<uint32_t*>(wsb + (other ? lay.vals_b : lay.vals_a));
+  int* n_kept = reinterpret_cast<int*>(wsb + lay.long_count) + 1;
+  compact_pairs_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, vals, static_cast<int>(n), keep, keys_out, vals_out, n_kept);
+  RB_LAUNCH_CHECK("compact_pairs_kernel");
+  count_launches(2);
+  *sorted_sel = other;
+  return RB_OK;
 }
 
 extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,

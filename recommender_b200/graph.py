@@ -24,7 +24,8 @@ class GraphedTrainStep:
     batch = (cat_features int[B,F], int_features f32[B,13], label) CUDA tensors of the captured shapes.
     The returned loss is a static device tensor overwritten by every replay."""
 
-    def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, sample_batch: Sequence[torch.Tensor], warmup: int = 3):
+    def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, sample_batch: Sequence[torch.Tensor], warmup: int = 3,
+                 fuse_sparse_updates: bool = False):
         if not all(t.is_cuda for t in sample_batch):
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
@@ -32,6 +33,12 @@ class GraphedTrainStep:
         self.static = tuple(torch.empty_like(t) for t in sample_batch)
         if hasattr(optimizer, "enable_device_scalars"):
             optimizer.enable_device_scalars(sample_batch[0].device)
+        # a captured step always runs backward + apply_gradients together, so the optimizer's row update of the rows a step
+        # touches once MAY run inside the backward (optimizers.fuse_sparse_updates).  Opt-in (argument or RB_FUSED_UPDATE=1):
+        # measured slower than the two-kernel chain on a B200 (r2_22 / r2_23) — the exactly-rounded Adam arithmetic
+        # needs the occupancy of the reduction kernel to hide, which the interaction kernel's shared-memory ring does not leave
+        if (fuse_sparse_updates or os.environ.get("RB_FUSED_UPDATE", "0") == "1") and hasattr(optimizer, "fuse_sparse_updates"):
+            optimizer.fuse_sparse_updates(model)
         for d, s in zip(self.static, sample_batch):
             d.copy_(s)
         # Autograd graphs of earlier eager steps pin their AccumulateGrad nodes to the stream they ran on (the

@@ -152,9 +152,18 @@ class _InteractFn(torch.autograd.Function):
         si, sg, tail = ctx.flags
         if dOut.stride(-1) != 1:
             dOut = dOut.contiguous()
-        dE, d_dense = ops.dot_interaction_bwd(dOut, table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
-                                              dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail,
-                                              row_cache=emb.row_cache, row_cache_hint=emb._hot_rows)
+        fused = emb._fused_update_args(idx)
+        if fused is not None:
+            # rows this step touches once get their optimizer update right here (rb_dot_interaction_bwd_update); the sorted
+            # reduction launched by apply_pending() then passes over them
+            dE, d_dense = ops.dot_interaction_bwd_update(dOut, table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
+                                                         dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail,
+                                                         row_cache=emb.row_cache, row_cache_hint=emb._hot_rows, **fused)
+            emb._fused_done = True
+        else:
+            dE, d_dense = ops.dot_interaction_bwd(dOut, table=emb.embeddings, idx=idx, field_row_offset=emb.row_offset_for(F),
+                                                  dense_vec=dense_vec, self_interaction=si, skip_gather=sg, tail=tail,
+                                                  row_cache=emb.row_cache, row_cache_hint=emb._hot_rows)
         emb._record(LookupGroup(idx, F, GradSource.per_position(dE, F), field_row_offset=emb.row_offset_for(F),
                                 hash_mod=emb.hash_mod))
         emb._grad_ready = torch.cuda.current_stream().record_event()    # dE is complete here: the row update may start
@@ -239,6 +248,11 @@ class Embedding(nn.Module):
         # The row update only needs the sorted pairs and dE: it is launched on the side stream as soon as the
         # interaction backward has written dE, so it overlaps the rest of the backward (bottom MLP) and the dense
         # optimizer step; join() brings the streams back together.
+        # Fused row update (optimizers.*.fuse_sparse_updates): the optimizer whose row update the fused lookup's backward
+        # applies to the rows a step touches once; None = every row goes through apply_pending()
+        self.fused_optimizer = None
+        self._single: Optional[torch.Tensor] = None       # uint8 [n]: flags written by the pre-sort (rb_sparse_bwd_mark_singletons)
+        self._fused_done = False
         self._grad_ready: Optional[torch.cuda.Event] = None
         self.after_grad_hooks: list = []      # called with the event above once the fused lookup's backward is queued
         self._apply_done: Optional[torch.cuda.Event] = None
@@ -285,6 +299,11 @@ class Embedding(nn.Module):
         with torch.cuda.stream(side):
             sel = ops.sparse_bwd_prepare(rows, D, [LookupGroup(idx, L, None, field_row_offset=field_row_offset, hash_mod=self.hash_mod)],
                                          self._sort_ws, hot_rows_flag=self._hot_rows)
+            if self.fused_optimizer is not None and self.hash_mod == 0 and D % 4 == 0:
+                if self._single is None or self._single.numel() < n:
+                    self._single = torch.empty(n, dtype=torch.uint8, device=self.embeddings.device)
+                self._sel_compact = ops.sparse_bwd_mark_singletons(rows, D, n, self._sort_ws, sel, self._single)
+                self._single_for = idx.data_ptr()
             done = side.record_event()
         if not torch.cuda.is_current_stream_capturing():
             idx.record_stream(side)
@@ -350,6 +369,43 @@ class Embedding(nn.Module):
             self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return out
 
+    def _ensure_state(self, kind: str, initial_accumulator_value=0.1):
+        """(state0, state1, created-just-now) of optimizer `kind` for this table."""
+        st = self.opt_state
+        fresh = False
+        if kind in ("adam_lazy", "adam_tf_dense"):
+            if "m" not in st:
+                st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
+                fresh = True
+            return st["m"], st["v"], fresh
+        if kind == "adagrad":
+            if "acc" not in st:
+                st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
+                fresh = True
+            return st["acc"], None, fresh
+        if kind == "sgd":
+            return None, None, False
+        raise ValueError(kind)
+
+    def _fused_update_args(self, idx: torch.Tensor):
+        """Keyword arguments of ops.dot_interaction_bwd_update when this backward may apply the optimizer to the rows the step
+        touches once, else None: an optimizer was armed (fuse_sparse_updates), its update is row-sparse, this lookup is the
+        one the pre-sort covers and no other use of the table has recorded a gradient in this step."""
+        opt = self.fused_optimizer
+        srt = self._sorted
+        if (opt is None or srt is None or srt[0] is None or self.pending or self._single is None
+                or srt[0].data_ptr() != idx.data_ptr() or srt[0].numel() != idx.numel()
+                or getattr(self, "_single_for", None) != idx.data_ptr()):
+            return None
+        kind = opt.sparse_kind
+        if kind not in ("sgd", "adagrad", "adam_lazy"):
+            return None
+        kw = dict(opt._sparse_kwargs())
+        s0, s1, _ = self._ensure_state(kind, kw.pop("initial_accumulator_value", 0.1))
+        torch.cuda.current_stream().wait_event(srt[3])          # the flags are written by the pre-sort's stream
+        step = opt.iterations if opt._prepared else opt.iterations + 1
+        return dict(single=self._single[: idx.numel()], state0=s0, state1=s1, optimizer=kind, step=step, **kw)
+
     def join(self) -> None:
         """Wait (on the current stream) for a row update launched on the side stream."""
         if self._apply_done is not None:
@@ -365,23 +421,13 @@ class Embedding(nn.Module):
             if kind == "adam_tf_dense":   # Keras moves every row every step, gradient or not
                 raise NotImplementedError("adam_tf_dense with no lookup in the step")
             return 0
-        st = self.opt_state
-        fresh_state = False           # state tensors created just now on the current stream: the side stream must see them
-        if kind in ("adam_lazy", "adam_tf_dense"):
-            if "m" not in st:
-                st["m"], st["v"] = torch.zeros_like(self.embeddings), torch.zeros_like(self.embeddings)
-                fresh_state = True
-            s0, s1 = st["m"], st["v"]
-        elif kind == "adagrad":
-            if "acc" not in st:
-                st["acc"] = torch.full_like(self.embeddings, initial_accumulator_value)
-                fresh_state = True
-            s0, s1 = st["acc"], None
-        elif kind == "sgd":
-            s0 = s1 = None
-        else:
-            raise ValueError(kind)
+        # fresh_state: state tensors created just now on the current stream: the side stream must see them
+        s0, s1, fresh_state = self._ensure_state(kind, initial_accumulator_value)
         groups, self.pending = self.pending, []
+        skip, self._fused_done = self._fused_done, False
+        if skip and len(groups) != 1:
+            raise RuntimeError("the fused row update (fuse_sparse_updates) serves tables looked up once per step; this step recorded "
+                               f"{len(groups)} uses after rows were already updated in the backward")
         sorted_, self._sorted = self._sorted, None
         n = sum(g.n for g in groups)
         if sorted_ is not None:
@@ -396,14 +442,18 @@ class Embedding(nn.Module):
                 else:
                     side.wait_event(grad_ready)
                 with torch.cuda.stream(side):
-                    ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, sorted_[2], optimizer=kind, step=step,
-                                         lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
+                    ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, self._sel_compact if skip else sorted_[2],
+                                         optimizer=kind, step=step, lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon,
+                                         alpha_dev=alpha_dev, skip_singletons=skip)
                     self._apply_done = side.record_event()
                 self._inflight = groups          # keeps dE alive until join(): the allocator must not hand it out meanwhile
                 return n
-            ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, sorted_[2], optimizer=kind, step=step, lr=lr,
-                                 beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
+            ops.sparse_bwd_apply(self.embeddings, s0, s1, groups, self._sort_ws, self._sel_compact if skip else sorted_[2],
+                                 optimizer=kind, step=step, lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev,
+                                 skip_singletons=skip)
         else:
+            if skip:
+                raise RuntimeError("fused row update: the pre-sorted pairs of this step are gone")
             ops.sparse_bwd_update(self.embeddings, s0, s1, groups, optimizer=kind, step=step, lr=lr, beta_1=beta_1,
                                   beta_2=beta_2, epsilon=epsilon, alpha_dev=alpha_dev)
         return n

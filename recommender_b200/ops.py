@@ -236,6 +236,34 @@ def dot_interaction_bwd(dOut, *, E=None, table=None, idx=None, field_row_offset=
     return dE, d_dense
 
 
+def dot_interaction_bwd_update(dOut, *, table, idx, single, state0, state1, field_row_offset=None, dense_vec=None,
+                               self_interaction=False, skip_gather=True, tail=False, optimizer="adam_lazy", step=1, lr=1e-3,
+                               beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None, row_cache=False, row_cache_hint=None,
+                               dE=None):
+    """rb_dot_interaction_bwd_update: the backward of the fused lookup + interaction that also applies the optimizer to
+    the rows flagged in `single` (uint8 [B*F], from sparse_bwd_mark_singletons) — their dE rows stay unwritten.
+    Returns (dE, d_dense)."""
+    _need_cuda(dOut, table, idx, single, state0, state1, field_row_offset, dense_vec)
+    _f32c(table, "table")
+    idx = idx.contiguous()
+    B, F = idx.shape
+    rows, D = table.shape
+    if dOut.stride(-1) != 1 or dOut.dim() != 2 or dOut.shape[0] != B:
+        raise ValueError("dOut must be [B, cols] (float32 or bfloat16) with unit inner stride")
+    if single.dtype != torch.uint8 or single.numel() != B * F or not single.is_contiguous():
+        raise ValueError("single must be a contiguous uint8 tensor with one flag per lookup position")
+    if dE is None:
+        dE = torch.empty(B, F, D, dtype=torch.float32, device=table.device)
+    d_dense = torch.empty(B, D, dtype=torch.float32, device=table.device) if dense_vec is not None else None
+    opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+    check(lib.rb_dot_interaction_bwd_update(_ptr(table), rows, _ptr(idx), _idx(idx), _ptr(field_row_offset), _ptr(dense_vec), B, F, D,
+                                            int(self_interaction), int(skip_gather), int(tail), _ptr(dOut), _float_type(dOut.dtype),
+                                            int(dOut.stride(0)), _ptr(dE), _ptr(d_dense), _ptr(single), _ptr(state0), _ptr(state1),
+                                            C.byref(opt), _lib.ROW_CACHE_ENUM[row_cache], _ptr(row_cache_hint), _stream()),
+          "rb_dot_interaction_bwd_update")
+    return dE, d_dense
+
+
 # --------------------------------------------------------------------------------------------
 # K7..K9: backward scatter + sparse optimizer
 # --------------------------------------------------------------------------------------------
@@ -348,16 +376,34 @@ def sparse_bwd_prepare(rows: int, D: int, groups: Sequence["LookupGroup"], ws: t
     return int(sel.value)
 
 
+def sparse_bwd_mark_singletons(rows: int, D: int, n: int, ws: torch.Tensor, sel: int, single: torch.Tensor) -> int:
+    """rb_sparse_bwd_mark_singletons: single[p] = 1 iff the row of lookup position p occurs once among the pairs sorted by
+    sparse_bwd_prepare(ws) — the rows dot_interaction_bwd_update may update on its own; the other rows' pairs are compacted.
+    Returns the selector to hand to sparse_bwd_apply(skip_singletons=True)."""
+    _need_cuda(ws, single)
+    if single.dtype != torch.uint8 or single.numel() < n:
+        raise ValueError("single must be uint8 with one element per lookup position")
+    s = C.c_int32(int(sel))
+    check(lib.rb_sparse_bwd_mark_singletons(int(rows), int(D), int(n), _ptr(ws), ws.numel(), C.byref(s), _ptr(single), _stream()),
+          "rb_sparse_bwd_mark_singletons")
+    return int(s.value)
+
+
 def sparse_bwd_apply(table, state0, state1, groups: Sequence["LookupGroup"], ws: torch.Tensor, sel: int, *, optimizer="adam_lazy",
-                     step=1, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None) -> None:
+                     step=1, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, alpha_dev=None, skip_singletons=False) -> None:
     """Phase 2 (rb_sparse_bwd_apply): segmented reduction + optimizer row update over pairs sorted by
-    sparse_bwd_prepare with the same groups and workspace."""
+    sparse_bwd_prepare with the same groups and workspace.  skip_singletons: rows that occur once were already updated by
+    dot_interaction_bwd_update (rb_sparse_bwd_apply_ex, RB_APPLY_SKIP_SINGLETONS)."""
     _need_cuda(table, state0, state1)
     for g in groups:
         _need_cuda(g.idx, g.field_row_offset, *g.grad.srcs, g.grad.mask_idx, g.grad.count, g.grad.fm_g, g.grad.fm_s)
     _f32c(table, "table")
     rows, D = table.shape
     opt = _opt_params(optimizer, step, lr, beta_1, beta_2, epsilon, alpha_dev)
+    if skip_singletons:
+        check(lib.rb_sparse_bwd_apply_ex(_ptr(table), _ptr(state0), _ptr(state1), rows, D, _groups_c(groups), len(groups), C.byref(opt),
+                                         _ptr(ws), ws.numel(), int(sel), 1, _stream()), "rb_sparse_bwd_apply_ex")
+        return
     check(lib.rb_sparse_bwd_apply(_ptr(table), _ptr(state0), _ptr(state1), rows, D, _groups_c(groups), len(groups), C.byref(opt),
                                   _ptr(ws), ws.numel(), int(sel), _stream()), "rb_sparse_bwd_apply")
 

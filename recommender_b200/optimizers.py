@@ -45,6 +45,19 @@ class _Optimizer:
     def _refresh_device_scalars(self) -> None:
         pass
 
+    def fuse_sparse_updates(self, model, enable: bool = True) -> int:
+        """Opt in to the fused row update: from now on the backward of a table's fused lookup (DLRM's lookup + interaction)
+        applies THIS optimizer's row update to the rows the step touches exactly once, where their gradient rows are produced
+        (rb_dot_interaction_bwd_update); apply_gradients() then covers the remaining rows.  Tables, states and results are
+        bit-identical to the unfused order — but the table changes during loss.backward(), so only a caller that always
+        follows backward() with apply_gradients() (a training step) may arm it.  Returns the number of tables armed."""
+        n = 0
+        for m in model.modules():
+            if hasattr(m, "fused_optimizer") and hasattr(m, "_fused_update_args"):
+                m.fused_optimizer = self if (enable and self.sparse_kind in ("sgd", "adagrad", "adam_lazy")) else None
+                n += m.fused_optimizer is not None
+        return n
+
     def _sparse_kwargs(self):
         raise NotImplementedError
 

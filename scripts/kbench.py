@@ -122,6 +122,33 @@ def main():
             grp = LookupGroup(ring[i % 4], F, GradSource.per_position(dE, F), field_row_offset=off)
             ops.sparse_bwd_update(table, m, v if a.optimizer.startswith("adam") else None, [grp], optimizer=a.optimizer, step=step[0])
         timeit("update", upd)
+    if "bwd_update" in which:     # the fused backward + row update (rows touched once) and the reduction over the remaining rows
+        ws = ops.sparse_workspace(B * F, D, V * T, dev)
+        single = torch.empty(B * F, dtype=torch.uint8, device=dev)
+        dEb = torch.empty(B, F, D, device=dev)
+        step = [0]
+        evs, evs2 = [], []
+        for i in range(a.iters + 3):
+            step[0] += 1
+            idx = ring[i % 4]
+            sel = ops.sparse_bwd_prepare(V * T, D, [LookupGroup(idx, F, None, field_row_offset=off)], ws)
+            sel = ops.sparse_bwd_mark_singletons(V * T, D, B * F, ws, sel, single)
+            s_, e_, e2_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            s_.record()
+            ops.dot_interaction_bwd_update(dout, table=table, idx=idx, single=single, state0=m, state1=v, field_row_offset=off,
+                                           dense_vec=dense, tail=True, optimizer=a.optimizer, step=step[0], dE=dEb)
+            e_.record()
+            grp = LookupGroup(idx, F, GradSource.per_position(dEb, F), field_row_offset=off)
+            ops.sparse_bwd_apply(table, m, v, [grp], ws, sel, optimizer=a.optimizer, step=step[0], skip_singletons=True)
+            e2_.record()
+            if i >= 3:
+                evs.append((s_, e_))
+                evs2.append((e_, e2_))
+        torch.cuda.synchronize()
+        for name, ev in (("bwd_update", evs), ("apply_rest", evs2)):
+            ts = sorted(x.elapsed_time(y) * 1e3 for x, y in ev)
+            res[name] = dict(us_median=ts[len(ts) // 2], us_min=ts[0], us_mean=sum(ts) / len(ts))
+        res["bwd_update"]["singletons"] = int(single.sum())
     if "apply" in which:     # the segmented reduction + row update alone (keys + sort outside the timed region, as in the step)
         ws = ops.sparse_workspace(B * F, D, V * T, dev)
         step = [0]

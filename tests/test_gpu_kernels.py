@@ -827,3 +827,94 @@ def test_kernels_stay_inside_their_outputs_and_repeat_bit_for_bit(ops):
     out = ops.dense_head_fwd(x, wv, bias[:1], "sigmoid")
     dout1 = torch.randn(rows, device="cuda", generator=g)
     thrice(lambda: tuple(t for t in ops.dense_head_bwd(dout1, out, "sigmoid", x, wv, want_dx_colsum=True)))
+
+
+# ---- fused row update of the rows a step touches once (rb_dot_interaction_bwd_update + RB_APPLY_SKIP_SINGLETONS) -------------
+
+@pytest.mark.parametrize("kind", ["adam_lazy", "adagrad", "sgd"])
+@pytest.mark.parametrize("T,V,D,B,dist,dtype", [
+    (26, 3000, 64, 1111, "uniform", torch.bfloat16),     # most rows touched once, ragged batch
+    (26, 300, 64, 999, "uniform", torch.bfloat16),       # most rows touched several times
+    (1, 20000, 64, 777, "zipf", torch.bfloat16),         # one shared table, hot rows
+    (26, 1000, 16, 640, "zipf", torch.float32),
+    (26, 1000, 128, 257, "uniform", torch.float32),
+    (26, 50000, 32, 512, "uniform", torch.bfloat16),     # every row touched once
+])
+def test_fused_singleton_update_equals_the_unfused_chain(ops, kind, T, V, D, B, dist, dtype):
+    """The same table and optimizer state as interaction backward -> sort -> duplicate-row sum -> optimizer row update, three
+    steps in a row (the state carries over), for every row-sparse optimizer: bit for bit on every row a step touches at most
+    twice (a sum of two terms has one association); rows with longer chains are summed tile by tile over the COMPACTED pair
+    list, whose tile borders fall elsewhere — same terms, same order, another association of the fp32 additions."""
+    from recommender_b200.ops import GradSource, LookupGroup
+    rng = np.random.default_rng(B + D)
+    F, rows = 26, V * T
+    W0 = cu(O.init_table(rng, rows, D))
+    off = torch.arange(T, device="cuda", dtype=torch.int64) * V if T > 1 else None
+    width = 27 * 27 + D
+    stride = (width + 7) // 8 * 8
+
+    def state():
+        if kind == "adam_lazy":
+            return torch.zeros_like(W0), torch.zeros_like(W0)
+        if kind == "adagrad":
+            return torch.full_like(W0, 0.1), None
+        return None, None
+
+    Wa, Wb = W0.clone(), W0.clone()
+    sa, sb = state(), state()
+    ws_a, ws_b = ops.sparse_workspace(B * F, D, rows, "cuda"), ops.sparse_workspace(B * F, D, rows, "cuda")
+    single = torch.empty(B * F, dtype=torch.uint8, device="cuda")
+    hp = dict(optimizer=kind, lr=1e-2)
+    n_single = 0
+    exact_rows = torch.ones(rows, dtype=torch.bool, device="cuda")
+    for step in (1, 2, 3):
+        if dist == "uniform":
+            idx = cu(rng.integers(0, V, size=(B, F)))
+        else:
+            idx = cu(np.minimum(rng.zipf(1.3, size=(B, F)) - 1, V - 1).astype(np.int64))
+        dense = cu(rng.normal(0, 0.1, size=(B, D)).astype(np.float32))
+        dout = cu(rng.normal(0, 1e-2, size=(B, stride)).astype(np.float32)).to(dtype)
+        same_inputs = torch.equal(Wa, Wb)          # false once a long chain has moved a row by a different last bit
+        # (a) the unfused chain
+        dE_a, dd_a = ops.dot_interaction_bwd(dout, table=Wa, idx=idx, field_row_offset=off, dense_vec=dense, tail=True)
+        grp = LookupGroup(idx, F, GradSource.per_position(dE_a, F), field_row_offset=off)
+        sel = ops.sparse_bwd_prepare(rows, D, [grp], ws_a)
+        ops.sparse_bwd_apply(Wa, sa[0], sa[1], [grp], ws_a, sel, step=step, **hp)
+        # (b) fused
+        grp0 = LookupGroup(idx, F, None, field_row_offset=off)
+        sel = ops.sparse_bwd_prepare(rows, D, [grp0], ws_b)
+        sel = ops.sparse_bwd_mark_singletons(rows, D, B * F, ws_b, sel, single)
+        dE_b, dd_b = ops.dot_interaction_bwd_update(dout, table=Wb, idx=idx, single=single, state0=sb[0], state1=sb[1],
+                                                    field_row_offset=off, dense_vec=dense, tail=True, step=step, **hp)
+        grp = LookupGroup(idx, F, GradSource.per_position(dE_b, F), field_row_offset=off)
+        ops.sparse_bwd_apply(Wb, sb[0], sb[1], [grp], ws_b, sel, step=step, skip_singletons=True, **hp)
+        # the flags say what numpy says
+        flat = (idx + (off[None] if off is not None else 0)).reshape(-1).cpu().numpy()
+        _, inv, cnt = np.unique(flat, return_inverse=True, return_counts=True)
+        np.testing.assert_array_equal(single.cpu().numpy(), (cnt[inv] == 1).astype(np.uint8))
+        n_single += int(single.sum())
+        keep = single.view(B, F) == 0
+        if same_inputs:
+            assert torch.equal(dd_a, dd_b)
+            assert torch.equal(dE_a[keep], dE_b[keep])
+        else:
+            torch.testing.assert_close(dd_a, dd_b, rtol=1e-3, atol=1e-7)
+            torch.testing.assert_close(dE_a[keep], dE_b[keep], rtol=1e-3, atol=1e-7)
+        short = torch.ones(rows, dtype=torch.bool, device="cuda")
+        uq, c_ = np.unique(flat, return_counts=True)
+        short[cu(uq[c_ >= 3])] = False
+        exact_rows &= short                                   # a row stays comparable bit for bit until a long chain touches it
+        for name, x, y in (("table", Wa, Wb), ("state0", sa[0], sb[0]), ("state1", sa[1], sb[1])):
+            if x is None:
+                continue
+            assert torch.equal(x[exact_rows], y[exact_rows]), f"step {step}: {name} differs on rows touched at most twice"
+            # longer chains: |error of the sum| ~ 1e-9 here; Adam's step alpha * m / (sqrt(v) + eps) amplifies it where the
+            # terms nearly cancel, bounded by a small fraction of one learning-rate step (lr = 1e-2)
+            if name == "table":
+                torch.testing.assert_close(x, y, rtol=0, atol=2e-6)
+            else:
+                torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-9)
+    assert not torch.equal(Wa, W0)
+    if V >= 3000 and dist == "uniform":
+        assert n_single > 0.5 * 3 * B * F
+    ops.check_oob("cuda")

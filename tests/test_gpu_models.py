@@ -24,13 +24,13 @@ def _mlp(g, name):
     return layers
 
 
-def _build_dlrm(g, fused=True, num_tables=1, V=None):
+def _build_dlrm(g, fused=True, num_tables=1, V=None, compute_dtype=None):
     from recommender_b200.model import DLRM
     bottom, top = _mlp(g, "bottom"), _mlp(g, "top")
     D = g["table"].shape[1]
     V = V or g["table"].shape[0]
     model = DLRM([W.shape[1] for W, _ in bottom], [W.shape[1] for W, _ in top], D, V, 26, 13, fused=fused,
-                 num_tables=num_tables, device="cuda")
+                 num_tables=num_tables, device="cuda", compute_dtype=compute_dtype)
     model.embedding_layer.embeddings.copy_(cu(g["table"]))
     model.bottom_mlp.load_arrays(bottom, "cuda")
     model.top_mlp.load_arrays(top, "cuda")
@@ -236,6 +236,45 @@ def test_graphed_train_step_equals_eager(cuda_lib, golden):
     assert torch.equal(t_g, t_e)
     for a, b in zip(p_g, p_e):
         assert torch.equal(a, b)
+
+
+def test_fused_row_update_inside_the_backward_equals_the_two_phase_step(cuda_lib, golden):
+    """optimizers.fuse_sparse_updates (opt-in): rows a step touches once are updated by the interaction backward itself, the
+    rest by the sorted reduction over the compacted pairs.  Same model after 5 steps as the plain step — eagerly and as one
+    CUDA graph (tables equal up to the association of duplicate sums longer than two terms)."""
+    from recommender_b200.graph import GraphedTrainStep
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden("dlrm_small")                 # Zipf ids: singletons, pairs and long chains in one batch
+    cat, dense_x, label = cu(g["cat"]), cu(g["dense"]), cu(g["label"])
+    n_steps = 5
+
+    def run(mode):
+        torch.manual_seed(0)
+        model = _build_dlrm(g, compute_dtype=torch.bfloat16)
+        opt = Adam()
+        if mode == "graph":
+            gs = GraphedTrainStep(model, opt, bce_clipped, (cat, dense_x, label), warmup=1, fuse_sparse_updates=True)
+            for _ in range(n_steps - gs.steps_run):
+                gs.step((cat, dense_x, label))
+        else:
+            if mode == "fused":
+                assert opt.fuse_sparse_updates(model) == 1
+            for _ in range(n_steps):
+                loss = bce_clipped(model({"cat_features": cat, "int_features": dense_x}), label)
+                loss.backward()
+                opt.apply_gradients(model)
+        torch.cuda.synchronize()
+        assert opt.iterations == n_steps
+        return model.embedding_layer.embeddings.clone(), [p.detach().clone() for p in model.parameters()]
+
+    t_ref, p_ref = run("plain")
+    for mode in ("fused", "graph"):
+        t, ps = run(mode)
+        torch.testing.assert_close(t, t_ref, rtol=1e-5, atol=1e-7)
+        assert (t != t_ref).float().mean().item() < 0.05          # all but the long chains: identical bits
+        for a, b in zip(ps, p_ref):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
 
 
 @pytest.fixture(scope="module")
