@@ -102,7 +102,9 @@ typedef struct rb_opt_params {
 typedef enum rb_grad_scale {
   RB_SCALE_NONE = 0,
   RB_SCALE_MEAN = 1,         /* g / L                                  */
-  RB_SCALE_MASKED_MEAN = 2   /* mask ? g / count[b] : 0                dien/layers.py:13-16 */
+  RB_SCALE_MASKED_MEAN = 2,  /* mask ? g / count[b] : 0                dien/layers.py:13-16 */
+  RB_SCALE_MASKED = 3        /* mask ? g : 0 (no division)             dien/layers.py:53-55: gradient rows of the masked
+                                positions are exactly zero and are never read — the producer need not write them */
 } rb_grad_scale;
 
 typedef struct rb_grad_source {
@@ -410,6 +412,9 @@ int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, c
 /* out_bf16[i] = bf16(dy[i] * activation'(y[i])) over n contiguous f32 elements: the ReluGrad / SigmoidGrad in front of the
  * last layer's gradient GEMMs. */
 int rb_dense_act_bwd(const float* dy, const float* y, int32_t activation, int64_t n, void* out_bf16, void* stream);
+/* the same with bf16 dy and y: the activation of a HIDDEN layer (dien/layers.py:37-38: Dense(80, sigmoid), Dense(40, sigmoid)),
+ * whose output the forward kept in bf16.  dz = bf16(f32(dy) * act'(f32(y))). */
+int rb_dense_act_bwd_bf16(const void* dy_bf16, const void* y_bf16, int32_t activation, int64_t n, void* out_bf16, void* stream);
 
 /* out_bf16[rows, ld_out] = [x (f32 [rows, in_dim], ldx) | 1.0 if ones_col | 0 ...]: the padded bf16 K operand of a first Dense layer. */
 int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim, int64_t ldx, void* out_bf16, int32_t ld_out, int32_t ones_col,
@@ -559,6 +564,37 @@ int rb_vocab_table_build(const uint64_t* vocab_keys, int64_t num_vocab, uint64_t
 /* ids_out[i] = id of tokens[i], 0 when absent (:61-64: OOV shares id 0 with the first vocabulary entry) */
 int rb_vocab_lookup(const uint64_t* tokens, int64_t n, const uint64_t* table_keys, const int32_t* table_vals,
                     int64_t capacity, int64_t* ids_out, void* stream);
+
+/* ---- DIN attention pooling ----------------------------------------------------------------
+ * dien/layers.py:34-59 LocalActivationUnit at its call site dien/model.py:42-53: the history rows are the concatenation
+ * of an item-table row and a category-table row (compute_flat_embedding, dien/model.py:14-19), mask = item id != 0
+ * (keras mask_zero, dien/model.py:11,43).  Only VALID positions get a feature row; they are numbered
+ * p = offsets[b] + (rank of l among sample b's valid positions).  The three Dense layers between rb_din_build_features
+ * and rb_din_pool_fwd run on rb_dense_fwd / rb_dense_head_fwd (sigmoid, sigmoid, none), their backward on
+ * rb_dense_head_bwd / rb_dense_act_bwd_bf16 / rb_dense_bwd_input / rb_dense_bwd_weight. */
+typedef struct rb_din_history {
+  const float* table0;  int64_t rows0;  int32_t D0;  const void* idx0;   /* item table, ids [B, L] */
+  const float* table1;  int64_t rows1;  int32_t D1;  const void* idx1;   /* category table or NULL / 0 / 0 / NULL */
+  int32_t idx_type;                                                     /* RB_I32 | RB_I64, both id arrays */
+  const void* mask;     int32_t mask_type;                              /* [B, L], != 0 = valid; NULL: idx0 != 0 */
+  int64_t B;            int32_t L;
+} rb_din_history;
+
+size_t rb_din_workspace_bytes(int64_t B);
+/* offsets int32[B + 1] (device): exclusive scan of the per-sample valid counts; offsets[B] = P, the number of feature rows */
+int rb_din_offsets(const rb_din_history* h, int32_t* offsets, void* ws, size_t ws_bytes, void* stream);
+/* x[p, :] = bf16([t_b | h_p | t_b - h_p | t_b * h_p | 0...]) for every valid position (dien/layers.py:48-49); target f32[B, E],
+ * E = D0 + D1; x bf16 [P, ldx], 4E <= ldx < 4E + 32 */
+int rb_din_build_features(const rb_din_history* h, const float* target, const int32_t* offsets, void* x_bf16, int64_t ldx, void* stream);
+/* rep[b, :] = sum over sample b's valid positions, in order of l, of w[p] * h_p   (dien/layers.py:53-57) */
+int rb_din_pool_fwd(const rb_din_history* h, const int32_t* offsets, const float* w, float* rep, void* stream);
+/* dw[p] = <d_rep[b], h_p> */
+int rb_din_pool_bwd_weights(const rb_din_history* h, const int32_t* offsets, const float* d_rep, float* dw, void* stream);
+/* dh[b, l, :] (f32 [B, L, E], written for valid positions; masked ones are zero-filled when zero_masked != 0, else left
+ * untouched: read them through RB_SCALE_MASKED) = dx[p, E:2E] - dx[p, 2E:3E] + dx[p, 3E:4E] * t_b + w[p] * d_rep[b];
+ * d_target[b, :] = sum_p dx[p, 0:E] + dx[p, 2E:3E] + dx[p, 3E:4E] * h_p */
+int rb_din_feature_bwd(const rb_din_history* h, const float* target, const int32_t* offsets, const void* dx_bf16, int64_t ldx,
+                       const float* w, const float* d_rep, float* dh, float* d_target, int32_t zero_masked, void* stream);
 
 #ifdef __cplusplus
 }

@@ -440,6 +440,65 @@ def masked_mean_backward(dout, mask):
     return (m[:, :, None] * per_bag[:, None, :]).astype(F32)
 
 
+# --------------------------------------------------------------------------------------
+# DIN attention pooling (dien/layers.py:34-59 at dien/model.py:42-53)
+# --------------------------------------------------------------------------------------
+
+def local_activation_unit(target, history, mask, layers, operand_dtype=None):
+    """dien/layers.py:42-59.  target f32[B, E] (the reference's [B, 1, E] squeezed), history f32[B, L, E], mask bool[B, L],
+    layers = [(W1[4E,80], b1), (W2[80,40], b2), (W3[40,1], b3)] (:37-39: sigmoid, sigmoid, none).
+    Returns (history_representation f32[B, E], cache).
+
+    operand_dtype='bf16' restates the rounding points of the CUDA path (csrc/din.cu + csrc/mlp.cu): the feature row
+    [t, h, t - h, t * h] is formed in fp32 and stored in bf16, every GEMM reads bf16 operands and accumulates in fp32, hidden
+    activations are stored in bf16; the Dense(1) logit, the mask and the weighted sum over fp32 history rows stay fp32."""
+    bf16 = operand_dtype == "bf16"
+    rnd = round_bf16 if bf16 else (lambda a: a)
+    B, L, E = history.shape
+    t = np.broadcast_to(target[:, None, :], (B, L, E))                                  # :47 tf.repeat
+    x = rnd(np.concatenate([t, history, (t - history).astype(F32), (t * history).astype(F32)], axis=-1).astype(F32))   # :48
+    (W1, b1), (W2, b2), (W3, b3) = layers
+    a1 = rnd(dense(x, rnd(W1), b1, "sigmoid"))                                           # :49
+    a2 = rnd(dense(a1, rnd(W2), b2, "sigmoid"))                                          # :50
+    w = dense(a2, rnd(W3), b3, None)                                                     # :51  [B, L, 1]
+    m = mask[..., None].astype(F32)                                                      # :52-53
+    w = (w * m).astype(F32)                                                              # :54
+    rep = np.zeros((B, E), dtype=F32)
+    for l in range(L):                                                                   # :55 weights^T . history, summed in position order
+        rep = (rep + (w[:, l, :] * history[:, l, :]).astype(F32)).astype(F32)
+    return rep, dict(target=target, history=history, mask=m, x=x, a1=a1, a2=a2, w=w, layers=layers, bf16=bf16)
+
+
+def local_activation_unit_backward(cache, d_rep):
+    """Hand-derived backward of local_activation_unit (pinned against torch autograd of the reference's own class in
+    tests/golden/din_attention.npz).  Returns d_target[B, E], d_history[B, L, E] (zero rows at masked positions — they still
+    appear in the IndexedSlices, like compute_his_average's) and [(dW, db)] x 3."""
+    rnd = round_bf16 if cache["bf16"] else (lambda a: a)
+    t, h, m, x, a1, a2, w = (cache[k] for k in ("target", "history", "mask", "x", "a1", "a2", "w"))
+    (W1, b1), (W2, b2), (W3, b3) = cache["layers"]
+    B, L, E = h.shape
+    dw = ((d_rep[:, None, :] * h).sum(axis=-1, keepdims=True, dtype=F32) * m).astype(F32)     # d/dw of w^T h, through `weights *= mask`
+    dW3 = np.einsum("blk,blo->ko", a2, dw).astype(F32)
+    db3 = dw.sum(axis=(0, 1), dtype=F32)
+    da2 = rnd((dw * rnd(W3)[None, None, :, 0]).astype(F32))
+    dz2 = rnd((da2 * a2 * (F32(1) - a2)).astype(F32))
+    dW2 = np.einsum("blk,blo->ko", a1, dz2).astype(F32)
+    db2 = dz2.sum(axis=(0, 1), dtype=F32)
+    da1 = rnd((dz2 @ rnd(W2).T).astype(F32))
+    dz1 = rnd((da1 * a1 * (F32(1) - a1)).astype(F32))
+    dW1 = np.einsum("blk,blo->ko", x, dz1).astype(F32)
+    db1 = dz1.sum(axis=(0, 1), dtype=F32)
+    dx = rnd((dz1 @ rnd(W1).T).astype(F32))
+    d0, d1, d2, d3 = dx[..., :E], dx[..., E:2 * E], dx[..., 2 * E:3 * E], dx[..., 3 * E:]
+    tb = t[:, None, :]
+    dh = ((((d1 - d2).astype(F32) + (d3 * tb).astype(F32)).astype(F32) + (w * d_rep[:, None, :]).astype(F32)).astype(F32) * m).astype(F32)
+    dt_pos = (((d0 + d2).astype(F32) + (d3 * h).astype(F32)).astype(F32) * m).astype(F32)
+    dt = np.zeros((B, E), dtype=F32)
+    for l in range(L):
+        dt = (dt + dt_pos[:, l, :]).astype(F32)
+    return dt, dh, [(dW1, db1), (dW2, db2), (dW3, db3)]
+
+
 def bag_pool(W, idx, mode="sum", mask=None):
     """Generic bag pooling used by the gather kernel's modes: sum / mean over L, or masked mean."""
     E = embedding_lookup(W, idx)

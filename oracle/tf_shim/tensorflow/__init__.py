@@ -47,6 +47,12 @@ def expand_dims(x, axis):
     return x.unsqueeze(axis)
 
 
+def repeat(x, repeats, axis):
+    """tf.repeat with one repeat count for the whole axis (dien/layers.py:47: repeats=[his_len] on a length-1 axis)."""
+    r = repeats[0] if isinstance(repeats, (list, tuple)) else repeats
+    return _t.repeat_interleave(x, int(r), dim=axis)
+
+
 def shape(x):
     return tuple(x.shape)
 

@@ -25,7 +25,7 @@ RB_I32, RB_I64 = 0, 1
 RB_F32, RB_BF16, RB_BF16_ONES = 0, 1, 2
 RB_POOL_SUM, RB_POOL_MEAN, RB_POOL_MASKED_MEAN = 1, 2, 3
 RB_OPT_SGD, RB_OPT_ADAGRAD, RB_OPT_ADAM_LAZY, RB_OPT_ADAM_TF_DENSE = 0, 1, 2, 3
-RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN = 0, 1, 2
+RB_SCALE_NONE, RB_SCALE_MEAN, RB_SCALE_MASKED_MEAN, RB_SCALE_MASKED = 0, 1, 2, 3
 RB_ROW_CACHE_L2, RB_ROW_CACHE_L1, RB_ROW_CACHE_AUTO = 0, 1, 2
 ROW_CACHE_ENUM = {False: RB_ROW_CACHE_L2, True: RB_ROW_CACHE_L1, "auto": RB_ROW_CACHE_AUTO, None: RB_ROW_CACHE_L2}
 RB_ACT_NONE, RB_ACT_RELU, RB_ACT_SIGMOID = 0, 1, 2
@@ -34,12 +34,18 @@ ACT_ENUM = {None: RB_ACT_NONE, "relu": RB_ACT_RELU, "sigmoid": RB_ACT_SIGMOID}
 OPTIMIZER_ENUM = {"sgd": RB_OPT_SGD, "adagrad": RB_OPT_ADAGRAD, "adam_lazy": RB_OPT_ADAM_LAZY,
                   "adam_tf_dense": RB_OPT_ADAM_TF_DENSE}
 POOL_ENUM = {"sum": RB_POOL_SUM, "mean": RB_POOL_MEAN, "masked_mean": RB_POOL_MASKED_MEAN}
-SCALE_ENUM = {"none": RB_SCALE_NONE, "mean": RB_SCALE_MEAN, "masked_mean": RB_SCALE_MASKED_MEAN}
+SCALE_ENUM = {"none": RB_SCALE_NONE, "mean": RB_SCALE_MEAN, "masked_mean": RB_SCALE_MASKED_MEAN, "masked": RB_SCALE_MASKED}
 
 
 class RbOptParams(C.Structure):
     _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_float), ("beta_1", C.c_float),
                 ("beta_2", C.c_float), ("epsilon", C.c_float), ("alpha_t_dev", C.c_void_p)]
+
+
+class RbDinHistory(C.Structure):
+    _fields_ = [("table0", C.c_void_p), ("rows0", C.c_int64), ("D0", C.c_int32), ("idx0", C.c_void_p),
+                ("table1", C.c_void_p), ("rows1", C.c_int64), ("D1", C.c_int32), ("idx1", C.c_void_p),
+                ("idx_type", C.c_int32), ("mask", C.c_void_p), ("mask_type", C.c_int32), ("B", C.c_int64), ("L", C.c_int32)]
 
 
 class RbGradSource(C.Structure):
@@ -117,6 +123,13 @@ SIGNATURES = {
     "rb_dense_head_bwd_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_dense_head_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
     "rb_dense_act_bwd": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "rb_dense_act_bwd_bf16": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "rb_din_workspace_bytes": (C.c_size_t, [_i64]),
+    "rb_din_offsets": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, C.c_size_t, _p]),
+    "rb_din_build_features": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, _p, _i64, _p]),
+    "rb_din_pool_fwd": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, _p, _p]),
+    "rb_din_pool_bwd_weights": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, _p, _p]),
+    "rb_din_feature_bwd": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, _p, _i64, _p, _p, _p, _p, _i32, _p]),
     "rb_dense_pack_input": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i32, _p]),
     "rb_dense_debug_stats": (C.c_int, [_p]),
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),

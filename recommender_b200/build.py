@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librecsys_b200.so")
 STAMP = os.path.join(LIB_DIR, "librecsys_b200.stamp")
-SOURCES = ["api.cu", "gather.cu", "interaction.cu", "sparse_update.cu", "exchange.cu", "dense.cu", "mlp.cu", "p2p.cu", "criteo_input.cu"]
+SOURCES = ["api.cu", "gather.cu", "interaction.cu", "sparse_update.cu", "exchange.cu", "dense.cu", "mlp.cu", "p2p.cu", "criteo_input.cu", "din.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -748,7 +748,7 @@ head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, i
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * per, r1 = min(r0 + per, rows);
     for (int64_t r = r0 + rl; r < r1; r += row_lanes) {
       float dz = dout[r];
-      const float o = out[r];
+      const float o = act != RB_ACT_NONE ? out[r] : 0.f;      // a head without activation has no forward output to read
       if (act == RB_ACT_SIGMOID) dz = dz * o * (1.0f - o);
       else if (act == RB_ACT_RELU) dz = o > 0.f ? dz : 0.f;
       if (vc == 0) db += dz;
@@ -824,6 +824,29 @@ act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int ac
   }
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// the same for a hidden layer whose output and incoming gradient are bf16 (dien/layers.py:37-38): 8 elements per thread
+__global__ void __launch_bounds__(256)
+act_bwd_bf16_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, int act, int64_t n8, uint4* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 d = __ldcs(dy + i);
+  const uint4 o = act != RB_ACT_NONE ? __ldcs(y + i) : make_uint4(0, 0, 0, 0);
+  const uint32_t dv[4] = {d.x, d.y, d.z, d.w}, ov[4] = {o.x, o.y, o.z, o.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float g0 = __uint_as_float(dv[k] << 16), g1 = __uint_as_float(dv[k] & 0xFFFF0000u);
+    if (act != RB_ACT_NONE) {
+      const float y0 = __uint_as_float(ov[k] << 16), y1 = __uint_as_float(ov[k] & 0xFFFF0000u);
+      g0 = act == RB_ACT_RELU ? (y0 > 0.f ? g0 : 0.f) : __fmul_rn(__fmul_rn(g0, y0), __fsub_rn(1.0f, y0));
+      g1 = act == RB_ACT_RELU ? (y1 > 0.f ? g1 : 0.f) : __fmul_rn(__fmul_rn(g1, y1), __fsub_rn(1.0f, y1));
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
+    r[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  out[i] = make_uint4(r[0], r[1], r[2], r[3]);
 }
 
 // x f32[rows, in_dim] -> bf16[rows, ld] = [x | 1 | 0 ...]: the K operand of the first Dense layer; the ones column makes
@@ -1204,6 +1227,18 @@ extern "C" int rb_dense_act_bwd(const float* dy, const float* y, int32_t activat
   RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
   act_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, activation, n / 4, static_cast<__nv_bfloat16*>(out_bf16));
   RB_LAUNCH_CHECK("act_bwd_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_dense_act_bwd_bf16(const void* dy_bf16, const void* y_bf16, int32_t activation, int64_t n, void* out_bf16, void* stream) {
+  RB_CHECK_ARG(dy_bf16 != nullptr && out_bf16 != nullptr && (activation == RB_ACT_NONE || y_bf16 != nullptr), RB_ERR_ARG, "a required pointer is null");
+  RB_CHECK_ARG(n > 0 && n % 8 == 0, RB_ERR_SHAPE, "act_bwd_bf16: element count must be a positive multiple of 8");
+  RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0,
+               RB_ERR_ALIGN, "act_bwd_bf16: pointers not 16-byte aligned");
+  RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
+  act_bwd_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy_bf16), static_cast<const uint4*>(y_bf16), activation, n / 8, static_cast<uint4*>(out_bf16));
+  RB_LAUNCH_CHECK("act_bwd_bf16_kernel");
   return RB_OK;
 }
 

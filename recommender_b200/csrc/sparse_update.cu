@@ -132,6 +132,10 @@ __device__ __forceinline__ void finish_grad(const GradGroupsDev& gg, const GradP
     const float denom = __ldg(g.count + q.b);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = keep ? __fdiv_rn(r.v[i], denom) : 0.f;
+  } else if (g.scale_mode == RB_SCALE_MASKED) {   // rows of masked positions were never written: whatever was read is dropped
+    const bool keep = load_raw_index(g.mask_idx, g.is64, q.p) != 0;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = keep ? r.v[i] : 0.f;
   }
   if (g.fm_g != nullptr) {  // dE += g_fm[b] * (s[b,:] - W[row,:])      (ctr/model.py:21-23 backward)
     const float gb = __ldg(g.fm_g + q.b);
@@ -767,7 +771,7 @@ static WsLayout ws_layout(int64_t n, int D, int64_t rows) {
 
 static int fill_grad_src(GradSrcDev* d, const rb_grad_source* g, int L, int idx_type, const void* idx, int vec) {
   RB_CHECK_ARG(g != nullptr && g->num_src >= 1 && g->num_src <= RB_MAX_GRAD_SOURCES, RB_ERR_ARG, "grad source count out of range");
-  RB_CHECK_ARG(g->scale_mode >= RB_SCALE_NONE && g->scale_mode <= RB_SCALE_MASKED_MEAN, RB_ERR_ARG, "bad scale mode");
+  RB_CHECK_ARG(g->scale_mode >= RB_SCALE_NONE && g->scale_mode <= RB_SCALE_MASKED, RB_ERR_ARG, "bad scale mode");
   d->num_src = g->num_src;
   d->scale_mode = g->scale_mode;
   d->L = L;
@@ -909,7 +913,7 @@ static int sort_groups(const rb_lookup_group* groups, int num_groups, int64_t ro
     if (g.n > 0) {
       IndexMap m = make_index_map(g.idx, g.idx_type, g.field_row_offset, g.hash_mod, rows, g.L);
       const void* mask = nullptr;
-      if (drop_masked && g.grad.scale_mode == RB_SCALE_MASKED_MEAN && rows < 0xFFFFFFFFll) {
+      if (drop_masked && (g.grad.scale_mode == RB_SCALE_MASKED_MEAN || g.grad.scale_mode == RB_SCALE_MASKED) && rows < 0xFFFFFFFFll) {
         mask = g.grad.mask_idx != nullptr ? g.grad.mask_idx : g.idx;
         dropped = true;
       }

@@ -615,6 +615,109 @@ def dense_act_bwd(dy, y, activation):
     return out
 
 
+def dense_act_bwd_bf16(dy, y, activation):
+    """bf16(dy * activation'(y)) for a hidden layer kept in bf16 (rb_dense_act_bwd_bf16); dy, y bf16 of the same contiguous shape."""
+    _need_cuda(dy, y)
+    if dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or not dy.is_contiguous() or not y.is_contiguous() or dy.shape != y.shape:
+        raise TypeError("act_bwd_bf16 takes two contiguous bfloat16 tensors of one shape")
+    out = torch.empty_like(dy)
+    check(lib.rb_dense_act_bwd_bf16(_ptr(dy), _ptr(y), _lib.ACT_ENUM[activation], dy.numel(), _ptr(out), _stream()), "rb_dense_act_bwd_bf16")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# DIN attention pooling (SURVEY §8f rank 4; csrc/din.cu)
+# --------------------------------------------------------------------------------------------
+
+class DinHistory:
+    """Python mirror of rb_din_history: the behaviour history as ids into an item table and (optionally) a category
+    table, whose rows concatenate to the E-wide history row (dien/model.py:14-19); mask = `mask` != 0, default item id != 0."""
+
+    def __init__(self, table0, idx0, table1=None, idx1=None, mask=None):
+        _need_cuda(table0, idx0, table1, idx1, mask)
+        _f32c(table0, "table0")
+        self.idx0 = idx0.contiguous()
+        if self.idx0.dim() != 2:
+            raise ValueError("history ids must be [B, L]")
+        self.table0, self.table1 = table0, table1
+        self.idx1 = None if idx1 is None else idx1.contiguous()
+        if (table1 is None) != (idx1 is None):
+            raise ValueError("give the second table together with its ids")
+        if table1 is not None:
+            _f32c(table1, "table1")
+            if self.idx1.shape != self.idx0.shape or self.idx1.dtype != self.idx0.dtype:
+                raise ValueError("both id arrays must share shape and dtype")
+        self.mask = None if mask is None else mask.contiguous()
+        if self.mask is not None and (self.mask.shape != self.idx0.shape or self.mask.dtype not in (torch.int32, torch.int64)):
+            raise ValueError("mask must be an int32 / int64 array of the ids' shape (nonzero = valid)")
+        self.B, self.L = self.idx0.shape
+        self.E = table0.shape[1] + (0 if table1 is None else table1.shape[1])
+
+    def to_c(self) -> _lib.RbDinHistory:
+        h = _lib.RbDinHistory()
+        h.table0, h.rows0, h.D0, h.idx0 = self.table0.data_ptr(), self.table0.shape[0], self.table0.shape[1], self.idx0.data_ptr()
+        if self.table1 is not None:
+            h.table1, h.rows1, h.D1, h.idx1 = self.table1.data_ptr(), self.table1.shape[0], self.table1.shape[1], self.idx1.data_ptr()
+        else:
+            h.table1, h.rows1, h.D1, h.idx1 = None, 0, 0, None
+        h.idx_type = _idx(self.idx0)
+        h.mask = _ptr(self.mask)
+        h.mask_type = _idx(self.mask) if self.mask is not None else _lib.RB_I64
+        h.B, h.L = self.B, self.L
+        return h
+
+
+def din_offsets(h: DinHistory) -> torch.Tensor:
+    """int32 [B + 1]: exclusive scan of the per-sample valid counts (rb_din_offsets); offsets[B] = number of feature rows."""
+    off = torch.empty(h.B + 1, dtype=torch.int32, device=h.idx0.device)
+    ws = _workspace(max(lib.rb_din_workspace_bytes(max(h.B, 1)), 256), h.idx0.device)
+    c = h.to_c()
+    check(lib.rb_din_offsets(C.byref(c), _ptr(off), _ptr(ws), ws.numel(), _stream()), "rb_din_offsets")
+    return off
+
+
+def din_build_features(h: DinHistory, target, offsets, P: int, ldx: int) -> torch.Tensor:
+    """bf16 [max(P, 1), ldx]: [t | h | t - h | t * h | 0...] per valid position (rb_din_build_features)."""
+    _need_cuda(target, offsets)
+    _f32c(target, "target")
+    x = torch.empty(max(P, 1), ldx, dtype=torch.bfloat16, device=target.device)
+    c = h.to_c()
+    check(lib.rb_din_build_features(C.byref(c), _ptr(target), _ptr(offsets), _ptr(x), ldx, _stream()), "rb_din_build_features")
+    return x
+
+
+def din_pool_fwd(h: DinHistory, offsets, w) -> torch.Tensor:
+    """rep f32 [B, E] = sum_p w[p] * h_p (rb_din_pool_fwd)."""
+    _need_cuda(offsets, w)
+    rep = torch.empty(h.B, h.E, dtype=torch.float32, device=w.device)
+    c = h.to_c()
+    check(lib.rb_din_pool_fwd(C.byref(c), _ptr(offsets), _ptr(_f32c(w, "w")), _ptr(rep), _stream()), "rb_din_pool_fwd")
+    return rep
+
+
+def din_pool_bwd_weights(h: DinHistory, offsets, d_rep, P: int) -> torch.Tensor:
+    """dw f32 [max(P, 1)] = <d_rep[b], h_p> (rb_din_pool_bwd_weights)."""
+    _need_cuda(offsets, d_rep)
+    dw = torch.empty(max(P, 1), dtype=torch.float32, device=d_rep.device)
+    c = h.to_c()
+    check(lib.rb_din_pool_bwd_weights(C.byref(c), _ptr(offsets), _ptr(_f32c(d_rep, "d_rep")), _ptr(dw), _stream()), "rb_din_pool_bwd_weights")
+    return dw
+
+
+def din_feature_bwd(h: DinHistory, target, offsets, dx, w, d_rep, zero_masked: bool = False):
+    """(dh f32 [B, L, E] — rows of valid positions; masked rows zero-filled only when zero_masked — , d_target f32 [B, E])
+    (rb_din_feature_bwd)."""
+    _need_cuda(target, offsets, dx, w, d_rep)
+    if dx.dtype != torch.bfloat16 or dx.dim() != 2 or dx.stride(1) != 1:
+        raise TypeError("dx must be a bfloat16 matrix with unit inner stride")
+    dh = torch.empty(h.B, h.L, h.E, dtype=torch.float32, device=dx.device)
+    dt = torch.empty(h.B, h.E, dtype=torch.float32, device=dx.device)
+    c = h.to_c()
+    check(lib.rb_din_feature_bwd(C.byref(c), _ptr(_f32c(target, "target")), _ptr(offsets), _ptr(dx), dx.stride(0), _ptr(_f32c(w, "w")),
+                                 _ptr(_f32c(d_rep, "d_rep")), _ptr(dh), _ptr(dt), int(bool(zero_masked)), _stream()), "rb_din_feature_bwd")
+    return dh, dt
+
+
 def dense_pack_input(x, ld: int, ones_col: bool = True):
     """bf16 [rows, ld] = [x | 1 | 0...] from f32 x [rows, in_dim] (rb_dense_pack_input)."""
     _need_cuda(x)

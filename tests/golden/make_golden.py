@@ -179,6 +179,49 @@ def golden_masked_mean(B=16, L=100, V_item=500, V_cat=40, D=18, seed=11):
                 dW_item=np_(model.item_embedding.embeddings.grad), dW_cat=np_(model.cat_embedding.embeddings.grad))
 
 
+def golden_din_attention(B=16, L=20, V_item=500, V_cat=40, D=18, seed=17):
+    """DIN's attention pooling from the reference's own classes: compute_flat_embedding (dien/model.py:14-19), the
+    mask_zero mask (dien/model.py:43) and LocalActivationUnit (dien/layers.py:34-59) as DIN.call wires them
+    (dien/model.py:42-50).  Reference D = 18 + 18 (dien/train.py:91-92), so E = 36 and the attention MLP reads 144 columns."""
+    layers_mod, model_mod = import_ref("dien", "layers", "model")
+    rng = np.random.default_rng(seed)
+    W_item, W_cat = O.init_table(rng, V_item, D), O.init_table(rng, V_cat, D)
+    lengths = rng.integers(1, L + 1, size=B)
+    lengths[0], lengths[1] = L, 1
+    item = np.zeros((B, L), dtype=np.int32)
+    cat = np.zeros((B, L), dtype=np.int32)
+    for b, n in enumerate(lengths):     # post-padding with zeros (dien/data_loader.py:44,48)
+        item[b, :n] = rng.integers(1, V_item, size=n)
+        cat[b, :n] = rng.integers(1, V_cat, size=n)
+    item[2, 0] = 0                      # a hole inside a history: the mask is item != 0 wherever it occurs
+    t_item = rng.integers(1, V_item, size=(B, 1)).astype(np.int32)
+    t_cat = rng.integers(1, V_cat, size=(B, 1)).astype(np.int32)
+    t_item[3, 0] = item[3, 0]           # a target that also occurs in its own history: two uses of one table row
+    model = model_mod.DIN(item_vocab_size=V_item, item_embedding_size=D, cat_vocab_size=V_cat, cat_embedding_size=D, mlp_units=[8, 1])
+    model.item_embedding.embeddings = torch.tensor(W_item, requires_grad=True)
+    model.cat_embedding.embeddings = torch.tensor(W_cat, requires_grad=True)
+    unit = model.local_activation_unit
+    mask = model.item_embedding.compute_mask(torch.tensor(item))                                    # dien/model.py:43
+    target = model.compute_flat_embedding((torch.tensor(t_item), torch.tensor(t_cat)))              # :44-45  [B, 1, E]
+    his = model.compute_flat_embedding((torch.tensor(item), torch.tensor(cat)))                     # :46-47  [B, L, E]
+    unit((target, his), mask=mask)                                                                  # builds the Dense layers
+    att = O.init_mlp(rng, 4 * 2 * D, [80, 40, 1])
+    att = [(W, rng.normal(0, 0.05, size=b.shape).astype(np.float32)) for W, b in att]               # non-zero biases
+    set_dense([unit.layer_1, unit.layer_2, unit.layer_3], att)
+    target.retain_grad()
+    his.retain_grad()
+    rep = unit((target, his), mask=mask)                                                            # :48
+    d_rep = rng.normal(0, 1e-1, size=tuple(rep.shape)).astype(np.float32)
+    rep.backward(torch.tensor(d_rep))
+    out = dict(item=item, cat=cat, t_item=t_item, t_cat=t_cat, W_item=W_item, W_cat=W_cat, rep=np_(rep), d_rep=d_rep,
+               d_target=np_(target.grad)[:, 0, :], d_his=np_(his.grad), dW_item=np_(model.item_embedding.embeddings.grad),
+               dW_cat=np_(model.cat_embedding.embeddings.grad))
+    for i, (layer, (W, b)) in enumerate(zip([unit.layer_1, unit.layer_2, unit.layer_3], att)):
+        out[f"att_W{i}"], out[f"att_b{i}"] = W, b
+        out[f"att_dW{i}"], out[f"att_db{i}"] = np_(layer.kernel.grad), np_(layer.bias.grad)
+    return out
+
+
 def golden_esmm(B=32, D=18, seed=13):
     """esmm/esmm.py:15-27 with two consumers (ctr and cvr towers) of one concat embedding."""
     (esmm_mod,) = import_ref("esmm", "esmm")
@@ -205,9 +248,12 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     jobs = dict(dlrm_small=golden_dlrm, deepfm_small=golden_deepfm, dot_interaction=golden_dot_interaction,
-                masked_mean=golden_masked_mean, esmm_small=golden_esmm,
+                masked_mean=golden_masked_mean, esmm_small=golden_esmm, din_attention=golden_din_attention,
                 dlrm_uniform=lambda: golden_dlrm(B=32, D=64, V=4096, bottom=(32, 64), top=(16, 1), seed=5, dist="uniform"))
+    only = sys.argv[1:]          # python make_golden.py [name ...]: regenerate just these fixtures
     for name, fn in jobs.items():
+        if only and name not in only:
+            continue
         arrays = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **arrays)

@@ -281,3 +281,45 @@ def test_bf16_operand_mlp_mode_restates_the_cuda_rounding_points():
     assert np.abs(prob - ref).max() <= 2.0 ** -6
     g = O.dlrm_backward(p, c, O.bce_clipped(prob, lab)[1], operand_dtype="bf16", mlp_dtype="bf16")
     assert g["dE"].shape == (32, 26, 16) and np.isfinite(g["dE"]).all()
+
+
+def _din_case(g):
+    his = O.compute_flat_embedding(g["W_item"], g["W_cat"], g["item"], g["cat"])
+    tgt = O.compute_flat_embedding(g["W_item"], g["W_cat"], g["t_item"], g["t_cat"])[:, 0, :]
+    layers = [(g[f"att_W{i}"], g[f"att_b{i}"]) for i in range(3)]
+    return tgt, his, g["item"] != 0, layers
+
+
+def test_din_local_activation_unit(golden):
+    """dien/layers.py:34-59 as DIN.call wires it (dien/model.py:42-50): the oracle's forward and hand-derived backward against
+    torch autograd of the reference's own class (tests/golden/make_golden.py::golden_din_attention)."""
+    g = golden("din_attention")
+    tgt, his, mask, layers = _din_case(g)
+    rep, cache = O.local_activation_unit(tgt, his, mask, layers)
+    np.testing.assert_allclose(rep, g["rep"], rtol=1e-5, atol=1e-7)
+    dt, dh, grads = O.local_activation_unit_backward(cache, g["d_rep"])
+    np.testing.assert_allclose(dt, g["d_target"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(dh, g["d_his"], rtol=1e-4, atol=1e-7)
+    assert (dh[~mask] == 0).all()
+    for i, (dW, db) in enumerate(grads):
+        np.testing.assert_allclose(dW, g[f"att_dW{i}"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(db, g[f"att_db{i}"], rtol=1e-4, atol=1e-6)
+    # table gradients: history rows + the target row, concatenated IndexedSlices summed per row (SURVEY A.1-A.2)
+    D = g["W_item"].shape[1]
+    for name, W, h_idx, t_idx, c0 in (("dW_item", g["W_item"], g["item"], g["t_item"], 0), ("dW_cat", g["W_cat"], g["cat"], g["t_cat"], D)):
+        dense = np.zeros_like(W)
+        np.add.at(dense, h_idx.reshape(-1), dh[:, :, c0:c0 + D].reshape(-1, D))
+        np.add.at(dense, t_idx.reshape(-1), dt[:, c0:c0 + D])
+        np.testing.assert_allclose(dense, g[name], rtol=1e-4, atol=1e-7)
+
+
+def test_din_bf16_operand_mode_stays_near_fp32(golden):
+    """The rounding points the CUDA path uses (bf16 feature rows, kernels and hidden activations; fp32 accumulation, logit and
+    weighted sum) move the result by bf16-level amounts only."""
+    g = golden("din_attention")
+    tgt, his, mask, layers = _din_case(g)
+    rep16, cache = O.local_activation_unit(tgt, his, mask, layers, operand_dtype="bf16")
+    assert np.abs(rep16 - g["rep"]).max() <= 3e-2 * np.abs(g["rep"]).max()
+    dt, dh, grads = O.local_activation_unit_backward(cache, g["d_rep"])
+    assert np.abs(dh - g["d_his"]).max() <= 6e-2 * np.abs(g["d_his"]).max()
+    assert np.abs(dt - g["d_target"]).max() <= 5e-2 * np.abs(g["d_target"]).max()
