@@ -332,6 +332,42 @@ def extra_lines(args, dev, model, graphed_step, peak):
                                         samples_per_s_fwd_bwd=B / (ms_f + ms_b) * 1e3)
     del wt, mh, vh, hist
 
+    # SURVEY §8f rank 4 at BASELINE config 4's shape: DIN attention pooling (dien/layers.py:34-59) over a behaviour history of
+    # 100 positions, item + category tables of D = 32 each (E = 64), ~50 % trailing pads.  One step = target + history lookups,
+    # the 4E -> 80 -> 40 -> 1 attention MLP on the valid positions (tcgen05 Dense kernels), weighted pooling, the whole
+    # backward and one sparse Adam update per table.
+    from recommender_b200.din import DIN
+    Vi, Vc, Dd = 400_000, 2_000, 32
+    g = torch.Generator(device=dev).manual_seed(4)
+    din = DIN(Vi, Dd, Vc, Dd, device=dev, generator=g)
+    lens = torch.randint(1, Lh + 1, (B, 1), device=dev, generator=g)
+    hi = torch.randint(1, Vi, (B, Lh), device=dev, generator=g)
+    hi = torch.where(torch.arange(Lh, device=dev)[None] < lens, hi, torch.zeros_like(hi))
+    hc = torch.where(hi != 0, hi % (Vc - 1) + 1, torch.zeros_like(hi))
+    ti = torch.randint(1, Vi, (B, 1), device=dev, generator=g)
+    din_in = dict(target_item=ti, target_cat=ti % (Vc - 1) + 1, pos_his_item=hi, pos_his_cat=hc)
+    d_out = torch.randn(B, 4 * Dd, device=dev, generator=g) * 1e-3
+    din_opt = Adam()
+    t_fwd = [0.0]
+
+    def din_step(i):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = din(din_in)
+        e1.record()
+        o.backward(d_out)
+        din_opt.apply_gradients(din)
+        t_fwd[0] = (e0, e1)
+    ms_d = _time_loop(din_step, 8)
+    torch.cuda.synchronize()
+    valid_d = int((hi != 0).sum())
+    flop = 2 * valid_d * (8 * Dd * 80 + 80 * 40 + 40) * 3      # forward + input-gradient + weight-gradient products
+    out["din_cfg4_attention"] = dict(batch=B, history=Lh, emb_dim=2 * Dd, valid_positions=valid_d, ms_per_step=ms_d,
+                                     fwd_ms=t_fwd[0][0].elapsed_time(t_fwd[0][1]), samples_per_s=B / ms_d * 1e3,
+                                     positions_per_s=valid_d / ms_d * 1e3, attention_mlp_tflops=flop / ms_d / 1e9,
+                                     note="eager (one host read-back of the valid-position count per step sizes the GEMMs)")
+    del din, din_opt, hi, hc
+
     # BASELINE config 5: 26 tables (vocab sizes cycled from esmm/train.py:197-215), D = 32, bag size 1, gradients of 2 (ESMM) and
     # 10 (MMOE) consumers added inside the scatter (esmm/esmm.py:15-24).  The tables live back to back in ONE tensor
     # (layers.Embedding(table_rows=...)): the 26 lookups + concat are one rb_gather_fwd over [B, 26] ids with per-field row

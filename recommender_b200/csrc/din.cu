@@ -43,10 +43,46 @@ __device__ __forceinline__ bool valid_at(const Tables& t, int64_t p) {
   return t.mask != nullptr ? load_raw_index(t.mask, t.mask_is64, p) != 0 : load_raw_index(t.idx[0], t.is64, p) != 0;
 }
 
-// column c of the history row at ids (i0, i1); out-of-range ids read as zeros (TF's GPU gather)
-__device__ __forceinline__ float hist_col(const Tables& t, int64_t i0, int64_t i1, int c) {
-  if (c < t.D[0]) return (i0 >= 0 && i0 < t.rows[0]) ? __ldg(t.tab[0] + i0 * t.D[0] + c) : 0.f;
-  return (i1 >= 0 && i1 < t.rows[1]) ? __ldg(t.tab[1] + i1 * t.D[1] + (c - t.D[0])) : 0.f;
+// VEC consecutive columns starting at c of the history row at ids (i0, i1); out-of-range ids read as zeros (TF's GPU gather,
+// SURVEY A.6).  VEC == 2 needs even D[0], D[1] (8-byte aligned pairs that never straddle the two tables).
+template <int VEC, int COLS>
+struct HRow {
+  float v[COLS][VEC];
+};
+constexpr int kUnroll = 4;      // history rows in flight per warp: these kernels wait on HBM latency, not on bandwidth
+
+template <int VEC>
+__device__ __forceinline__ void hist_cols(const Tables& t, int64_t i0, int64_t i1, int c, float (&out)[VEC]) {
+  const float* src = nullptr;
+  if (c < t.D[0]) {
+    if (i0 >= 0 && i0 < t.rows[0]) src = t.tab[0] + i0 * t.D[0] + c;
+  } else if (i1 >= 0 && i1 < t.rows[1]) {
+    src = t.tab[1] + i1 * t.D[1] + (c - t.D[0]);
+  }
+  if (src == nullptr) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) out[k] = 0.f;
+  } else if constexpr (VEC == 2) {
+    const float2 x = __ldg(reinterpret_cast<const float2*>(src));
+    out[0] = x.x;
+    out[1] = x.y;
+  } else {
+    out[0] = __ldg(src);
+  }
+}
+
+template <int VEC, int COLS>
+__device__ __forceinline__ HRow<VEC, COLS> load_hist(const Tables& t, int64_t i0, int64_t i1, int lane) {
+  HRow<VEC, COLS> h;
+#pragma unroll
+  for (int j = 0; j < COLS; ++j) {
+    const int c = (lane + 32 * j) * VEC;
+    if (c < t.E) hist_cols<VEC>(t, i0, i1, c, h.v[j]);
+    else
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) h.v[j][k] = 0.f;
+  }
+  return h;
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) count_valid_kernel(Tables t, int32_t* __restrict__ counts) {
@@ -62,8 +98,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) count_valid_kernel(Tables
   if (lane == 0) counts[b] = n;
 }
 
-// Walks the valid positions of sample b in order of l and calls f(l, p, i0, i1) with all 32 lanes converged.
-template <class F>
+// Walks the valid positions of sample b in order of l and calls f(l, p, h) with all 32 lanes converged, h = this lane's
+// columns of the position's history row.  The rows of kUnroll positions are requested together before the first is used.
+template <int VEC, int COLS, class F>
 __device__ __forceinline__ void for_valid_positions(const Tables& t, int64_t b, int lane, int32_t p0, F&& f) {
   int32_t p = p0;
   for (int l0 = 0; l0 < t.L; l0 += 32) {
@@ -75,16 +112,33 @@ __device__ __forceinline__ void for_valid_positions(const Tables& t, int64_t b, 
     const int64_t my1 = (in && t.idx[1] != nullptr) ? load_raw_index(t.idx[1], t.is64, q) : 0;
     unsigned m = __ballot_sync(0xffffffffu, v);
     while (m != 0) {
-      const int k = __ffs(m) - 1;
-      m &= m - 1;
-      const int64_t i0 = __shfl_sync(0xffffffffu, my0, k);
-      const int64_t i1 = __shfl_sync(0xffffffffu, my1, k);
-      f(l0 + k, p, i0, i1);
-      ++p;
+      int ks[kUnroll];
+      HRow<VEC, COLS> rows[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        ks[u] = m != 0 ? __ffs(m) - 1 : -1;
+        if (ks[u] >= 0) {
+          m &= m - 1;
+          rows[u] = load_hist<VEC, COLS>(t, __shfl_sync(0xffffffffu, my0, ks[u]), __shfl_sync(0xffffffffu, my1, ks[u]), lane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (ks[u] >= 0) {
+          f(l0 + ks[u], p, rows[u]);
+          ++p;
+        }
+      }
     }
   }
 }
 
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int VEC, int COLS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 build_features_kernel(Tables t, const float* __restrict__ target, const int32_t* __restrict__ offsets, __nv_bfloat16* __restrict__ X,
                       int64_t ldx) {
@@ -92,86 +146,94 @@ build_features_kernel(Tables t, const float* __restrict__ target, const int32_t*
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + threadIdx.x / 32;
   if (b >= t.B) return;
   const int E = t.E;
-  float tv[kMaxColsPerLane];
+  float tv[COLS][VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) {
-    const int c = lane + 32 * j;
-    tv[j] = c < E ? __ldg(target + b * E + c) : 0.f;
-  }
-  const int pad = static_cast<int>(ldx) - 4 * E;
-  for_valid_positions(t, b, lane, offsets[b], [&](int, int32_t p, int64_t i0, int64_t i1) {
-    __nv_bfloat16* row = X + static_cast<int64_t>(p) * ldx;
-    float hv[kMaxColsPerLane];
+  for (int j = 0; j < COLS; ++j)
 #pragma unroll
-    for (int j = 0; j < kMaxColsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      hv[j] = c < E ? hist_col(t, i0, i1, c) : 0.f;
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (lane + 32 * j) * VEC + k;
+      tv[j][k] = c < E ? __ldg(target + b * E + c) : 0.f;
     }
+  const int pad = static_cast<int>(ldx) - 4 * E;
+  for_valid_positions<VEC, COLS>(t, b, lane, offsets[b], [&](int, int32_t p, const HRow<VEC, COLS>& h) {
+    __nv_bfloat16* row = X + static_cast<int64_t>(p) * ldx;
 #pragma unroll
-    for (int j = 0; j < kMaxColsPerLane; ++j) {
-      const int c = lane + 32 * j;
+    for (int j = 0; j < COLS; ++j) {
+      const int c = (lane + 32 * j) * VEC;
       if (c < E) {
-        row[c] = __float2bfloat16_rn(tv[j]);
-        row[E + c] = __float2bfloat16_rn(hv[j]);
-        row[2 * E + c] = __float2bfloat16_rn(__fsub_rn(tv[j], hv[j]));
-        row[3 * E + c] = __float2bfloat16_rn(__fmul_rn(tv[j], hv[j]));
+        if constexpr (VEC == 2) {
+          *reinterpret_cast<uint32_t*>(row + c) = pack2(tv[j][0], tv[j][1]);
+          *reinterpret_cast<uint32_t*>(row + E + c) = pack2(h.v[j][0], h.v[j][1]);
+          *reinterpret_cast<uint32_t*>(row + 2 * E + c) = pack2(__fsub_rn(tv[j][0], h.v[j][0]), __fsub_rn(tv[j][1], h.v[j][1]));
+          *reinterpret_cast<uint32_t*>(row + 3 * E + c) = pack2(__fmul_rn(tv[j][0], h.v[j][0]), __fmul_rn(tv[j][1], h.v[j][1]));
+        } else {
+          row[c] = __float2bfloat16_rn(tv[j][0]);
+          row[E + c] = __float2bfloat16_rn(h.v[j][0]);
+          row[2 * E + c] = __float2bfloat16_rn(__fsub_rn(tv[j][0], h.v[j][0]));
+          row[3 * E + c] = __float2bfloat16_rn(__fmul_rn(tv[j][0], h.v[j][0]));
+        }
       }
     }
     if (lane < pad) row[4 * E + lane] = __float2bfloat16_rn(0.f);
   });
 }
 
+template <int VEC, int COLS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pool_fwd_kernel(Tables t, const int32_t* __restrict__ offsets, const float* __restrict__ w, float* __restrict__ rep) {
   const int lane = threadIdx.x % 32;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + threadIdx.x / 32;
   if (b >= t.B) return;
   const int E = t.E;
-  float acc[kMaxColsPerLane];
+  float acc[COLS][VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) acc[j] = 0.f;
-  for_valid_positions(t, b, lane, offsets[b], [&](int, int32_t p, int64_t i0, int64_t i1) {
+  for (int j = 0; j < COLS; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[j][k] = 0.f;
+  for_valid_positions<VEC, COLS>(t, b, lane, offsets[b], [&](int, int32_t p, const HRow<VEC, COLS>& h) {
     const float wp = __ldg(w + p);
 #pragma unroll
-    for (int j = 0; j < kMaxColsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      if (c < E) acc[j] = __fadd_rn(acc[j], __fmul_rn(wp, hist_col(t, i0, i1, c)));      // position order, explicit rounding
-    }
+    for (int j = 0; j < COLS; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[j][k] = __fadd_rn(acc[j][k], __fmul_rn(wp, h.v[j][k]));      // position order, explicit rounding
   });
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) {
-    const int c = lane + 32 * j;
-    if (c < E) rep[b * E + c] = acc[j];
-  }
+  for (int j = 0; j < COLS; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (lane + 32 * j) * VEC + k;
+      if (c < E) rep[b * E + c] = acc[j][k];
+    }
 }
 
+template <int VEC, int COLS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pool_bwd_weights_kernel(Tables t, const int32_t* __restrict__ offsets, const float* __restrict__ d_rep, float* __restrict__ dw) {
   const int lane = threadIdx.x % 32;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + threadIdx.x / 32;
   if (b >= t.B) return;
   const int E = t.E;
-  float g[kMaxColsPerLane];
+  float g[COLS][VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) {
-    const int c = lane + 32 * j;
-    g[j] = c < E ? __ldg(d_rep + b * E + c) : 0.f;
-  }
-  for_valid_positions(t, b, lane, offsets[b], [&](int, int32_t p, int64_t i0, int64_t i1) {
+  for (int j = 0; j < COLS; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (lane + 32 * j) * VEC + k;
+      g[j][k] = c < E ? __ldg(d_rep + b * E + c) : 0.f;
+    }
+  for_valid_positions<VEC, COLS>(t, b, lane, offsets[b], [&](int, int32_t p, const HRow<VEC, COLS>& h) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxColsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      if (c < E) s = fmaf(g[j], hist_col(t, i0, i1, c), s);
-    }
+    for (int j = 0; j < COLS; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s = fmaf(g[j][k], h.v[j][k], s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);      // fixed tree: deterministic
     if (lane == 0) dw[p] = s;
   });
 }
 
-__device__ __forceinline__ float bf16_at(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-
+template <int VEC, int COLS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 feature_bwd_kernel(Tables t, const float* __restrict__ target, const int32_t* __restrict__ offsets, const __nv_bfloat16* __restrict__ dX,
                    int64_t ldx, const float* __restrict__ w, const float* __restrict__ d_rep, float* __restrict__ dh,
@@ -180,47 +242,80 @@ feature_bwd_kernel(Tables t, const float* __restrict__ target, const int32_t* __
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + threadIdx.x / 32;
   if (b >= t.B) return;
   const int E = t.E;
-  float tv[kMaxColsPerLane], gv[kMaxColsPerLane], dt[kMaxColsPerLane];
+  float tv[COLS][VEC], gv[COLS][VEC], dt[COLS][VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) {
-    const int c = lane + 32 * j;
-    tv[j] = c < E ? __ldg(target + b * E + c) : 0.f;
-    gv[j] = c < E ? __ldg(d_rep + b * E + c) : 0.f;
-    dt[j] = 0.f;
-  }
+  for (int j = 0; j < COLS; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (lane + 32 * j) * VEC + k;
+      tv[j][k] = c < E ? __ldg(target + b * E + c) : 0.f;
+      gv[j][k] = c < E ? __ldg(d_rep + b * E + c) : 0.f;
+      dt[j][k] = 0.f;
+    }
   if (zero_masked) {      // a dense history gradient (materialised-history form): masked positions get explicit zeros
     for (int l = 0; l < t.L; ++l) {
       if (!valid_at(t, b * t.L + l)) {
-#pragma unroll
-        for (int j = 0; j < kMaxColsPerLane; ++j) {
-          const int c = lane + 32 * j;
-          if (c < E) dh[(b * t.L + l) * E + c] = 0.f;
-        }
+        for (int c = lane; c < E; c += 32) dh[(b * t.L + l) * E + c] = 0.f;
       }
     }
   }
-  for_valid_positions(t, b, lane, offsets[b], [&](int l, int32_t p, int64_t i0, int64_t i1) {
+  for_valid_positions<VEC, COLS>(t, b, lane, offsets[b], [&](int l, int32_t p, const HRow<VEC, COLS>& h) {
     const __nv_bfloat16* row = dX + static_cast<int64_t>(p) * ldx;
     const float wp = __ldg(w + p);
     float* out = dh + (b * t.L + l) * E;
 #pragma unroll
-    for (int j = 0; j < kMaxColsPerLane; ++j) {
-      const int c = lane + 32 * j;
+    for (int j = 0; j < COLS; ++j) {
+      const int c = (lane + 32 * j) * VEC;
       if (c < E) {
-        const float h = hist_col(t, i0, i1, c);
-        const float d0 = bf16_at(row + c), d1 = bf16_at(row + E + c), d2 = bf16_at(row + 2 * E + c), d3 = bf16_at(row + 3 * E + c);
-        // every op rounded explicitly, in this order: the oracle (oracle/ctr_oracle.py local_activation_unit_backward) does the same
-        out[c] = __fadd_rn(__fadd_rn(__fsub_rn(d1, d2), __fmul_rn(d3, tv[j])), __fmul_rn(wp, gv[j]));
-        dt[j] = __fadd_rn(dt[j], __fadd_rn(__fadd_rn(d0, d2), __fmul_rn(d3, h)));
+        float d[4][VEC];
+        if constexpr (VEC == 2) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const uint32_t u = __ldcs(reinterpret_cast<const uint32_t*>(row + s4 * E + c));
+            d[s4][0] = __uint_as_float(u << 16);
+            d[s4][1] = __uint_as_float(u & 0xFFFF0000u);
+          }
+        } else {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) d[s4][0] = __bfloat162float(row[s4 * E + c]);
+        }
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          // every op rounded explicitly, in this order: the oracle (oracle/ctr_oracle.py local_activation_unit_backward) does the same
+          o[k] = __fadd_rn(__fadd_rn(__fsub_rn(d[1][k], d[2][k]), __fmul_rn(d[3][k], tv[j][k])), __fmul_rn(wp, gv[j][k]));
+          dt[j][k] = __fadd_rn(dt[j][k], __fadd_rn(__fadd_rn(d[0][k], d[2][k]), __fmul_rn(d[3][k], h.v[j][k])));
+        }
+        if constexpr (VEC == 2) __stcs(reinterpret_cast<float2*>(out + c), make_float2(o[0], o[1]));
+        else out[c] = o[0];
       }
     }
   });
 #pragma unroll
-  for (int j = 0; j < kMaxColsPerLane; ++j) {
-    const int c = lane + 32 * j;
-    if (c < E) d_target[b * E + c] = dt[j];
-  }
+  for (int j = 0; j < COLS; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (lane + 32 * j) * VEC + k;
+      if (c < E) d_target[b * E + c] = dt[j][k];
+    }
 }
+
+// pairs of columns when every pair is 8-byte aligned and stays inside one table
+static bool pairs_ok(const Tables& t, int64_t ldx = 0) { return t.D[0] % 2 == 0 && t.D[1] % 2 == 0 && ldx % 2 == 0; }
+
+// KERNEL<VEC, COLS> for the row width at hand: COLS = column groups per lane = ceil(E / (32 * VEC))
+#define DIN_DISPATCH(KERNEL, PAIRS, ...)                                                                     \
+  {                                                                                                          \
+    const dim3 grid(grid_for(t.B, kWarpsPerBlock));                                                          \
+    const int vec = (PAIRS) ? 2 : 1;                                                                         \
+    const int cols = (t.E + 32 * vec - 1) / (32 * vec);                                                      \
+    if (vec == 2) {                                                                                          \
+      if (cols <= 1) KERNEL<2, 1><<<grid, kWarpsPerBlock * 32, 0, st>>>(__VA_ARGS__);                        \
+      else KERNEL<2, 2><<<grid, kWarpsPerBlock * 32, 0, st>>>(__VA_ARGS__);                                  \
+    } else if (cols <= 1) KERNEL<1, 1><<<grid, kWarpsPerBlock * 32, 0, st>>>(__VA_ARGS__);                   \
+    else if (cols <= 2) KERNEL<1, 2><<<grid, kWarpsPerBlock * 32, 0, st>>>(__VA_ARGS__);                     \
+    else KERNEL<1, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(__VA_ARGS__);                                    \
+  }
 
 static int fill(Tables* t, const rb_din_history* h) {
   RB_CHECK_ARG(h != nullptr, RB_ERR_ARG, "history description is null");
@@ -290,8 +385,8 @@ extern "C" int rb_din_build_features(const rb_din_history* h, const float* targe
   RB_CHECK_ARG(target != nullptr && offsets != nullptr && x_bf16 != nullptr, RB_ERR_ARG, "target / offsets / x is null");
   RB_CHECK_ARG(ldx >= 4 * t.E && ldx - 4 * t.E < 32, RB_ERR_ARG, "ldx must be 4E plus fewer than 32 pad columns");
   if (t.B == 0) return RB_OK;
-  build_features_kernel<<<grid_for(t.B, kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, target, offsets, static_cast<__nv_bfloat16*>(x_bf16), ldx);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DIN_DISPATCH(build_features_kernel, pairs_ok(t, ldx), t, target, offsets, static_cast<__nv_bfloat16*>(x_bf16), ldx)
   RB_LAUNCH_CHECK("din build_features_kernel");
   return RB_OK;
 }
@@ -302,7 +397,8 @@ extern "C" int rb_din_pool_fwd(const rb_din_history* h, const int32_t* offsets, 
   if (rc != RB_OK) return rc;
   RB_CHECK_ARG(offsets != nullptr && w != nullptr && rep != nullptr, RB_ERR_ARG, "offsets / w / rep is null");
   if (t.B == 0) return RB_OK;
-  pool_fwd_kernel<<<grid_for(t.B, kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(t, offsets, w, rep);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DIN_DISPATCH(pool_fwd_kernel, pairs_ok(t), t, offsets, w, rep)
   RB_LAUNCH_CHECK("din pool_fwd_kernel");
   return RB_OK;
 }
@@ -313,7 +409,8 @@ extern "C" int rb_din_pool_bwd_weights(const rb_din_history* h, const int32_t* o
   if (rc != RB_OK) return rc;
   RB_CHECK_ARG(offsets != nullptr && d_rep != nullptr && dw != nullptr, RB_ERR_ARG, "offsets / d_rep / dw is null");
   if (t.B == 0) return RB_OK;
-  pool_bwd_weights_kernel<<<grid_for(t.B, kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(t, offsets, d_rep, dw);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DIN_DISPATCH(pool_bwd_weights_kernel, pairs_ok(t), t, offsets, d_rep, dw)
   RB_LAUNCH_CHECK("din pool_bwd_weights_kernel");
   return RB_OK;
 }
@@ -328,8 +425,9 @@ extern "C" int rb_din_feature_bwd(const rb_din_history* h, const float* target, 
                RB_ERR_ARG, "a required pointer is null");
   RB_CHECK_ARG(ldx >= 4 * t.E, RB_ERR_ARG, "ldx smaller than 4E");
   if (t.B == 0) return RB_OK;
-  feature_bwd_kernel<<<grid_for(t.B, kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, target, offsets, static_cast<const __nv_bfloat16*>(dx_bf16), ldx, w, d_rep, dh, d_target, zero_masked);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DIN_DISPATCH(feature_bwd_kernel, pairs_ok(t, ldx), t, target, offsets, static_cast<const __nv_bfloat16*>(dx_bf16), ldx, w, d_rep, dh, d_target,
+               zero_masked)
   RB_LAUNCH_CHECK("din feature_bwd_kernel");
   return RB_OK;
 }

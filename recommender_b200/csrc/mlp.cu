@@ -715,6 +715,27 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, i
   if (lane == 0) out[r] = apply_activation(acc + (bias != nullptr ? __ldg(bias) : 0.f), act);
 }
 
+// Narrow heads (in_dim <= 64, e.g. the 40 -> 1 logit of DIN's attention unit, dien/layers.py:39): a warp per row would leave most
+// lanes idle, so one THREAD takes a row — its in_dim / 8 16-byte loads are contiguous and neighbouring threads read neighbouring rows.
+__global__ void __launch_bounds__(256)
+head_fwd_narrow_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                       const float* __restrict__ bias, int act, float* __restrict__ out) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int k = 0; k < in_dim; k += 8) {
+    const uint4 xv = __ldcs(reinterpret_cast<const uint4*>(x + r * ldx + k));
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + k));
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc = fmaf(__uint_as_float(xs[j] << 16), __uint_as_float(ws[j] << 16), acc);
+      acc = fmaf(__uint_as_float(xs[j] & 0xFFFF0000u), __uint_as_float(ws[j] & 0xFFFF0000u), acc);
+    }
+  }
+  out[r] = apply_activation(acc + (bias != nullptr ? __ldg(bias) : 0.f), act);
+}
+
 // Backward of the head.  dz[r] = dout[r] * act'(out[r]);  dx[r, :] = bf16(dz[r] * w[:]);  partial sums of
 // dW[k] = sum_r x[r, k] * dz[r] and db = sum_r dz[r] per CTA (slab of rows), reduced in CTA order by head_bwd_final_kernel.
 constexpr int kHeadBwdThreads = 256;
@@ -1183,8 +1204,13 @@ extern "C" int rb_dense_head_fwd(const void* x, int64_t rows, int32_t in_dim, in
   RB_CHECK_ARG(rows > 0 && in_dim > 0 && in_dim % 8 == 0 && ldx % 8 == 0 && ldx >= in_dim, RB_ERR_SHAPE, "head: in_dim and ldx must be multiples of 8");
   RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, RB_ERR_ALIGN, "head: x / w not 16-byte aligned");
   RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
-  head_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
-                                                                                  static_cast<const __nv_bfloat16*>(w), bias, activation, out);
+  if (in_dim <= 64)
+    head_fwd_narrow_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim,
+                                                                                             ldx, static_cast<const __nv_bfloat16*>(w), bias,
+                                                                                             activation, out);
+  else
+    head_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
+                                                                                    static_cast<const __nv_bfloat16*>(w), bias, activation, out);
   RB_LAUNCH_CHECK("head_fwd_kernel");
   return RB_OK;
 }
