@@ -436,7 +436,10 @@ seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
 // a run this tile owns the W / m / v rows — into the group's ring slot, completion counted in bytes by the slot's mbarrier;
 // the lanes then read their 16-byte slices.  Applies to plain gradients (one source tensor per use of the table, no
 // scaling, no FM term: DLRM, and the per-rank dE buffers of the sharded path) with rows that are multiples of 16 bytes.
-constexpr int kBulkRing = 4;       // entries in flight per group
+#ifndef RB_BULK_RING
+#define RB_BULK_RING 4
+#endif
+constexpr int kBulkRing = RB_BULK_RING;       // entries in flight per group
 
 __device__ __forceinline__ uint32_t su_saddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void su_mbar_init(uint64_t* bar, uint32_t count) {
@@ -466,7 +469,10 @@ __device__ __forceinline__ void su_mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-template <int VEC, int GS>
+// FLAT: one use of the table whose gradient rows lie one after the other in position order (dE[B, L, D] of the un-pooled lookup:
+// bag_stride == L * pos_stride) — row p sits at src + p * pos_stride, no group search and no division by L (SASS r2_33: the
+// general addressing was ~40 of the 241 warp instructions per entry of a kernel that issues 71 % of its cycles)
+template <int VEC, int GS, bool FLAT>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_bulk_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
                              const __grid_constant__ GradGroupsDev gsrc, OptSink sink, float* __restrict__ head_part,
@@ -523,15 +529,19 @@ seg_reduce_tiles_bulk_kernel(const uint32_t* __restrict__ keys, const uint32_t* 
   auto run_ends_at = [&](int j, uint32_t key) {
     return (j == tcnt - 1) ? !(has_next && tk[tcnt] == key) : (tk[j + 1] != key);
   };
+  const float* const flat_src = gsrc.g[0].src[0];
+  const int64_t flat_stride = gsrc.g[0].pos_stride[0];
   auto issue = [&](int j, int slot) {            // lane 0 of the group only
     if (j >= tcnt) return;
     const uint32_t key = tk[j];
     uint64_t* bar = my_bar + slot;
-    const GradPos q = decode_pos(gsrc, tp[j]);
     float* dst = my_ring + slot * kKinds * D;
     const bool update = run_ends_at(j, key) && !(cont_first && key == first_key);
     su_mbar_expect_tx(bar, row_bytes + (update ? state_bytes : 0u));
-    su_bulk_g2s(dst, grad_src0(gsrc, q, 0), row_bytes, bar);
+    const float* grow;
+    if constexpr (FLAT) grow = flat_src + static_cast<int64_t>(tp[j]) * flat_stride;
+    else grow = grad_src0(gsrc, decode_pos(gsrc, tp[j]), 0);
+    su_bulk_g2s(dst, grow, row_bytes, bar);
     if (update) {
       const int64_t o = static_cast<int64_t>(key) * D;
       if (ld_w) su_bulk_g2s(dst + D, sink.table + o, row_bytes, bar);
@@ -845,6 +855,7 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
     bulk = gk.num_src == 1 && gk.scale_mode == RB_SCALE_NONE && gk.fm_g == nullptr && gk.bag_stride[0] % 4 == 0 && gk.pos_stride[0] % 4 == 0 &&
            (reinterpret_cast<uintptr_t>(gk.src[0]) & 15) == 0;
   }
+  const bool flat = bulk && gsrc.num == 1 && g0.bag_stride[0] == static_cast<int64_t>(g0.L) * g0.pos_stride[0];
 #define CALL(V, G)                                                                                                      \
   {                                                                                                                     \
     constexpr int kGroups = kSegThreads / G;                                                                            \
@@ -852,10 +863,17 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
     if (bulk) {                                                                                                         \
       const size_t bulk_bytes = static_cast<size_t>(kGroups) * kBulkRing * 4 * gsrc.D * sizeof(float) + bulk_pad_bytes(); \
       if constexpr (std::is_same<Sink, OptSink>::value) {                                                               \
-        RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     static_cast<int>(bulk_bytes)));                                                    \
-        seg_reduce_tiles_bulk_kernel<V, G><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, gsrc, \
-                                                                                                      sink, head, tail); \
+        if (flat) {                                                                                                     \
+          RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       static_cast<int>(bulk_bytes)));                                                  \
+          seg_reduce_tiles_bulk_kernel<V, G, true><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, \
+                                                                                                              gsrc, sink, head, tail); \
+        } else {                                                                                                        \
+          RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       static_cast<int>(bulk_bytes)));                                                  \
+          seg_reduce_tiles_bulk_kernel<V, G, false><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, \
+                                                                                                               gsrc, sink, head, tail); \
+        }                                                                                                               \
       }                                                                                                                 \
     } else if (simple) {                                                                                                \
       if (ring_bytes > 40 * 1024)                                                                                       \
