@@ -8,5 +8,3 @@ timeout 900 $RUN bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_be
 echo "bench cfg3 exit $?"; tail -2 gpurun_out/${TAG}_bench_cfg3.err; head -c 260 gpurun_out/${TAG}_bench_cfg3.json; echo
 timeout 900 $RUN bench.py --gpus $N --steps 20 --warmup 5 --config2-sharded --sustain-seconds 0 > gpurun_out/${TAG}_bench_cfg2.json 2> gpurun_out/${TAG}_bench_cfg2.err
 echo "bench cfg2 exit $?"; tail -2 gpurun_out/${TAG}_bench_cfg2.err; head -c 260 gpurun_out/${TAG}_bench_cfg2.json; echo
-RB_PRIO_MAIN=0 RB_PRIO_WGRAD=0 timeout 900 $RUN bench.py --gpus $N --steps 20 --warmup 5 --config2-sharded --sustain-seconds 0 > gpurun_out/${TAG}_bench_cfg2_noprio.json 2> gpurun_out/${TAG}_bench_cfg2_noprio.err
-echo "bench cfg2 noprio exit $?"; head -c 260 gpurun_out/${TAG}_bench_cfg2_noprio.json; echo
