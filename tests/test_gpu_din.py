@@ -165,3 +165,43 @@ def test_config4_size_runs_and_is_deterministic(cuda_lib):
         outs.append((out.detach().clone(), model.local_activation_unit.kernels[0].grad.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+
+
+def test_three_uses_of_the_tables_in_one_step_with_the_negative_history(cuda_lib, golden):
+    """DIEN looks the same two tables up a third time for the NEGATIVE history (dien/model.py:69-71: compute_flat_embedding on
+    neg_his_item / neg_his_cat, un-pooled, consumed by the auxiliary loss).  Target lookup + attention-pooled positive history +
+    plain gather of the negative history in ONE step: each table's update is one call over three concatenated lookup groups
+    (SURVEY A.1), and equals the sum of the three gradients."""
+    from recommender_b200.optimizers import SGD
+    g = golden("din_attention")
+    tgt, his, mask, layers = _case(g)
+    model = _build_din(g)
+    rng = np.random.default_rng(23)
+    B, L = g["item"].shape
+    D = g["W_item"].shape[1]
+    neg_item = rng.integers(1, g["W_item"].shape[0], size=(B, L)).astype(np.int32)
+    neg_cat = rng.integers(1, g["W_cat"].shape[0], size=(B, L)).astype(np.int32)
+    d_neg = rng.normal(0, 1e-2, size=(B, L, 2 * D)).astype(np.float32)
+    inputs = {k: cu(g[n]) for k, n in (("target_item", "t_item"), ("target_cat", "t_cat"), ("pos_his_item", "item"), ("pos_his_cat", "cat"))}
+    out = model(inputs)
+    neg = model.compute_flat_embedding((cu(neg_item), cu(neg_cat)))                    # dien/model.py:69-71
+    np.testing.assert_array_equal(neg.detach().cpu().numpy(), O.compute_flat_embedding(g["W_item"], g["W_cat"], neg_item, neg_cat))
+    E = 2 * D
+    W_item0, W_cat0 = model.item_embedding.embeddings.clone(), model.cat_embedding.embeddings.clone()
+    torch.autograd.backward([out, neg], [torch.cat([torch.zeros_like(out[:, :E]), cu(g["d_rep"])], dim=1), cu(d_neg)])
+    assert len(model.item_embedding.pending) == 3 and len(model.cat_embedding.pending) == 3
+    SGD(learning_rate=1.0).apply_gradients(model)
+    rep16, cache = O.local_activation_unit(tgt, his, mask, layers, operand_dtype="bf16")
+    dt16, dh16, _ = O.local_activation_unit_backward(cache, g["d_rep"])
+    for W0, emb, h_idx, t_idx, n_idx, c0 in ((W_item0, model.item_embedding, g["item"], g["t_item"], neg_item, 0),
+                                             (W_cat0, model.cat_embedding, g["cat"], g["t_cat"], neg_cat, D)):
+        got = (W0 - emb.embeddings).cpu().numpy()
+        ref = np.zeros_like(got)
+        np.add.at(ref, h_idx.reshape(-1), dh16[:, :, c0:c0 + D].reshape(-1, D))
+        np.add.at(ref, t_idx.reshape(-1), dt16[:, c0:c0 + D])
+        np.add.at(ref, n_idx.reshape(-1), d_neg[:, :, c0:c0 + D].reshape(-1, D))
+        assert _rel(got, ref) <= 1e-2
+        only_neg = np.setdiff1d(n_idx.reshape(-1), np.concatenate([h_idx.reshape(-1), t_idx.reshape(-1)]))
+        exact = np.zeros_like(got)
+        np.add.at(exact, n_idx.reshape(-1), d_neg[:, :, c0:c0 + D].reshape(-1, D))
+        np.testing.assert_allclose(got[only_neg], exact[only_neg], rtol=2e-6, atol=8e-9)     # fp32 rows, same summation order; W0 - W rounds at 2^-24 |W|
