@@ -73,6 +73,9 @@ def parse_args():
                     help="N > 1: keep BASELINE config 2 (26 x 1M-row tables) row-wise sharded instead of config 3")
     ap.add_argument("--capacity-factor", type=float, default=0.0,
                     help="static per-owner pair capacity of the sharded table in units of the per-rank lookups (0 = 2.0 for config 3, 1.25 otherwise)")
+    ap.add_argument("--replicate-small", type=int, default=4096,
+                    help="config 3: tables of at most this many rows are replicated on every rank instead of row-sharded (0 = shard all; "
+                         "r2_39 at N = 8: 1.911 -> 1.624 ms per step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="batch of the CPU reference arm; 0 = the GPU arm's batch (its Keras dense-Adam passes cost the same whatever the batch)")
@@ -228,6 +231,8 @@ def workload_config(args, world):
                 else "layer by layer",
                 parallelism="single GPU" if world == 1 else (
                     f"row-wise sharded tables x{world}, rows and gradient rows read by the kernels over NVLink peer memory + data-parallel MLPs"
+                    + (f"; the {sum(1 for r in CRITEO_TB_ROWS if r <= args.replicate_small)} tables of <= {args.replicate_small} rows replicated "
+                       "on every rank (local reads, one all-gathered update)" if getattr(args, "criteo_tb", False) and args.replicate_small > 0 else "")
                     if args.exchange == "p2p" else f"{args.sharding}-wise sharded tables x{world}, NCCL all-to-all + data-parallel MLPs"),
                 l2="inputs larger than L2: tables %.1f GB, ring of %d batches, 436 MB gradient tensor per step" % (
                     args.tables * args.rows_per_table * args.emb_dim * 4 / 1e9, args.ring))
@@ -503,7 +508,8 @@ def run_b200(args):
     elif peer_memory_usable(args, dev):
         from recommender_b200.p2p import P2PShardedDLRM
         model = P2PShardedDLRM(BOTTOM[:-1] + [D], TOP, D, V, F_CAT, F_INT, num_tables=T, device=dev, compute_dtype=cd, generator=gen,
-                               table_rows=CRITEO_TB_ROWS if args.criteo_tb else None, capacity_factor=cap_factor)
+                               table_rows=CRITEO_TB_ROWS if args.criteo_tb else None, capacity_factor=cap_factor,
+                               replicate_rows_upto=args.replicate_small if args.criteo_tb else 0)
     else:
         from recommender_b200.sharded import ShardedDLRM
         args.criteo_tb = False           # the NCCL all-to-all fallback runs config 2 sharded
@@ -536,6 +542,8 @@ def run_b200(args):
         # inside `with torch.cuda.stream(side)`), so the bracketing events sit on the launching stream; the rendezvous barriers
         # are outside the brackets
         timer.install_on(model.embedding_layer, ["route", "collect_and_sort", "_interaction_fwd", "_interaction_bwd", "_apply_rows"], "p2p.")
+        if getattr(model.embedding_layer, "_small", None):
+            timer.install_on(model.embedding_layer, ["_small_reduce", "_small_exchange", "_small_update"], "p2p.")
 
     def barrier():
         if world > 1:
@@ -628,6 +636,10 @@ def run_b200(args):
         for tag, dt in (("fp32_towers", None), ("bf16_towers", torch.bfloat16)):
             try:
                 parity[tag] = p2p_selfcheck.run(dev, compute_dtype=dt)
+                if args.criteo_tb and args.replicate_small > 0 and tag == "bf16_towers":
+                    # the same check on unequal tables with the small ones replicated (the path config 3 takes)
+                    parity["bf16_towers_replicated_small_tables"] = p2p_selfcheck.run(
+                        dev, compute_dtype=dt, table_rows=[5000] * 20 + [3, 14, 63, 155, 976, 2208], replicate_rows_upto=4096)
             except Exception as e:                               # noqa: BLE001 - reported in the line, never hidden
                 parity[tag] = dict(error=f"{type(e).__name__}: {e}")
                 break
@@ -650,10 +662,13 @@ def run_b200(args):
                     dst.copy_(src, non_blocking=True)
                 h2d_done[buf].record(copy_stream)
 
+        host_loop_ms = [0.0]
+
         def e2e_loop(n, base):
             for ev in free:
                 ev.record(main)
             prefetch(0)
+            t_host = time.perf_counter()
             for i in range(n):
                 buf = i % 2
                 if i + 1 < n:
@@ -662,6 +677,7 @@ def run_b200(args):
                 loss = train_step(stage[buf])
                 free[buf].record(main)
                 loss_host[base + i].copy_(loss.detach(), non_blocking=True)      # the step's result, read every step
+            host_loop_ms[0] = (time.perf_counter() - t_host) * 1e3 / max(n, 1)   # host time to ENQUEUE one step (before the sync)
             torch.cuda.synchronize()
 
         e2e_loop(3, 0)
@@ -675,7 +691,7 @@ def run_b200(args):
         wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), 0.0)) / args.steps
         e2e = dict(value=B * world / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
-                   ms_per_step=e2e_ms, wall_ms_per_step=wall_ms / args.steps,
+                   ms_per_step=e2e_ms, wall_ms_per_step=wall_ms / args.steps, host_enqueue_ms_per_step=host_loop_ms[0],
                    api=("GraphedTrainStep.step (one CUDA graph: DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients)"
                         if use_graph else "DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients")
                        + " on batches staged from pinned host memory")
@@ -734,7 +750,10 @@ def run_b200(args):
         remote = (world - 1) / world
         nv_peak, nv_measured = 900.0, 770.0      # nominal per direction per GPU; peer-copy rate measured on this pool (B200_PROFILING.md)
         nv = {}
-        for name, nbytes in (("p2p._interaction_fwd", N * D * 2 * remote), ("p2p._apply_rows", N * D * 4 * remote)):
+        # lookups of tables replicated on every rank never leave the GPU: only the sharded tables' rows cross NVLink
+        n_small = len(getattr(model.embedding_layer, "_small", []) or [])
+        N_sharded = B * (F_CAT - n_small)
+        for name, nbytes in (("p2p._interaction_fwd", N_sharded * D * 2 * remote), ("p2p._apply_rows", N_sharded * D * 4 * remote)):
             if name in kernels:
                 gbs = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
                 kernels[name].update(nvlink_bytes=int(nbytes), nvlink_gbs=gbs, nvlink_frac=gbs / nv_peak)
@@ -744,7 +763,8 @@ def run_b200(args):
             roofline = dict(bound="nvlink", kernel=top, achieved=nv[top]["nvlink_gbs"], peak=nv_peak, unit="GB/s", frac=nv[top]["nvlink_frac"],
                             traffic=None, peak_source="nominal NVLink 5, 900 GB/s per direction per GPU",
                             frac_of_measured_peer_copy=nv[top]["nvlink_gbs"] / nv_measured,
-                            note="achieved = bytes this rank's kernel reads from PEER memory over NVLink ((G-1)/G of its rows: bf16 shadow rows "
+                            replicated_tables=n_small,
+                            note="achieved = bytes this rank's kernel reads from PEER memory over NVLink ((G-1)/G of the SHARDED tables' rows: bf16 shadow rows "
                                  "in the forward, fp32 gradient rows in the owner-side apply) / the CUDA-event time of that C call on its "
                                  "launching stream; the same kernels also move their local HBM share in that time")
 

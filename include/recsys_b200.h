@@ -316,6 +316,16 @@ int rb_dot_interaction_bwd_update(float* table, int64_t rows, const void* idx, i
                                   int32_t row_cache, const int32_t* row_cache_hint, void* stream);
 
 /*
+ * Update of tables REPLICATED on every rank of a sharded job from `num_lists` (one per rank, all-gathered) sorted
+ * lists of (row, summed gradient): list k = cap records of D + 1 floats — D gradient values, then the row id as int32 bits —
+ * rows ascending, padded with ids >= rows.  A row held by any list gets ONE optimizer update with the lists' gradients added
+ * in list order (the IndexedSlices of all replicas concatenated, SURVEY A.7, then A.2-A.3); other rows do not move.
+ * shadow_bf16 (optional): bf16 copy of the table kept in step.
+ */
+int rb_replicated_rows_update(float* table, float* state0, float* state1, int64_t rows, int32_t D, const float* lists,
+                              int32_t num_lists, int64_t cap, const rb_opt_params* opt, void* shadow_bf16, void* stream);
+
+/*
  * The same sort + segmented reduction WITHOUT the optimizer: writes the unique rows (ascending)
  * and their summed gradients — the deduplicated IndexedSlices itself.  Used by the parity tests
  * and by callers that own their optimizer.
@@ -446,6 +456,11 @@ size_t rb_bucket_by_owner_workspace_bytes(int64_t n, int32_t world);
  *                            interaction / gather kernels read the returned rows in place)
  *   counts_out     int64[world]: lookups per owner
  */
+/* rb_bucket_by_owner that leaves lookups whose row is >= skip_from_row out of every bucket (rows of replicated tables):
+ * not counted, no slot, inv_perm_out[p] = -1.  world <= 8. */
+int rb_bucket_by_owner_skip(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_row_offset,
+                            int64_t hash_mod, int32_t world, int64_t skip_from_row, int64_t* local_rows_out, int32_t* perm_out,
+                            int32_t* inv_perm_out, int64_t* counts_out, void* ws, size_t ws_bytes, void* stream);
 int rb_bucket_by_owner(const void* idx, int32_t idx_type, int64_t n, int32_t L,
                        const int64_t* field_row_offset, int64_t hash_mod, int32_t world,
                        int64_t* local_rows_out, int32_t* perm_out, int32_t* inv_perm_out,
@@ -482,12 +497,34 @@ int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev, int32_t wo
                                    int32_t self_interaction, int32_t skip_gather, int32_t tail,
                                    void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
                                    const void* const* shadow_ptrs_dev, void* stream);
+/* ... with tables REPLICATED on every rank behind the sharded ones: rows in [small_base, rows) are read from this rank's own copy
+ * (small_rep f32 / small_rep_bf16 [rows - small_base, D], the bf16 one when shadow shards are given) instead of a shard.  The
+ * Criteo-Terabyte cardinalities hold 11 tables of <= 2208 rows that take 42 % of all lookups: sharding them row-wise sends every
+ * one of those lookups to the same handful of owners. */
+int rb_dot_interaction_fwd_sharded_rep(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
+                                       const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                                       const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                                       int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                                       void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
+                                       const void* const* shadow_ptrs_dev, int64_t small_base, const float* small_rep,
+                                       const void* small_rep_bf16, void* stream);
 int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
                                    const void* idx, int32_t idx_type, const int64_t* field_row_offset,
                                    const float* dense_vec, int64_t B, int32_t F, int32_t D,
                                    int32_t self_interaction, int32_t skip_gather, int32_t tail,
                                    const void* dOut, int32_t dout_dtype, int64_t dout_stride,
                                    float* dE, float* d_dense, const void* x_saved, void* stream);
+
+/* rb_dot_interaction_bwd_sharded that writes the gradient rows of the fields with de_slot[f] >= 0 (DEVICE int32[F]; the fields of
+ * replicated tables) to the compact tensor dE_small[B, num_small, D] at column de_slot[f] instead of dE: their duplicate-row sum
+ * (rb_sparse_bwd_dedup) then reads one contiguous tensor.  Needs the saved operand rows (x_saved). */
+int rb_dot_interaction_bwd_sharded_split(const void* const* shard_ptrs_dev, int32_t world, int64_t rows,
+                                         const void* idx, int32_t idx_type, const int64_t* field_row_offset,
+                                         const float* dense_vec, int64_t B, int32_t F, int32_t D,
+                                         int32_t self_interaction, int32_t skip_gather, int32_t tail,
+                                         const void* dOut, int32_t dout_dtype, int64_t dout_stride,
+                                         float* dE, float* d_dense, const void* x_saved, const int32_t* de_slot, float* dE_small,
+                                         int32_t num_small, void* stream);
 
 /*
  * Owner side of the sharded backward.  Every rank k publishes its rb_bucket_by_owner outputs (local

@@ -94,6 +94,7 @@ SIGNATURES = {
     "rb_sparse_bwd_mark_singletons": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p, _p]),
     "rb_dot_interaction_bwd_update": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p, _p,
                                                 _p, _p, _p, C.POINTER(RbOptParams), _i32, _p, _p]),
+    "rb_replicated_rows_update": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i32, _i64, C.POINTER(RbOptParams), _p, _p]),
     "rb_sparse_bwd_dedup": (C.c_int, [_i64, _i32, _p, _i32, _i64, _i32, _p, _i64, C.POINTER(RbGradSource),
                                       _p, _p, _p, _p, C.c_size_t, _p, _p]),
     "rb_dense_opt_step": (C.c_int, [C.POINTER(RbDenseSlot), _i32, C.POINTER(RbOptParams), _p]),
@@ -106,8 +107,12 @@ SIGNATURES = {
     "rb_enable_peer_access": (C.c_int, [_i32]),
     "rb_dot_interaction_fwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p,
                                                  _p, _p]),
+    "rb_dot_interaction_fwd_sharded_rep": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p,
+                                                     _p, _i64, _p, _p, _p]),
     "rb_dot_interaction_bwd_sharded": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64,
                                                  _p, _p, _p, _p]),
+    "rb_dot_interaction_bwd_sharded_split": (C.c_int, [_p, _i32, _i64, _p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i64,
+                                                       _p, _p, _p, _p, _p, _i32, _p]),
     "rb_p2p_collect_keys": (C.c_int, [_i32, _i32, _i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64, _i64,
                                       _p, C.c_size_t, _i32, _p, _p, _p]),
     "rb_sparse_bwd_prepare_collected": (C.c_int, [_i64, _i32, _i64, _p, C.c_size_t, C.POINTER(C.c_int32), _p]),
@@ -135,6 +140,7 @@ SIGNATURES = {
     "rb_hash_ids": (C.c_int, [_p, _i32, _i64, _i64, _i32, _p, _p, _p, _p]),
     "rb_bucket_by_owner_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_bucket_by_owner": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "rb_bucket_by_owner_skip": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "rb_criteo_index_workspace_bytes": (C.c_size_t, [_i64]),
     "rb_criteo_index_lines": (C.c_int, [_p, _i64, _i64, _p, _p, _p, C.c_size_t, _p]),
     "rb_criteo_parse": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),

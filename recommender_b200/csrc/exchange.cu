@@ -30,7 +30,10 @@ __device__ __forceinline__ int64_t row_or_zero(const IndexMap& m, int64_t p) {
   return row < 0 ? 0 : row;  // out-of-range ids are clamped to row 0 (documented in the header)
 }
 
-__global__ void __launch_bounds__(kOwnerThreads) owner_count_kernel(IndexMap m, int64_t n, int world, int32_t* __restrict__ chunk_counts) {
+// skip_from: lookups whose row is >= skip_from belong to no owner (tables replicated on every rank, p2p.py): they are neither
+// counted nor given a slot
+__global__ void __launch_bounds__(kOwnerThreads) owner_count_kernel(IndexMap m, int64_t n, int world, int64_t skip_from,
+                                                                     int32_t* __restrict__ chunk_counts) {
   __shared__ int s_cnt[kMaxOwners];
   if (threadIdx.x < kMaxOwners) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -41,7 +44,8 @@ __global__ void __launch_bounds__(kOwnerThreads) owner_count_kernel(IndexMap m, 
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     if (base + i < n) {
-      const int o = static_cast<int>(row_or_zero(m, base + i) % world);
+      const int64_t r = row_or_zero(m, base + i);
+      const int o = r >= skip_from ? -1 : static_cast<int>(r % world);
 #pragma unroll
       for (int q = 0; q < kMaxOwners; ++q) cnt[q] += (o == q) ? 1 : 0;
     }
@@ -103,8 +107,8 @@ __global__ void __launch_bounds__(1024) owner_offsets_kernel(int32_t* __restrict
 }
 
 __global__ void __launch_bounds__(kOwnerThreads)
-owner_scatter_kernel(IndexMap m, int64_t n, int world, const int32_t* __restrict__ chunk_offsets, int64_t* __restrict__ local_rows,
-                     int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+owner_scatter_kernel(IndexMap m, int64_t n, int world, int64_t skip_from, const int32_t* __restrict__ chunk_offsets,
+                     int64_t* __restrict__ local_rows, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
   __shared__ int s_warp[kOwnerThreads / 32][kMaxOwners];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kChunk + threadIdx.x * kItems;
@@ -118,7 +122,8 @@ owner_scatter_kernel(IndexMap m, int64_t n, int world, const int32_t* __restrict
     owner[i] = -1;
     if (base + i < n) {
       row[i] = row_or_zero(m, base + i);
-      owner[i] = static_cast<int>(row[i] % world);
+      owner[i] = row[i] >= skip_from ? -1 : static_cast<int>(row[i] % world);
+      if (owner[i] < 0) inv_perm[base + i] = -1;
 #pragma unroll
       for (int q = 0; q < kMaxOwners; ++q) cnt[q] += (owner[i] == q) ? 1 : 0;
     }
@@ -244,9 +249,21 @@ extern "C" size_t rb_bucket_by_owner_workspace_bytes(int64_t n, int32_t world) {
   return bucket_ws(n, world).total;
 }
 
+extern "C" int rb_bucket_by_owner_skip(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_row_offset,
+                                       int64_t hash_mod, int32_t world, int64_t skip_from_row, int64_t* local_rows_out, int32_t* perm_out,
+                                       int32_t* inv_perm_out, int64_t* counts_out, void* ws, size_t ws_bytes, void* stream);
+
 extern "C" int rb_bucket_by_owner(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_row_offset,
                                   int64_t hash_mod, int32_t world, int64_t* local_rows_out, int32_t* perm_out,
                                   int32_t* inv_perm_out, int64_t* counts_out, void* ws, size_t ws_bytes, void* stream) {
+  return rb_bucket_by_owner_skip(idx, idx_type, n, L, field_row_offset, hash_mod, world, INT64_MAX, local_rows_out, perm_out, inv_perm_out,
+                                 counts_out, ws, ws_bytes, stream);
+}
+
+extern "C" int rb_bucket_by_owner_skip(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_row_offset,
+                                       int64_t hash_mod, int32_t world, int64_t skip_from_row, int64_t* local_rows_out, int32_t* perm_out,
+                                       int32_t* inv_perm_out, int64_t* counts_out, void* ws, size_t ws_bytes, void* stream) {
+  RB_CHECK_ARG(skip_from_row == INT64_MAX || world <= kMaxOwners, RB_ERR_ARG, "skip_from_row needs world <= %d (the counting partition)", kMaxOwners);
   RB_CHECK_ARG(n >= 0 && n < 0x7FFFFFFFll && L > 0, RB_ERR_ARG, "n must be in [0, 2^31) and L > 0");
   RB_CHECK_ARG(world >= 1 && world <= 1024, RB_ERR_ARG, "world must be in [1, 1024]");
   RB_CHECK_ARG(idx_type == RB_I32 || idx_type == RB_I64, RB_ERR_ARG, "bad index type");
@@ -272,11 +289,11 @@ extern "C" int rb_bucket_by_owner(const void* idx, int32_t idx_type, int64_t n, 
   if (world <= kMaxOwners) {      // the box's 8 GPUs: counting partition, no sort
     int32_t* chunk_counts = reinterpret_cast<int32_t*>(wsb + lay.chunk_counts);
     const int chunks = static_cast<int>((n + kChunk - 1) / kChunk);
-    owner_count_kernel<<<chunks, kOwnerThreads, 0, st>>>(m, n, world, chunk_counts);
+    owner_count_kernel<<<chunks, kOwnerThreads, 0, st>>>(m, n, world, skip_from_row, chunk_counts);
     RB_LAUNCH_CHECK("owner_count_kernel");
     owner_offsets_kernel<<<1, 1024, 0, st>>>(chunk_counts, chunks, world, counts_out);
     RB_LAUNCH_CHECK("owner_offsets_kernel");
-    owner_scatter_kernel<<<chunks, kOwnerThreads, 0, st>>>(m, n, world, chunk_counts, local_rows_out, perm_out, inv_perm_out);
+    owner_scatter_kernel<<<chunks, kOwnerThreads, 0, st>>>(m, n, world, skip_from_row, chunk_counts, local_rows_out, perm_out, inv_perm_out);
     RB_LAUNCH_CHECK("owner_scatter_kernel");
     return RB_OK;
   }

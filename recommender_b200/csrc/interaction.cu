@@ -71,6 +71,11 @@ struct IxArgs {
   int tail;
   int ncols;               // interaction columns (without tail)
   int pad_one;             // bf16 output rows: first pad column = 1.0 (RB_BF16_ONES)
+  const int32_t* de_slot;  // backward, optional [F]: de_slot[f] >= 0 sends the gradient rows of field f to the compact tensor
+  float* dE_small;         //   dE_small[B, num_small, D] at column de_slot[f] instead of dE[B, F, D] (fields of replicated tables)
+  int num_small;
+  uint32_t small_base;     // sharded forms: rows >= small_base belong to tables REPLICATED on every rank and are read from the
+  const void* small_rep;   //   local replica small_rep (row - small_base; fp32 rows, or bf16 rows in the shadow form) instead of a shard
   int row_cache;           // rb_row_cache: copy table rows through L1 (hot rows: Zipf ids, the OOV row) or past it (uniform ids)
   const int32_t* row_cache_hint;   // RB_ROW_CACHE_AUTO: device flag written by rb_sparse_bwd_prepare of this / the previous step
 };
@@ -150,7 +155,8 @@ __device__ __forceinline__ uint32_t load_sample_row(const IxArgs& a, int64_t b, 
 template <int D, int STRIDE, bool SHARDED>
 __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, uint32_t my_row, int F, float* dst_lane,
                                            int sub, const float* __restrict__ dense_lane, float* dense_dst,
-                                           const float* const* shard_base, uint32_t world, int col, bool l1) {
+                                           const float* const* shard_base, uint32_t world, int col, bool l1,
+                                           uint32_t small_base = 0xFFFFFFFFu, const float* small_rep = nullptr) {
   constexpr int kRowsPerIter = 32 / (D / 4);
 #pragma unroll 4
   for (int r0 = 0; r0 < F; r0 += kRowsPerIter) {
@@ -160,8 +166,12 @@ __device__ __forceinline__ void issue_rows(const float* __restrict__ src_lane, u
     const float* src = src_lane;
     if (ok) {
       if constexpr (SHARDED) {
-        const uint32_t local = row / world;
-        src = shard_base[row - local * world] + static_cast<size_t>(local) * D + col;
+        if (row >= small_base) {
+          src = small_rep + static_cast<size_t>(row - small_base) * D + col;       // replicated table: this rank's own copy
+        } else {
+          const uint32_t local = row / world;
+          src = shard_base[row - local * world] + static_cast<size_t>(local) * D + col;
+        }
       } else {
         src = src_lane + static_cast<size_t>(row) * D;
       }
@@ -304,7 +314,8 @@ dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, 
   auto issue = [&](int64_t bb, uint32_t rows, int st) {
     float* xn = xs_base + st * kXsFloats;
     issue_rows<D, STRIDE, SHARDED>(src_lane, rows, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
-                                   xn + F * STRIDE + lane * 4, shard_base, a.world, col, l1);
+                                   xn + F * STRIDE + lane * 4, shard_base, a.world, col, l1, a.small_base,
+                                   static_cast<const float*>(a.small_rep));
   };
   // prologue: the first kIxStages-1 samples of this warp are put in flight
 #pragma unroll
@@ -462,8 +473,12 @@ dot_interaction_fwd16_kernel(IxArgs a, const __nv_bfloat16* const* __restrict__ 
       const bool ok = row != kInvalidRow;
       const __nv_bfloat16* src = s_shards[0];
       if (ok) {
-        const uint32_t local = row / world;
-        src = s_shards[row - local * world] + static_cast<size_t>(local) * D + col;
+        if (row >= a.small_base) {
+          src = static_cast<const __nv_bfloat16*>(a.small_rep) + static_cast<size_t>(row - a.small_base) * D + col;
+        } else {
+          const uint32_t local = row / world;
+          src = s_shards[row - local * world] + static_cast<size_t>(local) * D + col;
+        }
       }
       if (r < F) cp_async16_ca(x16 + r * S16 + col, src, ok ? 16 : 0);
     }
@@ -629,6 +644,15 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
       is_emb[mt][h] = (i < F) && dE != nullptr;
       is_dense[mt][h] = (i == F) && a.dense_vec != nullptr && d_dense != nullptr;
     }
+  // fields whose gradient rows go to the compact tensor of the replicated tables
+  int de_slot[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = mt * 16 + g + h * 8;
+      de_slot[mt][h] = (a.de_slot != nullptr && i < F) ? __ldg(a.de_slot + i) : -1;
+    }
 
   const float* src_lane = (a.E != nullptr ? a.E : (SRC == 1 ? s_shards[0] : a.table)) + (lane % kLanesPerRow) * 4;
   const int sub = lane / kLanesPerRow;
@@ -661,7 +685,8 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
       }
     } else
     issue_rows<D, STRIDE, SRC == 1>(src_lane, row, F, xn + dst_off, sub, dense_lane_on ? a.dense_vec + bb * D + lane * 4 : nullptr,
-                          xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4, l1);
+                          xn + F * STRIDE + lane * 4, shard_base, a.world, (lane % kLanesPerRow) * 4, l1, a.small_base,
+                          static_cast<const float*>(a.small_rep));
     const DOUT* grow = dOut + bb * dout_stride;
     load_row_async<DOUT>(grow, reinterpret_cast<DOUT*>(sp + kXsFloats * 4 + 16), misalign_elems(grow), copy_width, lane);
   };
@@ -801,7 +826,10 @@ dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout
           if (UPD && is_emb[mt][h] && ((smask >> (mt * 16 + g + h * 8)) & 1u)) {
             // updated above
           } else if (is_emb[mt][h]) {
-            __stcs(reinterpret_cast<float2*>(de_lane + (mt * 16 + h * 8) * D + nt * 8), v);
+            if (de_slot[mt][h] >= 0)
+              __stcs(reinterpret_cast<float2*>(a.dE_small + (b * a.num_small + de_slot[mt][h]) * D + nt * 8 + t2), v);
+            else
+              __stcs(reinterpret_cast<float2*>(de_lane + (mt * 16 + h * 8) * D + nt * 8), v);
           } else if (is_dense[mt][h]) {
             const int col = nt * 8 + t2;
             if (a.tail) {
@@ -839,6 +867,11 @@ static int fill_args(IxArgs* a, const float* E, const float* table, int64_t rows
                      int skip_gather, int tail, const float* const* shards = nullptr, int world = 1) {
   a->row_cache = RB_ROW_CACHE_L2;
   a->row_cache_hint = nullptr;
+  a->small_base = 0xFFFFFFFFu;
+  a->small_rep = nullptr;
+  a->de_slot = nullptr;
+  a->dE_small = nullptr;
+  a->num_small = 0;
   RB_CHECK_ARG(B >= 0 && F > 0, RB_ERR_ARG, "bad B/F");
   RB_CHECK_ARG(D == 16 || D == 32 || D == 64 || D == 128, RB_ERR_SHAPE, "dot interaction needs D in {16,32,64,128}, got %d", D);
   const int Fp = F + (dense_vec != nullptr ? 1 : 0);
@@ -1136,16 +1169,42 @@ extern "C" int rb_dot_interaction_bwd(const float* E, const float* table, int64_
 
 // Row-wise sharded forms: the table is `world` shards in peer memory (shard_ptrs_dev: DEVICE array of
 // `world` device pointers, this rank's own shard included); `rows` is the GLOBAL row count.
+extern "C" int rb_dot_interaction_fwd_sharded_rep(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                                  int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                                  int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                                  int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
+                                                  const void* const* shadow_ptrs_dev, int64_t small_base, const float* small_rep,
+                                                  const void* small_rep_bf16, void* stream);
+
 extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
                                               int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                               int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
                                               int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
                                               const void* const* shadow_ptrs_dev, void* stream) {
+  return rb_dot_interaction_fwd_sharded_rep(shard_ptrs_dev, world, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D,
+                                            self_interaction, skip_gather, tail, out, out_dtype, out_stride, x_save, shadow_ptrs_dev, rows,
+                                            nullptr, nullptr, stream);
+}
+
+extern "C" int rb_dot_interaction_fwd_sharded_rep(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                                  int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                                  int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                                  int32_t tail, void* out, int32_t out_dtype, int64_t out_stride, void* x_save,
+                                                  const void* const* shadow_ptrs_dev, int64_t small_base, const float* small_rep,
+                                                  const void* small_rep_bf16, void* stream) {
   RB_CHECK_ARG(shard_ptrs_dev != nullptr, RB_ERR_ARG, "shard_ptrs_dev is null");
   IxArgs a;
   int rc = fill_args(&a, nullptr, nullptr, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather,
                      tail, reinterpret_cast<const float* const*>(shard_ptrs_dev), world);
   if (rc != RB_OK) return rc;
+  RB_CHECK_ARG(small_base >= 0 && small_base <= rows, RB_ERR_ARG, "small_base must lie in [0, rows]");
+  if (small_base < rows) {
+    const void* rep = shadow_ptrs_dev != nullptr ? small_rep_bf16 : static_cast<const void*>(small_rep);
+    RB_CHECK_ARG(rep != nullptr && (reinterpret_cast<uintptr_t>(rep) & 15) == 0, RB_ERR_ARG,
+                 "rows >= small_base need the local replica (bf16 with shadow shards, fp32 otherwise), 16 B aligned");
+    a.small_base = static_cast<uint32_t>(small_base);
+    a.small_rep = rep;
+  }
   if (B == 0) return RB_OK;
   RB_CHECK_ARG(x_save == nullptr || (reinterpret_cast<uintptr_t>(x_save) & 15) == 0, RB_ERR_ALIGN, "x_save not 16 B aligned");
   a.x_save = static_cast<__nv_bfloat16*>(x_save);
@@ -1166,12 +1225,33 @@ extern "C" int rb_dot_interaction_fwd_sharded(const void* const* shard_ptrs_dev,
   return launch_fwd<__nv_bfloat16>(a, D, static_cast<__nv_bfloat16*>(out), out_stride, static_cast<int>(out_stride), st);
 }
 
+extern "C" int rb_dot_interaction_bwd_sharded_split(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                                    int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                                    int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                                    int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
+                                                    float* d_dense, const void* x_saved, const int32_t* de_slot, float* dE_small,
+                                                    int32_t num_small, void* stream);
+
 extern "C" int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
                                               int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
                                               int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
                                               int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
                                               float* d_dense, const void* x_saved, void* stream) {
+  return rb_dot_interaction_bwd_sharded_split(shard_ptrs_dev, world, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D,
+                                              self_interaction, skip_gather, tail, dOut, dout_dtype, dout_stride, dE, d_dense, x_saved,
+                                              nullptr, nullptr, 0, stream);
+}
+
+extern "C" int rb_dot_interaction_bwd_sharded_split(const void* const* shard_ptrs_dev, int32_t world, int64_t rows, const void* idx,
+                                                    int32_t idx_type, const int64_t* field_row_offset, const float* dense_vec,
+                                                    int64_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t skip_gather,
+                                                    int32_t tail, const void* dOut, int32_t dout_dtype, int64_t dout_stride, float* dE,
+                                                    float* d_dense, const void* x_saved, const int32_t* de_slot, float* dE_small,
+                                                    int32_t num_small, void* stream) {
   RB_CHECK_ARG(shard_ptrs_dev != nullptr, RB_ERR_ARG, "shard_ptrs_dev is null");
+  RB_CHECK_ARG((de_slot == nullptr) == (dE_small == nullptr) && (de_slot == nullptr || (num_small >= 1 && num_small <= F && aligned_for(dE_small, 4) &&
+                                                                                       x_saved != nullptr && dE != nullptr)),
+               RB_ERR_ARG, "de_slot and dE_small come together, with 1 <= num_small <= F, saved operand rows and dE");
   IxArgs a;
   int rc = fill_args(&a, nullptr, nullptr, rows, idx, idx_type, field_row_offset, dense_vec, B, F, D, self_interaction, skip_gather,
                      tail, reinterpret_cast<const float* const*>(shard_ptrs_dev), world);
@@ -1179,6 +1259,9 @@ extern "C" int rb_dot_interaction_bwd_sharded(const void* const* shard_ptrs_dev,
   if (B == 0) return RB_OK;
   RB_CHECK_ARG(x_saved == nullptr || (reinterpret_cast<uintptr_t>(x_saved) & 15) == 0, RB_ERR_ALIGN, "x_saved not 16 B aligned");
   a.x_load = static_cast<const __nv_bfloat16*>(x_saved);
+  a.de_slot = de_slot;
+  a.dE_small = dE_small;
+  a.num_small = num_small;
   RB_CHECK_ARG(dOut != nullptr && dout_stride >= a.ncols + (a.tail ? D : 0), RB_ERR_ARG, "dOut is null or stride too small");
   RB_CHECK_ARG(dout_dtype == RB_F32 || dout_dtype == RB_BF16, RB_ERR_ARG, "bad dout_dtype %d", dout_dtype);
   RB_CHECK_ARG((dE == nullptr || aligned_for(dE, 4)) && (d_dense == nullptr || aligned_for(d_dense, 4)), RB_ERR_ALIGN,

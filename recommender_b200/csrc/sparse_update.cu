@@ -1217,6 +1217,78 @@ extern "C" int rb_sparse_bwd_mark_singletons(int64_t rows, int32_t D, int64_t n,
   return RB_OK;
 }
 
+// ---- tables replicated on every rank (p2p.py): one update from G short sorted (row, summed gradient) lists ------------------
+// list k (rank k's contribution) is `cap` records of D + 1 floats: D gradient values and the row id (int32 bits) in the last
+// one, rows ascending, padded behind the valid records with row ids >= rows.  One group of GS lanes per table row looks the row
+// up in every list (binary search), adds the hits in rank order and applies the optimizer once if any list held the row —
+// the lazy-update rule: untouched rows do not move.  Deterministic; every rank computes the same bits from the same lists.
+template <int VEC, int GS>
+__global__ void __launch_bounds__(256)
+replicated_rows_update_kernel(OptSink sink, int rows, const float* __restrict__ lists, int G, int cap) {
+  sink.prepare();
+  const int D = sink.D;
+  const int rec = D + 1;
+  const int r = (blockIdx.x * 256 + threadIdx.x) / GS;
+  const int lane = threadIdx.x % GS;
+  if (r >= rows) return;
+  const int c = lane * VEC;
+  const bool active = c < D;
+  Row<VEC> acc = zero_row<VEC>();
+  bool touched = false;
+  for (int k = 0; k < G; ++k) {
+    const float* L = lists + static_cast<int64_t>(k) * cap * rec;
+    int lo = 0, hi = cap;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__float_as_int(__ldg(L + static_cast<int64_t>(mid) * rec + D)) < r) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < cap && __float_as_int(__ldg(L + static_cast<int64_t>(lo) * rec + D)) == r) {
+      touched = true;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc.v[i] = __fadd_rn(acc.v[i], __ldg(L + static_cast<int64_t>(lo) * rec + c + i));
+      }
+    }
+  }
+  if (touched && active) {
+    const int64_t o = static_cast<int64_t>(r) * D + c;
+    Row<VEC> w = zero_row<VEC>(), m = zero_row<VEC>(), v = zero_row<VEC>();
+    w = ld_row_rw<VEC>(sink.table + o);
+    if (sink.opt != RB_OPT_SGD) m = ld_row_rw<VEC>(sink.s0 + o);
+    if (sink.opt == RB_OPT_ADAM_LAZY) v = ld_row_rw<VEC>(sink.s1 + o);
+    sink.template update_row<VEC>(o, acc, w, m, v);
+  }
+}
+
+extern "C" int rb_replicated_rows_update(float* table, float* state0, float* state1, int64_t rows, int32_t D, const float* lists,
+                                         int32_t num_lists, int64_t cap, const rb_opt_params* opt, void* shadow_bf16, void* stream) {
+  RB_CHECK_ARG(table != nullptr && lists != nullptr && opt != nullptr, RB_ERR_ARG, "table / lists / opt is null");
+  RB_CHECK_ARG(rows > 0 && rows < 0x7FFFFFFFll && num_lists >= 1 && num_lists <= RB_MAX_RANKS && cap >= 1 && cap < 0x7FFFFFFFll, RB_ERR_ARG,
+               "bad rows / num_lists / cap");
+  RowGeom geo;
+  RB_CHECK_ARG(row_geom(D, &geo) && D <= 128, RB_ERR_SHAPE, "unsupported embedding dim D=%d", D);
+  const int o = opt->optimizer;
+  RB_CHECK_ARG(o == RB_OPT_SGD || o == RB_OPT_ADAGRAD || o == RB_OPT_ADAM_LAZY, RB_ERR_ARG, "row-sparse optimizers only, got %d", o);
+  int rc = check_opt(opt, state0, state1, geo);
+  if (rc != RB_OK) return rc;
+  OptSink sink = make_sink(table, state0, state1, D, opt);
+  sink.shadow = static_cast<__nv_bfloat16*>(shadow_bf16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t threads = rows * geo.gs;
+#define RRU(V, GSZ) replicated_rows_update_kernel<V, GSZ><<<grid_for(threads, 256), 256, 0, st>>>(sink, static_cast<int>(rows), lists, num_lists, static_cast<int>(cap))
+  if (geo.vec == 4) {
+    if (geo.gs == 4) RRU(4, 4); else if (geo.gs == 8) RRU(4, 8); else if (geo.gs == 16) RRU(4, 16); else RRU(4, 32);
+  } else if (geo.vec == 2) {
+    if (geo.gs == 4) RRU(2, 4); else if (geo.gs == 8) RRU(2, 8); else if (geo.gs == 16) RRU(2, 16); else RRU(2, 32);
+  } else {
+    if (geo.gs == 4) RRU(1, 4); else if (geo.gs == 8) RRU(1, 8); else if (geo.gs == 16) RRU(1, 16); else RRU(1, 32);
+  }
+#undef RRU
+  RB_LAUNCH_CHECK("replicated_rows_update_kernel");
+  return RB_OK;
+}
+
 extern "C" int rb_sparse_bwd_update_groups(float* table, float* state0, float* state1, int64_t rows, int32_t D,
                                            const rb_lookup_group* groups, int32_t num_groups, const rb_opt_params* opt,
                                            void* ws, size_t ws_bytes, int32_t* oob_flag, void* stream) {

@@ -64,7 +64,7 @@ class DLRM(nn.Module):
     def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
                  num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, fused: bool = True, device=None,
                  compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
-                 collapse_linear: bool = False):
+                 collapse_linear: bool = False, table_rows: Optional[Sequence[int]] = None):
         super().__init__()
         if bottom_mlp_units[-1] != embedding_size:
             # ctr/model.py:52,55: the concat and the shape-asserting reshape need equal widths
@@ -75,7 +75,9 @@ class DLRM(nn.Module):
                               collapse_linear=collapse_linear)                                                 # :38
         self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator,
                            collapse_linear=collapse_linear)                                                    # :39
-        self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator)  # :42
+        # table_rows: one row count per field (BASELINE config 3's capped cardinalities) instead of num_tables x vocab_size
+        self.embedding_layer = Embedding(vocab_size, embedding_size, num_tables=num_tables, device=device, generator=generator,
+                                         table_rows=table_rows)                                                             # :42
         self.interaction = DotInteraction(False, True)                                                          # :43
         if fused:
             # the top tower's weight gradients wait until the interaction backward is queued (MLP.flush_wgrad)

@@ -183,7 +183,7 @@ class P2PShardedEmbedding(nn.Module):
 
     def __init__(self, input_dim: int, output_dim: int, *, num_tables: int = 1, link: PeerLink, device=None,
                  generator: Optional[torch.Generator] = None, capacity_factor: float = 1.25, bf16_shadow: bool = True,
-                 table_rows: Optional[Sequence[int]] = None):
+                 table_rows: Optional[Sequence[int]] = None, replicate_rows_upto: int = 0):
         super().__init__()
         self.link = link
         self.world, self.rank = link.world, link.rank
@@ -200,7 +200,39 @@ class P2PShardedEmbedding(nn.Module):
         # (the OOV / padding id 0 is the hottest row of every table, ctr/tfrecord_io.py:61-64) lands on different
         # ranks instead of piling up on rank 0; costs at most a few unused rows per table.
         self.table_rows = None if table_rows is None else [int(r) for r in table_rows]
-        if self.table_rows is not None:
+        # Tables of at most `replicate_rows_upto` rows are NOT sharded: every rank keeps a full copy (`small_table`), reads it
+        # locally in the forward, and all ranks apply the same update — each rank sums its own lookups' gradient rows per
+        # row, the G short (row, sum) lists are all-gathered, one sparse update over their concatenation runs everywhere.
+        # Row-wise sharding sends every lookup of a 3-row table to the same three owners: at the Criteo-Terabyte
+        # cardinalities 11 of 26 tables (42 % of the lookups) have <= 2208 rows.  Real ranks only (the update is a collective).
+        rows_list = self.table_rows if self.table_rows is not None else [self.input_dim] * self.num_tables
+        self._small = [t for t, r in enumerate(rows_list) if r <= int(replicate_rows_upto)] if (
+            int(replicate_rows_upto) > 0 and G > 1 and isinstance(link, DistPeerLink) and len(rows_list) > 1) else []
+        if len(self._small) == len(rows_list):
+            self._small = []                  # nothing left to shard: keep the plain layout
+        self.small_base = None
+        if self._small:
+            small_set = set(self._small)
+            big = [t for t in range(len(rows_list)) if t not in small_set]
+            starts, end = [0] * len(rows_list), 0
+            for j, t in enumerate(big):          # the sharded tables, staggered over the ranks like below
+                s0 = end + ((j % G) - end % G) % G
+                starts[t] = s0
+                end = s0 + rows_list[t]
+            shard_total = end
+            self.small_base = (shard_total + G - 1) // G * G       # virtual rows [small_base, total_rows): the replicated tables
+            off = 0
+            for t in self._small:
+                starts[t] = self.small_base + off
+                off += rows_list[t]
+            self.small_total = off
+            self.num_tables = len(rows_list)
+            self.table_rows = list(rows_list)
+            self._starts = starts
+            self.pitch = None
+            self._big = big
+            total = shard_total
+        elif self.table_rows is not None:
             # per-table row counts (BASELINE config 3): table t starts at the first row >= the previous table's end whose
             # owner is rank t mod G — the same staggering of the tables' hot id 0
             self.num_tables = len(self.table_rows)
@@ -220,7 +252,9 @@ class P2PShardedEmbedding(nn.Module):
             self._starts = [t * self.pitch for t in range(self.num_tables)]
             self.table_rows = [self.input_dim] * self.num_tables
             total = self.pitch * self.num_tables
-        self.total_rows = total
+        if not self._small:
+            self._big = list(range(self.num_tables))
+        self.total_rows = total if not self._small else self.small_base + self.small_total      # what the kernels range-check ids against
         self.local_rows = max((total - self.rank + G - 1) // G, 1)       # rows r with r mod G == rank
         shard_rows = max((total + G - 1) // G, 1)                        # same shape on every rank (rank 0's count)
         self._shard_full, self._shard_ptrs = link.alloc("shard", (shard_rows, self.output_dim), torch.float32)
@@ -229,14 +263,28 @@ class P2PShardedEmbedding(nn.Module):
         # bf16 shadow of the shard: what the other ranks' forwards read over NVLink (half the bytes, and exactly the
         # MMA operands); kept in step by the optimizer row update
         self.use_shadow = bool(bf16_shadow) and self.world > 1
+        self.small_table = self.small_shadow = None
         self._shadow_full = self._shadow_ptrs = self._shadow_ptr_dev = None
         if self.use_shadow:
             self._shadow_full, self._shadow_ptrs = link.alloc("shadow", (shard_rows, self.output_dim), torch.bfloat16)
             self.refresh_shadow()
         self._row_offset = (torch.tensor(self._starts, dtype=torch.int64, device=self.device) if self.num_tables > 1 else None)
-        self._starts_dev = torch.tensor(self._starts, dtype=torch.int64, device=self.device)
         self._rows_dev = torch.tensor(self.table_rows, dtype=torch.int64, device=self.device)
         self._unsharded_starts = torch.tensor([0] + self.table_rows[:-1], dtype=torch.int64, device=self.device).cumsum(0)
+        big_dev = torch.tensor(self._big, dtype=torch.int64, device=self.device)
+        self._starts_dev = torch.tensor(self._starts, dtype=torch.int64, device=self.device)[big_dev]      # sharded tables, ascending
+        self._big_rows_dev = self._rows_dev[big_dev]
+        self._big_unsharded_starts = self._unsharded_starts[big_dev]
+        self.small_state: Dict[str, torch.Tensor] = {}
+        if self._small:
+            D = self.output_dim
+            self.small_table = torch.empty(self.small_total + 1, D, dtype=torch.float32, device=self.device)   # + one scratch row
+            self.small_table.uniform_(-0.05, 0.05, generator=generator)
+            self.small_table[-1].zero_()
+            dist.broadcast(self.small_table, src=dist.get_global_rank(link.group, 0), group=link.group)         # one copy, everywhere
+            self.small_shadow = self.small_table.to(torch.bfloat16)
+            self._small_cols = torch.tensor(self._small, dtype=torch.int64, device=self.device)
+            self._small_rel_off = torch.tensor([self._starts[t] - self.small_base for t in self._small], dtype=torch.int64, device=self.device)
         self._anchor = torch.zeros((), dtype=torch.float32, device=self.device, requires_grad=True)
         self.opt_state: Dict[str, torch.Tensor] = {}
         self._shape = None           # (B_local, F) the step buffers were built for
@@ -247,6 +295,8 @@ class P2PShardedEmbedding(nn.Module):
         self._begun = None
         self._grad_ready = None
         self._apply_done = None
+        self._small_stream: Optional[torch.cuda.Stream] = None
+        self._small_done = None
 
     # ---- lazily built per-shape step buffers -----------------------------------------------------------------
     def _resolve(self, v):
@@ -274,6 +324,26 @@ class P2PShardedEmbedding(nn.Module):
         # the flag is mirrored into pinned host memory behind every collect (an async copy on the side stream, capturable),
         # so that the NEXT step's host code can notice an overflow without synchronising (poll_overflow)
         self._overflow_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        if self._small:
+            Fs = len(self._small)
+            ns = B * Fs
+            cap = min(ns, self.small_total)
+            self._small_cap = cap
+            self._idx_small = None                                      # [B, Fs] ids of the replicated tables' columns (built per step)
+            slot = torch.full((F,), -1, dtype=torch.int32)
+            slot[torch.tensor(self._small)] = torch.arange(Fs, dtype=torch.int32)
+            self._de_slot = slot.to(dev)
+            self._dE_small = torch.empty(B, Fs, D, dtype=torch.float32, device=dev)
+            self._su_rows = torch.empty(cap + 8, dtype=torch.int64, device=dev)
+            self._su_grad = torch.empty(cap + 8, D, dtype=torch.float32, device=dev)
+            self._su_num = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._cap_arange = torch.arange(cap, dtype=torch.int64, device=dev)
+            self._scratch_row = torch.full((1,), self.small_total, dtype=torch.int64, device=dev)
+            self._zero = torch.zeros((), dtype=torch.float32, device=dev)
+            # one record per (row, summed gradient): D gradient values + the row id as int32 bits (rb_replicated_rows_update)
+            self._pack_pad = torch.empty(cap, D + 1, dtype=torch.float32, device=dev)
+            self._pack_all = torch.empty(G, cap, D + 1, dtype=torch.float32, device=dev)
+            self._small_ws = ops.sparse_workspace(max(ns, 1), D, self.small_total, dev)
         self._shape = (B, F)
         self._side = torch.cuda.Stream(device=dev)
 
@@ -281,6 +351,8 @@ class P2PShardedEmbedding(nn.Module):
         """Re-derive the bf16 shadow from the fp32 shard (after loading weights; the optimizer keeps it in step afterwards)."""
         if self._shadow_full is not None:
             self._shadow_full.copy_(self._shard_full)
+        if self.small_shadow is not None:
+            self.small_shadow.copy_(self.small_table)
 
     def _shadow_ptrs_dev(self):
         if not self.use_shadow:
@@ -301,8 +373,8 @@ class P2PShardedEmbedding(nn.Module):
         g = torch.arange(self.local_rows, device=self.device, dtype=torch.int64) * self.world + self.rank   # global (staggered) row
         t = torch.searchsorted(self._starts_dev, g, right=True) - 1
         i = g - self._starts_dev[t]
-        ok = i < self._rows_dev[t]
-        return torch.where(ok, self._unsharded_starts[t] + i, torch.full_like(g, -1))
+        ok = i < self._big_rows_dev[t]
+        return torch.where(ok, self._big_unsharded_starts[t] + i, torch.full_like(g, -1))
 
     def cap_ids(self, ids: torch.Tensor) -> torch.Tensor:
         """row-in-table = id mod rows(table) for non-negative raw ids [B, num_tables]."""
@@ -314,7 +386,19 @@ class P2PShardedEmbedding(nn.Module):
         ids = self.full_row_ids()
         ok = ids >= 0
         self.embeddings[ok] = full[ids[ok]]
+        for t in self._small:
+            r, o = self.table_rows[t], self._starts[t] - self.small_base
+            u = int(self._unsharded_starts[t])
+            self.small_table[o:o + r] = full[u:u + r]
         self.refresh_shadow()
+
+    def small_into_full(self, full: torch.Tensor, local: Optional[torch.Tensor] = None) -> None:
+        """full[unsharded rows of the replicated tables] = this rank's copy (or `local`, a tensor shaped like it)."""
+        src = self.small_table if local is None else local
+        for t in self._small:
+            r, o = self.table_rows[t], self._starts[t] - self.small_base
+            u = int(self._unsharded_starts[t])
+            full[u:u + r] = src[o:o + r].to(full.device)
 
     def scatter_into_full(self, full: torch.Tensor, local: Optional[torch.Tensor] = None) -> None:
         """full[unsharded row] = this shard's rows (or `local`, e.g. an optimizer state of the same shape)."""
@@ -329,10 +413,15 @@ class P2PShardedEmbedding(nn.Module):
         B, F = idx.shape
         self._build(B, F)
         off = self._row_offset if self.num_tables > 1 else None
-        check(lib.rb_bucket_by_owner(idx.data_ptr(), ops._idx(idx), B * F, F, ops._ptr(off), 0, self.world,
-                                     self._b_rows.data_ptr(), self._b_perm.data_ptr(), self._inv_perm.data_ptr(),
-                                     self._b_counts.data_ptr(),
-                                     self._bucket_ws.data_ptr(), self._bucket_ws.numel(), ops._stream()), "rb_bucket_by_owner")
+        skip = self.small_base if self._small else (1 << 63) - 1      # lookups of the replicated tables belong to no owner
+        check(lib.rb_bucket_by_owner_skip(idx.data_ptr(), ops._idx(idx), B * F, F, ops._ptr(off), 0, self.world, skip,
+                                          self._b_rows.data_ptr(), self._b_perm.data_ptr(), self._inv_perm.data_ptr(),
+                                          self._b_counts.data_ptr(),
+                                          self._bucket_ws.data_ptr(), self._bucket_ws.numel(), ops._stream()), "rb_bucket_by_owner_skip")
+        if self._small:
+            if self._idx_small is None or self._idx_small.dtype != idx.dtype:
+                self._idx_small = torch.empty(B, len(self._small), dtype=idx.dtype, device=idx.device)
+            torch.index_select(idx, 1, self._small_cols, out=self._idx_small)
 
     def collect_and_sort(self) -> None:
         """Phase 2 (after every rank's route()): gather the pairs addressed to this owner and radix-sort them."""
@@ -356,13 +445,14 @@ class P2PShardedEmbedding(nn.Module):
         stride = (width + pad_to - 1) // pad_to * pad_to if out_dtype == torch.bfloat16 else width
         out = torch.empty(B, stride, dtype=out_dtype, device=idx.device)
         off = self._row_offset if self.num_tables > 1 else None
-        check(lib.rb_dot_interaction_fwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
-                                                 ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
-                                                 int(tail), out.data_ptr(),
-                                                 _lib.RB_BF16_ONES if (ones_col and out_dtype == torch.bfloat16 and stride > width)
-                                                 else ops._float_type(out_dtype), stride,
-                                                 self._x_saved.data_ptr() if self.save_rows else None, self._shadow_ptrs_dev(),
-                                                 ops._stream()), "rb_dot_interaction_fwd_sharded")
+        check(lib.rb_dot_interaction_fwd_sharded_rep(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
+                                                     ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
+                                                     int(tail), out.data_ptr(),
+                                                     _lib.RB_BF16_ONES if (ones_col and out_dtype == torch.bfloat16 and stride > width)
+                                                     else ops._float_type(out_dtype), stride,
+                                                     self._x_saved.data_ptr() if self.save_rows else None, self._shadow_ptrs_dev(),
+                                                     self.small_base if self._small else self.total_rows, ops._ptr(self.small_table),
+                                                     ops._ptr(self.small_shadow), ops._stream()), "rb_dot_interaction_fwd_sharded_rep")
         return out
 
     def _interaction_bwd(self, idx, dense_vec, flags, dOut):
@@ -371,12 +461,17 @@ class P2PShardedEmbedding(nn.Module):
         D = self.output_dim
         d_dense = torch.empty(B, D, dtype=torch.float32, device=idx.device)
         off = self._row_offset if self.num_tables > 1 else None
-        check(lib.rb_dot_interaction_bwd_sharded(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
-                                                 ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
-                                                 int(tail), dOut.data_ptr(), ops._float_type(dOut.dtype), int(dOut.stride(0)),
-                                                 self._dE.data_ptr(), d_dense.data_ptr(),
-                                                 self._x_saved.data_ptr() if self.save_rows else None, ops._stream()),
-              "rb_dot_interaction_bwd_sharded")
+        if self._small and not self.save_rows:
+            raise RuntimeError("replicated tables need save_rows=True (the backward reads the operand rows the forward saved)")
+        check(lib.rb_dot_interaction_bwd_sharded_split(self._shard_ptrs_dev().data_ptr(), self.world, self.total_rows, idx.data_ptr(),
+                                                       ops._idx(idx), ops._ptr(off), dense_vec.data_ptr(), B, F, D, int(si), int(sg),
+                                                       int(tail), dOut.data_ptr(), ops._float_type(dOut.dtype), int(dOut.stride(0)),
+                                                       self._dE.data_ptr(), d_dense.data_ptr(),
+                                                       self._x_saved.data_ptr() if self.save_rows else None,
+                                                       ops._ptr(self._de_slot) if self._small else None,      # replicated tables' rows
+                                                       ops._ptr(self._dE_small) if self._small else None,      # go to their own tensor
+                                                       len(self._small), ops._stream()),
+              "rb_dot_interaction_bwd_sharded_split")
         self._pending = True
         self._grad_ready = torch.cuda.current_stream().record_event()
         return d_dense
@@ -455,11 +550,62 @@ class P2PShardedEmbedding(nn.Module):
         else:
             side.wait_stream(torch.cuda.current_stream())
         self._grad_ready = None
+        if self._small:
+            # the replicated tables' update shares nothing with the sharded one but dE: its own stream, beside it
+            if self._small_stream is None:
+                self._small_stream = torch.cuda.Stream(device=self.device)
+            self._small_stream.wait_stream(side)
+            with torch.cuda.stream(self._small_stream):
+                self._apply_small(kind, opt, initial_accumulator_value)
+                self._small_done = self._small_stream.record_event()
         with torch.cuda.stream(side):
             self.link.barrier(1)                 # every rank's backward has written its dE and stopped reading the shards
             launch()
+            if self._small:
+                side.wait_event(self._small_done)
             self._apply_done = side.record_event()
         return self.n_local
+
+    def _apply_small(self, kind: str, opt, initial_accumulator_value: float) -> None:
+        """The replicated tables' step (current stream = side stream, after this rank's dE is written): local duplicate-row sum
+        (rb_sparse_bwd_dedup) -> all-gather of the G (row, sum) lists, padded to a static length with a scratch row ->
+        ONE sparse update over their concatenation (rb_sparse_bwd_update_groups), identical on every rank."""
+        B, F = self._shape
+        D, G, Fs, cap = self.output_dim, self.world, len(self._small), self._small_cap
+        st = self.small_state
+        if kind == "adam_lazy":
+            if "m" not in st:
+                st["m"], st["v"] = torch.zeros_like(self.small_table), torch.zeros_like(self.small_table)
+            s0, s1 = st["m"], st["v"]
+        elif kind == "adagrad":
+            if "acc" not in st:
+                st["acc"] = torch.full_like(self.small_table, initial_accumulator_value)
+            s0, s1 = st["acc"], None
+        else:
+            s0 = s1 = None
+        self._small_reduce()
+        self._small_exchange()
+        self._small_update(s0, s1, opt)
+
+    def _small_reduce(self) -> None:
+        B, F = self._shape
+        D, G, Fs, cap = self.output_dim, self.world, len(self._small), self._small_cap
+        grad = ops.GradSource.per_position(self._dE_small, Fs).to_c()        # written by the backward itself (de_slot)
+        check(lib.rb_sparse_bwd_dedup(self.small_total, D, self._idx_small.data_ptr(), ops._idx(self._idx_small), B * Fs, Fs,
+                                      self._small_rel_off.data_ptr(), 0, C.byref(grad), self._su_rows.data_ptr(), self._su_grad.data_ptr(),
+                                      self._su_num.data_ptr(), self._small_ws.data_ptr(), self._small_ws.numel(),
+                                      ops._ptr(ops.oob_flag(self.device)), ops._stream()), "rb_sparse_bwd_dedup (replicated tables)")
+        valid = self._cap_arange < self._su_num                    # records behind the last unique row: scratch id, zero gradient
+        self._pack_pad[:, :D].copy_(torch.where(valid[:, None], self._su_grad[:cap], self._zero))
+        self._pack_pad.view(torch.int32)[:, D].copy_(torch.where(valid, self._su_rows[:cap], self._scratch_row))
+
+    def _small_exchange(self) -> None:
+        dist.all_gather_into_tensor(self._pack_all.view(-1, self.output_dim + 1), self._pack_pad, group=self.link.group)
+
+    def _small_update(self, s0, s1, opt) -> None:
+        check(lib.rb_replicated_rows_update(self.small_table.data_ptr(), ops._ptr(s0), ops._ptr(s1), self.small_total, self.output_dim,
+                                            self._pack_all.data_ptr(), self.world, self._small_cap, C.byref(opt),
+                                            ops._ptr(self.small_shadow), ops._stream()), "rb_replicated_rows_update")
 
     def _apply_rows(self, s0, s1, opt) -> None:
         """The C call of the apply phase, on the current (side) stream: what bench.py brackets with CUDA events."""
@@ -499,7 +645,8 @@ class P2PShardedDLRM(nn.Module):
     def __init__(self, bottom_mlp_units: Sequence[int], top_mlp_units: Sequence[int], embedding_size: int, vocab_size: int,
                  num_cat_fea: int, num_int_fea: int, *, num_tables: int = 1, group=None, link: Optional[PeerLink] = None, device=None,
                  compute_dtype: Optional[torch.dtype] = None, generator: Optional[torch.Generator] = None,
-                 capacity_factor: float = 1.25, bf16_shadow: bool = True, table_rows: Optional[Sequence[int]] = None):
+                 capacity_factor: float = 1.25, bf16_shadow: bool = True, table_rows: Optional[Sequence[int]] = None,
+                 replicate_rows_upto: int = 0):
         super().__init__()
         if bottom_mlp_units[-1] != embedding_size:
             raise ValueError("bottom_mlp_units[-1] must equal embedding_size")       # ctr/model.py:52,55
@@ -509,7 +656,7 @@ class P2PShardedDLRM(nn.Module):
         self.top_mlp = MLP(top_mlp_units, "sigmoid", compute_dtype=compute_dtype, generator=generator)
         self.embedding_layer = P2PShardedEmbedding(vocab_size, embedding_size, num_tables=num_tables, link=self.link, device=device,
                                                    generator=generator, capacity_factor=capacity_factor, bf16_shadow=bf16_shadow,
-                                                   table_rows=table_rows)
+                                                   table_rows=table_rows, replicate_rows_upto=replicate_rows_upto)
         self.num_cat_fea, self.num_int_fea, self.embedding_size = num_cat_fea, num_int_fea, embedding_size
         self._synced = False
         self._flat = None

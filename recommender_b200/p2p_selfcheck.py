@@ -43,7 +43,7 @@ def synth_batch(B, V, seed, num_cat=26, num_int=13):
 
 
 def run(dev: torch.device, *, compute_dtype: Optional[torch.dtype] = None, V: int = 5000, D: int = 32, B: int = 512, T: int = 26,
-        steps: int = 3, group=None) -> Optional[Dict[str, float]]:
+        steps: int = 3, group=None, table_rows=None, replicate_rows_upto: int = 0) -> Optional[Dict[str, float]]:
     """Collective over `group`.  Returns {'max_abs_table_diff', 'max_abs_prob_diff', 'rows_moved', 'steps', ...} on rank 0,
     None elsewhere."""
     from .model import DLRM, bce_clipped
@@ -51,13 +51,20 @@ def run(dev: torch.device, *, compute_dtype: Optional[torch.dtype] = None, V: in
     from .p2p import P2PShardedDLRM
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bottom, top = [64, D], [64, 1]
-    params = init_params(4, bottom, top, D, V * T)
-    model = P2PShardedDLRM(bottom, top, D, V, 26, 13, num_tables=T, device=dev, compute_dtype=compute_dtype, group=group)
+    rows_list = [V] * T if table_rows is None else [int(r) for r in table_rows]
+    total = sum(rows_list)
+    cards = np.array(rows_list, dtype=np.int64)[None]
+    params = init_params(4, bottom, top, D, total)
+    model = P2PShardedDLRM(bottom, top, D, V, 26, 13, num_tables=T, device=dev, compute_dtype=compute_dtype, group=group,
+                           table_rows=table_rows, replicate_rows_upto=replicate_rows_upto,
+                           capacity_factor=2.0 if table_rows is not None else 1.25)
     model.embedding_layer.load_full_table(torch.tensor(params["table"]))
     model.bottom_mlp.load_arrays(params["bottom"], dev)
     model.top_mlp.load_arrays(params["top"], dev)
     opt = Adam()
     batches = [[synth_batch(B, V, seed=100 * s + r) for r in range(world)] for s in range(steps)]
+    if table_rows is not None:       # ids folded into every table's own cardinality
+        batches = [[(c % cards, d, l) for c, d, l in per_rank] for per_rank in batches]
     prob = None
     for s in range(steps):
         cat, dense_x, label = (torch.tensor(a, device=dev) for a in batches[s][rank])
@@ -77,13 +84,19 @@ def run(dev: torch.device, *, compute_dtype: Optional[torch.dtype] = None, V: in
     all_rows = [torch.empty_like(rows) for _ in range(world)]
     dist.all_gather(all_ids, ids, group=group)
     dist.all_gather(all_rows, rows, group=group)
+    replica_diff = 0.0
+    if emb.small_table is not None:          # every rank's copy of the replicated tables must hold the same bits
+        copies = [torch.empty_like(emb.small_table) for _ in range(world)]
+        dist.all_gather(copies, emb.small_table.contiguous(), group=group)
+        replica_diff = max(float((c - copies[0]).abs().max().item()) for c in copies)
     out = None
     if rank == 0:
-        full = torch.empty(V * T, D, device=dev)
+        full = torch.empty(total, D, device=dev)
         for k in range(world):
             okk = all_ids[k] >= 0
             full[all_ids[k][okk]] = all_rows[k][okk]
-        ref = DLRM(bottom, top, D, V, 26, 13, num_tables=T, device=dev, compute_dtype=compute_dtype)
+        emb.small_into_full(full)
+        ref = DLRM(bottom, top, D, V, 26, 13, num_tables=T, device=dev, compute_dtype=compute_dtype, table_rows=table_rows)
         ref.embedding_layer.embeddings.copy_(torch.tensor(params["table"]))
         ref.bottom_mlp.load_arrays(params["bottom"], dev)
         ref.top_mlp.load_arrays(params["top"], dev)
@@ -103,8 +116,10 @@ def run(dev: torch.device, *, compute_dtype: Optional[torch.dtype] = None, V: in
         got, want = full.cpu().numpy(), ref.embedding_layer.embeddings.cpu().numpy()
         moved = np.abs(want - params["table"]) > 0
         out = dict(max_abs_table_diff=float(np.abs(got - want).max()), max_abs_prob_diff=float((prob.detach() - rprob).abs().max().item()),
-                   rows_moved=int(moved.any(1).sum()), steps=steps, world=world,
-                   config=f"DLRM D={D}, {T} x {V}-row tables, B_local={B}, Zipf ids + 2% id 0, "
+                   rows_moved=int(moved.any(1).sum()), steps=steps, world=world, replicated_tables=len(emb._small),
+                   replica_max_abs_diff=replica_diff,
+                   config=f"DLRM D={D}, " + (f"{T} x {V}-row tables" if table_rows is None else f"tables of {min(rows_list)}..{max(rows_list)} rows") +
+                          f", B_local={B}, Zipf ids + 2% id 0, "
                           f"{'bf16' if compute_dtype == torch.bfloat16 else 'fp32'} towers, Adam (lazy rows)")
     dist.barrier(group=group)
     return out

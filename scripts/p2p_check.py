@@ -24,10 +24,15 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from recommender_b200 import p2p_selfcheck
     ok = True
-    for dtype, tol in ((None, 2e-6), (torch.bfloat16, 1e-4)):
-        res = p2p_selfcheck.run(dev, compute_dtype=dtype)
+    unequal = [5000] * 20 + [3, 14, 63, 155, 976, 2208]          # small tables beside sharded ones (BASELINE config 3 in miniature)
+    cases = [(None, 2e-6, {}), (torch.bfloat16, 1e-4, {}),
+             (None, 2e-6, dict(table_rows=unequal)), (None, 2e-6, dict(table_rows=unequal, replicate_rows_upto=4096)),
+             (torch.bfloat16, 1e-4, dict(table_rows=unequal, replicate_rows_upto=4096))]
+    for dtype, tol, kw in cases:
+        res = p2p_selfcheck.run(dev, compute_dtype=dtype, **kw)
         if rank == 0:
-            good = res["max_abs_table_diff"] <= tol and res["rows_moved"] > 0
+            good = res["max_abs_table_diff"] <= tol and res["rows_moved"] > 0 and res["replica_max_abs_diff"] == 0.0
+            good &= res["replicated_tables"] == (6 if kw.get("replicate_rows_upto") else 0)
             ok &= good
             print("p2p_check:", json.dumps(res), "OK" if good else "MISMATCH", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
