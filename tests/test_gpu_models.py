@@ -363,7 +363,8 @@ def test_two_real_ranks_sharded_equals_unsharded(cuda_lib):
                         "--master-port", "29541", os.path.join(repo, "scripts", "p2p_check.py")], capture_output=True, text=True, timeout=600,
                        env=env, cwd=repo)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") >= 2
+    assert r.stdout.count("OK") >= 5         # equal tables (fp32 / bf16 towers), unequal tables, and the small ones replicated (fp32 / bf16)
+    assert '"replicated_tables": 6' in r.stdout
 
 
 # ---- BASELINE config 2 at full size AGAINST THE NUMPY ORACLE (not only properties) ----------------------------------------
