@@ -746,11 +746,12 @@ def hash_ids(ids, vocab: int, world: int = 1):
     return rows, owner, local
 
 
-def bucket_by_owner(idx, world: int, *, L=1, field_row_offset=None, hash_mod=0):
-    """Stable partition of the lookups by owner rank = row mod world (rb_bucket_by_owner).
+def bucket_by_owner(idx, world: int, *, L=1, field_row_offset=None, hash_mod=0, skip_from_row=None):
+    """Stable partition of the lookups by owner rank = row mod world (rb_bucket_by_owner / rb_bucket_by_owner_skip).
 
     Returns (local_rows int64[n] in bucket order, perm int32[n]: bucket slot -> lookup position,
-    inv_perm int32[n]: lookup position -> bucket slot, counts int64[world])."""
+    inv_perm int32[n]: lookup position -> bucket slot, counts int64[world]).  skip_from_row: lookups whose row is >= it belong
+    to no owner (rows of replicated tables): not counted, no slot, inv_perm = -1; only the first sum(counts) slots are written."""
     _need_cuda(idx, field_row_offset)
     idx = idx.contiguous()
     n = idx.numel()
@@ -760,6 +761,11 @@ def bucket_by_owner(idx, world: int, *, L=1, field_row_offset=None, hash_mod=0):
     inv_perm = torch.empty(n, dtype=torch.int32, device=dev)
     counts = torch.empty(world, dtype=torch.int64, device=dev)
     ws = _workspace(max(lib.rb_bucket_by_owner_workspace_bytes(n, world), 256), dev)
+    if skip_from_row is not None:
+        check(lib.rb_bucket_by_owner_skip(_ptr(idx), _idx(idx), n, int(L), _ptr(field_row_offset), int(hash_mod), int(world), int(skip_from_row),
+                                          _ptr(local_rows), _ptr(perm), _ptr(inv_perm), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
+              "rb_bucket_by_owner_skip")
+        return local_rows, perm, inv_perm, counts
     check(lib.rb_bucket_by_owner(_ptr(idx), _idx(idx), n, int(L), _ptr(field_row_offset), int(hash_mod), int(world),
                                  _ptr(local_rows), _ptr(perm), _ptr(inv_perm), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
           "rb_bucket_by_owner")
