@@ -733,6 +733,12 @@ def run_b200(args):
                                  frac=gbs / peak, share_of_step=ms * cnt / k_eager / ms_step)
         else:
             kernels[name] = dict(ms=ms, calls_per_step=cnt / k_eager, share_of_step=ms * cnt / k_eager / ms_step)
+    for name in ("dense_opt_step", "colsum"):
+        if name in kernels:
+            # these small launches are bracketed on the main stream while the row update fills the SMs from its side stream: the
+            # event time is mostly time QUEUED for an SM, not kernel time (dense_opt_kernel alone: ~13 us; profiles/r2_20_timeline.txt)
+            kernels[name]["note"] = "event time on the main stream beside the side-stream row update: includes queueing for SMs; ms is not kernel time"
+            kernels[name].pop("share_of_step", None)
     roofline = None
     timed = {k: v for k, v in kernels.items() if "achieved_gbs" in v}
     if timed:
