@@ -419,6 +419,16 @@ int rb_dense_head_bwd(const float* dout, const float* out, int32_t activation, c
                       const void* w, void* dx, int64_t lddx, float* dw, float* db, float* dx_colsum, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* Dense(1) + sigmoid, the clipped binary cross-entropy of its output (rb_bce_clipped's formulas, batch mean) and the head's
+ * backward seeded with d loss = 1, in ONE pass over x: prob f32[rows], loss f32[1], dx bf16 [rows, in_dim] (optional), dw f32[in_dim],
+ * db f32[1], dx_colsum (optional) — bit-identical to rb_dense_head_fwd -> rb_bce_clipped -> rb_dense_head_bwd except for the order
+ * the loss terms are added.  ctr/model.py:56-57 + ctr/train.py:85-87,97 for models ending in Dense(1, sigmoid).
+ * in_dim in {8, 16, 32, 64, 128, 256}; label_type: 0 = f32, 1 = i64. */
+size_t rb_dense_head_bce_workspace_bytes(int64_t rows, int32_t in_dim);
+int rb_dense_head_bce(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, const float* bias, const void* label,
+                      int32_t label_type, float* prob, float* loss, void* dx, int64_t lddx, float* dw, float* db, float* dx_colsum,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* out_bf16[i] = bf16(dy[i] * activation'(y[i])) over n contiguous f32 elements: the ReluGrad / SigmoidGrad in front of the
  * last layer's gradient GEMMs. */
 int rb_dense_act_bwd(const float* dy, const float* y, int32_t activation, int64_t n, void* out_bf16, void* stream);

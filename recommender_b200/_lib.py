@@ -128,6 +128,8 @@ SIGNATURES = {
     "rb_dense_head_bwd_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "rb_dense_head_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
     "rb_dense_act_bwd": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "rb_dense_head_bce_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "rb_dense_head_bce": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
     "rb_dense_act_bwd_bf16": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
     "rb_din_workspace_bytes": (C.c_size_t, [_i64]),
     "rb_din_offsets": (C.c_int, [C.POINTER(RbDinHistory), _p, _p, C.c_size_t, _p]),

@@ -814,6 +814,150 @@ head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, i
 }
 
 // one warp per output column: lane l adds partials l, l + 32, ... (independent loads), then a fixed shuffle tree
+// Dense(1) + sigmoid, the clipped binary cross-entropy of its output and the head's backward in ONE pass over x (ctr/model.py:56-57,
+// ctr/train.py:85-87,97 for the model whose last layer is Dense(1, sigmoid)): the three-kernel sequence head_fwd -> bce -> head_bwd
+// reads x twice and sits on the step's critical path with ~8 small launches (50 us of a 1.33 ms step, profiles/r2_20_timeline.txt).
+// Same thread layout, row partition and accumulation order as head_bwd_kernel, same dot-product order as head_fwd_kernel, same
+// loss / dprob formulas as bce_partial_kernel (dense.cu): prob, dx, dW, db and the dx column sums come out bit-identical to the
+// unfused sequence; the loss differs only in the order its per-row terms are added.  The backward is seeded with d loss = 1.
+// vcols = in_dim / 8 must be a power of two <= 32 (a row's threads are lanes of one warp).
+__global__ void __launch_bounds__(kHeadBwdThreads)
+head_bce_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                const float* __restrict__ bias, const void* __restrict__ label, int label_is_i64, float inv_n, float* __restrict__ prob,
+                __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partial /* [grid, 2 * in_dim + 2]: dW | db | colsums | loss */) {
+  const int vcols = in_dim / 8;
+  const int row_lanes = kHeadBwdThreads / vcols;
+  const int vc = threadIdx.x % vcols, rl = threadIdx.x / vcols;
+  __shared__ float s_red[kHeadBwdThreads * 8];
+  __shared__ float s_db[kHeadBwdThreads];
+  __shared__ float s_loss[kHeadBwdThreads];
+  const int pstride = 2 * in_dim + 2;
+  const float eps = 1e-7f;
+  float acc[8], cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = cs[k] = 0.f;
+  float db = 0.f, loss = 0.f;
+  float wf[8];
+  {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + vc * 8));
+    const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wf[2 * j] = __uint_as_float(ws[j] << 16);
+      wf[2 * j + 1] = __uint_as_float(ws[j] & 0xFFFF0000u);
+    }
+  }
+  const float b0 = bias != nullptr ? __ldg(bias) : 0.f;
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * per, r1 = min(r0 + per, rows);
+  // every lane of a warp runs the same number of iterations (rows of one warp are r, r + 1, ... for its 32 / vcols groups):
+  // the shuffles below need the full warp
+  const int64_t n_iter = (r1 - r0 + row_lanes - 1) / row_lanes;
+  constexpr int kU = 4;                                   // rows whose x (and label) loads are in flight together per thread
+  for (int64_t it0 = 0; it0 < n_iter; it0 += kU) {
+    uint32_t xs[kU][4];
+    float yv[kU];
+    bool live[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t r = r0 + rl + (it0 + u) * row_lanes;
+      live[u] = (it0 + u < n_iter) && r < r1;
+      xs[u][0] = xs[u][1] = xs[u][2] = xs[u][3] = 0u;
+      yv[u] = 0.f;
+      if (live[u]) {
+        const uint4 xv = __ldcs(reinterpret_cast<const uint4*>(x + r * ldx + vc * 8));
+        xs[u][0] = xv.x; xs[u][1] = xv.y; xs[u][2] = xv.z; xs[u][3] = xv.w;
+        yv[u] = label_is_i64 ? static_cast<float>(static_cast<const int64_t*>(label)[r]) : static_cast<const float*>(label)[r];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (it0 + u >= n_iter) break;                       // uniform over the CTA
+      const int64_t r = r0 + rl + (it0 + u) * row_lanes;
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        z = fmaf(__uint_as_float(xs[u][j] << 16), wf[2 * j], z);
+        z = fmaf(__uint_as_float(xs[u][j] & 0xFFFF0000u), wf[2 * j + 1], z);
+      }
+      for (int o = 16; o > 0; o >>= 1) {                 // offsets >= vcols add lanes of other rows: skipped
+        const float t = __shfl_xor_sync(0xffffffffu, z, o);
+        if (o < vcols) z += t;
+      }
+      if (!live[u]) continue;
+      const float p = apply_activation(z + b0, RB_ACT_SIGMOID);
+      const float y = yv[u];
+      const float pc = fminf(fmaxf(p, eps), 1.0f - eps);
+      const float a = pc + eps, bq = (1.0f - pc) + eps;
+      const bool pass = (p >= eps) && (p <= 1.0f - eps);
+      const float dprob = pass ? (-(y / a) + (1.0f - y) / bq) * inv_n : 0.f;
+      const float dz = dprob * p * (1.0f - p);
+      if (vc == 0) {
+        prob[r] = p;
+        loss += -(y * logf(a) + (1.0f - y) * logf(bq));
+        db += dz;
+      }
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] = fmaf(__uint_as_float(xs[u][j] << 16), dz, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(__uint_as_float(xs[u][j] & 0xFFFF0000u), dz, acc[2 * j + 1]);
+        __nv_bfloat162 h = __floats2bfloat162_rn(dz * wf[2 * j], dz * wf[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        cs[2 * j] += __uint_as_float(pk[j] << 16);
+        cs[2 * j + 1] += __uint_as_float(pk[j] & 0xFFFF0000u);
+      }
+      if (dx != nullptr) __stcs(reinterpret_cast<uint4*>(dx + r * lddx + vc * 8), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = acc[k];
+  s_db[threadIdx.x] = db;
+  s_loss[threadIdx.x] = loss;
+  __syncthreads();
+  for (int c = threadIdx.x; c < in_dim; c += kHeadBwdThreads) {
+    float t = 0.f;
+    for (int l = 0; l < row_lanes; ++l) t += s_red[(l * vcols + c / 8) * 8 + (c % 8)];
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + c] = t;
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f, tl = 0.f;
+    for (int l = 0; l < row_lanes; ++l) {
+      t += s_db[l * vcols];
+      tl += s_loss[l * vcols];
+    }
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + in_dim] = t;
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + 2 * in_dim + 1] = tl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = cs[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < in_dim; c += kHeadBwdThreads) {
+    float t = 0.f;
+    for (int l = 0; l < row_lanes; ++l) t += s_red[(l * vcols + c / 8) * 8 + (c % 8)];
+    partial[static_cast<int64_t>(blockIdx.x) * pstride + in_dim + 1 + c] = t;
+  }
+}
+
+// partial[parts][2 * in_dim + 2] -> dW | db | dx column sums | loss (mean), CTA order
+__global__ void __launch_bounds__(256)
+head_bce_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float inv_n, float* __restrict__ dW, float* __restrict__ db,
+                      float* __restrict__ dx_colsum, float* __restrict__ loss) {
+  const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int pstride = 2 * in_dim + 2;
+  if (c >= pstride) return;
+  float t = 0.f;
+  for (int p = lane; p < parts; p += 32) t += partial[static_cast<int64_t>(p) * pstride + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane != 0) return;
+  if (c < in_dim) dW[c] = t;
+  else if (c == in_dim) db[0] = t;
+  else if (c == 2 * in_dim + 1) loss[0] = t * inv_n;
+  else if (dx_colsum != nullptr) dx_colsum[c - in_dim - 1] = t;
+}
+
 __global__ void __launch_bounds__(256)
 head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db,
                       float* __restrict__ dx_colsum) {
@@ -1242,6 +1386,37 @@ extern "C" int rb_dense_head_bwd(const float* dout, const float* out, int32_t ac
   RB_LAUNCH_CHECK("head_bwd_kernel");
   head_bwd_final_kernel<<<(2 * in_dim + 1 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, dw, db, dx_colsum);
   RB_LAUNCH_CHECK("head_bwd_final_kernel");
+  return RB_OK;
+}
+
+extern "C" size_t rb_dense_head_bce_workspace_bytes(int64_t rows, int32_t in_dim) {
+  if (rows <= 0 || in_dim <= 0) return 0;
+  return static_cast<size_t>(head_parts(rows)) * (2 * in_dim + 2) * sizeof(float) + 256;
+}
+
+extern "C" int rb_dense_head_bce(const void* x, int64_t rows, int32_t in_dim, int64_t ldx, const void* w, const float* bias, const void* label,
+                                 int32_t label_type, float* prob, float* loss, void* dx, int64_t lddx, float* dw, float* db, float* dx_colsum,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  RB_CHECK_ARG(x != nullptr && w != nullptr && label != nullptr && prob != nullptr && loss != nullptr && dw != nullptr && db != nullptr, RB_ERR_ARG,
+               "a required pointer is null");
+  RB_CHECK_ARG(label_type == 0 || label_type == 1, RB_ERR_ARG, "label_type: 0 = f32, 1 = i64");
+  const int vcols = in_dim / 8;
+  RB_CHECK_ARG(rows > 0 && in_dim >= 8 && in_dim % 8 == 0 && vcols <= 32 && (vcols & (vcols - 1)) == 0 && ldx % 8 == 0 && ldx >= in_dim &&
+                   (dx == nullptr || (lddx % 8 == 0 && lddx >= in_dim)),
+               RB_ERR_SHAPE, "fused head + loss: in_dim in {8, 16, 32, 64, 128, 256}, leading dimensions multiples of 8");
+  RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0, RB_ERR_ALIGN,
+               "head: x / w / dx not 16-byte aligned");
+  RB_CHECK_ARG(ws != nullptr && ws_bytes >= rb_dense_head_bce_workspace_bytes(rows, in_dim), RB_ERR_WORKSPACE,
+               "workspace too small: need %zu bytes, got %zu", rb_dense_head_bce_workspace_bytes(rows, in_dim), ws_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int parts = head_parts(rows);
+  const float inv_n = 1.0f / static_cast<float>(rows);
+  head_bce_kernel<<<parts, kHeadBwdThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w),
+                                                     bias, label, label_type, inv_n, prob, static_cast<__nv_bfloat16*>(dx), lddx,
+                                                     static_cast<float*>(ws));
+  RB_LAUNCH_CHECK("head_bce_kernel");
+  head_bce_final_kernel<<<(2 * in_dim + 2 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, inv_n, dw, db, dx_colsum, loss);
+  RB_LAUNCH_CHECK("head_bce_final_kernel");
   return RB_OK;
 }
 

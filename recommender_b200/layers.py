@@ -534,6 +534,8 @@ class _DenseStackFn(torch.autograd.Function):
         n = len(Ws)
         in_dim, final_activation = mlp.in_dim, mlp.final_activation
         raw = x.dtype != torch.bfloat16
+        label, mlp._bce_label = mlp._bce_label, None          # set by MLP.forward(bce_label=...): fuse the loss into the head
+        fused_head = None
         if raw:
             ones_col = Kp > in_dim
             x = ops.dense_pack_input(x.float(), Kp, ones_col)
@@ -544,7 +546,14 @@ class _DenseStackFn(torch.autograd.Function):
             last = i == n - 1
             Wp = _LinearBF16Fn._bf16_shadow(W, Kp if i == 0 else None)
             shadows.append(Wp)
-            if last and W.shape[1] == 1:
+            if last and W.shape[1] == 1 and label is not None:
+                # Dense(1, sigmoid) + clipped BCE + the head's backward in one pass over h (rb_dense_head_bce): `out` is the LOSS
+                want_dx = n > 1 or need_dx
+                want_cs = n > 1 and not (n == 2 and bool(ones_col) and Kp > in_dim)
+                prob, out, dxh, dwh, dbh, csh = ops.dense_head_bce(h, Wp.reshape(-1), b, label, want_dx=want_dx, want_dx_colsum=want_cs)
+                fused_head = (dxh, dwh, dbh, csh)
+                mlp.last_prob = prob
+            elif last and W.shape[1] == 1:
                 out = ops.dense_head_fwd(h, Wp.reshape(-1), b, final_activation).reshape(-1, 1)
             elif last:
                 out = ops.dense_fwd(h, Wp, b, final_activation, torch.float32)
@@ -553,6 +562,7 @@ class _DenseStackFn(torch.autograd.Function):
                 acts.append(h)
         ctx.save_for_backward(out, *acts, *shadows)
         ctx.mlp, ctx.n, ctx.ones_col, ctx.need_dx, ctx.raw = mlp, n, bool(ones_col) and Kp > in_dim, need_dx, raw
+        ctx.fused_head = fused_head
         return out
 
     @staticmethod
@@ -604,9 +614,12 @@ class _DenseStackFn(torch.autograd.Function):
         if Wp.shape[1] == 1:
             # the head also sums the columns of the dx it writes: the bias gradient of the layer below, without re-reading dx
             want_cs = n > 1 and not (n == 2 and ctx.ones_col)
-            res = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), act, h, Wp.reshape(-1), want_dx=want_dx, want_dx_colsum=want_cs)
-            dy, dw, db = res[:3]
-            head_cs = res[3] if want_cs else None
+            if ctx.fused_head is not None:        # computed with the loss in the forward (d loss = 1: `dout` is the seed of backward())
+                dy, dw, db, head_cs = ctx.fused_head
+            else:
+                res = ops.dense_head_bwd(dout.reshape(-1), out.reshape(-1), act, h, Wp.reshape(-1), want_dx=want_dx, want_dx_colsum=want_cs)
+                dy, dw, db = res[:3]
+                head_cs = res[3] if want_cs else None
             dw = dw[:in_dim] if n == 1 else dw
             for p_, g_ in ((Ws[n - 1], dw.reshape(-1, 1)), (bs[n - 1], db)):
                 if p_.grad is None:
@@ -710,6 +723,8 @@ class MLP(nn.Module):
         self._wgrad_done: Optional[torch.cuda.Event] = None
         self._wgrad_keep: list = []
         self._wgrad_join_queued = False
+        self._bce_label = None                            # one-shot: the next tcgen05 forward fuses Dense(1, sigmoid) + clipped BCE
+        self.last_prob: Optional[torch.Tensor] = None     # probabilities of the last fused-loss forward
         self.defer_wgrad = False                          # hold the weight-gradient products back until flush_wgrad()
         self._wgrad_deferred: list = []
         if final_activation not in (None, "relu", "sigmoid"):
@@ -808,11 +823,24 @@ class MLP(nn.Module):
             x = torch.sigmoid(x)
         return x
 
-    def forward(self, x: torch.Tensor, ones_col: bool = False) -> torch.Tensor:
+    def can_fuse_bce(self, x: torch.Tensor) -> bool:
+        """The last layer is Dense(1, sigmoid) on the tcgen05 path with a width rb_dense_head_bce serves."""
+        return (self.compute_dtype == torch.bfloat16 and len(self.kernels) >= 1 and self.final_activation == "sigmoid"
+                and int(self.kernels[-1].shape[1]) == 1 and ops.dense_head_bce_ok(int(self.kernels[-1].shape[0]))
+                and not (self.collapse_linear and len(self.kernels) >= 2) and self._tcgen05_ok(x))
+
+    def forward(self, x: torch.Tensor, ones_col: bool = False, bce_label: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ones_col=True: x arrives bf16, padded, with pad column `in_dim` already set to 1.0 (the fused interaction
-        kernel does that), which lets the first layer read its bias gradient off the weight-gradient GEMM."""
+        kernel does that), which lets the first layer read its bias gradient off the weight-gradient GEMM.
+        bce_label (only when can_fuse_bce(x)): returns the LOSS f32[1] = mean clipped binary cross-entropy of the probabilities
+        against the labels instead of the probabilities — head, loss and the head's backward in one kernel; the backward pass
+        must be seeded with 1 (loss.backward())."""
         if len(self.kernels) == 0:
             self.build(x.shape[-1], x.device)
+        if bce_label is not None:
+            if not self.can_fuse_bce(x):
+                raise RuntimeError("bce_label needs the bf16 tcgen05 path and a Dense(1, sigmoid) head of 8..256 inputs")
+            self._bce_label = bce_label.contiguous()
         collapse = self.collapse_linear and len(self.kernels) >= 2
         if self.compute_dtype is None:
             if collapse:

@@ -85,9 +85,20 @@ class DLRM(nn.Module):
             self.embedding_layer.after_grad_hooks.append(self.top_mlp.flush_wgrad)
         self.num_cat_fea, self.num_int_fea, self.embedding_size, self.fused = num_cat_fea, num_int_fea, embedding_size, fused
 
-    def forward(self, inputs, training=None, mask=None):
+    def forward_bce(self, inputs, label: torch.Tensor) -> torch.Tensor:
+        """bce_clipped(self(inputs), label) — ctr/model.py:45-58 + the loss of ctr/train.py:85-87 — with the last Dense(1, sigmoid),
+        the loss and the head's backward in ONE kernel (rb_dense_head_bce) when the top tower runs on the bf16 tcgen05 path; the
+        probabilities are left in `self.top_mlp.last_prob`.  Same numbers as the two-call form (the loss up to the order its terms
+        are added); for training steps that call `.backward()` on the returned loss itself."""
+        if label.dtype not in (torch.float32, torch.int64):
+            label = label.to(torch.float32)
+        return self.forward(inputs, _bce_label=label)
+
+    def forward(self, inputs, training=None, mask=None, _bce_label=None):
         int_features = inputs["int_features"].reshape(-1, self.num_int_fea)            # :47
         cat_features = inputs["cat_features"].reshape(-1, self.num_cat_fea)            # :48
+        if _bce_label is not None and not (self.fused and self.top_mlp.compute_dtype == torch.bfloat16):
+            return bce_clipped(self.forward(inputs), _bce_label)
         if self.fused and torch.is_grad_enabled():
             # the backward's sort of (row, position) pairs depends on the ids only: start it under the bottom MLP
             cat_features = self.embedding_layer.start_presort(cat_features)
@@ -101,6 +112,10 @@ class DLRM(nn.Module):
                 ones = width % 8 != 0          # a spare pad column exists: it carries 1.0 so that db comes with the dW GEMM
                 tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True,
                                                            out_dtype=torch.bfloat16, pad_to=8, ones_col=ones)   # :49,:51-55
+                if _bce_label is not None:
+                    if self.top_mlp.can_fuse_bce(tmlp_input):
+                        return self.top_mlp(tmlp_input, ones_col=ones, bce_label=_bce_label).reshape(())  # :56-57 + the loss
+                    return bce_clipped(self.top_mlp(tmlp_input, ones_col=ones).squeeze(1), _bce_label)
                 return self.top_mlp(tmlp_input, ones_col=ones).squeeze(1)                               # :56-57
             tmlp_input = self.embedding_layer.interact(cat_features, bmlp_output, False, True, True)   # :49,:51-55
         else:

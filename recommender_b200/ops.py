@@ -604,6 +604,32 @@ def dense_head_bwd(dout, out, activation, x, w, want_dx=True, want_dx_colsum=Fal
     return (dx, dw, db, cs) if want_dx_colsum else (dx, dw, db)
 
 
+def dense_head_bce(x, w, bias, label, want_dx=True, want_dx_colsum=False):
+    """Dense(1) + sigmoid, its clipped binary cross-entropy against `label` and the head's backward (seeded with d loss = 1) in one
+    pass over x (rb_dense_head_bce).  Returns (prob f32[rows], loss f32[1], dx bf16 | None, dW f32[in_dim], db f32[1], dx_colsum | None)."""
+    _need_cuda(x, w, bias, label)
+    _bf16m(x, "x")
+    rows, in_dim = x.shape
+    if label.dtype not in (torch.float32, torch.int64) or label.numel() != rows or not label.is_contiguous():
+        raise TypeError("label must be a contiguous float32 / int64 vector with one entry per row")
+    dev = x.device
+    prob = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dx = torch.empty(rows, in_dim, dtype=torch.bfloat16, device=dev) if want_dx else None
+    dw = torch.empty(in_dim, dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    cs = torch.empty(in_dim, dtype=torch.float32, device=dev) if want_dx_colsum else None
+    ws = _workspace(max(lib.rb_dense_head_bce_workspace_bytes(rows, in_dim), 256), dev)
+    check(lib.rb_dense_head_bce(_ptr(x), rows, in_dim, x.stride(0), _ptr(w), _ptr(bias), _ptr(label), 1 if label.dtype == torch.int64 else 0,
+                                _ptr(prob), _ptr(loss), _ptr(dx), in_dim, _ptr(dw), _ptr(db), _ptr(cs), _ptr(ws), ws.numel(), _stream()),
+          "rb_dense_head_bce")
+    return prob, loss, dx, dw, db, cs
+
+
+def dense_head_bce_ok(in_dim: int) -> bool:
+    return in_dim in (8, 16, 32, 64, 128, 256)
+
+
 def dense_act_bwd(dy, y, activation):
     """bf16(dy * activation'(y)) (rb_dense_act_bwd); dy, y f32 of the same contiguous shape."""
     _need_cuda(dy, y)

@@ -277,3 +277,57 @@ def test_deepfm_with_the_fused_deep_input_row_tracks_the_oracle(cuda_lib, golden
     ref = np.zeros_like(g["table"])
     np.add.at(ref, g["cat"].reshape(-1), rg["dE"].reshape(-1, D))
     assert np.abs(dtable - ref).max() <= tol * np.abs(ref).max() + 1e-9
+
+
+@pytest.mark.parametrize("in_dim,rows,ltype", [(256, 65536, torch.float32), (256, 1000, torch.int64), (64, 777, torch.float32), (8, 33, torch.int64)])
+def test_head_loss_and_head_backward_in_one_kernel(cuda_lib, in_dim, rows, ltype):
+    """rb_dense_head_bce against the three calls it replaces (rb_dense_head_fwd -> rb_bce_clipped -> rb_dense_head_bwd): the same
+    bits for prob, dx, dW, db and the dx column sums; the loss to the order its terms are added."""
+    from recommender_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(in_dim + rows)
+    x = (torch.randn(rows, in_dim, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(in_dim, generator=g, device="cuda") * in_dim ** -0.5).to(torch.bfloat16)
+    b = torch.randn(1, generator=g, device="cuda")
+    label = (torch.rand(rows, generator=g, device="cuda") < 0.3).to(ltype)
+    prob = ops.dense_head_fwd(x, w, b, "sigmoid")
+    loss, dprob = ops.bce_clipped(prob, label, want_grad=True)
+    dx, dw, db, cs = ops.dense_head_bwd(dprob, prob, "sigmoid", x, w, want_dx=True, want_dx_colsum=True)
+    p2, l2, dx2, dw2, db2, cs2 = ops.dense_head_bce(x, w, b, label, want_dx=True, want_dx_colsum=True)
+    if in_dim > 64:      # narrower heads: rb_dense_head_fwd adds the row's products in another order (one thread per row)
+        assert torch.equal(p2, prob)
+        assert torch.equal(dx2, dx) and torch.equal(dw2, dw) and torch.equal(db2, db) and torch.equal(cs2, cs)
+    else:
+        torch.testing.assert_close(p2, prob, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(dx2.float(), dx.float(), rtol=2e-2, atol=1e-9)
+        torch.testing.assert_close(dw2, dw, rtol=1e-4, atol=1e-8)
+        torch.testing.assert_close(db2, db, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(l2.reshape(()), loss.reshape(()), rtol=2e-6, atol=0)
+
+
+def test_dlrm_forward_bce_equals_model_then_loss(cuda_lib):
+    """DLRM.forward_bce (what GraphedTrainStep runs for bce_clipped) against bce_clipped(model(inputs), label): identical parameter
+    gradients, identical embedding gradient rows, the same loss."""
+    from recommender_b200.model import DLRM, bce_clipped
+    B, D, V = 512, 64, 3000
+
+    def run(fused):
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        model = DLRM([64, 32, D], [128, 256, 1], D, V, 26, 13, num_tables=26, device="cuda", compute_dtype=torch.bfloat16, generator=gen)
+        g2 = torch.Generator(device="cuda").manual_seed(8)
+        inputs = {"cat_features": torch.randint(0, V, (B, 26), device="cuda", generator=g2),
+                  "int_features": torch.rand(B, 13, device="cuda", generator=g2)}
+        label = (torch.rand(B, device="cuda", generator=g2) < 0.25).to(torch.int64)
+        loss = model.forward_bce(inputs, label) if fused else bce_clipped(model(inputs), label)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = [p.grad.clone() for p in model.parameters()]
+        dE = model.embedding_layer.pending[0].grad.srcs[0].clone()
+        return loss.detach().clone(), grads, dE, model
+
+    l0, g0, e0, _ = run(False)
+    l1, g1, e1, m1 = run(True)
+    torch.testing.assert_close(l1, l0, rtol=2e-6, atol=0)
+    assert torch.equal(e0, e1)
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b)
+    assert m1.top_mlp.last_prob is not None and m1.top_mlp.last_prob.shape == (B,)
