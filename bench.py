@@ -367,7 +367,38 @@ def extra_lines(args, dev, model, graphed_step, peak):
     torch.cuda.synchronize()
     valid_d = int((hi != 0).sum())
     flop = 2 * valid_d * (8 * Dd * 80 + 80 * 40 + 40) * 3      # forward + input-gradient + weight-gradient products
-    out["din_cfg4_attention"] = dict(batch=B, history=Lh, emb_dim=2 * Dd, valid_positions=valid_d, ms_per_step=ms_d,
+    # the gather kernels of the unit alone, against the HBM roofline (algorithmic bytes per valid position: DESIGN §4)
+    E_d = 2 * Dd
+    hist = ops.DinHistory(din.item_embedding.embeddings, hi, din.cat_embedding.embeddings, hc)
+    off_d = ops.din_offsets(hist)
+    tgt_d = torch.randn(B, E_d, device=dev, generator=g) * 0.05
+    w_d = torch.randn(valid_d, device=dev, generator=g)
+    drep_d = torch.randn(B, E_d, device=dev, generator=g) * 1e-3
+    dX_d = (torch.randn(valid_d, 4 * E_d, device=dev, generator=g) * 1e-3).to(torch.bfloat16)
+    din_kernels = {}
+    for name, fn, nbytes in (
+            ("build_features", lambda i: ops.din_build_features(hist, tgt_d, off_d, valid_d, 4 * E_d), valid_d * (E_d * 4 + 4 * E_d * 2) + B * Lh * 16),
+            ("pool_fwd", lambda i: ops.din_pool_fwd(hist, off_d, w_d), valid_d * (E_d * 4 + 4) + B * Lh * 16),
+            ("pool_bwd_weights", lambda i: ops.din_pool_bwd_weights(hist, off_d, drep_d, valid_d), valid_d * (E_d * 4 + 4) + B * Lh * 16),
+            ("feature_bwd", lambda i: ops.din_feature_bwd(hist, tgt_d, off_d, dX_d, w_d, drep_d), valid_d * (E_d * 4 * 2 + 4 * E_d * 2) + B * Lh * 16)):
+        ms_k = _time_loop(fn, 5, warm=2)
+        din_kernels[name] = dict(ms=ms_k, algorithmic_bytes=int(nbytes), gbs=nbytes / ms_k / 1e6, frac=nbytes / ms_k / 1e6 / peak)
+    # the reference's own arithmetic on the host cores (oracle.local_activation_unit forward + backward, numpy): a bounded sample
+    import numpy as _np
+    from oracle import ctr_oracle as _O
+    rng_c = _np.random.default_rng(4)
+    Bc = 256
+    his_c = rng_c.normal(0, 0.05, size=(Bc, Lh, E_d)).astype(_np.float32)
+    tgt_c = rng_c.normal(0, 0.05, size=(Bc, E_d)).astype(_np.float32)
+    mask_c = _np.arange(Lh)[None] < rng_c.integers(1, Lh + 1, size=(Bc, 1))
+    lay_c = [(rng_c.normal(0, 0.1, size=(a, b)).astype(_np.float32), _np.zeros(b, _np.float32)) for a, b in ((4 * E_d, 80), (80, 40), (40, 1))]
+    t_c = time.perf_counter()
+    rep_c, cache_c = _O.local_activation_unit(tgt_c, his_c, mask_c, lay_c)
+    _O.local_activation_unit_backward(cache_c, _np.ones_like(rep_c))
+    cpu_s = time.perf_counter() - t_c
+    out["din_cfg4_attention"] = dict(batch=B, history=Lh, emb_dim=2 * Dd, valid_positions=valid_d, ms_per_step=ms_d, kernels=din_kernels,
+                                     cpu_baseline=dict(value=int(mask_c.sum()) / cpu_s, unit="valid positions/s", cores=os.cpu_count(), kind="port",
+                                                       sample=f"oracle.local_activation_unit forward + backward (numpy, fp32) on {Bc} samples x {Lh} positions"),
                                      fwd_ms=t_fwd[0][0].elapsed_time(t_fwd[0][1]), samples_per_s=B / ms_d * 1e3,
                                      positions_per_s=valid_d / ms_d * 1e3, attention_mlp_tflops=flop / ms_d / 1e9,
                                      note="eager (one host read-back of the valid-position count per step sizes the GEMMs)")
