@@ -49,7 +49,7 @@ template <int VEC, int COLS>
 struct HRow {
   float v[COLS][VEC];
 };
-constexpr int kUnroll = 4;      // history rows in flight per warp: these kernels wait on HBM latency, not on bandwidth
+constexpr int kUnroll = 4;      // history rows per batch and warp, two batches in flight (8 per batch: fewer resident warps, slower — r2_51)
 
 template <int VEC>
 __device__ __forceinline__ void hist_cols(const Tables& t, int64_t i0, int64_t i1, int c, float (&out)[VEC]) {
@@ -111,23 +111,33 @@ __device__ __forceinline__ void for_valid_positions(const Tables& t, int64_t b, 
     const int64_t my0 = in ? load_raw_index(t.idx[0], t.is64, q) : 0;
     const int64_t my1 = (in && t.idx[1] != nullptr) ? load_raw_index(t.idx[1], t.is64, q) : 0;
     unsigned m = __ballot_sync(0xffffffffu, v);
-    while (m != 0) {
-      int ks[kUnroll];
-      HRow<VEC, COLS> rows[kUnroll];
+    // batches of kUnroll positions, double-buffered: the rows of the NEXT batch are requested before this batch is used
+    int ks[kUnroll], kn[kUnroll];
+    HRow<VEC, COLS> rows[kUnroll], rows_n[kUnroll];
+    auto fetch = [&](int (&kk)[kUnroll], HRow<VEC, COLS> (&rr)[kUnroll]) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        ks[u] = m != 0 ? __ffs(m) - 1 : -1;
-        if (ks[u] >= 0) {
+        kk[u] = m != 0 ? __ffs(m) - 1 : -1;
+        if (kk[u] >= 0) {
           m &= m - 1;
-          rows[u] = load_hist<VEC, COLS>(t, __shfl_sync(0xffffffffu, my0, ks[u]), __shfl_sync(0xffffffffu, my1, ks[u]), lane);
+          rr[u] = load_hist<VEC, COLS>(t, __shfl_sync(0xffffffffu, my0, kk[u]), __shfl_sync(0xffffffffu, my1, kk[u]), lane);
         }
       }
+    };
+    fetch(ks, rows);
+    while (ks[0] >= 0) {
+      fetch(kn, rows_n);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         if (ks[u] >= 0) {
           f(l0 + ks[u], p, rows[u]);
           ++p;
         }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        ks[u] = kn[u];
+        rows[u] = rows_n[u];
       }
     }
   }
