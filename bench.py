@@ -206,9 +206,15 @@ def run_reference(args):
     if rank != 0:
         return
     base, ms, done = time_cpu_reference(args, max(1, args.steps), max(0, args.warmup), budget_s=240)
+    cfg = workload_config(args, args.gpus)
+    if args.gpus > 1:
+        cfg["note"] = ("one replica's step on this host's cores, BASELINE config 2 tables: the b200 arm at N > 1 runs config 3, whose 187.8 M rows "
+                       "(48 GB of fp32 table + 96 GB of Keras Adam state, every row moved every step) do not fit a bounded CPU sample; same model, "
+                       "same batch per replica")
+        cfg["parallelism"] = "one replica on the host CPU"
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=done, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=workload_config(args, args.gpus), cpu_baseline=base,
+                config=cfg, cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
