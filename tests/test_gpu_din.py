@@ -205,3 +205,49 @@ def test_three_uses_of_the_tables_in_one_step_with_the_negative_history(cuda_lib
         exact = np.zeros_like(got)
         np.add.at(exact, n_idx.reshape(-1), d_neg[:, :, c0:c0 + D].reshape(-1, D))
         np.testing.assert_allclose(got[only_neg], exact[only_neg], rtol=2e-6, atol=8e-9)     # fp32 rows, same summation order; W0 - W rounds at 2^-24 |W|
+
+
+@pytest.mark.parametrize("D0,D1", [(17, 16), (64, 64), (20, 0), (4, 4)])
+def test_attention_pooling_other_row_widths(cuda_lib, D0, D1):
+    """Row widths that take the other kernel instantiations (odd widths: one column per lane; E = 128: two column groups per lane;
+    a single table) against the oracle's bf16-operand mode — forward, d_target and the history gradient rows."""
+    from recommender_b200.din import LocalActivationUnit
+    from recommender_b200.layers import Embedding
+    rng = np.random.default_rng(D0 * 100 + D1)
+    B, L, Vi, Vc = 37, 45, 200, 30
+    E = D0 + D1
+    Wi = O.init_table(rng, Vi, D0)
+    Wc = O.init_table(rng, Vc, D1) if D1 else None
+    lens = rng.integers(0, L + 1, size=B)
+    item = np.zeros((B, L), dtype=np.int64)
+    cat = np.zeros((B, L), dtype=np.int64)
+    for b, n in enumerate(lens):
+        item[b, :n] = rng.integers(1, Vi, size=n)
+        cat[b, :n] = rng.integers(1, Vc, size=n)
+    tgt = rng.normal(0, 0.05, size=(B, E)).astype(np.float32)
+    layers = O.init_mlp(rng, 4 * E, [80, 40, 1])
+    layers = [(W, rng.normal(0, 0.05, size=b.shape).astype(np.float32)) for W, b in layers]
+    his = O.embedding_lookup(Wi, item) if not D1 else O.compute_flat_embedding(Wi, Wc, item, cat)
+    mask = item != 0
+    rep16, cache = O.local_activation_unit(tgt, his, mask, layers, operand_dtype="bf16")
+    d_rep = rng.normal(0, 0.1, size=(B, E)).astype(np.float32)
+    dt16, dh16, _ = O.local_activation_unit_backward(cache, d_rep)
+    ei = Embedding(Vi, D0, mask_zero=True, device="cuda")
+    ei.embeddings.copy_(cu(Wi))
+    ei.presort = False
+    ec = None
+    if D1:
+        ec = Embedding(Vc, D1, mask_zero=True, device="cuda")
+        ec.embeddings.copy_(cu(Wc))
+        ec.presort = False
+    unit = LocalActivationUnit()
+    unit.load_arrays(layers, "cuda")
+    t = cu(tgt).requires_grad_()
+    rep = unit.attend(t, ei, cu(item), ec, cu(cat) if D1 else None)
+    rep.backward(cu(d_rep))
+    assert _rel(rep.detach().cpu().numpy(), rep16) <= 3e-3
+    assert _rel(t.grad.cpu().numpy(), dt16) <= 2e-2
+    src = ei.pending[0].grad.srcs[0]                       # dh[B, L, E]: rows of the valid positions
+    got = src.reshape(B, L, E).cpu().numpy()
+    assert _rel(got[mask], dh16[mask]) <= 2e-2
+    assert ei.pending[0].grad.scale == "masked" and (ec is None or len(ec.pending) == 1)
