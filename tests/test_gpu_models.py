@@ -277,6 +277,42 @@ def test_fused_row_update_inside_the_backward_equals_the_two_phase_step(cuda_lib
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
 
 
+def test_graphs_bound_to_input_buffers_equal_the_copying_step(cuda_lib, golden):
+    """GraphedTrainStep.bind_inputs: one captured graph per registered batch, replayed on that batch in place.  Same tables, same MLP
+    weights, same losses as the single graph that copies every batch into its static inputs — and an unregistered batch still
+    takes the copying path."""
+    from recommender_b200.graph import GraphedTrainStep
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden("dlrm_uniform")
+    cat, dense_x, label = cu(g["cat"]), cu(g["dense"]), cu(g["label"])
+    b0 = (cat, dense_x, label)
+    b1 = (cat.flip(0).contiguous(), dense_x.flip(0).contiguous(), label.flip(0).contiguous())
+    b2 = (cat.roll(3, 0).contiguous(), dense_x.roll(3, 0).contiguous(), label.roll(3, 0).contiguous())
+    order = [b1, b0, b1, b2, b0, b1]
+
+    def run(bind):
+        torch.manual_seed(0)
+        model = _build_dlrm(g, compute_dtype=torch.bfloat16)
+        opt = Adam()
+        gs = GraphedTrainStep(model, opt, bce_clipped, b0, warmup=1)
+        if bind:
+            gs.bind_inputs([b0, b1])
+            assert len(gs._bound) == 2
+        it0 = opt.iterations
+        losses = [float(gs.step(b).item()) for b in order]
+        torch.cuda.synchronize()
+        assert opt.iterations == it0 + len(order)
+        return losses, model.embedding_layer.embeddings.clone(), [p.detach().clone() for p in model.parameters()]
+
+    l_c, t_c, p_c = run(False)
+    l_b, t_b, p_b = run(True)
+    assert l_b == l_c
+    assert torch.equal(t_b, t_c)
+    for a, b in zip(p_b, p_c):
+        assert torch.equal(a, b)
+
+
 @pytest.fixture(scope="module")
 def full(cuda_lib):
     torch.manual_seed(4)
