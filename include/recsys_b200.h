@@ -163,6 +163,15 @@ int rb_gather_fwd(const float* table, int64_t rows, int32_t D,
                   float* out, int64_t out_stride, int32_t* oob_flag, void* stream);
 
 /*
+ * Per-table id validation for T tables stored back to back: raises *oob_flag when an id (after hash_mod) of field f = p % L lies
+ * outside [0, field_rows[f]).  The lookups themselves range-check the FINAL row against the total row count only, so such an
+ * id would read and update the next table; keras.layers.Embedding rejects it per table on CPU (InvalidArgument,
+ * ctr/model.py:19, :49).  One pass over the ids; n % L == 0; field_rows is a device array of L row counts.
+ */
+int rb_check_indices(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_rows,
+                     int64_t hash_mod, int32_t* oob_flag, void* stream);
+
+/*
  * Pooled lookup: out[b, :D] = pool_l table[row(b,l),:]   (written at out + b*out_stride).
  * Replaces tf.reduce_sum(E,axis=1) (ctr/model.py:21) and compute_flat_embedding +
  * compute_his_average (dien/model.py:14-19,25-31; dien/layers.py:5-17).

@@ -320,6 +320,21 @@ static int check_table(const float* table, int64_t rows, int D, RowGeom* g) {
 
 using namespace rb;
 
+// Per-table id validation (TF's CPU Gather rejects an id outside [0, input_dim) of ITS table; the lookups above range-check
+// the final row against the total row count only, so with T tables stored back to back an id >= rows(f) would land in
+// table f+1).  One coalesced pass over the ids; any violation raises the flag.
+__global__ void check_ids_kernel(const void* __restrict__ idx, int is64, int64_t n, int L, const int64_t* __restrict__ field_rows,
+                                 int64_t hash_mod, int32_t* __restrict__ oob_flag) {
+  bool bad = false;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t id = load_raw_index(idx, is64, p);
+    if (hash_mod > 0) id = static_cast<int64_t>(static_cast<uint64_t>(id) % static_cast<uint64_t>(hash_mod));
+    bad |= id < 0 || id >= __ldg(field_rows + (p % L));
+  }
+  if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) *oob_flag = 1;
+}
+
 extern "C" int rb_gather_fwd(const float* table, int64_t rows, int32_t D, const void* idx, int32_t idx_type,
                              int64_t n, int32_t L, const int64_t* field_row_offset, int64_t hash_mod, float* out,
                              int64_t out_stride, int32_t* oob_flag, void* stream) {
@@ -421,5 +436,17 @@ extern "C" int rb_hash_ids(const void* ids, int32_t idx_type, int64_t n, int64_t
   hash_ids_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, idx_type == RB_I64, n, vocab,
                                                                                   world, rows_out, owner_out, local_out);
   RB_LAUNCH_CHECK("hash_ids_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_check_indices(const void* idx, int32_t idx_type, int64_t n, int32_t L, const int64_t* field_rows,
+                                int64_t hash_mod, int32_t* oob_flag, void* stream) {
+  RB_CHECK_ARG(n >= 0 && L > 0 && (idx_type == RB_I32 || idx_type == RB_I64), RB_ERR_ARG, "bad n / L or index type");
+  if (n == 0) return RB_OK;
+  RB_CHECK_ARG(idx != nullptr && field_rows != nullptr && oob_flag != nullptr, RB_ERR_ARG, "idx / field_rows / oob_flag is null");
+  RB_CHECK_ARG(n % L == 0, RB_ERR_SHAPE, "n is not a multiple of L");
+  const unsigned int grid = static_cast<unsigned int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  check_ids_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, idx_type == RB_I64, n, L, field_rows, hash_mod, oob_flag);
+  RB_LAUNCH_CHECK("check_ids_kernel");
   return RB_OK;
 }

@@ -237,6 +237,7 @@ class Embedding(nn.Module):
         # when the lookup runs and overlaps the forward / MLPs (rb_sparse_bwd_prepare / _apply).
         self.presort = True
         import os
+        self.validate_ids = os.environ.get("RB_VALIDATE_IDS", "0") == "1"     # per-table id check before every lookup (check_ids)
         self.presort_at = os.environ.get("RB_PRESORT_AT", "start")      # "start": DLRM starts the sort before its bottom MLP
         # How the fused lookups copy table rows (rb_row_cache): "auto" lets the device decide per step from the hot-row census
         # the pre-sort takes of the ids (rows with >= 64 lookups holding more than a quarter of them: through L1)
@@ -272,6 +273,17 @@ class Embedding(nn.Module):
         if L != self.num_tables:
             raise ValueError(f"a {self.num_tables}-table embedding takes [B, {self.num_tables}] indices, got last dim {L}")
         return self._row_offset
+
+    def check_ids(self, idx: torch.Tensor) -> None:
+        """Per-table range check of raw ids [..., num_tables] (rb_check_indices): raises the device's out-of-range flag, which
+        ops.check_oob turns into the IndexError keras.layers.Embedding gives on CPU.  The lookups check the final row against
+        the total row count only — with several tables in one tensor an id >= rows(f) would otherwise read table f + 1.
+        Called by every lookup when `validate_ids` is set (RB_VALIDATE_IDS=1); one extra pass over the ids."""
+        if self.num_tables == 1 and self.table_rows is None:
+            return                                   # one table: the kernels' own check is the per-table check
+        if getattr(self, "_table_rows_dev", None) is None:
+            self._table_rows_dev = torch.full((self.num_tables,), self.input_dim, dtype=torch.int64, device=self.embeddings.device)
+        ops.check_indices(idx, self._table_rows_dev, hash_mod=self.hash_mod)
 
     def _record(self, group: LookupGroup) -> None:
         self.pending.append(group)
@@ -319,6 +331,8 @@ class Embedding(nn.Module):
         does not depend on the ids (DLRM's bottom MLP) so that the sort runs under it instead of beside the lookup.  Returns
         the (contiguous) index tensor the later lookup must be given."""
         idx = idx.contiguous()
+        if self.validate_ids:
+            self.check_ids(idx)
         L = idx.shape[-1] if idx.dim() >= 1 else 1
         self._presort(idx, L, self.row_offset_for(L))
         return idx
@@ -327,6 +341,8 @@ class Embedding(nn.Module):
     def forward(self, idx: torch.Tensor) -> torch.Tensor:
         """E[..., :] = embeddings[idx[...], :]   (ctr/model.py:19, :49)."""
         idx = idx.contiguous()
+        if self.validate_ids:
+            self.check_ids(idx)
         L = idx.shape[-1] if idx.dim() >= 1 else 1
         self._presort(idx, L, self.row_offset_for(L) if self.num_tables > 1 else None)
         return _GatherFn.apply(self._anchor, self, idx)
@@ -343,6 +359,8 @@ class Embedding(nn.Module):
     def lookup_fm(self, idx: torch.Tensor):
         """(E[B,F,D], fm[B]) of ctr/model.py:19-23 in one pass over the rows."""
         idx = idx.contiguous()
+        if self.validate_ids:
+            self.check_ids(idx)
         self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return _GatherFMFn.apply(self._anchor, self, idx)
 
@@ -350,6 +368,8 @@ class Embedding(nn.Module):
         """(deep bf16 [B, ld], fm [B]) of ctr/model.py:19-26: the lookup, the FM second order and the MLP's padded input row
         [flatten(E) | dense | 1 | 0...] in one pass over the rows (rb_gather_fm_deep_fwd)."""
         idx = idx.contiguous()
+        if self.validate_ids:
+            self.check_ids(idx)
         self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))
         return _GatherFMDeepFn.apply(self._anchor, self, idx, dense.float().contiguous(), int(ld))
 
@@ -360,6 +380,8 @@ class Embedding(nn.Module):
         emits the row in bf16, zero-padded to a multiple of `pad_to` columns (the K operand of a
         bf16 top MLP); its gradient then comes back in the same padded bf16 form."""
         idx = idx.contiguous()
+        if self.validate_ids:
+            self.check_ids(idx)
         late = self.presort_at == "after_lookup"
         if not late:
             self._presort(idx, idx.shape[1], self.row_offset_for(idx.shape[1]))

@@ -80,6 +80,18 @@ def check_oob(device) -> None:
 # --------------------------------------------------------------------------------------------
 # K1: lookups
 # --------------------------------------------------------------------------------------------
+def check_indices(idx, field_rows, *, hash_mod=0) -> None:
+    """Raise the device's out-of-range flag (read by check_oob) when an id of column f lies outside [0, field_rows[f]): the
+    per-table check keras.layers.Embedding makes on CPU, for T tables stored back to back (idx [..., T], field_rows int64[T])."""
+    _need_cuda(idx, field_rows)
+    idx = idx.contiguous()
+    L = int(field_rows.numel())
+    if idx.numel() % L != 0 or field_rows.dtype != torch.int64:
+        raise ValueError("check_indices takes ids with T columns and int64 row counts [T]")
+    check(lib.rb_check_indices(_ptr(idx), _idx(idx), idx.numel(), L, _ptr(field_rows), int(hash_mod), _ptr(oob_flag(idx.device)),
+                               _stream()), "rb_check_indices")
+
+
 
 def gather_fwd(table, idx, *, L=1, field_row_offset=None, hash_mod=0, out=None, out_stride=None):
     """out[p,:] = table[row(idx[p]),:]   (rb_gather_fwd).  idx any shape; returns [*idx.shape, D]."""

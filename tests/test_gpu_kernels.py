@@ -69,6 +69,42 @@ def test_gather_multi_table_offsets_and_hash(ops):
     np.testing.assert_array_equal(out, W[rows])
 
 
+@pytest.mark.parametrize("itype", [np.int64, np.int32])
+def test_per_table_id_check_flags_an_id_that_would_land_in_the_next_table(ops, itype):
+    """the lookups range-check the final row against the total row count only; rb_check_indices is the per-table
+    check keras.layers.Embedding makes on CPU (an id >= rows(f) is an InvalidArgument there, not a row of table f + 1)."""
+    rng = np.random.default_rng(3)
+    table_rows = np.array([7, 100, 3, 50], dtype=np.int64)
+    B = 1031                                                            # not a multiple of the block
+    ids = np.stack([rng.integers(0, r, size=B) for r in table_rows], axis=1).astype(itype)
+    ops.check_oob("cuda")
+    ops.check_indices(cu(ids), cu(table_rows))
+    ops.check_oob("cuda")                                               # every id inside its own table: nothing raised
+    for bad_col, bad_val in ((0, 7), (2, 3), (3, -1), (1, 100)):        # inside the 160-row tensor, outside its own table
+        bad = ids.copy()
+        bad[B - 1, bad_col] = bad_val
+        ops.check_indices(cu(bad), cu(table_rows))
+        with pytest.raises(IndexError):
+            ops.check_oob("cuda")
+    big = rng.integers(0, 2 ** 31 - 1, size=(B, 4)).astype(itype)        # folded first, like the lookups: id mod 3 fits every table
+    ops.check_indices(cu(big), cu(table_rows), hash_mod=3)
+    ops.check_oob("cuda")
+    ops.check_indices(torch.zeros(0, 4, dtype=torch.int64, device="cuda"), cu(table_rows))      # empty batch
+    ops.check_oob("cuda")
+
+
+def test_embedding_validate_ids_raises_like_the_cpu_lookup(ops):
+    from recommender_b200.layers import Embedding
+    emb = Embedding(10, 16, num_tables=3, device="cuda")
+    emb.validate_ids = True
+    good = torch.tensor([[0, 9, 5], [3, 3, 3]], device="cuda")
+    emb(good)
+    ops.check_oob("cuda")
+    emb(torch.tensor([[0, 10, 5]], device="cuda"))                      # row 20 of the 30-row tensor: table 2's row 0
+    with pytest.raises(IndexError):
+        ops.check_oob("cuda")
+
+
 def test_hash_ids_bit_exact(ops):
     rng = np.random.default_rng(2)
     ids = rng.integers(-2 ** 63, 2 ** 63 - 1, size=4097, dtype=np.int64)
