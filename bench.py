@@ -707,19 +707,26 @@ def run_b200(args):
 
         host_loop_ms = [0.0]
 
-        def e2e_loop(n, base):
+        def e2e_loop(n, base, h2d=True, d2h=True):
             for ev in free:
                 ev.record(main)
             prefetch(0)
             t_host = time.perf_counter()
             for i in range(n):
                 buf = i % 2
-                if i + 1 < n:
+                if i + 1 < n and (h2d or i == 0):
                     prefetch(i + 1)
-                main.wait_event(h2d_done[buf])
-                loss = train_step(stage[buf])
+                if h2d or i < 2:
+                    main.wait_event(h2d_done[buf])
+                # the step's result, read every step: GraphedTrainStep.step(loss_out=) copies it to the host on its own stream (on the
+                # main stream the 4-byte copy sits between two graph launches: ~40 us per step, r2_60 -> r2_62)
+                if use_graph and d2h:
+                    loss = train_step(stage[buf], loss_out=loss_host[base + i])
+                else:
+                    loss = train_step(stage[buf])
+                    if d2h:
+                        loss_host[base + i].copy_(loss.detach(), non_blocking=True)
                 free[buf].record(main)
-                loss_host[base + i].copy_(loss.detach(), non_blocking=True)      # the step's result, read every step
             host_loop_ms[0] = (time.perf_counter() - t_host) * 1e3 / max(n, 1)   # host time to ENQUEUE one step (before the sync)
             torch.cuda.synchronize()
 
@@ -733,8 +740,20 @@ def run_b200(args):
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), 0.0)) / args.steps
+        probe = None
+        if os.environ.get("RB_E2E_PROBE", "0") == "1":       # diagnostic: where the distance to `value` comes from (untimed extras)
+            probe = {}
+            for tag, kw in (("full", {}), ("no_d2h", dict(d2h=False)), ("no_h2d", dict(h2d=False)), ("neither", dict(h2d=False, d2h=False))):
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                p0.record()
+                e2e_loop(args.steps, 3, **kw)
+                p1.record()
+                torch.cuda.synchronize()
+                probe[tag] = p0.elapsed_time(p1) / args.steps
         e2e = dict(value=B * world / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                    ms_per_step=e2e_ms, wall_ms_per_step=wall_ms / args.steps, host_enqueue_ms_per_step=host_loop_ms[0],
+                   **({"probe_ms_per_step": probe} if probe else {}),
                    api=("GraphedTrainStep.step (one CUDA graph: DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients)"
                         if use_graph else "DLRM.__call__ + bce_clipped + backward + Adam.apply_gradients")
                        + " on batches staged from pinned host memory")

@@ -313,6 +313,35 @@ def test_graphs_bound_to_input_buffers_equal_the_copying_step(cuda_lib, golden):
         assert torch.equal(a, b)
 
 
+def test_losses_read_on_the_side_stream_are_the_steps_losses(cuda_lib, golden):
+    """GraphedTrainStep.step(loss_out=pinned slot): the loss of EVERY step reaches the host without a synchronisation in the loop,
+    for bound graphs (each owns its loss tensor) and for the copying graph (one loss tensor rewritten every step)."""
+    from recommender_b200.graph import GraphedTrainStep
+    from recommender_b200.model import bce_clipped
+    from recommender_b200.optimizers import Adam
+    g = golden("dlrm_uniform")
+    cat, dense_x, label = cu(g["cat"]), cu(g["dense"]), cu(g["label"])
+    b0 = (cat, dense_x, label)
+    b1 = (cat.flip(0).contiguous(), dense_x.flip(0).contiguous(), label.flip(0).contiguous())
+    b2 = (cat.roll(3, 0).contiguous(), dense_x.roll(3, 0).contiguous(), label.roll(3, 0).contiguous())
+    order = [b1, b0, b1, b2, b2, b0, b1, b0, b0, b2] * 3
+
+    def run(async_read):
+        torch.manual_seed(0)
+        model = _build_dlrm(g, compute_dtype=torch.bfloat16)
+        gs = GraphedTrainStep(model, Adam(), bce_clipped, b0, warmup=1)
+        gs.bind_inputs([b0, b1])
+        host = torch.full((len(order),), float("nan")).pin_memory()
+        if async_read:
+            for i, b in enumerate(order):
+                gs.step(b, loss_out=host[i])
+            torch.cuda.synchronize()
+            return host.tolist()
+        return [float(gs.step(b).item()) for b in order]
+
+    assert run(True) == run(False)
+
+
 @pytest.fixture(scope="module")
 def full(cuda_lib):
     torch.manual_seed(4)
