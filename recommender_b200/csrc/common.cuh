@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/recsys_b200.h"
 
@@ -263,6 +264,41 @@ inline IndexMap make_index_map(const void* idx, int idx_type, const int64_t* off
 
 // keys / positions input buffers inside a sparse-backward workspace (sparse_update.cu), filled by p2p.cu
 int sparse_ws_key_buffers(int64_t n, int D, int64_t rows, void* ws, uint32_t** keys, uint32_t** vals);
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// A kernel launched with the attribute below may be placed on the SMs while the kernel before it in the stream still drains;
+// it orders itself behind that kernel's completion (and memory flush) with griddep_wait(), which EVERY kernel launched this way
+// executes before it touches global memory, so that a chain of such kernels stays transitively ordered.  Without the
+// attribute (or when the preceding stream operation is not a kernel) the wait returns at once.  Works inside stream capture
+// (a programmatic edge of the graph).  RB_PDL=0 turns the attribute off everywhere.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RB_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned int grid, unsigned int block, size_t smem, cudaStream_t st,
+                                    bool programmatic, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (programmatic && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 inline unsigned int grid_for(int64_t work_items, int items_per_block) {
   int64_t b = (work_items + items_per_block - 1) / items_per_block;

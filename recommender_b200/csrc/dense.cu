@@ -28,6 +28,7 @@ constexpr int kDenseThreads = 256;
 // Keras `_resource_apply_dense` formulas, every op explicitly rounded so
 // the result matches the numpy oracle bit for bit.
 __global__ void __launch_bounds__(kDenseThreads) dense_opt_kernel(const __grid_constant__ DenseSlots s) {
+  griddep_wait();
   int t = 0;
   while (t + 1 < s.num && static_cast<int>(blockIdx.x) >= s.chunk_start[t + 1]) ++t;
   const int64_t base = static_cast<int64_t>(blockIdx.x - s.chunk_start[t]) * kDenseChunk;
@@ -86,6 +87,7 @@ __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(kColThreads)
 colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int cols, int64_t row_stride, float* __restrict__ partial) {
+  griddep_wait();
   __shared__ float s_red[kColThreads * 8];
   const int vcols = cols / 8;                      // vector columns
   const int row_lanes = kColThreads / vcols;       // rows handled in parallel (vcols <= 256)
@@ -131,6 +133,7 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int cols, int64_t r
 constexpr int kFinalWarps = 32;
 __global__ void __launch_bounds__(kFinalWarps * 32) colsum_final_kernel(const float* __restrict__ partial, int nparts, int cols,
                                                                          float* __restrict__ out) {
+  griddep_wait();
   __shared__ float s_w[kFinalWarps][32];
   const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + lane;
@@ -165,6 +168,7 @@ constexpr int kBceThreads = 256;
 __global__ void __launch_bounds__(kBceThreads)
 bce_partial_kernel(const float* __restrict__ prob, const void* __restrict__ label, int label_is_i64, int64_t n, float inv_n,
                    float* __restrict__ dprob, float* __restrict__ partial) {
+  griddep_wait();
   __shared__ float s_red[kBceThreads / 32];
   const float eps = 1e-7f;
   float acc = 0.f;
@@ -191,6 +195,7 @@ bce_partial_kernel(const float* __restrict__ prob, const void* __restrict__ labe
 }
 
 __global__ void bce_final_kernel(const float* __restrict__ partial, int nparts, float inv_n, float* __restrict__ loss) {
+  griddep_wait();
   float t = 0.f;
   for (int i = 0; i < nparts; ++i) t += partial[i];
   loss[0] = t * inv_n;
@@ -250,7 +255,7 @@ extern "C" int rb_dense_opt_step(const rb_dense_slot* slots, int32_t num, const 
   }
   for (int t = num; t <= RB_MAX_DENSE_TENSORS; ++t) s.chunk_start[t] = chunks;
   if (chunks == 0) return RB_OK;
-  dense_opt_kernel<<<chunks, kDenseThreads, 0, static_cast<cudaStream_t>(stream)>>>(s);
+  RB_CUDA(launch_dependent(dense_opt_kernel, chunks, kDenseThreads, 0, static_cast<cudaStream_t>(stream), true, s));
   RB_LAUNCH_CHECK("dense_opt_kernel");
   return RB_OK;
 }
@@ -279,11 +284,11 @@ extern "C" int rb_colsum(const void* x, int32_t dtype, int64_t rows, int32_t col
   const int parts = colsum_parts(rows);
   float* partial = static_cast<float*>(ws);
   if (dtype == RB_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<parts, kColThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, row_stride, partial);
+    RB_CUDA(launch_dependent(colsum_partial_kernel<__nv_bfloat16>, parts, kColThreads, 0, st, true, static_cast<const __nv_bfloat16*>(x), rows, cols, row_stride, partial));
   else
-    colsum_partial_kernel<float><<<parts, kColThreads, 0, st>>>(static_cast<const float*>(x), rows, cols, row_stride, partial);
+    RB_CUDA(launch_dependent(colsum_partial_kernel<float>, parts, kColThreads, 0, st, true, static_cast<const float*>(x), rows, cols, row_stride, partial));
   RB_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<(cols + 31) / 32, kFinalWarps * 32, 0, st>>>(partial, parts, cols, out);
+  RB_CUDA(launch_dependent(colsum_final_kernel, (cols + 31) / 32, kFinalWarps * 32, 0, st, true, partial, parts, cols, out));
   RB_LAUNCH_CHECK("colsum_final_kernel");
   return RB_OK;
 }
@@ -299,9 +304,9 @@ extern "C" int rb_bce_clipped(const float* prob, const void* label, int32_t labe
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int parts = bce_parts(n);
   const float inv_n = 1.0f / static_cast<float>(n);
-  bce_partial_kernel<<<parts, kBceThreads, 0, st>>>(prob, label, label_type, n, inv_n, dprob_out, static_cast<float*>(ws));
+  RB_CUDA(launch_dependent(bce_partial_kernel, parts, kBceThreads, 0, st, true, prob, label, label_type, n, inv_n, dprob_out, static_cast<float*>(ws)));
   RB_LAUNCH_CHECK("bce_partial_kernel");
-  bce_final_kernel<<<1, 1, 0, st>>>(static_cast<const float*>(ws), parts, inv_n, loss_out);
+  RB_CUDA(launch_dependent(bce_final_kernel, 1, 1, 0, st, true, static_cast<const float*>(ws), parts, inv_n, loss_out));
   RB_LAUNCH_CHECK("bce_final_kernel");
   return RB_OK;
 }

@@ -250,6 +250,7 @@ __device__ __forceinline__ void load_row_async(const T* __restrict__ grow, T* gs
 template <int D, typename OUT, bool SHARDED>
 __global__ void __launch_bounds__(IxWarps<D>::value * 32, 1)
 dot_interaction_fwd_kernel(IxArgs a, OUT* __restrict__ out, int64_t out_stride, int write_width, int os_bytes) {
+  griddep_wait();      // launched programmatically behind the kernel before it (common.cuh)
   constexpr int STRIDE = D + RB_IX_FWD_PAD;  // floats; (D+8) % 32 == 8 -> conflict-free 64-bit fragment loads
   constexpr int kXsFloats = 32 * STRIDE;
   const int kIxWarps = blockDim.x / 32;
@@ -573,6 +574,7 @@ template <int D, typename DOUT, bool SELF, int SRC, bool UPD = false>
 __global__ void __launch_bounds__(UPD ? kIxUpdWarps * 32 : IxWarps<D>::value * 32, 1)
 dot_interaction_bwd_kernel(IxArgs a, const DOUT* __restrict__ dOut, int64_t dout_stride, float* __restrict__ dE,
                            float* __restrict__ d_dense, int copy_width, int gs_bytes, IxUpdate u = IxUpdate{}) {
+  griddep_wait();      // launched programmatically behind the kernel before it (common.cuh)
   static_assert(!UPD || SRC == 0, "the fused row update reads fp32 rows of the local table");
   constexpr int STRIDE = D + 4;  // floats; 2*(D+4) % 32 == 8 -> conflict-free 32-bit B-fragment loads
   constexpr int MS = D + 8;      // floats per staged m / v row: conflict-free 64-bit accesses of the epilogue
@@ -947,8 +949,8 @@ static int launch_fwd(const IxArgs& a, int D, OUT* out, int64_t out_stride, int 
     } else {                                                                                                            \
       rc = set_smem(dot_interaction_fwd_kernel<DD, OUT, false>, smem);                                                  \
       if (rc != RB_OK) return rc;                                                                                       \
-      dot_interaction_fwd_kernel<DD, OUT, false><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, out, out_stride, write_width, \
-                                                                                                  os_bytes);            \
+      RB_CUDA(launch_dependent(dot_interaction_fwd_kernel<DD, OUT, false>, persistent_grid(a.B, W), W * 32, smem, st, true, a, out, \
+                               out_stride, write_width, os_bytes));                                                     \
     }                                                                                                                   \
   }
   if (D == 16) LAUNCH(16) else if (D == 32) LAUNCH(32) else if (D == 64) LAUNCH(64) else LAUNCH(128)
@@ -994,9 +996,8 @@ static int launch_fwd16(const IxArgs& a, int D, const __nv_bfloat16* const* shad
   {                                                                                                                     \
     rc = set_smem(dot_interaction_bwd_kernel<DD, DOUT, SELFV, SRCV>, smem);                                             \
     if (rc != RB_OK) return rc;                                                                                         \
-    dot_interaction_bwd_kernel<DD, DOUT, SELFV, SRCV><<<persistent_grid(a.B, W), W * 32, smem, st>>>(a, dOut, dout_stride, dE, \
-                                                                                                       d_dense, copy_width,  \
-                                                                                                       gs_bytes);       \
+    RB_CUDA(launch_dependent(dot_interaction_bwd_kernel<DD, DOUT, SELFV, SRCV>, persistent_grid(a.B, W), W * 32, smem, st, true, a, dOut, \
+                             dout_stride, dE, d_dense, copy_width, gs_bytes, IxUpdate{}));                              \
   }
 #define BWD_DISPATCH(DD, MODE)                                                                                          \
   if (a.self_interaction) {                                                                                             \

@@ -361,6 +361,9 @@ __device__ __forceinline__ void dense_gemm_body(const CUtensorMap& map_a, const 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (descriptor prefetch, barriers, tensor-memory allocation) may run while the kernel before this one in the
+  // stream drains (programmatic dependent launch, common.cuh); nothing below may
+  griddep_wait();
 
   const int total = g.m_blocks * g.n_blocks * g.splits;
 
@@ -669,6 +672,7 @@ dense_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 // dW[m, n] = sum over splits (in split order) of the fp32 partial tiles; eight loads in flight per thread
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N, float* __restrict__ out, int64_t ldo) {
+  griddep_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int nv = N / 4;
   if (i >= static_cast<int64_t>(M) * nv) return;
@@ -696,6 +700,7 @@ reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_s
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                 const float* __restrict__ bias, int act, float* __restrict__ out) {
+  griddep_wait();
   const int lane = threadIdx.x % 32;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + threadIdx.x / 32;
   if (r >= rows) return;
@@ -720,6 +725,7 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, i
 __global__ void __launch_bounds__(256)
 head_fwd_narrow_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ bias, int act, float* __restrict__ out) {
+  griddep_wait();
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (r >= rows) return;
   float acc = 0.f;
@@ -743,6 +749,7 @@ __global__ void __launch_bounds__(kHeadBwdThreads)
 head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int act, const __nv_bfloat16* __restrict__ x, int64_t rows,
                 int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t lddx,
                 float* __restrict__ partial /* [grid, 2 * in_dim + 1]: dW | db | column sums of dx */) {
+  griddep_wait();
   // thread = (row lane rl, vector column vc): vc covers 8 consecutive columns
   const int vcols = in_dim / 8;
   const int row_lanes = kHeadBwdThreads / vcols;
@@ -825,6 +832,7 @@ __global__ void __launch_bounds__(kHeadBwdThreads)
 head_bce_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                 const float* __restrict__ bias, const void* __restrict__ label, int label_is_i64, float inv_n, float* __restrict__ prob,
                 __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partial /* [grid, 2 * in_dim + 2]: dW | db | colsums | loss */) {
+  griddep_wait();
   const int vcols = in_dim / 8;
   const int row_lanes = kHeadBwdThreads / vcols;
   const int vc = threadIdx.x % vcols, rl = threadIdx.x / vcols;
@@ -944,6 +952,7 @@ head_bce_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, i
 __global__ void __launch_bounds__(256)
 head_bce_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float inv_n, float* __restrict__ dW, float* __restrict__ db,
                       float* __restrict__ dx_colsum, float* __restrict__ loss) {
+  griddep_wait();
   const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   const int pstride = 2 * in_dim + 2;
   if (c >= pstride) return;
@@ -961,6 +970,7 @@ head_bce_final_kernel(const float* __restrict__ partial, int parts, int in_dim, 
 __global__ void __launch_bounds__(256)
 head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db,
                       float* __restrict__ dx_colsum) {
+  griddep_wait();
   const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   const int pstride = 2 * in_dim + 1;
   if (c >= pstride) return;
@@ -977,6 +987,7 @@ head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, 
 // dy_pre[r, c] = bf16(dy[r, c] * act'(y[r, c])): the activation's backward in front of the last layer's GEMMs
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, int64_t n4, __nv_bfloat16* __restrict__ out) {
+  griddep_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
   const float4 d = __ldcs(reinterpret_cast<const float4*>(dy) + i);
@@ -994,6 +1005,7 @@ act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int ac
 // the same for a hidden layer whose output and incoming gradient are bf16 (dien/layers.py:37-38): 8 elements per thread
 __global__ void __launch_bounds__(256)
 act_bwd_bf16_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, int act, int64_t n8, uint4* __restrict__ out) {
+  griddep_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n8) return;
   const uint4 d = __ldcs(dy + i);
@@ -1018,6 +1030,7 @@ act_bwd_bf16_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, i
 // row in_dim of that layer's weight-gradient GEMM its bias gradient
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, __nv_bfloat16* __restrict__ out, int ld, int ones_col) {
+  griddep_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= rows * ld) return;
   const int64_t r = i / ld;
@@ -1268,7 +1281,8 @@ static int launch_gemm(const Operand& a, const Operand& b, int M, int N, int K, 
   const int workers = pl.cg == 2 ? std::min(pl.workers, max_pair_clusters()) : pl.workers;
   int grid = std::min(total, workers) * pl.cg;
   if (pl.resident) grid = std::min(workers / g.n_blocks, g.m_blocks) * g.n_blocks;      // a CTA keeps its column block
-  kernels[pl.cg - 1][c_f32 ? 1 : 0][activation]<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, g);
+  RB_CUDA(launch_dependent(kernels[pl.cg - 1][c_f32 ? 1 : 0][activation], static_cast<unsigned int>(grid), kThreads, kSmemBytes, st, true, ma, mb,
+                           mc, g));
   RB_LAUNCH_CHECK("dense_gemm_kernel");
   return RB_OK;
 }
@@ -1337,7 +1351,7 @@ extern "C" int rb_dense_bwd_weight(const void* x, int64_t rows, int32_t in_dim, 
                        &split_stride);
   if (rc != RB_OK) return rc;
   const int64_t work = static_cast<int64_t>(in_dim) * (units / 4);
-  reduce_splits_kernel<<<grid_for(work, 256), 256, 0, st>>>(static_cast<const float*>(ws), splits, split_stride, in_dim, units, dw, lddw);
+  RB_CUDA(launch_dependent(reduce_splits_kernel, grid_for(work, 256), 256, 0, st, true, static_cast<const float*>(ws), splits, split_stride, in_dim, units, dw, lddw));
   RB_LAUNCH_CHECK("reduce_splits_kernel");
   return RB_OK;
 }
@@ -1349,12 +1363,9 @@ extern "C" int rb_dense_head_fwd(const void* x, int64_t rows, int32_t in_dim, in
   RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, RB_ERR_ALIGN, "head: x / w not 16-byte aligned");
   RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
   if (in_dim <= 64)
-    head_fwd_narrow_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim,
-                                                                                             ldx, static_cast<const __nv_bfloat16*>(w), bias,
-                                                                                             activation, out);
+    RB_CUDA(launch_dependent(head_fwd_narrow_kernel, grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream), true, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w), bias, activation, out));
   else
-    head_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
-                                                                                    static_cast<const __nv_bfloat16*>(w), bias, activation, out);
+    RB_CUDA(launch_dependent(head_fwd_kernel, grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream), true, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w), bias, activation, out));
   RB_LAUNCH_CHECK("head_fwd_kernel");
   return RB_OK;
 }
@@ -1380,11 +1391,9 @@ extern "C" int rb_dense_head_bwd(const float* dout, const float* out, int32_t ac
                "workspace too small: need %zu bytes, got %zu", rb_dense_head_bwd_workspace_bytes(rows, in_dim), ws_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int parts = head_parts(rows);
-  head_bwd_kernel<<<parts, kHeadBwdThreads, 0, st>>>(dout, out, activation, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx,
-                                                     static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(dx), lddx,
-                                                     static_cast<float*>(ws));
+  RB_CUDA(launch_dependent(head_bwd_kernel, parts, kHeadBwdThreads, 0, st, true, dout, out, activation, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(dx), lddx, static_cast<float*>(ws)));
   RB_LAUNCH_CHECK("head_bwd_kernel");
-  head_bwd_final_kernel<<<(2 * in_dim + 1 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, dw, db, dx_colsum);
+  RB_CUDA(launch_dependent(head_bwd_final_kernel, (2 * in_dim + 1 + 7) / 8, 256, 0, st, true, static_cast<const float*>(ws), parts, in_dim, dw, db, dx_colsum));
   RB_LAUNCH_CHECK("head_bwd_final_kernel");
   return RB_OK;
 }
@@ -1411,11 +1420,9 @@ extern "C" int rb_dense_head_bce(const void* x, int64_t rows, int32_t in_dim, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int parts = head_parts(rows);
   const float inv_n = 1.0f / static_cast<float>(rows);
-  head_bce_kernel<<<parts, kHeadBwdThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w),
-                                                     bias, label, label_type, inv_n, prob, static_cast<__nv_bfloat16*>(dx), lddx,
-                                                     static_cast<float*>(ws));
+  RB_CUDA(launch_dependent(head_bce_kernel, parts, kHeadBwdThreads, 0, st, true, static_cast<const __nv_bfloat16*>(x), rows, in_dim, ldx, static_cast<const __nv_bfloat16*>(w), bias, label, label_type, inv_n, prob, static_cast<__nv_bfloat16*>(dx), lddx, static_cast<float*>(ws)));
   RB_LAUNCH_CHECK("head_bce_kernel");
-  head_bce_final_kernel<<<(2 * in_dim + 2 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(ws), parts, in_dim, inv_n, dw, db, dx_colsum, loss);
+  RB_CUDA(launch_dependent(head_bce_final_kernel, (2 * in_dim + 2 + 7) / 8, 256, 0, st, true, static_cast<const float*>(ws), parts, in_dim, inv_n, dw, db, dx_colsum, loss));
   RB_LAUNCH_CHECK("head_bce_final_kernel");
   return RB_OK;
 }
@@ -1426,7 +1433,7 @@ extern "C" int rb_dense_act_bwd(const float* dy, const float* y, int32_t activat
   RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
                RB_ERR_ALIGN, "act_bwd: pointers not aligned");
   RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
-  act_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, activation, n / 4, static_cast<__nv_bfloat16*>(out_bf16));
+  RB_CUDA(launch_dependent(act_bwd_kernel, grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), true, dy, y, activation, n / 4, static_cast<__nv_bfloat16*>(out_bf16)));
   RB_LAUNCH_CHECK("act_bwd_kernel");
   return RB_OK;
 }
@@ -1437,8 +1444,7 @@ extern "C" int rb_dense_act_bwd_bf16(const void* dy_bf16, const void* y_bf16, in
   RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0,
                RB_ERR_ALIGN, "act_bwd_bf16: pointers not 16-byte aligned");
   RB_CHECK_ARG(activation >= RB_ACT_NONE && activation <= RB_ACT_SIGMOID, RB_ERR_ARG, "bad activation %d", activation);
-  act_bwd_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(dy_bf16), static_cast<const uint4*>(y_bf16), activation, n / 8, static_cast<uint4*>(out_bf16));
+  RB_CUDA(launch_dependent(act_bwd_bf16_kernel, grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream), true, static_cast<const uint4*>(dy_bf16), static_cast<const uint4*>(y_bf16), activation, n / 8, static_cast<uint4*>(out_bf16)));
   RB_LAUNCH_CHECK("act_bwd_bf16_kernel");
   return RB_OK;
 }
@@ -1447,8 +1453,7 @@ extern "C" int rb_dense_pack_input(const float* x, int64_t rows, int32_t in_dim,
                                    void* stream) {
   RB_CHECK_ARG(x != nullptr && out_bf16 != nullptr, RB_ERR_ARG, "x / out is null");
   RB_CHECK_ARG(rows > 0 && in_dim > 0 && ld_out >= in_dim + (ones_col ? 1 : 0) && ldx >= in_dim, RB_ERR_SHAPE, "pack_input: bad sizes");
-  pack_input_kernel<<<grid_for(rows * ld_out, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, in_dim, ldx,
-                                                                                              static_cast<__nv_bfloat16*>(out_bf16), ld_out, ones_col);
+  RB_CUDA(launch_dependent(pack_input_kernel, grid_for(rows * ld_out, 256), 256, 0, static_cast<cudaStream_t>(stream), true, x, rows, in_dim, ldx, static_cast<__nv_bfloat16*>(out_bf16), ld_out, ones_col));
   RB_LAUNCH_CHECK("pack_input_kernel");
   return RB_OK;
 }

@@ -14,6 +14,8 @@
 //      following tiles in order and calls the sink; chains longer than kLongChain tiles (hot
 //      rows: OOV id 0, 3-row ESMM tables) are queued and reduced by a whole CTA each in
 //      seg_long_chain_kernel with a fixed split, so the result is run-to-run identical.
+//      Both are launched programmatically (griddepcontrol) while the tile kernel drains: which tiles own a crossing run is
+//      decided from the sorted keys alone, and only the owners wait for the tile kernel's partial sums (r2_65: 511 -> 507 us).
 // HBM traffic is the algorithmic minimum: each gradient row once, each touched table/state
 // row read once and written once; sort traffic is 16 B per lookup per pass.
 #include <cuda_bf16.h>
@@ -311,6 +313,13 @@ __global__ void write_num_unique_kernel(const int32_t* __restrict__ seg_incl, in
   out[0] = (n > 0) ? static_cast<int64_t>(seg_incl[n - 1]) : 0;
 }
 
+// ---- programmatic dependent launch (griddepcontrol): the border kernels of step 3 are launched while the tile kernel drains ----
+// The tile kernel releases its dependents as soon as every one of its CTAs has started; seg_chain_kernel's CTAs then take the SM
+// slots the tile kernel's last wave frees, decide from the sorted keys alone (final before the tile kernel started) whether
+// their tile owns a border-crossing run — all but a few hundred of 53 k tiles at config 2 do not, and exit — and only the owners
+// wait for the tile kernel's completion before they read its partial sums.  Thread 0 of the grid always waits, so that the
+// completion of each kernel of the chain still implies the completion of the one before it.
+
 // ---- step 2: tiles -------------------------------------------------------------------------------------
 // Every lane runs a private kRing-deep pipeline over ITS columns of the tile's entries: the gradient
 // row slice (and, for an entry that closes a run owned by this tile, the W / state row slices) are
@@ -321,7 +330,9 @@ template <int VEC, int GS, class Sink, bool SIMPLE>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
                         const __grid_constant__ GradGroupsDev gsrc, Sink sink, float* __restrict__ head_part,
-                        float* __restrict__ tail_part) {
+                        float* __restrict__ tail_part, int* __restrict__ long_count) {
+  griddep_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *long_count = 0;   // seg_chain_kernel appends to the list only after this grid is complete
   if (n_dev != nullptr) n = min(n, __ldg(n_dev));   // padded capacity (sharded path): only the first *n_dev pairs are real
   sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
@@ -490,7 +501,9 @@ template <int VEC, int GS, bool FLAT>
 __global__ void __launch_bounds__(kSegThreads)
 seg_reduce_tiles_bulk_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ n_dev,
                              const __grid_constant__ GradGroupsDev gsrc, OptSink sink, float* __restrict__ head_part,
-                             float* __restrict__ tail_part) {
+                             float* __restrict__ tail_part, int* __restrict__ long_count) {
+  griddep_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *long_count = 0;   // seg_chain_kernel appends to the list only after this grid is complete
   if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
@@ -640,16 +653,24 @@ __global__ void __launch_bounds__(kSegThreads)
 seg_chain_kernel(const uint32_t* __restrict__ keys, int n, const int* __restrict__ n_dev, int D, Sink sink,
                  const float* __restrict__ head_part, const float* __restrict__ tail_part, LongChain* __restrict__ long_list,
                  int* __restrict__ long_count, int long_cap) {
+  griddep_launch_dependents();
   if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   sink.prepare();
   const int tile_id = blockIdx.x * (kSegThreads / GS) + threadIdx.x / GS;
   const int lane = threadIdx.x % GS;
   const int gbase = tile_id * kTile;
-  if (gbase + kTile >= n) return;                       // no following tile: nothing can continue
-  const uint32_t key = keys[gbase + kTile - 1];
-  if (keys[gbase + kTile] != key) return;               // the trailing run ends here
-  const bool whole_tile = (keys[gbase] == key);
-  if (whole_tile && gbase > 0 && keys[gbase - 1] == key) return;  // interior tile of someone else's chain
+  // the sorted keys alone say whether this tile owns a run that crosses its border: decided while the tile kernel still runs
+  bool owns = gbase + kTile < n;                        // else no following tile: nothing can continue
+  uint32_t key = 0;
+  if (owns) {
+    key = keys[gbase + kTile - 1];
+    owns = keys[gbase + kTile] == key;                  // else the trailing run ends here
+    if (owns && keys[gbase] == key && gbase > 0 && keys[gbase - 1] == key) owns = false;  // interior tile of someone else's chain
+  }
+  const bool anchor = blockIdx.x == 0 && threadIdx.x == 0;   // this grid must not complete before the tile kernel has
+  if (!owns && !anchor) return;
+  griddep_wait();                                       // the tile kernel's partial sums (and its rows) are complete and visible
+  if (!owns) return;
   // this tile owns the run: find where it starts (inside the tile) and where it ends
   int start = kTile - 1;
   while (start > 0 && keys[gbase + start - 1] == key) --start;
@@ -685,6 +706,7 @@ template <int VEC, int GS, class Sink>
 __global__ void __launch_bounds__(kSegThreads)
 seg_long_chain_kernel(int D, Sink sink, const float* __restrict__ head_part, const float* __restrict__ tail_part,
                       const LongChain* __restrict__ long_list, const int* __restrict__ long_count, int long_cap) {
+  griddep_wait();                                       // the list seg_chain_kernel appended to is complete
   sink.prepare();
   constexpr int kGroups = kSegThreads / GS;
   __shared__ float s_part[kGroups * 128];  // D <= 128
@@ -859,7 +881,7 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
   float* tail = reinterpret_cast<float*>(ws + lay.tail_part);
   LongChain* ll = reinterpret_cast<LongChain*>(ws + lay.long_list);
   int* lc = reinterpret_cast<int*>(ws + lay.long_count);
-  RB_CUDA(cudaMemsetAsync(lc, 0, sizeof(int), st));
+  static const bool pdl = [] { const char* e = getenv("RB_SEG_PDL"); return e == nullptr || e[0] != '0'; }();
   const int tiles = (n + kTile - 1) / kTile;
   const int cap = long_list_cap(n);
   const GradSrcDev& g0 = gsrc.g[0];
@@ -884,12 +906,12 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
           RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        static_cast<int>(bulk_bytes)));                                                  \
           seg_reduce_tiles_bulk_kernel<V, G, true><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, \
-                                                                                                              gsrc, sink, head, tail); \
+                                                                                                              gsrc, sink, head, tail, lc); \
         } else {                                                                                                        \
           RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_bulk_kernel<V, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        static_cast<int>(bulk_bytes)));                                                  \
           seg_reduce_tiles_bulk_kernel<V, G, false><<<grid_for(tiles, kGroups), kSegThreads, bulk_bytes, st>>>(keys, vals, n, n_dev, \
-                                                                                                               gsrc, sink, head, tail); \
+                                                                                                               gsrc, sink, head, tail, lc); \
         }                                                                                                               \
       }                                                                                                                 \
     } else if (simple) {                                                                                                \
@@ -897,17 +919,17 @@ static int run_segments(const RowGeom& geo, const uint32_t* keys, const uint32_t
         RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      static_cast<int>(ring_bytes)));                                                    \
       seg_reduce_tiles_kernel<V, G, Sink, true><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, \
-                                                                                                            gsrc, sink, head, tail); \
+                                                                                                            gsrc, sink, head, tail, lc); \
     } else {                                                                                                            \
       if (ring_bytes > 40 * 1024)                                                                                       \
         RB_CUDA(cudaFuncSetAttribute(seg_reduce_tiles_kernel<V, G, Sink, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      static_cast<int>(ring_bytes)));                                                    \
       seg_reduce_tiles_kernel<V, G, Sink, false><<<grid_for(tiles, kGroups), kSegThreads, ring_bytes, st>>>(keys, vals, n, n_dev, \
-                                                                                                             gsrc, sink, head, tail); \
+                                                                                                             gsrc, sink, head, tail, lc); \
     }                                                                                                                   \
-    seg_chain_kernel<V, G, Sink><<<grid_for(tiles, kGroups), kSegThreads, 0, st>>>(keys, n, n_dev, gsrc.D, sink, head, tail, ll, lc, \
-                                                                                   cap);                                 \
-    seg_long_chain_kernel<V, G, Sink><<<2 * kNumSMs, kSegThreads, 0, st>>>(gsrc.D, sink, head, tail, ll, lc, cap);      \
+    RB_CUDA(launch_dependent(seg_chain_kernel<V, G, Sink>, grid_for(tiles, kGroups), kSegThreads, 0, st, pdl, keys, n, n_dev, gsrc.D, sink, \
+                             head, tail, ll, lc, cap));                                                                  \
+    RB_CUDA(launch_dependent(seg_long_chain_kernel<V, G, Sink>, 2 * kNumSMs, kSegThreads, 0, st, pdl, gsrc.D, sink, head, tail, ll, lc, cap)); \
   }
   if (geo.vec == 4) {
     if (geo.gs == 4) CALL(4, 4) else if (geo.gs == 8) CALL(4, 8) else if (geo.gs == 16) CALL(4, 16) else CALL(4, 32)
