@@ -142,6 +142,10 @@ int rb_version(void);
 const char* rb_last_error(void);
 /* Kernels of this library launched by this process so far (cub's sort/scan passes are not counted). */
 uint64_t rb_kernel_launches(void);
+/* Programmatic dependent launch of this library's kernels (a kernel is placed on the SMs while the one before it in the stream
+ * drains, and orders itself with griddepcontrol.wait): 1 = on, 0 = off, -1 = the RB_PDL environment variable decides (default
+ * on).  Read at every launch; a captured CUDA graph keeps what was set when it was captured. */
+void rb_set_pdl(int32_t mode);
 /* alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) in fp32, as Keras evaluates it. Host only. */
 float rb_adam_alpha_t(float lr, float beta_1, float beta_2, int32_t step);
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "rb_version": (C.c_int, []),
     "rb_last_error": (C.c_char_p, []),
     "rb_kernel_launches": (C.c_uint64, []),
+    "rb_set_pdl": (None, [_i32]),
     "rb_adam_alpha_t": (C.c_float, [_f, _f, _f, _i32]),
     "rb_gather_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
     "rb_check_indices": (C.c_int, [_p, _i32, _i64, _i32, _p, _i64, _p, _p]),

@@ -270,18 +270,14 @@ int sparse_ws_key_buffers(int64_t n, int D, int64_t rows, void* ws, uint32_t** k
 // it orders itself behind that kernel's completion (and memory flush) with griddep_wait(), which EVERY kernel launched this way
 // executes before it touches global memory, so that a chain of such kernels stays transitively ordered.  Without the
 // attribute (or when the preceding stream operation is not a kernel) the wait returns at once.  Works inside stream capture
-// (a programmatic edge of the graph).  RB_PDL=0 turns the attribute off everywhere.
+// (a programmatic edge of the graph).  RB_PDL=0 / rb_set_pdl(0) turn the attribute off everywhere: measured on a B200, the
+// single-GPU step gains 1.7 % (r2_67: 1.328 -> 1.306 ms) and the peer-memory sharded step LOSES 1.5 % (r2_69, N = 2: 1.380 ->
+// 1.400 ms), so p2p.py switches it off.
 #if defined(__CUDACC__)
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("RB_PDL");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
+bool pdl_enabled();      // api.cu: rb_set_pdl, else the RB_PDL environment variable (default on)
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned int grid, unsigned int block, size_t smem, cudaStream_t st,

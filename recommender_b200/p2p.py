@@ -189,6 +189,10 @@ class P2PShardedEmbedding(nn.Module):
         self.world, self.rank = link.world, link.rank
         if self.world > _lib.RB_MAX_RANKS:
             raise ValueError(f"at most {_lib.RB_MAX_RANKS} ranks")
+        if self.world > 1 and "RB_PDL" not in os.environ:
+            # programmatic dependent launch pays on one GPU (step 1.328 -> 1.306 ms) and costs on the sharded step
+            # (r2_69, N = 2: 1.380 -> 1.400 ms): off for every kernel this process launches from here on
+            lib.rb_set_pdl(0)
         self.input_dim, self.output_dim, self.num_tables = int(input_dim), int(output_dim), int(num_tables)
         self.capacity_factor = float(capacity_factor)
         self.save_rows = True     # forward keeps the bf16 operand rows so the backward does not cross NVLink again
