@@ -117,6 +117,22 @@ def test_argument_validation_of_the_dense_and_peer_memory_entry_points(cuda_lib)
     assert L.rb_ipc_open(None, None) == -1 and L.rb_shared_alloc(0, None, None) == -1
 
 
+def test_argument_validation_of_the_id_check_and_the_launch_mode_switch(cuda_lib):
+    L = cuda_lib
+    idx = (C.c_int64 * 8)()
+    rows = (C.c_int64 * 4)(3, 3, 3, 3)
+    flag = (C.c_int32 * 1)()
+    i, r, f = C.addressof(idx), C.addressof(rows), C.addressof(flag)
+    assert L.rb_check_indices(i, _lib.RB_I64, 8, 0, r, 0, f, None) == -1          # L must be positive
+    assert L.rb_check_indices(i, 7, 8, 4, r, 0, f, None) == -1                    # index type
+    assert L.rb_check_indices(None, _lib.RB_I64, 8, 4, r, 0, f, None) == -1 and b"null" in L.rb_last_error()
+    assert L.rb_check_indices(i, _lib.RB_I64, 8, 4, r, 0, None, None) == -1       # the flag is the result: required
+    assert L.rb_check_indices(i, _lib.RB_I64, 7, 4, r, 0, f, None) == -2          # n is a whole number of samples
+    assert L.rb_check_indices(i, _lib.RB_I64, 0, 4, r, 0, f, None) == 0           # empty batch: nothing launched
+    for mode in (0, 1, -1):                                                       # host-side flag only; -1 = back to RB_PDL
+        L.rb_set_pdl(mode)
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     from recommender_b200 import ops
