@@ -276,6 +276,18 @@ int sparse_ws_key_buffers(int64_t n, int D, int64_t rows, void* ws, uint32_t** k
 #if defined(__CUDACC__)
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// RB_PDL_RELEASE=1 (build time): small kernels (no shared memory to speak of) release their dependents right after their own
+// wait, so that the next kernel's CTAs — a Dense GEMM's, say — become resident beside them and run their prologue early.
+// Measured SLOWER than leaving the release to the kernel's end (r2_72, A/B on one box, twice: 1.331 / 1.342 against 1.318 /
+// 1.316 ms per step): the early CTAs hold shared memory and tensor memory the other streams' kernels could have used.  Off.
+#ifndef RB_PDL_RELEASE
+#define RB_PDL_RELEASE 0
+#endif
+__device__ __forceinline__ void griddep_release() {
+#if RB_PDL_RELEASE
+  griddep_launch_dependents();
+#endif
+}
 
 bool pdl_enabled();      // api.cu: rb_set_pdl, else the RB_PDL environment variable (default on)
 

@@ -29,6 +29,7 @@ constexpr int kDenseThreads = 256;
 // the result matches the numpy oracle bit for bit.
 __global__ void __launch_bounds__(kDenseThreads) dense_opt_kernel(const __grid_constant__ DenseSlots s) {
   griddep_wait();
+  griddep_release();
   int t = 0;
   while (t + 1 < s.num && static_cast<int>(blockIdx.x) >= s.chunk_start[t + 1]) ++t;
   const int64_t base = static_cast<int64_t>(blockIdx.x - s.chunk_start[t]) * kDenseChunk;
@@ -88,6 +89,7 @@ template <typename T>
 __global__ void __launch_bounds__(kColThreads)
 colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int cols, int64_t row_stride, float* __restrict__ partial) {
   griddep_wait();
+  griddep_release();
   __shared__ float s_red[kColThreads * 8];
   const int vcols = cols / 8;                      // vector columns
   const int row_lanes = kColThreads / vcols;       // rows handled in parallel (vcols <= 256)
@@ -134,6 +136,7 @@ constexpr int kFinalWarps = 32;
 __global__ void __launch_bounds__(kFinalWarps * 32) colsum_final_kernel(const float* __restrict__ partial, int nparts, int cols,
                                                                          float* __restrict__ out) {
   griddep_wait();
+  griddep_release();
   __shared__ float s_w[kFinalWarps][32];
   const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + lane;
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(kBceThreads)
 bce_partial_kernel(const float* __restrict__ prob, const void* __restrict__ label, int label_is_i64, int64_t n, float inv_n,
                    float* __restrict__ dprob, float* __restrict__ partial) {
   griddep_wait();
+  griddep_release();
   __shared__ float s_red[kBceThreads / 32];
   const float eps = 1e-7f;
   float acc = 0.f;
@@ -196,6 +200,7 @@ bce_partial_kernel(const float* __restrict__ prob, const void* __restrict__ labe
 
 __global__ void bce_final_kernel(const float* __restrict__ partial, int nparts, float inv_n, float* __restrict__ loss) {
   griddep_wait();
+  griddep_release();
   float t = 0.f;
   for (int i = 0; i < nparts; ++i) t += partial[i];
   loss[0] = t * inv_n;

@@ -673,6 +673,7 @@ dense_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N, float* __restrict__ out, int64_t ldo) {
   griddep_wait();
+  griddep_release();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int nv = N / 4;
   if (i >= static_cast<int64_t>(M) * nv) return;
@@ -701,6 +702,7 @@ __global__ void __launch_bounds__(256)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                 const float* __restrict__ bias, int act, float* __restrict__ out) {
   griddep_wait();
+  griddep_release();
   const int lane = threadIdx.x % 32;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + threadIdx.x / 32;
   if (r >= rows) return;
@@ -726,6 +728,7 @@ __global__ void __launch_bounds__(256)
 head_fwd_narrow_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                        const float* __restrict__ bias, int act, float* __restrict__ out) {
   griddep_wait();
+  griddep_release();
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (r >= rows) return;
   float acc = 0.f;
@@ -750,6 +753,7 @@ head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, i
                 int in_dim, int64_t ldx, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t lddx,
                 float* __restrict__ partial /* [grid, 2 * in_dim + 1]: dW | db | column sums of dx */) {
   griddep_wait();
+  griddep_release();
   // thread = (row lane rl, vector column vc): vc covers 8 consecutive columns
   const int vcols = in_dim / 8;
   const int row_lanes = kHeadBwdThreads / vcols;
@@ -833,6 +837,7 @@ head_bce_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int in_dim, i
                 const float* __restrict__ bias, const void* __restrict__ label, int label_is_i64, float inv_n, float* __restrict__ prob,
                 __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partial /* [grid, 2 * in_dim + 2]: dW | db | colsums | loss */) {
   griddep_wait();
+  griddep_release();
   const int vcols = in_dim / 8;
   const int row_lanes = kHeadBwdThreads / vcols;
   const int vc = threadIdx.x % vcols, rl = threadIdx.x / vcols;
@@ -953,6 +958,7 @@ __global__ void __launch_bounds__(256)
 head_bce_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float inv_n, float* __restrict__ dW, float* __restrict__ db,
                       float* __restrict__ dx_colsum, float* __restrict__ loss) {
   griddep_wait();
+  griddep_release();
   const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   const int pstride = 2 * in_dim + 2;
   if (c >= pstride) return;
@@ -971,6 +977,7 @@ __global__ void __launch_bounds__(256)
 head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, float* __restrict__ dW, float* __restrict__ db,
                       float* __restrict__ dx_colsum) {
   griddep_wait();
+  griddep_release();
   const int c = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   const int pstride = 2 * in_dim + 1;
   if (c >= pstride) return;
@@ -988,6 +995,7 @@ head_bwd_final_kernel(const float* __restrict__ partial, int parts, int in_dim, 
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, int64_t n4, __nv_bfloat16* __restrict__ out) {
   griddep_wait();
+  griddep_release();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
   const float4 d = __ldcs(reinterpret_cast<const float4*>(dy) + i);
@@ -1006,6 +1014,7 @@ act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int ac
 __global__ void __launch_bounds__(256)
 act_bwd_bf16_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, int act, int64_t n8, uint4* __restrict__ out) {
   griddep_wait();
+  griddep_release();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n8) return;
   const uint4 d = __ldcs(dy + i);
@@ -1031,6 +1040,7 @@ act_bwd_bf16_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, i
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ x, int64_t rows, int in_dim, int64_t ldx, __nv_bfloat16* __restrict__ out, int ld, int ones_col) {
   griddep_wait();
+  griddep_release();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= rows * ld) return;
   const int64_t r = i / ld;
