@@ -233,6 +233,100 @@ def test_keras_sparse_adam_is_dense_adam_on_the_scattered_gradient():
     assert untouched.size and not np.array_equal(W[untouched], W0[untouched])      # rows without a gradient moved too
 
 
+def test_lazy_adam_against_torch_sparse_adam():
+    """The row-sparse rule the benchmarked step uses (oracle.adam_lazy = the fused CUDA row update): moments and rows move on
+    touched rows only, the bias correction counts GLOBAL steps.  torch.optim.SparseAdam implements the same published rule
+    (coalesced gradient, m / v updated at its indices only, step_size = lr * sqrt(1 - b2^t) / (1 - b1^t), eps added to sqrt(v))."""
+    import torch
+    rng = np.random.default_rng(21)
+    V, D = 60, 8
+    W0 = rng.normal(0, 0.05, size=(V, D)).astype(np.float32)
+    W = W0.copy()
+    st = dict(m=np.zeros_like(W), v=np.zeros_like(W))
+    p = torch.nn.Parameter(torch.tensor(W0))
+    opt = torch.optim.SparseAdam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-7)
+    never = np.ones(V, bool)
+    for step in range(1, 7):
+        idx = rng.integers(0, 40, size=(16, 3))                       # duplicates inside a step; rows 40.. never touched
+        dE = rng.normal(0, 1e-2, size=(16, 3, D)).astype(np.float32)
+        never[idx.reshape(-1)] = False
+        O.sparse_backward_update(W, st, idx, dE, "adam_lazy", step=step)
+        p.grad = torch.sparse_coo_tensor(torch.tensor(idx.reshape(1, -1)), torch.tensor(dE.reshape(-1, D)), (V, D))
+        opt.step()
+        # a step moves a weight by <= lr = 1e-3; the 1.3e-5 in v (below) is 6.5e-6 of that through the square root
+        np.testing.assert_allclose(W, p.detach().numpy(), rtol=2e-6, atol=1e-8 * step, err_msg=f"step {step}")
+        sd = opt.state[p]
+        np.testing.assert_allclose(st["m"], sd["exp_avg"].numpy(), rtol=2e-6, atol=1e-9)     # m + (g - m)(1 - b1) there: cancellation
+        # v: the oracle forms 1 - beta_2 in fp32 as TF does (0.00099998713), torch in double (0.001): 1.3e-5 apart
+        np.testing.assert_allclose(st["v"], sd["exp_avg_sq"].numpy(), rtol=3e-5, atol=1e-14)
+    assert never.any() and np.array_equal(W[never], W0[never])        # the lazy rule: rows without a gradient stay bit for bit
+
+
+def test_sparse_adagrad_and_sgd_against_torch():
+    """A.4: acc += g^2 on the touched rows, var -= lr * g / (sqrt(acc) + eps) — torch.optim.Adagrad's sparse branch with the
+    same initial accumulator and epsilon; and plain SGD."""
+    import torch
+    rng = np.random.default_rng(22)
+    V, D = 50, 4
+    W0 = rng.normal(0, 0.05, size=(V, D)).astype(np.float32)
+    Wa, Ws = W0.copy(), W0.copy()
+    st = dict(acc=np.full_like(W0, 0.1))
+    pa, ps = torch.nn.Parameter(torch.tensor(W0)), torch.nn.Parameter(torch.tensor(W0))
+    oa = torch.optim.Adagrad([pa], lr=1e-3, initial_accumulator_value=0.1, eps=1e-7)
+    os_ = torch.optim.SGD([ps], lr=1e-2)
+    for step in range(1, 5):
+        idx = rng.integers(0, 30, size=(12, 2))
+        dE = rng.normal(0, 1e-1, size=(12, 2, D)).astype(np.float32)
+        O.sparse_backward_update(Wa, st, idx, dE, "adagrad", lr=1e-3, epsilon=1e-7)
+        O.sparse_backward_update(Ws, {}, idx, dE, "sgd", lr=1e-2)
+        g = torch.sparse_coo_tensor(torch.tensor(idx.reshape(1, -1)), torch.tensor(dE.reshape(-1, D)), (V, D))
+        pa.grad, ps.grad = g, g.to_dense()
+        oa.step()
+        os_.step()
+        np.testing.assert_allclose(Wa, pa.detach().numpy(), rtol=2e-6, atol=2e-9, err_msg=f"adagrad step {step}")
+        np.testing.assert_allclose(st["acc"], oa.state[pa]["sum"].numpy(), rtol=2e-6)
+        np.testing.assert_allclose(Ws, ps.detach().numpy(), rtol=2e-6, atol=2e-9, err_msg=f"sgd step {step}")
+
+
+def test_losses_and_initialisers_against_torch():
+    """Keras binary_crossentropy on probabilities (clip to [1e-7, 1 - 1e-7], log(p + 1e-7)) and on logits, against
+    torch.nn.functional on float64 with autograd gradients; Glorot-uniform limit against torch.nn.init's."""
+    import torch
+    import torch.nn.functional as Fn
+    rng = np.random.default_rng(23)
+    n = 257
+    prob = rng.uniform(0.01, 0.99, size=n).astype(np.float32)
+    label = rng.integers(0, 2, size=n).astype(np.float32)
+    edge = prob.copy()
+    edge[:3] = (0.0, 1.0, 5e-8)                                      # outside the clip: zero gradient
+    _, dp_edge = O.bce_clipped(edge, label)
+    assert np.all(dp_edge[:3] == 0) and np.all(dp_edge[3:] != 0)     # Keras' clip_by_value passes no gradient outside the range
+    loss, dp = O.bce_clipped(prob, label)
+    pt = torch.tensor(prob, dtype=torch.float64, requires_grad=True)
+    pc = pt.clamp(1e-7, 1 - 1e-7)
+    y = torch.tensor(label, dtype=torch.float64)
+    ref = -(y * torch.log(pc + 1e-7) + (1 - y) * torch.log(1 - pc + 1e-7)).mean()
+    ref.backward()
+    np.testing.assert_allclose(loss, ref.item(), rtol=2e-6)
+    np.testing.assert_allclose(dp, pt.grad.numpy(), rtol=2e-5, atol=1e-9)
+    # inside the clip it is torch's own BCE up to the +eps in the log
+    np.testing.assert_allclose(loss, Fn.binary_cross_entropy(pc.detach(), y).item(), rtol=1e-5)
+    logit = rng.normal(0, 3, size=n).astype(np.float32)
+    l2, dl = O.bce_logits(logit, label)
+    lt = torch.tensor(logit, dtype=torch.float64, requires_grad=True)
+    r2 = Fn.binary_cross_entropy_with_logits(lt, y)
+    r2.backward()
+    np.testing.assert_allclose(l2, r2.item(), rtol=2e-6)
+    np.testing.assert_allclose(dl, lt.grad.numpy(), rtol=2e-5, atol=1e-9)
+    W = O.glorot_uniform(np.random.default_rng(0), 800, 512)
+    t = torch.empty(512, 800)
+    torch.manual_seed(0)
+    torch.nn.init.xavier_uniform_(t)
+    lim = np.sqrt(6.0 / (800 + 512))
+    assert np.abs(W).max() <= lim and np.abs(W).max() > 0.99 * lim
+    assert t.abs().max().item() <= lim * (1 + 1e-6) and t.abs().max().item() > 0.99 * lim
+
+
 def test_dedup_order_against_pandas_factorize():
     """A.2: tf.unique returns the unique ids in FIRST-OCCURRENCE order; pandas.factorize has the same contract."""
     import pandas as pd
